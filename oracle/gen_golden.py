@@ -1,0 +1,220 @@
+"""oracle/gen_golden.py — generate tests/golden/*.pt from the UNMODIFIED reference modules.
+
+*** TEST INFRASTRUCTURE.  Run in the build container only (needs /root/reference). ***
+
+    python oracle/gen_golden.py            # rewrites tests/golden/*.pt
+
+The reference hot path (``anemoi.models.layers.{processor,mapper,block,conv}``,
+``anemoi.models.triton.utils``, ``anemoi.models.distributed.khop_edges``) is imported straight from
+``/root/reference/models/src`` with ``oracle/standins`` supplying the three packages this image lacks
+(torch_geometric, hydra, anemoi.utils — behaviour spec in SURVEY.md Appendix A).  Each fixture holds
+the seeded inputs, the reference ``state_dict`` and the reference output, fp32 on CPU, ``pyg``
+attention backend (the Triton backend needs CUDA; ``block.py:608-612`` falls back by itself).
+
+Fixture sizes follow the reference's own tests: 100 nodes / 200 edges for processors
+(``models/tests/layers/processor/test_graphconv_processor.py:44-56``), 200 -> 178 nodes / 300 edges
+for mappers (``models/tests/layers/mapper/test_graphconv_mapper.py:58-103``), the Triton parity
+shapes ``(n_src,n_dst,h,d)`` of ``models/tests/integration/triton/test_triton_gt.py:49-57`` and the
+seeded graphs of ``models/tests/distributed/test_khop_edges.py:21-38``; plus BASELINE.json cfg1
+(1 000 nodes / 4 000 edges / GNNProcessor 2x32).
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, "standins"))
+sys.path.insert(1, "/root/reference/models/src")
+sys.path.insert(2, ROOT)
+
+import torch  # noqa: E402
+
+from anemoi.models.distributed.khop_edges import build_graph_partition  # noqa: E402
+from anemoi.models.distributed.khop_edges import sort_edge_index_by_dst  # noqa: E402
+from anemoi.models.distributed.shapes import BipartiteGraphShardInfo  # noqa: E402
+from anemoi.models.distributed.shapes import GraphShardInfo  # noqa: E402
+from anemoi.models.layers.conv import GraphTransformerConv  # noqa: E402
+from anemoi.models.layers.mapper import GNNBackwardMapper  # noqa: E402
+from anemoi.models.layers.mapper import GNNForwardMapper  # noqa: E402
+from anemoi.models.layers.mapper import GraphTransformerBackwardMapper  # noqa: E402
+from anemoi.models.layers.mapper import GraphTransformerForwardMapper  # noqa: E402
+from anemoi.models.layers.processor import GNNProcessor  # noqa: E402
+from anemoi.models.layers.processor import GraphTransformerProcessor  # noqa: E402
+from anemoi.models.triton.utils import edge_index_to_csc  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def rand_graph(n_src, n_dst, n_edges, edge_dim, seed, sort=True):
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.stack([torch.randint(0, n_src, (n_edges,), generator=g), torch.randint(0, n_dst, (n_edges,), generator=g)])
+    if sort:
+        ei = ei[:, torch.sort(ei[1], stable=True)[1]]
+    return ei, torch.randn(n_edges, edge_dim, generator=g)
+
+
+def sd_of(m):
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def randomise(m, seed):
+    """Default torch init leaves LayerNorm at (1, 0) and is seeded here; perturb LN so affine terms are tested."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "norm" in n:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    return m
+
+
+@torch.no_grad()
+def gnn_processor_case(name, n, e, c, layers, edge_dim, seed):
+    torch.manual_seed(seed)
+    m = randomise(
+        GNNProcessor(num_channels=c, num_layers=layers, num_chunks=1, mlp_extra_layers=0, edge_dim=edge_dim, layer_kernels=None), seed
+    ).eval()
+    ei, ea = rand_graph(n, n, e, edge_dim, seed)
+    x = torch.randn(n, c, generator=torch.Generator().manual_seed(seed + 1))
+    y = m(x, 1, GraphShardInfo(nodes=[n], edges=None), ea, ei, None)
+    torch.save(
+        {"kind": "gnn_processor", "cfg": dict(num_channels=c, num_layers=layers, edge_dim=edge_dim), "sd": sd_of(m), "x": x,
+         "edge_attr": ea, "edge_index": ei, "y": y}, os.path.join(OUT, name + ".pt"))  # fmt: skip
+    print(name, tuple(y.shape), float(y.abs().mean()))
+
+
+@torch.no_grad()
+def gt_processor_case(name, n, e, c, heads, layers, edge_dim, seed, qk_norm=False, sort=True):
+    torch.manual_seed(seed)
+    m = randomise(
+        GraphTransformerProcessor(num_layers=layers, num_channels=c, num_chunks=1, num_heads=heads, mlp_hidden_ratio=4,
+                                  edge_dim=edge_dim, qk_norm=qk_norm, layer_kernels=None, graph_attention_backend="pyg"), seed
+    ).eval()  # fmt: skip
+    ei, ea = rand_graph(n, n, e, edge_dim, seed, sort=sort)
+    x = torch.randn(n, c, generator=torch.Generator().manual_seed(seed + 1))
+    y = m(x, 1, GraphShardInfo(nodes=None, edges=None), ea, ei, None, edges_are_dst_sorted=sort)
+    torch.save(
+        {"kind": "gt_processor", "cfg": dict(num_channels=c, num_layers=layers, num_heads=heads, edge_dim=edge_dim, qk_norm=qk_norm),
+         "sorted": sort, "sd": sd_of(m), "x": x, "edge_attr": ea, "edge_index": ei, "y": y}, os.path.join(OUT, name + ".pt"))  # fmt: skip
+    print(name, tuple(y.shape), float(y.abs().mean()))
+
+
+@torch.no_grad()
+def mapper_cases(seed=7):
+    n_src, n_dst, e, edge_dim, c = 200, 178, 300, 3, 64
+    in_src, in_dst, out_dst = 10, 6, 5
+    ei, ea = rand_graph(n_src, n_dst, e, edge_dim, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    shard = BipartiteGraphShardInfo(src_nodes=None, dst_nodes=None, edges=None)
+
+    torch.manual_seed(seed)
+    m = randomise(GNNForwardMapper(in_channels_src=in_src, in_channels_dst=in_dst, hidden_dim=c, num_chunks=1, mlp_extra_layers=0,
+                                   edge_dim=edge_dim, layer_kernels=None), seed).eval()  # fmt: skip
+    xs, xd = torch.randn(n_src, in_src, generator=g), torch.randn(n_dst, in_dst, generator=g)
+    ys, yd = m((xs, xd), 1, shard, ea, ei, None)
+    torch.save({"kind": "gnn_forward_mapper", "cfg": dict(in_channels_src=in_src, in_channels_dst=in_dst, hidden_dim=c, edge_dim=edge_dim),
+                "sd": sd_of(m), "x_src": xs, "x_dst": xd, "edge_attr": ea, "edge_index": ei, "y_src": ys, "y_dst": yd},
+               os.path.join(OUT, "gnn_forward_mapper.pt"))  # fmt: skip
+    print("gnn_forward_mapper", tuple(ys.shape), tuple(yd.shape))
+
+    torch.manual_seed(seed)
+    ei_b, ea_b = rand_graph(n_dst, n_src, e, edge_dim, seed + 3)  # hidden (178) -> data (200)
+    m = randomise(GNNBackwardMapper(in_channels_src=c, in_channels_dst=in_src, hidden_dim=c, out_channels_dst=out_dst, num_chunks=1,
+                                    mlp_extra_layers=0, edge_dim=edge_dim, layer_kernels=None), seed).eval()  # fmt: skip
+    xs, xd = torch.randn(n_dst, c, generator=g), torch.randn(n_src, c, generator=g)
+    y = m((xs, xd), 1, shard, ea_b, ei_b, None)
+    torch.save({"kind": "gnn_backward_mapper", "cfg": dict(in_channels_src=c, in_channels_dst=in_src, hidden_dim=c, out_channels_dst=out_dst,
+                                                            edge_dim=edge_dim),
+                "sd": sd_of(m), "x_src": xs, "x_dst": xd, "edge_attr": ea_b, "edge_index": ei_b, "y": y},
+               os.path.join(OUT, "gnn_backward_mapper.pt"))  # fmt: skip
+    print("gnn_backward_mapper", tuple(y.shape))
+
+    for chunks in (1, 4):
+        torch.manual_seed(seed)
+        m = randomise(GraphTransformerForwardMapper(in_channels_src=in_src, in_channels_dst=in_dst, hidden_dim=c, num_chunks=chunks,
+                                                    num_heads=4, mlp_hidden_ratio=4, edge_dim=edge_dim, layer_kernels=None,
+                                                    graph_attention_backend="pyg"), seed).eval()  # fmt: skip
+        g2 = torch.Generator().manual_seed(seed + 5)
+        xs, xd = torch.randn(n_src, in_src, generator=g2), torch.randn(n_dst, in_dst, generator=g2)
+        ys, yd = m((xs, xd), 1, shard, ea, ei, None)
+        assert ys is xs
+        torch.save({"kind": "gt_forward_mapper", "cfg": dict(in_channels_src=in_src, in_channels_dst=in_dst, hidden_dim=c, num_heads=4,
+                                                            edge_dim=edge_dim, num_chunks=chunks),
+                    "sd": sd_of(m), "x_src": xs, "x_dst": xd, "edge_attr": ea, "edge_index": ei, "y_dst": yd},
+                   os.path.join(OUT, f"gt_forward_mapper_chunks{chunks}.pt"))  # fmt: skip
+        print("gt_forward_mapper", chunks, tuple(yd.shape), float(yd.abs().mean()))
+
+    torch.manual_seed(seed)
+    m = randomise(GraphTransformerBackwardMapper(in_channels_src=c, in_channels_dst=in_src, hidden_dim=c, out_channels_dst=out_dst,
+                                                 num_chunks=2, num_heads=4, mlp_hidden_ratio=4, edge_dim=edge_dim, layer_kernels=None,
+                                                 graph_attention_backend="pyg"), seed).eval()  # fmt: skip
+    g2 = torch.Generator().manual_seed(seed + 6)
+    xs, xd = torch.randn(n_dst, c, generator=g2), torch.randn(n_src, in_src, generator=g2)
+    y = m((xs, xd), 1, shard, ea_b, ei_b, None)
+    torch.save({"kind": "gt_backward_mapper", "cfg": dict(in_channels_src=c, in_channels_dst=in_src, hidden_dim=c, out_channels_dst=out_dst,
+                                                         num_heads=4, edge_dim=edge_dim, num_chunks=2),
+                "sd": sd_of(m), "x_src": xs, "x_dst": xd, "edge_attr": ea_b, "edge_index": ei_b, "y": y},
+               os.path.join(OUT, "gt_backward_mapper.pt"))  # fmt: skip
+    print("gt_backward_mapper", tuple(y.shape))
+
+
+@torch.no_grad()
+def attention_conv_cases():
+    """GraphTransformerConv (PyG path) on the reference's Triton parity shapes + a zero-in-degree case."""
+    cases = []
+    for i, (n_src, n_dst, h, d) in enumerate([(4, 10, 2, 4), (4, 10, 6, 4), (4, 10, 2, 6), (4, 10, 6, 6), (50, 40, 4, 32)]):
+        g = torch.Generator().manual_seed(100 + i)
+        n_edges = 3 * n_dst
+        ei = torch.stack([torch.randint(0, n_src, (n_edges,), generator=g), torch.randint(0, max(n_dst - 2, 1), (n_edges,), generator=g)])
+        ei = ei[:, torch.sort(ei[1], stable=True)[1]]  # last two dst rows have in-degree 0
+        q, k, v = torch.randn(n_dst, h, d, generator=g), torch.randn(n_src, h, d, generator=g), torch.randn(n_src, h, d, generator=g)
+        e = torch.randn(n_edges, h, d, generator=g)
+        out = GraphTransformerConv(out_channels=d)(q, k, v, e, ei, size=(n_src, n_dst))
+        cases.append({"q": q, "k": k, "v": v, "e": e, "edge_index": ei, "out": out})
+    torch.save({"kind": "gt_conv", "cases": cases}, os.path.join(OUT, "gt_conv.pt"))
+    print("gt_conv", len(cases))
+
+
+def integer_cases():
+    """triton/utils.py:25-70 and distributed/khop_edges.py on seeded graphs (test_khop_edges.py:21-38 style)."""
+    cases = []
+    for seed, (n_src, n_dst, n_edges) in zip((42, 43, 44, 45), ((50, 40, 300), (17, 23, 91), (1, 1, 5), (64, 64, 0))):
+        g = torch.Generator().manual_seed(seed)
+        ei = torch.stack([torch.randint(0, n_src, (n_edges,), generator=g), torch.randint(0, n_dst, (n_edges,), generator=g)])
+        sorted_ei, perm = sort_edge_index_by_dst(ei)
+        (row, colptr), perm2, (rowptr, edge_ids, edge_dst) = edge_index_to_csc(ei, (n_src, n_dst), edges_are_dst_sorted=False)
+        case = {"edge_index": ei, "num_nodes": (n_src, n_dst), "sorted": sorted_ei, "perm": perm, "row": row, "colptr": colptr,
+                "rowptr": rowptr, "edge_ids": edge_ids, "edge_dst": edge_dst, "partitions": {}}  # fmt: skip
+        for parts in (1, 2, 3, 4, 7):
+            if n_edges == 0:
+                continue
+            p = build_graph_partition(sorted_ei, parts, (n_src, n_dst))
+            mats = []
+            x_src = torch.arange(n_src, dtype=torch.float32).view(-1, 1)
+            x_dst = torch.arange(n_dst, dtype=torch.float32).view(-1, 1)
+            ea = torch.arange(n_edges, dtype=torch.float32).view(-1, 1)
+            for cid in range(parts):
+                (xs_c, xd_c), ea_c, ei_c, _ = p.materialise(cid, (x_src, x_dst), ea, sorted_ei)
+                mats.append({"src_ids": xs_c.view(-1).long(), "dst_ids": xd_c.view(-1).long(), "edge_ids": ea_c.view(-1).long(), "edge_index": ei_c})
+            case["partitions"][parts] = {"dst_splits": list(p.dst_splits), "edge_splits": list(p.edge_splits), "chunks": mats}
+        cases.append(case)
+    torch.save({"kind": "integer", "cases": cases}, os.path.join(OUT, "integer_path.pt"))
+    print("integer", len(cases))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    gnn_processor_case("gnn_processor_small", 100, 200, 32, 2, 3, seed=1)
+    gnn_processor_case("gnn_processor_cfg1", 1000, 4000, 32, 2, 3, seed=1234)
+    gt_processor_case("gt_processor_small", 100, 200, 64, 4, 2, 11, seed=2)
+    gt_processor_case("gt_processor_qknorm", 100, 200, 64, 4, 2, 11, seed=3, qk_norm=True)
+    gt_processor_case("gt_processor_unsorted", 100, 200, 64, 4, 2, 11, seed=4, sort=False)
+    mapper_cases()
+    attention_conv_cases()
+    integer_cases()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,203 @@
+// common.cuh — shared helpers for libanemoi_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/anemoi_b200.h"
+
+namespace anemoi {
+
+// ---- error reporting across the C ABI (thread-local message, errno-style codes) ----------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define ANEMOI_CHECK_ARG(cond, ...)      \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::anemoi::set_error(__VA_ARGS__);  \
+      return -1;                         \
+    }                                    \
+  } while (0)
+
+#define ANEMOI_CUDA(call)                                         \
+  do {                                                            \
+    cudaError_t _e = (call);                                      \
+    if (_e != cudaSuccess) return ::anemoi::cuda_fail(_e, #call); \
+  } while (0)
+
+inline int launch_status(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return cuda_fail(e, what);
+  }
+  return 0;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;  // B200
+  }
+  return n;
+}
+
+// ---- dtype helpers -------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) {
+  return __bfloat162float(v);
+}
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+// runtime-typed scalar access (epilogues: residual / out may be f32 or bf16)
+__device__ __forceinline__ float load_as_f32(const void* p, int64_t i, int dtype) {
+  return dtype == ANEMOI_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void store_from_f32(void* p, int64_t i, int dtype, float v) {
+  if (dtype == ANEMOI_BF16)
+    reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else
+    reinterpret_cast<float*>(p)[i] = v;
+}
+
+// exact (erf) GELU, torch.nn.GELU() default — layers/utils.py:107-110
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(t);
+}
+
+// load VEC contiguous elements (VEC*sizeof(T) bytes, 16B vectors where possible) as fp32
+template <typename T, int VEC>
+__device__ __forceinline__ void load_vec_f32(const T* __restrict__ p, float (&out)[VEC]) {
+  if constexpr (sizeof(T) == 4) {
+    if constexpr (VEC % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC / 4; ++i) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+        out[4 * i] = t.x, out[4 * i + 1] = t.y, out[4 * i + 2] = t.z, out[4 * i + 3] = t.w;
+      }
+    } else if constexpr (VEC % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC / 2; ++i) {
+        float2 t = __ldg(reinterpret_cast<const float2*>(p) + i);
+        out[2 * i] = t.x, out[2 * i + 1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) out[i] = __ldg(reinterpret_cast<const float*>(p) + i);
+    }
+  } else {
+    if constexpr (VEC % 8 == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC / 8; ++i) {
+        uint4 t = __ldg(reinterpret_cast<const uint4*>(p) + i);
+        float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+        out[8 * i] = a.x, out[8 * i + 1] = a.y, out[8 * i + 2] = b.x, out[8 * i + 3] = b.y;
+        out[8 * i + 4] = c.x, out[8 * i + 5] = c.y, out[8 * i + 6] = d.x, out[8 * i + 7] = d.y;
+      }
+    } else if constexpr (VEC % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC / 4; ++i) {
+        uint2 t = __ldg(reinterpret_cast<const uint2*>(p) + i);
+        float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y);
+        out[4 * i] = a.x, out[4 * i + 1] = a.y, out[4 * i + 2] = b.x, out[4 * i + 3] = b.y;
+      }
+    } else if constexpr (VEC % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC / 2; ++i) {
+        float2 a = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(p) + i));
+        out[2 * i] = a.x, out[2 * i + 1] = a.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) out[i] = __bfloat162float(p[i]);
+    }
+  }
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void store_vec_f32(T* __restrict__ p, const float (&v)[VEC]) {
+  if constexpr (sizeof(T) == 4) {
+    if constexpr (VEC % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC / 4; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else if constexpr (VEC % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC / 2; ++i) reinterpret_cast<float2*>(p)[i] = make_float2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) reinterpret_cast<float*>(p)[i] = v[i];
+    }
+  } else {
+    if constexpr (VEC % 8 == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC / 8; ++i)
+        reinterpret_cast<uint4*>(p)[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                                    pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+    } else if constexpr (VEC % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC / 4; ++i)
+        reinterpret_cast<uint2*>(p)[i] = make_uint2(pack_bf16x2(v[4 * i], v[4 * i + 1]), pack_bf16x2(v[4 * i + 2], v[4 * i + 3]));
+    } else if constexpr (VEC % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < VEC / 2; ++i) reinterpret_cast<uint32_t*>(p)[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) p[i] = __float2bfloat16_rn(v[i]);
+    }
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- epilogue shared by the two GEMM kernels --------------------------------------------------------------
+struct EpiParams {
+  const float* bias;    // [N] or null
+  const float* g1;      // gather-add table 1 [*, ldg] fp32 or null
+  const int32_t* idx1;  // [M]
+  const float* g2;
+  const int32_t* idx2;
+  int64_t ldg;
+  const void* residual;  // [M, ldr] or null
+  int64_t ldr;
+  int r_dtype;
+  void* out;  // [M, ldo]
+  int64_t ldo;
+  int o_dtype;
+  int64_t M, N;
+  int flags;
+};
+
+}  // namespace anemoi

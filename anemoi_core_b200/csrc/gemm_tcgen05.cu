@@ -1,0 +1,413 @@
+// gemm_tcgen05.cu — bf16 Linear on the 5th-gen tensor cores (sm_100a): out = epi(A[M,K] . W[N,K]^T).
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor 2-D loads of a 128x64 A tile and a BNx64 W tile (both
+//                      K-major, 128-byte swizzle) into a STAGES-deep shared-memory ring, mbarrier complete_tx.
+//   warp 1 (one lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16, fp32 accumulators in
+//                      TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of i+1;
+//                      tcgen05.commit releases smem slots / publishes the accumulator.
+//   warp 2             TMEM allocator (tcgen05.alloc / dealloc).
+//   warps 4..11        epilogue: tcgen05.ld 32x32b (one accumulator row per thread, warp w owns TMEM lanes
+//                      32*(w%4).., column half (w-4)/4), then bias / gather-add / erf-GELU / residual in fp32 and
+//                      16-byte stores.  One row per thread is also what the gather-add epilogue wants: the edge's
+//                      two projected node rows are contiguous per thread.
+// K tails and M/N tails rely on TMA out-of-bounds zero fill + masked stores.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "gemm.h"
+
+namespace anemoi {
+
+namespace ptx {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t it = 0; !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && it > (1u << 27)) __trap();  // a protocol bug must fail loudly, never hang the device
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+}  // namespace ptx
+
+constexpr int kBM = 128, kBK = 64;
+constexpr int kThreads = 384;  // warps 0..3 control, 4..11 epilogue
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
+  static constexpr int kWBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kWBytes;
+  static constexpr int kTmemCols = 2 * BN;  // 128 / 256 / 512: powers of two
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// UMMA shared-memory descriptor for a K-major, 128-byte-swizzled tile (rows of 64 bf16 = 128 B; 8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                      // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset between 8-row core-matrix groups
+  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int num_kb, int tiles_m,
+                             int tiles_n, int vec_ok, const EpiParams ep) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base address slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = tiles_m * tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(tfull_bar(s), 1);
+      ptx::mbar_init(tempty_bar(s), 8);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
+          ptx::mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          ptx::tma_load_2d(a_dst, &tmA, full_bar(stage), kb * kBK, m_blk * kBM);
+          ptx::tma_load_2d(a_dst + Cfg::kABytes, &tmW, full_bar(stage), kb * kBK, n_blk * BN);
+          if (++stage == Cfg::kStages) stage = 0, phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major A and B, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
+          const uint64_t a_desc = make_sw128_desc(a_addr);
+          const uint64_t b_desc = make_sw128_desc(a_addr + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle span: +2 in 16-byte units
+            ptx::umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar(stage));  // frees this smem slot once the MMAs above have read it
+          if (++stage == Cfg::kStages) stage = 0, phase ^= 1u;
+        }
+        ptx::umma_commit(tfull_bar(as));  // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // column half
+    constexpr int kColsPerWarp = BN / 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      ptx::mbar_wait(tfull_bar(as), aphase);
+      ptx::tc_fence_after();
+      const int64_t row = (int64_t)m_blk * kBM + q * 32 + lane;
+      const bool row_ok = row < ep.M;
+      const float* g1row = (ep.g1 && row_ok) ? ep.g1 + (int64_t)ep.idx1[row] * ep.ldg : nullptr;
+      const float* g2row = (ep.g2 && row_ok) ? ep.g2 + (int64_t)ep.idx2[row] * ep.ldg : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < kColsPerWarp; c += 32) {
+        uint32_t r[32];
+        const int col_in_tile = half * kColsPerWarp + c;
+        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + col_in_tile), r);
+        ptx::tmem_wait_ld();
+        const int64_t col0 = (int64_t)n_blk * BN + col_in_tile;
+        if (row_ok && col0 < ep.N) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int64_t col = col0 + g * 8;
+            if (col >= ep.N) break;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+            if (vec_ok && col + 8 <= ep.N) {
+              if (ep.bias) {
+                float t[8];
+                load_vec_f32<float, 8>(ep.bias + col, t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += t[j];
+              }
+              if (g1row) {
+                float t[8];
+                load_vec_f32<float, 8>(g1row + col, t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += t[j];
+              }
+              if (g2row) {
+                float t[8];
+                load_vec_f32<float, 8>(g2row + col, t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += t[j];
+              }
+              if (ep.flags & ANEMOI_EPI_GELU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+              }
+              if (ep.residual) {
+                float t[8];
+                if (ep.r_dtype == ANEMOI_BF16)
+                  load_vec_f32<__nv_bfloat16, 8>(reinterpret_cast<const __nv_bfloat16*>(ep.residual) + row * ep.ldr + col, t);
+                else
+                  load_vec_f32<float, 8>(reinterpret_cast<const float*>(ep.residual) + row * ep.ldr + col, t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += t[j];
+              }
+              if (ep.o_dtype == ANEMOI_BF16)
+                store_vec_f32<__nv_bfloat16, 8>(reinterpret_cast<__nv_bfloat16*>(ep.out) + row * ep.ldo + col, v);
+              else
+                store_vec_f32<float, 8>(reinterpret_cast<float*>(ep.out) + row * ep.ldo + col, v);
+            } else {
+              for (int j = 0; j < 8 && col + j < ep.N; ++j) {
+                float a = v[j];
+                const int64_t n = col + j;
+                if (ep.bias) a += ep.bias[n];
+                if (g1row) a += g1row[n];
+                if (g2row) a += g2row[n];
+                if (ep.flags & ANEMOI_EPI_GELU) a = gelu_erf(a);
+                if (ep.residual) a += load_as_f32(ep.residual, row * ep.ldr + n, ep.r_dtype);
+                store_from_f32(ep.out, row * ep.ldo + n, ep.o_dtype, a);
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---- host side: TMA descriptors -----------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  int64_t rows, cols, ld;
+  int box_rows;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    auto mix = [&](int64_t v) { h ^= std::hash<int64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.rows), mix(k.cols), mix(k.ld), mix(k.box_rows);
+    return h;
+  }
+};
+
+// bf16 [rows, cols] row-major, leading dimension ld (elements); box = box_rows x 64 columns, 128-byte swizzle, zero OOB fill.
+static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("linear(tcgen05): cuTensorMapEncodeTiled not available from the driver");
+    return -2;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("linear(tcgen05): cuTensorMapEncodeTiled failed with CUresult %d (ptr %p rows %lld cols %lld ld %lld box %d)", (int)r, ptr,
+              (long long)rows, (long long)cols, (long long)ld, box_rows);
+    return -2;
+  }
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
+  return 0;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, int64_t K, int vec_ok, const EpiParams& ep, cudaStream_t s) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel)");
+    attr_set = true;
+  }
+  const int tiles_m = (int)((ep.M + kBM - 1) / kBM), tiles_n = (int)((ep.N + BN - 1) / BN);
+  const int num_kb = (int)((K + kBK - 1) / kBK);
+  const int64_t tiles = (int64_t)tiles_m * tiles_n;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  gemm_bf16_tcgen05_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmA, tmW, num_kb, tiles_m, tiles_n, vec_ok, ep);
+  return launch_status("gemm_bf16_tcgen05_kernel");
+}
+
+int linear_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t K, const EpiParams& ep, cudaStream_t s) {
+  // tile width: widest tile that keeps at least ~2 waves of CTAs busy
+  const int64_t tiles_m = (ep.M + kBM - 1) / kBM;
+  int bn = 256;
+  if (ep.N <= 64)
+    bn = 64;
+  else if (ep.N <= 128 || tiles_m * ((ep.N + 255) / 256) < 2 * (int64_t)num_sms())
+    bn = 128;
+  if (bn == 128 && ep.N <= 64) bn = 64;
+  CUtensorMap tmA, tmW;
+  int rc = get_tensor_map(A, ep.M, K, lda, kBM, &tmA);
+  if (rc) return rc;
+  rc = get_tensor_map(W, ep.N, K, ldw, bn, &tmW);
+  if (rc) return rc;
+  auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const int os = ep.o_dtype == ANEMOI_BF16 ? 2 : 4, rs = ep.r_dtype == ANEMOI_BF16 ? 2 : 4;
+  const int vec_ok = a16(ep.out) && (ep.ldo * os) % 16 == 0 && (!ep.bias || a16(ep.bias)) &&
+                     (!ep.residual || (a16(ep.residual) && (ep.ldr * rs) % 16 == 0)) &&
+                     ((!ep.g1 && !ep.g2) || ((!ep.g1 || a16(ep.g1)) && (!ep.g2 || a16(ep.g2)) && ep.ldg % 4 == 0));
+  switch (bn) {
+    case 64: return launch<64>(tmA, tmW, K, vec_ok, ep, s);
+    case 128: return launch<128>(tmA, tmW, K, vec_ok, ep, s);
+    default: return launch<256>(tmA, tmW, K, vec_ok, ep, s);
+  }
+}
+
+}  // namespace anemoi

@@ -1,0 +1,170 @@
+// layernorm.cu — row LayerNorm (+ optional residual), one warp per (row, group).  HBM-bound: one read of x
+// (+ residual), one write of y; 16-byte vector accesses on the fast path; fp32 statistics (two-pass in registers).
+#include "common.cuh"
+
+namespace anemoi {
+
+// Fast path: C % 8 == 0, C <= 256*ITERS, all row starts 16-byte aligned.  Lane owns 8 contiguous elements per iteration.
+template <typename TI, typename TR, typename TO, int ITERS>
+__global__ void __launch_bounds__(256) layer_norm_vec_kernel(const TI* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const TR* __restrict__ res, int64_t ldr,
+                                                             TO* __restrict__ y, int64_t ldy, int64_t M, int64_t groups, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < M * groups; w += warps_total) {
+    const int64_t m = w / groups, g = w - m * groups;
+    const TI* xr = x + m * ldx + g * C;
+    float v[ITERS][8];
+    float s = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = it * 256 + lane * 8;
+      if (c < C) {
+        load_vec_f32<TI, 8>(xr + c, v[it]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[it][i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[it][i] = 0.f;
+      }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = it * 256 + lane * 8;
+      if (c < C) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = v[it][i] - mean;
+          q += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = it * 256 + lane * 8;
+      if (c < C) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (v[it][i] - mean) * rstd;
+        if (gamma) {
+          float gm[8];
+          load_vec_f32<float, 8>(gamma + c, gm);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] *= gm[i];
+        }
+        if (beta) {
+          float bt[8];
+          load_vec_f32<float, 8>(beta + c, bt);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += bt[i];
+        }
+        if (res) {
+          float r[8];
+          load_vec_f32<TR, 8>(res + m * ldr + g * C + c, r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += r[i];
+        }
+        store_vec_f32<TO, 8>(y + m * ldy + g * C + c, o);
+      }
+    }
+  }
+}
+
+// Generic path: any C / alignment.  Lane strides over the row; re-reads hit L1.
+__global__ void __launch_bounds__(256) layer_norm_generic_kernel(const void* __restrict__ x, int64_t ldx, int x_dtype,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 const void* __restrict__ res, int64_t ldr, int r_dtype, void* __restrict__ y,
+                                                                 int64_t ldy, int y_dtype, int64_t M, int64_t groups, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < M * groups; w += warps_total) {
+    const int64_t m = w / groups, g = w - m * groups;
+    const int64_t xo = m * ldx + g * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += load_as_f32(x, xo + c, x_dtype);
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float d = load_as_f32(x, xo + c, x_dtype) - mean;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    for (int c = lane; c < C; c += 32) {
+      float o = (load_as_f32(x, xo + c, x_dtype) - mean) * rstd;
+      if (gamma) o *= gamma[c];
+      if (beta) o += beta[c];
+      if (res) o += load_as_f32(res, m * ldr + g * C + c, r_dtype);
+      store_from_f32(y, m * ldy + g * C + c, y_dtype, o);
+    }
+  }
+}
+
+template <typename TI, typename TR, typename TO>
+static int launch_vec(const void* x, int64_t ldx, const float* gamma, const float* beta, const void* res, int64_t ldr, void* y, int64_t ldy,
+                      int64_t M, int64_t groups, int C, float eps, cudaStream_t s) {
+  const int64_t rows = M * groups;
+  int64_t blocks = (rows + 7) / 8;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+#define LN_LAUNCH(IT)                                                                                                             \
+  layer_norm_vec_kernel<TI, TR, TO, IT><<<(unsigned)blocks, 256, 0, s>>>((const TI*)x, ldx, gamma, beta, (const TR*)res, ldr, (TO*)y, ldy, M, \
+                                                                         groups, C, eps)
+  if (C <= 256)
+    LN_LAUNCH(1);
+  else if (C <= 512)
+    LN_LAUNCH(2);
+  else if (C <= 1024)
+    LN_LAUNCH(4);
+  else
+    LN_LAUNCH(8);
+#undef LN_LAUNCH
+  return launch_status("layer_norm_vec_kernel");
+}
+
+}  // namespace anemoi
+
+using namespace anemoi;
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int anemoi_b200_layer_norm(const void* x, int64_t ldx, int x_dtype, const float* gamma, const float* beta, const void* residual,
+                                      int64_t ldr, int r_dtype, void* y, int64_t ldy, int y_dtype, int64_t M, int64_t groups, int64_t C,
+                                      float eps, void* stream) {
+  ANEMOI_CHECK_ARG(M >= 0 && groups >= 1 && C >= 1 && C < (1 << 30), "layer_norm: bad shape");
+  ANEMOI_CHECK_ARG(ldx >= groups * C && ldy >= groups * C, "layer_norm: leading dimension too small");
+  ANEMOI_CHECK_ARG((x_dtype | 1) == 1 && (y_dtype | 1) == 1 && (r_dtype | 1) == 1, "layer_norm: bad dtype");
+  if (M == 0) return 0;
+  ANEMOI_CHECK_ARG(x && y, "layer_norm: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int xs = x_dtype == ANEMOI_BF16 ? 2 : 4, ys = y_dtype == ANEMOI_BF16 ? 2 : 4, rs = r_dtype == ANEMOI_BF16 ? 2 : 4;
+  const bool vec = C % 8 == 0 && C <= 2048 && aligned16(x) && aligned16(y) && (ldx * xs) % 16 == 0 && (ldy * ys) % 16 == 0 &&
+                   (C * xs) % 16 == 0 && (C * ys) % 16 == 0 && (!gamma || aligned16(gamma)) && (!beta || aligned16(beta)) &&
+                   (!residual || (aligned16(residual) && (ldr * rs) % 16 == 0 && (C * rs) % 16 == 0));
+  if (vec) {
+    const int key = x_dtype * 4 + (residual ? r_dtype : x_dtype) * 2 + y_dtype;
+    switch (key) {
+#define LN_CASE(K, TI, TR, TO) \
+  case K:                      \
+    return launch_vec<TI, TR, TO>(x, ldx, gamma, beta, residual, ldr, y, ldy, M, groups, (int)C, eps, s)
+      LN_CASE(0, float, float, float);
+      LN_CASE(1, float, float, __nv_bfloat16);
+      LN_CASE(2, float, __nv_bfloat16, float);
+      LN_CASE(3, float, __nv_bfloat16, __nv_bfloat16);
+      LN_CASE(4, __nv_bfloat16, float, float);
+      LN_CASE(5, __nv_bfloat16, float, __nv_bfloat16);
+      LN_CASE(6, __nv_bfloat16, __nv_bfloat16, float);
+      LN_CASE(7, __nv_bfloat16, __nv_bfloat16, __nv_bfloat16);
+#undef LN_CASE
+    }
+  }
+  const int64_t rows = M * groups;
+  int64_t blocks = (rows + 7) / 8;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  layer_norm_generic_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, ldx, x_dtype, gamma, beta, residual, ldr, r_dtype, y, ldy, y_dtype, M, groups,
+                                                             (int)C, eps);
+  return launch_status("layer_norm_generic_kernel");
+}

@@ -1,0 +1,114 @@
+// misc.cu — error plumbing, CSR build (integer path), cast/pad/gather copies.
+#include "common.cuh"
+
+namespace anemoi {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return -2;
+}
+
+// ---- CSR build ---------------------------------------------------------------------------------------------
+// colptr[i] = #{ e : dst[e] < i }  for dst non-decreasing == first edge position whose dst >= i.
+// One thread per edge boundary: edge e (0..E) fills colptr[(dst[e-1], dst[e]]] = e  (dst[-1] = -1, dst[E] = n_dst).
+// Each colptr entry is written by exactly one thread => no atomics, bit-exact with index2ptr on sorted input
+// (triton/utils.py:61: index2ptr(col, num_nodes[1])).  Also narrows src to int32 and validates.
+__global__ void csr_build_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E, int64_t n_src, int64_t n_dst,
+                                 int64_t* __restrict__ colptr64, int32_t* __restrict__ colptr32, int32_t* __restrict__ src32,
+                                 int32_t* __restrict__ dst32, int32_t* __restrict__ status) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e > E) return;
+  int64_t hi = (e == E) ? n_dst : dst[e];
+  int64_t lo = (e == 0) ? -1 : dst[e - 1];
+  int bad = 0;
+  if (e < E) {
+    int64_t s = src[e];
+    if (s < 0 || s >= n_src || hi < 0 || hi >= n_dst) bad |= 2;
+    src32[e] = (int32_t)s;
+    if (dst32) dst32[e] = (int32_t)hi;
+  }
+  if (hi < lo) bad |= 1;
+  if (bad) {
+    atomicOr(status, bad);
+    return;
+  }
+  if (lo < -1) lo = -1;
+  if (hi > n_dst) hi = n_dst;
+  for (int64_t i = lo + 1; i <= hi; ++i) {
+    if (colptr64) colptr64[i] = e;
+    colptr32[i] = (int32_t)e;
+  }
+}
+
+// ---- cast / pad / gather -----------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void cast_pad_kernel(const TI* __restrict__ in, int64_t ldi, const int32_t* __restrict__ idx, TO* __restrict__ out, int64_t ldo,
+                                int64_t M, int64_t K, int64_t Kpad) {
+  int64_t total = M * Kpad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t m = i / Kpad, c = i - m * Kpad;
+    float v = 0.f;
+    if (c < K) {
+      int64_t r = idx ? (int64_t)idx[m] : m;
+      v = to_f32<TI>(in[r * ldi + c]);
+    }
+    out[m * ldo + c] = from_f32<TO>(v);
+  }
+}
+
+}  // namespace anemoi
+
+using namespace anemoi;
+
+extern "C" int anemoi_b200_abi_version(void) { return 1; }
+extern "C" const char* anemoi_b200_last_error(void) { return g_err; }
+
+extern "C" int anemoi_b200_csr_build(const int64_t* edge_index, int64_t n_edges, int64_t n_src, int64_t n_dst, int64_t* colptr64,
+                                     int32_t* colptr32, int32_t* src32, int32_t* dst32, int32_t* status, void* stream) {
+  ANEMOI_CHECK_ARG(n_edges >= 0 && n_src >= 0 && n_dst >= 0, "csr_build: negative size");
+  ANEMOI_CHECK_ARG(n_edges < (1ll << 31) && n_src < (1ll << 31) && n_dst < (1ll << 31) - 1, "csr_build: sizes must fit int32");
+  ANEMOI_CHECK_ARG(colptr32 && status && (n_edges == 0 || (edge_index && src32)), "csr_build: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  ANEMOI_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
+  int threads = 256;
+  int64_t blocks = (n_edges + 1 + threads - 1) / threads;
+  csr_build_kernel<<<(unsigned)blocks, threads, 0, s>>>(edge_index, edge_index ? edge_index + n_edges : nullptr, n_edges, n_src, n_dst,
+                                                        colptr64, colptr32, src32, dst32, status);
+  return launch_status("csr_build_kernel");
+}
+
+extern "C" int anemoi_b200_cast_pad(const void* in, int64_t ldi, int i_dtype, const int32_t* idx, void* out, int64_t ldo, int o_dtype,
+                                    int64_t M, int64_t K, int64_t Kpad, void* stream) {
+  ANEMOI_CHECK_ARG(M >= 0 && K >= 0 && Kpad >= K && ldo >= Kpad && ldi >= K, "cast_pad: bad shape");
+  if (M == 0 || Kpad == 0) return 0;
+  ANEMOI_CHECK_ARG(in && out, "cast_pad: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  int threads = 256;
+  int64_t blocks = (M * Kpad + threads - 1) / threads;
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+#define LAUNCH(TI, TO) \
+  cast_pad_kernel<TI, TO><<<(unsigned)blocks, threads, 0, s>>>((const TI*)in, ldi, idx, (TO*)out, ldo, M, K, Kpad)
+  if (i_dtype == ANEMOI_F32 && o_dtype == ANEMOI_F32)
+    LAUNCH(float, float);
+  else if (i_dtype == ANEMOI_F32 && o_dtype == ANEMOI_BF16)
+    LAUNCH(float, __nv_bfloat16);
+  else if (i_dtype == ANEMOI_BF16 && o_dtype == ANEMOI_F32)
+    LAUNCH(__nv_bfloat16, float);
+  else if (i_dtype == ANEMOI_BF16 && o_dtype == ANEMOI_BF16)
+    LAUNCH(__nv_bfloat16, __nv_bfloat16);
+  else {
+    set_error("cast_pad: bad dtype %d -> %d", i_dtype, o_dtype);
+    return -1;
+  }
+#undef LAUNCH
+  return launch_status("cast_pad_kernel");
+}

@@ -1,0 +1,52 @@
+"""Forward halves of the reference's sharding collectives (distributed/graph.py:66-253, primitives.py:144-183) for the
+dst-range ("edges") strategy: every rank owns a contiguous range of destination rows and all edges into them
+(khop_edges.py:266-314), so no cross-rank reduction is needed — only source rows move.
+
+One process per GPU, ``torch.distributed`` process group (NCCL over NVLink/NVSwitch on the B200 box, Gloo in the
+CPU tests).  With ``model_comm_group`` None or of size 1 every function is the identity.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def group_size(group: Optional[dist.ProcessGroup]) -> int:
+    return 1 if group is None else dist.get_world_size(group=group)
+
+
+def group_rank(group: Optional[dist.ProcessGroup]) -> int:
+    return 0 if group is None else dist.get_rank(group=group)
+
+
+def shard_rows(x: Tensor, sizes: Optional[list[int]], group: Optional[dist.ProcessGroup]) -> Tensor:
+    """Local row range of a replicated tensor (reference ``shard_tensor`` forward, graph.py:66-91)."""
+    if group_size(group) == 1 or sizes is None:
+        return x
+    r = group_rank(group)
+    start = sum(sizes[:r])
+    return x[start : start + sizes[r]]
+
+
+def gather_rows(x: Tensor, sizes: Optional[list[int]], group: Optional[dist.ProcessGroup]) -> Tensor:
+    """All-gather row shards into the full tensor (reference ``gather_tensor`` / ``sync_tensor`` forward,
+    graph.py:94-135, primitives.py:144-183).  Shards may differ by one row (balanced partition); NCCL's
+    all_gather_into_tensor needs equal sizes, so unequal shards go through the list form."""
+    world = group_size(group)
+    if world == 1:
+        return x
+    if sizes is None:
+        raise ValueError("gather_rows: per-rank shard sizes are required when the model group has more than one rank")
+    if len(sizes) != world or x.shape[0] != sizes[group_rank(group)]:
+        raise ValueError(f"gather_rows: local shard has {x.shape[0]} rows, shard sizes {sizes} (world {world})")
+    x = x.contiguous()
+    out = torch.empty((sum(sizes),) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    if len(set(sizes)) == 1:
+        dist.all_gather_into_tensor(out, x, group=group)
+    else:
+        dist.all_gather(list(torch.split(out, sizes, dim=0)), x, group=group)
+    return out

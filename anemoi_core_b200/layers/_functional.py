@@ -1,0 +1,155 @@
+"""Shared forward plumbing: compute-dtype choice, packed (cast / concatenated / K-padded) weights, fused MLP runs,
+and the per-graph CSR cache.  Everything numerical is a call into ``ops`` (the C ABI)."""
+
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Callable
+from typing import Optional
+from typing import Sequence
+
+import torch
+from torch import Tensor
+from torch import nn
+
+from .. import ops
+
+SUPPORTED = (torch.float32, torch.bfloat16)
+
+
+def compute_dtype(*tensors: Tensor) -> torch.dtype:
+    """bf16 under ``torch.autocast(dtype=bfloat16)`` or for bf16 inputs (tcgen05 path); fp32 otherwise (parity mode)."""
+    if torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
+    else:
+        dt = tensors[0].dtype
+        for t in tensors[1:]:
+            if t.dtype != dt:
+                dt = torch.promote_types(dt, t.dtype)
+    if dt not in SUPPORTED:
+        raise NotImplementedError(f"compute dtype {dt} is not implemented (float32 and bfloat16 are)")
+    return dt
+
+
+def forward_only_guard(module: nn.Module) -> None:
+    if module.training and torch.is_grad_enabled():
+        raise NotImplementedError(
+            "anemoi_core_b200 implements the forward pass only (SURVEY.md §8f rank 3: backward is a later row); "
+            "call .eval() and/or run under torch.no_grad()"
+        )
+
+
+def round8(k: int) -> int:
+    return (k + 7) // 8 * 8
+
+
+class WeightPack:
+    """Derived tensors of a module's parameters (dtype casts, row-concatenations, zero K-padding), rebuilt when a
+    source parameter changes (in-place update, ``load_state_dict``, ``.to()``)."""
+
+    def __init__(self) -> None:
+        self._store: dict = {}
+
+    def get(self, key, sources: Sequence[Optional[Tensor]], build: Callable[[], Tensor]) -> Tensor:
+        sig = tuple(None if t is None else (t.data_ptr(), t._version, t.device, t.dtype, tuple(t.shape)) for t in sources)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        with torch.no_grad():
+            val = build()
+        self._store[key] = (sig, val)
+        return val
+
+    def weight(self, layers: Sequence[nn.Module], dt: torch.dtype, cols: Optional[slice] = None) -> Tensor:
+        """Row-concatenated weights of ``layers`` ([sum N_i, K]) in dtype ``dt``; for bf16 the K dimension is zero-padded
+        to a multiple of 8 (TMA needs 16-byte row strides).  ``cols`` selects input columns (split of a concatenated input)."""
+        ws = [l.weight for l in layers]
+
+        def build() -> Tensor:
+            w = torch.cat([x.detach() for x in ws], 0) if len(ws) > 1 else ws[0].detach()
+            if cols is not None:
+                w = w[:, cols]
+            k = w.shape[1]
+            if dt == torch.bfloat16 and k % 8:
+                w = torch.nn.functional.pad(w, (0, round8(k) - k))
+            return w.to(dt).contiguous()
+
+        return self.get(("w", tuple(id(l) for l in layers), dt, None if cols is None else (cols.start, cols.stop)), ws, build)
+
+    def bias(self, layers: Sequence[nn.Module]) -> Optional[Tensor]:
+        bs = [getattr(l, "bias", None) for l in layers]
+        if all(b is None for b in bs):
+            return None
+
+        def build() -> Tensor:
+            parts = [b.detach().float() if b is not None else torch.zeros(l.weight.shape[0], device=l.weight.device) for b, l in zip(bs, layers)]
+            return torch.cat(parts).contiguous()
+
+        return self.get(("b", tuple(id(l) for l in layers)), bs, build)
+
+    def f32(self, p: Optional[Tensor]) -> Optional[Tensor]:
+        if p is None:
+            return None
+        if p.dtype == torch.float32 and p.is_contiguous():
+            return p.detach()
+        return self.get(("f32", id(p)), [p], lambda: p.detach().float().contiguous())
+
+
+def as_operand(x: Tensor, dt: torch.dtype, k_weight: int) -> Tensor:
+    """Make ``x`` [M, K] a GEMM A-operand of dtype ``dt`` whose width matches the (possibly K-padded) weight."""
+    if x.dim() != 2:
+        raise ValueError(f"expected [nodes, channels], got {tuple(x.shape)}")
+    k = x.shape[1]
+    if x.dtype == dt and k == k_weight and x.stride(1) == 1:
+        return x
+    return ops.cast_pad(x, dt, k_weight)
+
+
+def fused_linear(pack: WeightPack, x: Tensor, layers: Sequence[nn.Module], dt: torch.dtype, cols: Optional[slice] = None, **kw) -> Tensor:
+    """``x @ cat(W_i).T + cat(b_i)`` with the epilogue options of ``ops.linear`` (gelu / residual / gathers / out)."""
+    for l in layers:
+        if not hasattr(l, "weight") or l.weight.dim() != 2:
+            raise NotImplementedError(f"{type(l).__name__} is not a Linear-like parameter container (needs a 2-D .weight)")
+    w = pack.weight(layers, dt, cols)
+    bias = pack.bias(layers) if kw.pop("use_bias", True) else None
+    return ops.linear(as_operand(x, dt, w.shape[1]), w, bias, **kw)
+
+
+def layer_norm_mod(pack: WeightPack, ln: nn.Module, x: Tensor, dt: torch.dtype, residual: Optional[Tensor] = None, groups: int = 1) -> Tensor:
+    from .normalization import _check_plain_layernorm
+
+    _check_plain_layernorm(ln)
+    return ops.layer_norm(x, pack.f32(ln.weight), pack.f32(ln.bias), ln.eps, residual=residual, out_dtype=dt, groups=groups)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# per-graph CSR cache
+# ------------------------------------------------------------------------------------------------------------
+_CSR_CACHE: "OrderedDict[tuple, tuple[Tensor, ops.GraphCSR]]" = OrderedDict()
+_CSR_CACHE_SIZE = 16
+
+
+def csr_for(edge_index: Tensor, n_src: int, n_dst: int) -> ops.GraphCSR:
+    """CSR plan of a dst-sorted edge_index, cached on the tensor's identity (storage pointer, version, shape).  The
+    cache holds a reference to the tensor so its storage cannot be recycled under the key.  Built once per static
+    graph; the reference rebuilds its CSC (two sorts) per layer per forward (layers/block.py:779-782)."""
+    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), tuple(edge_index.stride()), str(edge_index.device), n_src, n_dst)
+    hit = _CSR_CACHE.get(key)
+    if hit is not None:
+        _CSR_CACHE.move_to_end(key)
+        return hit[1]
+    validate = not torch.cuda.is_current_stream_capturing()
+    csr = ops.build_csr(edge_index, n_src, n_dst, validate=validate)
+    _CSR_CACHE[key] = (edge_index, csr)
+    while len(_CSR_CACHE) > _CSR_CACHE_SIZE:
+        _CSR_CACHE.popitem(last=False)
+    return csr
+
+
+def pad_edge_attr(edge_attr: Tensor) -> Tensor:
+    """fp32 [E, ceil4(d_e)] zero-padded copy of the raw edge attributes (16-byte rows for the fused lin_edge path)."""
+    d = edge_attr.shape[1]
+    d4 = (d + 3) // 4 * 4
+    if edge_attr.dtype == torch.float32 and d == d4 and edge_attr.is_contiguous():
+        return edge_attr
+    return ops.cast_pad(edge_attr, torch.float32, d4)

@@ -1,0 +1,301 @@
+"""Processor / mapper blocks (reference: layers/block.py:275-479 GraphConv*, :482-1273 GraphTransformer*).
+
+Same constructor kwargs, forward signatures, return values and ``state_dict`` keys as the reference blocks.
+Forward = a short, fixed sequence of fused sm_100a kernels (DESIGN.md lists them per block); single-GPU or
+dst-range-sharded across a model communication group (``distributed/graph.py``).
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+from typing import Union
+
+import torch
+from torch import Tensor
+from torch import nn
+
+from .. import ops
+from ..distributed.graph import gather_rows
+from ..distributed.graph import group_size
+from ..distributed.shapes import BipartiteGraphShardInfo
+from ..distributed.shapes import GraphShardInfo
+from . import _functional as Fn
+from .conv import GraphConv
+from .mlp import MLP
+from .utils import compute_mlp_hidden_dim
+from .utils import load_layer_kernels
+
+PairTensor = tuple[Tensor, Tensor]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GraphConv (GNN) blocks
+# ------------------------------------------------------------------------------------------------------------
+class GraphConvBaseBlock(nn.Module):
+    """Edge-MLP message passing + node MLP (block.py:275-358)."""
+
+    def __init__(
+        self,
+        *,
+        in_channels: int,
+        out_channels: int,
+        num_chunks: int = 1,
+        mlp_extra_layers: int = 0,
+        mlp_hidden_ratio: float = 1.0,
+        mlp_implementation: str = "mlp",
+        update_src_nodes: bool = True,
+        layer_kernels=None,
+        edge_dim: Optional[int] = None,
+        **kwargs,
+    ) -> None:
+        super().__init__()
+        layer_kernels = load_layer_kernels(layer_kernels)
+        hidden_dim = compute_mlp_hidden_dim(out_channels, mlp_hidden_ratio)
+        mlp_kw = dict(layer_kernels=layer_kernels, n_extra_layers=mlp_extra_layers + 1, mlp_implementation=mlp_implementation)
+        self.emb_edges = MLP(edge_dim, hidden_dim, out_channels, **mlp_kw) if edge_dim else None
+        self.update_src_nodes = update_src_nodes
+        self.num_chunks = num_chunks  # edge chunking only bounds the reference's [E, 3C] temporaries; nothing to bound here
+        self.node_mlp = MLP(2 * in_channels, hidden_dim, out_channels, **mlp_kw)
+        self.conv = GraphConv(in_channels=in_channels, out_channels=out_channels, layer_kernels=layer_kernels, mlp_extra_layers=mlp_extra_layers,
+                              mlp_implementation=mlp_implementation)  # fmt: skip
+        self.in_channels, self.out_channels = in_channels, out_channels
+
+    def _node_update(self, x: Tensor, agg_buf: Tensor, dt: torch.dtype) -> Tensor:
+        """node_mlp(cat[x, out]) + x, with ``out`` already sitting in the right half of ``agg_buf`` [N, 2C]."""
+        C = self.in_channels
+        ops.cast_pad(x, dt, out=agg_buf[:, :C])
+        return self.node_mlp.run(agg_buf, dt, residual=agg_buf[:, :C])
+
+
+class GraphConvProcessorBlock(GraphConvBaseBlock):
+    def forward(
+        self,
+        x: Tensor,
+        edge_attr: Tensor,
+        edge_index: Tensor,
+        shard_info: Optional[GraphShardInfo] = None,
+        model_comm_group=None,
+        size=None,
+        **layer_kwargs,
+    ) -> tuple[Tensor, Tensor]:
+        Fn.forward_only_guard(self)
+        dt = Fn.compute_dtype(x, edge_attr)
+        if self.emb_edges is not None:
+            edge_attr = self.emb_edges.run(edge_attr, dt)
+        # block.py:375 — every rank needs all source rows: all-gather of the node shards (no-op on one GPU)
+        x_full = gather_rows(x, shard_info.nodes if shard_info is not None else None, model_comm_group)
+        n_local = x.shape[0]
+        csr = Fn.csr_for(edge_index, x_full.shape[0], x_full.shape[0])
+        C = self.in_channels
+        if group_size(model_comm_group) > 1:
+            # local edges only reach local dst rows; aggregate over the full index range and keep our rows (block.py:391)
+            agg_full = torch.empty((x_full.shape[0], C), dtype=dt, device=x.device)
+            _, edges_new = self.conv.run(x_full, x_full, edge_attr, csr, dt, out=agg_full)
+            rank = torch.distributed.get_rank(model_comm_group)
+            start = sum(shard_info.nodes[:rank])
+            agg_buf = torch.empty((n_local, 2 * C), dtype=dt, device=x.device)
+            ops.cast_pad(agg_full[start : start + n_local], dt, out=agg_buf[:, C:])
+        else:
+            agg_buf = torch.empty((n_local, 2 * C), dtype=dt, device=x.device)
+            _, edges_new = self.conv.run(x_full, x_full, edge_attr, csr, dt, out=agg_buf[:, C:])
+        return self._node_update(x, agg_buf, dt), edges_new
+
+
+class GraphConvMapperBlock(GraphConvBaseBlock):
+    def forward(
+        self,
+        x: PairTensor,
+        edge_attr: Tensor,
+        edge_index: Tensor,
+        shard_info: Optional[BipartiteGraphShardInfo] = None,
+        model_comm_group=None,
+        size=None,
+        **layer_kwargs,
+    ) -> tuple[PairTensor, Tensor]:
+        Fn.forward_only_guard(self)
+        if group_size(model_comm_group) > 1:
+            raise NotImplementedError("sharded GraphConv mappers: run the mappers replicated or with model_comm_group=None")
+        x_src, x_dst = x
+        dt = Fn.compute_dtype(x_src, x_dst, edge_attr)
+        C = self.in_channels
+        csr = Fn.csr_for(edge_index, x_src.shape[0], x_dst.shape[0])
+        agg_buf = torch.empty((x_dst.shape[0], 2 * C), dtype=dt, device=x_dst.device)
+        _, edges_new = self.conv.run(x_src, x_dst, edge_attr, csr, dt, out=agg_buf[:, C:])
+        dst_new = self._node_update(x_dst, agg_buf, dt)
+        src_new = x_src
+        if self.update_src_nodes:  # block.py:475 — the same node_mlp on cat[x_src, x_src]
+            src_buf = torch.empty((x_src.shape[0], 2 * C), dtype=dt, device=x_src.device)
+            ops.cast_pad(x_src, dt, out=src_buf[:, :C])
+            ops.cast_pad(x_src, dt, out=src_buf[:, C:])
+            src_new = self.node_mlp.run(src_buf, dt, residual=src_buf[:, :C])
+        return (src_new, dst_new), edges_new
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GraphTransformer blocks
+# ------------------------------------------------------------------------------------------------------------
+class GraphTransformerBaseBlock(nn.Module):
+    """Edge-softmax attention block (block.py:482-687).  Per forward:
+    LN -> one GEMM for q|k|v|self -> fused attention(+lin_edge, +self) -> projection GEMM(+skip) -> LN -> MLP GEMMs(+residual).
+    """
+
+    def __init__(
+        self,
+        *,
+        in_channels: int,
+        hidden_dim: int,
+        out_channels: int,
+        num_heads: int,
+        edge_dim: int,
+        bias: bool = True,
+        qk_norm: bool = False,
+        mlp_implementation: str = "mlp",
+        update_src_nodes: bool = False,
+        layer_kernels=None,
+        attn_channels: Optional[int] = None,
+        graph_attention_backend: str = "triton",
+        edge_pre_mlp: bool = False,
+        **kwargs,
+    ) -> None:
+        super().__init__()
+        k = load_layer_kernels(layer_kernels)
+        self.update_src_nodes = update_src_nodes
+        self.attn_channels = out_channels if attn_channels is None else attn_channels
+        if self.attn_channels <= 0:
+            raise ValueError(f"attn_channels must be > 0, got {self.attn_channels}")
+        if self.attn_channels % num_heads != 0:
+            raise ValueError(f"attn_channels ({self.attn_channels}) must be divisible by num_heads ({num_heads}) in {self.__class__.__name__}.")
+        self.out_channels_conv = self.attn_channels // num_heads
+        self.num_heads = num_heads
+        self.qk_norm = qk_norm
+        A = num_heads * self.out_channels_conv
+        self.lin_key = k.Linear(in_channels, A)
+        self.lin_query = k.Linear(in_channels, A)
+        self.lin_value = k.Linear(in_channels, A)
+        self.lin_self = k.Linear(in_channels, A, bias=bias)
+        self.lin_edge = k.Linear(edge_dim, A)
+        self.projection = k.Linear(self.attn_channels, out_channels)
+        if self.qk_norm:
+            self.q_norm = k.QueryNorm(self.out_channels_conv)
+            self.k_norm = k.KeyNorm(self.out_channels_conv)
+        self.layer_norm_attention = k.LayerNorm(normalized_shape=in_channels)
+        self.layer_norm_mlp_dst = k.LayerNorm(normalized_shape=out_channels)
+        self.node_dst_mlp = MLP(out_channels, hidden_dim, out_channels, layer_kernels=k, n_extra_layers=0, layer_norm=False,
+                                mlp_implementation=mlp_implementation)  # fmt: skip
+        self.edge_pre_mlp = nn.Sequential(k.Linear(edge_dim, edge_dim), k.Activation()) if edge_pre_mlp else nn.Identity()
+        if graph_attention_backend not in ("triton", "pyg", "b200"):
+            raise ValueError(f"Backend '{graph_attention_backend}' not supported for {self.__class__.__name__}")
+        # accepted for config compatibility; there is exactly one implementation here (the sm_100a kernel)
+        self.graph_attention_backend = graph_attention_backend
+        self._pack = Fn.WeightPack()
+
+    # -- pieces -------------------------------------------------------------------------------------------------
+    def prepare_edges(self, edge_attr: Tensor) -> Tensor:
+        """Raw edge attributes -> fp32 [E, ceil4(d_e)] operand of the fused lin_edge (after edge_pre_mlp if present)."""
+        if not isinstance(self.edge_pre_mlp, nn.Identity):
+            lin = self.edge_pre_mlp[0]
+            edge_attr = Fn.fused_linear(self._pack, edge_attr.float() if edge_attr.dtype != torch.float32 else edge_attr, [lin], torch.float32,
+                                        gelu=True)  # fmt: skip
+        return Fn.pad_edge_attr(edge_attr)
+
+    def _attention(self, q: Tensor, k: Tensor, v: Tensor, x_r: Tensor, edge_attr_p: Tensor, csr: ops.GraphCSR, dt: torch.dtype) -> Tensor:
+        """att + x_r, with lin_edge fused into the attention kernel."""
+        if self.qk_norm:
+            for t, norm in ((q, self.q_norm), (k, self.k_norm)):
+                ops.layer_norm(t, self._pack.f32(norm.weight), self._pack.f32(getattr(norm, "bias", None)), norm.eps, out=t, groups=self.num_heads)
+        w_e = self._pack.get(("w_edge",), [self.lin_edge.weight], lambda: self.lin_edge.weight.detach().float().contiguous())
+        b_e = self._pack.f32(self.lin_edge.bias)
+        return ops.gt_attention(q, k, v, csr, self.num_heads, edge_attr=edge_attr_p, w_edge=w_e, b_edge=b_e, add=x_r)
+
+    def _tail(self, att_plus_self: Tensor, x_skip: Tensor, dt: torch.dtype) -> Tensor:
+        """projection(att + x_r) + x_skip ; then MLP(LN(.)) + .   (block.py:1019-1023 / :1268-1271)."""
+        skip = x_skip if x_skip.dtype in Fn.SUPPORTED else x_skip.float()
+        out = Fn.fused_linear(self._pack, att_plus_self, [self.projection], dt, residual=skip)
+        h = Fn.layer_norm_mod(self._pack, self.layer_norm_mlp_dst, out, dt)
+        return self.node_dst_mlp.run(h, dt, residual=out)
+
+
+class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
+    def __init__(self, *, shard_strategy: str = "edges", **kwargs) -> None:
+        super().__init__(**kwargs)
+        if shard_strategy not in ("edges", "heads"):
+            raise ValueError(f"Invalid shard strategy '{shard_strategy}'")
+        self.shard_strategy = shard_strategy
+
+    def forward(
+        self,
+        x: Tensor,
+        edge_attr: Tensor,
+        edge_index: Tensor,
+        shard_info: Optional[GraphShardInfo] = None,
+        batch_size: int = 1,
+        size=None,
+        model_comm_group=None,
+        cond: Optional[Tensor] = None,
+        edges_are_dst_sorted: bool = True,
+        edge_attr_prepared: Optional[Tensor] = None,
+        **kwargs,
+    ) -> tuple[Tensor, Tensor]:
+        Fn.forward_only_guard(self)
+        if cond is not None:
+            raise NotImplementedError("conditional LayerNorm (cond=...) is not implemented")
+        dt = Fn.compute_dtype(x)
+        A = self.attn_channels
+        xn = Fn.layer_norm_mod(self._pack, self.layer_norm_attention, x, dt)
+        qkvs = Fn.fused_linear(self._pack, xn, [self.lin_query, self.lin_key, self.lin_value, self.lin_self], dt)
+        q, kv, x_r = qkvs[:, :A], qkvs[:, A : 3 * A], qkvs[:, 3 * A :]
+        # edges strategy, block.py:1148-1183: each rank owns a dst range; it needs the k|v rows of all sources
+        kv_full = gather_rows(kv, shard_info.nodes if shard_info is not None else None, model_comm_group)
+        csr = Fn.csr_for(edge_index, kv_full.shape[0], x.shape[0])
+        ea = edge_attr_prepared if edge_attr_prepared is not None else self.prepare_edges(edge_attr)
+        att = self._attention(q, kv_full[:, :A], kv_full[:, A:], x_r, ea, csr, dt)
+        return self._tail(att, x, dt), edge_attr
+
+
+class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
+    def __init__(self, *, shard_strategy: str = "edges", **kwargs) -> None:
+        super().__init__(**kwargs)
+        k = load_layer_kernels(kwargs.get("layer_kernels"))
+        in_channels, out_channels = kwargs["in_channels"], kwargs["out_channels"]
+        self.layer_norm_attention_src = k.LayerNorm(normalized_shape=in_channels)
+        self.layer_norm_attention_dest = self.layer_norm_attention  # alias, as in the reference (block.py:941)
+        if self.update_src_nodes:
+            self.layer_norm_mlp_src = k.LayerNorm(normalized_shape=out_channels)
+            self.node_src_mlp = MLP(out_channels, kwargs["hidden_dim"], out_channels, layer_kernels=k, n_extra_layers=0, layer_norm=False,
+                                    mlp_implementation=kwargs.get("mlp_implementation", "mlp"))  # fmt: skip
+        else:
+            self.layer_norm_mlp_src = nn.Identity()
+            self.node_src_mlp = nn.Identity()
+        self.shard_strategy = shard_strategy
+
+    def forward(
+        self,
+        x: PairTensor,
+        edge_attr: Tensor,
+        edge_index: Tensor,
+        shard_info: Optional[BipartiteGraphShardInfo] = None,
+        batch_size: int = 1,
+        size=None,
+        model_comm_group=None,
+        cond=None,
+        edges_are_dst_sorted: bool = True,
+        **layer_kwargs,
+    ) -> tuple[PairTensor, Tensor]:
+        Fn.forward_only_guard(self)
+        if cond is not None:
+            raise NotImplementedError("conditional LayerNorm (cond=...) is not implemented")
+        x_src, x_dst = x
+        dt = Fn.compute_dtype(x_src, x_dst)
+        A = self.attn_channels
+        xs_n = Fn.layer_norm_mod(self._pack, self.layer_norm_attention_src, x_src, dt)
+        xd_n = Fn.layer_norm_mod(self._pack, self.layer_norm_attention_dest, x_dst, dt)
+        kv = Fn.fused_linear(self._pack, xs_n, [self.lin_key, self.lin_value], dt)
+        qs = Fn.fused_linear(self._pack, xd_n, [self.lin_query, self.lin_self], dt)
+        csr = Fn.csr_for(edge_index, x_src.shape[0], x_dst.shape[0])
+        att = self._attention(qs[:, :A], kv[:, :A], kv[:, A:], qs[:, A:], self.prepare_edges(edge_attr), csr, dt)
+        dst_new = self._tail(att, x_dst, dt)
+        src_new = x_src
+        if self.update_src_nodes:
+            h = Fn.layer_norm_mod(self._pack, self.layer_norm_mlp_src, x_src, dt)
+            src_new = self.node_src_mlp.run(h, dt, residual=x_src if x_src.dtype in Fn.SUPPORTED else x_src.float())
+        return (src_new, dst_new), edge_attr

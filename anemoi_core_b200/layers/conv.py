@@ -1,0 +1,111 @@
+"""Graph message-passing operators (reference: layers/conv.py:29-81 GraphConv, :84-147 GraphTransformerConv).
+
+No torch_geometric ``MessagePassing`` here: both operators run over the cached dst-sorted CSR on sm_100a kernels.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+from typing import Union
+
+import torch
+from torch import Tensor
+from torch import nn
+
+from .. import ops
+from ..distributed.khop_edges import sort_edge_index_by_dst
+from . import _functional as Fn
+from .mlp import MLP
+
+PairTensor = tuple[Tensor, Tensor]
+
+
+def _sorted_plan(edge_index: Tensor, n_src: int, n_dst: int) -> tuple[ops.GraphCSR, Optional[Tensor]]:
+    """CSR plan for ``edge_index``; if it turns out not to be dst-sorted, stable-sort it (like the reference's
+    ``edge_index_to_csc(..., edges_are_dst_sorted=False)``, triton/utils.py:49-59) and return the int32 permutation."""
+    try:
+        return Fn.csr_for(edge_index, n_src, n_dst), None
+    except ValueError as err:
+        if "not sorted" not in str(err):
+            raise
+    sorted_ei, perm = sort_edge_index_by_dst(edge_index)
+    return ops.build_csr(sorted_ei.contiguous(), n_src, n_dst), perm.to(torch.int32)
+
+
+class GraphConv(nn.Module):
+    """e' = edge_mlp([x_dst[dst], x_src[src], e]) + e ;  out[d] = sum_{edges into d} e'   (conv.py:66-81).
+
+    Kernel decomposition: the first Linear of ``edge_mlp`` acts on a concatenation, so
+    ``W1 [x_i; x_j; e] = (W1_i x_dst)[dst] + (W1_j x_src)[src] + W1_e e``: two node-level GEMMs (N rows instead of E)
+    feed a gather-add epilogue of the edge-level GEMM, the [E, 3C] concatenation never exists; the LayerNorm, the
+    ``+ e`` residual and the scatter-sum are one segmented-reduction kernel over the dst-sorted edges.
+    """
+
+    def __init__(self, in_channels: int, out_channels: int, layer_kernels=None, mlp_extra_layers: int = 0, mlp_implementation: str = "mlp", **kwargs):
+        super().__init__()
+        self.in_channels = in_channels
+        self.edge_mlp = MLP(3 * in_channels, out_channels, out_channels, layer_kernels=layer_kernels, n_extra_layers=mlp_extra_layers + 1,
+                            mlp_implementation=mlp_implementation)  # fmt: skip
+        self._pack = Fn.WeightPack()
+
+    def run(self, x_src: Tensor, x_dst: Tensor, edge_attr: Tensor, csr: ops.GraphCSR, dt: torch.dtype, out: Optional[Tensor] = None):
+        C = self.in_channels
+        mlp = self.edge_mlp
+        if mlp.layer_norm is None:
+            raise NotImplementedError("GraphConv.edge_mlp without LayerNorm")
+        first = mlp.mlp[0]
+        # node-level projections of the first edge-MLP layer, fp32 so the gather-add is a single rounding
+        p_i = Fn.fused_linear(self._pack, x_dst, [first], dt, cols=slice(0, C), use_bias=False, out_dtype=torch.float32)
+        p_j = Fn.fused_linear(self._pack, x_src, [first], dt, cols=slice(C, 2 * C), use_bias=False, out_dtype=torch.float32)
+        e = Fn.as_operand(edge_attr, dt, edge_attr.shape[1])
+        # hidden layers through the MLP runner up to (not including) the LayerNorm
+        mods = list(mlp.mlp)
+        h, i, is_first = e, 0, True
+        while i < len(mods):
+            lin = mods[i]
+            act = i + 1 < len(mods) and not hasattr(mods[i + 1], "weight")
+            kw = {}
+            if is_first:
+                kw = {"gather1": (p_i, csr.dst32), "gather2": (p_j, csr.src32), "cols": slice(2 * C, 3 * C)}
+            h = Fn.fused_linear(mlp._pack, h, [lin], dt, gelu=act, **kw)
+            i += 2 if act else 1
+            is_first = False
+        ln = mlp.layer_norm
+        e_new, out = ops.graphconv_ln_aggregate(h, mlp._pack.f32(ln.weight), mlp._pack.f32(ln.bias), e, csr, ln.eps, out=out)
+        return out, e_new
+
+    def forward(self, x: Union[Tensor, PairTensor], edge_attr: Tensor, edge_index: Tensor, size=None):
+        Fn.forward_only_guard(self)
+        x_src, x_dst = x if isinstance(x, (tuple, list)) else (x, x)
+        dt = Fn.compute_dtype(x_src, x_dst, edge_attr)
+        csr, perm = _sorted_plan(edge_index, x_src.shape[0], x_dst.shape[0])
+        if perm is not None:
+            raise ValueError("GraphConv returns per-edge features in edge order: pass a dst-sorted edge_index (sort_edge_index_by_dst)")
+        return self.run(x_src, x_dst, edge_attr, csr, dt)
+
+
+class GraphTransformerConv(nn.Module):
+    """out[d,h] = sum_e softmax_e(q[d,h].(k[src_e,h]+e[e,h]) / sqrt(Ch)) (v[src_e,h]+e[e,h])   (conv.py:103-147).
+
+    Operator-level boundary of the reference (``self.conv(query, key, value, edges, edge_index, size)``,
+    block.py:787-791) with the edge projection materialised; the blocks use the fused lin_edge form instead."""
+
+    def __init__(self, out_channels: int, dropout: float = 0.0, **kwargs):
+        super().__init__()
+        if dropout:
+            raise NotImplementedError("attention dropout is training-only and not implemented (forward/inference path)")
+        self.out_channels = out_channels
+        self.dropout = dropout
+
+    def forward(self, query: Tensor, key: Tensor, value: Tensor, edge_attr: Optional[Tensor], edge_index: Tensor, size=None) -> Tensor:
+        n_dst, heads, ch = query.shape
+        n_src = key.shape[0]
+        csr, perm = _sorted_plan(edge_index, n_src, n_dst)
+        dt = query.dtype
+        e = None
+        if edge_attr is not None:
+            e = edge_attr.reshape(edge_attr.shape[0], heads * ch)
+            e = ops.cast_pad(e, dt, idx=perm) if (perm is not None or e.dtype != dt) else e
+        out = ops.gt_attention(query.reshape(n_dst, heads * ch), key.reshape(n_src, heads * ch), value.reshape(n_src, heads * ch), csr, heads,
+                               e_proj=e)  # fmt: skip
+        return out.reshape(n_dst, heads, ch)

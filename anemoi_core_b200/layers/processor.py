@@ -1,0 +1,195 @@
+"""Processors: stacks of N message-passing blocks (reference: layers/processor.py:52-147, 319-626).
+
+Drop-in for ``anemoi.models.layers.processor.{GNNProcessor, GraphTransformerProcessor}``: keyword-only constructors
+with the reference's names, ``forward(x, batch_size, shard_info, edge_attr, edge_index, model_comm_group=None,
+edges_are_dst_sorted=True)``, blocks held in ``self.proc`` (same ``state_dict`` keys).  Activation checkpointing
+and CPU offload are training-memory devices of the reference and are accepted but inert on this forward path.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+from torch import nn
+
+from ..distributed.graph import group_rank
+from ..distributed.graph import group_size
+from ..distributed.khop_edges import build_graph_partition
+from ..distributed.khop_edges import ensure_edges_are_dst_sorted
+from ..distributed.shapes import GraphShardInfo
+from . import _functional as Fn
+from .block import GraphConvProcessorBlock
+from .block import GraphTransformerProcessorBlock
+from .utils import compute_mlp_hidden_dim
+from .utils import load_layer_kernels
+
+
+class BaseProcessor(nn.Module):
+    def __init__(
+        self,
+        *,
+        num_layers: int,
+        num_channels: int,
+        num_chunks: int,
+        cpu_offload: bool = False,
+        gradient_checkpointing: bool = True,
+        layer_kernels=None,
+        **kwargs,
+    ) -> None:
+        super().__init__()
+        if num_layers % num_chunks != 0:
+            raise AssertionError(
+                f"Number of processor layers ({num_layers}) has to be divisible by the number of processor chunks ({num_chunks})."
+            )
+        if cpu_offload:
+            raise NotImplementedError("cpu_offload is a training-memory option of the reference; not part of the B200 forward path")
+        self.num_layers = num_layers
+        self.num_chunks = num_chunks
+        self.chunk_size = num_layers // num_chunks
+        self.num_channels = num_channels
+        self.gradient_checkpointing = gradient_checkpointing
+        self.layer_factory = load_layer_kernels(layer_kernels)
+
+    def build_layers(self, layer_class, **layer_kwargs) -> None:
+        self.proc = nn.ModuleList([layer_class(**layer_kwargs) for _ in range(self.num_layers)])
+
+
+def _shard_edges_by_dst(edge_attr: Tensor, edge_index: Tensor, n_dst: int, n_src: int, group) -> tuple[Tensor, Tensor, list[int]]:
+    """Keep the edges into this rank's balanced dst range (reference ``shard_edges_1hop``, khop_edges.py:266-314).
+    Indices stay global.  Returns (edge_attr, edge_index, per-rank edge counts)."""
+    world = group_size(group)
+    part = build_graph_partition(edge_index, world, (n_src, n_dst))
+    e0, e1 = part.edge_range(group_rank(group))
+    return edge_attr[e0:e1], edge_index[:, e0:e1], list(part.edge_splits)
+
+
+class GNNProcessor(BaseProcessor):
+    """GraphConv processor (processor.py:319-455).  Layer 0 embeds the raw edge attributes; each layer hands its
+    updated edge features to the next."""
+
+    def __init__(
+        self,
+        *,
+        num_channels: int,
+        num_layers: int,
+        num_chunks: int,
+        mlp_extra_layers: int,
+        edge_dim: int,
+        mlp_hidden_ratio: float = 1.0,
+        mlp_implementation: str = "mlp",
+        cpu_offload: bool = False,
+        layer_kernels=None,
+        **kwargs,
+    ) -> None:
+        super().__init__(num_channels=num_channels, num_layers=num_layers, num_chunks=num_chunks, cpu_offload=cpu_offload,
+                         layer_kernels=layer_kernels, **kwargs)  # fmt: skip
+        build = dict(in_channels=num_channels, out_channels=num_channels, num_chunks=1, mlp_extra_layers=mlp_extra_layers,
+                     mlp_hidden_ratio=mlp_hidden_ratio, mlp_implementation=mlp_implementation, layer_kernels=self.layer_factory)  # fmt: skip
+        self.build_layers(GraphConvProcessorBlock, edge_dim=None, **build)
+        self.proc[0] = GraphConvProcessorBlock(edge_dim=edge_dim, **build)
+
+    def forward(
+        self,
+        x: Tensor,
+        batch_size: int,
+        shard_info: GraphShardInfo,
+        edge_attr: Tensor,
+        edge_index: Tensor,
+        model_comm_group=None,
+        edges_are_dst_sorted: bool = True,
+        *args,
+        **kwargs,
+    ) -> Tensor:
+        Fn.forward_only_guard(self)
+        n_nodes = sum(shard_info.nodes) if shard_info is not None and shard_info.nodes_are_sharded() else x.shape[0]
+        if shard_info is None:
+            shard_info = GraphShardInfo()
+        if not shard_info.edges_are_sharded():
+            edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
+            if group_size(model_comm_group) > 1:
+                edge_attr, edge_index, edge_sizes = _shard_edges_by_dst(edge_attr, edge_index, n_nodes, n_nodes, model_comm_group)
+                shard_info = GraphShardInfo(nodes=shard_info.nodes, edges=edge_sizes)
+        for block in self.proc:
+            x, edge_attr = block(x, edge_attr, edge_index, shard_info, model_comm_group)
+        return x
+
+
+class GraphTransformerProcessor(BaseProcessor):
+    """GraphTransformer processor (processor.py:458-626).  The raw edge attributes are shared by all layers; each
+    layer owns its lin_edge, fused into its attention kernel."""
+
+    def __init__(
+        self,
+        *,
+        num_layers: int,
+        num_channels: int,
+        num_chunks: int,
+        num_heads: int,
+        mlp_hidden_ratio: float,
+        edge_dim: int,
+        attn_channels: Optional[int] = None,
+        qk_norm: bool = False,
+        mlp_implementation: str = "mlp",
+        cpu_offload: bool = False,
+        layer_kernels=None,
+        shard_strategy: str = "edges",
+        graph_attention_backend: str = "triton",
+        edge_pre_mlp: bool = False,
+        **kwargs,
+    ) -> None:
+        super().__init__(num_channels=num_channels, num_layers=num_layers, num_chunks=num_chunks, cpu_offload=cpu_offload,
+                         layer_kernels=layer_kernels, **kwargs)  # fmt: skip
+        if shard_strategy not in ("edges", "heads"):
+            raise AssertionError(f"Invalid shard strategy '{shard_strategy}' for {self.__class__.__name__}. Supported strategies are 'edges' and 'heads'.")
+        if shard_strategy == "heads":
+            raise NotImplementedError("shard_strategy='heads' (Ulysses all-to-all) is not implemented; use 'edges' (SURVEY.md §2.4)")
+        self.shard_strategy = shard_strategy
+        self.build_layers(
+            GraphTransformerProcessorBlock,
+            in_channels=num_channels,
+            hidden_dim=compute_mlp_hidden_dim(num_channels, mlp_hidden_ratio),
+            out_channels=num_channels,
+            attn_channels=attn_channels,
+            num_heads=num_heads,
+            layer_kernels=self.layer_factory,
+            qk_norm=qk_norm,
+            mlp_implementation=mlp_implementation,
+            shard_strategy=shard_strategy,
+            graph_attention_backend=graph_attention_backend,
+            edge_dim=edge_dim,
+            edge_pre_mlp=edge_pre_mlp,
+        )
+
+    def forward(
+        self,
+        x: Tensor,
+        batch_size: int,
+        shard_info: GraphShardInfo,
+        edge_attr: Tensor,
+        edge_index: Tensor,
+        model_comm_group=None,
+        edges_are_dst_sorted: bool = True,
+        *args,
+        **kwargs,
+    ) -> Tensor:
+        Fn.forward_only_guard(self)
+        if shard_info is None:
+            shard_info = GraphShardInfo()
+        n_nodes = sum(shard_info.nodes) if shard_info.nodes_are_sharded() else x.shape[0]
+        if not shard_info.edges_are_sharded():
+            edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
+            if group_size(model_comm_group) > 1:
+                edge_attr, edge_index, edge_sizes = _shard_edges_by_dst(edge_attr, edge_index, n_nodes, n_nodes, model_comm_group)
+                shard_info = GraphShardInfo(nodes=shard_info.nodes, edges=edge_sizes)
+        if group_size(model_comm_group) > 1:
+            # local dst rows only: relabel dst to the local range (src ids stay global, sources are all-gathered per layer)
+            start = sum(shard_info.nodes[: group_rank(model_comm_group)])
+            edge_index = torch.stack([edge_index[0], edge_index[1] - start])
+        shared_edges = None
+        if all(isinstance(b.edge_pre_mlp, nn.Identity) for b in self.proc):
+            shared_edges = self.proc[0].prepare_edges(edge_attr)  # one padded fp32 copy for all layers
+        for block in self.proc:
+            x, _ = block(x, edge_attr, edge_index, shard_info, batch_size, n_nodes, model_comm_group, edge_attr_prepared=shared_edges)
+        return x

@@ -1,0 +1,306 @@
+"""Tensor-level wrappers over the C ABI (``include/anemoi_b200.h``): each function checks shapes, passes raw device
+pointers + leading dimensions + the current CUDA stream, and returns torch tensors.  No compute happens in Python
+or PyTorch here; a CPU tensor is an error (there is no fallback path).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import BF16
+from ._lib import EPI_GELU
+from ._lib import F32
+
+__all__ = ["GraphCSR", "build_csr", "layer_norm", "linear", "gt_attention", "graphconv_ln_aggregate", "cast_pad", "dtype_code"]
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise TypeError(f"anemoi_core_b200 computes in float32 or bfloat16, got {dt}")
+
+
+def _need_cuda(*tensors: Optional[Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("anemoi_core_b200 kernels run on CUDA tensors only (sm_100a); got a CPU tensor and there is no CPU fallback")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _rows(t: Tensor) -> tuple[int, int, int]:
+    """(rows, cols, leading dimension) of a 2-D tensor whose last dimension is contiguous."""
+    if t.dim() != 2:
+        raise ValueError(f"expected a 2-D tensor, got shape {tuple(t.shape)}")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise ValueError("last dimension must be contiguous")
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+    return t.shape[0], t.shape[1], ld
+
+
+def _f32(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise TypeError("bias / LayerNorm / edge parameters must be contiguous float32 tensors")
+    return t
+
+
+# ------------------------------------------------------------------------------------------------------------
+# integer path
+# ------------------------------------------------------------------------------------------------------------
+@dataclass
+class GraphCSR:
+    """Cached per-graph index plan (replaces the per-layer ``edge_index_to_csc`` of layers/block.py:779-782)."""
+
+    n_src: int
+    n_dst: int
+    n_edges: int
+    colptr: Tensor  # int64 [n_dst+1]  — reference dtype (triton/utils.py:61)
+    colptr32: Tensor  # int32 [n_dst+1]
+    src32: Tensor  # int32 [E]
+    dst32: Tensor  # int32 [E]
+
+
+def build_csr(edge_index: Tensor, n_src: int, n_dst: int, validate: bool = True) -> GraphCSR:
+    """CSR of a dst-sorted ``edge_index`` [2, E] int64.  ``validate`` synchronises once to raise on unsorted /
+    out-of-range input (the reference trusts ``edges_are_dst_sorted``; we check once per cached graph)."""
+    _need_cuda(edge_index)
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise TypeError("edge_index must be an int64 tensor of shape [2, E]")
+    edge_index = edge_index.contiguous()
+    n_edges = edge_index.shape[1]
+    dev = edge_index.device
+    colptr = torch.empty(n_dst + 1, dtype=torch.int64, device=dev)
+    colptr32 = torch.empty(n_dst + 1, dtype=torch.int32, device=dev)
+    src32 = torch.empty(n_edges, dtype=torch.int32, device=dev)
+    dst32 = torch.empty(n_edges, dtype=torch.int32, device=dev)
+    status = torch.empty(1, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    rc = lib.anemoi_b200_csr_build(
+        _ptr(edge_index), n_edges, n_src, n_dst, _ptr(colptr), _ptr(colptr32), _ptr(src32), _ptr(dst32), _ptr(status), _stream()
+    )
+    _lib.check(rc, "anemoi_b200_csr_build")
+    if validate:
+        st = int(status.item())
+        if st & 2:
+            raise ValueError(f"edge_index has node ids outside [0, {n_src}) x [0, {n_dst})")
+        if st & 1:
+            raise ValueError("edge_index is not sorted by destination; sort it (sort_edge_index_by_dst) or pass edges_are_dst_sorted=False")
+    return GraphCSR(n_src, n_dst, n_edges, colptr, colptr32, src32, dst32)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# float kernels
+# ------------------------------------------------------------------------------------------------------------
+def layer_norm(
+    x: Tensor,
+    weight: Optional[Tensor],
+    bias: Optional[Tensor],
+    eps: float = 1e-5,
+    residual: Optional[Tensor] = None,
+    out: Optional[Tensor] = None,
+    out_dtype: Optional[torch.dtype] = None,
+    groups: int = 1,
+) -> Tensor:
+    """y = LayerNorm(x) (* weight + bias) (+ residual) over the last ``C = x.shape[1] / groups`` elements."""
+    _need_cuda(x, weight, bias, residual, out)
+    M, W, ldx = _rows(x)
+    if W % groups:
+        raise ValueError("row width not divisible by groups")
+    C = W // groups
+    if out is None:
+        out = torch.empty((M, W), dtype=out_dtype or x.dtype, device=x.device)
+    _, Wo, ldy = _rows(out)
+    if Wo != W or out.shape[0] != M:
+        raise ValueError("output shape mismatch")
+    ldr, rdt = 0, F32
+    if residual is not None:
+        Mr, Wr, ldr = _rows(residual)
+        if (Mr, Wr) != (M, W):
+            raise ValueError("residual shape mismatch")
+        rdt = dtype_code(residual.dtype)
+    for p in (weight, bias):
+        if p is not None and p.numel() != C:
+            raise ValueError("LayerNorm parameter size mismatch")
+    rc = _lib.load().anemoi_b200_layer_norm(
+        _ptr(x), ldx, dtype_code(x.dtype), _ptr(_f32(weight)), _ptr(_f32(bias)), _ptr(residual), ldr, rdt, _ptr(out), ldy,
+        dtype_code(out.dtype), M, groups, C, float(eps), _stream())  # fmt: skip
+    _lib.check(rc, "anemoi_b200_layer_norm")
+    return out
+
+
+def linear(
+    a: Tensor,
+    weight: Tensor,
+    bias: Optional[Tensor] = None,
+    gelu: bool = False,
+    residual: Optional[Tensor] = None,
+    gather1: Optional[tuple[Tensor, Tensor]] = None,
+    gather2: Optional[tuple[Tensor, Tensor]] = None,
+    out: Optional[Tensor] = None,
+    out_dtype: Optional[torch.dtype] = None,
+) -> Tensor:
+    """out = [gelu](a @ weight.T + bias + g1[idx1] + g2[idx2]) + residual.
+
+    ``a`` [M, K] and ``weight`` [N, K] share a dtype (bf16 -> tcgen05 tensor cores, fp32 -> exact FFMA);
+    ``gatherX = (table fp32 [*, >=N], idx int32 [M])``.
+    """
+    _need_cuda(a, weight, bias, residual, out)
+    M, K, lda = _rows(a)
+    N, Kw, ldw = _rows(weight)
+    if K != Kw:
+        raise ValueError(f"linear: inner dimensions differ ({K} vs {Kw})")
+    if a.dtype != weight.dtype:
+        raise TypeError(f"linear: operand dtypes differ ({a.dtype} vs {weight.dtype})")
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype or a.dtype, device=a.device)
+    Mo, No, ldo = _rows(out)
+    if (Mo, No) != (M, N):
+        raise ValueError("linear: output shape mismatch")
+    ldr, rdt = 0, F32
+    if residual is not None:
+        Mr, Nr, ldr = _rows(residual)
+        if (Mr, Nr) != (M, N):
+            raise ValueError("linear: residual shape mismatch")
+        rdt = dtype_code(residual.dtype)
+    g1 = i1 = g2 = i2 = None
+    ldg = 0
+    for n, g in enumerate((gather1, gather2)):
+        if g is None:
+            continue
+        tab, idx = g
+        _need_cuda(tab, idx)
+        _, Ng, ld = _rows(tab)
+        if tab.dtype != torch.float32 or Ng < N or idx.dtype != torch.int32 or idx.numel() != M or not idx.is_contiguous():
+            raise TypeError("linear: gather tables must be float32 [*, >=N] with contiguous int32 indices [M]")
+        if ldg not in (0, ld):
+            raise ValueError("linear: the two gather tables must share a leading dimension")
+        ldg = ld
+        if n == 0:
+            g1, i1 = tab, idx
+        else:
+            g2, i2 = tab, idx
+    if g1 is None and g2 is not None:
+        g1, i1, g2, i2 = g2, i2, None, None
+    rc = _lib.load().anemoi_b200_linear(
+        _ptr(a), lda, _ptr(weight), ldw, dtype_code(a.dtype), _ptr(_f32(bias)), _ptr(g1), _ptr(i1), _ptr(g2), _ptr(i2), ldg, _ptr(residual),
+        ldr, rdt, _ptr(out), ldo, dtype_code(out.dtype), M, N, K, EPI_GELU if gelu else 0, _stream())  # fmt: skip
+    _lib.check(rc, "anemoi_b200_linear")
+    return out
+
+
+def gt_attention(
+    q: Tensor,
+    k: Tensor,
+    v: Tensor,
+    csr: GraphCSR,
+    heads: int,
+    e_proj: Optional[Tensor] = None,
+    edge_attr: Optional[Tensor] = None,
+    w_edge: Optional[Tensor] = None,
+    b_edge: Optional[Tensor] = None,
+    add: Optional[Tensor] = None,
+    out: Optional[Tensor] = None,
+) -> Tensor:
+    """Edge-softmax attention over the cached CSR.  q [n_dst, H*Ch]; k, v [n_src, H*Ch] (column slices allowed).
+
+    Either ``e_proj`` [E, H*Ch] (materialised lin_edge output, reference operator boundary) or the fused form
+    ``edge_attr`` fp32 [E, d_e] (+ ``w_edge`` fp32 [H*Ch, d_e], ``b_edge`` fp32 [H*Ch]).  ``add`` is summed into the output.
+    """
+    _need_cuda(q, k, v, e_proj, edge_attr, w_edge, b_edge, add, out)
+    n_dst, C, ldq = _rows(q)
+    n_src, Ck, ldk = _rows(k)
+    n_src_v, Cv, ldv = _rows(v)
+    if not (C == Ck == Cv) or n_src != n_src_v or C % heads:
+        raise ValueError("gt_attention: q/k/v shape mismatch")
+    if n_dst != csr.n_dst or n_src != csr.n_src:
+        raise ValueError(f"gt_attention: CSR is for ({csr.n_src}, {csr.n_dst}) nodes, tensors have ({n_src}, {n_dst})")
+    if not (q.dtype == k.dtype == v.dtype):
+        raise TypeError("gt_attention: q/k/v dtypes differ")
+    if out is None:
+        out = torch.empty((n_dst, C), dtype=q.dtype, device=q.device)
+    _, Co, ldo = _rows(out)
+    if Co != C or out.dtype != q.dtype:
+        raise ValueError("gt_attention: output mismatch")
+    lde_proj = lde = ldw_e = d_e = ldadd = 0
+    if e_proj is not None:
+        E, Ce, lde_proj = _rows(e_proj)
+        if E != csr.n_edges or Ce != C or e_proj.dtype != q.dtype:
+            raise ValueError("gt_attention: e_proj mismatch")
+    if edge_attr is not None:
+        E, d_e_pad, lde = _rows(edge_attr)
+        Cw, d_e, ldw_e = _rows(w_edge)
+        if E != csr.n_edges or Cw != C or d_e > d_e_pad or edge_attr.dtype != torch.float32 or w_edge.dtype != torch.float32:
+            raise ValueError("gt_attention: fused lin_edge arguments mismatch")
+    if add is not None:
+        na, Ca, ldadd = _rows(add)
+        if (na, Ca) != (n_dst, C) or add.dtype != q.dtype:
+            raise ValueError("gt_attention: add mismatch")
+    rc = _lib.load().anemoi_b200_gt_attention_fwd(
+        _ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(e_proj), lde_proj, _ptr(edge_attr), lde, d_e, _ptr(w_edge), ldw_e, _ptr(_f32(b_edge)),
+        _ptr(csr.src32), _ptr(csr.colptr32), _ptr(add), ldadd, _ptr(out), ldo, n_dst, heads, C // heads, dtype_code(q.dtype), _stream())  # fmt: skip
+    _lib.check(rc, "anemoi_b200_gt_attention_fwd")
+    return out
+
+
+def graphconv_ln_aggregate(
+    h: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], e: Tensor, csr: GraphCSR, eps: float = 1e-5, out: Optional[Tensor] = None
+) -> tuple[Tensor, Tensor]:
+    """(e_new, out): e_new = LayerNorm(h) + e ; out[d] = sum of e_new over the (dst-sorted) edges into d."""
+    _need_cuda(h, weight, bias, e, out)
+    E, C, ldh = _rows(h)
+    Ee, Ce, lde = _rows(e)
+    if (E, C) != (Ee, Ce) or E != csr.n_edges or h.dtype != e.dtype:
+        raise ValueError("graphconv_ln_aggregate: h / e mismatch")
+    e_new = torch.empty((E, C), dtype=h.dtype, device=h.device)
+    if out is None:
+        out = torch.empty((csr.n_dst, C), dtype=h.dtype, device=h.device)
+    no, Co, ldo = _rows(out)
+    if (no, Co) != (csr.n_dst, C) or out.dtype != h.dtype:
+        raise ValueError("graphconv_ln_aggregate: output mismatch")
+    rc = _lib.load().anemoi_b200_graphconv_ln_aggregate(
+        _ptr(h), ldh, _ptr(_f32(weight)), _ptr(_f32(bias)), _ptr(e), lde, _ptr(e_new), C, _ptr(csr.colptr32), _ptr(out), ldo, csr.n_dst, C,
+        float(eps), dtype_code(h.dtype), _stream())  # fmt: skip
+    _lib.check(rc, "anemoi_b200_graphconv_ln_aggregate")
+    return e_new, out
+
+
+def cast_pad(x: Tensor, dtype: torch.dtype, k_pad: Optional[int] = None, idx: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """Copy/cast [M, K] into [M, k_pad] (zero-filled tail), optionally gathering rows ``x[idx]`` (idx int32)."""
+    _need_cuda(x, idx, out)
+    M, K, ldi = _rows(x)
+    if idx is not None:
+        if idx.dtype != torch.int32 or not idx.is_contiguous():
+            raise TypeError("cast_pad: idx must be contiguous int32")
+        M = idx.numel()
+    k_pad = K if k_pad is None else k_pad
+    if out is None:
+        out = torch.empty((M, k_pad), dtype=dtype, device=x.device)
+    Mo, Ko, ldo = _rows(out)
+    if Mo != M or Ko < k_pad:
+        raise ValueError("cast_pad: output mismatch")
+    rc = _lib.load().anemoi_b200_cast_pad(_ptr(x), ldi, dtype_code(x.dtype), _ptr(idx), _ptr(out), ldo, dtype_code(out.dtype), M, K, k_pad, _stream())
+    _lib.check(rc, "anemoi_b200_cast_pad")
+    return out

@@ -1,0 +1,119 @@
+/* anemoi_b200.h — C ABI of libanemoi_b200.so: hand-written sm_100a kernels for the anemoi-models graph
+ * message-passing forward (GraphConv / GraphTransformer processor blocks + grid<->mesh mappers).
+ *
+ * The reference (ecmwf/anemoi-core) has NO native code; every entry point below replaces a chain of
+ * PyTorch / torch_geometric / Triton calls of the reference hot path.  Paths are relative to
+ * /root/reference/models/src/anemoi/models/ .  INTEGRATION.md shows the ctypes binding and where the
+ * reference's modules would call each symbol.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers owned by the caller (PyTorch).  The library never allocates or frees
+ *    device memory and keeps no global device state; host-side it only caches TMA descriptors.
+ *  - Every call only ENQUEUES work on `stream` (a cudaStream_t / CUstream passed as void*): no device
+ *    synchronisation, CUDA-graph capturable, re-entrant, one caller thread per device.
+ *  - Matrices are row-major with an explicit leading dimension in ELEMENTS (`ld*`), so column slices of wider
+ *    buffers (q|k|v|self, x|aggregate) are passed without copies.
+ *  - dtype codes: ANEMOI_F32 = 0, ANEMOI_BF16 = 1.  Biases, LayerNorm affine parameters, edge attributes and
+ *    the lin_edge weights are always fp32.  Accumulation is always fp32.
+ *  - Index arrays produced by anemoi_b200_csr_build are int32 (`src32`, `colptr32`); the reference-facing
+ *    `colptr64` keeps the reference's int64 dtype (triton/utils.py:61-70) for bit-exact comparison.
+ *  - Return value: 0 on success, negative on error (-1 bad argument, -2 CUDA error, -3 unsupported shape);
+ *    anemoi_b200_last_error() returns a thread-local message.  Nothing throws or exits across the ABI.
+ */
+#ifndef ANEMOI_B200_H
+#define ANEMOI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANEMOI_F32 0
+#define ANEMOI_BF16 1
+
+#if defined(__GNUC__)
+#define ANEMOI_API __attribute__((visibility("default")))
+#else
+#define ANEMOI_API
+#endif
+
+/* anemoi_b200_linear flags */
+#define ANEMOI_EPI_GELU 1 /* exact (erf) GELU after bias/gather-add, before residual  (torch.nn.GELU default) */
+
+ANEMOI_API int anemoi_b200_abi_version(void);
+ANEMOI_API const char* anemoi_b200_last_error(void);
+
+/* -- integer path ------------------------------------------------------------------------------------------
+ * Replaces triton/utils.py:25-70 `edge_index_to_csc` (colptr = index2ptr(dst); row = src) and the sortedness
+ * check of distributed/khop_edges.py:43-48 for an edge_index [2,E] int64 that is already dst-sorted
+ * (layers/graph_provider.py:185).  Built once per static graph instead of per layer per forward
+ * (layers/block.py:779-782).
+ *   edge_index : int64 [2, n_edges] row-major (row 0 = src, row 1 = dst)
+ *   colptr64   : int64 [n_dst+1]  (may be NULL)      colptr32 : int32 [n_dst+1]
+ *   src32      : int32 [n_edges]                     dst32 : int32 [n_edges] (may be NULL)
+ *   status     : int32 [1], bit0 set if dst not non-decreasing, bit1 if an index is out of range
+ */
+ANEMOI_API int anemoi_b200_csr_build(const int64_t* edge_index, int64_t n_edges, int64_t n_src, int64_t n_dst, int64_t* colptr64,
+                          int32_t* colptr32, int32_t* src32, int32_t* dst32, int32_t* status, void* stream);
+
+/* -- LayerNorm ---------------------------------------------------------------------------------------------
+ * torch.nn.LayerNorm / AutocastLayerNorm (layers/normalization.py:19-31) over the last `C` elements, eps as
+ * given, optional affine (gamma/beta may be NULL), optional residual added AFTER the normalisation
+ * (GraphConv: e' = LN(h) + e, conv.py:75-76; node_mlp(...) + x, block.py:393).
+ * x is addressed as x[m*ldx + g*C + c] for m < M, g < groups (groups > 1: per-head q/k norm, block.py:655-660).
+ */
+ANEMOI_API int anemoi_b200_layer_norm(const void* x, int64_t ldx, int x_dtype, const float* gamma, const float* beta, const void* residual,
+                           int64_t ldr, int r_dtype, void* y, int64_t ldy, int y_dtype, int64_t M, int64_t groups, int64_t C,
+                           float eps, void* stream);
+
+/* -- Linear with fused epilogue ----------------------------------------------------------------------------
+ * out[M,N] = epi( A[M,K] . W[N,K]^T ),  epi(acc) = [gelu]( acc + bias + g1[idx1[m]] + g2[idx2[m]] ) + residual
+ * Replaces torch.nn.Linear (+ GELU, + residual add, + the torch.cat([x_i, x_j, e]) of conv.py:74 through the
+ * gather-add terms: W.[x_i;x_j;e] = (W_i x_dst)[dst] + (W_j x_src)[src] + W_e e ).
+ *   a_dtype == ANEMOI_BF16 : A, W bf16 -> tcgen05 (UMMA 128xBNx16, TMA SW128 operands, TMEM accumulators).
+ *                            Requires lda % 8 == 0, ldw % 8 == 0, 16-byte aligned A and W.
+ *   a_dtype == ANEMOI_F32  : A, W fp32 -> fp32 FFMA path (parity mode; no tensor cores, no TF32 rounding).
+ *   bias  : fp32 [N] or NULL.  g1/g2 : fp32 [*, ldg] gathered by int32 row indices idx1/idx2 [M], or NULL.
+ *   residual : [M, ldr] of r_dtype or NULL.   out : [M, ldo] of o_dtype.
+ */
+ANEMOI_API int anemoi_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, int a_dtype, const float* bias, const float* g1,
+                       const int32_t* idx1, const float* g2, const int32_t* idx2, int64_t ldg, const void* residual, int64_t ldr,
+                       int r_dtype, void* out, int64_t ldo, int o_dtype, int64_t M, int64_t N, int64_t K, int flags, void* stream);
+
+/* -- GraphTransformer edge-softmax attention (forward) -------------------------------------------------------
+ * Replaces layers/conv.py:103-147 (GraphTransformerConv, PyG softmax) and triton/gt.py:81-179 / :390-428
+ * (`anemoi::graph_transformer_attention`), optionally fused with lin_edge (block.py:623-635):
+ *   out[d,h,:] = sum_e alpha[e,h] (v[src_e,h,:] + eproj[e,h,:]) (+ add[d,h,:]),
+ *   alpha = softmax over edges into d of  q[d,h,:].(k[src_e,h,:] + eproj[e,h,:]) / sqrt(Ch)
+ * with eproj either materialised (`e`, [E, H*Ch] of `dtype`) or computed in-kernel from the raw edge
+ * attributes: eproj[e] = w_edge . edge_attr[e] + b_edge  (edge_attr fp32 [E, lde], w_edge fp32 [H*Ch, ldw_e]).
+ * Zero in-degree rows give 0 (+ add), like gt.py:112-119.  fp32 online softmax.
+ *   q [n_dst, ldq], k,v [n_src, ldk/ldv], add/out [n_dst, ld*] of `dtype`; src32/colptr32 from csr_build.
+ */
+ANEMOI_API int anemoi_b200_gt_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* e,
+                                 int64_t lde_proj, const float* edge_attr, int64_t lde, int64_t edge_dim, const float* w_edge,
+                                 int64_t ldw_e, const float* b_edge, const int32_t* src32, const int32_t* colptr32,
+                                 const void* add, int64_t ldadd, void* out, int64_t ldo, int64_t n_dst, int64_t heads, int64_t ch,
+                                 int dtype, void* stream);
+
+/* -- GraphConv tail: LayerNorm + residual + dst-segmented sum ------------------------------------------------
+ * Replaces the tail of layers/conv.py:73-81: e'[i] = LN(h[i]) + e[i]  (written to e_new) and
+ * out[d] = sum_{edges i into d} e'[i]  (scatter-sum; deterministic segmented reduction over the dst-sorted
+ * edges, fp32 accumulation, no atomics).  h, e, e_new : [E, ld*]; out : [n_dst, ldo].
+ */
+ANEMOI_API int anemoi_b200_graphconv_ln_aggregate(const void* h, int64_t ldh, const float* gamma, const float* beta, const void* e, int64_t lde,
+                                       void* e_new, int64_t ldn, const int32_t* colptr32, void* out, int64_t ldo, int64_t n_dst,
+                                       int64_t C, float eps, int dtype, void* stream);
+
+/* -- helpers -----------------------------------------------------------------------------------------------
+ * cast/copy a [M, K] matrix into a [M, ldo] buffer (zero-filling columns K..Kpad-1), any of f32/bf16 <-> f32/bf16,
+ * optionally gathering rows: out[m] = in[idx[m]] (idx int32, may be NULL).
+ */
+ANEMOI_API int anemoi_b200_cast_pad(const void* in, int64_t ldi, int i_dtype, const int32_t* idx, void* out, int64_t ldo, int o_dtype, int64_t M,
+                         int64_t K, int64_t Kpad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANEMOI_B200_H */

@@ -1,0 +1,246 @@
+"""Kernel-level parity on a B200 (-m gpu): every C-ABI entry point against the oracle / a plain fp32 PyTorch statement
+of the same op on the same seeded inputs.  Integer outputs bit-exact; fp32 kernels to ~1e-5; bf16 kernels are compared
+with an fp32 reference evaluated on the SAME bf16-rounded operands (so the only differences are fp32 accumulation
+order and the final bf16 rounding: tolerance 2^-7 relative to the row scale)."""
+import math
+
+import pytest
+import torch
+
+from oracle import restatement as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from anemoi_core_b200 import ops as _ops
+
+    return _ops
+
+
+def _rand_graph(n_src, n_dst, n_edges, seed, zero_tail=0):
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.stack([torch.randint(0, n_src, (n_edges,), generator=g), torch.randint(0, max(n_dst - zero_tail, 1), (n_edges,), generator=g)])
+    return ei[:, torch.sort(ei[1], stable=True)[1]]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_csr_build_bit_exact(ops, golden):
+    for c in golden("integer_path")["cases"]:
+        n_src, n_dst = c["num_nodes"]
+        csr = ops.build_csr(c["sorted"].cuda(), n_src, n_dst)
+        assert csr.colptr.dtype == torch.int64
+        assert torch.equal(csr.colptr.cpu(), c["colptr"])
+        assert torch.equal(csr.colptr32.cpu().long(), c["colptr"])
+        assert torch.equal(csr.src32.cpu().long(), c["sorted"][0])
+        assert torch.equal(csr.dst32.cpu().long(), c["sorted"][1])
+    # larger, with empty rows at both ends
+    ei = _rand_graph(5000, 7000, 60000, 3, zero_tail=50)
+    ei[1] += 0
+    csr = ops.build_csr(ei.cuda(), 5000, 7000)
+    assert torch.equal(csr.colptr.cpu(), R.index2ptr(ei[1], 7000))
+
+
+def test_csr_build_rejects_unsorted_and_out_of_range(ops):
+    ei = torch.tensor([[0, 1, 2], [2, 1, 0]])
+    with pytest.raises(ValueError, match="not sorted"):
+        ops.build_csr(ei.cuda(), 3, 3)
+    with pytest.raises(ValueError, match="outside"):
+        ops.build_csr(torch.tensor([[0, 5], [0, 1]]).cuda(), 3, 3)
+
+
+@pytest.mark.parametrize("C,groups", [(32, 1), (64, 1), (512, 1), (1024, 1), (100, 1), (2048, 1), (16, 4), (32, 16), (6, 6)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_layer_norm(ops, C, groups, dt):
+    g = torch.Generator().manual_seed(C + groups)
+    M = 777
+    x = (torch.randn(M, groups * C, generator=g) * 2 + 0.5).to(dt)
+    w, b = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    r = torch.randn(M, groups * C, generator=g).to(dt)
+    ref = torch.nn.functional.layer_norm(x.float().view(M, groups, C), (C,), w, b, 1e-5).view(M, -1) + r.float()
+    y = ops.layer_norm(x.cuda(), w.cuda(), b.cuda(), 1e-5, residual=r.cuda(), groups=groups)
+    assert y.dtype == dt
+    tol = 2e-5 if dt == torch.float32 else 2**-7
+    torch.testing.assert_close(y.float().cpu(), ref, atol=tol * 4, rtol=tol)
+    # no affine, no residual, fp32 output from any input, strided input (column slice)
+    wide = torch.zeros(M, groups * C + 8, dtype=dt)
+    wide[:, : groups * C] = x
+    y2 = ops.layer_norm(wide.cuda()[:, : groups * C], None, None, 1e-5, out_dtype=torch.float32, groups=groups)
+    ref2 = torch.nn.functional.layer_norm(x.float().view(M, groups, C), (C,), None, None, 1e-5).view(M, -1)
+    torch.testing.assert_close(y2.cpu(), ref2, atol=1e-4, rtol=1e-4)
+
+
+def _linear_ref(a, w, bias, gelu, residual, g1, i1, g2, i2):
+    y = a.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    if g1 is not None:
+        y = y + g1[i1.long()][:, : y.shape[1]]
+    if g2 is not None:
+        y = y + g2[i2.long()][:, : y.shape[1]]
+    if gelu:
+        y = torch.nn.functional.gelu(y)
+    if residual is not None:
+        y = y + residual.float()
+    return y
+
+
+LINEAR_SHAPES = [
+    # M, N, K           fp32 FFMA path and bf16 tcgen05 path (K >= 64, K % 8 == 0) / bf16 FFMA path (small or odd K)
+    (300, 512, 512),
+    (1000, 2048, 512),
+    (129, 512, 2048),
+    (257, 88, 512),
+    (4099, 64, 64),
+    (515, 200, 216),
+    (100, 64, 11),
+    (77, 33, 70),
+    (1, 8, 64),
+]
+
+
+@pytest.mark.parametrize("M,N,K", LINEAR_SHAPES)
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("epi", ["plain", "bias_gelu", "bias_res", "gather"])
+def test_linear(ops, M, N, K, dt, epi):
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).to(dt)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dt)
+    bias = torch.randn(N, generator=g) if epi != "plain" else None
+    residual = torch.randn(M, N, generator=g).to(dt) if epi == "bias_res" else None
+    g1 = i1 = g2 = i2 = None
+    if epi == "gather":
+        ldg = (N + 3) // 4 * 4
+        g1, g2 = torch.randn(50, ldg, generator=g), torch.randn(60, ldg, generator=g)
+        i1 = torch.randint(0, 50, (M,), generator=g, dtype=torch.int32)
+        i2 = torch.randint(0, 60, (M,), generator=g, dtype=torch.int32)
+    ref = _linear_ref(a, w, bias, epi in ("bias_gelu", "gather"), residual, g1, i1, g2, i2)
+    cu = lambda t: None if t is None else t.cuda()
+    y = ops.linear(cu(a), cu(w), cu(bias), gelu=epi in ("bias_gelu", "gather"), residual=cu(residual),
+                   gather1=None if g1 is None else (cu(g1)[:, :N] if ldg == N else cu(g1), cu(i1)),
+                   gather2=None if g2 is None else (cu(g2)[:, :N] if ldg == N else cu(g2), cu(i2)))  # fmt: skip
+    assert y.dtype == dt and tuple(y.shape) == (M, N)
+    if dt == torch.float32:
+        torch.testing.assert_close(y.cpu(), ref, atol=2e-5, rtol=2e-5)
+    else:
+        scale = ref.abs().max().item()
+        err = (y.float().cpu() - ref).abs().max().item()
+        assert err <= 2**-7 * scale + 1e-3, f"max err {err} at scale {scale}"
+    # fp32 output from bf16 operands (node projections for the gather-add epilogue)
+    if dt == torch.bfloat16 and epi == "plain":
+        y32 = ops.linear(cu(a), cu(w), out_dtype=torch.float32)
+        torch.testing.assert_close(y32.cpu(), ref, atol=1e-3, rtol=1e-3)
+
+
+def test_linear_strided_views(ops):
+    """Column slices of wider buffers as A, residual and out (how the blocks pass q|k|v|self and x|aggregate)."""
+    g = torch.Generator().manual_seed(5)
+    for dt in (torch.float32, torch.bfloat16):
+        big_a = torch.randn(333, 1024, generator=g).to(dt).cuda()
+        w = (torch.randn(256, 512, generator=g) / 22).to(dt).cuda()
+        big_o = torch.zeros(333, 768, dtype=dt, device="cuda")
+        res = torch.randn(333, 512, generator=g).to(dt).cuda()
+        ops.linear(big_a[:, 512:], w, residual=res[:, 256:], out=big_o[:, 256:512])
+        ref = big_a[:, 512:].float() @ w.float().t() + res[:, 256:].float()
+        tol = 2e-5 if dt == torch.float32 else 2**-7 * ref.abs().max().item()
+        assert (big_o[:, 256:512].float() - ref).abs().max().item() <= tol + 1e-5
+        assert torch.all(big_o[:, :256] == 0) and torch.all(big_o[:, 512:] == 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_gt_attention_golden_conv_cases(ops, golden):
+    """The reference's own Triton-parity shapes (test_triton_gt.py:49-57, non-power-of-two heads/channels) + zero in-degree rows,
+    at the reference's bar atol=1e-4 (test_triton_gt.py:135-136)."""
+    for c in golden("gt_conv")["cases"]:
+        n_dst, H, Ch = c["q"].shape
+        n_src = c["k"].shape[0]
+        csr = ops.build_csr(c["edge_index"].cuda(), n_src, n_dst)
+        out = ops.gt_attention(c["q"].reshape(n_dst, -1).cuda(), c["k"].reshape(n_src, -1).cuda(), c["v"].reshape(n_src, -1).cuda(), csr, H,
+                               e_proj=c["e"].reshape(-1, H * Ch).cuda())  # fmt: skip
+        torch.testing.assert_close(out.cpu().view(n_dst, H, Ch), c["out"], atol=1e-4, rtol=0)
+        assert torch.all(out[-2:] == 0)
+
+
+@pytest.mark.parametrize("H,Ch", [(16, 32), (16, 64), (4, 16), (8, 8), (2, 32), (3, 20)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_gt_attention_modes(ops, H, Ch, dt):
+    """Materialised-e and fused-lin_edge forms against the oracle (PyG-softmax statement) on a bipartite random graph."""
+    g = torch.Generator().manual_seed(H * 100 + Ch)
+    n_src, n_dst, E, d_e = 300, 257, 2500, 11
+    ei = _rand_graph(n_src, n_dst, E, 11, zero_tail=3)
+    C = H * Ch
+    q = torch.randn(n_dst, C, generator=g).to(dt)
+    k = torch.randn(n_src, C, generator=g).to(dt)
+    v = torch.randn(n_src, C, generator=g).to(dt)
+    a = torch.randn(E, d_e, generator=g)
+    w_e, b_e = torch.randn(C, d_e, generator=g) / 3, torch.randn(C, generator=g)
+    add = torch.randn(n_dst, C, generator=g).to(dt)
+    e_proj = (a @ w_e.t() + b_e).to(dt)
+    sh = lambda t, n: t.float().view(n, H, Ch)
+    ref = R.gt_attention(sh(q, n_dst), sh(k, n_src), sh(v, n_src), sh(e_proj, E), ei, n_dst).view(n_dst, C)
+    csr = ops.build_csr(ei.cuda(), n_src, n_dst)
+    out1 = ops.gt_attention(q.cuda(), k.cuda(), v.cuda(), csr, H, e_proj=e_proj.cuda())
+    a_pad = torch.zeros(E, 12)
+    a_pad[:, :d_e] = a
+    out2 = ops.gt_attention(q.cuda(), k.cuda(), v.cuda(), csr, H, edge_attr=a_pad.cuda(), w_edge=w_e.cuda(), b_edge=b_e.cuda(), add=add.cuda())
+    tol = 1e-4 if dt == torch.float32 else 2**-6 * ref.abs().max().item()
+    assert (out1.float().cpu() - ref).abs().max().item() <= tol
+    # fused form: e_proj is never rounded to bf16, so compare against the fp32-e reference for bf16 too
+    ref2 = R.gt_attention(sh(q, n_dst), sh(k, n_src), sh(v, n_src), (a @ w_e.t() + b_e).view(E, H, Ch), ei, n_dst).view(n_dst, C) + add.float()
+    assert (out2.float().cpu() - ref2).abs().max().item() <= (2e-4 if dt == torch.float32 else 2**-6 * ref2.abs().max().item())
+    assert torch.equal(out2[-3:].float().cpu(), add[-3:].float())  # zero in-degree rows: exactly 0 + add
+
+
+def test_gt_attention_strided_qkv(ops):
+    """q|k|v|self as column slices of one [N, 4C] buffer (the block layout)."""
+    g = torch.Generator().manual_seed(9)
+    N, E, H, Ch = 400, 3000, 16, 32
+    C = H * Ch
+    ei = _rand_graph(N, N, E, 21)
+    buf = torch.randn(N, 4 * C, generator=g).to(torch.bfloat16).cuda()
+    a_pad = torch.randn(E, 12, generator=g)
+    a_pad[:, 11] = 0
+    w_e, b_e = torch.randn(C, 11, generator=g) / 3, torch.randn(C, generator=g)
+    csr = ops.build_csr(ei.cuda(), N, N)
+    out = ops.gt_attention(buf[:, :C], buf[:, C : 2 * C], buf[:, 2 * C : 3 * C], csr, H, edge_attr=a_pad.cuda(), w_edge=w_e.cuda(), b_edge=b_e.cuda(),
+                           add=buf[:, 3 * C :])  # fmt: skip
+    b = buf.float().cpu()
+    sh = lambda t: t.reshape(-1, H, Ch)
+    ref = R.gt_attention(sh(b[:, :C]), sh(b[:, C : 2 * C]), sh(b[:, 2 * C : 3 * C]), sh(a_pad[:, :11] @ w_e.t() + b_e), ei, N).view(N, C) + b[:, 3 * C :]
+    assert (out.float().cpu() - ref).abs().max().item() <= 2**-6 * ref.abs().max().item()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C", [32, 64, 512, 1024, 100])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_graphconv_ln_aggregate(ops, C, dt):
+    g = torch.Generator().manual_seed(C)
+    n_src, n_dst, E = 200, 150, 1300
+    ei = _rand_graph(n_src, n_dst, E, 5, zero_tail=4)
+    h = (torch.randn(E, C, generator=g) * 1.5).to(dt)
+    e = torch.randn(E, C, generator=g).to(dt)
+    w, b = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    csr = ops.build_csr(ei.cuda(), n_src, n_dst)
+    e_new, out = ops.graphconv_ln_aggregate(h.cuda(), w.cuda(), b.cuda(), e.cuda(), csr)
+    ref_e = (torch.nn.functional.layer_norm(h.float(), (C,), w, b, 1e-5) + e.float()).to(dt).float()
+    ref_out = R.scatter_sum(ref_e, ei[1], n_dst)
+    tol = 2e-5 if dt == torch.float32 else 2**-7
+    torch.testing.assert_close(e_new.float().cpu(), ref_e, atol=4 * tol, rtol=2 * tol)
+    torch.testing.assert_close(out.float().cpu(), ref_out, atol=16 * tol * (1 if dt == torch.float32 else 4), rtol=2 * tol)
+    assert torch.all(out[-4:] == 0)
+
+
+def test_cast_pad(ops):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(100, 13, generator=g)
+    idx = torch.randint(0, 100, (37,), generator=g, dtype=torch.int32)
+    y = ops.cast_pad(x.cuda(), torch.bfloat16, 16, idx=idx.cuda())
+    ref = torch.zeros(37, 16)
+    ref[:, :13] = x[idx.long()]
+    assert torch.equal(y.float().cpu(), ref.to(torch.bfloat16).float())
+
+
+def test_cpu_tensor_is_an_error(ops):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.layer_norm(torch.randn(4, 8), None, None)

@@ -1,0 +1,116 @@
+"""CPU tests of the host-side mirror: integer path vs the reference goldens (bit-exact), state_dict compatibility with
+the reference modules, constructor validation, layer_kernels plugin resolution, and the no-CPU-fallback contract."""
+import pytest
+import torch
+
+from anemoi_core_b200.distributed import khop_edges as K
+from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_range
+from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
+from anemoi_core_b200.distributed.shapes import BipartiteGraphShardInfo
+from anemoi_core_b200.distributed.shapes import GraphShardInfo
+from anemoi_core_b200.layers import GNNBackwardMapper
+from anemoi_core_b200.layers import GNNForwardMapper
+from anemoi_core_b200.layers import GNNProcessor
+from anemoi_core_b200.layers import GraphTransformerBackwardMapper
+from anemoi_core_b200.layers import GraphTransformerForwardMapper
+from anemoi_core_b200.layers import GraphTransformerProcessor
+from anemoi_core_b200.layers.utils import compute_mlp_hidden_dim
+from anemoi_core_b200.layers.utils import load_layer_kernels
+
+
+def test_balanced_partition():
+    # reference semantics: first `rem` parts get one extra (balanced_partition.py:16-41)
+    assert get_balanced_partition_sizes(10, 3) == [4, 3, 3]
+    assert get_balanced_partition_sizes(3, 5) == [1, 1, 1, 0, 0]
+    assert get_balanced_partition_sizes(0, 2) == [0, 0]
+    assert sum(get_balanced_partition_sizes(40962, 8)) == 40962
+    assert get_balanced_partition_range(10, 3, 1) == (4, 7)
+    with pytest.raises(ValueError):
+        get_balanced_partition_sizes(4, 0)
+
+
+def test_integer_path_matches_reference_goldens(golden):
+    for c in golden("integer_path")["cases"]:
+        ei, nn = c["edge_index"], c["num_nodes"]
+        s, perm = K.sort_edge_index_by_dst(ei)
+        assert torch.equal(s, c["sorted"]) and torch.equal(perm, c["perm"])
+        assert K.is_edge_index_dst_sorted(s)
+        for parts, p in c["partitions"].items():
+            gp = K.build_graph_partition(s, parts, nn)
+            assert list(gp.dst_splits) == p["dst_splits"] and list(gp.edge_splits) == p["edge_splits"]
+            for cid, m in enumerate(p["chunks"]):
+                (d0, d1), (e0, e1), connected, local = gp.materialise(cid, s)
+                assert torch.equal(torch.arange(d0, d1), m["dst_ids"]) and torch.equal(torch.arange(e0, e1), m["edge_ids"])
+                assert torch.equal(connected, m["src_ids"]) and torch.equal(local, m["edge_index"])
+
+
+def test_ensure_sorted_permutes_attributes_with_edges():
+    ei = torch.tensor([[0, 1, 2, 3], [3, 1, 2, 1]])
+    ea = torch.arange(4.0).view(4, 1)
+    ea2, ei2 = K.ensure_edges_are_dst_sorted(ea, ei, edges_are_dst_sorted=False)
+    assert ei2.tolist() == [[1, 3, 2, 0], [1, 1, 2, 3]] and ea2.view(-1).tolist() == [1.0, 3.0, 2.0, 0.0]
+    ea3, ei3 = K.ensure_edges_are_dst_sorted(ea, ei, edges_are_dst_sorted=True)
+    assert ea3 is ea and ei3 is ei
+
+
+CASES = [
+    ("gnn_processor_small", GNNProcessor, dict(num_chunks=1, mlp_extra_layers=0)),
+    ("gt_processor_small", GraphTransformerProcessor, dict(num_chunks=1, mlp_hidden_ratio=4)),
+    ("gt_processor_qknorm", GraphTransformerProcessor, dict(num_chunks=1, mlp_hidden_ratio=4)),
+    ("gnn_forward_mapper", GNNForwardMapper, dict(num_chunks=1, mlp_extra_layers=0)),
+    ("gnn_backward_mapper", GNNBackwardMapper, dict(num_chunks=1, mlp_extra_layers=0)),
+    ("gt_forward_mapper_chunks4", GraphTransformerForwardMapper, dict(mlp_hidden_ratio=4)),
+    ("gt_backward_mapper", GraphTransformerBackwardMapper, dict(mlp_hidden_ratio=4)),
+]
+
+
+@pytest.mark.parametrize("name,cls,extra", CASES)
+def test_reference_state_dicts_load_strictly(golden, name, cls, extra):
+    """Parameter names/shapes are part of the drop-in surface (inference checkpoints pickle modules)."""
+    g = golden(name)
+    m = cls(**g["cfg"], **extra)
+    res = m.load_state_dict(g["sd"], strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert set(m.state_dict().keys()) == set(g["sd"].keys())
+
+
+def test_constructor_validation_like_the_reference():
+    with pytest.raises(AssertionError, match="divisible"):
+        GNNProcessor(num_channels=8, num_layers=3, num_chunks=2, mlp_extra_layers=0, edge_dim=3)
+    with pytest.raises(ValueError, match="divisible by num_heads"):
+        GraphTransformerProcessor(num_layers=1, num_channels=30, num_chunks=1, num_heads=4, mlp_hidden_ratio=4, edge_dim=3)
+    with pytest.raises(AssertionError, match="out_channels_dst"):
+        GraphTransformerForwardMapper(in_channels_src=4, in_channels_dst=4, hidden_dim=8, out_channels_dst=3, num_heads=2, mlp_hidden_ratio=2,
+                                      edge_dim=3)  # fmt: skip
+    # tolerated extra YAML keys (gnn.yaml:22-32)
+    GNNProcessor(num_channels=8, num_layers=2, num_chunks=1, mlp_extra_layers=0, edge_dim=3, trainable_size=8, sub_graph_edge_attributes=["a"],
+                 gradient_checkpointing=False)  # fmt: skip
+    assert compute_mlp_hidden_dim(10, 0.25) == 3
+    with pytest.raises(ValueError):
+        compute_mlp_hidden_dim(10, 0)
+
+
+def test_layer_kernels_plugin_hook():
+    k = load_layer_kernels({"LayerNorm": {"_target_": "anemoi.models.layers.normalization.AutocastLayerNorm"},
+                            "Linear": {"_target_": "torch.nn.Linear", "_partial_": True}})  # fmt: skip
+    from anemoi_core_b200.layers.normalization import AutocastLayerNorm
+
+    assert isinstance(k.LayerNorm(normalized_shape=8), AutocastLayerNorm)
+    assert isinstance(k.Linear(4, 4), torch.nn.Linear)
+    assert isinstance(k.Activation(), torch.nn.GELU)
+    with pytest.raises(ImportError):
+        load_layer_kernels({"Linear": {"_target_": "no.such.module.Linear"}})
+    m = GNNProcessor(num_channels=8, num_layers=1, num_chunks=1, mlp_extra_layers=0, edge_dim=3,
+                     layer_kernels={"LayerNorm": {"_target_": "anemoi.models.layers.normalization.AutocastLayerNorm"}})  # fmt: skip
+    assert isinstance(m.proc[0].node_mlp.layer_norm, AutocastLayerNorm)
+
+
+def test_no_cpu_fallback_and_forward_only():
+    m = GNNProcessor(num_channels=8, num_layers=1, num_chunks=1, mlp_extra_layers=0, edge_dim=3).eval()
+    ei = torch.tensor([[0, 1], [0, 1]])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(2, 8), 1, GraphShardInfo(nodes=[2]), torch.randn(2, 3), ei)
+    m.train()
+    with pytest.raises(NotImplementedError, match="forward pass only"):
+        m(torch.randn(2, 8), 1, GraphShardInfo(nodes=[2]), torch.randn(2, 3), ei)
+    assert BipartiteGraphShardInfo().edges_are_sharded() is False and GraphShardInfo(nodes=[1]).nodes_are_sharded()

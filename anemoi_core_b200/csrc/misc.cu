@@ -65,6 +65,15 @@ __global__ void cast_pad_kernel(const TI* __restrict__ in, int64_t ldi, const in
   }
 }
 
+__global__ void add_kernel(const void* __restrict__ a, int64_t lda, int adt, const void* __restrict__ b, int64_t ldb, int bdt, void* __restrict__ out,
+                           int64_t ldo, int odt, int64_t M, int64_t C) {
+  const int64_t total = M * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / C, c = i - m * C;
+    store_from_f32(out, m * ldo + c, odt, load_as_f32(a, m * lda + c, adt) + load_as_f32(b, m * ldb + c, bdt));
+  }
+}
+
 }  // namespace anemoi
 
 using namespace anemoi;
@@ -111,4 +120,16 @@ extern "C" int anemoi_b200_cast_pad(const void* in, int64_t ldi, int i_dtype, co
   }
 #undef LAUNCH
   return launch_status("cast_pad_kernel");
+}
+
+extern "C" int anemoi_b200_add(const void* a, int64_t lda, int a_dtype, const void* b, int64_t ldb, int b_dtype, void* out, int64_t ldo,
+                               int o_dtype, int64_t M, int64_t C, void* stream) {
+  ANEMOI_CHECK_ARG(M >= 0 && C >= 0 && lda >= C && ldb >= C && ldo >= C, "add: bad shape");
+  ANEMOI_CHECK_ARG((a_dtype | 1) == 1 && (b_dtype | 1) == 1 && (o_dtype | 1) == 1, "add: bad dtype");
+  if (M == 0 || C == 0) return 0;
+  ANEMOI_CHECK_ARG(a && b && out, "add: null pointer");
+  int64_t blocks = (M * C + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+  add_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, lda, a_dtype, b, ldb, b_dtype, out, ldo, o_dtype, M, C);
+  return launch_status("add_kernel");
 }

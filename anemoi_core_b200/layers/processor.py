@@ -56,13 +56,29 @@ class BaseProcessor(nn.Module):
         self.proc = nn.ModuleList([layer_class(**layer_kwargs) for _ in range(self.num_layers)])
 
 
-def _shard_edges_by_dst(edge_attr: Tensor, edge_index: Tensor, n_dst: int, n_src: int, group) -> tuple[Tensor, Tensor, list[int]]:
+_SHARD_CACHE: dict = {}
+
+
+def _shard_edges_by_dst(edge_attr: Tensor, edge_index: Tensor, n_dst: int, n_src: int, group, relabel_dst: bool = False):
     """Keep the edges into this rank's balanced dst range (reference ``shard_edges_1hop``, khop_edges.py:266-314).
-    Indices stay global.  Returns (edge_attr, edge_index, per-rank edge counts)."""
-    world = group_size(group)
-    part = build_graph_partition(edge_index, world, (n_src, n_dst))
-    e0, e1 = part.edge_range(group_rank(group))
-    return edge_attr[e0:e1], edge_index[:, e0:e1], list(part.edge_splits)
+    src ids stay global; dst ids stay global (GNN: the aggregate is computed over the full index range, block.py:375-391)
+    or are relabelled to the local range (GraphTransformer).  The split is computed once per (graph, group) and cached.
+    Returns (edge_attr view, edge_index, per-rank edge counts)."""
+    world, rank = group_size(group), group_rank(group)
+    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), str(edge_index.device), n_dst, n_src, world, rank, relabel_dst)
+    hit = _SHARD_CACHE.get(key)
+    if hit is None:
+        part = build_graph_partition(edge_index, world, (n_src, n_dst))
+        e0, e1 = part.edge_range(rank)
+        local = edge_index[:, e0:e1].clone()
+        if relabel_dst:
+            local[1] -= part.dst_range(rank)[0]
+        hit = (edge_index, e0, e1, local.contiguous(), list(part.edge_splits))
+        if len(_SHARD_CACHE) > 16:
+            _SHARD_CACHE.clear()
+        _SHARD_CACHE[key] = hit
+    _, e0, e1, local, edge_sizes = hit
+    return edge_attr[e0:e1], local, edge_sizes
 
 
 class GNNProcessor(BaseProcessor):
@@ -181,12 +197,11 @@ class GraphTransformerProcessor(BaseProcessor):
         if not shard_info.edges_are_sharded():
             edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
             if group_size(model_comm_group) > 1:
-                edge_attr, edge_index, edge_sizes = _shard_edges_by_dst(edge_attr, edge_index, n_nodes, n_nodes, model_comm_group)
+                # local dst rows only: dst relabelled to the local range (src ids stay global, sources are all-gathered per layer)
+                edge_attr, edge_index, edge_sizes = _shard_edges_by_dst(edge_attr, edge_index, n_nodes, n_nodes, model_comm_group, relabel_dst=True)
                 shard_info = GraphShardInfo(nodes=shard_info.nodes, edges=edge_sizes)
-        if group_size(model_comm_group) > 1:
-            # local dst rows only: relabel dst to the local range (src ids stay global, sources are all-gathered per layer)
-            start = sum(shard_info.nodes[: group_rank(model_comm_group)])
-            edge_index = torch.stack([edge_index[0], edge_index[1] - start])
+        elif group_size(model_comm_group) > 1:
+            raise NotImplementedError("pre-sharded edges: pass the full dst-sorted edge list and let the processor shard it (cached)")
         shared_edges = None
         if all(isinstance(b.edge_pre_mlp, nn.Identity) for b in self.proc):
             shared_edges = self.proc[0].prepare_edges(edge_attr)  # one padded fp32 copy for all layers

@@ -16,7 +16,50 @@ from ._lib import BF16
 from ._lib import EPI_GELU
 from ._lib import F32
 
-__all__ = ["GraphCSR", "build_csr", "layer_norm", "linear", "gt_attention", "graphconv_ln_aggregate", "cast_pad", "dtype_code"]
+__all__ = ["GraphCSR", "build_csr", "layer_norm", "linear", "gt_attention", "graphconv_ln_aggregate", "cast_pad", "add", "dtype_code"]
+
+
+# ---- instrumentation: launch counter and optional CUDA-event timing of every C-ABI call (bench.py roofline leg) -------
+LAUNCHES = 0  # kernels launched through the C ABI since import (each entry point launches exactly one kernel)
+_TIMER = None  # None or a list collecting (name, start_event, end_event, flops, bytes)
+
+
+def start_timing() -> list:
+    global _TIMER
+    _TIMER = []
+    return _TIMER
+
+
+def stop_timing() -> list:
+    global _TIMER
+    rec, _TIMER = _TIMER, None
+    return rec or []
+
+
+class _Timed:
+    __slots__ = ("name", "flops", "bytes", "ev")
+
+    def __init__(self, name: str, flops: float = 0.0, nbytes: float = 0.0):
+        self.name, self.flops, self.bytes, self.ev = name, flops, nbytes, None
+
+    def __enter__(self):
+        global LAUNCHES
+        LAUNCHES += 1
+        if _TIMER is not None:
+            self.ev = torch.cuda.Event(enable_timing=True)
+            self.ev.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            _TIMER.append((self.name, self.ev, end, self.flops, self.bytes))
+        return False
+
+
+def _nbytes(*ts: Optional[Tensor]) -> float:
+    return float(sum(t.shape[0] * t.shape[1] * t.element_size() if t.dim() == 2 else t.numel() * t.element_size() for t in ts if t is not None))
 
 
 def dtype_code(dt: torch.dtype) -> int:
@@ -98,9 +141,10 @@ def build_csr(edge_index: Tensor, n_src: int, n_dst: int, validate: bool = True)
     dst32 = torch.empty(n_edges, dtype=torch.int32, device=dev)
     status = torch.empty(1, dtype=torch.int32, device=dev)
     lib = _lib.load()
-    rc = lib.anemoi_b200_csr_build(
-        _ptr(edge_index), n_edges, n_src, n_dst, _ptr(colptr), _ptr(colptr32), _ptr(src32), _ptr(dst32), _ptr(status), _stream()
-    )
+    with _Timed("csr_build", 0.0, 24.0 * n_edges + 12.0 * n_dst):
+        rc = lib.anemoi_b200_csr_build(
+            _ptr(edge_index), n_edges, n_src, n_dst, _ptr(colptr), _ptr(colptr32), _ptr(src32), _ptr(dst32), _ptr(status), _stream()
+        )
     _lib.check(rc, "anemoi_b200_csr_build")
     if validate:
         st = int(status.item())
@@ -144,9 +188,10 @@ def layer_norm(
     for p in (weight, bias):
         if p is not None and p.numel() != C:
             raise ValueError("LayerNorm parameter size mismatch")
-    rc = _lib.load().anemoi_b200_layer_norm(
-        _ptr(x), ldx, dtype_code(x.dtype), _ptr(_f32(weight)), _ptr(_f32(bias)), _ptr(residual), ldr, rdt, _ptr(out), ldy,
-        dtype_code(out.dtype), M, groups, C, float(eps), _stream())  # fmt: skip
+    with _Timed("layer_norm", 8.0 * M * W, _nbytes(x, residual, out)):
+        rc = _lib.load().anemoi_b200_layer_norm(
+            _ptr(x), ldx, dtype_code(x.dtype), _ptr(_f32(weight)), _ptr(_f32(bias)), _ptr(residual), ldr, rdt, _ptr(out), ldy,
+            dtype_code(out.dtype), M, groups, C, float(eps), _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_layer_norm")
     return out
 
@@ -204,9 +249,12 @@ def linear(
             g2, i2 = tab, idx
     if g1 is None and g2 is not None:
         g1, i1, g2, i2 = g2, i2, None, None
-    rc = _lib.load().anemoi_b200_linear(
-        _ptr(a), lda, _ptr(weight), ldw, dtype_code(a.dtype), _ptr(_f32(bias)), _ptr(g1), _ptr(i1), _ptr(g2), _ptr(i2), ldg, _ptr(residual),
-        ldr, rdt, _ptr(out), ldo, dtype_code(out.dtype), M, N, K, EPI_GELU if gelu else 0, _stream())  # fmt: skip
+    tc = a.dtype == torch.bfloat16 and K >= 64 and lda % 8 == 0 and ldw % 8 == 0 and a.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0
+    gbytes = (4.0 * M * N if g1 is not None else 0.0) + (4.0 * M * N if g2 is not None else 0.0)
+    with _Timed("linear_tcgen05" if tc else "linear_ffma", 2.0 * M * N * K, _nbytes(a, weight, residual, out) + gbytes):
+        rc = _lib.load().anemoi_b200_linear(
+            _ptr(a), lda, _ptr(weight), ldw, dtype_code(a.dtype), _ptr(_f32(bias)), _ptr(g1), _ptr(i1), _ptr(g2), _ptr(i2), ldg, _ptr(residual),
+            ldr, rdt, _ptr(out), ldo, dtype_code(out.dtype), M, N, K, EPI_GELU if gelu else 0, _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_linear")
     return out
 
@@ -258,9 +306,14 @@ def gt_attention(
         na, Ca, ldadd = _rows(add)
         if (na, Ca) != (n_dst, C) or add.dtype != q.dtype:
             raise ValueError("gt_attention: add mismatch")
-    rc = _lib.load().anemoi_b200_gt_attention_fwd(
-        _ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(e_proj), lde_proj, _ptr(edge_attr), lde, d_e, _ptr(w_edge), ldw_e, _ptr(_f32(b_edge)),
-        _ptr(csr.src32), _ptr(csr.colptr32), _ptr(add), ldadd, _ptr(out), ldo, n_dst, heads, C // heads, dtype_code(q.dtype), _stream())  # fmt: skip
+    # algorithmic bytes: q, k, v, add read once + out written once + per-edge index/attributes (or e_proj)
+    es = q.element_size()
+    abytes = es * C * (2.0 * n_dst + 2.0 * n_src + (n_dst if add is not None else 0)) + csr.n_edges * (4.0 + 4.0 * lde + (es * C if e_proj is not None else 0)) + 4.0 * n_dst
+    aflops = csr.n_edges * (4.0 * C + 4.0 * d_e * heads) + n_dst * 4.0 * d_e * C
+    with _Timed("gt_attention", aflops, abytes):
+        rc = _lib.load().anemoi_b200_gt_attention_fwd(
+            _ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(e_proj), lde_proj, _ptr(edge_attr), lde, d_e, _ptr(w_edge), ldw_e, _ptr(_f32(b_edge)),
+            _ptr(csr.src32), _ptr(csr.colptr32), _ptr(add), ldadd, _ptr(out), ldo, n_dst, heads, C // heads, dtype_code(q.dtype), _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_gt_attention_fwd")
     return out
 
@@ -280,9 +333,10 @@ def graphconv_ln_aggregate(
     no, Co, ldo = _rows(out)
     if (no, Co) != (csr.n_dst, C) or out.dtype != h.dtype:
         raise ValueError("graphconv_ln_aggregate: output mismatch")
-    rc = _lib.load().anemoi_b200_graphconv_ln_aggregate(
-        _ptr(h), ldh, _ptr(_f32(weight)), _ptr(_f32(bias)), _ptr(e), lde, _ptr(e_new), C, _ptr(csr.colptr32), _ptr(out), ldo, csr.n_dst, C,
-        float(eps), dtype_code(h.dtype), _stream())  # fmt: skip
+    with _Timed("graphconv_ln_aggregate", 10.0 * E * C, _nbytes(h, e, e_new, out) + 4.0 * csr.n_dst):
+        rc = _lib.load().anemoi_b200_graphconv_ln_aggregate(
+            _ptr(h), ldh, _ptr(_f32(weight)), _ptr(_f32(bias)), _ptr(e), lde, _ptr(e_new), C, _ptr(csr.colptr32), _ptr(out), ldo, csr.n_dst, C,
+            float(eps), dtype_code(h.dtype), _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_graphconv_ln_aggregate")
     return e_new, out
 
@@ -301,6 +355,21 @@ def cast_pad(x: Tensor, dtype: torch.dtype, k_pad: Optional[int] = None, idx: Op
     Mo, Ko, ldo = _rows(out)
     if Mo != M or Ko < k_pad:
         raise ValueError("cast_pad: output mismatch")
-    rc = _lib.load().anemoi_b200_cast_pad(_ptr(x), ldi, dtype_code(x.dtype), _ptr(idx), _ptr(out), ldo, dtype_code(out.dtype), M, K, k_pad, _stream())
+    with _Timed("cast_pad", 0.0, float(M) * (K * x.element_size() + k_pad * out.element_size())):
+        rc = _lib.load().anemoi_b200_cast_pad(_ptr(x), ldi, dtype_code(x.dtype), _ptr(idx), _ptr(out), ldo, dtype_code(out.dtype), M, K, k_pad, _stream())
     _lib.check(rc, "anemoi_b200_cast_pad")
+    return out
+
+
+def add(a: Tensor, b: Tensor, out_dtype: Optional[torch.dtype] = None) -> Tensor:
+    """a + b (fp32 add, any mix of f32/bf16 operands) — the latent skip around the processor."""
+    _need_cuda(a, b)
+    M, C, lda = _rows(a)
+    Mb, Cb, ldb = _rows(b)
+    if (M, C) != (Mb, Cb):
+        raise ValueError("add: shape mismatch")
+    out = torch.empty((M, C), dtype=out_dtype or a.dtype, device=a.device)
+    with _Timed("add", float(M) * C, _nbytes(a, b, out)):
+        rc = _lib.load().anemoi_b200_add(_ptr(a), lda, dtype_code(a.dtype), _ptr(b), ldb, dtype_code(b.dtype), _ptr(out), C, dtype_code(out.dtype), M, C, _stream())
+    _lib.check(rc, "anemoi_b200_add")
     return out

@@ -1,0 +1,383 @@
+"""bench.py — forward ms/step of the graph message-passing hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|small]
+
+Workload (default cfg2 = BASELINE.json configs[1]): O96 grid (40 320 points) -> icosahedral level-6 multi-scale mesh
+(40 962 nodes, 327 600 edges), GraphTransformer encoder + 16 x 512 processor (16 heads) + decoder, bf16 autocast,
+batch 1, synthetic inputs N(0,1), PyTorch-default random-init weights (seed 1234).  One "step" = encoder -> processor ->
+latent skip -> decoder (models/encoder_processor_decoder.py:260-324).
+
+Printed JSON (one line, rank 0):
+  value / ms_per_step : device-resident step (inputs already in HBM), whole step replayed as one CUDA graph, CUDA events
+                        per step, L2 flushed between timed steps, max over ranks.
+  e2e                 : same step through the public module API with HOST (pinned) input buffers: H2D of the inputs,
+                        the step, D2H of the output, all inside the timed region.
+  roofline            : dominant kernel class measured live with CUDA events around every C-ABI launch (eager pass).
+  cpu_baseline        : the oracle port (oracle/restatement.py, fp32, all host threads) on a bounded sample, rank 0, N=1.
+  --impl reference    : the reference's CPU path (oracle port: the Python reference cannot travel to the GPU box).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (grid, mesh level, kind, channels, layers, heads, in_grid, in_mesh, out_grid)
+    "cfg2": dict(grid="o96", mesh_level=6, kind="graphtransformer", C=512, layers=16, heads=16, in_grid=212, in_mesh=12, out_grid=88,
+                 desc="O96 grid (40320 pts) -> ico-6 multi-scale mesh (40962 nodes, 327600 edges), GraphTransformer enc + 16x512 proc (16 heads) + dec"),
+    "cfg3": dict(grid="n320", mesh_level=6, kind="gnn", C=1024, layers=16, heads=16, in_grid=212, in_mesh=12, out_grid=88,
+                 desc="N320 grid (542080 pts) -> ico-6 mesh, GNN enc + 16x1024 proc + dec"),
+    "small": dict(grid="o32", mesh_level=4, kind="graphtransformer", C=512, layers=4, heads=16, in_grid=212, in_mesh=12, out_grid=88,
+                  desc="O32 grid -> ico-4 mesh, GraphTransformer 4x512 (smoke-size)"),
+}  # fmt: skip
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tensor": d["bf16_tflops_sustained"], "tensor_burst": d["bf16_tflops"], "src": "measured"}
+    return {"hbm": 6650.0, "tensor": 1400.0, "tensor_burst": 1590.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")  # fmt: skip
+
+    def __init__(self, device_index: int):
+        self.idx, self.proc, self.lines = device_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if mx and x > 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(w, gr, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(gr["n_grid"], w["in_grid"], generator=g), torch.randn(gr["n_mesh"], w["in_mesh"], generator=g)
+
+
+def build_model(w, gr):
+    from anemoi_core_b200.model import EncProcDec
+
+    torch.manual_seed(1234)
+    return EncProcDec(w["kind"], in_grid=w["in_grid"], in_mesh=w["in_mesh"], out_grid=w["out_grid"], num_channels=w["C"], num_layers=w["layers"],
+                      edge_dim=gr["edge_dim"], num_heads=w["heads"]).eval()  # fmt: skip
+
+
+def state_dicts(model):
+    return {k: {n: p.detach().clone() for n, p in getattr(model, k).state_dict().items()} for k in ("encoder", "processor", "decoder")}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU reference leg (oracle port)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(w, gr, sds, x_grid, x_mesh, sample_layers):
+    """One bounded CPU sample: encoder + `sample_layers` processor layers + decoder (fp32).  Returns (t_enc, t_layers, t_dec) seconds."""
+    from oracle import restatement as R
+
+    H, L = w["heads"], w["layers"]
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        if w["kind"] == "graphtransformer":
+            _, lat = R.gt_forward_mapper(sds["encoder"], x_grid, x_mesh, gr["enc_attr"], gr["enc_index"], H)
+            t1 = time.perf_counter()
+            proc = R.gt_processor(sds["processor"], lat, gr["proc_attr"], gr["proc_index"], L, H, max_layers=sample_layers)
+            t2 = time.perf_counter()
+            R.gt_backward_mapper(sds["decoder"], proc + lat, x_grid, gr["dec_attr"], gr["dec_index"], H)
+        else:
+            src_emb, lat = R.gnn_forward_mapper(sds["encoder"], x_grid, x_mesh, gr["enc_attr"], gr["enc_index"])
+            t1 = time.perf_counter()
+            proc = R.gnn_processor(sds["processor"], lat, gr["proc_attr"], gr["proc_index"], L, max_layers=sample_layers)
+            t2 = time.perf_counter()
+            R.gnn_backward_mapper(sds["decoder"], proc + lat, src_emb, gr["dec_attr"], gr["dec_index"])
+        t3 = time.perf_counter()
+    return t1 - t0, t2 - t1, t3 - t2
+
+
+def cpu_baseline(w, gr, sds, x_grid, x_mesh, repeats=1, sample_layers=2):
+    torch.set_num_threads(os.cpu_count() or 1)
+    best = None
+    for _ in range(repeats + 1):  # first pass is the warm-up
+        te, tl, td = cpu_reference_step(w, gr, sds, x_grid, x_mesh, sample_layers)
+        best = (te, tl, td)
+    te, tl, td = best
+    full = te + td + tl * w["layers"] / sample_layers
+    return {
+        "value": full * 1e3,
+        "unit": "ms/step",
+        "cores": torch.get_num_threads(),
+        "kind": "port",
+        "sample": f"oracle/restatement.py fp32 on CPU: encoder {te:.2f}s + {sample_layers} of {w['layers']} processor layers {tl:.2f}s + decoder {td:.2f}s; "
+                  f"processor scaled x{w['layers'] / sample_layers:g} (layers are identical)",
+    }  # fmt: skip
+
+
+def run_reference(args, w):
+    """--impl reference: the reference's CPU path (oracle port, all host threads), K bounded samples."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from anemoi_core_b200.synthetic import build_graph
+
+    gr = build_graph(w["grid"], w["mesh_level"])
+    model = build_model(w, gr)
+    sds = state_dicts(model)
+    x_grid, x_mesh = make_inputs(w, gr)
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample_layers = 1
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(w, gr, sds, x_grid, x_mesh, sample_layers)
+    vals = []
+    t_budget = time.perf_counter()
+    for _ in range(args.steps):
+        te, tl, td = cpu_reference_step(w, gr, sds, x_grid, x_mesh, sample_layers)
+        vals.append((te + td + tl * w["layers"] / sample_layers) * 1e3)
+        if time.perf_counter() - t_budget > 150.0:  # keep the arm within a few minutes whatever K is
+            break
+    ms = statistics.mean(vals)
+    line = {
+        "impl": "reference", "metric": "forward ms/step", "value": ms, "unit": "ms/step", "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": f"{args.workload}: {w['desc']}", "batch": 1, "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": ms, "unit": "ms/step", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"per step: encoder + {sample_layers} of {w['layers']} processor layers + decoder on CPU (oracle port of the "
+                                   f"reference PyTorch path), processor time scaled x{w['layers'] / sample_layers:g}; {len(vals)} samples"},
+        "e2e": {"value": ms, "unit": "ms/step", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }  # fmt: skip
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+    args.warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    from anemoi_core_b200 import ops
+    from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
+    from anemoi_core_b200.synthetic import build_graph
+
+    gr = build_graph(w["grid"], w["mesh_level"])
+    model = build_model(w, gr)
+    sds = state_dicts(model) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    model = model.to(dev)
+    gd = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in gr.items()}
+    x_grid_h, x_mesh_h = make_inputs(w, gr)
+    x_grid_h, x_mesh_h = x_grid_h.pin_memory(), x_mesh_h.pin_memory()
+    x_grid, x_mesh = x_grid_h.to(dev), x_mesh_h.to(dev)
+    mesh_shards = get_balanced_partition_sizes(gr["n_mesh"], world) if world > 1 else None
+
+    def step(xg, xm):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            return model(xg, xm, gd, group, mesh_shards)
+
+    # ---- warm-up (also builds CSR plans, packed weights, TMA descriptors) and launch count per step --------------------
+    for _ in range(2):
+        out = step(x_grid, x_mesh)
+    torch.cuda.synchronize()
+    n0 = ops.LAUNCHES
+    out = step(x_grid, x_mesh)
+    launches_per_step = ops.LAUNCHES - n0
+    torch.cuda.synchronize()
+
+    use_graph = not args.no_graph and world == 1
+    if use_graph:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            replay = model.capture(x_grid, x_mesh, gd)
+        run = lambda: replay()  # noqa: E731
+    else:
+        run = lambda: step(x_grid, x_mesh)  # noqa: E731
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_()  # L2 flush between timed iterations, outside the event pair
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = [a.elapsed_time(b) for a, b in evs]
+        return sum(ms) / len(ms), wall
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms_dev, wall_dev = timed(run, args.steps, args.warmup)
+
+    # ---- e2e: host buffers in, host buffer out ----------------------------------------------------------------------------
+    out_h = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+
+    if use_graph:
+
+        def e2e_step():
+            o = replay(x_grid_h, x_mesh_h)  # H2D into the graph's static inputs, replay
+            out_h.copy_(o, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    else:
+
+        def e2e_step():
+            o = step(x_grid_h.to(dev, non_blocking=True), x_mesh_h.to(dev, non_blocking=True))
+            out_h.copy_(o, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    ms_e2e, _ = timed(e2e_step, args.steps, 3)
+    clk = clocks.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_dev, ms_e2e = t.tolist()
+
+    # ---- roofline leg: CUDA events around every C-ABI launch, eager, over 3 steps -------------------------------------------
+    pk = peaks()
+    for _ in range(2):
+        step(x_grid, x_mesh)
+    torch.cuda.synchronize()
+    ops.start_timing()
+    n_prof = 3
+    for _ in range(n_prof):
+        flush.zero_()
+        step(x_grid, x_mesh)
+    torch.cuda.synchronize()
+    rec = ops.stop_timing()
+    agg = {}
+    for name, a, b, fl, by in rec:
+        d = agg.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        d["ms"] += a.elapsed_time(b)
+        d["flops"] += fl
+        d["bytes"] += by
+        d["launches"] += 1
+    total_ms = sum(d["ms"] for d in agg.values()) or 1.0
+    kernels = {}
+    for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        tf = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        gb = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        kernels[name] = {"share": round(d["ms"] / total_ms, 4), "us_per_launch": round(1e3 * d["ms"] / d["launches"], 2),
+                         "launches_per_step": d["launches"] // n_prof, "tflops": round(tf, 2), "gbs": round(gb, 1),
+                         "frac_tensor": round(tf / pk["tensor"], 4), "frac_hbm": round(gb / pk["hbm"], 4)}  # fmt: skip
+    top = next(iter(kernels))
+    topd = agg[top]
+    if top == "linear_tcgen05":
+        ach = topd["flops"] / (topd["ms"] * 1e-3) / 1e12
+        roofline = {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tensor"], "traffic": None, "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
+                    "share_of_step": kernels[top]["share"]}  # fmt: skip
+    else:
+        ach = topd["bytes"] / (topd["ms"] * 1e-3) / 1e9
+        roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
+                    "peak_source": pk["src"], "share_of_step": kernels[top]["share"]}  # fmt: skip
+
+    if rank != 0:
+        torch.distributed.destroy_process_group()
+        return
+    line = {
+        "metric": "forward ms/step", "value": ms_dev, "unit": "ms/step", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "batch": 1, "precision": "bf16 autocast, fp32 accumulate",
+                   "launch": "cuda-graph replay" if use_graph else "eager", "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
+                   "parallelism": "single GPU" if world == 1 else f"processor dst-range sharded over {world} GPUs (all-gather of k|v rows per layer), mappers replicated"},
+        "e2e": {"value": ms_e2e, "unit": "ms/step", "h2d_bytes_per_step": x_grid_h.numel() * 4 + x_mesh_h.numel() * 4,
+                "d2h_bytes_per_step": out_h.numel() * out_h.element_size()},
+        "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step,
+        "clocks": clk,
+        "roofline": roofline,
+        "kernels": kernels,
+        "wall_s_timed_region": wall_dev,
+    }  # fmt: skip
+    if sds is not None:
+        line["cpu_baseline"] = cpu_baseline(w, gr, sds, x_grid_h, x_mesh_h)
+    else:
+        line["cpu_baseline"] = {"value": None, "unit": "ms/step", "cores": 0, "kind": "port", "sample": "timed at N=1 only"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -113,6 +113,11 @@ ANEMOI_API int anemoi_b200_graphconv_ln_aggregate(const void* h, int64_t ldh, co
 ANEMOI_API int anemoi_b200_cast_pad(const void* in, int64_t ldi, int i_dtype, const int32_t* idx, void* out, int64_t ldo, int o_dtype, int64_t M,
                          int64_t K, int64_t Kpad, void* stream);
 
+/* out[m, c] = a[m, c] + b[m, c] — the latent skip connection around the processor
+ * (models/encoder_processor_decoder.py:295-296), any mix of f32 / bf16, fp32 add. */
+ANEMOI_API int anemoi_b200_add(const void* a, int64_t lda, int a_dtype, const void* b, int64_t ldb, int b_dtype, void* out, int64_t ldo,
+                               int o_dtype, int64_t M, int64_t C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

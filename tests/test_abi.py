@@ -17,7 +17,7 @@ def header_symbols():
 def test_header_declares_the_expected_entry_points():
     syms = header_symbols()
     assert {"anemoi_b200_csr_build", "anemoi_b200_layer_norm", "anemoi_b200_linear", "anemoi_b200_gt_attention_fwd",
-            "anemoi_b200_graphconv_ln_aggregate", "anemoi_b200_cast_pad", "anemoi_b200_last_error", "anemoi_b200_abi_version"} <= syms  # fmt: skip
+            "anemoi_b200_graphconv_ln_aggregate", "anemoi_b200_cast_pad", "anemoi_b200_add", "anemoi_b200_last_error", "anemoi_b200_abi_version"} <= syms  # fmt: skip
 
 
 def test_library_exports_every_header_symbol_and_ctypes_table_matches():

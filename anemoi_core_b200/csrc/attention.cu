@@ -25,9 +25,13 @@ struct AttnParams {
   const float* edge_attr;  // [E, lde] fp32
   int64_t lde;
   int edge_dim;
-  const float* w_edge;  // [H*Ch, ldw_e] fp32
+  const float* w_edge;  // [H*Ch, ldw_e] fp32 (generic kernel only)
   int64_t ldw_e;
   const float* b_edge;  // [H*Ch] or null
+  const void* qw;       // [n_dst, ldqw]: per-head W_e^T q (slab kernel, MODE 2)
+  void* abar;           // [n_dst, ldabar]: per-head sum_e alpha_e a_e (slab kernel, MODE 2)
+  int64_t ldqw, ldabar;
+  int dp;               // per-head stride inside qw / abar rows
   const int32_t* src;
   const int32_t* colptr;
   int64_t n_dst;
@@ -35,134 +39,255 @@ struct AttnParams {
   float scale;
 };
 
-// MODE 0: no edge term; 1: materialised eproj; 2: fused lin_edge from raw attributes.
-template <typename T, int VEC, int MODE>
-__global__ void __launch_bounds__(256) gt_attention_warp_kernel(const AttnParams p) {
-  extern __shared__ float s_w[];  // MODE 2: W_e re-laid out as [(j*VEC + c)*32 + lane] (bank-conflict free), then b_e as [c*32+lane]
-  const int lane = threadIdx.x & 31;
-  const int D = p.edge_dim;
-  if constexpr (MODE == 2) {
-    const int C = 32 * VEC;
-    for (int i = threadIdx.x; i < C * D; i += blockDim.x) {
-      const int ch = i / D, j = i - ch * D;
-      s_w[(j * VEC + (ch % VEC)) * 32 + ch / VEC] = p.w_edge[(int64_t)ch * p.ldw_e + j];
+// ---- slab kernel ---------------------------------------------------------------------------------------------
+// Work item = (range of kNodesPerRange consecutive dst nodes, channel slab).  A slab is NCH x 512 bytes of a node row:
+// lane l owns the 16-byte chunks (j*32 + l), j < NCH, so every gathered k / v row segment is read by ONE fully
+// coalesced 512-byte warp load per chunk.  A head spans LPH = Ch / EPC consecutive lanes of a chunk (EPC = elements per
+// 16 bytes); a lane therefore serves NCH heads, one per chunk.
+// Memory-level parallelism (the kernel is latency / L2 bound, not FLOP bound): colptr of the whole range and the src ids
+// of the range's (contiguous) edge run are fetched with coalesced loads ahead of use and handed out by shuffles; the
+// gathers of kBatch = 4 edges (k and v, all chunks) are issued back to back before any arithmetic; q / qw of the next
+// node are prefetched during the current one.
+// MODE 1: materialised eproj (may be null = no edge term).
+// MODE 2: fused lin_edge.  The caller supplies qw[d,h,:] = W_e,h^T q[d,h,:] (folded into the q GEMM) and receives
+//         abar[d,h,:] = sum_e alpha_e a_e (W_e is applied to it inside the projection GEMM); the attribute index space is
+//         split over the LPH lanes of a head (lane o owns attributes o, o+LPH, ...), so the per-edge cost of the edge term
+//         is ceil(D/LPH) loads and 2*ceil(D/LPH) FMAs per lane and rides on the score's shuffle reduction.
+constexpr int kNodesPerRange = 8;
+constexpr int kBatch = 4;
+
+template <typename T>
+struct ChunkT {
+  static constexpr int EPC = 16 / (int)sizeof(T);
+  __device__ static __forceinline__ void unpack(const uint4& u, float (&f)[EPC]) {
+    if constexpr (sizeof(T) == 4) {
+      f[0] = __uint_as_float(u.x), f[1] = __uint_as_float(u.y), f[2] = __uint_as_float(u.z), f[3] = __uint_as_float(u.w);
+    } else {
+      f[0] = __uint_as_float(u.x << 16), f[1] = __uint_as_float(u.x & 0xffff0000u);
+      f[2] = __uint_as_float(u.y << 16), f[3] = __uint_as_float(u.y & 0xffff0000u);
+      f[4] = __uint_as_float(u.z << 16), f[5] = __uint_as_float(u.z & 0xffff0000u);
+      f[6] = __uint_as_float(u.w << 16), f[7] = __uint_as_float(u.w & 0xffff0000u);
     }
-    for (int i = threadIdx.x; i < C; i += blockDim.x) s_w[C * D + (i % VEC) * 32 + i / VEC] = p.b_edge ? p.b_edge[i] : 0.f;
-    __syncthreads();
   }
-  const int lph = p.ch / VEC;  // lanes per head (power of two)
-  const T* __restrict__ qp = reinterpret_cast<const T*>(p.q);
-  const T* __restrict__ kp = reinterpret_cast<const T*>(p.k);
-  const T* __restrict__ vp = reinterpret_cast<const T*>(p.v);
-  const T* __restrict__ ep = reinterpret_cast<const T*>(p.e);
+  __device__ static __forceinline__ uint4 pack(const float (&f)[EPC]) {
+    if constexpr (sizeof(T) == 4) {
+      return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    } else {
+      return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+  }
+};
+
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+template <typename T, int NCH, int LPH, int MODE>
+__global__ void __launch_bounds__(128, 3) gt_attention_slab_kernel(const AttnParams p, int n_slabs, int active_lanes) {
+  using CT = ChunkT<T>;
+  constexpr int EPC = CT::EPC;
+  constexpr int NA = (kMaxEdgeDim + LPH - 1) / LPH;  // attribute slots per lane (upper bound; `na` of them are live)
+  constexpr int SLAB = NCH * 32 * EPC;               // channels per slab
+  const int lane = threadIdx.x & 31;
+  const bool active = lane < active_lanes;  // narrow rows (< 512 bytes): the idle lanes shadow lane 0 and never store
+  const int lane_eff = active ? lane : 0;
+  const int sub = lane & (LPH - 1);
+  const int na = MODE == 2 ? (p.edge_dim + LPH - 1) / LPH : 0;
+  const char* __restrict__ qp = reinterpret_cast<const char*>(p.q);
+  const char* __restrict__ kp = reinterpret_cast<const char*>(p.k);
+  const char* __restrict__ vp = reinterpret_cast<const char*>(p.v);
+  const char* __restrict__ ep = reinterpret_cast<const char*>(p.e);
+  const int64_t ldq_b = p.ldq * (int64_t)sizeof(T), ldk_b = p.ldk * (int64_t)sizeof(T), ldv_b = p.ldv * (int64_t)sizeof(T);
+  const int64_t lde_b = p.lde_proj * (int64_t)sizeof(T);
+  const int64_t n_ranges = (p.n_dst + kNodesPerRange - 1) / kNodesPerRange;
+  const int64_t items = n_ranges * n_slabs;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t d = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); d < p.n_dst; d += warps_total) {
-    const int e0 = p.colptr[d], e1 = p.colptr[d + 1];
-    float q[VEC], acc[VEC];
-    load_vec_f32<T, VEC>(qp + d * p.ldq + lane * VEC, q);
+  const float qscale = p.scale * 1.4426950408889634f;  // scores in the log2 domain -> ex2
+
+  for (int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < items; item += warps_total) {
+    const int slab = (int)(item % n_slabs);
+    const int64_t n0 = (item / n_slabs) * kNodesPerRange;
+    const int nn = (int)min((int64_t)kNodesPerRange, p.n_dst - n0);
+    const int64_t lane_off = ((int64_t)slab * SLAB + (int64_t)lane_eff * EPC) * (int64_t)sizeof(T);  // byte offset of chunk 0 within a row
+    const int cp = __ldg(p.colptr + n0 + min(lane, nn));  // lanes 0..nn hold colptr[n0 + lane]
+    int blk_base = __shfl_sync(0xffffffffu, cp, 0);
+    const int E1 = __shfl_sync(0xffffffffu, cp, nn);
+    int src_cur = (blk_base + lane < E1) ? __ldg(p.src + blk_base + lane) : 0;
+    int src_nxt = (blk_base + 32 + lane < E1) ? __ldg(p.src + blk_base + 32 + lane) : 0;
+    // head index of each of this lane's chunks and the lane's attribute offsets inside qw / abar rows
+    int qw_off[NCH];
 #pragma unroll
-    for (int c = 0; c < VEC; ++c) q[c] *= p.scale, acc[c] = 0.f;
-    float qw[kMaxEdgeDim], abar[kMaxEdgeDim];
-    if constexpr (MODE == 2) {
+    for (int j = 0; j < NCH; ++j) qw_off[j] = ((slab * SLAB + (j * 32 + lane_eff) * EPC) / p.ch) * p.dp + sub;
+    uint4 q_raw[NCH];
+    float qw_raw[NCH][NA];
 #pragma unroll
-      for (int j = 0; j < kMaxEdgeDim; ++j) {
-        qw[j] = 0.f, abar[j] = 0.f;
-        if (j < D) {
-          float t = 0.f;
+    for (int j = 0; j < NCH; ++j) {
+      q_raw[j] = ldg16(qp + n0 * ldq_b + lane_off + j * 512);
+      if constexpr (MODE == 2) {
 #pragma unroll
-          for (int c = 0; c < VEC; ++c) t += q[c] * s_w[(j * VEC + c) * 32 + lane];
-          for (int o = 1; o < lph; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-          qw[j] = t;
-        }
+        for (int t = 0; t < NA; ++t)
+          qw_raw[j][t] = (t < na && sub + t * LPH < p.dp) ? to_f32<T>(reinterpret_cast<const T*>(p.qw)[n0 * p.ldqw + qw_off[j] + t * LPH]) : 0.f;
       }
     }
-    float m_i = -INFINITY, l_i = 0.f;
-    for (int eb = e0; eb < e1; eb += 2) {
-      // two edges per iteration: independent gathers in flight, one rescale of the accumulators
-      const bool two = eb + 1 < e1;
-      const int s0 = p.src[eb], s1 = two ? p.src[eb + 1] : s0;
-      float k0[VEC], k1[VEC], v0[VEC], v1[VEC];
-      load_vec_f32<T, VEC>(kp + (int64_t)s0 * p.ldk + lane * VEC, k0);
-      load_vec_f32<T, VEC>(kp + (int64_t)s1 * p.ldk + lane * VEC, k1);
-      load_vec_f32<T, VEC>(vp + (int64_t)s0 * p.ldv + lane * VEC, v0);
-      load_vec_f32<T, VEC>(vp + (int64_t)s1 * p.ldv + lane * VEC, v1);
-      float a0[kMaxEdgeDim], a1[kMaxEdgeDim];
-      if constexpr (MODE == 1) {
-        float t0[VEC], t1[VEC];
-        load_vec_f32<T, VEC>(ep + (int64_t)eb * p.lde_proj + lane * VEC, t0);
-        load_vec_f32<T, VEC>(ep + (int64_t)(two ? eb + 1 : eb) * p.lde_proj + lane * VEC, t1);
+
+    for (int nd = 0; nd < nn; ++nd) {
+      const int64_t d = n0 + nd;
+      const int e0 = __shfl_sync(0xffffffffu, cp, nd), e1 = __shfl_sync(0xffffffffu, cp, nd + 1);
+      float q[NCH][EPC], acc[NCH][EPC], m_i[NCH], l_i[NCH], qw[NCH][NA], abar[NCH][NA];
 #pragma unroll
-        for (int c = 0; c < VEC; ++c) k0[c] += t0[c], v0[c] += t0[c], k1[c] += t1[c], v1[c] += t1[c];
+      for (int j = 0; j < NCH; ++j) {
+        CT::unpack(q_raw[j], q[j]);
+        m_i[j] = -INFINITY, l_i[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPC; ++i) q[j][i] *= qscale, acc[j][i] = 0.f;
+#pragma unroll
+        for (int t = 0; t < NA; ++t) qw[j][t] = MODE == 2 ? qw_raw[j][t] * qscale : 0.f, abar[j][t] = 0.f;
       }
-      if constexpr (MODE == 2) {
-        const float* ap0 = p.edge_attr + (int64_t)eb * p.lde;
-        const float* ap1 = p.edge_attr + (int64_t)(two ? eb + 1 : eb) * p.lde;
+      if (nd + 1 < nn) {  // prefetch the next node's q / qw
 #pragma unroll
-        for (int j = 0; j < kMaxEdgeDim; j += 4) {
-          if (j < D) {  // lde is a multiple of 4 and rows are zero-padded (host contract)
-            const float4 t0 = __ldg(reinterpret_cast<const float4*>(ap0 + j));
-            const float4 t1 = __ldg(reinterpret_cast<const float4*>(ap1 + j));
-            a0[j] = t0.x, a0[j + 1] = t0.y, a0[j + 2] = t0.z, a0[j + 3] = t0.w;
-            a1[j] = t1.x, a1[j + 1] = t1.y, a1[j + 2] = t1.z, a1[j + 3] = t1.w;
-          } else {
-            a0[j] = a0[j + 1] = a0[j + 2] = a0[j + 3] = 0.f;
-            a1[j] = a1[j + 1] = a1[j + 2] = a1[j + 3] = 0.f;
+        for (int j = 0; j < NCH; ++j) {
+          q_raw[j] = ldg16(qp + (d + 1) * ldq_b + lane_off + j * 512);
+          if constexpr (MODE == 2) {
+#pragma unroll
+            for (int t = 0; t < NA; ++t)
+              if (t < na && sub + t * LPH < p.dp) qw_raw[j][t] = to_f32<T>(reinterpret_cast<const T*>(p.qw)[(d + 1) * p.ldqw + qw_off[j] + t * LPH]);
           }
         }
       }
-      float sc0 = 0.f, sc1 = 0.f;
+      for (int eb = e0; eb < e1; eb += kBatch) {
+        // ---- src ids of this batch from the prefetched blocks ----
+        if (eb - blk_base >= 32) {
+          blk_base += 32;
+          src_cur = src_nxt;
+          src_nxt = (blk_base + 32 + lane < E1) ? __ldg(p.src + blk_base + 32 + lane) : 0;
+        }
+        int sid[kBatch], eid[kBatch];
 #pragma unroll
-      for (int c = 0; c < VEC; ++c) sc0 += q[c] * k0[c], sc1 += q[c] * k1[c];
-      for (int o = 1; o < lph; o <<= 1) {
-        sc0 += __shfl_xor_sync(0xffffffffu, sc0, o);
-        sc1 += __shfl_xor_sync(0xffffffffu, sc1, o);
-      }
-      if constexpr (MODE == 2) {
+        for (int b = 0; b < kBatch; ++b) {
+          eid[b] = min(eb + b, e1 - 1);
+          const int off = eid[b] - blk_base;
+          const int a0 = __shfl_sync(0xffffffffu, src_cur, off & 31), a1 = __shfl_sync(0xffffffffu, src_nxt, off & 31);
+          sid[b] = off < 32 ? a0 : a1;
+        }
+        // ---- issue all gathers of the batch ----
+        uint4 k_raw[kBatch][NCH], v_raw[kBatch][NCH], e_raw[kBatch][NCH];
+        float at[kBatch][NA];
 #pragma unroll
-        for (int j = 0; j < kMaxEdgeDim; ++j)
-          if (j < D) sc0 += qw[j] * a0[j], sc1 += qw[j] * a1[j];
-      }
-      if (!two) sc1 = -INFINITY;
-      const float m_new = fmaxf(m_i, fmaxf(sc0, sc1));
-      const float corr = __expf(m_i - m_new);  // exp(-inf) = 0 on the first iteration
-      const float w0 = __expf(sc0 - m_new), w1 = __expf(sc1 - m_new);
-      l_i = l_i * corr + w0 + w1;
-      m_i = m_new;
+        for (int b = 0; b < kBatch; ++b) {
+          const char* kr = kp + (int64_t)sid[b] * ldk_b + lane_off;
+          const char* vr = vp + (int64_t)sid[b] * ldv_b + lane_off;
 #pragma unroll
-      for (int c = 0; c < VEC; ++c) acc[c] = acc[c] * corr + w0 * v0[c] + w1 * v1[c];
-      if constexpr (MODE == 2) {
+          for (int j = 0; j < NCH; ++j) {
+            k_raw[b][j] = ldg16(kr + j * 512);
+            v_raw[b][j] = ldg16(vr + j * 512);
+            if constexpr (MODE == 1) e_raw[b][j] = ep ? ldg16(ep + (int64_t)eid[b] * lde_b + lane_off + j * 512) : make_uint4(0, 0, 0, 0);
+          }
+          if constexpr (MODE == 2) {
+            const float* ar = p.edge_attr + (int64_t)eid[b] * p.lde + sub;  // rows are zero-padded to >= na*LPH floats (host contract)
 #pragma unroll
-        for (int j = 0; j < kMaxEdgeDim; ++j)
-          if (j < D) abar[j] = abar[j] * corr + w0 * a0[j] + w1 * a1[j];
-      }
-    }
-    float o[VEC];
-    if (e1 > e0) {
-      const float inv = 1.0f / l_i;
+            for (int t = 0; t < NA; ++t) at[b][t] = t < na ? __ldg(ar + t * LPH) : 0.f;
+          }
+        }
+        // ---- scores ----
+        float sc[kBatch][NCH];
 #pragma unroll
-      for (int c = 0; c < VEC; ++c) o[c] = acc[c] * inv;
-      if constexpr (MODE == 2) {
-        const int C = 32 * VEC;
+        for (int b = 0; b < kBatch; ++b)
 #pragma unroll
-        for (int c = 0; c < VEC; ++c) {
-          float t = s_w[C * D + c * 32 + lane];
+          for (int j = 0; j < NCH; ++j) {
+            float kf[EPC];
+            CT::unpack(k_raw[b][j], kf);
+            float t = 0.f;
+            if constexpr (MODE == 1) {
+              float ef[EPC];
+              CT::unpack(e_raw[b][j], ef);
 #pragma unroll
-          for (int j = 0; j < kMaxEdgeDim; ++j)
-            if (j < D) t += s_w[(j * VEC + c) * 32 + lane] * (abar[j] * inv);
-          o[c] += t;
+              for (int i = 0; i < EPC; ++i) t += q[j][i] * (kf[i] + ef[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < EPC; ++i) t += q[j][i] * kf[i];
+            }
+            if constexpr (MODE == 2) {
+#pragma unroll
+              for (int tt = 0; tt < NA; ++tt)
+                if (tt < na) t += qw[j][tt] * at[b][tt];
+            }
+#pragma unroll
+            for (int o = 1; o < LPH; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            sc[b][j] = (eb + b < e1) ? t : -INFINITY;
+          }
+        // ---- online softmax update ----
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          float mx = m_i[j];
+#pragma unroll
+          for (int b = 0; b < kBatch; ++b) mx = fmaxf(mx, sc[b][j]);
+          const float corr = exp2f(m_i[j] - mx);
+          float w[kBatch], wsum = 0.f;
+#pragma unroll
+          for (int b = 0; b < kBatch; ++b) w[b] = exp2f(sc[b][j] - mx), wsum += w[b];
+          l_i[j] = l_i[j] * corr + wsum;
+          m_i[j] = mx;
+#pragma unroll
+          for (int i = 0; i < EPC; ++i) acc[j][i] *= corr;
+#pragma unroll
+          for (int b = 0; b < kBatch; ++b) {
+            float vf[EPC];
+            CT::unpack(v_raw[b][j], vf);
+            if constexpr (MODE == 1) {
+              float ef[EPC];
+              CT::unpack(e_raw[b][j], ef);
+#pragma unroll
+              for (int i = 0; i < EPC; ++i) acc[j][i] += w[b] * (vf[i] + ef[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < EPC; ++i) acc[j][i] += w[b] * vf[i];
+            }
+          }
+          if constexpr (MODE == 2) {
+#pragma unroll
+            for (int t = 0; t < NA; ++t)
+              if (t < na) {
+                float s2 = abar[j][t] * corr;
+#pragma unroll
+                for (int b = 0; b < kBatch; ++b) s2 += w[b] * at[b][t];
+                abar[j][t] = s2;
+              }
+          }
         }
       }
-    } else {
+      // ---- finalise node d ----
+      const bool has_edges = e1 > e0;
 #pragma unroll
-      for (int c = 0; c < VEC; ++c) o[c] = 0.f;  // zero in-degree (gt.py:112-119)
-    }
-    if (p.add) {
-      float r[VEC];
-      load_vec_f32<T, VEC>(reinterpret_cast<const T*>(p.add) + d * p.ldadd + lane * VEC, r);
+      for (int j = 0; j < NCH; ++j) {
+        float o[EPC];
+        const float inv = has_edges ? 1.0f / l_i[j] : 0.f;
 #pragma unroll
-      for (int c = 0; c < VEC; ++c) o[c] += r[c];
+        for (int i = 0; i < EPC; ++i) o[i] = acc[j][i] * inv;
+        if constexpr (MODE == 2) {
+          if (has_edges && p.b_edge) {  // + b_e * sum(alpha) = + b_e
+            const float* bp = p.b_edge + slab * SLAB + (j * 32 + lane_eff) * EPC;
+#pragma unroll
+            for (int i = 0; i < EPC; i += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(bp + i));
+              o[i] += bv.x, o[i + 1] += bv.y, o[i + 2] += bv.z, o[i + 3] += bv.w;
+            }
+          }
+          if (active) {
+#pragma unroll
+            for (int t = 0; t < NA; ++t)
+              if (t < na && sub + t * LPH < p.dp)
+                reinterpret_cast<T*>(p.abar)[d * p.ldabar + qw_off[j] + t * LPH] = from_f32<T>(abar[j][t] * inv);
+          }
+        }
+        if (active) {
+          if (p.add) {
+            float r[EPC];
+            CT::unpack(ldg16(reinterpret_cast<const char*>(p.add) + (d * p.ldadd) * (int64_t)sizeof(T) + lane_off + j * 512), r);
+#pragma unroll
+            for (int i = 0; i < EPC; ++i) o[i] += r[i];
+          }
+          *reinterpret_cast<uint4*>(reinterpret_cast<char*>(p.out) + (d * p.ldo) * (int64_t)sizeof(T) + lane_off + j * 512) = CT::pack(o);
+        }
+      }
     }
-    store_vec_f32<T, VEC>(reinterpret_cast<T*>(p.out) + d * p.ldo + lane * VEC, o);
   }
 }
 
@@ -234,43 +359,52 @@ __global__ void __launch_bounds__(256) gt_attention_generic_kernel(const AttnPar
   }
 }
 
-template <typename T, int VEC>
-static int launch_warp(const AttnParams& p, int mode, cudaStream_t s) {
-  const int warps_per_block = 8;
-  int64_t blocks = (p.n_dst + warps_per_block - 1) / warps_per_block;
-  const int64_t cap = (int64_t)num_sms() * 8;
+template <typename T, int NCH, int LPH>
+static int launch_slab(const AttnParams& p, int mode, int n_slabs, int active_lanes, cudaStream_t s) {
+  const int64_t items = ((p.n_dst + kNodesPerRange - 1) / kNodesPerRange) * n_slabs;
+  const int warps_per_block = 4;
+  int64_t blocks = (items + warps_per_block - 1) / warps_per_block;
+  const int64_t cap = (int64_t)num_sms() * 3;  // 3 resident CTAs per SM (168 registers x 128 threads), persistent over the items
   if (blocks > cap) blocks = cap;
-  const size_t smem = mode == 2 ? (size_t)(32 * VEC) * (p.edge_dim + 1) * sizeof(float) : 0;
-  if (mode == 0) {
-    gt_attention_warp_kernel<T, VEC, 0><<<(unsigned)blocks, 256, 0, s>>>(p);
-  } else if (mode == 1) {
-    gt_attention_warp_kernel<T, VEC, 1><<<(unsigned)blocks, 256, 0, s>>>(p);
-  } else {
-    if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(gt_attention_warp_kernel<T, VEC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attention)");
-    }
-    gt_attention_warp_kernel<T, VEC, 2><<<(unsigned)blocks, 256, smem, s>>>(p);
+  if (mode == 2)
+    gt_attention_slab_kernel<T, NCH, LPH, 2><<<(unsigned)blocks, 128, 0, s>>>(p, n_slabs, active_lanes);
+  else
+    gt_attention_slab_kernel<T, NCH, LPH, 1><<<(unsigned)blocks, 128, 0, s>>>(p, n_slabs, active_lanes);
+  return launch_status("gt_attention_slab_kernel");
+}
+
+template <typename T, int NCH>
+static int launch_slab_lph(const AttnParams& p, int mode, int lph, int n_slabs, int active_lanes, cudaStream_t s) {
+  switch (lph) {
+    case 2: return launch_slab<T, NCH, 2>(p, mode, n_slabs, active_lanes, s);
+    case 4: return launch_slab<T, NCH, 4>(p, mode, n_slabs, active_lanes, s);
+    case 8: return launch_slab<T, NCH, 8>(p, mode, n_slabs, active_lanes, s);
+    case 16: return launch_slab<T, NCH, 16>(p, mode, n_slabs, active_lanes, s);
+    default: return 1;  // not a fast-path shape
   }
-  return launch_status("gt_attention_warp_kernel");
 }
 
 template <typename T>
-static int dispatch(const AttnParams& p, int mode, bool aligned, cudaStream_t s) {
+static int dispatch(const AttnParams& p, int mode, bool aligned, bool folded, cudaStream_t s) {
   const int C = p.heads * p.ch;
-  if (aligned && C % 32 == 0) {
-    const int vec = C / 32;
-    const bool ok = p.ch % vec == 0 && ((p.ch / vec) & (p.ch / vec - 1)) == 0 && p.ch / vec <= 32;
-    if (ok) {
-      switch (vec) {
-        case 2: return launch_warp<T, 2>(p, mode, s);
-        case 4: return launch_warp<T, 4>(p, mode, s);
-        case 8: return launch_warp<T, 8>(p, mode, s);
-        case 16: return launch_warp<T, 16>(p, mode, s);
-        case 32: return launch_warp<T, 32>(p, mode, s);
-        default: break;
-      }
+  constexpr int EPC = ChunkT<T>::EPC;
+  if (aligned && C % EPC == 0 && p.ch % EPC == 0) {
+    const int lph = p.ch / EPC;
+    const int chunks = C / EPC;  // 16-byte chunks per row
+    int rc = 1;
+    if (chunks < 32) {
+      rc = launch_slab_lph<T, 1>(p, mode, lph, 1, chunks, s);  // narrow rows: part of the warp idles
+    } else if (chunks % 32 == 0 && (32 % lph) == 0) {
+      const int full = chunks / 32;
+      rc = (full % 2 == 0) ? launch_slab_lph<T, 2>(p, mode, lph, full / 2, 32, s) : launch_slab_lph<T, 1>(p, mode, lph, full, 32, s);
     }
+    if (rc <= 0) return rc;
+  }
+  if (folded) {
+    set_error("gt_attention: the folded lin_edge form needs a slab-kernel shape (16-byte aligned rows, Ch/(16/elemsize) in {2,4,8,16}, <= 16 "
+              "attributes padded to 16 floats); use the w_edge form for H=%d Ch=%d",
+              p.heads, p.ch);
+    return -3;
   }
   if (p.ch > 256) {
     set_error("gt_attention: channels per head %d > 256 unsupported", p.ch);
@@ -295,9 +429,9 @@ using namespace anemoi;
 
 extern "C" int anemoi_b200_gt_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* e,
                                             int64_t lde_proj, const float* edge_attr, int64_t lde, int64_t edge_dim, const float* w_edge,
-                                            int64_t ldw_e, const float* b_edge, const int32_t* src32, const int32_t* colptr32, const void* add,
-                                            int64_t ldadd, void* out, int64_t ldo, int64_t n_dst, int64_t heads, int64_t ch, int dtype,
-                                            void* stream) {
+                                            int64_t ldw_e, const float* b_edge, const void* qw, int64_t ldqw, void* abar, int64_t ldabar,
+                                            int64_t dp, const int32_t* src32, const int32_t* colptr32, const void* add, int64_t ldadd, void* out,
+                                            int64_t ldo, int64_t n_dst, int64_t heads, int64_t ch, int dtype, void* stream) {
   ANEMOI_CHECK_ARG(n_dst >= 0 && heads >= 1 && ch >= 1, "gt_attention: bad shape");
   ANEMOI_CHECK_ARG(dtype == ANEMOI_F32 || dtype == ANEMOI_BF16, "gt_attention: bad dtype %d", dtype);
   if (n_dst == 0) return 0;
@@ -305,25 +439,28 @@ extern "C" int anemoi_b200_gt_attention_fwd(const void* q, int64_t ldq, const vo
   ANEMOI_CHECK_ARG(!(e && edge_attr), "gt_attention: pass either a materialised edge projection or raw edge attributes, not both");
   const int64_t C = heads * ch;
   ANEMOI_CHECK_ARG(ldq >= C && ldk >= C && ldv >= C && ldo >= C, "gt_attention: leading dimension < heads*ch");
-  int mode = e ? 1 : (edge_attr ? 2 : 0);
+  const int mode = e ? 1 : (edge_attr ? 2 : 0);
+  const bool folded = mode == 2 && qw != nullptr;
   if (mode == 2) {
-    ANEMOI_CHECK_ARG(w_edge && edge_dim >= 1 && lde >= edge_dim && ldw_e >= edge_dim, "gt_attention: bad fused lin_edge arguments");
+    ANEMOI_CHECK_ARG(edge_dim >= 1 && lde >= edge_dim, "gt_attention: bad edge attribute shape");
+    ANEMOI_CHECK_ARG(folded || (w_edge && ldw_e >= edge_dim), "gt_attention: fused lin_edge needs either qw/abar (folded form) or w_edge");
+    ANEMOI_CHECK_ARG(!folded || (abar && dp >= edge_dim && ldqw >= heads * dp && ldabar >= heads * dp), "gt_attention: bad folded lin_edge arguments");
   }
   AttnParams p;
   p.q = q, p.k = k, p.v = v, p.e = e, p.add = add, p.out = out;
   p.ldq = ldq, p.ldk = ldk, p.ldv = ldv, p.lde_proj = lde_proj, p.ldadd = ldadd, p.ldo = ldo;
   p.edge_attr = edge_attr, p.lde = lde, p.edge_dim = (int)edge_dim, p.w_edge = w_edge, p.ldw_e = ldw_e, p.b_edge = b_edge;
+  p.qw = qw, p.abar = abar, p.ldqw = ldqw, p.ldabar = ldabar, p.dp = (int)dp;
   p.src = src32, p.colptr = colptr32, p.n_dst = n_dst, p.heads = (int)heads, p.ch = (int)ch;
   p.scale = 1.0f / sqrtf((float)ch);
   const int es = dtype == ANEMOI_BF16 ? 2 : 4;
   auto al = [&](const void* ptr, int64_t ld) { return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * es) % 16 == 0); };
-  bool aligned = al(q, ldq) && al(k, ldk) && al(v, ldv) && al(e, lde_proj) && al(add, ldadd) && al(out, ldo);
+  bool slab_ok = al(q, ldq) && al(k, ldk) && al(v, ldv) && al(e, lde_proj) && al(add, ldadd) && al(out, ldo);
   if (mode == 2) {
-    // fast fused path contract: <= 16 attributes, rows padded to a multiple of 4 floats and 16-byte aligned
-    const bool fused_ok = edge_dim <= kMaxEdgeDim && lde % 4 == 0 && lde >= ((edge_dim + 3) / 4) * 4 &&
-                          (reinterpret_cast<uintptr_t>(edge_attr) & 15) == 0;
-    aligned = aligned && fused_ok;
+    // slab (fast) path needs the folded form, <= 16 attributes, rows zero-padded to 16 floats, 16-byte aligned bias
+    slab_ok = slab_ok && folded && edge_dim <= kMaxEdgeDim && lde >= kMaxEdgeDim && (!b_edge || (reinterpret_cast<uintptr_t>(b_edge) & 15) == 0);
   }
   cudaStream_t s = (cudaStream_t)stream;
-  return dtype == ANEMOI_BF16 ? dispatch<__nv_bfloat16>(p, mode, aligned, s) : dispatch<float>(p, mode, aligned, s);
+  const int rc = dtype == ANEMOI_BF16 ? dispatch<__nv_bfloat16>(p, mode, slab_ok, folded, s) : dispatch<float>(p, mode, slab_ok, folded, s);
+  return rc;
 }

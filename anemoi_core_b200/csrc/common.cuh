@@ -85,6 +85,24 @@ __device__ __forceinline__ void store_from_f32(void* p, int64_t i, int dtype, fl
 // exact (erf) GELU, torch.nn.GELU() default — layers/utils.py:107-110
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// Same function to ~2e-7 absolute (Abramowitz-Stegun 7.1.26 erfc, |err| <= 1.5e-7): two MUFU (rcp, ex2) + ~12 FP32 ops instead
+// of erff's ~35.  Used in the tensor-core GEMM epilogue, where the exact-erf GELU would make the epilogue the critical path.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ax, 0.3275911f * 0.70710678118654752440f, 1.0f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float ex;  // exp(-(x/sqrt2)^2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(x * x * (-0.5f * 1.4426950408889634f)));
+  const float h = 0.5f * poly * ex;                                 // 0.5 * erfc(|x|/sqrt2)
+  const float xh = x * h;
+  return x > 0.f ? x - xh : xh;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

@@ -8,9 +8,11 @@
 //                      tcgen05.commit releases smem slots / publishes the accumulator.
 //   warp 2             TMEM allocator (tcgen05.alloc / dealloc).
 //   warps 4..11        epilogue: tcgen05.ld 32x32b (one accumulator row per thread, warp w owns TMEM lanes
-//                      32*(w%4).., column half (w-4)/4), then bias / gather-add / erf-GELU / residual in fp32 and
-//                      16-byte stores.  One row per thread is also what the gather-add epilogue wants: the edge's
-//                      two projected node rows are contiguous per thread.
+//                      32*(w%4).., column half (w-4)/4), bias / gather-add / GELU / residual in fp32, then the
+//                      32-row x 128-byte sub-tile goes through a per-warp 128B-swizzled staging buffer and leaves as ONE
+//                      TMA store (cp.async.bulk.tensor, hardware bounds clipping, no per-element address math); the
+//                      residual sub-tile arrives the same way (TMA load into the staging buffer).  A slow element-wise
+//                      epilogue covers unaligned outputs / mixed residual dtypes.
 // K tails and M/N tails rely on TMA out-of-bounds zero fill + masked stores.
 #include <cuda.h>
 
@@ -51,6 +53,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
                "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -95,12 +113,13 @@ constexpr int kThreads = 384;  // warps 0..3 control, 4..11 epilogue
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = BN == 256 ? 4 : 6;
   static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
   static constexpr int kWBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kWBytes;
   static constexpr int kTmemCols = 2 * BN;  // 128 / 256 / 512: powers of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 8 * 4096;  // one 32-row x 128-byte transpose buffer per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // UMMA shared-memory descriptor for a K-major, 128-byte-swizzled tile (rows of 64 bf16 = 128 B; 8-row groups 1024 B apart).
@@ -114,20 +133,203 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// Epilogue mode bits (host-selected, warp-uniform): 0 = slow element-wise path.
+constexpr int kEpiFast = 1, kEpiOutF32 = 2, kEpiGelu = 4, kEpiRes = 8, kEpiGather = 16;
+
+struct EpiCtx {
+  uint32_t tmem_base, stg, res_bar, tfull0, tempty0;
+  int lane, q, half, num_tiles, tiles_n, first_tile, tile_stride;
+};
+
+// Fast epilogue: templated so that the inner loop has no runtime dtype / flag branches.
+template <int BN, bool OUT_F32, bool GELU, bool RES, bool GATHER>
+__device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams& ep, const CUtensorMap* tmOut, const CUtensorMap* tmRes) {
+  constexpr int kColsPerWarp = BN / 2;
+  constexpr int CW = OUT_F32 ? 32 : 64;  // columns per 128-byte staging row
+  constexpr int ROUNDS = kColsPerWarp / CW;
+  static_assert(kColsPerWarp % CW == 0, "tile width");
+  const int lane = cx.lane;
+  const uint32_t my_row = cx.stg + lane * 128;
+  const uint32_t sw = (uint32_t)(lane & 7);
+  uint32_t res_phase = 0;
+  int it = 0;
+  for (int tile = cx.first_tile; tile < cx.num_tiles; tile += cx.tile_stride, ++it) {
+    const int m_blk = tile / cx.tiles_n, n_blk = tile - m_blk * cx.tiles_n;
+    const int as = it & 1;
+    const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+    const int row0 = m_blk * kBM + cx.q * 32;
+    const float* g1row = nullptr;
+    const float* g2row = nullptr;
+    if constexpr (GATHER) {
+      const int64_t r = min((int64_t)row0 + lane, ep.M - 1);
+      if (ep.g1) g1row = ep.g1 + (int64_t)__ldg(ep.idx1 + r) * ep.ldg;
+      if (ep.g2) g2row = ep.g2 + (int64_t)__ldg(ep.idx2 + r) * ep.ldg;
+    }
+#pragma unroll 1
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+      const int col_in_tile = cx.half * kColsPerWarp + rd * CW;
+      const int col0 = n_blk * BN + col_in_tile;
+      // the previous TMA store must have finished READING the staging buffer before it is overwritten
+      if (lane == 0) ptx::bulk_wait_read0();
+      __syncwarp();
+      if constexpr (RES) {
+        if (lane == 0) {
+          ptx::mbar_expect_tx(cx.res_bar, 4096);
+          ptx::tma_load_2d(cx.stg, tmRes, cx.res_bar, col0, row0);  // OOB rows / columns arrive as zeros
+        }
+      }
+      if (rd == 0) {
+        ptx::mbar_wait(cx.tfull0 + 8u * as, aphase);
+        ptx::tc_fence_after();
+      }
+      if constexpr (RES) {
+        ptx::mbar_wait(cx.res_bar, res_phase);
+        res_phase ^= 1u;
+      }
+#pragma unroll
+      for (int h32 = 0; h32 < CW; h32 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(cx.tmem_base + ((uint32_t)(cx.q * 32) << 16) + (uint32_t)(as * BN + col_in_tile + h32), r);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = col0 + h32 + g * 8;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+          if (col + 8 <= (int)ep.N) {
+            if (ep.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col)), b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + 1);
+              v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+            }
+            if constexpr (GATHER) {
+              if (g1row) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(g1row + col)), b1 = __ldg(reinterpret_cast<const float4*>(g1row + col) + 1);
+                v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+              }
+              if (g2row) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(g2row + col)), b1 = __ldg(reinterpret_cast<const float4*>(g2row + col) + 1);
+                v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+              }
+            }
+          } else if (col < (int)ep.N) {  // ragged last 8-column group of the matrix
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (col + j < (int)ep.N) {
+                if (ep.bias) v[j] += ep.bias[col + j];
+                if constexpr (GATHER) {
+                  if (g1row) v[j] += g1row[col + j];
+                  if (g2row) v[j] += g2row[col + j];
+                }
+              }
+            }
+          }
+          if constexpr (GELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = gelu_erf_fast(v[j]);
+          }
+          if constexpr (OUT_F32) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint32_t addr = my_row + ((((uint32_t)(h32 + g * 8) * 4u >> 4) + hh) ^ sw) * 16u;
+              if constexpr (RES) {
+                const uint4 rv = ptx::lds128(addr);
+                v[4 * hh] += __uint_as_float(rv.x), v[4 * hh + 1] += __uint_as_float(rv.y);
+                v[4 * hh + 2] += __uint_as_float(rv.z), v[4 * hh + 3] += __uint_as_float(rv.w);
+              }
+              ptx::sts128(addr, __float_as_uint(v[4 * hh]), __float_as_uint(v[4 * hh + 1]), __float_as_uint(v[4 * hh + 2]),
+                          __float_as_uint(v[4 * hh + 3]));
+            }
+          } else {
+            const uint32_t addr = my_row + ((((uint32_t)(h32 + g * 8) * 2u) >> 4) ^ sw) * 16u;
+            if constexpr (RES) {
+              const uint4 rv = ptx::lds128(addr);
+              v[0] += __uint_as_float(rv.x << 16), v[1] += __uint_as_float(rv.x & 0xffff0000u);
+              v[2] += __uint_as_float(rv.y << 16), v[3] += __uint_as_float(rv.y & 0xffff0000u);
+              v[4] += __uint_as_float(rv.z << 16), v[5] += __uint_as_float(rv.z & 0xffff0000u);
+              v[6] += __uint_as_float(rv.w << 16), v[7] += __uint_as_float(rv.w & 0xffff0000u);
+            }
+            ptx::sts128(addr, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          }
+        }
+      }
+      if (rd == ROUNDS - 1) {  // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(cx.tempty0 + 8u * as);
+      }
+      ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_2d(tmOut, cx.stg, col0, row0);  // rows >= M / columns >= N are clipped by the hardware
+        ptx::bulk_commit();
+      }
+    }
+  }
+  if (lane == 0) ptx::bulk_wait0();
+}
+
+// Slow element-wise epilogue: any alignment / dtype mix.  One accumulator row per thread, direct global accesses.
+template <int BN>
+__device__ __noinline__ void epilogue_generic(const EpiCtx& cx, const EpiParams& ep) {
+  constexpr int kColsPerWarp = BN / 2;
+  const int lane = cx.lane;
+  int it = 0;
+  for (int tile = cx.first_tile; tile < cx.num_tiles; tile += cx.tile_stride, ++it) {
+    const int m_blk = tile / cx.tiles_n, n_blk = tile - m_blk * cx.tiles_n;
+    const int as = it & 1;
+    const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+    ptx::mbar_wait(cx.tfull0 + 8u * as, aphase);
+    ptx::tc_fence_after();
+    const int64_t row = (int64_t)m_blk * kBM + cx.q * 32 + lane;
+    const bool row_ok = row < ep.M;
+    const float* g1row = (ep.g1 && row_ok) ? ep.g1 + (int64_t)ep.idx1[row] * ep.ldg : nullptr;
+    const float* g2row = (ep.g2 && row_ok) ? ep.g2 + (int64_t)ep.idx2[row] * ep.ldg : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < kColsPerWarp; c += 32) {
+      uint32_t r[32];
+      const int col_in_tile = cx.half * kColsPerWarp + c;
+      ptx::tmem_ld_32x32b_x32(cx.tmem_base + ((uint32_t)(cx.q * 32) << 16) + (uint32_t)(as * BN + col_in_tile), r);
+      ptx::tmem_wait_ld();
+      const int64_t col0 = (int64_t)n_blk * BN + col_in_tile;
+      if (row_ok) {
+#pragma unroll 1
+        for (int j = 0; j < 32; ++j) {
+          const int64_t n = col0 + j;
+          if (n >= ep.N) break;
+          float a = __uint_as_float(r[j]);
+          if (ep.bias) a += ep.bias[n];
+          if (g1row) a += g1row[n];
+          if (g2row) a += g2row[n];
+          if (ep.flags & ANEMOI_EPI_GELU) a = gelu_erf_fast(a);
+          if (ep.residual) a += load_as_f32(ep.residual, row * ep.ldr + n, ep.r_dtype);
+          store_from_f32(ep.out, row * ep.ldo + n, ep.o_dtype, a);
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(cx.tempty0 + 8u * as);
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-    gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int num_kb, int tiles_m,
-                             int tiles_n, int vec_ok, const EpiParams ep) {
+    gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, int num_kb, int tiles_m,
+                             int tiles_n, int epi_mode, const EpiParams ep) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
-  // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base address slot
+  const uint32_t staging_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t bar_base = staging_base + Cfg::kStagingBytes;
+  // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], res[8], then the TMEM base address slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  auto res_bar = [&](int w) { return bar_base + 8u * (2 * Cfg::kStages + 4 + w); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = tiles_m * tiles_n;
@@ -135,6 +337,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmW);
+    if (epi_mode & kEpiFast) ptx::prefetch_tmap(&tmOut);
+    if (epi_mode & kEpiRes) ptx::prefetch_tmap(&tmRes);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -145,6 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       ptx::mbar_init(tfull_bar(s), 1);
       ptx::mbar_init(tempty_bar(s), 8);  // one arrive per epilogue warp
     }
+    for (int w = 0; w < 8; ++w) ptx::mbar_init(res_bar(w), 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -207,89 +412,34 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp >= 4) {
     // ===== epilogue =====
-    const int q = warp & 3;           // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;  // column half
-    constexpr int kColsPerWarp = BN / 2;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
-      const int as = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      ptx::mbar_wait(tfull_bar(as), aphase);
-      ptx::tc_fence_after();
-      const int64_t row = (int64_t)m_blk * kBM + q * 32 + lane;
-      const bool row_ok = row < ep.M;
-      const float* g1row = (ep.g1 && row_ok) ? ep.g1 + (int64_t)ep.idx1[row] * ep.ldg : nullptr;
-      const float* g2row = (ep.g2 && row_ok) ? ep.g2 + (int64_t)ep.idx2[row] * ep.ldg : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < kColsPerWarp; c += 32) {
-        uint32_t r[32];
-        const int col_in_tile = half * kColsPerWarp + c;
-        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + col_in_tile), r);
-        ptx::tmem_wait_ld();
-        const int64_t col0 = (int64_t)n_blk * BN + col_in_tile;
-        if (row_ok && col0 < ep.N) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int64_t col = col0 + g * 8;
-            if (col >= ep.N) break;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-            if (vec_ok && col + 8 <= ep.N) {
-              if (ep.bias) {
-                float t[8];
-                load_vec_f32<float, 8>(ep.bias + col, t);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += t[j];
-              }
-              if (g1row) {
-                float t[8];
-                load_vec_f32<float, 8>(g1row + col, t);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += t[j];
-              }
-              if (g2row) {
-                float t[8];
-                load_vec_f32<float, 8>(g2row + col, t);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += t[j];
-              }
-              if (ep.flags & ANEMOI_EPI_GELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-              }
-              if (ep.residual) {
-                float t[8];
-                if (ep.r_dtype == ANEMOI_BF16)
-                  load_vec_f32<__nv_bfloat16, 8>(reinterpret_cast<const __nv_bfloat16*>(ep.residual) + row * ep.ldr + col, t);
-                else
-                  load_vec_f32<float, 8>(reinterpret_cast<const float*>(ep.residual) + row * ep.ldr + col, t);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += t[j];
-              }
-              if (ep.o_dtype == ANEMOI_BF16)
-                store_vec_f32<__nv_bfloat16, 8>(reinterpret_cast<__nv_bfloat16*>(ep.out) + row * ep.ldo + col, v);
-              else
-                store_vec_f32<float, 8>(reinterpret_cast<float*>(ep.out) + row * ep.ldo + col, v);
-            } else {
-              for (int j = 0; j < 8 && col + j < ep.N; ++j) {
-                float a = v[j];
-                const int64_t n = col + j;
-                if (ep.bias) a += ep.bias[n];
-                if (g1row) a += g1row[n];
-                if (g2row) a += g2row[n];
-                if (ep.flags & ANEMOI_EPI_GELU) a = gelu_erf(a);
-                if (ep.residual) a += load_as_f32(ep.residual, row * ep.ldr + n, ep.r_dtype);
-                store_from_f32(ep.out, row * ep.ldo + n, ep.o_dtype, a);
-              }
-            }
-          }
-        }
+    EpiCtx cx;
+    cx.tmem_base = tmem_base, cx.lane = lane, cx.q = warp & 3, cx.half = (warp - 4) >> 2;
+    cx.stg = staging_base + (uint32_t)(warp - 4) * 4096u, cx.res_bar = res_bar(warp - 4);
+    cx.tfull0 = tfull_bar(0), cx.tempty0 = tempty_bar(0);
+    cx.num_tiles = num_tiles, cx.tiles_n = tiles_n, cx.first_tile = blockIdx.x, cx.tile_stride = gridDim.x;
+    if (!(epi_mode & kEpiFast)) {
+      epilogue_generic<BN>(cx, ep);
+    } else {
+#define ANEMOI_EPI_CASE(F32, GELU, RES, GATHER)                                                                          \
+  case (F32 ? kEpiOutF32 : 0) | (GELU ? kEpiGelu : 0) | (RES ? kEpiRes : 0) | (GATHER ? kEpiGather : 0):                   \
+    epilogue_fast<BN, F32, GELU, RES, GATHER>(cx, ep, &tmOut, &tmRes);                                                     \
+    break;
+      switch (epi_mode & ~kEpiFast) {
+        ANEMOI_EPI_CASE(false, false, false, false)
+        ANEMOI_EPI_CASE(false, true, false, false)
+        ANEMOI_EPI_CASE(false, false, true, false)
+        ANEMOI_EPI_CASE(false, true, true, false)
+        ANEMOI_EPI_CASE(true, false, false, false)
+        ANEMOI_EPI_CASE(true, true, false, false)
+        ANEMOI_EPI_CASE(true, false, true, false)
+        ANEMOI_EPI_CASE(true, true, true, false)
+        ANEMOI_EPI_CASE(false, false, false, true)
+        ANEMOI_EPI_CASE(false, true, false, true)
+        ANEMOI_EPI_CASE(true, false, false, true)
+        ANEMOI_EPI_CASE(true, true, false, true)
+        default: __trap();  // host never selects another combination
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+#undef ANEMOI_EPI_CASE
     }
   }
   ptx::tc_fence_before();
@@ -320,23 +470,26 @@ static PFN_encodeTiled get_encode() {
 struct MapKey {
   const void* ptr;
   int64_t rows, cols, ld;
-  int box_rows;
-  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+  int box_rows, es;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && es == o.es;
+  }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr);
     auto mix = [&](int64_t v) { h ^= std::hash<int64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.rows), mix(k.cols), mix(k.ld), mix(k.box_rows);
+    mix(k.rows), mix(k.cols), mix(k.ld), mix(k.box_rows), mix(k.es);
     return h;
   }
 };
 
-// bf16 [rows, cols] row-major, leading dimension ld (elements); box = box_rows x 64 columns, 128-byte swizzle, zero OOB fill.
-static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+// [rows, cols] row-major of element size es (2 = bf16, 4 = fp32), leading dimension ld (elements); box = box_rows x 128 bytes,
+// 128-byte swizzle, zero OOB fill on loads / clipping on stores.
+static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out, int es = 2) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, rows, cols, ld, box_rows};
+  MapKey key{ptr, rows, cols, ld, box_rows, es};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -351,10 +504,10 @@ static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t l
     return -2;
   }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(out, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("linear(tcgen05): cuTensorMapEncodeTiled failed with CUresult %d (ptr %p rows %lld cols %lld ld %lld box %d)", (int)r, ptr,
@@ -368,7 +521,8 @@ static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t l
 }
 
 template <int BN>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, int64_t K, int vec_ok, const EpiParams& ep, cudaStream_t s) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmOut, const CUtensorMap& tmRes, int64_t K, int epi_mode,
+                  const EpiParams& ep, cudaStream_t s) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -380,34 +534,40 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, int64_t K, int
   const int num_kb = (int)((K + kBK - 1) / kBK);
   const int64_t tiles = (int64_t)tiles_m * tiles_n;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  gemm_bf16_tcgen05_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmA, tmW, num_kb, tiles_m, tiles_n, vec_ok, ep);
+  gemm_bf16_tcgen05_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmA, tmW, tmOut, tmRes, num_kb, tiles_m, tiles_n, epi_mode, ep);
   return launch_status("gemm_bf16_tcgen05_kernel");
 }
 
 int linear_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t K, const EpiParams& ep, cudaStream_t s) {
-  // tile width: widest tile that keeps at least ~2 waves of CTAs busy
+  // tile width: 256 unless that leaves fewer than ~2 waves of CTAs
   const int64_t tiles_m = (ep.M + kBM - 1) / kBM;
   int bn = 256;
-  if (ep.N <= 64)
-    bn = 64;
-  else if (ep.N <= 128 || tiles_m * ((ep.N + 255) / 256) < 2 * (int64_t)num_sms())
-    bn = 128;
-  if (bn == 128 && ep.N <= 64) bn = 64;
-  CUtensorMap tmA, tmW;
+  if (ep.N <= 128 || tiles_m * ((ep.N + 255) / 256) < 2 * (int64_t)num_sms()) bn = 128;
+  CUtensorMap tmA, tmW, tmOut, tmRes;
   int rc = get_tensor_map(A, ep.M, K, lda, kBM, &tmA);
   if (rc) return rc;
   rc = get_tensor_map(W, ep.N, K, ldw, bn, &tmW);
   if (rc) return rc;
   auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  const int os = ep.o_dtype == ANEMOI_BF16 ? 2 : 4, rs = ep.r_dtype == ANEMOI_BF16 ? 2 : 4;
-  const int vec_ok = a16(ep.out) && (ep.ldo * os) % 16 == 0 && (!ep.bias || a16(ep.bias)) &&
-                     (!ep.residual || (a16(ep.residual) && (ep.ldr * rs) % 16 == 0)) &&
-                     ((!ep.g1 && !ep.g2) || ((!ep.g1 || a16(ep.g1)) && (!ep.g2 || a16(ep.g2)) && ep.ldg % 4 == 0));
-  switch (bn) {
-    case 64: return launch<64>(tmA, tmW, K, vec_ok, ep, s);
-    case 128: return launch<128>(tmA, tmW, K, vec_ok, ep, s);
-    default: return launch<256>(tmA, tmW, K, vec_ok, ep, s);
+  const int os = ep.o_dtype == ANEMOI_BF16 ? 2 : 4;
+  const bool gather = ep.g1 || ep.g2;
+  // fast epilogue: TMA-storable output, 16-byte aligned bias / gather rows, residual (if any) of the output dtype and TMA-loadable
+  bool fast = a16(ep.out) && (ep.ldo * os) % 16 == 0 && (!ep.bias || a16(ep.bias)) &&
+              (!gather || ((!ep.g1 || a16(ep.g1)) && (!ep.g2 || a16(ep.g2)) && ep.ldg % 4 == 0 && !ep.residual));
+  if (ep.residual) fast = fast && ep.r_dtype == ep.o_dtype && a16(ep.residual) && (ep.ldr * os) % 16 == 0;
+  int epi_mode = 0;
+  tmOut = tmA, tmRes = tmA;  // placeholders when unused
+  if (fast) {
+    epi_mode = kEpiFast | (os == 4 ? kEpiOutF32 : 0) | ((ep.flags & ANEMOI_EPI_GELU) ? kEpiGelu : 0) | (ep.residual ? kEpiRes : 0) |
+               (gather ? kEpiGather : 0);
+    rc = get_tensor_map(ep.out, ep.M, ep.N, ep.ldo, 32, &tmOut, os);
+    if (rc) return rc;
+    if (ep.residual) {
+      rc = get_tensor_map(ep.residual, ep.M, ep.N, ep.ldr, 32, &tmRes, os);
+      if (rc) return rc;
+    }
   }
+  return bn == 128 ? launch<128>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s) : launch<256>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s);
 }
 
 }  // namespace anemoi

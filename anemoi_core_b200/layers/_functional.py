@@ -146,10 +146,11 @@ def csr_for(edge_index: Tensor, n_src: int, n_dst: int) -> ops.GraphCSR:
     return csr
 
 
-def pad_edge_attr(edge_attr: Tensor) -> Tensor:
-    """fp32 [E, ceil4(d_e)] zero-padded copy of the raw edge attributes (16-byte rows for the fused lin_edge path)."""
+def pad_edge_attr(edge_attr: Tensor, width: int = 0) -> Tensor:
+    """fp32 [E, width] zero-padded copy of the raw edge attributes (``width`` = 16 for the folded attention path: one
+    64-byte row = two full sectors per edge; default ceil4(d_e))."""
     d = edge_attr.shape[1]
-    d4 = (d + 3) // 4 * 4
-    if edge_attr.dtype == torch.float32 and d == d4 and edge_attr.is_contiguous():
+    w = width or (d + 3) // 4 * 4
+    if edge_attr.dtype == torch.float32 and d == w and edge_attr.is_contiguous():
         return edge_attr
-    return ops.cast_pad(edge_attr, torch.float32, d4)
+    return ops.cast_pad(edge_attr, torch.float32, w)

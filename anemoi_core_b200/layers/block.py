@@ -189,28 +189,126 @@ class GraphTransformerBaseBlock(nn.Module):
         self.graph_attention_backend = graph_attention_backend
         self._pack = Fn.WeightPack()
 
+    # -- lin_edge folding -----------------------------------------------------------------------------------------
+    # eproj = W_e a + b_e enters attention linearly, so (include/anemoi_b200.h, form 3)
+    #   q.(k + eproj)          = q.k + (W_e,h^T q_h).a + const      -> qw = x_n (W_e,h^T W_q,h)^T : extra columns of the q GEMM
+    #   sum alpha (v + eproj)  = sum alpha v + W_e,h abar_h + b_e   -> projection(att + W_e abar) = [att | abar] [W_p | W_p W_e]^T
+    # The folded weights are built once per parameter version in fp32.
+    def _fold_dims(self) -> tuple[int, int, int]:
+        d = self.lin_edge.weight.shape[1]
+        dp = (d + 3) // 4 * 4
+        return d, dp, Fn.round8(self.num_heads * dp)
+
+    def _use_fold(self, dt: torch.dtype) -> bool:
+        return ops.attention_fold_supported(self.attn_channels, self.num_heads, dt, self.lin_edge.weight.shape[1])
+
+    def _w_edge_heads(self) -> Tensor:
+        H, Ch = self.num_heads, self.out_channels_conv
+        return self.lin_edge.weight.detach().float().view(H, Ch, -1)  # [H, Ch, D]
+
+    def _dst_weight(self, layers, dt: torch.dtype, fold_q: bool) -> tuple[Tensor, Optional[Tensor]]:
+        """Row-concatenated weight/bias of the dst-side GEMM; with ``fold_q`` the rows (h, a) = W_e,h[:, a]^T W_q,h are appended."""
+        if not fold_q:
+            return self._pack.weight(layers, dt), self._pack.bias(layers)
+        H, Ch = self.num_heads, self.out_channels_conv
+        d, dp, hdp = self._fold_dims()
+        srcs = [l.weight for l in layers] + [getattr(l, "bias", None) for l in layers] + [self.lin_edge.weight]
+
+        def build_w() -> Tensor:
+            we = self._w_edge_heads()
+            wq = self.lin_query.weight.detach().float().view(H, Ch, -1)
+            wf = torch.zeros(hdp, wq.shape[-1], device=wq.device)
+            wf[: H * dp].view(H, dp, -1)[:, :d] = torch.einsum("hca,hci->hai", we, wq)
+            w = torch.cat([l.weight.detach().float() for l in layers] + [wf], 0)
+            k = w.shape[1]
+            if dt == torch.bfloat16 and k % 8:
+                w = torch.nn.functional.pad(w, (0, Fn.round8(k) - k))
+            return w.to(dt).contiguous()
+
+        def build_b() -> Tensor:
+            we = self._w_edge_heads()
+            bf = torch.zeros(hdp, device=we.device)
+            if self.lin_query.bias is not None:
+                bf[: H * dp].view(H, dp)[:, :d] = torch.einsum("hca,hc->ha", we, self.lin_query.bias.detach().float().view(H, Ch))
+            parts = [l.bias.detach().float() if l.bias is not None else torch.zeros(l.weight.shape[0], device=we.device) for l in layers]
+            return torch.cat(parts + [bf]).contiguous()
+
+        key = tuple(id(l) for l in layers)
+        return self._pack.get(("w_dst_fold", key, dt), srcs, build_w), self._pack.get(("b_dst_fold", key), srcs, build_b)
+
+    def _qw_blockdiag(self, dt: torch.dtype) -> Tensor:
+        """[hdp, A] block-diagonal W_e^T for the qk_norm case (qw must be taken from the normalised query)."""
+        H, Ch = self.num_heads, self.out_channels_conv
+        d, dp, hdp = self._fold_dims()
+
+        def build() -> Tensor:
+            we = self._w_edge_heads()
+            w = torch.zeros(hdp, H * Ch, device=we.device)
+            for h in range(H):
+                w[h * dp : h * dp + d, h * Ch : (h + 1) * Ch] = we[h].t()
+            return w.to(dt).contiguous()
+
+        return self._pack.get(("w_qw_bd", dt), [self.lin_edge.weight], build)
+
+    def _proj_weight(self, dt: torch.dtype, fold: bool) -> Tensor:
+        if not fold:
+            return self._pack.weight([self.projection], dt)
+        H, Ch = self.num_heads, self.out_channels_conv
+        d, dp, hdp = self._fold_dims()
+
+        def build() -> Tensor:
+            we = self._w_edge_heads()
+            wp = self.projection.weight.detach().float()  # [C_out, A]
+            wf = torch.zeros(wp.shape[0], hdp, device=wp.device)
+            wf[:, : H * dp].view(-1, H, dp)[:, :, :d] = torch.einsum("ohc,hca->oha", wp.view(-1, H, Ch), we)
+            return torch.cat([wp, wf], 1).to(dt).contiguous()
+
+        return self._pack.get(("w_proj_fold", dt), [self.projection.weight, self.lin_edge.weight], build)
+
     # -- pieces -------------------------------------------------------------------------------------------------
-    def prepare_edges(self, edge_attr: Tensor) -> Tensor:
-        """Raw edge attributes -> fp32 [E, ceil4(d_e)] operand of the fused lin_edge (after edge_pre_mlp if present)."""
+    def prepare_edges(self, edge_attr: Tensor, dt: torch.dtype = torch.bfloat16) -> Tensor:
+        """Raw edge attributes -> fp32 zero-padded operand of the fused lin_edge (after edge_pre_mlp if present):
+        16 floats per edge for the folded slab kernel, ceil4(d_e) for the in-kernel projection path."""
         if not isinstance(self.edge_pre_mlp, nn.Identity):
             lin = self.edge_pre_mlp[0]
             edge_attr = Fn.fused_linear(self._pack, edge_attr.float() if edge_attr.dtype != torch.float32 else edge_attr, [lin], torch.float32,
                                         gelu=True)  # fmt: skip
-        return Fn.pad_edge_attr(edge_attr)
+        return Fn.pad_edge_attr(edge_attr, ops.ATTN_MAX_EDGE_DIM if self._use_fold(dt) else 0)
 
-    def _attention(self, q: Tensor, k: Tensor, v: Tensor, x_r: Tensor, edge_attr_p: Tensor, csr: ops.GraphCSR, dt: torch.dtype) -> Tensor:
-        """att + x_r, with lin_edge fused into the attention kernel."""
+    def _attend_project(self, xd_n: Tensor, k: Tensor, v: Tensor, dst_layers, edge_attr_p: Tensor, csr: ops.GraphCSR, x_skip: Tensor,
+                        dt: torch.dtype, dst_buf: Optional[Tensor] = None) -> Tensor:  # fmt: skip
+        """dst-side GEMM (q | [k | v |] self | qw) -> attention (+ self) -> projection (+ skip) -> LN -> MLP (+ residual).
+
+        ``dst_layers`` = the Linear containers of the dst-side GEMM *after* lin_query (processor: key, value, self — k and v then
+        come out of the same GEMM and ``k``/``v`` are None; mapper: self only).  ``dst_buf`` lets the processor pass a precomputed GEMM.
+        """
+        A, H = self.attn_channels, self.num_heads
+        fold = self._use_fold(dt)
+        d, dp, hdp = self._fold_dims()
+        layers = [self.lin_query] + list(dst_layers)
+        if dst_buf is None:
+            w, b = self._dst_weight(layers, dt, fold and not self.qk_norm)
+            dst_buf = ops.linear(Fn.as_operand(xd_n, dt, w.shape[1]), w, b)
+        n_lin = len(layers)
+        q = dst_buf[:, :A]
+        x_r = dst_buf[:, (n_lin - 1) * A : n_lin * A]
+        if k is None:
+            k, v = dst_buf[:, A : 2 * A], dst_buf[:, 2 * A : 3 * A]
         if self.qk_norm:
             for t, norm in ((q, self.q_norm), (k, self.k_norm)):
-                ops.layer_norm(t, self._pack.f32(norm.weight), self._pack.f32(getattr(norm, "bias", None)), norm.eps, out=t, groups=self.num_heads)
-        w_e = self._pack.get(("w_edge",), [self.lin_edge.weight], lambda: self.lin_edge.weight.detach().float().contiguous())
+                ops.layer_norm(t, self._pack.f32(norm.weight), self._pack.f32(getattr(norm, "bias", None)), norm.eps, out=t, groups=H)
         b_e = self._pack.f32(self.lin_edge.bias)
-        return ops.gt_attention(q, k, v, csr, self.num_heads, edge_attr=edge_attr_p, w_edge=w_e, b_edge=b_e, add=x_r)
-
-    def _tail(self, att_plus_self: Tensor, x_skip: Tensor, dt: torch.dtype) -> Tensor:
-        """projection(att + x_r) + x_skip ; then MLP(LN(.)) + .   (block.py:1019-1023 / :1268-1271)."""
+        if fold:
+            qw = ops.linear(q, self._qw_blockdiag(dt)) if self.qk_norm else dst_buf[:, n_lin * A :]
+            att = torch.empty((q.shape[0], A + hdp), dtype=dt, device=q.device)
+            if hdp != H * dp:
+                att[:, A + H * dp :].zero_()
+            ops.gt_attention(q, k, v, csr, H, edge_attr=edge_attr_p, b_edge=b_e, qw=qw, abar=att[:, A:], dp=dp, add=x_r, out=att[:, :A])
+        else:
+            w_e = self._pack.get(("w_edge",), [self.lin_edge.weight], lambda: self.lin_edge.weight.detach().float().contiguous())
+            att = ops.gt_attention(q, k, v, csr, H, edge_attr=edge_attr_p, w_edge=w_e, b_edge=b_e, add=x_r)
         skip = x_skip if x_skip.dtype in Fn.SUPPORTED else x_skip.float()
-        out = Fn.fused_linear(self._pack, att_plus_self, [self.projection], dt, residual=skip)
+        out = ops.linear(att, self._proj_weight(dt, fold), self._pack.bias([self.projection]), residual=skip)
         h = Fn.layer_norm_mod(self._pack, self.layer_norm_mlp_dst, out, dt)
         return self.node_dst_mlp.run(h, dt, residual=out)
 
@@ -242,14 +340,20 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
         dt = Fn.compute_dtype(x)
         A = self.attn_channels
         xn = Fn.layer_norm_mod(self._pack, self.layer_norm_attention, x, dt)
-        qkvs = Fn.fused_linear(self._pack, xn, [self.lin_query, self.lin_key, self.lin_value, self.lin_self], dt)
-        q, kv, x_r = qkvs[:, :A], qkvs[:, A : 3 * A], qkvs[:, 3 * A :]
-        # edges strategy, block.py:1148-1183: each rank owns a dst range; it needs the k|v rows of all sources
-        kv_full = gather_rows(kv, shard_info.nodes if shard_info is not None else None, model_comm_group)
+        ea = edge_attr_prepared if edge_attr_prepared is not None else self.prepare_edges(edge_attr, dt)
+        world = group_size(model_comm_group)
+        if world == 1:
+            csr = Fn.csr_for(edge_index, x.shape[0], x.shape[0])
+            return self._attend_project(xn, None, None, [self.lin_key, self.lin_value, self.lin_self], ea, csr, x, dt), edge_attr
+        # edges strategy (block.py:1148-1183): each rank owns a dst range and needs the k | v rows of every source node
+        w, b = self._dst_weight([self.lin_query, self.lin_key, self.lin_value, self.lin_self], dt, self._use_fold(dt) and not self.qk_norm)
+        buf = ops.linear(Fn.as_operand(xn, dt, w.shape[1]), w, b)
+        kv_full = gather_rows(buf[:, A : 3 * A], shard_info.nodes, model_comm_group)
         csr = Fn.csr_for(edge_index, kv_full.shape[0], x.shape[0])
-        ea = edge_attr_prepared if edge_attr_prepared is not None else self.prepare_edges(edge_attr)
-        att = self._attention(q, kv_full[:, :A], kv_full[:, A:], x_r, ea, csr, dt)
-        return self._tail(att, x, dt), edge_attr
+        if self.qk_norm:
+            raise NotImplementedError("qk_norm with a sharded processor")
+        out = self._attend_project(xn, kv_full[:, :A], kv_full[:, A:], [self.lin_key, self.lin_value, self.lin_self], ea, csr, x, dt, dst_buf=buf)
+        return out, edge_attr
 
 
 class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
@@ -290,10 +394,8 @@ class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
         xs_n = Fn.layer_norm_mod(self._pack, self.layer_norm_attention_src, x_src, dt)
         xd_n = Fn.layer_norm_mod(self._pack, self.layer_norm_attention_dest, x_dst, dt)
         kv = Fn.fused_linear(self._pack, xs_n, [self.lin_key, self.lin_value], dt)
-        qs = Fn.fused_linear(self._pack, xd_n, [self.lin_query, self.lin_self], dt)
         csr = Fn.csr_for(edge_index, x_src.shape[0], x_dst.shape[0])
-        att = self._attention(qs[:, :A], kv[:, :A], kv[:, A:], qs[:, A:], self.prepare_edges(edge_attr), csr, dt)
-        dst_new = self._tail(att, x_dst, dt)
+        dst_new = self._attend_project(xd_n, kv[:, :A], kv[:, A:], [self.lin_self], self.prepare_edges(edge_attr, dt), csr, x_dst, dt)
         src_new = x_src
         if self.update_src_nodes:
             h = Fn.layer_norm_mod(self._pack, self.layer_norm_mlp_src, x_src, dt)

@@ -259,6 +259,21 @@ def linear(
     return out
 
 
+ATTN_MAX_EDGE_DIM = 16  # attributes per edge the fused attention kernel accepts (rows zero-padded to this many floats)
+
+
+def attention_fold_supported(channels: int, heads: int, dtype: torch.dtype, edge_dim: int) -> bool:
+    """True if the coalesced slab attention kernel (and with it the folded lin_edge form) handles this shape."""
+    epc = 16 // (2 if dtype == torch.bfloat16 else 4)
+    if channels % heads or channels % epc or edge_dim > ATTN_MAX_EDGE_DIM:
+        return False
+    ch = channels // heads
+    if ch % epc or ch // epc not in (2, 4, 8, 16):
+        return False
+    chunks = channels // epc
+    return chunks < 32 or chunks % 32 == 0
+
+
 def gt_attention(
     q: Tensor,
     k: Tensor,
@@ -269,15 +284,20 @@ def gt_attention(
     edge_attr: Optional[Tensor] = None,
     w_edge: Optional[Tensor] = None,
     b_edge: Optional[Tensor] = None,
+    qw: Optional[Tensor] = None,
+    abar: Optional[Tensor] = None,
+    dp: int = 0,
     add: Optional[Tensor] = None,
     out: Optional[Tensor] = None,
 ) -> Tensor:
     """Edge-softmax attention over the cached CSR.  q [n_dst, H*Ch]; k, v [n_src, H*Ch] (column slices allowed).
 
-    Either ``e_proj`` [E, H*Ch] (materialised lin_edge output, reference operator boundary) or the fused form
-    ``edge_attr`` fp32 [E, d_e] (+ ``w_edge`` fp32 [H*Ch, d_e], ``b_edge`` fp32 [H*Ch]).  ``add`` is summed into the output.
+    Edge term, one of: ``e_proj`` [E, H*Ch] (materialised lin_edge output, the reference operator boundary);
+    ``edge_attr`` fp32 [E, >=d_e] + ``w_edge`` fp32 [H*Ch, d_e] (+ ``b_edge``): projection inside the kernel;
+    ``edge_attr`` fp32 [E, 16] (zero-padded) + ``qw`` / ``abar`` [n_dst, >= H*dp]: folded form (see include/anemoi_b200.h).
+    ``add`` is summed into the output.
     """
-    _need_cuda(q, k, v, e_proj, edge_attr, w_edge, b_edge, add, out)
+    _need_cuda(q, k, v, e_proj, edge_attr, w_edge, b_edge, qw, abar, add, out)
     n_dst, C, ldq = _rows(q)
     n_src, Ck, ldk = _rows(k)
     n_src_v, Cv, ldv = _rows(v)
@@ -292,16 +312,27 @@ def gt_attention(
     _, Co, ldo = _rows(out)
     if Co != C or out.dtype != q.dtype:
         raise ValueError("gt_attention: output mismatch")
-    lde_proj = lde = ldw_e = d_e = ldadd = 0
+    lde_proj = lde = ldw_e = d_e = ldadd = ldqw = ldabar = 0
     if e_proj is not None:
         E, Ce, lde_proj = _rows(e_proj)
         if E != csr.n_edges or Ce != C or e_proj.dtype != q.dtype:
             raise ValueError("gt_attention: e_proj mismatch")
     if edge_attr is not None:
         E, d_e_pad, lde = _rows(edge_attr)
-        Cw, d_e, ldw_e = _rows(w_edge)
-        if E != csr.n_edges or Cw != C or d_e > d_e_pad or edge_attr.dtype != torch.float32 or w_edge.dtype != torch.float32:
-            raise ValueError("gt_attention: fused lin_edge arguments mismatch")
+        if E != csr.n_edges or edge_attr.dtype != torch.float32:
+            raise ValueError("gt_attention: edge_attr must be float32 [E, >= d_e]")
+        if qw is not None:
+            if abar is None or dp <= 0:
+                raise ValueError("gt_attention: folded form needs qw, abar and dp")
+            _, wq, ldqw = _rows(qw)
+            _, wa, ldabar = _rows(abar)
+            if wq < heads * dp or wa < heads * dp or qw.dtype != q.dtype or abar.dtype != q.dtype or qw.shape[0] != n_dst or abar.shape[0] != n_dst:
+                raise ValueError("gt_attention: qw / abar mismatch")
+            d_e = min(dp, d_e_pad)
+        else:
+            Cw, d_e, ldw_e = _rows(w_edge)
+            if Cw != C or d_e > d_e_pad or w_edge.dtype != torch.float32:
+                raise ValueError("gt_attention: fused lin_edge arguments mismatch")
     if add is not None:
         na, Ca, ldadd = _rows(add)
         if (na, Ca) != (n_dst, C) or add.dtype != q.dtype:
@@ -313,7 +344,8 @@ def gt_attention(
     with _Timed("gt_attention", aflops, abytes):
         rc = _lib.load().anemoi_b200_gt_attention_fwd(
             _ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(e_proj), lde_proj, _ptr(edge_attr), lde, d_e, _ptr(w_edge), ldw_e, _ptr(_f32(b_edge)),
-            _ptr(csr.src32), _ptr(csr.colptr32), _ptr(add), ldadd, _ptr(out), ldo, n_dst, heads, C // heads, dtype_code(q.dtype), _stream())  # fmt: skip
+            _ptr(qw), ldqw, _ptr(abar), ldabar, dp, _ptr(csr.src32), _ptr(csr.colptr32), _ptr(add), ldadd, _ptr(out), ldo, n_dst, heads,
+            C // heads, dtype_code(q.dtype), _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_gt_attention_fwd")
     return out
 

@@ -86,16 +86,21 @@ ANEMOI_API int anemoi_b200_linear(const void* A, int64_t lda, const void* W, int
  * (`anemoi::graph_transformer_attention`), optionally fused with lin_edge (block.py:623-635):
  *   out[d,h,:] = sum_e alpha[e,h] (v[src_e,h,:] + eproj[e,h,:]) (+ add[d,h,:]),
  *   alpha = softmax over edges into d of  q[d,h,:].(k[src_e,h,:] + eproj[e,h,:]) / sqrt(Ch)
- * with eproj either materialised (`e`, [E, H*Ch] of `dtype`) or computed in-kernel from the raw edge
- * attributes: eproj[e] = w_edge . edge_attr[e] + b_edge  (edge_attr fp32 [E, lde], w_edge fp32 [H*Ch, ldw_e]).
- * Zero in-degree rows give 0 (+ add), like gt.py:112-119.  fp32 online softmax.
- *   q [n_dst, ldq], k,v [n_src, ldk/ldv], add/out [n_dst, ld*] of `dtype`; src32/colptr32 from csr_build.
+ * Zero in-degree rows give 0 (+ add), like gt.py:112-119.  fp32 online softmax.  Three forms of the edge term:
+ *   (1) materialised: `e` = eproj [E, H*Ch] of `dtype` (the reference operator boundary);
+ *   (2) in-kernel projection: edge_attr fp32 [E, lde] + w_edge fp32 [H*Ch, ldw_e] + b_edge -> eproj = w_edge.a + b_edge;
+ *   (3) folded (the fast path, eproj is linear in a):  q.(W a + b) = (W^T q).a + const  and
+ *       sum alpha (W a + b) = W (sum alpha a) + b, so the caller passes qw[d,h,:dp] = W_h^T q[d,h,:] (extra columns of the q GEMM)
+ *       and receives abar[d,h,:dp] = sum_e alpha a_e, which it feeds to the projection GEMM through W; the kernel adds b_edge.
+ *       The [E, H*Ch] edge tensor (the largest tensor of the layer in the reference) never exists.  Needs edge_dim <= 16
+ *       and edge_attr rows zero-padded to lde >= 16.
+ *   q [n_dst, ldq], k,v [n_src, ldk/ldv], add/out [n_dst, ld*], qw/abar [n_dst, >= heads*dp] of `dtype`; src32/colptr32 from csr_build.
  */
 ANEMOI_API int anemoi_b200_gt_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* e,
                                  int64_t lde_proj, const float* edge_attr, int64_t lde, int64_t edge_dim, const float* w_edge,
-                                 int64_t ldw_e, const float* b_edge, const int32_t* src32, const int32_t* colptr32,
-                                 const void* add, int64_t ldadd, void* out, int64_t ldo, int64_t n_dst, int64_t heads, int64_t ch,
-                                 int dtype, void* stream);
+                                 int64_t ldw_e, const float* b_edge, const void* qw, int64_t ldqw, void* abar, int64_t ldabar, int64_t dp,
+                                 const int32_t* src32, const int32_t* colptr32, const void* add, int64_t ldadd, void* out, int64_t ldo,
+                                 int64_t n_dst, int64_t heads, int64_t ch, int dtype, void* stream);
 
 /* -- GraphConv tail: LayerNorm + residual + dst-segmented sum ------------------------------------------------
  * Replaces the tail of layers/conv.py:73-81: e'[i] = LN(h[i]) + e[i]  (written to e_new) and

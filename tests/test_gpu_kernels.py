@@ -192,6 +192,46 @@ def test_gt_attention_modes(ops, H, Ch, dt):
     assert torch.equal(out2[-3:].float().cpu(), add[-3:].float())  # zero in-degree rows: exactly 0 + add
 
 
+@pytest.mark.parametrize("H,Ch,d_e", [(16, 32, 11), (16, 64, 11), (4, 16, 3), (8, 64, 16), (2, 32, 5)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_gt_attention_folded_lin_edge(ops, H, Ch, d_e, dt):
+    """Folded form (include/anemoi_b200.h form 3, the path the blocks use): qw = W_e,h^T q_h in, abar = sum alpha a out;
+    out + W_e abar must equal attention with the materialised projection.  Strided q|k|v|self|qw buffer like the block's."""
+    if not ops.attention_fold_supported(H * Ch, H, dt, d_e):
+        pytest.skip("shape served by the generic kernel")
+    g = torch.Generator().manual_seed(H * 1000 + Ch + d_e)
+    n_src, n_dst, E = 300, 301, 2600
+    ei = _rand_graph(n_src, n_dst, E, 13, zero_tail=5)
+    C = H * Ch
+    dp = (d_e + 3) // 4 * 4
+    a = torch.randn(E, d_e, generator=g)
+    w_e, b_e = torch.randn(C, d_e, generator=g) / 3, torch.randn(C, generator=g)
+    buf = torch.randn(n_dst, 2 * C + H * dp, generator=g)  # q | self | qw
+    k = torch.randn(n_src, C, generator=g).to(dt)
+    v = torch.randn(n_src, C, generator=g).to(dt)
+    q32 = buf[:, :C].to(dt).float()
+    qw = torch.zeros(n_dst, H, dp)
+    qw[:, :, :d_e] = torch.einsum("nhc,hca->nha", q32.view(n_dst, H, Ch), w_e.view(H, Ch, d_e))
+    buf[:, 2 * C :] = qw.view(n_dst, -1)
+    buf = buf.to(dt).cuda()
+    a16 = torch.zeros(E, 16)
+    a16[:, :d_e] = a
+    csr = ops.build_csr(ei.cuda(), n_src, n_dst)
+    out = torch.empty(n_dst, C + H * dp, dtype=dt, device="cuda")
+    ops.gt_attention(buf[:, :C], k.cuda(), v.cuda(), csr, H, edge_attr=a16.cuda(), b_edge=b_e.cuda(), qw=buf[:, 2 * C :], abar=out[:, C:], dp=dp,
+                     add=buf[:, C : 2 * C], out=out[:, :C])  # fmt: skip
+    o = out.float().cpu()
+    abar = o[:, C:].view(n_dst, H, dp)[:, :, :d_e]
+    full = o[:, :C] + torch.einsum("nha,hca->nhc", abar, w_e.view(H, Ch, d_e)).reshape(n_dst, C)
+    sh = lambda t, n: t.float().view(n, H, Ch)
+    ref = R.gt_attention(sh(q32, n_dst), sh(k, n_src), sh(v, n_src), (a @ w_e.t() + b_e).view(E, H, Ch), ei, n_dst).view(n_dst, C)
+    ref = ref + buf[:, C : 2 * C].float().cpu()
+    tol = 3e-4 if dt == torch.float32 else 2**-5 * ref.abs().max().item()
+    assert (full - ref).abs().max().item() <= tol
+    assert torch.equal(o[-5:, :C], buf[-5:, C : 2 * C].float().cpu())  # zero in-degree: 0 + add, no bias
+    assert torch.all(o[-5:, C:] == 0)
+
+
 def test_gt_attention_strided_qkv(ops):
     """q|k|v|self as column slices of one [N, 4C] buffer (the block layout)."""
     g = torch.Generator().manual_seed(9)

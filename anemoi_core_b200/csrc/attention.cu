@@ -117,14 +117,14 @@ __global__ void __launch_bounds__(128, 3) gt_attention_slab_kernel(const AttnPar
 #pragma unroll
     for (int j = 0; j < NCH; ++j) qw_off[j] = ((slab * SLAB + (j * 32 + lane_eff) * EPC) / p.ch) * p.dp + sub;
     uint4 q_raw[NCH];
-    float qw_raw[NCH][NA];
+    T qw_raw[NCH][NA];  // raw (unconverted) so that the prefetch does not wait on its own load
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
       q_raw[j] = ldg16(qp + n0 * ldq_b + lane_off + j * 512);
       if constexpr (MODE == 2) {
 #pragma unroll
         for (int t = 0; t < NA; ++t)
-          qw_raw[j][t] = (t < na && sub + t * LPH < p.dp) ? to_f32<T>(reinterpret_cast<const T*>(p.qw)[n0 * p.ldqw + qw_off[j] + t * LPH]) : 0.f;
+          qw_raw[j][t] = (t < na && sub + t * LPH < p.dp) ? reinterpret_cast<const T*>(p.qw)[n0 * p.ldqw + qw_off[j] + t * LPH] : from_f32<T>(0.f);
       }
     }
 
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(128, 3) gt_attention_slab_kernel(const AttnPar
 #pragma unroll
         for (int i = 0; i < EPC; ++i) q[j][i] *= qscale, acc[j][i] = 0.f;
 #pragma unroll
-        for (int t = 0; t < NA; ++t) qw[j][t] = MODE == 2 ? qw_raw[j][t] * qscale : 0.f, abar[j][t] = 0.f;
+        for (int t = 0; t < NA; ++t) qw[j][t] = MODE == 2 ? to_f32<T>(qw_raw[j][t]) * qscale : 0.f, abar[j][t] = 0.f;
       }
       if (nd + 1 < nn) {  // prefetch the next node's q / qw
 #pragma unroll
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(128, 3) gt_attention_slab_kernel(const AttnPar
           if constexpr (MODE == 2) {
 #pragma unroll
             for (int t = 0; t < NA; ++t)
-              if (t < na && sub + t * LPH < p.dp) qw_raw[j][t] = to_f32<T>(reinterpret_cast<const T*>(p.qw)[(d + 1) * p.ldqw + qw_off[j] + t * LPH]);
+              if (t < na && sub + t * LPH < p.dp) qw_raw[j][t] = reinterpret_cast<const T*>(p.qw)[(d + 1) * p.ldqw + qw_off[j] + t * LPH];
           }
         }
       }

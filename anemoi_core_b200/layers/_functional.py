@@ -55,7 +55,7 @@ class WeightPack:
         hit = self._store.get(key)
         if hit is not None and hit[0] == sig:
             return hit[1]
-        with torch.no_grad():
+        with torch.no_grad(), torch.autocast("cuda", enabled=False):  # derived weights are built in fp32, never under autocast
             val = build()
         self._store[key] = (sig, val)
         return val

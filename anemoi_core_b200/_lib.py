@@ -15,7 +15,8 @@ from ctypes import c_int64
 from ctypes import c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libanemoi_b200.so")
+# ANEMOI_B200_LIB selects another build of the same library (A/B kernel experiments); the default is the in-tree build.
+LIB_PATH = os.environ.get("ANEMOI_B200_LIB") or os.path.join(_HERE, "lib", "libanemoi_b200.so")
 
 F32, BF16 = 0, 1
 EPI_GELU = 1

@@ -53,8 +53,17 @@ struct AttnParams {
 //         abar[d,h,:] = sum_e alpha_e a_e (W_e is applied to it inside the projection GEMM); the attribute index space is
 //         split over the LPH lanes of a head (lane o owns attributes o, o+LPH, ...), so the per-edge cost of the edge term
 //         is ceil(D/LPH) loads and 2*ceil(D/LPH) FMAs per lane and rides on the score's shuffle reduction.
-constexpr int kNodesPerRange = 8;
-constexpr int kBatch = 4;
+#ifndef ATTN_NODES_PER_RANGE
+#define ATTN_NODES_PER_RANGE 8
+#endif
+#ifndef ATTN_BATCH
+#define ATTN_BATCH 4
+#endif
+#ifndef ATTN_MINBLOCKS
+#define ATTN_MINBLOCKS 3
+#endif
+[[maybe_unused]] constexpr int kNodesPerRange = ATTN_NODES_PER_RANGE;
+constexpr int kBatch = ATTN_BATCH;
 
 template <typename T>
 struct ChunkT {
@@ -81,7 +90,7 @@ struct ChunkT {
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 template <typename T, int NCH, int LPH, int MODE>
-__global__ void __launch_bounds__(128, 3) gt_attention_slab_kernel(const AttnParams p, int n_slabs, int active_lanes) {
+__global__ void __launch_bounds__(128, ATTN_MINBLOCKS) gt_attention_slab_kernel(const AttnParams p, int n_slabs, int active_lanes) {
   using CT = ChunkT<T>;
   constexpr int EPC = CT::EPC;
   constexpr int NA = (kMaxEdgeDim + LPH - 1) / LPH;  // attribute slots per lane (upper bound; `na` of them are live)
@@ -117,14 +126,14 @@ __global__ void __launch_bounds__(128, 3) gt_attention_slab_kernel(const AttnPar
 #pragma unroll
     for (int j = 0; j < NCH; ++j) qw_off[j] = ((slab * SLAB + (j * 32 + lane_eff) * EPC) / p.ch) * p.dp + sub;
     uint4 q_raw[NCH];
-    T qw_raw[NCH][NA];  // raw (unconverted) so that the prefetch does not wait on its own load
+    float qw_raw[NCH][NA];
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
       q_raw[j] = ldg16(qp + n0 * ldq_b + lane_off + j * 512);
       if constexpr (MODE == 2) {
 #pragma unroll
         for (int t = 0; t < NA; ++t)
-          qw_raw[j][t] = (t < na && sub + t * LPH < p.dp) ? reinterpret_cast<const T*>(p.qw)[n0 * p.ldqw + qw_off[j] + t * LPH] : from_f32<T>(0.f);
+          qw_raw[j][t] = (t < na && sub + t * LPH < p.dp) ? to_f32<T>(reinterpret_cast<const T*>(p.qw)[n0 * p.ldqw + qw_off[j] + t * LPH]) : 0.f;
       }
     }
 
@@ -139,7 +148,7 @@ __global__ void __launch_bounds__(128, 3) gt_attention_slab_kernel(const AttnPar
 #pragma unroll
         for (int i = 0; i < EPC; ++i) q[j][i] *= qscale, acc[j][i] = 0.f;
 #pragma unroll
-        for (int t = 0; t < NA; ++t) qw[j][t] = MODE == 2 ? to_f32<T>(qw_raw[j][t]) * qscale : 0.f, abar[j][t] = 0.f;
+        for (int t = 0; t < NA; ++t) qw[j][t] = MODE == 2 ? qw_raw[j][t] * qscale : 0.f, abar[j][t] = 0.f;
       }
       if (nd + 1 < nn) {  // prefetch the next node's q / qw
 #pragma unroll
@@ -148,7 +157,7 @@ __global__ void __launch_bounds__(128, 3) gt_attention_slab_kernel(const AttnPar
           if constexpr (MODE == 2) {
 #pragma unroll
             for (int t = 0; t < NA; ++t)
-              if (t < na && sub + t * LPH < p.dp) qw_raw[j][t] = reinterpret_cast<const T*>(p.qw)[(d + 1) * p.ldqw + qw_off[j] + t * LPH];
+              if (t < na && sub + t * LPH < p.dp) qw_raw[j][t] = to_f32<T>(reinterpret_cast<const T*>(p.qw)[(d + 1) * p.ldqw + qw_off[j] + t * LPH]);
           }
         }
       }
@@ -291,6 +300,283 @@ __global__ void __launch_bounds__(128, 3) gt_attention_slab_kernel(const AttnPar
   }
 }
 
+// ---- pipelined kernel (cp.async ring) ----------------------------------------------------------------------------
+// Same lane/chunk layout as the slab kernel, but the gathered rows no longer land in registers: every warp owns a ring of
+// kSlots shared-memory slots and streams the k | v row segments (and the 64-byte attribute row, or the materialised e segment)
+// of its edges into it with 16-byte cp.async (LDGSTS), kSlots - kBatch .. kSlots edges ahead of the arithmetic and ACROSS
+// destination-node boundaries: the edges of a contiguous dst range are one contiguous run of the dst-sorted edge list.
+// Bytes in flight are bounded by shared memory (kSlots x 2 KB per warp) instead of the register file, so the warp never waits
+// on a gather it has just issued; one cp.async group per edge (empty groups past the end keep the count uniform) and
+// cp.async.wait_group<kSlots - kBatch> before a batch is consumed.
+// Work split: each warp takes a contiguous range of dst nodes holding ~E / (#warps) edges (boundaries by a warp-wide 32-ary
+// search of colptr), so there is no per-range pipeline restart and the load is balanced by edges.
+#ifndef ATTN_SLOTS
+#define ATTN_SLOTS 6
+#endif
+#ifndef ATTN_PIPE_MINBLOCKS
+#define ATTN_PIPE_MINBLOCKS 4
+#endif
+constexpr int kSlots = ATTN_SLOTS;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds16(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// first n in [0, n_dst] with colptr[n] >= x (colptr non-decreasing, colptr[n_dst] = E); warp-wide 32-ary search
+__device__ __forceinline__ int colptr_lower_bound(const int32_t* __restrict__ colptr, int n_dst, int x, int lane) {
+  int lo = 0, hi = n_dst;  // answer in [lo, hi]
+  while (hi - lo > 0) {
+    const int span = hi - lo;
+    const int step = (span + 31) / 32;
+    const int pos = min(lo + lane * step, hi);
+    const bool ge = __ldg(colptr + pos) >= x;
+    const unsigned m = __ballot_sync(0xffffffffu, ge);
+    if (m == 0) {  // all probed positions < x: answer beyond the last probe
+      lo = min(lo + 31 * step, hi) + 1;
+      if (lo > hi) return hi;  // cannot happen when colptr[hi] >= x
+    } else {
+      const int f = __ffs(m) - 1;  // first probe with colptr >= x
+      hi = min(lo + f * step, hi);
+      lo = f == 0 ? hi : min(lo + (f - 1) * step, hi) + 1;
+      if (lo > hi) lo = hi;
+    }
+  }
+  return lo;
+}
+
+template <typename T, int NCH, int LPH, int MODE>
+__global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_kernel(const AttnParams p, int n_slabs, int active_lanes) {
+  using CT = ChunkT<T>;
+  constexpr int EPC = CT::EPC;
+  constexpr int NA = (kMaxEdgeDim + LPH - 1) / LPH;
+  constexpr int SLAB = NCH * 32 * EPC;
+  constexpr int kKV = NCH * 512;                                          // bytes of one k (or v) row segment
+  constexpr int kSlotBytes = 2 * kKV + (MODE == 2 ? 64 : kKV);             // k | v | attributes-or-e
+  extern __shared__ __align__(16) uint8_t smem_ring[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const bool active = lane < active_lanes;
+  const int lane_eff = active ? lane : 0;
+  const int sub = lane & (LPH - 1);
+  const int na = MODE == 2 ? (p.edge_dim + LPH - 1) / LPH : 0;
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem_ring) + (uint32_t)(wib * kSlots * kSlotBytes);
+  const char* __restrict__ qp = reinterpret_cast<const char*>(p.q);
+  const char* __restrict__ kp = reinterpret_cast<const char*>(p.k);
+  const char* __restrict__ vp = reinterpret_cast<const char*>(p.v);
+  const char* __restrict__ ep = reinterpret_cast<const char*>(p.e);
+  const int64_t ldq_b = p.ldq * (int64_t)sizeof(T), ldk_b = p.ldk * (int64_t)sizeof(T), ldv_b = p.ldv * (int64_t)sizeof(T);
+  const int64_t lde_b = p.lde_proj * (int64_t)sizeof(T);
+  const float qscale = p.scale * 1.4426950408889634f;
+
+  // ---- this warp's (slab, dst range) ----
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int w = blockIdx.x * (blockDim.x >> 5) + wib;
+  const int slab = w % n_slabs, r = w / n_slabs, R = warps_total / n_slabs;
+  if (r >= R) return;
+  const int n_edges = __ldg(p.colptr + p.n_dst);
+  const int lo_e = (int)((int64_t)n_edges * r / R), hi_e = (int)((int64_t)n_edges * (r + 1) / R);
+  const int n_lo = r == 0 ? 0 : colptr_lower_bound(p.colptr, (int)p.n_dst, lo_e, lane);
+  const int n_hi = r == R - 1 ? (int)p.n_dst : colptr_lower_bound(p.colptr, (int)p.n_dst, hi_e, lane);
+  if (n_lo >= n_hi) return;
+  const int64_t lane_off = ((int64_t)slab * SLAB + (int64_t)lane_eff * EPC) * (int64_t)sizeof(T);
+  const int E0 = __ldg(p.colptr + n_lo), E1 = __ldg(p.colptr + n_hi);
+
+  // ---- producer state: src ids streamed in blocks of 32, one cp.async group per edge ----
+  int pe = E0;  // next edge to issue
+  int pblk = E0;
+  int psrc = (pblk + lane < E1) ? __ldg(p.src + pblk + lane) : 0;
+  int psrc_n = (pblk + 32 + lane < E1) ? __ldg(p.src + pblk + 32 + lane) : 0;
+  auto issue = [&]() {
+    if (pe < E1) {
+      if (pe - pblk >= 32) {
+        pblk += 32;
+        psrc = psrc_n;
+        psrc_n = (pblk + 32 + lane < E1) ? __ldg(p.src + pblk + 32 + lane) : 0;
+      }
+      const int sid = __shfl_sync(0xffffffffu, psrc, pe - pblk);
+      const uint32_t slot = ring + (uint32_t)(((pe - E0) % kSlots) * kSlotBytes);
+      const char* kr = kp + (int64_t)sid * ldk_b + lane_off;
+      const char* vr = vp + (int64_t)sid * ldv_b + lane_off;
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        cp_async16(slot + j * 512 + lane * 16, kr + j * 512);
+        cp_async16(slot + kKV + j * 512 + lane * 16, vr + j * 512);
+      }
+      if constexpr (MODE == 2) {
+        if (lane < 4) cp_async16(slot + 2 * kKV + lane * 16, p.edge_attr + (int64_t)pe * p.lde + lane * 4);
+      } else {
+        if (ep) {
+#pragma unroll
+          for (int j = 0; j < NCH; ++j) cp_async16(slot + 2 * kKV + j * 512 + lane * 16, ep + (int64_t)pe * lde_b + lane_off + j * 512);
+        }
+      }
+      ++pe;
+    }
+    cp_async_commit();  // empty past the end: keeps "groups issued = edges consumed + kSlots" uniform
+  };
+#pragma unroll 1
+  for (int i = 0; i < kSlots; ++i) issue();
+
+  int qw_off[NCH];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) qw_off[j] = ((slab * SLAB + (j * 32 + lane_eff) * EPC) / p.ch) * p.dp + sub;
+
+  int cbase = n_lo;  // colptr block: lanes hold colptr[cbase + lane]
+  int cp = __ldg(p.colptr + min(cbase + lane, n_hi));
+  for (int d = n_lo; d < n_hi; ++d) {
+    if (d - cbase >= 31) {
+      cbase = d;
+      cp = __ldg(p.colptr + min(cbase + lane, n_hi));
+    }
+    const int e0 = __shfl_sync(0xffffffffu, cp, d - cbase), e1 = __shfl_sync(0xffffffffu, cp, d - cbase + 1);
+    float q[NCH][EPC], acc[NCH][EPC], m_i[NCH], l_i[NCH], qw[NCH][NA], abar[NCH][NA];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      CT::unpack(ldg16(qp + (int64_t)d * ldq_b + lane_off + j * 512), q[j]);
+      m_i[j] = -INFINITY, l_i[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < EPC; ++i) q[j][i] *= qscale, acc[j][i] = 0.f;
+#pragma unroll
+      for (int t = 0; t < NA; ++t) {
+        abar[j][t] = 0.f;
+        qw[j][t] = 0.f;
+        if constexpr (MODE == 2) {
+          if (t < na && sub + t * LPH < p.dp) qw[j][t] = to_f32<T>(reinterpret_cast<const T*>(p.qw)[(int64_t)d * p.ldqw + qw_off[j] + t * LPH]) * qscale;
+        }
+      }
+    }
+    for (int eb = e0; eb < e1; eb += kBatch) {
+      const int nb = min(kBatch, e1 - eb);
+      cp_async_wait<kSlots - kBatch>();  // edges eb .. eb+kBatch-1 have landed (this lane's copies)
+      __syncwarp();                      // ... and every other lane's
+      float sc[kBatch][NCH], at[kBatch][NA];
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const uint32_t slot = ring + (uint32_t)(((min(eb + b, e1 - 1) - E0) % kSlots) * kSlotBytes);
+        if constexpr (MODE == 2) {
+#pragma unroll
+          for (int t = 0; t < NA; ++t) at[b][t] = t < na ? lds32f(slot + 2 * kKV + (sub + t * LPH) * 4) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          float kf[EPC];
+          CT::unpack(lds16(slot + j * 512 + lane * 16), kf);
+          float t = 0.f;
+          if constexpr (MODE == 1) {
+            if (ep) {
+              float ef[EPC];
+              CT::unpack(lds16(slot + 2 * kKV + j * 512 + lane * 16), ef);
+#pragma unroll
+              for (int i = 0; i < EPC; ++i) kf[i] += ef[i];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < EPC; ++i) t += q[j][i] * kf[i];
+          if constexpr (MODE == 2) {
+#pragma unroll
+            for (int tt = 0; tt < NA; ++tt)
+              if (tt < na) t += qw[j][tt] * at[b][tt];
+          }
+#pragma unroll
+          for (int o = 1; o < LPH; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          sc[b][j] = b < nb ? t : -INFINITY;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        float mx = m_i[j];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) mx = fmaxf(mx, sc[b][j]);
+        const float corr = exp2f(m_i[j] - mx);
+        float wgt[kBatch], wsum = 0.f;
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) wgt[b] = exp2f(sc[b][j] - mx), wsum += wgt[b];
+        l_i[j] = l_i[j] * corr + wsum;
+        m_i[j] = mx;
+#pragma unroll
+        for (int i = 0; i < EPC; ++i) acc[j][i] *= corr;
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+          const uint32_t slot = ring + (uint32_t)(((min(eb + b, e1 - 1) - E0) % kSlots) * kSlotBytes);
+          float vf[EPC];
+          CT::unpack(lds16(slot + kKV + j * 512 + lane * 16), vf);
+          if constexpr (MODE == 1) {
+            if (ep) {
+              float ef[EPC];
+              CT::unpack(lds16(slot + 2 * kKV + j * 512 + lane * 16), ef);
+#pragma unroll
+              for (int i = 0; i < EPC; ++i) vf[i] += ef[i];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < EPC; ++i) acc[j][i] += wgt[b] * vf[i];
+        }
+        if constexpr (MODE == 2) {
+#pragma unroll
+          for (int t = 0; t < NA; ++t)
+            if (t < na) {
+              float s2 = abar[j][t] * corr;
+#pragma unroll
+              for (int b = 0; b < kBatch; ++b) s2 += wgt[b] * at[b][t];
+              abar[j][t] = s2;
+            }
+        }
+      }
+      __syncwarp();  // all lanes are done reading these slots before they are refilled
+      for (int i = 0; i < nb; ++i) issue();
+    }
+    // ---- finalise node d ----
+    const bool has_edges = e1 > e0;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      float o[EPC];
+      const float inv = has_edges ? 1.0f / l_i[j] : 0.f;
+#pragma unroll
+      for (int i = 0; i < EPC; ++i) o[i] = acc[j][i] * inv;
+      if constexpr (MODE == 2) {
+        if (has_edges && p.b_edge) {
+          const float* bp = p.b_edge + slab * SLAB + (j * 32 + lane_eff) * EPC;
+#pragma unroll
+          for (int i = 0; i < EPC; i += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(bp + i));
+            o[i] += bv.x, o[i + 1] += bv.y, o[i + 2] += bv.z, o[i + 3] += bv.w;
+          }
+        }
+        if (active) {
+#pragma unroll
+          for (int t = 0; t < NA; ++t)
+            if (t < na && sub + t * LPH < p.dp)
+              reinterpret_cast<T*>(p.abar)[(int64_t)d * p.ldabar + qw_off[j] + t * LPH] = from_f32<T>(abar[j][t] * inv);
+        }
+      }
+      if (active) {
+        if (p.add) {
+          float rr[EPC];
+          CT::unpack(ldg16(reinterpret_cast<const char*>(p.add) + ((int64_t)d * p.ldadd) * (int64_t)sizeof(T) + lane_off + j * 512), rr);
+#pragma unroll
+          for (int i = 0; i < EPC; ++i) o[i] += rr[i];
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<char*>(p.out) + ((int64_t)d * p.ldo) * (int64_t)sizeof(T) + lane_off + j * 512) = CT::pack(o);
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
 // Generic shapes (any H, Ch <= 256, any alignment): one warp per (dst, head), lanes stride over the head's channels.
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) gt_attention_generic_kernel(const AttnParams p) {
@@ -359,18 +645,43 @@ __global__ void __launch_bounds__(256) gt_attention_generic_kernel(const AttnPar
   }
 }
 
+template <typename T, int NCH, int LPH, int MODE>
+static int launch_pipe_mode(const AttnParams& p, int n_slabs, int active_lanes, cudaStream_t s) {
+  constexpr int kSlotBytes = 2 * NCH * 512 + (MODE == 2 ? 64 : NCH * 512);
+  constexpr int smem = 4 * kSlots * kSlotBytes;  // 4 warps per CTA
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    cudaError_t e = cudaFuncSetAttribute(gt_attention_pipe_kernel<T, NCH, LPH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attention)");
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, gt_attention_pipe_kernel<T, NCH, LPH, MODE>, 128, smem);
+    if (e != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 1;
+  }
+  // one persistent wave; every warp gets ~E/#warps edges; #warps must be a multiple of n_slabs (4 | warps, n_slabs in {1,2,4,...})
+  int64_t blocks = (int64_t)num_sms() * blocks_per_sm;
+  const int64_t max_useful = (p.n_dst * n_slabs + 3) / 4;
+  if (blocks > max_useful) blocks = max_useful;
+  while ((blocks * 4) % n_slabs) ++blocks;
+  gt_attention_pipe_kernel<T, NCH, LPH, MODE><<<(unsigned)blocks, 128, smem, s>>>(p, n_slabs, active_lanes);
+  return launch_status("gt_attention_pipe_kernel");
+}
+
 template <typename T, int NCH, int LPH>
 static int launch_slab(const AttnParams& p, int mode, int n_slabs, int active_lanes, cudaStream_t s) {
+#ifdef ATTN_USE_SLAB_KERNEL
   const int64_t items = ((p.n_dst + kNodesPerRange - 1) / kNodesPerRange) * n_slabs;
   const int warps_per_block = 4;
   int64_t blocks = (items + warps_per_block - 1) / warps_per_block;
-  const int64_t cap = (int64_t)num_sms() * 3;  // 3 resident CTAs per SM (168 registers x 128 threads), persistent over the items
+  const int64_t cap = (int64_t)num_sms() * ATTN_MINBLOCKS;  // resident CTAs per SM (register-limited), persistent over the items
   if (blocks > cap) blocks = cap;
   if (mode == 2)
     gt_attention_slab_kernel<T, NCH, LPH, 2><<<(unsigned)blocks, 128, 0, s>>>(p, n_slabs, active_lanes);
   else
     gt_attention_slab_kernel<T, NCH, LPH, 1><<<(unsigned)blocks, 128, 0, s>>>(p, n_slabs, active_lanes);
   return launch_status("gt_attention_slab_kernel");
+#else
+  return mode == 2 ? launch_pipe_mode<T, NCH, LPH, 2>(p, n_slabs, active_lanes, s)
+                   : launch_pipe_mode<T, NCH, LPH, 1>(p, n_slabs, active_lanes, s);
+#endif
 }
 
 template <typename T, int NCH>

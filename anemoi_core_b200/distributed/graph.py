@@ -47,6 +47,17 @@ def gather_rows(x: Tensor, sizes: Optional[list[int]], group: Optional[dist.Proc
     out = torch.empty((sum(sizes),) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     if len(set(sizes)) == 1:
         dist.all_gather_into_tensor(out, x, group=group)
+    elif dist.get_backend(group) == "nccl":
+        dist.all_gather(list(torch.split(out, sizes, dim=0)), x, group=group)  # NCCL handles unequal shards (grouped send/recv)
     else:
-        dist.all_gather(list(torch.split(out, sizes, dim=0)), x, group=group)
+        # Gloo needs equal shapes: pad every shard to the largest one, like the reference (primitives.py:170-183)
+        m = max(sizes)
+        padded = x.new_zeros((m,) + tuple(x.shape[1:]))
+        padded[: x.shape[0]] = x
+        buf = x.new_empty((world * m,) + tuple(x.shape[1:]))
+        dist.all_gather_into_tensor(buf, padded, group=group)
+        off = 0
+        for r, n in enumerate(sizes):
+            out[off : off + n] = buf[r * m : r * m + n]
+            off += n
     return out

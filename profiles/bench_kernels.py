@@ -1,0 +1,75 @@
+"""Isolated kernel timings at cfg2 shapes (ico-6 mesh, C=512, H=16, bf16): attention (folded lin_edge) and the four
+per-layer GEMMs.  CUDA events, L2 flushed before every timed launch, median of N.  Usage (on the GPU box):
+    python profiles/bench_kernels.py [attn] [gemm] [--reps 30]
+Prints one JSON line per kernel with us, achieved GB/s or TFLOP/s and the fraction of the measured peaks."""
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from anemoi_core_b200 import ops  # noqa: E402
+from anemoi_core_b200.synthetic import build_graph  # noqa: E402
+
+reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 30
+which = [a for a in sys.argv[1:] if not a.startswith("--") and not a.isdigit()] or ["attn", "gemm"]
+pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+dev = torch.device("cuda")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    return statistics.median(ts), min(ts)
+
+
+g = torch.Generator().manual_seed(0)
+if "attn" in which:
+    gr = build_graph("o96", 6)
+    N, E, H, Ch, dp = gr["n_mesh"], gr["proc_index"].shape[1], 16, 32, 12
+    C = H * Ch
+    csr = ops.build_csr(gr["proc_index"].to(dev), N, N)
+    buf = torch.randn(N, 4 * C + H * dp, generator=g).to(torch.bfloat16).to(dev)
+    ea = torch.zeros(E, 16)
+    ea[:, :11] = gr["proc_attr"]
+    ea = ea.to(dev)
+    b_e = torch.randn(C, generator=g).to(dev)
+    out = torch.empty(N, C + H * dp, dtype=torch.bfloat16, device=dev)
+
+    def attn():
+        ops.gt_attention(buf[:, :C], buf[:, C : 2 * C], buf[:, 2 * C : 3 * C], csr, H, edge_attr=ea, b_edge=b_e, qw=buf[:, 4 * C :], abar=out[:, C:], dp=dp,
+                         add=buf[:, 3 * C : 4 * C], out=out[:, :C])  # fmt: skip
+
+    med, mn = timeit(attn)
+    # algorithmic bytes: q, k, v, self read + out written (N*C*2 each) + qw/abar + per edge: src id 4 B + 64 B attributes
+    alg = 5 * N * C * 2 + 2 * N * H * dp * 2 + E * (4 + 64) + 4 * N
+    print(json.dumps({"kernel": "gt_attention(folded)", "us_median": round(med, 1), "us_min": round(mn, 1), "alg_MB": round(alg / 1e6, 1),
+                      "GBs": round(alg / med / 1e3, 1), "frac_hbm_measured": round(alg / med / 1e3 / pk["hbm_gbs"], 3),
+                      "gathered_MB": round(E * 2 * C * 2 / 1e6, 1)}))  # fmt: skip
+
+if "gemm" in which:
+    M = 40962
+    for name, N_, K, gelu, res in (("qkv+self+qw", 2240, 512, False, False), ("projection", 512, 704, False, True), ("mlp1+gelu", 2048, 512, True, False),
+                                   ("mlp2+res", 512, 2048, False, True)):  # fmt: skip
+        a = torch.randn(M, K, generator=g).to(torch.bfloat16).to(dev)
+        w = (torch.randn(N_, K, generator=g) / K**0.5).to(torch.bfloat16).to(dev)
+        bias = torch.randn(N_, generator=g).to(dev)
+        r = torch.randn(M, N_, generator=g).to(torch.bfloat16).to(dev) if res else None
+        o = torch.empty(M, N_, dtype=torch.bfloat16, device=dev)
+        med, mn = timeit(lambda: ops.linear(a, w, bias, gelu=gelu, residual=r, out=o))
+        fl = 2.0 * M * N_ * K
+        print(json.dumps({"kernel": f"linear {name} [{M}x{K}]x[{K}x{N_}]", "us_median": round(med, 1), "us_min": round(mn, 1),
+                          "TFLOPs": round(fl / med / 1e6, 1), "frac_tensor_burst": round(fl / med / 1e6 / pk["bf16_tflops"], 3)}))  # fmt: skip

@@ -1,0 +1,70 @@
+"""2-GPU (NCCL) parity of the dst-range sharded processors against the single-GPU result (-m gpu, needs >= 2 devices;
+skipped on a 1-GPU box).  Reference behaviour: layers/block.py:375-391 (GNN: all-gather x, local edges, keep local rows)
+and block.py:1148-1183 (GraphTransformer edges strategy).  Outputs must be identical to the unsharded run up to fp32
+summation order (the per-row arithmetic is the same kernels on the same rows): tolerance 1e-5 relative."""
+import os
+import tempfile
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, init_file, ret):
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"file://{init_file}", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
+        from anemoi_core_b200.distributed.graph import gather_rows
+        from anemoi_core_b200.distributed.graph import shard_rows
+        from anemoi_core_b200.distributed.shapes import GraphShardInfo
+        from anemoi_core_b200.layers import GNNProcessor
+        from anemoi_core_b200.layers import GraphTransformerProcessor
+        from anemoi_core_b200.synthetic import build_graph
+
+        gr = build_graph("o32", mesh_level=4)
+        n = gr["n_mesh"]
+        ea, ei = gr["proc_attr"].cuda(), gr["proc_index"].cuda()
+        sizes = get_balanced_partition_sizes(n, world)
+        group = dist.group.WORLD
+        msgs = []
+        for kind in ("gt", "gnn"):
+            for dt in (torch.float32, torch.bfloat16):
+                torch.manual_seed(0)
+                if kind == "gt":
+                    m = GraphTransformerProcessor(num_layers=2, num_channels=256, num_chunks=1, num_heads=8, mlp_hidden_ratio=4, edge_dim=gr["edge_dim"])
+                else:
+                    m = GNNProcessor(num_channels=128, num_layers=2, num_chunks=1, mlp_extra_layers=0, edge_dim=gr["edge_dim"])
+                m = m.cuda().eval()
+                c = 256 if kind == "gt" else 128
+                x = torch.randn(n, c, generator=torch.Generator().manual_seed(1)).cuda()
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dt == torch.bfloat16):
+                    full = m(x, 1, GraphShardInfo(nodes=[n]), ea, ei)
+                    local = m(shard_rows(x, sizes, group).contiguous(), 1, GraphShardInfo(nodes=sizes), ea, ei, group)
+                    got = gather_rows(local, sizes, group)
+                err = ((got.float() - full.float()).abs().max() / full.float().abs().max()).item()
+                tol = 1e-5 if dt == torch.float32 else 2e-2
+                msgs.append((kind, str(dt), err, err <= tol))
+        ret[rank] = msgs
+    except Exception as e:  # noqa: BLE001
+        import traceback
+
+        ret[rank] = f"{type(e).__name__}: {e}\n{traceback.format_exc()}"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_processors_match_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        ret = mp.Manager().dict()
+        mp.spawn(_worker, args=(world, os.path.join(d, "rdv"), ret), nprocs=world, join=True)
+        for r in range(world):
+            assert isinstance(ret.get(r), list), ret.get(r)
+            for kind, dt, err, ok in ret[r]:
+                assert ok, f"rank {r} {kind} {dt}: sharded vs single rel err {err:.3e}"

@@ -16,6 +16,7 @@
 // K tails and M/N tails rely on TMA out-of-bounds zero fill + masked stores.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -52,6 +53,48 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
                "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+// ---- 2-CTA (cta_group::2) helpers -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t cta) {  // same smem offset in CTA `cta` of the cluster (shared::cluster address)
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are accounted on the LEADER CTA's mbarrier (cluster address), data into this CTA's smem
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {  // arrives on the barrier at this smem offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
@@ -111,11 +154,14 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 constexpr int kBM = 128, kBK = 64;
 constexpr int kThreads = 384;  // warps 0..3 control, 4..11 epilogue
 
-template <int BN>
+// CG = 1: one CTA computes a 128 x BN tile.  CG = 2 (cta_group::2): a CTA pair computes 256 x BN; each CTA holds 128 accumulator
+// rows and loads its own 128 A rows plus HALF of the W rows (BN/2), so operand traffic per flop drops by a third
+// (128 flop per L2 byte instead of 85 at BN = 256) and the W tile is read from shared memory once per pair.
+template <int BN, int CG = 1>
 struct GemmCfg {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
   static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
-  static constexpr int kWBytes = BN * kBK * 2;
+  static constexpr int kWBytes = (BN / CG) * kBK * 2;
+  static constexpr int kStages = (kABytes + kWBytes) == 49152 ? 4 : 6;
   static constexpr int kStageBytes = kABytes + kWBytes;
   static constexpr int kTmemCols = 2 * BN;  // 128 / 256 / 512: powers of two
   static constexpr int kStagingBytes = 8 * 4096;  // one 32-row x 128-byte transpose buffer per epilogue warp
@@ -137,8 +183,10 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 constexpr int kEpiFast = 1, kEpiOutF32 = 2, kEpiGelu = 4, kEpiRes = 8, kEpiGather = 16;
 
 struct EpiCtx {
-  uint32_t tmem_base, stg, res_bar, tfull0, tempty0;
+  uint32_t tmem_base, stg, res_bar, tfull0, tempty0;  // tempty0: cluster address of the (leader's) accumulator-empty barriers when CG = 2
   int lane, q, half, num_tiles, tiles_n, first_tile, tile_stride;
+  int tile_m, row_off;  // rows per tile (128 * CG) and this CTA's row offset inside the tile
+  bool remote_empty;
 };
 
 // Fast epilogue: templated so that the inner loop has no runtime dtype / flag branches.
@@ -157,7 +205,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
     const int m_blk = tile / cx.tiles_n, n_blk = tile - m_blk * cx.tiles_n;
     const int as = it & 1;
     const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-    const int row0 = m_blk * kBM + cx.q * 32;
+    const int row0 = m_blk * cx.tile_m + cx.row_off + cx.q * 32;
     const float* g1row = nullptr;
     const float* g2row = nullptr;
     if constexpr (GATHER) {
@@ -256,7 +304,12 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
       if (rd == ROUNDS - 1) {  // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(cx.tempty0 + 8u * as);
+        if (lane == 0) {
+          if (cx.remote_empty)
+            ptx::mbar_arrive_cluster(cx.tempty0 + 8u * as);
+          else
+            ptx::mbar_arrive(cx.tempty0 + 8u * as);
+        }
       }
       ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
       __syncwarp();
@@ -281,7 +334,7 @@ __device__ __noinline__ void epilogue_generic(const EpiCtx& cx, const EpiParams&
     const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
     ptx::mbar_wait(cx.tfull0 + 8u * as, aphase);
     ptx::tc_fence_after();
-    const int64_t row = (int64_t)m_blk * kBM + cx.q * 32 + lane;
+    const int64_t row = (int64_t)m_blk * cx.tile_m + cx.row_off + cx.q * 32 + lane;
     const bool row_ok = row < ep.M;
     const float* g1row = (ep.g1 && row_ok) ? ep.g1 + (int64_t)ep.idx1[row] * ep.ldg : nullptr;
     const float* g2row = (ep.g2 && row_ok) ? ep.g2 + (int64_t)ep.idx2[row] * ep.ldg : nullptr;
@@ -309,16 +362,21 @@ __device__ __noinline__ void epilogue_generic(const EpiCtx& cx, const EpiParams&
     }
     ptx::tc_fence_before();
     __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(cx.tempty0 + 8u * as);
+    if (lane == 0) {
+      if (cx.remote_empty)
+        ptx::mbar_arrive_cluster(cx.tempty0 + 8u * as);
+      else
+        ptx::mbar_arrive(cx.tempty0 + 8u * as);
+    }
   }
 }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, int num_kb, int tiles_m,
                              int tiles_n, int epi_mode, const EpiParams ep) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t staging_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
@@ -332,7 +390,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = tiles_m * tiles_n;
+  const int num_tiles = tiles_m * tiles_n;  // tiles of (128*CG) x BN
+  const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int first_tile = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_stride = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -342,52 +404,68 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
-      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(full_bar(s), CG);  // CG = 2: the leader's expect_tx arrive + the peer producer's remote arrive
       ptx::mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
-      ptx::mbar_init(tempty_bar(s), 8);  // one arrive per epilogue warp
+      ptx::mbar_init(tempty_bar(s), 8 * CG);  // one arrive per epilogue warp (of both CTAs)
     }
     for (int w = 0; w < 8; ++w) ptx::mbar_init(res_bar(w), 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    ptx::tmem_relinquish();
+    if constexpr (CG == 2) {
+      ptx::tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+      ptx::tmem_relinquish_2sm();
+    } else {
+      ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
+      // ===== TMA producer (both CTAs of a pair: own A rows, own half of the W rows) =====
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+        const int a_row = m_blk * (kBM * CG) + (int)rank * kBM;
+        const int w_row = n_blk * BN + (int)rank * (BN / CG);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
-          ptx::mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          ptx::tma_load_2d(a_dst, &tmA, full_bar(stage), kb * kBK, m_blk * kBM);
-          ptx::tma_load_2d(a_dst + Cfg::kABytes, &tmW, full_bar(stage), kb * kBK, n_blk * BN);
+          if constexpr (CG == 2) {
+            const uint32_t lbar = ptx::mapa(full_bar(stage), 0);  // completion bytes of both CTAs' loads land on the leader's barrier
+            if (leader)
+              ptx::mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+            ptx::tma_load_2d_2sm(a_dst, &tmA, lbar, kb * kBK, a_row);
+            ptx::tma_load_2d_2sm(a_dst + Cfg::kABytes, &tmW, lbar, kb * kBK, w_row);
+            if (!leader) ptx::mbar_arrive_cluster(lbar);
+          } else {
+            ptx::mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            ptx::tma_load_2d(a_dst, &tmA, full_bar(stage), kb * kBK, a_row);
+            ptx::tma_load_2d(a_dst + Cfg::kABytes, &tmW, full_bar(stage), kb * kBK, w_row);
+          }
           if (++stage == Cfg::kStages) stage = 0, phase ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    if (lane == 0 && leader) {
+      // ===== MMA issuer (leader CTA only when CG = 2) =====
       // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major A and B, N>>3 at bit 17, M>>4 at bit 24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((kBM * CG) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
@@ -402,12 +480,16 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle span: +2 in 16-byte units
-            ptx::umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CG == 2)
+              ptx::umma_bf16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              ptx::umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          ptx::umma_commit(empty_bar(stage));  // frees this smem slot once the MMAs above have read it
+          // frees this smem slot (in both CTAs when CG = 2) once the MMAs above have read it
+          if constexpr (CG == 2) ptx::umma_commit_2sm(empty_bar(stage)); else ptx::umma_commit(empty_bar(stage));
           if (++stage == Cfg::kStages) stage = 0, phase ^= 1u;
         }
-        ptx::umma_commit(tfull_bar(as));  // accumulator complete
+        if constexpr (CG == 2) ptx::umma_commit_2sm(tfull_bar(as)); else ptx::umma_commit(tfull_bar(as));  // accumulator complete
       }
     }
   } else if (warp >= 4) {
@@ -415,8 +497,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     EpiCtx cx;
     cx.tmem_base = tmem_base, cx.lane = lane, cx.q = warp & 3, cx.half = (warp - 4) >> 2;
     cx.stg = staging_base + (uint32_t)(warp - 4) * 4096u, cx.res_bar = res_bar(warp - 4);
-    cx.tfull0 = tfull_bar(0), cx.tempty0 = tempty_bar(0);
-    cx.num_tiles = num_tiles, cx.tiles_n = tiles_n, cx.first_tile = blockIdx.x, cx.tile_stride = gridDim.x;
+    cx.tfull0 = tfull_bar(0);
+    cx.remote_empty = CG == 2;
+    cx.tempty0 = CG == 2 ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
+    cx.tile_m = kBM * CG, cx.row_off = (int)rank * kBM;
+    cx.num_tiles = num_tiles, cx.tiles_n = tiles_n, cx.first_tile = first_tile, cx.tile_stride = tile_stride;
     if (!(epi_mode & kEpiFast)) {
       epilogue_generic<BN>(cx, ep);
     } else {
@@ -442,11 +527,12 @@ __global__ void __launch_bounds__(kThreads, 1)
 #undef ANEMOI_EPI_CASE
     }
   }
+  __syncwarp();  // re-converge the single-lane producer / MMA warps before the aligned barrier
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();  // the peer may still signal our barriers / read our smem until here
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CG == 2) ptx::tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols); else ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -520,33 +606,56 @@ static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t l
   return 0;
 }
 
-template <int BN>
+template <int BN, int CG>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmOut, const CUtensorMap& tmRes, int64_t K, int epi_mode,
                   const EpiParams& ep, cudaStream_t s) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel)");
     attr_set = true;
   }
-  const int tiles_m = (int)((ep.M + kBM - 1) / kBM), tiles_n = (int)((ep.N + BN - 1) / BN);
+  const int tiles_m = (int)((ep.M + kBM * CG - 1) / (kBM * CG)), tiles_n = (int)((ep.N + BN - 1) / BN);
   const int num_kb = (int)((K + kBK - 1) / kBK);
   const int64_t tiles = (int64_t)tiles_m * tiles_n;
-  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  gemm_bf16_tcgen05_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmA, tmW, tmOut, tmRes, num_kb, tiles_m, tiles_n, epi_mode, ep);
+  int sms = num_sms();
+  if (CG == 2) sms &= ~1;
+  int grid = (int)(tiles * CG < sms ? tiles * CG : sms);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = Cfg::kSmemBytes, cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CG>, tmA, tmW, tmOut, tmRes, num_kb, tiles_m, tiles_n, epi_mode, ep);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_bf16_tcgen05_kernel)");
   return launch_status("gemm_bf16_tcgen05_kernel");
 }
 
+// The cta_group::2 kernel is correct (tests/test_gpu_kernels.py::test_linear_large_two_cta) but measured SLOWER than the single-CTA one
+// on this B200 (174 vs 109 us for qkv, 176 vs 90 us for MLP-2; ncu: the MMA issuer never waits, tensor pipe 27 % active, ~565 cycles
+// per UTCHMMA.2CTA instead of 128 -> the peer-CTA operand fetch does not keep up; profiles/README.md).  It stays opt-in
+// (ANEMOI_B200_GEMM_CG=2) until that is understood.
+static int env_cta_group() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ANEMOI_B200_GEMM_CG");
+    v = (e && e[0] == '2') ? 2 : 1;
+  }
+  return v;
+}
+
 int linear_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t K, const EpiParams& ep, cudaStream_t s) {
-  // tile width: 256 unless that leaves fewer than ~2 waves of CTAs
+  // 2-CTA 256x256 tiles when the problem is large enough to fill the 74 CTA pairs at least twice; else single-CTA 128 x {256,128}
   const int64_t tiles_m = (ep.M + kBM - 1) / kBM;
-  int bn = 256;
+  int bn = 256, cg = 1;
   if (ep.N <= 128 || tiles_m * ((ep.N + 255) / 256) < 2 * (int64_t)num_sms()) bn = 128;
+  if (bn == 256 && env_cta_group() == 2 && ((ep.M + 255) / 256) * ((ep.N + 255) / 256) >= (int64_t)num_sms()) cg = 2;
   CUtensorMap tmA, tmW, tmOut, tmRes;
   int rc = get_tensor_map(A, ep.M, K, lda, kBM, &tmA);
   if (rc) return rc;
-  rc = get_tensor_map(W, ep.N, K, ldw, bn, &tmW);
+  rc = get_tensor_map(W, ep.N, K, ldw, bn / cg, &tmW);
   if (rc) return rc;
   auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const int os = ep.o_dtype == ANEMOI_BF16 ? 2 : 4;
@@ -567,7 +676,8 @@ int linear_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, int64
       if (rc) return rc;
     }
   }
-  return bn == 128 ? launch<128>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s) : launch<256>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s);
+  if (cg == 2) return launch<256, 2>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s);
+  return bn == 128 ? launch<128, 1>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s) : launch<256, 1>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s);
 }
 
 }  // namespace anemoi

@@ -133,6 +133,34 @@ def test_linear(ops, M, N, K, dt, epi):
         torch.testing.assert_close(y32.cpu(), ref, atol=1e-3, rtol=1e-3)
 
 
+@pytest.mark.parametrize("M,N,K,epi", [(40962, 2240, 512, "bias"), (40962, 512, 704, "bias_res"), (20001, 2048, 512, "bias_gelu"), (37900, 512, 2048, "bias_res"),
+                                       (40962, 1000, 520, "bias_gelu")])
+def test_linear_large_two_cta(ops, M, N, K, epi):
+    """Shapes large enough for the cta_group::2 kernel (256x256 tiles per CTA pair), ragged M / N / K tails included.
+    (The 2-CTA kernel is opt-in through ANEMOI_B200_GEMM_CG=2, read once per process: CI runs this file a second time with it set.)
+    Checker: fp32 torch matmul on the same bf16-rounded operands (on the GPU: the CPU would take minutes)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g, device="cuda")
+    res = torch.randn(M, N, generator=g, device="cuda").to(torch.bfloat16) if epi == "bias_res" else None
+    y = ops.linear(a, w, bias, gelu=epi == "bias_gelu", residual=res)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = a.float() @ w.float().t() + bias
+    if epi == "bias_gelu":
+        ref = torch.nn.functional.gelu(ref)
+    if res is not None:
+        ref = ref + res.float()
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 2**-7 * ref.abs().max().item() + 1e-3, f"max err {err}"
+    # a second call with fp32 output (node projections of the GNN path)
+    y32 = ops.linear(a, w, bias, gelu=epi == "bias_gelu", residual=None, out_dtype=torch.float32)
+    ref32 = a.float() @ w.float().t() + bias
+    if epi == "bias_gelu":
+        ref32 = torch.nn.functional.gelu(ref32)
+    assert (y32 - ref32).abs().max().item() <= 2e-3 * max(1.0, ref32.abs().max().item())
+
+
 def test_linear_strided_views(ops):
     """Column slices of wider buffers as A, residual and out (how the blocks pass q|k|v|self and x|aggregate)."""
     g = torch.Generator().manual_seed(5)

@@ -15,7 +15,7 @@ from anemoi_core_b200 import ops  # noqa: E402
 from anemoi_core_b200.synthetic import build_graph  # noqa: E402
 
 reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 30
-which = [a for a in sys.argv[1:] if not a.startswith("--") and not a.isdigit()] or ["attn", "gemm"]
+which = [a for a in sys.argv[1:] if not a.startswith("--") and not a.isdigit()] or ["attn", "gemm", "gc"]
 pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
 dev = torch.device("cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -73,3 +73,17 @@ if "gemm" in which:
         fl = 2.0 * M * N_ * K
         print(json.dumps({"kernel": f"linear {name} [{M}x{K}]x[{K}x{N_}]", "us_median": round(med, 1), "us_min": round(mn, 1),
                           "TFLOPs": round(fl / med / 1e6, 1), "frac_tensor_burst": round(fl / med / 1e6 / pk["bf16_tflops"], 3)}))  # fmt: skip
+
+if "gc" in which:
+    gr = build_graph("o96", 6)
+    N, E = gr["n_mesh"], gr["proc_index"].shape[1]
+    csr = ops.build_csr(gr["proc_index"].to(dev), N, N)
+    for C in (1024, 512, 256):
+        h = torch.randn(E, C, generator=g).to(torch.bfloat16).to(dev)
+        e = torch.randn(E, C, generator=g).to(torch.bfloat16).to(dev)
+        w, b = torch.randn(C, generator=g).to(dev), torch.randn(C, generator=g).to(dev)
+        out = torch.empty(N, C, dtype=torch.bfloat16, device=dev)
+        med, mn = timeit(lambda: ops.graphconv_ln_aggregate(h, w, b, e, csr, out=out))
+        alg = 3 * E * C * 2 + N * C * 2 + 4 * N
+        print(json.dumps({"kernel": f"graphconv_ln_aggregate C={C} (E={E})", "us_median": round(med, 1), "us_min": round(mn, 1), "alg_MB": round(alg / 1e6, 1),
+                          "GBs": round(alg / med / 1e3, 1), "frac_hbm_measured": round(alg / med / 1e3 / pk["hbm_gbs"], 3)}))  # fmt: skip

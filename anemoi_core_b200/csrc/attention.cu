@@ -63,7 +63,7 @@ struct AttnParams {
 #define ATTN_MINBLOCKS 3
 #endif
 [[maybe_unused]] constexpr int kNodesPerRange = ATTN_NODES_PER_RANGE;
-constexpr int kBatch = ATTN_BATCH;
+[[maybe_unused]] constexpr int kBatch = ATTN_BATCH;
 
 template <typename T>
 struct ChunkT {
@@ -311,10 +311,10 @@ __global__ void __launch_bounds__(128, ATTN_MINBLOCKS) gt_attention_slab_kernel(
 // Work split: each warp takes a contiguous range of dst nodes holding ~E / (#warps) edges (boundaries by a warp-wide 32-ary
 // search of colptr), so there is no per-range pipeline restart and the load is balanced by edges.
 #ifndef ATTN_SLOTS
-#define ATTN_SLOTS 6
+#define ATTN_SLOTS 8
 #endif
 #ifndef ATTN_PIPE_MINBLOCKS
-#define ATTN_PIPE_MINBLOCKS 4
+#define ATTN_PIPE_MINBLOCKS 3
 #endif
 constexpr int kSlots = ATTN_SLOTS;
 
@@ -359,6 +359,11 @@ __device__ __forceinline__ int colptr_lower_bound(const int32_t* __restrict__ co
   return lo;
 }
 
+#ifndef ATTN_PIPE_BATCH
+#define ATTN_PIPE_BATCH 3
+#endif
+constexpr int kPBatch = ATTN_PIPE_BATCH;  // 3 divides every in-degree of the icosahedral multi-scale mesh (6, 12, ... 36): no padded slots
+
 template <typename T, int NCH, int LPH, int MODE>
 __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_kernel(const AttnParams p, int n_slabs, int active_lanes) {
   using CT = ChunkT<T>;
@@ -367,6 +372,7 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
   constexpr int SLAB = NCH * 32 * EPC;
   constexpr int kKV = NCH * 512;                                          // bytes of one k (or v) row segment
   constexpr int kSlotBytes = 2 * kKV + (MODE == 2 ? 64 : kKV);             // k | v | attributes-or-e
+  static_assert(kSlots > kPBatch, "ring must be deeper than a batch");
   extern __shared__ __align__(16) uint8_t smem_ring[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const bool active = lane < active_lanes;
@@ -378,8 +384,10 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
   const char* __restrict__ kp = reinterpret_cast<const char*>(p.k);
   const char* __restrict__ vp = reinterpret_cast<const char*>(p.v);
   const char* __restrict__ ep = reinterpret_cast<const char*>(p.e);
+  const char* __restrict__ addp = reinterpret_cast<const char*>(p.add);
+  const T* __restrict__ qwp = reinterpret_cast<const T*>(p.qw);
   const int64_t ldq_b = p.ldq * (int64_t)sizeof(T), ldk_b = p.ldk * (int64_t)sizeof(T), ldv_b = p.ldv * (int64_t)sizeof(T);
-  const int64_t lde_b = p.lde_proj * (int64_t)sizeof(T);
+  const int64_t lde_b = p.lde_proj * (int64_t)sizeof(T), ldadd_b = p.ldadd * (int64_t)sizeof(T);
   const float qscale = p.scale * 1.4426950408889634f;
 
   // ---- this warp's (slab, dst range) ----
@@ -395,8 +403,9 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
   const int64_t lane_off = ((int64_t)slab * SLAB + (int64_t)lane_eff * EPC) * (int64_t)sizeof(T);
   const int E0 = __ldg(p.colptr + n_lo), E1 = __ldg(p.colptr + n_hi);
 
-  // ---- producer state: src ids streamed in blocks of 32, one cp.async group per edge ----
+  // ---- producer state: src ids streamed in blocks of 32, one cp.async group per edge, running ring position ----
   int pe = E0;  // next edge to issue
+  int ppos = 0;  // its ring slot
   int pblk = E0;
   int psrc = (pblk + lane < E1) ? __ldg(p.src + pblk + lane) : 0;
   int psrc_n = (pblk + 32 + lane < E1) ? __ldg(p.src + pblk + 32 + lane) : 0;
@@ -408,23 +417,24 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
         psrc_n = (pblk + 32 + lane < E1) ? __ldg(p.src + pblk + 32 + lane) : 0;
       }
       const int sid = __shfl_sync(0xffffffffu, psrc, pe - pblk);
-      const uint32_t slot = ring + (uint32_t)(((pe - E0) % kSlots) * kSlotBytes);
+      const uint32_t slot = ring + (uint32_t)(ppos * kSlotBytes) + lane * 16;
       const char* kr = kp + (int64_t)sid * ldk_b + lane_off;
       const char* vr = vp + (int64_t)sid * ldv_b + lane_off;
 #pragma unroll
       for (int j = 0; j < NCH; ++j) {
-        cp_async16(slot + j * 512 + lane * 16, kr + j * 512);
-        cp_async16(slot + kKV + j * 512 + lane * 16, vr + j * 512);
+        cp_async16(slot + j * 512, kr + j * 512);
+        cp_async16(slot + kKV + j * 512, vr + j * 512);
       }
       if constexpr (MODE == 2) {
-        if (lane < 4) cp_async16(slot + 2 * kKV + lane * 16, p.edge_attr + (int64_t)pe * p.lde + lane * 4);
+        if (lane < 4) cp_async16(slot + 2 * kKV, p.edge_attr + (int64_t)pe * p.lde + lane * 4);
       } else {
         if (ep) {
 #pragma unroll
-          for (int j = 0; j < NCH; ++j) cp_async16(slot + 2 * kKV + j * 512 + lane * 16, ep + (int64_t)pe * lde_b + lane_off + j * 512);
+          for (int j = 0; j < NCH; ++j) cp_async16(slot + 2 * kKV + j * 512, ep + (int64_t)pe * lde_b + lane_off + j * 512);
         }
       }
       ++pe;
+      if (++ppos == kSlots) ppos = 0;
     }
     cp_async_commit();  // empty past the end: keeps "groups issued = edges consumed + kSlots" uniform
   };
@@ -435,6 +445,30 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
 #pragma unroll
   for (int j = 0; j < NCH; ++j) qw_off[j] = ((slab * SLAB + (j * 32 + lane_eff) * EPC) / p.ch) * p.dp + sub;
 
+  // node-level operands (q, qw, add) of the NEXT node are fetched one node ahead into registers (L1 path; the gathers use cp.async.cg)
+  uint4 q_nx[NCH], add_nx[NCH];
+  T qw_nx[NCH][NA];
+  auto fetch_node = [&](int d) {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      q_nx[j] = ldg16(qp + (int64_t)d * ldq_b + lane_off + j * 512);
+      if (addp) add_nx[j] = ldg16(addp + (int64_t)d * ldadd_b + lane_off + j * 512);
+      if constexpr (MODE == 2) {
+#pragma unroll
+        for (int t = 0; t < NA; ++t)
+          if (t < na && sub + t * LPH < p.dp) qw_nx[j][t] = qwp[(int64_t)d * p.ldqw + qw_off[j] + t * LPH];
+      }
+    }
+  };
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    add_nx[j] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int t = 0; t < NA; ++t) qw_nx[j][t] = from_f32<T>(0.f);
+  }
+  fetch_node(n_lo);
+
+  int cpos = 0;  // ring slot of the next edge to consume
   int cbase = n_lo;  // colptr block: lanes hold colptr[cbase + lane]
   int cp = __ldg(p.colptr + min(cbase + lane, n_hi));
   for (int d = n_lo; d < n_hi; ++d) {
@@ -444,46 +478,49 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
     }
     const int e0 = __shfl_sync(0xffffffffu, cp, d - cbase), e1 = __shfl_sync(0xffffffffu, cp, d - cbase + 1);
     float q[NCH][EPC], acc[NCH][EPC], m_i[NCH], l_i[NCH], qw[NCH][NA], abar[NCH][NA];
+    uint4 add_cur[NCH];
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
-      CT::unpack(ldg16(qp + (int64_t)d * ldq_b + lane_off + j * 512), q[j]);
+      CT::unpack(q_nx[j], q[j]);
+      add_cur[j] = add_nx[j];
       m_i[j] = -INFINITY, l_i[j] = 0.f;
 #pragma unroll
       for (int i = 0; i < EPC; ++i) q[j][i] *= qscale, acc[j][i] = 0.f;
 #pragma unroll
-      for (int t = 0; t < NA; ++t) {
-        abar[j][t] = 0.f;
-        qw[j][t] = 0.f;
-        if constexpr (MODE == 2) {
-          if (t < na && sub + t * LPH < p.dp) qw[j][t] = to_f32<T>(reinterpret_cast<const T*>(p.qw)[(int64_t)d * p.ldqw + qw_off[j] + t * LPH]) * qscale;
-        }
-      }
+      for (int t = 0; t < NA; ++t) abar[j][t] = 0.f, qw[j][t] = MODE == 2 ? to_f32<T>(qw_nx[j][t]) * qscale : 0.f;
     }
-    for (int eb = e0; eb < e1; eb += kBatch) {
-      const int nb = min(kBatch, e1 - eb);
-      cp_async_wait<kSlots - kBatch>();  // edges eb .. eb+kBatch-1 have landed (this lane's copies)
-      __syncwarp();                      // ... and every other lane's
-      float sc[kBatch][NCH], at[kBatch][NA];
+    if (d + 1 < n_hi) fetch_node(d + 1);
+    for (int eb = e0; eb < e1; eb += kPBatch) {
+      const int nb = min(kPBatch, e1 - eb);
+      cp_async_wait<kSlots - kPBatch>();  // edges eb .. eb+kPBatch-1 have landed (this lane's copies)
+      __syncwarp();                       // ... and every other lane's
+      uint32_t sl[kPBatch];               // slot addresses of the batch (entries past the node's last edge alias slot 0: valid data, weight 0)
 #pragma unroll
-      for (int b = 0; b < kBatch; ++b) {
-        const uint32_t slot = ring + (uint32_t)(((min(eb + b, e1 - 1) - E0) % kSlots) * kSlotBytes);
+      for (int b = 0; b < kPBatch; ++b) {
+        int pos = cpos + (b < nb ? b : 0);
+        if (pos >= kSlots) pos -= kSlots;
+        sl[b] = ring + (uint32_t)(pos * kSlotBytes) + lane * 16;
+      }
+      float sc[kPBatch][NCH], at[kPBatch][NA];
+#pragma unroll
+      for (int b = 0; b < kPBatch; ++b) {
         if constexpr (MODE == 2) {
 #pragma unroll
-          for (int t = 0; t < NA; ++t) at[b][t] = t < na ? lds32f(slot + 2 * kKV + (sub + t * LPH) * 4) : 0.f;
+          for (int t = 0; t < NA; ++t) at[b][t] = t < na ? lds32f(sl[b] - lane * 16 + 2 * kKV + (sub + t * LPH) * 4) : 0.f;
         }
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
           float kf[EPC];
-          CT::unpack(lds16(slot + j * 512 + lane * 16), kf);
-          float t = 0.f;
+          CT::unpack(lds16(sl[b] + j * 512), kf);
           if constexpr (MODE == 1) {
             if (ep) {
               float ef[EPC];
-              CT::unpack(lds16(slot + 2 * kKV + j * 512 + lane * 16), ef);
+              CT::unpack(lds16(sl[b] + 2 * kKV + j * 512), ef);
 #pragma unroll
               for (int i = 0; i < EPC; ++i) kf[i] += ef[i];
             }
           }
+          float t = 0.f;
 #pragma unroll
           for (int i = 0; i < EPC; ++i) t += q[j][i] * kf[i];
           if constexpr (MODE == 2) {
@@ -500,24 +537,23 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
       for (int j = 0; j < NCH; ++j) {
         float mx = m_i[j];
 #pragma unroll
-        for (int b = 0; b < kBatch; ++b) mx = fmaxf(mx, sc[b][j]);
+        for (int b = 0; b < kPBatch; ++b) mx = fmaxf(mx, sc[b][j]);
         const float corr = exp2f(m_i[j] - mx);
-        float wgt[kBatch], wsum = 0.f;
+        float wgt[kPBatch], wsum = 0.f;
 #pragma unroll
-        for (int b = 0; b < kBatch; ++b) wgt[b] = exp2f(sc[b][j] - mx), wsum += wgt[b];
+        for (int b = 0; b < kPBatch; ++b) wgt[b] = exp2f(sc[b][j] - mx), wsum += wgt[b];
         l_i[j] = l_i[j] * corr + wsum;
         m_i[j] = mx;
 #pragma unroll
         for (int i = 0; i < EPC; ++i) acc[j][i] *= corr;
 #pragma unroll
-        for (int b = 0; b < kBatch; ++b) {
-          const uint32_t slot = ring + (uint32_t)(((min(eb + b, e1 - 1) - E0) % kSlots) * kSlotBytes);
+        for (int b = 0; b < kPBatch; ++b) {
           float vf[EPC];
-          CT::unpack(lds16(slot + kKV + j * 512 + lane * 16), vf);
+          CT::unpack(lds16(sl[b] + kKV + j * 512), vf);
           if constexpr (MODE == 1) {
             if (ep) {
               float ef[EPC];
-              CT::unpack(lds16(slot + 2 * kKV + j * 512 + lane * 16), ef);
+              CT::unpack(lds16(sl[b] + 2 * kKV + j * 512), ef);
 #pragma unroll
               for (int i = 0; i < EPC; ++i) vf[i] += ef[i];
             }
@@ -531,11 +567,13 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
             if (t < na) {
               float s2 = abar[j][t] * corr;
 #pragma unroll
-              for (int b = 0; b < kBatch; ++b) s2 += wgt[b] * at[b][t];
+              for (int b = 0; b < kPBatch; ++b) s2 += wgt[b] * at[b][t];
               abar[j][t] = s2;
             }
         }
       }
+      cpos += nb;
+      if (cpos >= kSlots) cpos -= kSlots;
       __syncwarp();  // all lanes are done reading these slots before they are refilled
       for (int i = 0; i < nb; ++i) issue();
     }
@@ -564,9 +602,9 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
         }
       }
       if (active) {
-        if (p.add) {
+        if (addp) {
           float rr[EPC];
-          CT::unpack(ldg16(reinterpret_cast<const char*>(p.add) + ((int64_t)d * p.ldadd) * (int64_t)sizeof(T) + lane_off + j * 512), rr);
+          CT::unpack(add_cur[j], rr);
 #pragma unroll
           for (int i = 0; i < EPC; ++i) o[i] += rr[i];
         }

@@ -43,6 +43,14 @@ def round8(k: int) -> int:
     return (k + 7) // 8 * 8
 
 
+def pad_k(k: int, dt: torch.dtype) -> int:
+    """K of a bf16 GEMM operand: multiple of 8 (16-byte TMA row stride) and at least 64 (one 128-byte swizzle span), so that
+    even the edge_dim = 3..11 and in_channels = 12 embeddings run on the tcgen05 kernel instead of the FFMA one; fp32 untouched."""
+    if dt != torch.bfloat16:
+        return k
+    return max(64, round8(k))
+
+
 class WeightPack:
     """Derived tensors of a module's parameters (dtype casts, row-concatenations, zero K-padding), rebuilt when a
     source parameter changes (in-place update, ``load_state_dict``, ``.to()``)."""
@@ -70,8 +78,8 @@ class WeightPack:
             if cols is not None:
                 w = w[:, cols]
             k = w.shape[1]
-            if dt == torch.bfloat16 and k % 8:
-                w = torch.nn.functional.pad(w, (0, round8(k) - k))
+            if pad_k(k, dt) != k:
+                w = torch.nn.functional.pad(w, (0, pad_k(k, dt) - k))
             return w.to(dt).contiguous()
 
         return self.get(("w", tuple(id(l) for l in layers), dt, None if cols is None else (cols.start, cols.stop)), ws, build)

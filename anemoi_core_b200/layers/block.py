@@ -221,8 +221,8 @@ class GraphTransformerBaseBlock(nn.Module):
             wf[: H * dp].view(H, dp, -1)[:, :d] = torch.einsum("hca,hci->hai", we, wq)
             w = torch.cat([l.weight.detach().float() for l in layers] + [wf], 0)
             k = w.shape[1]
-            if dt == torch.bfloat16 and k % 8:
-                w = torch.nn.functional.pad(w, (0, Fn.round8(k) - k))
+            if Fn.pad_k(k, dt) != k:
+                w = torch.nn.functional.pad(w, (0, Fn.pad_k(k, dt) - k))
             return w.to(dt).contiguous()
 
         def build_b() -> Tensor:

@@ -40,6 +40,8 @@ WORKLOADS = {
                  desc="O96 grid (40320 pts) -> ico-6 multi-scale mesh (40962 nodes, 327600 edges), GraphTransformer enc + 16x512 proc (16 heads) + dec"),
     "cfg3": dict(grid="n320", mesh_level=6, kind="gnn", C=1024, layers=16, heads=16, in_grid=212, in_mesh=12, out_grid=88,
                  desc="N320 grid (542080 pts) -> ico-6 mesh, GNN enc + 16x1024 proc + dec"),
+    "cfg5": dict(grid="o96", mesh_level=6, kind="graphtransformer", C=512, layers=16, heads=16, in_grid=212, in_mesh=12, out_grid=88, rollout=40,
+                 desc="cfg2 model, 40-step autoregressive rollout (prognostic outputs written back into the newest input time slot, forcings/statics held), per-step latency"),
     "small": dict(grid="o32", mesh_level=4, kind="graphtransformer", C=512, layers=4, heads=16, in_grid=212, in_mesh=12, out_grid=88,
                   desc="O32 grid -> ico-4 mesh, GraphTransformer 4x512 (smoke-size)"),
 }  # fmt: skip
@@ -200,7 +202,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))  # cfg2 = BASELINE.json configs[1] (the metric's config)
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -306,6 +308,25 @@ def main():
             torch.cuda.current_stream().synchronize()
 
     ms_e2e, _ = timed(e2e_step, args.steps, 3)
+
+    # ---- cfg5: autoregressive rollout (training/tasks/forecaster.py:155-205 semantics): slot t <- slot t+1, newest slot <- prediction ----
+    rollout = None
+    if w.get("rollout"):
+        nv = 100  # variables per time slot; the model predicts the first out_grid of them (prognostic), the rest are forcings
+        xg = x_grid.clone()
+        lat = []
+        for i in range(w["rollout"]):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            y = replay(xg) if use_graph else step(xg, x_mesh)
+            xg[:, :nv].copy_(xg[:, nv : 2 * nv])  # shift the time window
+            xg[:, nv : nv + w["out_grid"]].copy_(y)  # newest slot <- prognostic prediction (forcings and statics stay)
+            b.record()
+            torch.cuda.synchronize()
+            lat.append(a.elapsed_time(b))
+        steady = sorted(lat[1:])
+        rollout = {"steps": w["rollout"], "mean_ms": sum(steady) / len(steady), "p50_ms": steady[len(steady) // 2],
+                   "p99_ms": steady[min(len(steady) - 1, int(0.99 * len(steady)))], "first_ms": lat[0]}
     clk = clocks.stop() if rank == 0 else None
 
     if world > 1:
@@ -370,6 +391,8 @@ def main():
         "kernels": kernels,
         "wall_s_timed_region": wall_dev,
     }  # fmt: skip
+    if rollout is not None:
+        line["rollout"] = rollout
     if sds is not None:
         line["cpu_baseline"] = cpu_baseline(w, gr, sds, x_grid_h, x_mesh_h)
     else:

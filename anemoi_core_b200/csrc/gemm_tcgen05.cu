@@ -69,8 +69,11 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t cta) {  // same
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// relaxed: the arrive orders nothing by itself (TMEM reads are ordered by tcgen05.wait::ld + tcgen05.fence, TMA data by complete_tx).
+// A .release.cluster arrive compiles to MEMBAR.ALL.CTA + ERRBAR, which in the producer thread waits for the bulk copies it has just
+// issued and serialises the pipeline (measured: 2080 cycles per k-block instead of ~512).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion bytes are accounted on the LEADER CTA's mbarrier (cluster address), data into this CTA's smem
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
@@ -165,7 +168,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kWBytes;
   static constexpr int kTmemCols = 2 * BN;  // 128 / 256 / 512: powers of two
   static constexpr int kStagingBytes = 8 * 4096;  // one 32-row x 128-byte transpose buffer per epilogue warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias tile*/;
 };
 
 // UMMA shared-memory descriptor for a K-major, 128-byte-swizzled tile (rows of 64 bf16 = 128 B; 8-row groups 1024 B apart).
@@ -181,12 +184,17 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 
 // Epilogue mode bits (host-selected, warp-uniform): 0 = slow element-wise path.
 constexpr int kEpiFast = 1, kEpiOutF32 = 2, kEpiGelu = 4, kEpiRes = 8, kEpiGather = 16;
+// debug ablations (ANEMOI_B200_GEMM_ABLATE, results are then wrong by construction): skip TMA loads / skip the epilogue body / skip the MMAs
+constexpr int kAblNoLoad = 256, kAblNoEpi = 512, kAblNoMma = 1024, kAblNoStore = 2048, kAblNoBias = 4096, kAblNoTmemLd = 8192;
+constexpr int kAblMask = kAblNoLoad | kAblNoEpi | kAblNoMma | kAblNoStore | kAblNoBias | kAblNoTmemLd;
 
 struct EpiCtx {
+  uint32_t bias_smem;  // 256 floats: the tile's bias slice, shared by the four warps of a column half
   uint32_t tmem_base, stg, res_bar, tfull0, tempty0;  // tempty0: cluster address of the (leader's) accumulator-empty barriers when CG = 2
   int lane, q, half, num_tiles, tiles_n, first_tile, tile_stride;
   int tile_m, row_off;  // rows per tile (128 * CG) and this CTA's row offset inside the tile
   bool remote_empty;
+  int abl;  // debug ablation bits
 };
 
 // Fast epilogue: templated so that the inner loop has no runtime dtype / flag branches.
@@ -206,6 +214,26 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
     const int as = it & 1;
     const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
     const int row0 = m_blk * cx.tile_m + cx.row_off + cx.q * 32;
+    if (ep.bias) {
+      // the tile's bias slice goes to shared memory once per column half (one coalesced 512-byte load) instead of two broadcast
+      // global loads per 8 columns per thread (measured: the bias loads were ~25 % of the kernel time)
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + cx.half) : "memory");  // previous tile's readers are done
+      if (cx.q == 0) {
+        const int c = n_blk * BN + cx.half * kColsPerWarp + lane * 4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c + 4 <= (int)ep.N) {
+          b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + c));
+        } else {
+          if (c < (int)ep.N) b4.x = ep.bias[c];
+          if (c + 1 < (int)ep.N) b4.y = ep.bias[c + 1];
+          if (c + 2 < (int)ep.N) b4.z = ep.bias[c + 2];
+        }
+        if (lane * 4 < kColsPerWarp)
+          ptx::sts128(cx.bias_smem + (uint32_t)(cx.half * kColsPerWarp + lane * 4) * 4u, __float_as_uint(b4.x), __float_as_uint(b4.y),
+                      __float_as_uint(b4.z), __float_as_uint(b4.w));
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + cx.half) : "memory");
+    }
     const float* g1row = nullptr;
     const float* g2row = nullptr;
     if constexpr (GATHER) {
@@ -218,7 +246,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
       const int col_in_tile = cx.half * kColsPerWarp + rd * CW;
       const int col0 = n_blk * BN + col_in_tile;
       // the previous TMA store must have finished READING the staging buffer before it is overwritten
-      if (lane == 0) ptx::bulk_wait_read0();
+      if (lane == 0 && !(cx.abl & kAblNoStore)) ptx::bulk_wait_read0();
       __syncwarp();
       if constexpr (RES) {
         if (lane == 0) {
@@ -237,19 +265,26 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
 #pragma unroll
       for (int h32 = 0; h32 < CW; h32 += 32) {
         uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(cx.tmem_base + ((uint32_t)(cx.q * 32) << 16) + (uint32_t)(as * BN + col_in_tile + h32), r);
-        ptx::tmem_wait_ld();
+        if (!(cx.abl & kAblNoTmemLd)) {
+          ptx::tmem_ld_32x32b_x32(cx.tmem_base + ((uint32_t)(cx.q * 32) << 16) + (uint32_t)(as * BN + col_in_tile + h32), r);
+          ptx::tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0x3f800000u + j;
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int col = col0 + h32 + g * 8;
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+          if (ep.bias && !(cx.abl & kAblNoBias)) {
+            const uint32_t ba = cx.bias_smem + (uint32_t)(col_in_tile + h32 + g * 8) * 4u;
+            const uint4 b0 = ptx::lds128(ba), b1 = ptx::lds128(ba + 16);
+            v[0] += __uint_as_float(b0.x), v[1] += __uint_as_float(b0.y), v[2] += __uint_as_float(b0.z), v[3] += __uint_as_float(b0.w);
+            v[4] += __uint_as_float(b1.x), v[5] += __uint_as_float(b1.y), v[6] += __uint_as_float(b1.z), v[7] += __uint_as_float(b1.w);
+          }
           if (col + 8 <= (int)ep.N) {
-            if (ep.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col)), b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + 1);
-              v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
-            }
             if constexpr (GATHER) {
               if (g1row) {
                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(g1row + col)), b1 = __ldg(reinterpret_cast<const float4*>(g1row + col) + 1);
@@ -264,7 +299,6 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               if (col + j < (int)ep.N) {
-                if (ep.bias) v[j] += ep.bias[col + j];
                 if constexpr (GATHER) {
                   if (g1row) v[j] += g1row[col + j];
                   if (g2row) v[j] += g2row[col + j];
@@ -313,7 +347,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
       }
       ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0 && !(cx.abl & kAblNoStore)) {
         ptx::tma_store_2d(tmOut, cx.stg, col0, row0);  // rows >= M / columns >= N are clipped by the hardware
         ptx::bulk_commit();
       }
@@ -404,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
-      ptx::mbar_init(full_bar(s), CG);  // CG = 2: the leader's expect_tx arrive + the peer producer's remote arrive
+      ptx::mbar_init(full_bar(s), 1);  // CG = 2: the leader's expect_tx covers the bytes of BOTH CTAs' loads; the peer only issues loads
       ptx::mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -441,13 +475,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
-          if constexpr (CG == 2) {
+          if (epi_mode & kAblNoLoad) {
+            if (CG == 1 || leader) ptx::mbar_arrive(full_bar(stage));
+          } else if constexpr (CG == 2) {
             const uint32_t lbar = ptx::mapa(full_bar(stage), 0);  // completion bytes of both CTAs' loads land on the leader's barrier
             if (leader)
               ptx::mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
             ptx::tma_load_2d_2sm(a_dst, &tmA, lbar, kb * kBK, a_row);
             ptx::tma_load_2d_2sm(a_dst + Cfg::kABytes, &tmW, lbar, kb * kBK, w_row);
-            if (!leader) ptx::mbar_arrive_cluster(lbar);
           } else {
             ptx::mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
             ptx::tma_load_2d(a_dst, &tmA, full_bar(stage), kb * kBK, a_row);
@@ -479,6 +514,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint64_t b_desc = make_sw128_desc(a_addr + Cfg::kABytes);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
+            if (epi_mode & kAblNoMma) break;
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle span: +2 in 16-byte units
             if constexpr (CG == 2)
               ptx::umma_bf16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
@@ -500,16 +536,29 @@ __global__ void __launch_bounds__(kThreads, 1)
     cx.tfull0 = tfull_bar(0);
     cx.remote_empty = CG == 2;
     cx.tempty0 = CG == 2 ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
+    cx.bias_smem = bar_base + 256;
     cx.tile_m = kBM * CG, cx.row_off = (int)rank * kBM;
+    cx.abl = epi_mode & kAblMask;
     cx.num_tiles = num_tiles, cx.tiles_n = tiles_n, cx.first_tile = first_tile, cx.tile_stride = tile_stride;
-    if (!(epi_mode & kEpiFast)) {
+    if (epi_mode & kAblNoEpi) {
+      int it = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
+        ptx::mbar_wait(cx.tfull0 + 8u * (it & 1), (uint32_t)(it >> 1) & 1u);
+        ptx::tc_fence_after();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (cx.remote_empty) ptx::mbar_arrive_cluster(cx.tempty0 + 8u * (it & 1)); else ptx::mbar_arrive(cx.tempty0 + 8u * (it & 1));
+        }
+      }
+    } else if (!(epi_mode & kEpiFast)) {
       epilogue_generic<BN>(cx, ep);
     } else {
 #define ANEMOI_EPI_CASE(F32, GELU, RES, GATHER)                                                                          \
   case (F32 ? kEpiOutF32 : 0) | (GELU ? kEpiGelu : 0) | (RES ? kEpiRes : 0) | (GATHER ? kEpiGather : 0):                   \
     epilogue_fast<BN, F32, GELU, RES, GATHER>(cx, ep, &tmOut, &tmRes);                                                     \
     break;
-      switch (epi_mode & ~kEpiFast) {
+      switch (epi_mode & ~kEpiFast & ~kAblMask) {
         ANEMOI_EPI_CASE(false, false, false, false)
         ANEMOI_EPI_CASE(false, true, false, false)
         ANEMOI_EPI_CASE(false, false, true, false)
@@ -633,15 +682,15 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensor
   return launch_status("gemm_bf16_tcgen05_kernel");
 }
 
-// The cta_group::2 kernel is correct (tests/test_gpu_kernels.py::test_linear_large_two_cta) but measured SLOWER than the single-CTA one
-// on this B200 (174 vs 109 us for qkv, 176 vs 90 us for MLP-2; ncu: the MMA issuer never waits, tensor pipe 27 % active, ~565 cycles
-// per UTCHMMA.2CTA instead of 128 -> the peer-CTA operand fetch does not keep up; profiles/README.md).  It stays opt-in
-// (ANEMOI_B200_GEMM_CG=2) until that is understood.
+// cta_group::2 (256x256 per CTA pair) is the default for problems that fill the 74 pairs; ANEMOI_B200_GEMM_CG=1 forces the single-CTA
+// kernel (A/B measurements: profiles/README.md).  History: the first 2-CTA version was 2x SLOWER than the single-CTA one because the peer
+// producer's `mbarrier.arrive.release.cluster` compiled to MEMBAR.ALL.CTA + ERRBAR, which waits for the bulk copies just issued and
+// serialised the ring (2080 cycles per k-block); with a single expect_tx on the leader covering both CTAs' bytes it is 10-25 % faster.
 static int env_cta_group() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("ANEMOI_B200_GEMM_CG");
-    v = (e && e[0] == '2') ? 2 : 1;
+    v = (e && e[0] == '1') ? 1 : 2;
   }
   return v;
 }
@@ -675,6 +724,14 @@ int linear_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, int64
       rc = get_tensor_map(ep.residual, ep.M, ep.N, ep.ldr, 32, &tmRes, os);
       if (rc) return rc;
     }
+  }
+  {
+    static int abl = -1;
+    if (abl < 0) {
+      const char* e = getenv("ANEMOI_B200_GEMM_ABLATE");
+      abl = e ? atoi(e) : 0;
+    }
+    epi_mode |= (abl << 8) & kAblMask;
   }
   if (cg == 2) return launch<256, 2>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s);
   return bn == 128 ? launch<128, 1>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s) : launch<256, 1>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s);

@@ -394,7 +394,10 @@ class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
         xs_n = Fn.layer_norm_mod(self._pack, self.layer_norm_attention_src, x_src, dt)
         xd_n = Fn.layer_norm_mod(self._pack, self.layer_norm_attention_dest, x_dst, dt)
         kv = Fn.fused_linear(self._pack, xs_n, [self.lin_key, self.lin_value], dt)
-        csr = Fn.csr_for(edge_index, x_src.shape[0], x_dst.shape[0])
+        if group_size(model_comm_group) > 1 and shard_info is not None and shard_info.src_is_sharded():
+            # edges strategy (reference mapper.py:248-297 / khop_edges.py:317-409): every rank needs the k | v rows of all sources
+            kv = gather_rows(kv, shard_info.src_nodes, model_comm_group)
+        csr = Fn.csr_for(edge_index, kv.shape[0], x_dst.shape[0])
         dst_new = self._attend_project(xd_n, kv[:, :A], kv[:, A:], [self.lin_self], self.prepare_edges(edge_attr, dt), csr, x_dst, dt)
         src_new = x_src
         if self.update_src_nodes:

@@ -61,8 +61,8 @@ class BaseMapper(nn.Module):
     def _single_rank_only(model_comm_group) -> None:
         if group_size(model_comm_group) > 1:
             raise NotImplementedError(
-                "mappers run replicated (model_comm_group=None) in this build; the dst-range sharding of the processors is in "
-                "layers/processor.py (DESIGN.md, multi-GPU)"
+                "GNN (GraphConv) mappers run replicated (model_comm_group=None) in this build; the GraphTransformer mappers and both "
+                "processors implement the dst-range sharding (DESIGN.md, multi-GPU)"
             )
 
 
@@ -121,14 +121,36 @@ class GraphTransformerBaseMapper(BaseMapper):
     def post_process(self, x_dst: Tensor, dt: torch.dtype) -> Tensor:
         return x_dst
 
-    def _run(self, x: PairTensor, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted) -> Tensor:
+    def _run(self, x: PairTensor, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted,
+             keep_x_dst_sharded: bool = True) -> Tensor:  # fmt: skip
+        """Single GPU, or dst-range sharded over ``model_comm_group`` (reference "edges" strategy, mapper.py:248-386):
+        ``x[1]`` is then this rank's slice of the destination rows (``shard_info.dst_nodes``), ``x[0]`` either the full source
+        tensor (``shard_info.src_nodes is None``) or this rank's slice (its k | v rows are all-gathered inside the block);
+        the full dst-sorted edge list is cut to the edges into the local rows (cached per graph and group)."""
         Fn.forward_only_guard(self)
-        self._single_rank_only(model_comm_group)
         edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
+        world = group_size(model_comm_group)
+        if world > 1:
+            if shard_info is None or not shard_info.dst_is_sharded():
+                raise ValueError("sharded mapper: shard_info.dst_nodes (per-rank destination row counts) is required")
+            if shard_info.edges_are_sharded():
+                raise NotImplementedError("pre-sharded mapper edges: pass the full dst-sorted edge list (the split is cached)")
+            from .processor import _shard_edges_by_dst
+
+            n_src = sum(shard_info.src_nodes) if shard_info.src_is_sharded() else x[0].shape[0]
+            edge_attr, edge_index, edge_sizes = _shard_edges_by_dst(edge_attr, edge_index, sum(shard_info.dst_nodes), n_src, model_comm_group,
+                                                                    relabel_dst=True, dst_splits=shard_info.dst_nodes)  # fmt: skip
+            shard_info = BipartiteGraphShardInfo(src_nodes=shard_info.src_nodes, dst_nodes=shard_info.dst_nodes, edges=edge_sizes)
         dt = Fn.compute_dtype(*x)
         x_src, x_dst = self.pre_process(x, dt)
-        (_, x_dst_out), _ = self.proc((x_src, x_dst), edge_attr, edge_index, shard_info, batch_size, (x_src.shape[0], x_dst.shape[0]), None)
-        return self.post_process(x_dst_out, dt)
+        (_, x_dst_out), _ = self.proc((x_src, x_dst), edge_attr, edge_index, shard_info, batch_size, (x_src.shape[0], x_dst.shape[0]),
+                                      model_comm_group if world > 1 else None)  # fmt: skip
+        out = self.post_process(x_dst_out, dt)
+        if world > 1 and not keep_x_dst_sharded:
+            from ..distributed.graph import gather_rows
+
+            out = gather_rows(out, shard_info.dst_nodes, model_comm_group)
+        return out
 
 
 class GraphTransformerForwardMapper(GraphTransformerBaseMapper):
@@ -156,7 +178,7 @@ class GraphTransformerForwardMapper(GraphTransformerBaseMapper):
         edges_are_dst_sorted: bool = True,
         **kwargs,
     ) -> PairTensor:
-        return x[0], self._run(x, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted)
+        return x[0], self._run(x, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted, keep_x_dst_sharded)
 
 
 class GraphTransformerBackwardMapper(GraphTransformerBaseMapper):
@@ -193,7 +215,7 @@ class GraphTransformerBackwardMapper(GraphTransformerBaseMapper):
         edges_are_dst_sorted: bool = True,
         **kwargs,
     ) -> Tensor:
-        return self._run(x, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted)
+        return self._run(x, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted, keep_x_dst_sharded)
 
 
 # ------------------------------------------------------------------------------------------------------------

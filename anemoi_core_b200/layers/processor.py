@@ -59,16 +59,17 @@ class BaseProcessor(nn.Module):
 _SHARD_CACHE: dict = {}
 
 
-def _shard_edges_by_dst(edge_attr: Tensor, edge_index: Tensor, n_dst: int, n_src: int, group, relabel_dst: bool = False):
+def _shard_edges_by_dst(edge_attr: Tensor, edge_index: Tensor, n_dst: int, n_src: int, group, relabel_dst: bool = False, dst_splits=None):
     """Keep the edges into this rank's balanced dst range (reference ``shard_edges_1hop``, khop_edges.py:266-314).
     src ids stay global; dst ids stay global (GNN: the aggregate is computed over the full index range, block.py:375-391)
     or are relabelled to the local range (GraphTransformer).  The split is computed once per (graph, group) and cached.
     Returns (edge_attr view, edge_index, per-rank edge counts)."""
     world, rank = group_size(group), group_rank(group)
-    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), str(edge_index.device), n_dst, n_src, world, rank, relabel_dst)
+    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), str(edge_index.device), n_dst, n_src, world, rank, relabel_dst,
+           None if dst_splits is None else tuple(dst_splits))
     hit = _SHARD_CACHE.get(key)
     if hit is None:
-        part = build_graph_partition(edge_index, world, (n_src, n_dst))
+        part = build_graph_partition(edge_index, world, (n_src, n_dst), dst_splits=dst_splits)
         e0, e1 = part.edge_range(rank)
         local = edge_index[:, e0:e1].clone()
         if relabel_dst:

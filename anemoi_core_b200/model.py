@@ -48,25 +48,41 @@ class EncProcDec(nn.Module):
             raise ValueError(f"unknown model kind {kind!r}")
         self._graph: Optional[torch.cuda.CUDAGraph] = None
 
-    def forward(self, x_grid: Tensor, x_mesh: Tensor, graph: dict, model_comm_group=None, mesh_shards: Optional[list[int]] = None) -> Tensor:
+    def forward(self, x_grid: Tensor, x_mesh: Tensor, graph: dict, model_comm_group=None, mesh_shards: Optional[list[int]] = None,
+                grid_shards: Optional[list[int]] = None) -> Tensor:
+        """One forward step.  With ``model_comm_group`` (and per-rank ``mesh_shards`` / ``grid_shards``) every stage is dst-range sharded:
+        encoder (full grid sources, local mesh rows), processor (local rows, per-layer all-gather of k|v or x), latent skip, decoder (local
+        mesh sources all-gathered as k|v, local grid rows); the output rows are gathered at the end.  GNN mappers run replicated."""
+        from .distributed.graph import gather_rows
+        from .distributed.graph import group_size
+        from .distributed.graph import shard_rows
+
+        if group_size(model_comm_group) > 1 and mesh_shards is not None:
+            g = model_comm_group
+            if self.kind == "graphtransformer" and grid_shards is not None:
+                x_mesh_l = shard_rows(x_mesh, mesh_shards, g)
+                x_grid_l = shard_rows(x_grid, grid_shards, g)
+                _, x_local = self.encoder((x_grid, x_mesh_l), 1, BipartiteGraphShardInfo(src_nodes=None, dst_nodes=mesh_shards), graph["enc_attr"],
+                                          graph["enc_index"], g, keep_x_dst_sharded=True)  # fmt: skip
+                y_local = self.processor(x_local, 1, GraphShardInfo(nodes=mesh_shards), graph["proc_attr"], graph["proc_index"], g)
+                y_local = ops.add(y_local, x_local)  # latent skip (:295-296)
+                return self.decoder((y_local, x_grid_l), 1, BipartiteGraphShardInfo(src_nodes=mesh_shards, dst_nodes=grid_shards), graph["dec_attr"],
+                                    graph["dec_index"], g, keep_x_dst_sharded=False)  # fmt: skip
+            bi = BipartiteGraphShardInfo()
+            x_data_latent, x_latent = self.encoder((x_grid, x_mesh), 1, bi, graph["enc_attr"], graph["enc_index"])
+            x_local = shard_rows(x_latent, mesh_shards, g)
+            y_local = self.processor(x_local, 1, GraphShardInfo(nodes=mesh_shards), graph["proc_attr"], graph["proc_index"], g)
+            y_local = ops.add(y_local, x_local)
+            x_proc = gather_rows(y_local, mesh_shards, g)
+            return self.decoder((x_proc, x_data_latent), 1, bi, graph["dec_attr"], graph["dec_index"])
         bi = BipartiteGraphShardInfo()
         x_data_latent, x_latent = self.encoder((x_grid, x_mesh), 1, bi, graph["enc_attr"], graph["enc_index"])
-        n_mesh = x_latent.shape[0]
-        if model_comm_group is not None and mesh_shards is not None:
-            from .distributed.graph import gather_rows
-            from .distributed.graph import shard_rows
-
-            x_local = shard_rows(x_latent, mesh_shards, model_comm_group)
-            y_local = self.processor(x_local, 1, GraphShardInfo(nodes=mesh_shards), graph["proc_attr"], graph["proc_index"], model_comm_group)
-            y_local = ops.add(y_local, x_local)  # latent skip (:295-296)
-            x_proc = gather_rows(y_local, mesh_shards, model_comm_group)
-        else:
-            x_proc = self.processor(x_latent, 1, GraphShardInfo(nodes=[n_mesh]), graph["proc_attr"], graph["proc_index"])
-            x_proc = ops.add(x_proc, x_latent)
+        x_proc = self.processor(x_latent, 1, GraphShardInfo(nodes=[x_latent.shape[0]]), graph["proc_attr"], graph["proc_index"])
+        x_proc = ops.add(x_proc, x_latent)  # latent skip (:295-296)
         return self.decoder((x_proc, x_data_latent), 1, bi, graph["dec_attr"], graph["dec_index"])
 
     # -- CUDA graph of one whole step ------------------------------------------------------------------------------
-    def capture(self, x_grid: Tensor, x_mesh: Tensor, graph: dict, warmup: int = 2):
+    def capture(self, x_grid: Tensor, x_mesh: Tensor, graph: dict, warmup: int = 2, **fwd_kwargs):
         """Capture the forward on static input buffers; returns ``replay(x_grid=None, x_mesh=None) -> Tensor`` (static output).
         ~150 kernel launches of 5-200 us each become one graph launch."""
         static_grid, static_mesh = x_grid.clone(), x_mesh.clone()
@@ -74,11 +90,11 @@ class EncProcDec(nn.Module):
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(warmup):
-                self.forward(static_grid, static_mesh, graph)
+                self.forward(static_grid, static_mesh, graph, **fwd_kwargs)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(g):
-            static_out = self.forward(static_grid, static_mesh, graph)
+            static_out = self.forward(static_grid, static_mesh, graph, **fwd_kwargs)
         self._graph = g
 
         def replay(new_grid: Optional[Tensor] = None, new_mesh: Optional[Tensor] = None) -> Tensor:

@@ -238,10 +238,11 @@ def main():
     x_grid_h, x_mesh_h = x_grid_h.pin_memory(), x_mesh_h.pin_memory()
     x_grid, x_mesh = x_grid_h.to(dev), x_mesh_h.to(dev)
     mesh_shards = get_balanced_partition_sizes(gr["n_mesh"], world) if world > 1 else None
+    grid_shards = get_balanced_partition_sizes(gr["n_grid"], world) if world > 1 else None
 
     def step(xg, xm):
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-            return model(xg, xm, gd, group, mesh_shards)
+            return model(xg, xm, gd, group, mesh_shards, grid_shards)
 
     # ---- warm-up (also builds CSR plans, packed weights, TMA descriptors) and launch count per step --------------------
     for _ in range(2):
@@ -252,10 +253,21 @@ def main():
     launches_per_step = ops.LAUNCHES - n0
     torch.cuda.synchronize()
 
-    use_graph = not args.no_graph and world == 1
+    use_graph = not args.no_graph
     if use_graph:
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            replay = model.capture(x_grid, x_mesh, gd)
+        try:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                replay = model.capture(x_grid, x_mesh, gd, model_comm_group=group, mesh_shards=mesh_shards, grid_shards=grid_shards)
+        except Exception as e:  # noqa: BLE001  (e.g. a collective that cannot be captured): fall back to eager launches, and say so
+            if world == 1:
+                raise
+            print(f"[bench] CUDA-graph capture with NCCL failed on rank {rank} ({type(e).__name__}: {e}); using eager launches", file=sys.stderr)
+            use_graph = False
+    if world > 1:  # all ranks must agree
+        flag = torch.tensor([1 if use_graph else 0], device=dev)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        use_graph = bool(flag.item())
+    if use_graph:
         run = lambda: replay()  # noqa: E731
     else:
         run = lambda: step(x_grid, x_mesh)  # noqa: E731
@@ -381,7 +393,7 @@ def main():
         "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['desc']}", "batch": 1, "precision": "bf16 autocast, fp32 accumulate",
                    "launch": "cuda-graph replay" if use_graph else "eager", "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
-                   "parallelism": "single GPU" if world == 1 else f"processor dst-range sharded over {world} GPUs (all-gather of k|v rows per layer), mappers replicated"},
+                   "parallelism": "single GPU" if world == 1 else f"encoder / processor / decoder dst-range sharded over {world} GPUs (all-gather of k|v rows per layer over NCCL)"},
         "e2e": {"value": ms_e2e, "unit": "ms/step", "h2d_bytes_per_step": x_grid_h.numel() * 4 + x_mesh_h.numel() * 4,
                 "d2h_bytes_per_step": out_h.numel() * out_h.element_size()},
         "gpu_launches": launches_per_step * args.steps,

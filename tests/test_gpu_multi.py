@@ -48,6 +48,22 @@ def _worker(rank, world, init_file, ret):
                 err = ((got.float() - full.float()).abs().max() / full.float().abs().max()).item()
                 tol = 1e-5 if dt == torch.float32 else 2e-2
                 msgs.append((kind, str(dt), err, err <= tol))
+        # whole encoder -> processor -> decoder step, every stage dst-range sharded, against the single-GPU step
+        from anemoi_core_b200.model import EncProcDec
+
+        torch.manual_seed(5)
+        model = EncProcDec("graphtransformer", in_grid=20, in_mesh=12, out_grid=9, num_channels=256, num_layers=2, edge_dim=gr["edge_dim"],
+                           num_heads=8).cuda().eval()  # fmt: skip
+        gd = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in gr.items()}
+        gen = torch.Generator().manual_seed(9)
+        xg, xm = torch.randn(gr["n_grid"], 20, generator=gen).cuda(), torch.randn(n, 12, generator=gen).cuda()
+        gsz = get_balanced_partition_sizes(gr["n_grid"], world)
+        for dt in (torch.float32, torch.bfloat16):
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dt == torch.bfloat16):
+                full = model(xg, xm, gd)
+                got = model(xg, xm, gd, group, sizes, gsz)
+            err = ((got.float() - full.float()).abs().max() / full.float().abs().max()).item()
+            msgs.append(("encprocdec", str(dt), err, err <= (1e-5 if dt == torch.float32 else 2e-2) and got.shape == full.shape))
         ret[rank] = msgs
     except Exception as e:  # noqa: BLE001
         import traceback

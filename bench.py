@@ -253,7 +253,8 @@ def main():
     launches_per_step = ops.LAUNCHES - n0
     torch.cuda.synchronize()
 
-    use_graph = not args.no_graph
+    # NCCL collectives inside the captured graph hung on the 2-GPU box (round 1); multi-GPU runs launch eagerly unless ANEMOI_BENCH_GRAPH_NCCL=1
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("ANEMOI_BENCH_GRAPH_NCCL") == "1")
     if use_graph:
         try:
             with torch.autocast("cuda", dtype=torch.bfloat16):

@@ -57,9 +57,14 @@ class WeightPack:
 
     def __init__(self) -> None:
         self._store: dict = {}
+        self.frozen = False  # inference: skip the per-call parameter-version check (see freeze_packed_weights)
 
     def get(self, key, sources: Sequence[Optional[Tensor]], build: Callable[[], Tensor]) -> Tensor:
-        sig = tuple(None if t is None else (t.data_ptr(), t._version, t.device, t.dtype, tuple(t.shape)) for t in sources)
+        if self.frozen:
+            hit = self._store.get(key)
+            if hit is not None:
+                return hit[1]
+        sig = tuple(None if t is None else (t.data_ptr(), t._version) for t in sources)  # storage identity + in-place version counter
         hit = self._store.get(key)
         if hit is not None and hit[0] == sig:
             return hit[1]
@@ -101,6 +106,17 @@ class WeightPack:
         if p.dtype == torch.float32 and p.is_contiguous():
             return p.detach()
         return self.get(("f32", id(p)), [p], lambda: p.detach().float().contiguous())
+
+
+def freeze_packed_weights(module: nn.Module, frozen: bool = True) -> nn.Module:
+    """Inference switch: stop re-validating the derived (cast / concatenated / folded) weights against the parameters on every
+    call (a tuple of data_ptr / _version per source tensor, a few microseconds per GEMM on the host).  Call again with False —
+    or after it, mutate nothing — before changing parameters."""
+    for m in module.modules():
+        pack = getattr(m, "_pack", None)
+        if isinstance(pack, WeightPack):
+            pack.frozen = frozen
+    return module
 
 
 def as_operand(x: Tensor, dt: torch.dtype, k_weight: int) -> Tensor:

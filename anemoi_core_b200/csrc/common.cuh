@@ -216,6 +216,9 @@ struct EpiParams {
   int o_dtype;
   int64_t M, N;
   int flags;
+  // folded LayerNorm of the A operand: out = rstd_m * (acc - mean_m * colsum_n) + bias_n, applied before GELU
+  const float* ln_stats;   // [M, 2] = (mean, rstd) per row, or null
+  const float* ln_colsum;  // [N] = sum_k W'[n, k] of the gamma-scaled weight
 };
 
 }  // namespace anemoi

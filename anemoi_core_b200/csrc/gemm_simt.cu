@@ -9,6 +9,7 @@
 namespace anemoi {
 
 __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int64_t m, int64_t n, float acc) {
+  if (ep.ln_stats) acc = ep.ln_stats[2 * m + 1] * (acc - ep.ln_stats[2 * m] * ep.ln_colsum[n]);
   if (ep.bias) acc += ep.bias[n];
   if (ep.g1) acc += ep.g1[(int64_t)ep.idx1[m] * ep.ldg + n];
   if (ep.g2) acc += ep.g2[(int64_t)ep.idx2[m] * ep.ldg + n];

@@ -107,6 +107,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -151,6 +152,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace ptx
 
@@ -168,7 +178,10 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kWBytes;
   static constexpr int kTmemCols = 2 * BN;  // 128 / 256 / 512: powers of two
   static constexpr int kStagingBytes = 8 * 4096;  // one 32-row x 128-byte transpose buffer per epilogue warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias tile*/;
+  // layout: [barriers 256 B | bias tile 1 KB | LN column-sum tile 1 KB | pad to 3 KB][operand ring][epilogue staging] = exactly the 227 KB a
+  // CTA may own (BN = 256); relies on the dynamic shared window starting 1024-byte aligned (checked in the kernel, traps otherwise)
+  static constexpr int kHeadBytes = 3072;
+  static constexpr int kSmemBytes = kHeadBytes + kStages * kStageBytes + kStagingBytes;
 };
 
 // UMMA shared-memory descriptor for a K-major, 128-byte-swizzled tile (rows of 64 bf16 = 128 B; 8-row groups 1024 B apart).
@@ -183,7 +196,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 }
 
 // Epilogue mode bits (host-selected, warp-uniform): 0 = slow element-wise path.
-constexpr int kEpiFast = 1, kEpiOutF32 = 2, kEpiGelu = 4, kEpiRes = 8, kEpiGather = 16;
+constexpr int kEpiFast = 1, kEpiOutF32 = 2, kEpiGelu = 4, kEpiRes = 8, kEpiGather = 16, kEpiLnFold = 32;
 // debug ablations (ANEMOI_B200_GEMM_ABLATE, results are then wrong by construction): skip TMA loads / skip the epilogue body / skip the MMAs
 constexpr int kAblNoLoad = 256, kAblNoEpi = 512, kAblNoMma = 1024, kAblNoStore = 2048, kAblNoBias = 4096, kAblNoTmemLd = 8192;
 constexpr int kAblMask = kAblNoLoad | kAblNoEpi | kAblNoMma | kAblNoStore | kAblNoBias | kAblNoTmemLd;
@@ -198,16 +211,19 @@ struct EpiCtx {
 };
 
 // Fast epilogue: templated so that the inner loop has no runtime dtype / flag branches.
-template <int BN, bool OUT_F32, bool GELU, bool RES, bool GATHER>
+// Each warp owns 32 accumulator rows x kColsPerWarp columns and walks them in rounds of 64 bytes of output per row (32 bf16 / 16 fp32
+// columns).  The warp's 4 KB staging area is split into TWO 32-row x 64-byte buffers (64-byte-swizzled, the layout of a TMA box with a
+// 64-byte inner extent) used alternately: the TMA store of round r drains while round r+1 is computed (cp.async.bulk.wait_group.read 1).
+template <int BN, bool OUT_F32, bool GELU, bool RES, bool GATHER, bool LNF>
 __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams& ep, const CUtensorMap* tmOut, const CUtensorMap* tmRes) {
   constexpr int kColsPerWarp = BN / 2;
-  constexpr int CW = OUT_F32 ? 32 : 64;  // columns per 128-byte staging row
+  constexpr int CW = OUT_F32 ? 16 : 32;  // columns per 64-byte staging row
   constexpr int ROUNDS = kColsPerWarp / CW;
+  constexpr int NG = CW / 8;  // groups of 8 columns per round
   static_assert(kColsPerWarp % CW == 0, "tile width");
   const int lane = cx.lane;
-  const uint32_t my_row = cx.stg + lane * 128;
-  const uint32_t sw = (uint32_t)(lane & 7);
-  uint32_t res_phase = 0;
+  const uint32_t sw = (uint32_t)((lane >> 1) & 3);  // 64B swizzle: 16-byte chunk index ^= (row >> 1) & 3
+  uint32_t res_phase = 0, rcount = 0;
   int it = 0;
   for (int tile = cx.first_tile; tile < cx.num_tiles; tile += cx.tile_stride, ++it) {
     const int m_blk = tile / cx.tiles_n, n_blk = tile - m_blk * cx.tiles_n;
@@ -232,7 +248,29 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
           ptx::sts128(cx.bias_smem + (uint32_t)(cx.half * kColsPerWarp + lane * 4) * 4u, __float_as_uint(b4.x), __float_as_uint(b4.y),
                       __float_as_uint(b4.z), __float_as_uint(b4.w));
       }
+      if constexpr (LNF) {
+        if (cx.q == 1) {  // the second warp of the half stages the column sums of the gamma-scaled weight
+          const int c = n_blk * BN + cx.half * kColsPerWarp + lane * 4;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c + 4 <= (int)ep.N) {
+            b4 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + c));
+          } else {
+            if (c < (int)ep.N) b4.x = ep.ln_colsum[c];
+            if (c + 1 < (int)ep.N) b4.y = ep.ln_colsum[c + 1];
+            if (c + 2 < (int)ep.N) b4.z = ep.ln_colsum[c + 2];
+          }
+          if (lane * 4 < kColsPerWarp)
+            ptx::sts128(cx.bias_smem + 1024u + (uint32_t)(cx.half * kColsPerWarp + lane * 4) * 4u, __float_as_uint(b4.x), __float_as_uint(b4.y),
+                        __float_as_uint(b4.z), __float_as_uint(b4.w));
+        }
+      }
       asm volatile("bar.sync %0, 128;" ::"r"(1 + cx.half) : "memory");
+    }
+    float ln_mean = 0.f, ln_rstd = 1.f;
+    if constexpr (LNF) {
+      const int64_t r = min((int64_t)row0 + lane, ep.M - 1);
+      const float2 st = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + r);
+      ln_mean = st.x, ln_rstd = st.y;
     }
     const float* g1row = nullptr;
     const float* g2row = nullptr;
@@ -242,98 +280,32 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
       if (ep.g2) g2row = ep.g2 + (int64_t)__ldg(ep.idx2 + r) * ep.ldg;
     }
 #pragma unroll 1
-    for (int rd = 0; rd < ROUNDS; ++rd) {
+    for (int rd = 0; rd < ROUNDS; ++rd, ++rcount) {
       const int col_in_tile = cx.half * kColsPerWarp + rd * CW;
       const int col0 = n_blk * BN + col_in_tile;
-      // the previous TMA store must have finished READING the staging buffer before it is overwritten
-      if (lane == 0 && !(cx.abl & kAblNoStore)) ptx::bulk_wait_read0();
+      const uint32_t buf = cx.stg + (rcount & 1u) * 2048u;
+      const uint32_t my_row = buf + lane * 64;
+      // the TMA store issued from this buffer two rounds ago must have finished READING it
+      if (lane == 0 && !(cx.abl & kAblNoStore)) ptx::bulk_wait_read1();
       __syncwarp();
       if constexpr (RES) {
         if (lane == 0) {
-          ptx::mbar_expect_tx(cx.res_bar, 4096);
-          ptx::tma_load_2d(cx.stg, tmRes, cx.res_bar, col0, row0);  // OOB rows / columns arrive as zeros
+          ptx::mbar_expect_tx(cx.res_bar, 2048);
+          ptx::tma_load_2d(buf, tmRes, cx.res_bar, col0, row0);  // OOB rows / columns arrive as zeros
         }
       }
       if (rd == 0) {
         ptx::mbar_wait(cx.tfull0 + 8u * as, aphase);
         ptx::tc_fence_after();
       }
-      if constexpr (RES) {
-        ptx::mbar_wait(cx.res_bar, res_phase);
-        res_phase ^= 1u;
-      }
+      uint32_t r[32];
+      if (!(cx.abl & kAblNoTmemLd)) {
+        const uint32_t taddr = cx.tmem_base + ((uint32_t)(cx.q * 32) << 16) + (uint32_t)(as * BN + col_in_tile);
+        if constexpr (OUT_F32) ptx::tmem_ld_32x32b_x16(taddr, r); else ptx::tmem_ld_32x32b_x32(taddr, r);
+        ptx::tmem_wait_ld();
+      } else {
 #pragma unroll
-      for (int h32 = 0; h32 < CW; h32 += 32) {
-        uint32_t r[32];
-        if (!(cx.abl & kAblNoTmemLd)) {
-          ptx::tmem_ld_32x32b_x32(cx.tmem_base + ((uint32_t)(cx.q * 32) << 16) + (uint32_t)(as * BN + col_in_tile + h32), r);
-          ptx::tmem_wait_ld();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0x3f800000u + j;
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int col = col0 + h32 + g * 8;
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-          if (ep.bias && !(cx.abl & kAblNoBias)) {
-            const uint32_t ba = cx.bias_smem + (uint32_t)(col_in_tile + h32 + g * 8) * 4u;
-            const uint4 b0 = ptx::lds128(ba), b1 = ptx::lds128(ba + 16);
-            v[0] += __uint_as_float(b0.x), v[1] += __uint_as_float(b0.y), v[2] += __uint_as_float(b0.z), v[3] += __uint_as_float(b0.w);
-            v[4] += __uint_as_float(b1.x), v[5] += __uint_as_float(b1.y), v[6] += __uint_as_float(b1.z), v[7] += __uint_as_float(b1.w);
-          }
-          if (col + 8 <= (int)ep.N) {
-            if constexpr (GATHER) {
-              if (g1row) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(g1row + col)), b1 = __ldg(reinterpret_cast<const float4*>(g1row + col) + 1);
-                v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
-              }
-              if (g2row) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(g2row + col)), b1 = __ldg(reinterpret_cast<const float4*>(g2row + col) + 1);
-                v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
-              }
-            }
-          } else if (col < (int)ep.N) {  // ragged last 8-column group of the matrix
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (col + j < (int)ep.N) {
-                if constexpr (GATHER) {
-                  if (g1row) v[j] += g1row[col + j];
-                  if (g2row) v[j] += g2row[col + j];
-                }
-              }
-            }
-          }
-          if constexpr (GELU) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = gelu_erf_fast(v[j]);
-          }
-          if constexpr (OUT_F32) {
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const uint32_t addr = my_row + ((((uint32_t)(h32 + g * 8) * 4u >> 4) + hh) ^ sw) * 16u;
-              if constexpr (RES) {
-                const uint4 rv = ptx::lds128(addr);
-                v[4 * hh] += __uint_as_float(rv.x), v[4 * hh + 1] += __uint_as_float(rv.y);
-                v[4 * hh + 2] += __uint_as_float(rv.z), v[4 * hh + 3] += __uint_as_float(rv.w);
-              }
-              ptx::sts128(addr, __float_as_uint(v[4 * hh]), __float_as_uint(v[4 * hh + 1]), __float_as_uint(v[4 * hh + 2]),
-                          __float_as_uint(v[4 * hh + 3]));
-            }
-          } else {
-            const uint32_t addr = my_row + ((((uint32_t)(h32 + g * 8) * 2u) >> 4) ^ sw) * 16u;
-            if constexpr (RES) {
-              const uint4 rv = ptx::lds128(addr);
-              v[0] += __uint_as_float(rv.x << 16), v[1] += __uint_as_float(rv.x & 0xffff0000u);
-              v[2] += __uint_as_float(rv.y << 16), v[3] += __uint_as_float(rv.y & 0xffff0000u);
-              v[4] += __uint_as_float(rv.z << 16), v[5] += __uint_as_float(rv.z & 0xffff0000u);
-              v[6] += __uint_as_float(rv.w << 16), v[7] += __uint_as_float(rv.w & 0xffff0000u);
-            }
-            ptx::sts128(addr, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          }
-        }
+        for (int j = 0; j < 32; ++j) r[j] = 0x3f800000u + j;
       }
       if (rd == ROUNDS - 1) {  // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
         ptx::tc_fence_before();
@@ -345,10 +317,83 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
             ptx::mbar_arrive(cx.tempty0 + 8u * as);
         }
       }
+      if constexpr (RES) {
+        ptx::mbar_wait(cx.res_bar, res_phase);
+        res_phase ^= 1u;
+      }
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int col = col0 + g * 8;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+        if constexpr (LNF) {
+          const uint32_t sa = cx.bias_smem + 1024u + (uint32_t)(col_in_tile + g * 8) * 4u;
+          const uint4 s0 = ptx::lds128(sa), s1 = ptx::lds128(sa + 16);
+          const float nm = -ln_mean;
+          v[0] = ln_rstd * fmaf(nm, __uint_as_float(s0.x), v[0]), v[1] = ln_rstd * fmaf(nm, __uint_as_float(s0.y), v[1]);
+          v[2] = ln_rstd * fmaf(nm, __uint_as_float(s0.z), v[2]), v[3] = ln_rstd * fmaf(nm, __uint_as_float(s0.w), v[3]);
+          v[4] = ln_rstd * fmaf(nm, __uint_as_float(s1.x), v[4]), v[5] = ln_rstd * fmaf(nm, __uint_as_float(s1.y), v[5]);
+          v[6] = ln_rstd * fmaf(nm, __uint_as_float(s1.z), v[6]), v[7] = ln_rstd * fmaf(nm, __uint_as_float(s1.w), v[7]);
+        }
+        if (ep.bias && !(cx.abl & kAblNoBias)) {
+          const uint32_t ba = cx.bias_smem + (uint32_t)(col_in_tile + g * 8) * 4u;
+          const uint4 b0 = ptx::lds128(ba), b1 = ptx::lds128(ba + 16);
+          v[0] += __uint_as_float(b0.x), v[1] += __uint_as_float(b0.y), v[2] += __uint_as_float(b0.z), v[3] += __uint_as_float(b0.w);
+          v[4] += __uint_as_float(b1.x), v[5] += __uint_as_float(b1.y), v[6] += __uint_as_float(b1.z), v[7] += __uint_as_float(b1.w);
+        }
+        if constexpr (GATHER) {
+          if (col + 8 <= (int)ep.N) {
+            if (g1row) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(g1row + col)), b1 = __ldg(reinterpret_cast<const float4*>(g1row + col) + 1);
+              v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+            }
+            if (g2row) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(g2row + col)), b1 = __ldg(reinterpret_cast<const float4*>(g2row + col) + 1);
+              v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+            }
+          } else if (col < (int)ep.N) {  // ragged last 8-column group of the matrix
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (col + j < (int)ep.N) {
+                if (g1row) v[j] += g1row[col + j];
+                if (g2row) v[j] += g2row[col + j];
+              }
+            }
+          }
+        }
+        if constexpr (GELU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = gelu_erf_fast(v[j]);
+        }
+        if constexpr (OUT_F32) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const uint32_t addr = my_row + ((((uint32_t)(2 * g + hh)) ^ sw) << 4);
+            if constexpr (RES) {
+              const uint4 rv = ptx::lds128(addr);
+              v[4 * hh] += __uint_as_float(rv.x), v[4 * hh + 1] += __uint_as_float(rv.y);
+              v[4 * hh + 2] += __uint_as_float(rv.z), v[4 * hh + 3] += __uint_as_float(rv.w);
+            }
+            ptx::sts128(addr, __float_as_uint(v[4 * hh]), __float_as_uint(v[4 * hh + 1]), __float_as_uint(v[4 * hh + 2]),
+                        __float_as_uint(v[4 * hh + 3]));
+          }
+        } else {
+          const uint32_t addr = my_row + ((((uint32_t)g) ^ sw) << 4);
+          if constexpr (RES) {
+            const uint4 rv = ptx::lds128(addr);
+            v[0] += __uint_as_float(rv.x << 16), v[1] += __uint_as_float(rv.x & 0xffff0000u);
+            v[2] += __uint_as_float(rv.y << 16), v[3] += __uint_as_float(rv.y & 0xffff0000u);
+            v[4] += __uint_as_float(rv.z << 16), v[5] += __uint_as_float(rv.z & 0xffff0000u);
+            v[6] += __uint_as_float(rv.w << 16), v[7] += __uint_as_float(rv.w & 0xffff0000u);
+          }
+          ptx::sts128(addr, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+      }
       ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
       __syncwarp();
       if (lane == 0 && !(cx.abl & kAblNoStore)) {
-        ptx::tma_store_2d(tmOut, cx.stg, col0, row0);  // rows >= M / columns >= N are clipped by the hardware
+        ptx::tma_store_2d(tmOut, buf, col0, row0);  // rows >= M / columns >= N are clipped by the hardware
         ptx::bulk_commit();
       }
     }
@@ -385,6 +430,7 @@ __device__ __noinline__ void epilogue_generic(const EpiCtx& cx, const EpiParams&
           const int64_t n = col0 + j;
           if (n >= ep.N) break;
           float a = __uint_as_float(r[j]);
+          if (ep.ln_stats) a = ep.ln_stats[2 * row + 1] * (a - ep.ln_stats[2 * row] * ep.ln_colsum[n]);
           if (ep.bias) a += ep.bias[n];
           if (g1row) a += g1row[n];
           if (g2row) a += g2row[n];
@@ -412,9 +458,10 @@ __global__ void __launch_bounds__(kThreads, 1)
                              int tiles_n, int epi_mode, const EpiParams ep) {
   using Cfg = GemmCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = ptx::smem_u32(smem_raw);
+  if (bar_base & 1023u) __trap();  // the 128B-swizzled operand tiles need 1024-byte alignment (no static shared memory in this kernel)
+  const uint32_t smem_base = bar_base + Cfg::kHeadBytes;
   const uint32_t staging_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
-  const uint32_t bar_base = staging_base + Cfg::kStagingBytes;
   // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], res[8], then the TMEM base address slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
@@ -556,7 +603,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     } else {
 #define ANEMOI_EPI_CASE(F32, GELU, RES, GATHER)                                                                          \
   case (F32 ? kEpiOutF32 : 0) | (GELU ? kEpiGelu : 0) | (RES ? kEpiRes : 0) | (GATHER ? kEpiGather : 0):                   \
-    epilogue_fast<BN, F32, GELU, RES, GATHER>(cx, ep, &tmOut, &tmRes);                                                     \
+    epilogue_fast<BN, F32, GELU, RES, GATHER, false>(cx, ep, &tmOut, &tmRes);                                              \
+    break;
+#define ANEMOI_EPI_CASE_LN(F32, GELU)                                                                                     \
+  case (F32 ? kEpiOutF32 : 0) | (GELU ? kEpiGelu : 0) | kEpiLnFold:                                                        \
+    epilogue_fast<BN, F32, GELU, false, false, true>(cx, ep, &tmOut, &tmRes);                                              \
     break;
       switch (epi_mode & ~kEpiFast & ~kAblMask) {
         ANEMOI_EPI_CASE(false, false, false, false)
@@ -571,9 +622,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         ANEMOI_EPI_CASE(false, true, false, true)
         ANEMOI_EPI_CASE(true, false, false, true)
         ANEMOI_EPI_CASE(true, true, false, true)
+        ANEMOI_EPI_CASE_LN(false, false)
+        ANEMOI_EPI_CASE_LN(false, true)
+        ANEMOI_EPI_CASE_LN(true, false)
+        ANEMOI_EPI_CASE_LN(true, true)
         default: __trap();  // host never selects another combination
       }
 #undef ANEMOI_EPI_CASE
+#undef ANEMOI_EPI_CASE_LN
     }
   }
   __syncwarp();  // re-converge the single-lane producer / MMA warps before the aligned barrier
@@ -605,26 +661,26 @@ static PFN_encodeTiled get_encode() {
 struct MapKey {
   const void* ptr;
   int64_t rows, cols, ld;
-  int box_rows, es;
+  int box_rows, es, inner;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && es == o.es;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && es == o.es && inner == o.inner;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr);
     auto mix = [&](int64_t v) { h ^= std::hash<int64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.rows), mix(k.cols), mix(k.ld), mix(k.box_rows), mix(k.es);
+    mix(k.rows), mix(k.cols), mix(k.ld), mix(k.box_rows), mix(k.es), mix(k.inner);
     return h;
   }
 };
 
 // [rows, cols] row-major of element size es (2 = bf16, 4 = fp32), leading dimension ld (elements); box = box_rows x 128 bytes,
 // 128-byte swizzle, zero OOB fill on loads / clipping on stores.
-static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out, int es = 2) {
+static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out, int es = 2, int inner = 128) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, rows, cols, ld, box_rows, es};
+  MapKey key{ptr, rows, cols, ld, box_rows, es, inner};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -640,10 +696,10 @@ static int get_tensor_map(const void* ptr, int64_t rows, int64_t cols, int64_t l
   }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * es};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(inner / es), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   inner == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("linear(tcgen05): cuTensorMapEncodeTiled failed with CUresult %d (ptr %p rows %lld cols %lld ld %lld box %d)", (int)r, ptr,
               (long long)rows, (long long)cols, (long long)ld, box_rows);
@@ -713,15 +769,17 @@ int linear_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, int64
   bool fast = a16(ep.out) && (ep.ldo * os) % 16 == 0 && (!ep.bias || a16(ep.bias)) &&
               (!gather || ((!ep.g1 || a16(ep.g1)) && (!ep.g2 || a16(ep.g2)) && ep.ldg % 4 == 0 && !ep.residual));
   if (ep.residual) fast = fast && ep.r_dtype == ep.o_dtype && a16(ep.residual) && (ep.ldr * os) % 16 == 0;
+  // folded LayerNorm: fast path needs a (non-null) bias tile, no residual / gather, aligned stats and column sums
+  if (ep.ln_stats) fast = fast && ep.bias && !ep.residual && !gather && a16(ep.ln_colsum) && (reinterpret_cast<uintptr_t>(ep.ln_stats) & 7) == 0;
   int epi_mode = 0;
   tmOut = tmA, tmRes = tmA;  // placeholders when unused
   if (fast) {
     epi_mode = kEpiFast | (os == 4 ? kEpiOutF32 : 0) | ((ep.flags & ANEMOI_EPI_GELU) ? kEpiGelu : 0) | (ep.residual ? kEpiRes : 0) |
-               (gather ? kEpiGather : 0);
-    rc = get_tensor_map(ep.out, ep.M, ep.N, ep.ldo, 32, &tmOut, os);
+               (gather ? kEpiGather : 0) | (ep.ln_stats ? kEpiLnFold : 0);
+    rc = get_tensor_map(ep.out, ep.M, ep.N, ep.ldo, 32, &tmOut, os, 64);
     if (rc) return rc;
     if (ep.residual) {
-      rc = get_tensor_map(ep.residual, ep.M, ep.N, ep.ldr, 32, &tmRes, os);
+      rc = get_tensor_map(ep.residual, ep.M, ep.N, ep.ldr, 32, &tmRes, os, 64);
       if (rc) return rc;
     }
   }

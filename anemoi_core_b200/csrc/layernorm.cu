@@ -73,6 +73,43 @@ __global__ void __launch_bounds__(256) layer_norm_vec_kernel(const TI* __restric
   }
 }
 
+// Row statistics only (mean, rstd): the LayerNorm itself is folded into the consuming GEMM (gemm_tcgen05.cu).  One warp per row,
+// 16-byte loads, two-pass variance in registers; reads x once, writes 8 bytes per row.
+template <typename TI, int ITERS>
+__global__ void __launch_bounds__(256) row_stats_kernel(const TI* __restrict__ x, int64_t ldx, float2* __restrict__ stats, int64_t M, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < M; m += warps_total) {
+    const TI* xr = x + m * ldx;
+    float v[ITERS][8];
+    float s = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = it * 256 + lane * 8;
+      if (c < C) {
+        load_vec_f32<TI, 8>(xr + c, v[it]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[it][i];
+      }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = it * 256 + lane * 8;
+      if (c < C) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = v[it][i] - mean;
+          q += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    if (lane == 0) stats[m] = make_float2(mean, rstd);
+  }
+}
+
 // Generic path: any C / alignment.  Lane strides over the row; re-reads hit L1.
 __global__ void __launch_bounds__(256) layer_norm_generic_kernel(const void* __restrict__ x, int64_t ldx, int x_dtype,
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -167,4 +204,35 @@ extern "C" int anemoi_b200_layer_norm(const void* x, int64_t ldx, int x_dtype, c
   layer_norm_generic_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, ldx, x_dtype, gamma, beta, residual, ldr, r_dtype, y, ldy, y_dtype, M, groups,
                                                              (int)C, eps);
   return launch_status("layer_norm_generic_kernel");
+}
+
+extern "C" int anemoi_b200_row_stats(const void* x, int64_t ldx, int x_dtype, float* stats, int64_t M, int64_t C, float eps, void* stream) {
+  ANEMOI_CHECK_ARG(M >= 0 && C >= 8 && C % 8 == 0 && C <= 2048 && ldx >= C, "row_stats: need C % 8 == 0, 8 <= C <= 2048");
+  ANEMOI_CHECK_ARG(x_dtype == ANEMOI_F32 || x_dtype == ANEMOI_BF16, "row_stats: bad dtype");
+  if (M == 0) return 0;
+  ANEMOI_CHECK_ARG(x && stats, "row_stats: null pointer");
+  const int es = x_dtype == ANEMOI_BF16 ? 2 : 4;
+  ANEMOI_CHECK_ARG(aligned16(x) && (ldx * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(stats) & 7) == 0, "row_stats: rows must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t blocks = (M + 7) / 8;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+#define RS_LAUNCH(T, IT) row_stats_kernel<T, IT><<<(unsigned)blocks, 256, 0, s>>>((const T*)x, ldx, reinterpret_cast<float2*>(stats), M, (int)C, eps)
+#define RS_PICK(T)        \
+  if (C <= 256)           \
+    RS_LAUNCH(T, 1);      \
+  else if (C <= 512)      \
+    RS_LAUNCH(T, 2);      \
+  else if (C <= 1024)     \
+    RS_LAUNCH(T, 4);      \
+  else                    \
+    RS_LAUNCH(T, 8)
+  if (x_dtype == ANEMOI_BF16) {
+    RS_PICK(__nv_bfloat16);
+  } else {
+    RS_PICK(float);
+  }
+#undef RS_PICK
+#undef RS_LAUNCH
+  return launch_status("row_stats_kernel");
 }

@@ -139,6 +139,62 @@ def fused_linear(pack: WeightPack, x: Tensor, layers: Sequence[nn.Module], dt: t
     return ops.linear(as_operand(x, dt, w.shape[1]), w, bias, **kw)
 
 
+def can_fold_ln(ln: nn.Module, k: int, dt: torch.dtype) -> bool:
+    """A LayerNorm directly in front of a tcgen05 GEMM is folded into it (bf16 path only; the fp32 parity path keeps the kernel)."""
+    return dt == torch.bfloat16 and isinstance(ln, torch.nn.LayerNorm) and k % 8 == 0 and 64 <= k <= 2048
+
+
+def ln_linear(pack: WeightPack, x: Tensor, ln: nn.Module, key, sources: Sequence[Optional[Tensor]], build32: Callable[[], tuple], dt: torch.dtype,
+              **kw) -> Tensor:  # fmt: skip
+    """``linear(LayerNorm(x))`` for the weight / bias produced by ``build32() -> (w fp32 [N, K], b fp32 [N] | None)``.
+
+    bf16: the LayerNorm is folded into the GEMM — W' = W * gamma, bias' = b + W beta, colsum = sum_k bf16(W') — and only the per-row
+    (mean, rstd) are computed beforehand (``ops.row_stats`` on the bf16 operand, so constant rows cancel exactly); the normalised
+    activations are never written.  fp32 (parity mode) or unsupported shapes: LayerNorm kernel, then the plain GEMM."""
+    from .normalization import _check_plain_layernorm
+
+    _check_plain_layernorm(ln)
+    k = x.shape[1]
+    srcs = list(sources) + [ln.weight, ln.bias]
+    if can_fold_ln(ln, k, dt):
+
+        def build():
+            w32, b32 = build32()
+            gamma = ln.weight.detach().float() if ln.weight is not None else torch.ones(k, device=w32.device)
+            beta = ln.bias.detach().float() if ln.bias is not None else torch.zeros(k, device=w32.device)
+            wf = (w32 * gamma).to(dt).contiguous()
+            bias = (b32 if b32 is not None else torch.zeros(w32.shape[0], device=w32.device)) + w32 @ beta
+            return wf, bias.contiguous(), wf.float().sum(1).contiguous()
+
+        wf, bias, colsum = pack.get(("ln_fold", key, dt), srcs, build)
+        a = as_operand(x, dt, k)
+        return ops.linear(a, wf, bias, ln_stats=ops.row_stats(a, ln.eps), ln_colsum=colsum, **kw)
+
+    def build_plain():
+        w32, b32 = build32()
+        kk = w32.shape[1]
+        if pad_k(kk, dt) != kk:
+            w32 = torch.nn.functional.pad(w32, (0, pad_k(kk, dt) - kk))
+        return w32.to(dt).contiguous(), (None if b32 is None else b32.contiguous())
+
+    w, b = pack.get(("ln_plain", key, dt), srcs, build_plain)
+    xn = ops.layer_norm(x, pack.f32(ln.weight), pack.f32(ln.bias), ln.eps, out_dtype=dt)
+    return ops.linear(as_operand(xn, dt, w.shape[1]), w, b, **kw)
+
+
+def cat_linear32(layers: Sequence[nn.Module]) -> tuple:
+    """fp32 (weight, bias) of row-concatenated Linear containers."""
+    w = torch.cat([l.weight.detach().float() for l in layers], 0)
+    if all(getattr(l, "bias", None) is None for l in layers):
+        return w, None
+    b = torch.cat([l.bias.detach().float() if l.bias is not None else torch.zeros(l.weight.shape[0], device=w.device) for l in layers])
+    return w, b
+
+
+def linear_sources(layers: Sequence[nn.Module]) -> list:
+    return [l.weight for l in layers] + [getattr(l, "bias", None) for l in layers]
+
+
 def layer_norm_mod(pack: WeightPack, ln: nn.Module, x: Tensor, dt: torch.dtype, residual: Optional[Tensor] = None, groups: int = 1) -> Tensor:
     from .normalization import _check_plain_layernorm
 

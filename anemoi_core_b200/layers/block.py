@@ -206,35 +206,31 @@ class GraphTransformerBaseBlock(nn.Module):
         H, Ch = self.num_heads, self.out_channels_conv
         return self.lin_edge.weight.detach().float().view(H, Ch, -1)  # [H, Ch, D]
 
-    def _dst_weight(self, layers, dt: torch.dtype, fold_q: bool) -> tuple[Tensor, Optional[Tensor]]:
-        """Row-concatenated weight/bias of the dst-side GEMM; with ``fold_q`` the rows (h, a) = W_e,h[:, a]^T W_q,h are appended."""
+    def _dst_weight32(self, layers, fold_q: bool) -> tuple[Tensor, Optional[Tensor]]:
+        """fp32 (weight, bias) of the dst-side GEMM: rows of ``layers`` concatenated; with ``fold_q`` the rows
+        (h, a) = W_e,h[:, a]^T W_q,h (and their bias W_e,h[:, a]^T b_q,h) are appended."""
+        w, b = Fn.cat_linear32(layers)
         if not fold_q:
-            return self._pack.weight(layers, dt), self._pack.bias(layers)
+            return w, b
         H, Ch = self.num_heads, self.out_channels_conv
         d, dp, hdp = self._fold_dims()
-        srcs = [l.weight for l in layers] + [getattr(l, "bias", None) for l in layers] + [self.lin_edge.weight]
+        we = self._w_edge_heads()
+        wq = self.lin_query.weight.detach().float().view(H, Ch, -1)
+        wf = torch.zeros(hdp, wq.shape[-1], device=wq.device)
+        wf[: H * dp].view(H, dp, -1)[:, :d] = torch.einsum("hca,hci->hai", we, wq)
+        bf = torch.zeros(hdp, device=we.device)
+        if self.lin_query.bias is not None:
+            bf[: H * dp].view(H, dp)[:, :d] = torch.einsum("hca,hc->ha", we, self.lin_query.bias.detach().float().view(H, Ch))
+        if b is None:
+            b = torch.zeros(w.shape[0], device=w.device)
+        return torch.cat([w, wf], 0), torch.cat([b, bf])
 
-        def build_w() -> Tensor:
-            we = self._w_edge_heads()
-            wq = self.lin_query.weight.detach().float().view(H, Ch, -1)
-            wf = torch.zeros(hdp, wq.shape[-1], device=wq.device)
-            wf[: H * dp].view(H, dp, -1)[:, :d] = torch.einsum("hca,hci->hai", we, wq)
-            w = torch.cat([l.weight.detach().float() for l in layers] + [wf], 0)
-            k = w.shape[1]
-            if Fn.pad_k(k, dt) != k:
-                w = torch.nn.functional.pad(w, (0, Fn.pad_k(k, dt) - k))
-            return w.to(dt).contiguous()
-
-        def build_b() -> Tensor:
-            we = self._w_edge_heads()
-            bf = torch.zeros(hdp, device=we.device)
-            if self.lin_query.bias is not None:
-                bf[: H * dp].view(H, dp)[:, :d] = torch.einsum("hca,hc->ha", we, self.lin_query.bias.detach().float().view(H, Ch))
-            parts = [l.bias.detach().float() if l.bias is not None else torch.zeros(l.weight.shape[0], device=we.device) for l in layers]
-            return torch.cat(parts + [bf]).contiguous()
-
-        key = tuple(id(l) for l in layers)
-        return self._pack.get(("w_dst_fold", key, dt), srcs, build_w), self._pack.get(("b_dst_fold", key), srcs, build_b)
+    def _dst_gemm(self, x_raw: Tensor, ln: nn.Module, layers, dt: torch.dtype) -> Tensor:
+        """LayerNorm + dst-side GEMM (q | ... | self | qw); the LayerNorm is folded into the GEMM on the bf16 path."""
+        fold_q = self._use_fold(dt) and not self.qk_norm
+        key = ("dst", tuple(id(l) for l in layers), fold_q)
+        srcs = Fn.linear_sources(layers) + [self.lin_edge.weight]
+        return Fn.ln_linear(self._pack, x_raw, ln, key, srcs, lambda: self._dst_weight32(layers, fold_q), dt)
 
     def _qw_blockdiag(self, dt: torch.dtype) -> Tensor:
         """[hdp, A] block-diagonal W_e^T for the qk_norm case (qw must be taken from the normalised query)."""
@@ -275,8 +271,8 @@ class GraphTransformerBaseBlock(nn.Module):
                                         gelu=True)  # fmt: skip
         return Fn.pad_edge_attr(edge_attr, ops.ATTN_MAX_EDGE_DIM if self._use_fold(dt) else 0)
 
-    def _attend_project(self, xd_n: Tensor, k: Tensor, v: Tensor, dst_layers, edge_attr_p: Tensor, csr: ops.GraphCSR, x_skip: Tensor,
-                        dt: torch.dtype, dst_buf: Optional[Tensor] = None) -> Tensor:  # fmt: skip
+    def _attend_project(self, x_dst: Tensor, ln_dst: nn.Module, k: Tensor, v: Tensor, dst_layers, edge_attr_p: Tensor, csr: ops.GraphCSR,
+                        x_skip: Tensor, dt: torch.dtype, dst_buf: Optional[Tensor] = None) -> Tensor:  # fmt: skip
         """dst-side GEMM (q | [k | v |] self | qw) -> attention (+ self) -> projection (+ skip) -> LN -> MLP (+ residual).
 
         ``dst_layers`` = the Linear containers of the dst-side GEMM *after* lin_query (processor: key, value, self — k and v then
@@ -287,8 +283,7 @@ class GraphTransformerBaseBlock(nn.Module):
         d, dp, hdp = self._fold_dims()
         layers = [self.lin_query] + list(dst_layers)
         if dst_buf is None:
-            w, b = self._dst_weight(layers, dt, fold and not self.qk_norm)
-            dst_buf = ops.linear(Fn.as_operand(xd_n, dt, w.shape[1]), w, b)
+            dst_buf = self._dst_gemm(x_dst, ln_dst, layers, dt)
         n_lin = len(layers)
         q = dst_buf[:, :A]
         x_r = dst_buf[:, (n_lin - 1) * A : n_lin * A]
@@ -309,8 +304,7 @@ class GraphTransformerBaseBlock(nn.Module):
             att = ops.gt_attention(q, k, v, csr, H, edge_attr=edge_attr_p, w_edge=w_e, b_edge=b_e, add=x_r)
         skip = x_skip if x_skip.dtype in Fn.SUPPORTED else x_skip.float()
         out = ops.linear(att, self._proj_weight(dt, fold), self._pack.bias([self.projection]), residual=skip)
-        h = Fn.layer_norm_mod(self._pack, self.layer_norm_mlp_dst, out, dt)
-        return self.node_dst_mlp.run(h, dt, residual=out)
+        return self.node_dst_mlp.run(out, dt, residual=out, pre_ln=self.layer_norm_mlp_dst)
 
 
 class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
@@ -339,20 +333,20 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
             raise NotImplementedError("conditional LayerNorm (cond=...) is not implemented")
         dt = Fn.compute_dtype(x)
         A = self.attn_channels
-        xn = Fn.layer_norm_mod(self._pack, self.layer_norm_attention, x, dt)
+        ln = self.layer_norm_attention
+        dst_layers = [self.lin_key, self.lin_value, self.lin_self]
         ea = edge_attr_prepared if edge_attr_prepared is not None else self.prepare_edges(edge_attr, dt)
         world = group_size(model_comm_group)
         if world == 1:
             csr = Fn.csr_for(edge_index, x.shape[0], x.shape[0])
-            return self._attend_project(xn, None, None, [self.lin_key, self.lin_value, self.lin_self], ea, csr, x, dt), edge_attr
+            return self._attend_project(x, ln, None, None, dst_layers, ea, csr, x, dt), edge_attr
         # edges strategy (block.py:1148-1183): each rank owns a dst range and needs the k | v rows of every source node
-        w, b = self._dst_weight([self.lin_query, self.lin_key, self.lin_value, self.lin_self], dt, self._use_fold(dt) and not self.qk_norm)
-        buf = ops.linear(Fn.as_operand(xn, dt, w.shape[1]), w, b)
+        buf = self._dst_gemm(x, ln, [self.lin_query] + dst_layers, dt)
         kv_full = gather_rows(buf[:, A : 3 * A], shard_info.nodes, model_comm_group)
         csr = Fn.csr_for(edge_index, kv_full.shape[0], x.shape[0])
         if self.qk_norm:
             raise NotImplementedError("qk_norm with a sharded processor")
-        out = self._attend_project(xn, kv_full[:, :A], kv_full[:, A:], [self.lin_key, self.lin_value, self.lin_self], ea, csr, x, dt, dst_buf=buf)
+        out = self._attend_project(x, ln, kv_full[:, :A], kv_full[:, A:], dst_layers, ea, csr, x, dt, dst_buf=buf)
         return out, edge_attr
 
 
@@ -391,16 +385,16 @@ class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
         x_src, x_dst = x
         dt = Fn.compute_dtype(x_src, x_dst)
         A = self.attn_channels
-        xs_n = Fn.layer_norm_mod(self._pack, self.layer_norm_attention_src, x_src, dt)
-        xd_n = Fn.layer_norm_mod(self._pack, self.layer_norm_attention_dest, x_dst, dt)
-        kv = Fn.fused_linear(self._pack, xs_n, [self.lin_key, self.lin_value], dt)
+        kv_layers = [self.lin_key, self.lin_value]
+        kv = Fn.ln_linear(self._pack, x_src, self.layer_norm_attention_src, ("kv",), Fn.linear_sources(kv_layers), lambda: Fn.cat_linear32(kv_layers), dt)
         if group_size(model_comm_group) > 1 and shard_info is not None and shard_info.src_is_sharded():
             # edges strategy (reference mapper.py:248-297 / khop_edges.py:317-409): every rank needs the k | v rows of all sources
             kv = gather_rows(kv, shard_info.src_nodes, model_comm_group)
         csr = Fn.csr_for(edge_index, kv.shape[0], x_dst.shape[0])
-        dst_new = self._attend_project(xd_n, kv[:, :A], kv[:, A:], [self.lin_self], self.prepare_edges(edge_attr, dt), csr, x_dst, dt)
+        dst_new = self._attend_project(x_dst, self.layer_norm_attention_dest, kv[:, :A], kv[:, A:], [self.lin_self], self.prepare_edges(edge_attr, dt),
+                                       csr, x_dst, dt)
         src_new = x_src
         if self.update_src_nodes:
-            h = Fn.layer_norm_mod(self._pack, self.layer_norm_mlp_src, x_src, dt)
-            src_new = self.node_src_mlp.run(h, dt, residual=x_src if x_src.dtype in Fn.SUPPORTED else x_src.float())
+            src_new = self.node_src_mlp.run(x_src, dt, residual=x_src if x_src.dtype in Fn.SUPPORTED else x_src.float(),
+                                            pre_ln=self.layer_norm_mlp_src)
         return (src_new, dst_new), edge_attr

@@ -200,8 +200,8 @@ class GraphTransformerBackwardMapper(GraphTransformerBaseMapper):
         return x_src, Fn.fused_linear(self._pack, x_dst, [self.emb_nodes_dst], dt)
 
     def post_process(self, x_dst: Tensor, dt: torch.dtype) -> Tensor:
-        h = Fn.layer_norm_mod(self._pack, self.node_data_extractor[0], x_dst, dt)
-        return Fn.fused_linear(self._pack, h, [self.node_data_extractor[1]], dt)
+        lin = self.node_data_extractor[1]
+        return Fn.ln_linear(self._pack, x_dst, self.node_data_extractor[0], ("extractor",), Fn.linear_sources([lin]), lambda: Fn.cat_linear32([lin]), dt)
 
     def forward(
         self,

@@ -63,6 +63,7 @@ class MLP(nn.Module):
         first_gathers: Optional[tuple] = None,
         first_cols: Optional[slice] = None,
         out: Optional[Tensor] = None,
+        pre_ln: Optional[nn.Module] = None,
     ) -> Tensor:
         """Fused forward in compute dtype ``dt``.  ``residual`` is added after the last op (LayerNorm if present).
         ``first_gathers`` / ``first_cols`` feed the split first layer of GraphConv's edge MLP (gather-add epilogue)."""
@@ -77,7 +78,11 @@ class MLP(nn.Module):
                 kw["gather1"], kw["gather2"] = first_gathers
             if last and self.layer_norm is None:
                 kw["residual"], kw["out"] = residual, out
-            x = Fn.fused_linear(self._pack, x, [lin], dt, cols=first_cols if first else None, gelu=act, **kw)
+            if first and pre_ln is not None:  # LayerNorm(x) feeding the first Linear: folded into that GEMM on the bf16 path
+                x = Fn.ln_linear(self._pack, x, pre_ln, ("pre_ln", id(lin)), Fn.linear_sources([lin]), lambda lin=lin: Fn.cat_linear32([lin]), dt,
+                                 gelu=act, **kw)
+            else:
+                x = Fn.fused_linear(self._pack, x, [lin], dt, cols=first_cols if first else None, gelu=act, **kw)
             i += 2 if act else 1
             first = False
         if self.layer_norm is not None:

@@ -16,7 +16,7 @@ from ._lib import BF16
 from ._lib import EPI_GELU
 from ._lib import F32
 
-__all__ = ["GraphCSR", "build_csr", "layer_norm", "linear", "gt_attention", "graphconv_ln_aggregate", "cast_pad", "add", "dtype_code"]
+__all__ = ["GraphCSR", "build_csr", "layer_norm", "row_stats", "linear", "gt_attention", "graphconv_ln_aggregate", "cast_pad", "add", "dtype_code"]
 
 
 # ---- instrumentation: launch counter and optional CUDA-event timing of every C-ABI call (bench.py roofline leg) -------
@@ -206,8 +206,13 @@ def linear(
     gather2: Optional[tuple[Tensor, Tensor]] = None,
     out: Optional[Tensor] = None,
     out_dtype: Optional[torch.dtype] = None,
+    ln_stats: Optional[Tensor] = None,
+    ln_colsum: Optional[Tensor] = None,
 ) -> Tensor:
     """out = [gelu](a @ weight.T + bias + g1[idx1] + g2[idx2]) + residual.
+
+    With ``ln_stats`` [M, 2] (``row_stats(a)``) and ``ln_colsum`` [N] the LayerNorm of ``a`` is folded in:
+    out = [gelu](rstd * (a @ weight.T - mean * colsum) + bias) for ``weight`` already scaled by the LayerNorm gamma.
 
     ``a`` [M, K] and ``weight`` [N, K] share a dtype (bf16 -> tcgen05 tensor cores, fp32 -> exact FFMA);
     ``gatherX = (table fp32 [*, >=N], idx int32 [M])``.
@@ -252,9 +257,14 @@ def linear(
     tc = a.dtype == torch.bfloat16 and K >= 64 and lda % 8 == 0 and ldw % 8 == 0 and a.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0
     gbytes = (4.0 * M * N if g1 is not None else 0.0) + (4.0 * M * N if g2 is not None else 0.0)
     with _Timed("linear_tcgen05" if tc else "linear_ffma", 2.0 * M * N * K, _nbytes(a, weight, residual, out) + gbytes):
+        if (ln_stats is None) != (ln_colsum is None):
+            raise ValueError("linear: ln_stats and ln_colsum go together")
+        if ln_stats is not None and (ln_stats.shape != (M, 2) or ln_colsum.numel() != N or ln_stats.dtype != torch.float32):
+            raise ValueError("linear: ln_stats must be float32 [M, 2] and ln_colsum float32 [N]")
         rc = _lib.load().anemoi_b200_linear(
             _ptr(a), lda, _ptr(weight), ldw, dtype_code(a.dtype), _ptr(_f32(bias)), _ptr(g1), _ptr(i1), _ptr(g2), _ptr(i2), ldg, _ptr(residual),
-            ldr, rdt, _ptr(out), ldo, dtype_code(out.dtype), M, N, K, EPI_GELU if gelu else 0, _stream())  # fmt: skip
+            ldr, rdt, _ptr(out), ldo, dtype_code(out.dtype), M, N, K, EPI_GELU if gelu else 0, _ptr(_f32(ln_stats)), _ptr(_f32(ln_colsum)),
+            _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_linear")
     return out
 
@@ -405,3 +415,14 @@ def add(a: Tensor, b: Tensor, out_dtype: Optional[torch.dtype] = None) -> Tensor
         rc = _lib.load().anemoi_b200_add(_ptr(a), lda, dtype_code(a.dtype), _ptr(b), ldb, dtype_code(b.dtype), _ptr(out), C, dtype_code(out.dtype), M, C, _stream())
     _lib.check(rc, "anemoi_b200_add")
     return out
+
+
+def row_stats(x: Tensor, eps: float = 1e-5) -> Tensor:
+    """Per-row LayerNorm statistics [M, 2] = (mean, 1/sqrt(var + eps)) for the LayerNorm folded into ``linear``."""
+    _need_cuda(x)
+    M, C, ldx = _rows(x)
+    stats = torch.empty((M, 2), dtype=torch.float32, device=x.device)
+    with _Timed("row_stats", 4.0 * M * C, float(M) * C * x.element_size() + 8.0 * M):
+        rc = _lib.load().anemoi_b200_row_stats(_ptr(x), ldx, dtype_code(x.dtype), _ptr(stats), M, C, float(eps), _stream())
+    _lib.check(rc, "anemoi_b200_row_stats")
+    return stats

@@ -76,10 +76,18 @@ ANEMOI_API int anemoi_b200_layer_norm(const void* x, int64_t ldx, int x_dtype, c
  *   a_dtype == ANEMOI_F32  : A, W fp32 -> fp32 FFMA path (parity mode; no tensor cores, no TF32 rounding).
  *   bias  : fp32 [N] or NULL.  g1/g2 : fp32 [*, ldg] gathered by int32 row indices idx1/idx2 [M], or NULL.
  *   residual : [M, ldr] of r_dtype or NULL.   out : [M, ldo] of o_dtype.
+ *   ln_stats / ln_colsum (both or neither): LayerNorm of the A operand folded into the GEMM.  With W' = W * gamma (per input column),
+ *     LN(x) W^T + b = rstd_m (x W'^T - mean_m colsum_n) + (b + W beta),  colsum_n = sum_k W'[n,k]:  the caller passes the RAW x as A,
+ *     W' as W, (b + W beta) as bias, per-row (mean, rstd) from anemoi_b200_row_stats as ln_stats [M,2] and colsum [N]; the separate
+ *     LayerNorm pass (one read + one write of the activations) disappears.
  */
 ANEMOI_API int anemoi_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, int a_dtype, const float* bias, const float* g1,
                        const int32_t* idx1, const float* g2, const int32_t* idx2, int64_t ldg, const void* residual, int64_t ldr,
-                       int r_dtype, void* out, int64_t ldo, int o_dtype, int64_t M, int64_t N, int64_t K, int flags, void* stream);
+                       int r_dtype, void* out, int64_t ldo, int o_dtype, int64_t M, int64_t N, int64_t K, int flags, const float* ln_stats,
+                       const float* ln_colsum, void* stream);
+
+/* per-row LayerNorm statistics (mean, 1/sqrt(var + eps)), two-pass in registers: stats[m] = (mean, rstd), x [M, ldx] of x_dtype */
+ANEMOI_API int anemoi_b200_row_stats(const void* x, int64_t ldx, int x_dtype, float* stats, int64_t M, int64_t C, float eps, void* stream);
 
 /* -- GraphTransformer edge-softmax attention (forward) -------------------------------------------------------
  * Replaces layers/conv.py:103-147 (GraphTransformerConv, PyG softmax) and triton/gt.py:81-179 / :390-428

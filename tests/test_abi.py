@@ -17,7 +17,8 @@ def header_symbols():
 def test_header_declares_the_expected_entry_points():
     syms = header_symbols()
     assert {"anemoi_b200_csr_build", "anemoi_b200_layer_norm", "anemoi_b200_linear", "anemoi_b200_gt_attention_fwd",
-            "anemoi_b200_graphconv_ln_aggregate", "anemoi_b200_cast_pad", "anemoi_b200_add", "anemoi_b200_last_error", "anemoi_b200_abi_version"} <= syms  # fmt: skip
+            "anemoi_b200_graphconv_ln_aggregate", "anemoi_b200_cast_pad", "anemoi_b200_add", "anemoi_b200_row_stats", "anemoi_b200_last_error",
+            "anemoi_b200_abi_version"} <= syms  # fmt: skip
 
 
 def test_library_exports_every_header_symbol_and_ctypes_table_matches():
@@ -41,5 +42,5 @@ def test_version_and_error_string_calls_work_without_a_gpu():
     assert lib.anemoi_b200_abi_version() == 1
     assert isinstance(lib.anemoi_b200_last_error(), bytes)
     # argument validation happens before any CUDA call: a bad shape is reported through the error channel
-    rc = lib.anemoi_b200_linear(None, 0, None, 0, 0, None, None, None, None, None, 0, None, 0, 0, None, 0, 0, -1, 1, 1, 0, None)
+    rc = lib.anemoi_b200_linear(None, 0, None, 0, 0, None, None, None, None, None, 0, None, 0, 0, None, 0, 0, -1, 1, 1, 0, None, None, None)
     assert rc == -1 and b"bad shape" in lib.anemoi_b200_last_error()

@@ -161,6 +161,29 @@ def test_linear_large_two_cta(ops, M, N, K, epi):
     assert (y32 - ref32).abs().max().item() <= 2e-3 * max(1.0, ref32.abs().max().item())
 
 
+@pytest.mark.parametrize("M,N,K,gelu", [(5000, 2240, 512, False), (40962, 2048, 512, True), (777, 88, 512, False), (3000, 512, 64, True)])
+def test_linear_with_folded_layer_norm(ops, M, N, K, gelu):
+    """LN(x) W^T + b through the folded form (row_stats + gamma-scaled weight + column sums) against LayerNorm -> Linear in fp32."""
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = (torch.randn(M, K, generator=g, device="cuda") * 1.7 + 0.6).to(torch.bfloat16)
+    w32 = torch.randn(N, K, generator=g, device="cuda") / math.sqrt(K)
+    b32 = torch.randn(N, generator=g, device="cuda")
+    gamma, beta = 1 + 0.2 * torch.randn(K, generator=g, device="cuda"), 0.3 * torch.randn(K, generator=g, device="cuda")
+    wf = (w32 * gamma).to(torch.bfloat16)
+    bias = b32 + w32 @ beta
+    stats = ops.row_stats(x, 1e-5)
+    xf = x.float()
+    torch.testing.assert_close(stats[:, 0], xf.mean(1), atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(stats[:, 1], (xf.var(1, unbiased=False) + 1e-5).rsqrt(), atol=1e-4, rtol=1e-4)
+    y = ops.linear(x, wf, bias, gelu=gelu, ln_stats=stats, ln_colsum=wf.float().sum(1).contiguous())
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = torch.nn.functional.layer_norm(xf, (K,), gamma, beta, 1e-5) @ w32.t() + b32
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 2**-6 * ref.abs().max().item() + 1e-3, f"max err {err}"
+
+
 def test_linear_strided_views(ops):
     """Column slices of wider buffers as A, residual and out (how the blocks pass q|k|v|self and x|aggregate)."""
     g = torch.Generator().manual_seed(5)

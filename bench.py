@@ -379,10 +379,16 @@ def main():
                          "frac_tensor": round(tf / pk["tensor"], 4), "frac_hbm": round(gb / pk["hbm"], 4)}  # fmt: skip
     top = next(iter(kernels))
     topd = agg[top]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    if top == "linear_tcgen05" and os.path.exists(tpath):
+        # dram__bytes_read + dram__bytes_write per launch from the committed `ncu --set full` capture of this kernel (not measurable here)
+        traffic = json.load(open(tpath))["avg_dram_bytes_per_launch"]
     if top == "linear_tcgen05":
         ach = topd["flops"] / (topd["ms"] * 1e-3) / 1e12
         roofline = {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tensor"], "traffic": None, "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
+                    "frac": ach / pk["tensor"], "traffic": traffic, "traffic_unit": "bytes per launch (DRAM read+write, ncu, profiles/r1_gemm_traffic.json)",
+                    "algorithmic_bytes_per_launch": topd["bytes"] / topd["launches"], "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
                     "share_of_step": kernels[top]["share"]}  # fmt: skip
     else:
         ach = topd["bytes"] / (topd["ms"] * 1e-3) / 1e9

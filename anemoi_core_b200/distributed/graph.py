@@ -32,6 +32,43 @@ def shard_rows(x: Tensor, sizes: Optional[list[int]], group: Optional[dist.Proce
     return x[start : start + sizes[r]]
 
 
+class SegmentedCapture:
+    """CUDA-graph capture of a sharded forward as a chain [graph_0, all-gather, graph_1, all-gather, ...]: the compute between two
+    collectives is captured (one graph launch instead of dozens of kernel launches), the NCCL all-gathers run eagerly between the
+    replays.  (Capturing the NCCL calls themselves hung on the 2-GPU box in round 1.)  ``gather_rows`` consults the active instance."""
+
+    active: "Optional[SegmentedCapture]" = None
+
+    def __init__(self) -> None:
+        self.items: list = []
+        self.pool = torch.cuda.graph_pool_handle()
+        self._g: Optional[torch.cuda.CUDAGraph] = None
+
+    def begin(self) -> None:
+        self._g = torch.cuda.CUDAGraph()
+        self._g.capture_begin(pool=self.pool, capture_error_mode="thread_local")
+
+    def end(self) -> None:
+        self._g.capture_end()
+        self.items.append(("graph", self._g))
+        self._g = None
+
+    def gather(self, x: Tensor, sizes: list[int], group) -> Tensor:
+        self.end()
+        out = _all_gather_rows(x, sizes, group)  # eager: allocates the persistent output and exercises the collective
+        self.items.append(("gather", out, x, list(sizes), group))
+        self.begin()
+        return out
+
+    def replay(self) -> None:
+        for it in self.items:
+            if it[0] == "graph":
+                it[1].replay()
+            else:
+                _, out, x, sizes, group = it
+                _all_gather_rows(x, sizes, group, out=out)
+
+
 def gather_rows(x: Tensor, sizes: Optional[list[int]], group: Optional[dist.ProcessGroup]) -> Tensor:
     """All-gather row shards into the full tensor (reference ``gather_tensor`` / ``sync_tensor`` forward,
     graph.py:94-135, primitives.py:144-183).  Shards may differ by one row (balanced partition); NCCL's
@@ -43,8 +80,15 @@ def gather_rows(x: Tensor, sizes: Optional[list[int]], group: Optional[dist.Proc
         raise ValueError("gather_rows: per-rank shard sizes are required when the model group has more than one rank")
     if len(sizes) != world or x.shape[0] != sizes[group_rank(group)]:
         raise ValueError(f"gather_rows: local shard has {x.shape[0]} rows, shard sizes {sizes} (world {world})")
-    x = x.contiguous()
-    out = torch.empty((sum(sizes),) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    if SegmentedCapture.active is not None:
+        return SegmentedCapture.active.gather(x.contiguous(), sizes, group)
+    return _all_gather_rows(x.contiguous(), sizes, group)
+
+
+def _all_gather_rows(x: Tensor, sizes: list[int], group, out: Optional[Tensor] = None) -> Tensor:
+    world = len(sizes)
+    if out is None:
+        out = torch.empty((sum(sizes),) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     if len(set(sizes)) == 1:
         dist.all_gather_into_tensor(out, x, group=group)
     elif dist.get_backend(group) == "nccl":

@@ -93,7 +93,8 @@ class EncProcDec(nn.Module):
                 self.forward(static_grid, static_mesh, graph, **fwd_kwargs)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(g):
+        # thread_local: the NCCL watchdog thread polls CUDA events while we capture; in the default (global) mode that poisons the capture
+        with torch.no_grad(), torch.cuda.graph(g, capture_error_mode="thread_local"):
             static_out = self.forward(static_grid, static_mesh, graph, **fwd_kwargs)
         self._graph = g
 
@@ -103,6 +104,39 @@ class EncProcDec(nn.Module):
             if new_mesh is not None:
                 static_mesh.copy_(new_mesh, non_blocking=True)
             g.replay()
+            return static_out
+
+        return replay
+
+    def capture_segmented(self, x_grid: Tensor, x_mesh: Tensor, graph: dict, warmup: int = 2, **fwd_kwargs):
+        """Multi-GPU variant of ``capture``: the compute between two all-gathers is captured as a CUDA graph, the NCCL all-gathers run
+        eagerly in between (``distributed.graph.SegmentedCapture``).  Returns ``replay(x_grid=None, x_mesh=None) -> Tensor``."""
+        from .distributed.graph import SegmentedCapture
+
+        static_grid, static_mesh = x_grid.clone(), x_mesh.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                self.forward(static_grid, static_mesh, graph, **fwd_kwargs)
+            torch.cuda.synchronize()
+            seg = SegmentedCapture()
+            SegmentedCapture.active = seg
+            try:
+                seg.begin()
+                static_out = self.forward(static_grid, static_mesh, graph, **fwd_kwargs)
+                seg.end()
+            finally:
+                SegmentedCapture.active = None
+        torch.cuda.current_stream().wait_stream(side)
+        self._graph = seg
+
+        def replay(new_grid: Optional[Tensor] = None, new_mesh: Optional[Tensor] = None) -> Tensor:
+            if new_grid is not None:
+                static_grid.copy_(new_grid, non_blocking=True)
+            if new_mesh is not None:
+                static_mesh.copy_(new_mesh, non_blocking=True)
+            seg.replay()
             return static_out
 
         return replay

@@ -256,12 +256,16 @@ def main():
     launches_per_step = ops.LAUNCHES - n0
     torch.cuda.synchronize()
 
-    # NCCL collectives inside the captured graph hung on the 2-GPU box (round 1); multi-GPU runs launch eagerly unless ANEMOI_BENCH_GRAPH_NCCL=1
-    use_graph = not args.no_graph and (world == 1 or os.environ.get("ANEMOI_BENCH_GRAPH_NCCL") == "1")
+    # N = 1: the whole step is one CUDA graph.  N > 1: NCCL calls inside a captured graph hung on the 2-GPU box (round 1), so the compute
+    # between two all-gathers is captured and the collectives run eagerly between the segment replays (SegmentedCapture).
+    use_graph = not args.no_graph
     if use_graph:
         try:
             with torch.autocast("cuda", dtype=torch.bfloat16):
-                replay = model.capture(x_grid, x_mesh, gd, model_comm_group=group, mesh_shards=mesh_shards, grid_shards=grid_shards)
+                if world == 1:
+                    replay = model.capture(x_grid, x_mesh, gd)
+                else:
+                    replay = model.capture_segmented(x_grid, x_mesh, gd, model_comm_group=group, mesh_shards=mesh_shards, grid_shards=grid_shards)
         except Exception as e:  # noqa: BLE001  (e.g. a collective that cannot be captured): fall back to eager launches, and say so
             if world == 1:
                 raise
@@ -402,7 +406,7 @@ def main():
         "metric": "forward ms/step", "value": ms_dev, "unit": "ms/step", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['desc']}", "batch": 1, "precision": "bf16 autocast, fp32 accumulate",
-                   "launch": "cuda-graph replay" if use_graph else "eager", "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
+                   "launch": ("cuda-graph replay" if world == 1 else "cuda-graph segments + eager NCCL all-gathers") if use_graph else "eager", "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
                    "parallelism": "single GPU" if world == 1 else f"encoder / processor / decoder dst-range sharded over {world} GPUs (all-gather of k|v rows per layer over NCCL)"},
         "e2e": {"value": ms_e2e, "unit": "ms/step", "h2d_bytes_per_step": x_grid_h.numel() * 4 + x_mesh_h.numel() * 4,
                 "d2h_bytes_per_step": out_h.numel() * out_h.element_size()},

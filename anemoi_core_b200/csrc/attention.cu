@@ -520,9 +520,11 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
               for (int i = 0; i < EPC; ++i) kf[i] += ef[i];
             }
           }
-          float t = 0.f;
+          // packed fp32x2 FMAs (FFMA2): the kernel is issue-bound, two lanes of work per issue slot
+          float2 t2 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int i = 0; i < EPC; ++i) t += q[j][i] * kf[i];
+          for (int i = 0; i < EPC; i += 2) t2 = __ffma2_rn(make_float2(q[j][i], q[j][i + 1]), make_float2(kf[i], kf[i + 1]), t2);
+          float t = t2.x + t2.y;
           if constexpr (MODE == 2) {
 #pragma unroll
             for (int tt = 0; tt < NA; ++tt)
@@ -544,8 +546,12 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
         for (int b = 0; b < kPBatch; ++b) wgt[b] = exp2f(sc[b][j] - mx), wsum += wgt[b];
         l_i[j] = l_i[j] * corr + wsum;
         m_i[j] = mx;
+        const float2 corr2 = make_float2(corr, corr);
 #pragma unroll
-        for (int i = 0; i < EPC; ++i) acc[j][i] *= corr;
+        for (int i = 0; i < EPC; i += 2) {
+          const float2 a2 = __fmul2_rn(make_float2(acc[j][i], acc[j][i + 1]), corr2);
+          acc[j][i] = a2.x, acc[j][i + 1] = a2.y;
+        }
 #pragma unroll
         for (int b = 0; b < kPBatch; ++b) {
           float vf[EPC];
@@ -558,8 +564,12 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
               for (int i = 0; i < EPC; ++i) vf[i] += ef[i];
             }
           }
+          const float2 w2 = make_float2(wgt[b], wgt[b]);
 #pragma unroll
-          for (int i = 0; i < EPC; ++i) acc[j][i] += wgt[b] * vf[i];
+          for (int i = 0; i < EPC; i += 2) {
+            const float2 a2 = __ffma2_rn(w2, make_float2(vf[i], vf[i + 1]), make_float2(acc[j][i], acc[j][i + 1]));
+            acc[j][i] = a2.x, acc[j][i + 1] = a2.y;
+          }
         }
         if constexpr (MODE == 2) {
 #pragma unroll

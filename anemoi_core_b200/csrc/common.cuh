@@ -103,6 +103,27 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return x > 0.f ? x - xh : xh;
 }
 
+// Two GELUs per call on the packed fp32x2 pipe (FFMA2 / FMUL2: one issue slot for two lanes of work — the epilogue is issue-bound).
+// gelu(x) = max(x, 0) - |x| * 0.5 * erfc(|x| / sqrt2), same A&S 7.1.26 erfc as gelu_erf_fast (0.5 folded into the coefficients).
+__device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 u = __ffma2_rn(ax, make_float2(0.3275911f * 0.70710678118654752440f, 0.3275911f * 0.70710678118654752440f), make_float2(1.f, 1.f));
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  float2 p = __ffma2_rn(t, make_float2(0.5f * 1.061405429f, 0.5f * 1.061405429f), make_float2(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+  p = __ffma2_rn(p, t, make_float2(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+  p = __ffma2_rn(p, t, make_float2(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+  p = __ffma2_rn(p, t, make_float2(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+  p = __fmul2_rn(p, t);
+  const float2 arg = __fmul2_rn(__fmul2_rn(x, x), make_float2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f));
+  float2 ex;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.x) : "f"(arg.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.y) : "f"(arg.y));
+  const float2 axh = __fmul2_rn(ax, __fmul2_rn(p, ex));
+  return __ffma2_rn(axh, make_float2(-1.f, -1.f), make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

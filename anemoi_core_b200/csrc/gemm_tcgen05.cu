@@ -330,11 +330,15 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
         if constexpr (LNF) {
           const uint32_t sa = cx.bias_smem + 1024u + (uint32_t)(col_in_tile + g * 8) * 4u;
           const uint4 s0 = ptx::lds128(sa), s1 = ptx::lds128(sa + 16);
-          const float nm = -ln_mean;
-          v[0] = ln_rstd * fmaf(nm, __uint_as_float(s0.x), v[0]), v[1] = ln_rstd * fmaf(nm, __uint_as_float(s0.y), v[1]);
-          v[2] = ln_rstd * fmaf(nm, __uint_as_float(s0.z), v[2]), v[3] = ln_rstd * fmaf(nm, __uint_as_float(s0.w), v[3]);
-          v[4] = ln_rstd * fmaf(nm, __uint_as_float(s1.x), v[4]), v[5] = ln_rstd * fmaf(nm, __uint_as_float(s1.y), v[5]);
-          v[6] = ln_rstd * fmaf(nm, __uint_as_float(s1.z), v[6]), v[7] = ln_rstd * fmaf(nm, __uint_as_float(s1.w), v[7]);
+          // rstd * (acc - mean * s) = acc * rstd + s * (-rstd * mean): two packed FMAs per pair (the bias add below is the third)
+          const float2 r2 = make_float2(ln_rstd, ln_rstd), m2 = make_float2(-ln_rstd * ln_mean, -ln_rstd * ln_mean);
+          const float sv[8] = {__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s0.z), __uint_as_float(s0.w),
+                               __uint_as_float(s1.x), __uint_as_float(s1.y), __uint_as_float(s1.z), __uint_as_float(s1.w)};
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float2 t2 = __ffma2_rn(make_float2(sv[j], sv[j + 1]), m2, __fmul2_rn(make_float2(v[j], v[j + 1]), r2));
+            v[j] = t2.x, v[j + 1] = t2.y;
+          }
         }
         if (ep.bias && !(cx.abl & kAblNoBias)) {
           const uint32_t ba = cx.bias_smem + (uint32_t)(col_in_tile + g * 8) * 4u;
@@ -364,7 +368,10 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
         }
         if constexpr (GELU) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = gelu_erf_fast(v[j]);
+          for (int j = 0; j < 8; j += 2) {
+            const float2 g2 = gelu_erf_fast2(make_float2(v[j], v[j + 1]));
+            v[j] = g2.x, v[j + 1] = g2.y;
+          }
         }
         if constexpr (OUT_F32) {
 #pragma unroll

@@ -327,24 +327,33 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+        const bool has_bias = ep.bias && !(cx.abl & kAblNoBias);
+        float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (has_bias) {
+          const uint32_t ba = cx.bias_smem + (uint32_t)(col_in_tile + g * 8) * 4u;
+          const uint4 b0 = ptx::lds128(ba), b1 = ptx::lds128(ba + 16);
+          bv[0] = __uint_as_float(b0.x), bv[1] = __uint_as_float(b0.y), bv[2] = __uint_as_float(b0.z), bv[3] = __uint_as_float(b0.w);
+          bv[4] = __uint_as_float(b1.x), bv[5] = __uint_as_float(b1.y), bv[6] = __uint_as_float(b1.z), bv[7] = __uint_as_float(b1.w);
+        }
         if constexpr (LNF) {
           const uint32_t sa = cx.bias_smem + 1024u + (uint32_t)(col_in_tile + g * 8) * 4u;
           const uint4 s0 = ptx::lds128(sa), s1 = ptx::lds128(sa + 16);
-          // rstd * (acc - mean * s) = acc * rstd + s * (-rstd * mean): two packed FMAs per pair (the bias add below is the third)
+          // rstd * (acc - mean * s) + b = acc * rstd + (s * (-rstd * mean) + b): two packed FMAs per pair of columns
           const float2 r2 = make_float2(ln_rstd, ln_rstd), m2 = make_float2(-ln_rstd * ln_mean, -ln_rstd * ln_mean);
           const float sv[8] = {__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s0.z), __uint_as_float(s0.w),
                                __uint_as_float(s1.x), __uint_as_float(s1.y), __uint_as_float(s1.z), __uint_as_float(s1.w)};
 #pragma unroll
           for (int j = 0; j < 8; j += 2) {
-            const float2 t2 = __ffma2_rn(make_float2(sv[j], sv[j + 1]), m2, __fmul2_rn(make_float2(v[j], v[j + 1]), r2));
+            const float2 c2 = __ffma2_rn(make_float2(sv[j], sv[j + 1]), m2, make_float2(bv[j], bv[j + 1]));
+            const float2 t2 = __ffma2_rn(make_float2(v[j], v[j + 1]), r2, c2);
             v[j] = t2.x, v[j + 1] = t2.y;
           }
-        }
-        if (ep.bias && !(cx.abl & kAblNoBias)) {
-          const uint32_t ba = cx.bias_smem + (uint32_t)(col_in_tile + g * 8) * 4u;
-          const uint4 b0 = ptx::lds128(ba), b1 = ptx::lds128(ba + 16);
-          v[0] += __uint_as_float(b0.x), v[1] += __uint_as_float(b0.y), v[2] += __uint_as_float(b0.z), v[3] += __uint_as_float(b0.w);
-          v[4] += __uint_as_float(b1.x), v[5] += __uint_as_float(b1.y), v[6] += __uint_as_float(b1.z), v[7] += __uint_as_float(b1.w);
+        } else if (has_bias) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float2 t2 = __fadd2_rn(make_float2(v[j], v[j + 1]), make_float2(bv[j], bv[j + 1]));
+            v[j] = t2.x, v[j + 1] = t2.y;
+          }
         }
         if constexpr (GATHER) {
           if (col + 8 <= (int)ep.N) {

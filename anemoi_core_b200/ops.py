@@ -354,7 +354,7 @@ def gt_attention(
     with _Timed("gt_attention", aflops, abytes):
         rc = _lib.load().anemoi_b200_gt_attention_fwd(
             _ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(e_proj), lde_proj, _ptr(edge_attr), lde, d_e, _ptr(w_edge), ldw_e, _ptr(_f32(b_edge)),
-            _ptr(qw), ldqw, _ptr(abar), ldabar, dp, _ptr(csr.src32), _ptr(csr.colptr32), _ptr(add), ldadd, _ptr(out), ldo, n_dst, heads,
+            _ptr(qw), ldqw, _ptr(abar), ldabar, dp, _ptr(csr.src32) or _ptr(csr.colptr32), _ptr(csr.colptr32), _ptr(add), ldadd, _ptr(out), ldo, n_dst, heads,
             C // heads, dtype_code(q.dtype), _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_gt_attention_fwd")
     return out

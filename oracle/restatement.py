@@ -250,7 +250,7 @@ def _gt_core(sd, prefix, xs_n, xd_n, x_dst_skip, edge_attr, edge_index, num_head
         edge_attr = F.gelu(_linear(sd, prefix + ".edge_pre_mlp.0", edge_attr))
     e = _linear(sd, prefix + ".lin_edge", edge_attr)
     H = num_heads
-    q, k, v, e = (t.reshape(t.shape[0], H, -1) for t in (q, k, v, e))
+    q, k, v, e = (t.reshape(t.shape[0], H, t.shape[1] // H) for t in (q, k, v, e))  # explicit width: an empty edge list stays reshapeable
     if prefix + ".q_norm.weight" in sd:  # block.py:655-660 — AutocastLayerNorm(Ch, bias=False)
         q = F.layer_norm(q, (q.shape[-1],), sd[prefix + ".q_norm.weight"], None, 1e-5).type_as(q)
         k = F.layer_norm(k, (k.shape[-1],), sd[prefix + ".k_norm.weight"], None, 1e-5).type_as(k)

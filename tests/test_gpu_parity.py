@@ -189,3 +189,61 @@ def test_invariances_like_the_reference_tests():
         y1 = m(x, 1, shard1(), gr["attr"].cuda(), gr["index"].cuda())
         y2 = m(x, 1, shard1(), gr["attr"][perm].cuda(), gr["index"][:, perm].cuda(), edges_are_dst_sorted=False)
     torch.testing.assert_close(y1, y2, atol=1e-4, rtol=0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_cfg2_step_parity():
+    """BASELINE.json north_star: parity of the whole forward on O96 / ico-6 (GraphTransformer encoder + 16 x 512 processor + decoder)
+    against the reference algorithm (oracle, fp32 CPU, ~10 s): fp32 path <= 1e-4 relative, bf16 path rel-L2 <= 2e-2."""
+    from anemoi_core_b200.model import EncProcDec
+    from anemoi_core_b200.synthetic import build_graph
+
+    gr = build_graph("o96", 6)
+    torch.manual_seed(1234)
+    m = EncProcDec("graphtransformer", in_grid=212, in_mesh=12, out_grid=88, num_channels=512, num_layers=16, edge_dim=gr["edge_dim"], num_heads=16).eval()
+    sds = {k: {n: p.detach().clone() for n, p in getattr(m, k).state_dict().items()} for k in ("encoder", "processor", "decoder")}
+    g = torch.Generator().manual_seed(1234)
+    xg, xm = torch.randn(gr["n_grid"], 212, generator=g), torch.randn(gr["n_mesh"], 12, generator=g)
+    with torch.no_grad():
+        ref = R.gt_encode_process_decode(sds, gr, xg, xm, 16, 16)
+    m = m.cuda()
+    gd = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in gr.items()}
+    with torch.no_grad():
+        y32 = m(xg.cuda(), xm.cuda(), gd)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y16 = m(xg.cuda(), xm.cuda(), gd)
+    assert_fp32_parity(y32, ref, "cfg2 full step fp32")
+    mx, l2 = rel_err(y16, ref)
+    assert y16.dtype == torch.bfloat16 and l2 <= 2e-2, f"cfg2 bf16 rel-L2 {l2:.3e} (max-rel {mx:.3e})"
+
+
+def test_edge_cases_empty_and_isolated():
+    """Edge cases the reference handles implicitly: an empty edge list and destination nodes without edges (gt.py:112-119)."""
+    from anemoi_core_b200 import ops
+    from anemoi_core_b200.layers import GNNProcessor
+    from anemoi_core_b200.layers import GraphTransformerProcessor
+
+    n, c = 64, 64
+    x = torch.randn(n, c, generator=torch.Generator().manual_seed(0))
+    ei_empty = torch.zeros(2, 0, dtype=torch.long)
+    ea_empty = torch.zeros(0, 5)
+    csr = ops.build_csr(ei_empty.cuda(), n, n)
+    assert torch.all(csr.colptr == 0) and csr.colptr.numel() == n + 1
+    for cls, kw in ((GraphTransformerProcessor, dict(num_heads=4, mlp_hidden_ratio=2)), (GNNProcessor, dict(mlp_extra_layers=0))):
+        torch.manual_seed(1)
+        m = cls(num_layers=2, num_channels=c, num_chunks=1, edge_dim=5, **kw).eval()
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        m = m.cuda()
+        with torch.no_grad():
+            y = m(x.cuda(), 1, shard1(n), ea_empty.cuda(), ei_empty.cuda())
+        ref = (R.gt_processor(sd, x, ea_empty, ei_empty, 2, 4) if cls is GraphTransformerProcessor else R.gnn_processor(sd, x, ea_empty, ei_empty, 2))
+        assert_fp32_parity(y, ref, f"{cls.__name__} with no edges")
+    # a single edge into the last node, everything else isolated
+    ei = torch.tensor([[3], [n - 1]])
+    ea = torch.randn(1, 5, generator=torch.Generator().manual_seed(2))
+    torch.manual_seed(3)
+    m = GraphTransformerProcessor(num_layers=1, num_channels=c, num_chunks=1, num_heads=4, mlp_hidden_ratio=2, edge_dim=5).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        y = m.cuda()(x.cuda(), 1, shard1(n), ea.cuda(), ei.cuda())
+    assert_fp32_parity(y, R.gt_processor(sd, x, ea, ei, 1, 4), "single edge")

@@ -114,3 +114,25 @@ def test_no_cpu_fallback_and_forward_only():
     with pytest.raises(NotImplementedError, match="forward pass only"):
         m(torch.randn(2, 8), 1, GraphShardInfo(nodes=[2]), torch.randn(2, 3), ei)
     assert BipartiteGraphShardInfo().edges_are_sharded() is False and GraphShardInfo(nodes=[1]).nodes_are_sharded()
+
+
+def test_gelu_exp2_polynomial():
+    """The tensor-core epilogue's GELU (csrc/common.cuh gelu_erf_fast: max(x,0) - |x| * exp2(P5(|x|))) restated in fp32 numpy with the
+    coefficients parsed from the source: within 1e-6 absolute of the exact erf-GELU (torch.nn.GELU(), reference layers/utils.py:107-110)."""
+    import re
+    from pathlib import Path
+
+    import numpy as np
+
+    src = (Path(__file__).resolve().parents[1] / "anemoi_core_b200" / "csrc" / "common.cuh").read_text()
+    m = re.search(r"#define ANEMOI_GELU_P5 (.*)", src)
+    c = [np.float32(t.strip().rstrip("f")) for t in m.group(1).split(",")]
+    assert len(c) == 6
+    x = np.concatenate([np.linspace(-30, 30, 600001), [0.0, -0.0, 1e-30, -1e-30, 1e4, -1e4]]).astype(np.float32)
+    t = np.minimum(np.abs(x), np.float32(10.0))
+    p = np.full_like(t, c[5])
+    for k in range(4, -1, -1):
+        p = (p * t + c[k]).astype(np.float32)
+    y = np.maximum(x, 0) - t.astype(np.float64) * np.exp2(p.astype(np.float64))
+    ref = torch.nn.functional.gelu(torch.from_numpy(x).double()).numpy()
+    assert np.abs(y - ref).max() <= 1e-6

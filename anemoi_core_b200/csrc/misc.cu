@@ -74,9 +74,104 @@ __global__ void add_kernel(const void* __restrict__ a, int64_t lda, int adt, con
   }
 }
 
+// ---- model glue either side of the encoder / decoder ------------------------------------------------------
+// assemble_input: out[(b e g), t * V + v] = x[b, t, e, g, v];  out[(b e g), T * V + a] = attrs[row % attr_rows, a];  zero pad up to Kpad.
+// Replaces einops.rearrange + torch.cat (+ the autocast cast of the embedding Linear) of `_assemble_input`
+// (models/encoder_processor_decoder.py:98-127) with one pass that writes the embedding GEMM's A operand directly.
+// One warp per output row: T contiguous V-float reads, one contiguous A-float read, one contiguous row write.
+template <typename TO>
+__global__ void assemble_input_kernel(const float* __restrict__ x, int64_t B, int64_t T, int64_t E, int64_t G, int64_t V,
+                                      const float* __restrict__ attrs, int64_t A, int64_t attr_rows, TO* __restrict__ out, int64_t ldo,
+                                      int64_t Kpad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = B * E * G;
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int64_t g = row % G, be = row / G, e = be % E, b = be / E;
+    TO* o = out + row * ldo;
+    for (int64_t t = 0; t < T; ++t) {
+      const float* xr = x + (((b * T + t) * E + e) * G + g) * V;
+      for (int64_t v = lane; v < V; v += 32) o[t * V + v] = from_f32<TO>(__ldg(xr + v));
+    }
+    const float* ar = attrs ? attrs + (row % attr_rows) * A : nullptr;
+    for (int64_t a = lane; a < Kpad - T * V; a += 32) o[T * V + a] = from_f32<TO>(a < A ? __ldg(ar + a) : 0.f);
+  }
+}
+
+// assemble_output: y[b, t, e, g, v] = bound_v( dec[(b e g), t * V + v] + (skip_src[v] >= 0 ? x[b, step, e, g, skip_src[v]] : 0) )
+// with bound_v = identity / relu / leaky_relu(0.01) per output variable.  Replaces the rearrange, dtype cast, clone, indexed residual
+// add and the index_put of every bounding layer of `_assemble_output` (models/encoder_processor_decoder.py:129-163,
+// layers/residual.py:60-81 SkipConnection, layers/bounding.py:81-94).
+template <typename TI>
+__global__ void assemble_output_kernel(const TI* __restrict__ dec, int64_t ldd, const float* __restrict__ x, int64_t B, int64_t T_in, int64_t E,
+                                       int64_t G, int64_t V_in, int64_t step, const int32_t* __restrict__ skip_src,
+                                       const int32_t* __restrict__ bound, float* __restrict__ y, int64_t T_out, int64_t V_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = B * E * G;
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int64_t g = row % G, be = row / G, e = be % E, b = be / E;
+    const float* xr = x ? x + (((b * T_in + step) * E + e) * G + g) * V_in : nullptr;
+    for (int64_t v = lane; v < V_out; v += 32) {
+      const int32_t src = skip_src ? __ldg(skip_src + v) : -1;
+      const float sk = (src >= 0 && xr) ? __ldg(xr + src) : 0.f;
+      const int32_t bd = bound ? __ldg(bound + v) : 0;
+      for (int64_t t = 0; t < T_out; ++t) {
+        float val = to_f32<TI>(dec[row * ldd + t * V_out + v]) + sk;
+        if (bd == 1) val = fmaxf(val, 0.f);
+        else if (bd == 2) val = val > 0.f ? val : 0.01f * val;
+        y[(((b * T_out + t) * E + e) * G + g) * V_out + v] = val;
+      }
+    }
+  }
+}
+
 }  // namespace anemoi
 
 using namespace anemoi;
+
+extern "C" int anemoi_b200_assemble_input(const float* x, int64_t B, int64_t T, int64_t E, int64_t G, int64_t V, const float* attrs, int64_t A,
+                                          int64_t attr_rows, void* out, int64_t ldo, int64_t Kpad, int o_dtype, void* stream) {
+  ANEMOI_CHECK_ARG(B >= 0 && T >= 0 && E >= 0 && G >= 0 && V >= 0 && A >= 0, "assemble_input: negative size");
+  ANEMOI_CHECK_ARG(Kpad >= T * V + A && ldo >= Kpad, "assemble_input: Kpad / ldo too small");
+  ANEMOI_CHECK_ARG(A == 0 || (attrs && attr_rows > 0), "assemble_input: attributes without rows");
+  const int64_t rows = B * E * G;
+  if (rows == 0 || Kpad == 0) return 0;
+  ANEMOI_CHECK_ARG(out && (x || T * V == 0), "assemble_input: null pointer");
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (o_dtype == ANEMOI_F32)
+    assemble_input_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(x, B, T, E, G, V, attrs, A, attr_rows, (float*)out, ldo, Kpad);
+  else if (o_dtype == ANEMOI_BF16)
+    assemble_input_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(x, B, T, E, G, V, attrs, A, attr_rows, (__nv_bfloat16*)out, ldo, Kpad);
+  else {
+    set_error("assemble_input: bad dtype %d", o_dtype);
+    return -1;
+  }
+  return launch_status("assemble_input_kernel");
+}
+
+extern "C" int anemoi_b200_assemble_output(const void* dec, int64_t ldd, int d_dtype, const float* x, int64_t B, int64_t T_in, int64_t E, int64_t G,
+                                           int64_t V_in, int64_t step, const int32_t* skip_src, const int32_t* bound, float* y, int64_t T_out,
+                                           int64_t V_out, void* stream) {
+  ANEMOI_CHECK_ARG(B >= 0 && E >= 0 && G >= 0 && T_out >= 0 && V_out >= 0 && ldd >= T_out * V_out, "assemble_output: bad shape");
+  ANEMOI_CHECK_ARG(!skip_src || !x || (step >= 0 && step < T_in && V_in > 0), "assemble_output: residual step out of range");
+  const int64_t rows = B * E * G;
+  if (rows == 0 || T_out * V_out == 0) return 0;
+  ANEMOI_CHECK_ARG(dec && y, "assemble_output: null pointer");
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (d_dtype == ANEMOI_F32)
+    assemble_output_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const float*)dec, ldd, x, B, T_in, E, G, V_in, step, skip_src, bound, y, T_out, V_out);
+  else if (d_dtype == ANEMOI_BF16)
+    assemble_output_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)dec, ldd, x, B, T_in, E, G, V_in, step, skip_src, bound,
+                                                                          y, T_out, V_out);
+  else {
+    set_error("assemble_output: bad dtype %d", d_dtype);
+    return -1;
+  }
+  return launch_status("assemble_output_kernel");
+}
 
 extern "C" int anemoi_b200_abi_version(void) { return 1; }
 extern "C" const char* anemoi_b200_last_error(void) { return g_err; }

@@ -7,6 +7,11 @@ from .block import GraphTransformerMapperBlock
 from .block import GraphTransformerProcessorBlock
 from .conv import GraphConv
 from .conv import GraphTransformerConv
+from .graph import NamedNodesAttributes
+from .graph import TrainableTensor
+from .graph_provider import NoOpGraphProvider
+from .graph_provider import StaticGraphProvider
+from .graph_provider import create_graph_provider
 from .mapper import GNNBackwardMapper
 from .mapper import GNNForwardMapper
 from .mapper import GraphTransformerBackwardMapper
@@ -29,4 +34,9 @@ __all__ = [
     "GNNBackwardMapper",
     "GraphTransformerForwardMapper",
     "GraphTransformerBackwardMapper",
+    "TrainableTensor",
+    "NamedNodesAttributes",
+    "StaticGraphProvider",
+    "NoOpGraphProvider",
+    "create_graph_provider",
 ]

@@ -133,14 +133,17 @@ class GraphTransformerBaseMapper(BaseMapper):
         if world > 1:
             if shard_info is None or not shard_info.dst_is_sharded():
                 raise ValueError("sharded mapper: shard_info.dst_nodes (per-rank destination row counts) is required")
-            if shard_info.edges_are_sharded():
-                raise NotImplementedError("pre-sharded mapper edges: pass the full dst-sorted edge list (the split is cached)")
+            from .processor import _localise_presharded_edges
             from .processor import _shard_edges_by_dst
 
-            n_src = sum(shard_info.src_nodes) if shard_info.src_is_sharded() else x[0].shape[0]
-            edge_attr, edge_index, edge_sizes = _shard_edges_by_dst(edge_attr, edge_index, sum(shard_info.dst_nodes), n_src, model_comm_group,
-                                                                    relabel_dst=True, dst_splits=shard_info.dst_nodes)  # fmt: skip
-            shard_info = BipartiteGraphShardInfo(src_nodes=shard_info.src_nodes, dst_nodes=shard_info.dst_nodes, edges=edge_sizes)
+            if shard_info.edges_are_sharded():
+                # the graph provider already cut the list to the edges into our rows (global dst ids): relabel dst only
+                edge_index = _localise_presharded_edges(edge_index, shard_info.dst_nodes, model_comm_group)
+            else:
+                n_src = sum(shard_info.src_nodes) if shard_info.src_is_sharded() else x[0].shape[0]
+                edge_attr, edge_index, edge_sizes = _shard_edges_by_dst(edge_attr, edge_index, sum(shard_info.dst_nodes), n_src, model_comm_group,
+                                                                        relabel_dst=True, dst_splits=shard_info.dst_nodes)  # fmt: skip
+                shard_info = BipartiteGraphShardInfo(src_nodes=shard_info.src_nodes, dst_nodes=shard_info.dst_nodes, edges=edge_sizes)
         dt = Fn.compute_dtype(*x)
         x_src, x_dst = self.pre_process(x, dt)
         (_, x_dst_out), _ = self.proc((x_src, x_dst), edge_attr, edge_index, shard_info, batch_size, (x_src.shape[0], x_dst.shape[0]),

@@ -82,6 +82,27 @@ def _shard_edges_by_dst(edge_attr: Tensor, edge_index: Tensor, n_dst: int, n_src
     return edge_attr[e0:e1], local, edge_sizes
 
 
+_LOCAL_CACHE: dict = {}
+
+
+def _localise_presharded_edges(edge_index: Tensor, dst_splits, group) -> Tensor:
+    """Edges that arrive already cut to this rank's dst range (``StaticGraphProvider.get_edges(shard_edges=True)``, reference
+    graph_provider.py:246-256) keep GLOBAL dst ids; the GraphTransformer kernels index local rows, so dst is relabelled once per
+    (tensor, group) and the result cached on the tensor identity."""
+    rank = group_rank(group)
+    start = int(sum(dst_splits[:rank]))
+    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), str(edge_index.device), start)
+    hit = _LOCAL_CACHE.get(key)
+    if hit is None:
+        local = edge_index.clone()
+        local[1] -= start
+        hit = (edge_index, local.contiguous())  # holding the source tensor keeps its data_ptr from being reused
+        if len(_LOCAL_CACHE) > 16:
+            _LOCAL_CACHE.clear()
+        _LOCAL_CACHE[key] = hit
+    return hit[1]
+
+
 class GNNProcessor(BaseProcessor):
     """GraphConv processor (processor.py:319-455).  Layer 0 embeds the raw edge attributes; each layer hands its
     updated edge features to the next."""
@@ -202,7 +223,7 @@ class GraphTransformerProcessor(BaseProcessor):
                 edge_attr, edge_index, edge_sizes = _shard_edges_by_dst(edge_attr, edge_index, n_nodes, n_nodes, model_comm_group, relabel_dst=True)
                 shard_info = GraphShardInfo(nodes=shard_info.nodes, edges=edge_sizes)
         elif group_size(model_comm_group) > 1:
-            raise NotImplementedError("pre-sharded edges: pass the full dst-sorted edge list and let the processor shard it (cached)")
+            edge_index = _localise_presharded_edges(edge_index, shard_info.nodes, model_comm_group)
         shared_edges = None
         if all(isinstance(b.edge_pre_mlp, nn.Identity) for b in self.proc):
             shared_edges = self.proc[0].prepare_edges(edge_attr, Fn.compute_dtype(x))  # one padded fp32 copy for all layers

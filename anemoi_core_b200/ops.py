@@ -426,3 +426,55 @@ def row_stats(x: Tensor, eps: float = 1e-5) -> Tensor:
         rc = _lib.load().anemoi_b200_row_stats(_ptr(x), ldx, dtype_code(x.dtype), _ptr(stats), M, C, float(eps), _stream())
     _lib.check(rc, "anemoi_b200_row_stats")
     return stats
+
+
+def assemble_input(x: Tensor, attrs: Optional[Tensor], out_dtype: torch.dtype, pad_to: int = 8) -> Tensor:
+    """``cat([rearrange(x, "b t e g v -> (b e g) (t v)"), attrs], -1)`` in ``out_dtype`` with the row length zero-padded to a multiple
+    of ``pad_to`` (so the result is directly the A operand of the embedding GEMM).  Returns the [B*E*G, T*V+A] view of the padded buffer.
+    Reference: models/encoder_processor_decoder.py:98-127."""
+    _need_cuda(x)
+    if x.dim() != 5:
+        raise ValueError("assemble_input: x must be (batch, time, ensemble, grid, vars)")
+    x = x.contiguous().float()
+    B, T, E, G, V = x.shape
+    A = 0 if attrs is None else attrs.shape[1]
+    if attrs is not None:
+        _need_cuda(attrs)
+        attrs = attrs.contiguous().float()
+        if (B * E * G) % attrs.shape[0] != 0:
+            raise ValueError(f"assemble_input: {attrs.shape[0]} attribute rows do not tile {B * E * G} node rows")
+    K = T * V + A
+    Kpad = (K + pad_to - 1) // pad_to * pad_to
+    out = torch.empty((B * E * G, Kpad), dtype=out_dtype, device=x.device)
+    with _Timed("assemble_input", 0.0, float(x.numel()) * 4 + out.numel() * out.element_size()):
+        rc = _lib.load().anemoi_b200_assemble_input(_ptr(x), B, T, E, G, V, _ptr(attrs) if attrs is not None else None, A,
+                                                    attrs.shape[0] if attrs is not None else 0, _ptr(out), Kpad, Kpad, dtype_code(out_dtype), _stream())  # fmt: skip
+    _lib.check(rc, "anemoi_b200_assemble_input")
+    return out[:, :K]
+
+
+def assemble_output(dec: Tensor, x: Optional[Tensor], batch: int, ensemble: int, n_step_output: int, step: int = -1,
+                    skip_src: Optional[Tensor] = None, bound: Optional[Tensor] = None) -> Tensor:  # fmt: skip
+    """``rearrange(dec, "(b e g) (t v) -> b t e g v")`` as fp32 + residual of the input's ``step`` slice on the prognostic variables +
+    per-variable ReLU / LeakyReLU bounding, one pass.  ``skip_src`` / ``bound``: int32 [V_out] device tensors (see include/anemoi_b200.h).
+    Reference: models/encoder_processor_decoder.py:129-163."""
+    _need_cuda(dec)
+    M, C, ldd = _rows(dec)
+    if M % (batch * ensemble) or C % n_step_output:
+        raise ValueError("assemble_output: decoder output does not factor into (batch ensemble grid) x (time vars)")
+    G, V_out = M // (batch * ensemble), C // n_step_output
+    T_in = V_in = 0
+    if x is not None:
+        _need_cuda(x)
+        x = x.contiguous().float()
+        T_in, V_in = x.shape[1], x.shape[4]
+        if x.shape[0] != batch or x.shape[2] != ensemble or x.shape[3] != G:
+            raise ValueError("assemble_output: residual input does not match the decoder output rows")
+        step = step % T_in
+    y = torch.empty((batch, n_step_output, ensemble, G, V_out), dtype=torch.float32, device=dec.device)
+    with _Timed("assemble_output", 0.0, float(M) * C * dec.element_size() + y.numel() * 4.0):
+        rc = _lib.load().anemoi_b200_assemble_output(_ptr(dec), ldd, dtype_code(dec.dtype), _ptr(x) if x is not None else None, batch, T_in, ensemble, G,
+                                                     V_in, step, _ptr(skip_src) if skip_src is not None else None,
+                                                     _ptr(bound) if bound is not None else None, _ptr(y), n_step_output, V_out, _stream())  # fmt: skip
+    _lib.check(rc, "anemoi_b200_assemble_output")
+    return y

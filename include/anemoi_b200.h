@@ -131,6 +131,26 @@ ANEMOI_API int anemoi_b200_cast_pad(const void* in, int64_t ldi, int i_dtype, co
 ANEMOI_API int anemoi_b200_add(const void* a, int64_t lda, int a_dtype, const void* b, int64_t ldb, int b_dtype, void* out, int64_t ldo,
                                int o_dtype, int64_t M, int64_t C, void* stream);
 
+/* -- model glue either side of the path -------------------------------------------------
+ * Replaces `_assemble_input` (models/encoder_processor_decoder.py:98-127): einops.rearrange(x, "batch time ensemble grid vars ->
+ * (batch ensemble grid) (time vars)") + torch.cat with the node attributes (+ the autocast cast in front of the embedding Linear).
+ * x : fp32 [B, T, E, G, V] contiguous; attrs : fp32 [attr_rows, A] (row r of the output reads attrs[r % attr_rows]), may be NULL when
+ * A == 0; out : [B*E*G, ldo] of o_dtype, columns [0, T*V) = data, [T*V, T*V+A) = attributes, [T*V+A, Kpad) = 0.
+ */
+ANEMOI_API int anemoi_b200_assemble_input(const float* x, int64_t B, int64_t T, int64_t E, int64_t G, int64_t V, const float* attrs, int64_t A,
+                               int64_t attr_rows, void* out, int64_t ldo, int64_t Kpad, int o_dtype, void* stream);
+
+/* Replaces `_assemble_output` (models/encoder_processor_decoder.py:129-163) with the SkipConnection residual (layers/residual.py:60-81)
+ * and the ReLU / LeakyReLU boundings (layers/bounding.py:81-94) fused:
+ *   y[b, t, e, g, v] = bound_v(dec[(b e g), t*V_out + v] + (skip_src[v] >= 0 ? x[b, step, e, g, skip_src[v]] : 0))
+ * dec : [B*E*G, ldd] of d_dtype; x : fp32 [B, T_in, E, G, V_in] (may be NULL: no residual); skip_src : int32 [V_out] input-variable index
+ * of each output variable or -1 (may be NULL); bound : int32 [V_out] 0 = none, 1 = relu, 2 = leaky_relu(0.01) (may be NULL);
+ * y : fp32 [B, T_out, E, G, V_out] contiguous.
+ */
+ANEMOI_API int anemoi_b200_assemble_output(const void* dec, int64_t ldd, int d_dtype, const float* x, int64_t B, int64_t T_in, int64_t E, int64_t G,
+                                int64_t V_in, int64_t step, const int32_t* skip_src, const int32_t* bound, float* y, int64_t T_out,
+                                int64_t V_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

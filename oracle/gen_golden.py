@@ -204,8 +204,47 @@ def integer_cases():
     print("integer", len(cases))
 
 
+@torch.no_grad()
+def graph_provider_cases(seed=11):
+    """StaticGraphProvider / TrainableTensor / NamedNodesAttributes (layers/graph_provider.py:145-291, layers/graph.py:20-118) on a
+    seeded UNSORTED bipartite sub-graph with two fixed attributes and a randomised trainable tensor; batch sizes 1 and 3."""
+    from torch_geometric.data import HeteroData
+
+    from anemoi.models.layers.graph import NamedNodesAttributes
+    from anemoi.models.layers.graph_provider import StaticGraphProvider
+
+    g = torch.Generator().manual_seed(seed)
+    n_src, n_dst, e = 37, 29, 160
+    graph = HeteroData()
+    graph["data"].x = torch.rand(n_src, 2, generator=g) * 3.0 - 1.5
+    graph["hidden"].x = torch.rand(n_dst, 2, generator=g) * 3.0 - 1.5
+    sub = graph[("data", "to", "hidden")]
+    sub.edge_index = torch.stack([torch.randint(0, n_src, (e,), generator=g), torch.randint(0, n_dst, (e,), generator=g)])
+    sub.edge_length = torch.rand(e, 1, generator=g)
+    sub.edge_dirs = torch.randn(e, 2, generator=g)
+    prov = StaticGraphProvider(graph=sub, edge_attributes=["edge_length", "edge_dirs"], src_size=n_src, dst_size=n_dst, trainable_size=3)
+    prov.trainable.trainable.copy_(torch.randn(e, 3, generator=g))
+    out = {"kind": "graph_provider", "n_src": n_src, "n_dst": n_dst, "edge_index": sub.edge_index, "edge_length": sub.edge_length,
+           "edge_dirs": sub.edge_dirs, "coords": {"data": graph["data"].x, "hidden": graph["hidden"].x}, "sd": sd_of(prov), "edge_dim": prov.edge_dim,
+           "edges": {}}  # fmt: skip
+    for bs in (1, 3):
+        ea, ei, sizes = prov.get_edges(batch_size=bs, model_comm_group=None, act_checkpoint=False)
+        assert sizes is None
+        out["edges"][bs] = {"edge_attr": ea.clone(), "edge_index": ei.clone()}
+    attrs = NamedNodesAttributes({"hidden": 4}, graph)
+    attrs.trainable_tensors["hidden"].trainable.copy_(torch.randn(n_dst, 4, generator=g))
+    out["attrs_sd"] = sd_of(attrs)
+    out["attrs"] = {(name, bs): attrs(name, batch_size=bs).clone() for name in ("data", "hidden") for bs in (1, 2)}
+    out["attr_ndims"] = dict(attrs.attr_ndims)
+    out["num_nodes"] = dict(attrs.num_nodes)
+    out["coords_back"] = {name: attrs.get_coordinates(name).clone() for name in ("data", "hidden")}
+    torch.save(out, os.path.join(OUT, "graph_provider.pt"))
+    print("graph_provider", prov.edge_dim, tuple(out["edges"][3]["edge_index"].shape))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    graph_provider_cases()
     gnn_processor_case("gnn_processor_small", 100, 200, 32, 2, 3, seed=1)
     gnn_processor_case("gnn_processor_cfg1", 1000, 4000, 32, 2, 3, seed=1234)
     gt_processor_case("gt_processor_small", 100, 200, 64, 4, 2, 11, seed=2)

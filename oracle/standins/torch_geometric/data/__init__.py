@@ -2,14 +2,25 @@ class _Store(dict):
     __getattr__ = dict.__getitem__
     __setattr__ = dict.__setitem__
 
+    @property
+    def num_nodes(self):
+        return self["x"].shape[0]
+
 
 class HeteroData(dict):
-    """Dict-of-stores stand-in: data["name"].x, data[("a","to","b")].edge_index ..."""
+    """Dict-of-stores stand-in: data["name"].x, data[("a","to","b")].edge_index ...; node sets are the str keys."""
 
     def __getitem__(self, key):
         if key not in self:
             super().__setitem__(key, _Store())
         return super().__getitem__(key)
+
+    @property
+    def node_types(self):
+        return [k for k in self.keys() if isinstance(k, str)]
+
+    def node_items(self):
+        return [(k, v) for k, v in self.items() if isinstance(k, str)]
 
     def to(self, *a, **k):
         return self

@@ -1,6 +1,6 @@
 """Isolated kernel timings at cfg2 shapes (ico-6 mesh, C=512, H=16, bf16): attention (folded lin_edge) and the four
 per-layer GEMMs.  CUDA events, L2 flushed before every timed launch, median of N.  Usage (on the GPU box):
-    python profiles/bench_kernels.py [attn] [gemm] [--reps 30]
+    python profiles/bench_kernels.py [attn] [gemm] [gc] [cublas] [--reps 30]
 Prints one JSON line per kernel with us, achieved GB/s or TFLOP/s and the fraction of the measured peaks."""
 import json
 import os
@@ -71,8 +71,14 @@ if "gemm" in which:
         o = torch.empty(M, N_, dtype=torch.bfloat16, device=dev)
         med, mn = timeit(lambda: ops.linear(a, w, bias, gelu=gelu, residual=r, out=o))
         fl = 2.0 * M * N_ * K
-        print(json.dumps({"kernel": f"linear {name} [{M}x{K}]x[{K}x{N_}]", "us_median": round(med, 1), "us_min": round(mn, 1),
-                          "TFLOPs": round(fl / med / 1e6, 1), "frac_tensor_burst": round(fl / med / 1e6 / pk["bf16_tflops"], 3)}))  # fmt: skip
+        rec = {"kernel": f"linear {name} [{M}x{K}]x[{K}x{N_}]", "us_median": round(med, 1), "us_min": round(mn, 1),
+               "TFLOPs": round(fl / med / 1e6, 1), "frac_tensor_burst": round(fl / med / 1e6 / pk["bf16_tflops"], 3)}
+        if "cublas" in which:  # library yardstick: the bare GEMM of the same shape (no bias / GELU / residual), cuBLAS through torch.matmul
+            wt = w.t()
+            cm, _ = timeit(lambda: torch.matmul(a, wt, out=o))
+            rec["cublas_plain_gemm_us"] = round(cm, 1)
+            rec["cublas_TFLOPs"] = round(fl / cm / 1e6, 1)
+        print(json.dumps(rec))
 
 if "gc" in which:
     gr = build_graph("o96", 6)

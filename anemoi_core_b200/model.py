@@ -1,7 +1,7 @@
 """Encoder -> processor -> decoder forward step (the call sequence of ``AnemoiModelEncProcDec.forward``,
 models/encoder_processor_decoder.py:260-324) over the drop-in mappers / processor, plus CUDA-graph capture of the whole
-step.  This is the unit the benchmark times ("forward ms/step", BASELINE.json); the surrounding model glue
-(input assembly, boundings, pre/post-processors) stays with the caller.
+step (``EncProcDec``: the unit the benchmark times, "forward ms/step", BASELINE.json), and the reference model around it
+(``AnemoiModelEncProcDec``: graph providers, node attributes, input / output assembly, residual, boundings - SURVEY.md §8f ranks 1-2).
 """
 
 from __future__ import annotations
@@ -140,3 +140,154 @@ class EncProcDec(nn.Module):
             return static_out
 
         return replay
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# The reference model around the step
+# ------------------------------------------------------------------------------------------------------------------------
+_BOUND_CODES = {"relu": 1, "leaky_relu": 2}
+
+
+class AnemoiModelEncProcDec(nn.Module):
+    """``anemoi.models.models.AnemoiModelEncProcDec`` (models/encoder_processor_decoder.py:33-330) with explicit constructor arguments in
+    place of the hydra / DotDict configuration: the same sub-module names - ``node_attributes``, ``encoder_graph_provider[ds]``,
+    ``encoder[ds]``, ``processor_graph_provider``, ``processor``, ``decoder_graph_provider[ds]``, ``decoder[ds]`` - hence the same
+    ``state_dict`` keys (a reference checkpoint loads with ``strict=True``), and the same ``forward(x: dict[str, Tensor], *,
+    model_comm_group=None, grid_shard_sizes=None) -> dict[str, Tensor]`` on ``(batch, time, ensemble, grid, vars)`` tensors.
+
+    ``_assemble_input`` is one kernel that writes the embedding GEMM's operand (``ops.assemble_input``), ``_assemble_output`` one kernel
+    that fuses the rearrange, the SkipConnection residual on the prognostic variables and the ReLU / LeakyReLU boundings
+    (``ops.assemble_output``); the graph providers hand back identity-stable tensors so every CSR plan is built once.
+
+    graph_data: ``{node_set: {"x": coords}}`` plus ``{(src, "to", dst): {"edge_index": ..., <attribute>: ...}}`` (a PyG ``HeteroData`` works).
+    boundings: ``{dataset: [("relu" | "leaky_relu", [output variable indices]), ...]}``.
+    Model sharding: GraphTransformer kind, hidden rows sharded like the reference (balanced dst ranges, provider-sharded edges);
+    the grid stays replicated unless ``grid_shard_sizes`` is given.
+    """
+
+    def __init__(self, kind: str, *, graph_data, dataset_names=("data",), hidden_nodes_name: str = "hidden", edge_attributes: list[str],
+                 num_channels: int, n_step_input: int, n_step_output: int, num_input_channels: dict[str, int], num_output_channels: dict[str, int],
+                 internal_input_idx: dict[str, list[int]], internal_output_idx: dict[str, list[int]], encoder: dict, processor: dict, decoder: dict,
+                 trainable_parameters: Optional[dict[str, int]] = None, latent_skip: bool = True, boundings: Optional[dict] = None,
+                 residual_step: int = -1) -> None:  # fmt: skip
+        super().__init__()
+        from .layers import NamedNodesAttributes
+        from .layers import create_graph_provider
+
+        if kind not in ("graphtransformer", "gnn"):
+            raise ValueError(f"unknown model kind {kind!r}")
+        self.kind, self.dataset_names, self._graph_name_hidden = kind, list(dataset_names), hidden_nodes_name
+        self.num_channels, self.n_step_input, self.n_step_output, self.latent_skip = num_channels, n_step_input, n_step_output, latent_skip
+        self.residual_step = residual_step
+        tp = dict(trainable_parameters or {})
+        node_sets = {k: v for k, v in graph_data.items() if isinstance(k, str)}
+        self.node_attributes = NamedNodesAttributes({n: tp.get(n, 0) for n in node_sets}, node_sets)
+        self._internal_input_idx = {k: list(v) for k, v in internal_input_idx.items()}
+        self._internal_output_idx = {k: list(v) for k, v in internal_output_idx.items()}
+        self.input_dim = {ds: n_step_input * num_input_channels[ds] + self.node_attributes.attr_ndims[ds] for ds in self.dataset_names}
+        self.input_dim_latent = self.node_attributes.attr_ndims[hidden_nodes_name]
+        self.output_dim = {ds: n_step_output * num_output_channels[ds] for ds in self.dataset_names}
+        self.num_output_channels = dict(num_output_channels)
+        n = self.node_attributes.num_nodes
+        hid = hidden_nodes_name
+        if kind == "graphtransformer":
+            enc_cls, proc_cls, dec_cls = GraphTransformerForwardMapper, GraphTransformerProcessor, GraphTransformerBackwardMapper
+        else:
+            enc_cls, proc_cls, dec_cls = GNNForwardMapper, GNNProcessor, GNNBackwardMapper
+        self.encoder_graph_provider, self.encoder = nn.ModuleDict(), nn.ModuleDict()
+        self.decoder_graph_provider, self.decoder = nn.ModuleDict(), nn.ModuleDict()
+        for ds in self.dataset_names:
+            self.encoder_graph_provider[ds] = create_graph_provider(graph=graph_data[(ds, "to", hid)], edge_attributes=edge_attributes, src_size=n[ds],
+                                                                   dst_size=n[hid], trainable_size=tp.get("data2hidden", 0))  # fmt: skip
+            self.encoder[ds] = enc_cls(in_channels_src=self.input_dim[ds], in_channels_dst=self.input_dim_latent, hidden_dim=num_channels,
+                                       edge_dim=self.encoder_graph_provider[ds].edge_dim, **encoder)  # fmt: skip
+        self.processor_graph_provider = create_graph_provider(graph=graph_data[(hid, "to", hid)], edge_attributes=edge_attributes, src_size=n[hid],
+                                                              dst_size=n[hid], trainable_size=tp.get("hidden2hidden", 0))  # fmt: skip
+        self.processor = proc_cls(num_channels=num_channels, edge_dim=self.processor_graph_provider.edge_dim, **processor)
+        for ds in self.dataset_names:
+            self.decoder_graph_provider[ds] = create_graph_provider(graph=graph_data[(hid, "to", ds)], edge_attributes=edge_attributes, src_size=n[hid],
+                                                                   dst_size=n[ds], trainable_size=tp.get("hidden2data", 0))  # fmt: skip
+            # GT: the decoder embeds the raw assembled grid input (mapper.py:698-701); GNN: its dst input is the encoder's src embedding
+            in_dst = self.input_dim[ds] if kind == "graphtransformer" else num_channels
+            self.decoder[ds] = dec_cls(in_channels_src=num_channels, in_channels_dst=in_dst, hidden_dim=num_channels, out_channels_dst=self.output_dim[ds],
+                                       edge_dim=self.decoder_graph_provider[ds].edge_dim, **decoder)  # fmt: skip
+        # per-output-variable tables of the fused output kernel (plain attributes like the reference's bounding index tensors: no state_dict keys)
+        self._tables: dict = {}
+        self._bound_spec = {ds: list((boundings or {}).get(ds, [])) for ds in self.dataset_names}
+
+    def _output_tables(self, ds: str, device) -> tuple[Tensor, Tensor]:
+        key = (ds, str(device))
+        if key not in self._tables:
+            v_out = self.num_output_channels[ds]
+            skip = torch.full((v_out,), -1, dtype=torch.int32)
+            skip[torch.tensor(self._internal_output_idx[ds], dtype=torch.long)] = torch.tensor(self._internal_input_idx[ds], dtype=torch.int32)
+            bound = torch.zeros(v_out, dtype=torch.int32)
+            for name, idx in self._bound_spec[ds]:  # applied in order; relu and leaky_relu are idempotent, the last one listed for a variable wins
+                bound[torch.tensor(list(idx), dtype=torch.long)] = _BOUND_CODES[name]
+            self._tables[key] = (skip.to(device), bound.to(device))
+        return self._tables[key]
+
+    def _assemble_input(self, x: Tensor, batch_size: int, grid_shard_sizes, model_comm_group, dataset_name: str, dt: torch.dtype):
+        from .distributed.graph import shard_rows
+        from .layers._functional import pad_k
+
+        attrs = self.node_attributes(dataset_name, batch_size=batch_size)
+        sizes = grid_shard_sizes[dataset_name] if grid_shard_sizes is not None else None
+        if sizes is not None:
+            attrs = shard_rows(attrs, sizes, model_comm_group)
+        k = x.shape[1] * x.shape[4] + attrs.shape[1]
+        return ops.assemble_input(x, attrs, dt, k_pad=pad_k(k, dt)), sizes
+
+    def forward(self, x: dict[str, Tensor], *, model_comm_group=None, grid_shard_sizes=None, **kwargs) -> dict[str, Tensor]:
+        from .distributed.balanced_partition import get_balanced_partition_sizes
+        from .distributed.graph import group_size
+        from .distributed.graph import shard_rows
+        from .layers._functional import compute_dtype
+
+        names = list(x.keys())
+        batch = {t.shape[0] for t in x.values()}
+        ens = {t.shape[2] for t in x.values()}
+        assert len(batch) == 1 and len(ens) == 1, "Dimensions must be the same across datasets"
+        batch_size, ensemble_size = batch.pop(), ens.pop()
+        world = group_size(model_comm_group)
+        if world > 1:
+            assert batch_size == 1 and ensemble_size == 1, "Only batch / ensemble size 1 per device when the model is sharded across GPUs"
+            if self.kind != "graphtransformer":
+                raise NotImplementedError("sharded forward of the GNN model: shard the processor through EncProcDec, the GNN mappers run replicated")
+        dt = compute_dtype(*x.values())
+        hid = self._graph_name_hidden
+        x_hidden = self.node_attributes(hid, batch_size=batch_size)
+        sizes_hidden = get_balanced_partition_sizes(x_hidden.shape[0], world) if world > 1 else None
+        x_hidden = shard_rows(x_hidden, sizes_hidden, model_comm_group)
+        latents, x_data_latents, sizes_data = [], {}, {}
+        for ds in names:
+            x_data, sizes_data[ds] = self._assemble_input(x[ds], batch_size, grid_shard_sizes, model_comm_group, ds, dt)
+            ea, ei, es = self.encoder_graph_provider[ds].get_edges(batch_size=batch_size, model_comm_group=model_comm_group)
+            info = BipartiteGraphShardInfo(src_nodes=sizes_data[ds], dst_nodes=sizes_hidden, edges=es)
+            x_data_latents[ds], lat = self.encoder[ds]((x_data, x_hidden), batch_size, info, ea, ei, model_comm_group, keep_x_dst_sharded=True)
+            latents.append(lat)
+        x_latent = latents[0]
+        for lat in latents[1:]:
+            x_latent = ops.add(x_latent, lat)
+        ea, ei, es = self.processor_graph_provider.get_edges(batch_size=batch_size, model_comm_group=model_comm_group)
+        x_proc = self.processor(x_latent, batch_size, GraphShardInfo(nodes=sizes_hidden if world > 1 else [x_latent.shape[0]], edges=es), ea, ei,
+                                model_comm_group)  # fmt: skip
+        if self.latent_skip:
+            x_proc = ops.add(x_proc, x_latent)
+        out = {}
+        for ds in names:
+            ea, ei, es = self.decoder_graph_provider[ds].get_edges(batch_size=batch_size, model_comm_group=model_comm_group)
+            info = BipartiteGraphShardInfo(src_nodes=sizes_hidden, dst_nodes=sizes_data[ds], edges=es)
+            if world > 1 and sizes_data[ds] is None:
+                # replicated grid: every rank owns a balanced slice of the grid rows inside the decoder and the output is gathered
+                n_grid = x_data_latents[ds].shape[0]
+                info = BipartiteGraphShardInfo(src_nodes=sizes_hidden, dst_nodes=get_balanced_partition_sizes(n_grid, world), edges=None)
+                ea, ei, _ = self.decoder_graph_provider[ds].get_edges(batch_size=batch_size, model_comm_group=model_comm_group, shard_edges=False)
+                x_dst = shard_rows(x_data_latents[ds], info.dst_nodes, model_comm_group)
+                dec = self.decoder[ds]((x_proc, x_dst), batch_size, info, ea, ei, model_comm_group, keep_x_dst_sharded=False)
+            else:
+                dec = self.decoder[ds]((x_proc, x_data_latents[ds]), batch_size, info, ea, ei, model_comm_group,
+                                       keep_x_dst_sharded=sizes_data[ds] is not None)  # fmt: skip
+            skip, bound = self._output_tables(ds, dec.device)
+            out[ds] = ops.assemble_output(dec, x[ds], batch_size, ensemble_size, self.n_step_output, self.residual_step, skip, bound).to(x[ds].dtype)
+        return out

@@ -428,29 +428,30 @@ def row_stats(x: Tensor, eps: float = 1e-5) -> Tensor:
     return stats
 
 
-def assemble_input(x: Tensor, attrs: Optional[Tensor], out_dtype: torch.dtype, pad_to: int = 8) -> Tensor:
-    """``cat([rearrange(x, "b t e g v -> (b e g) (t v)"), attrs], -1)`` in ``out_dtype`` with the row length zero-padded to a multiple
-    of ``pad_to`` (so the result is directly the A operand of the embedding GEMM).  Returns the [B*E*G, T*V+A] view of the padded buffer.
+def assemble_input(x: Tensor, attrs: Optional[Tensor], out_dtype: torch.dtype, k_pad: Optional[int] = None) -> Tensor:
+    """``cat([rearrange(x, "b t e g v -> (b e g) (t v)"), attrs], -1)`` in ``out_dtype``; with ``k_pad`` the rows are zero-padded to that
+    width, so the result is directly the (K-padded) A operand of the embedding GEMM.  Returns [B*E*G, k_pad or T*V+A].
     Reference: models/encoder_processor_decoder.py:98-127."""
-    _need_cuda(x)
+    _need_cuda(x, attrs)
     if x.dim() != 5:
         raise ValueError("assemble_input: x must be (batch, time, ensemble, grid, vars)")
     x = x.contiguous().float()
     B, T, E, G, V = x.shape
     A = 0 if attrs is None else attrs.shape[1]
     if attrs is not None:
-        _need_cuda(attrs)
         attrs = attrs.contiguous().float()
-        if (B * E * G) % attrs.shape[0] != 0:
+        if B * E * G > 0 and (attrs.shape[0] == 0 or (B * E * G) % attrs.shape[0] != 0):
             raise ValueError(f"assemble_input: {attrs.shape[0]} attribute rows do not tile {B * E * G} node rows")
     K = T * V + A
-    Kpad = (K + pad_to - 1) // pad_to * pad_to
+    Kpad = K if k_pad is None else int(k_pad)
+    if Kpad < K:
+        raise ValueError("assemble_input: k_pad smaller than the assembled width")
     out = torch.empty((B * E * G, Kpad), dtype=out_dtype, device=x.device)
     with _Timed("assemble_input", 0.0, float(x.numel()) * 4 + out.numel() * out.element_size()):
-        rc = _lib.load().anemoi_b200_assemble_input(_ptr(x), B, T, E, G, V, _ptr(attrs) if attrs is not None else None, A,
-                                                    attrs.shape[0] if attrs is not None else 0, _ptr(out), Kpad, Kpad, dtype_code(out_dtype), _stream())  # fmt: skip
+        rc = _lib.load().anemoi_b200_assemble_input(_ptr(x), B, T, E, G, V, _ptr(attrs), A, attrs.shape[0] if attrs is not None else 0, _ptr(out),
+                                                    Kpad, Kpad, dtype_code(out_dtype), _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_assemble_input")
-    return out[:, :K]
+    return out
 
 
 def assemble_output(dec: Tensor, x: Optional[Tensor], batch: int, ensemble: int, n_step_output: int, step: int = -1,

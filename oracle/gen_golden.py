@@ -242,9 +242,127 @@ def graph_provider_cases(seed=11):
     print("graph_provider", prov.edge_dim, tuple(out["edges"][3]["edge_index"].shape))
 
 
+def _load_reference_model_class():
+    """``AnemoiModelEncProcDec`` from the unmodified reference file.  Its package ``anemoi.models.models`` cannot be imported here
+    (``base.py`` needs omegaconf / anemoi.graphs / the pre-processor stack), so the FILE is loaded under a stub package whose
+    ``BaseGraphModel`` is an ``nn.Module`` carrying the two one-line helpers ``forward`` calls (base.py:204-223, restated).  Everything
+    that is exercised - ``forward``, ``_assemble_input``, ``_assemble_output``, ``_assert_valid_sharding`` - is the reference's code."""
+    import importlib.util
+    import types
+
+    class BaseGraphModel(torch.nn.Module):
+        def _resolve_in_out_sharded(self, dataset_names, grid_shard_sizes):  # base.py:204-216
+            return {n: False if grid_shard_sizes is None else grid_shard_sizes[n] is not None for n in dataset_names}
+
+        def _get_consistent_dim(self, x, dim):  # base.py:218-223
+            sizes = [_x.shape[dim] for _x in x.values()]
+            assert all(b == sizes[0] for b in sizes)
+            return sizes[0]
+
+    pkg = types.ModuleType("anemoi.models.models")
+    pkg.__path__ = []
+    pkg.BaseGraphModel = BaseGraphModel
+    sys.modules["anemoi.models.models"] = pkg
+    path = "/root/reference/models/src/anemoi/models/models/encoder_processor_decoder.py"
+    spec = importlib.util.spec_from_file_location("anemoi.models.models.encoder_processor_decoder", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.AnemoiModelEncProcDec
+
+
+class _SkipConnection(torch.nn.Module):
+    """layers/residual.py:60-81 restated (that module imports anemoi.graphs, absent here): most recent input step, expanded over the
+    output steps."""
+
+    def __init__(self, step: int = -1):
+        super().__init__()
+        self.step = step
+
+    def forward(self, x, grid_shard_sizes=None, model_comm_group=None, n_step_output=None):
+        x_skip = x[:, self.step, ...]
+        return x_skip if n_step_output is None else x_skip.unsqueeze(1).expand(-1, n_step_output, -1, -1, -1)
+
+
+@torch.no_grad()
+def model_cases(seed=21):
+    """Whole ``AnemoiModelEncProcDec.forward`` (models/encoder_processor_decoder.py:185-330) for both model kinds on a small seeded graph:
+    reference graph providers (trainable edge tensors), NamedNodesAttributes (trainable node tensors), mappers, processor, latent skip,
+    SkipConnection residual on the prognostic variables and a ReluBounding; batch 2, 2 input steps, 1 output step."""
+    from torch_geometric.data import HeteroData
+
+    from anemoi.models.layers.bounding import ReluBounding
+    from anemoi.models.layers.graph import NamedNodesAttributes
+    from anemoi.models.layers.graph_provider import create_graph_provider
+
+    Model = _load_reference_model_class()
+    g = torch.Generator().manual_seed(seed)
+    n_data, n_hid, C, heads = 60, 24, 32, 4
+    n_in, n_out, t_in, t_out, batch = 7, 5, 2, 1, 2  # 7 input variables (5 prognostic + 2 forcings), 5 outputs
+    in_prog, out_prog = [0, 1, 2, 4, 5], [0, 1, 2, 3, 4]  # model.input.prognostic / model.output.prognostic index lists
+    graph = HeteroData()
+    graph["data"].x = torch.rand(n_data, 2, generator=g) * 3.0 - 1.5
+    graph["hidden"].x = torch.rand(n_hid, 2, generator=g) * 3.0 - 1.5
+
+    def sub(src, dst, n_src, n_dst, e):
+        st = graph[(src, "to", dst)]
+        dst_ids = torch.cat([torch.arange(n_dst), torch.randint(0, n_dst, (e - n_dst,), generator=g)])  # every dst row has an edge
+        st.edge_index = torch.stack([torch.randint(0, n_src, (e,), generator=g), dst_ids[torch.randperm(e, generator=g)]])
+        st.edge_length = torch.rand(e, 1, generator=g)
+        st.edge_dirs = torch.randn(e, 2, generator=g)
+        return st
+
+    subs = {"enc": sub("data", "hidden", n_data, n_hid, 150), "proc": sub("hidden", "hidden", n_hid, n_hid, 120),
+            "dec": sub("hidden", "data", n_hid, n_data, 200)}  # fmt: skip
+    x = torch.randn(batch, t_in, 1, n_data, n_in, generator=g)
+    out = {"kind": "model", "dims": dict(n_data=n_data, n_hid=n_hid, C=C, heads=heads, n_in=n_in, n_out=n_out, t_in=t_in, t_out=t_out, batch=batch),
+           "in_prog": in_prog, "out_prog": out_prog, "bound_vars": [1, 3], "coords": {"data": graph["data"].x, "hidden": graph["hidden"].x},
+           "graph": {k: {"edge_index": v.edge_index, "edge_length": v.edge_length, "edge_dirs": v.edge_dirs} for k, v in subs.items()},
+           "x": x, "cases": {}}  # fmt: skip
+    for kind in ("graphtransformer", "gnn"):
+        torch.manual_seed(seed)
+        m = Model.__new__(Model)
+        torch.nn.Module.__init__(m)
+        m._graph_name_hidden, m.n_step_output, m.latent_skip = "hidden", t_out, True
+        m._internal_input_idx, m._internal_output_idx = {"data": in_prog}, {"data": out_prog}
+        m.node_attributes = NamedNodesAttributes({"data": 0, "hidden": 3}, graph)
+        m.node_attributes.trainable_tensors["hidden"].trainable.copy_(torch.randn(n_hid, 3, generator=g))
+        prov = {k: create_graph_provider(graph=v, edge_attributes=["edge_length", "edge_dirs"], src_size=s, dst_size=d, trainable_size=2)
+                for (k, v), (s, d) in zip(subs.items(), ((n_data, n_hid), (n_hid, n_hid), (n_hid, n_data)))}  # fmt: skip
+        for pv in prov.values():
+            pv.trainable.trainable.copy_(0.5 * torch.randn(pv.trainable.trainable.shape, generator=g))
+        m.encoder_graph_provider = torch.nn.ModuleDict({"data": prov["enc"]})
+        m.processor_graph_provider = prov["proc"]
+        m.decoder_graph_provider = torch.nn.ModuleDict({"data": prov["dec"]})
+        in_dim = t_in * n_in + m.node_attributes.attr_ndims["data"]
+        lat_dim = m.node_attributes.attr_ndims["hidden"]
+        edge_dim = prov["enc"].edge_dim
+        if kind == "graphtransformer":
+            kw = dict(num_heads=heads, mlp_hidden_ratio=4, edge_dim=edge_dim, layer_kernels=None, graph_attention_backend="pyg", num_chunks=1)
+            enc = GraphTransformerForwardMapper(in_channels_src=in_dim, in_channels_dst=lat_dim, hidden_dim=C, **kw)
+            proc = GraphTransformerProcessor(num_layers=2, num_channels=C, **kw)
+            dec = GraphTransformerBackwardMapper(in_channels_src=C, in_channels_dst=in_dim, hidden_dim=C, out_channels_dst=t_out * n_out, **kw)
+        else:
+            kw = dict(mlp_extra_layers=0, edge_dim=edge_dim, layer_kernels=None, num_chunks=1)
+            enc = GNNForwardMapper(in_channels_src=in_dim, in_channels_dst=lat_dim, hidden_dim=C, **kw)
+            proc = GNNProcessor(num_layers=2, num_channels=C, **kw)
+            dec = GNNBackwardMapper(in_channels_src=C, in_channels_dst=in_dim, hidden_dim=C, out_channels_dst=t_out * n_out, **kw)
+        m.encoder = torch.nn.ModuleDict({"data": randomise(enc, seed)})
+        m.processor = randomise(proc, seed + 1)
+        m.decoder = torch.nn.ModuleDict({"data": randomise(dec, seed + 2)})
+        m.residual = torch.nn.ModuleDict({"data": _SkipConnection(step=-1)})
+        name_to_index = {f"v{i}": i for i in range(n_out)}
+        m.boundings = torch.nn.ModuleDict({"data": torch.nn.ModuleList([ReluBounding(variables=["v1", "v3"], name_to_index=name_to_index)])})
+        m.eval()
+        y = m({"data": x.clone()})["data"]
+        out["cases"][kind] = {"sd": sd_of(m), "y": y.clone(), "in_dim": in_dim, "lat_dim": lat_dim, "edge_dim": edge_dim}
+        print("model", kind, tuple(y.shape), float(y.abs().mean()))
+    torch.save(out, os.path.join(OUT, "model_forward.pt"))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     graph_provider_cases()
+    model_cases()
     gnn_processor_case("gnn_processor_small", 100, 200, 32, 2, 3, seed=1)
     gnn_processor_case("gnn_processor_cfg1", 1000, 4000, 32, 2, 3, seed=1234)
     gt_processor_case("gt_processor_small", 100, 200, 64, 4, 2, 11, seed=2)

@@ -312,3 +312,78 @@ def gnn_encode_process_decode(sds, graph, x_grid, x_mesh, num_layers, autocast_l
     proc = gnn_processor(sds["processor"], lat, graph["proc_attr"], graph["proc_index"], num_layers, autocast_ln, max_layers)
     proc = proc + lat
     return gnn_backward_mapper(sds["decoder"], proc, src_emb, graph["dec_attr"], graph["dec_index"], autocast_ln)
+
+
+# ----------------------------------------------------------------------------------------------
+# graph providers, node attributes and the model glue either side of the step
+# ----------------------------------------------------------------------------------------------
+def static_graph_provider_edges(edge_index: Tensor, attrs: list[Tensor], trainable: Optional[Tensor], src_size: int, dst_size: int,
+                                batch_size: int) -> tuple[Tensor, Tensor]:  # fmt: skip
+    """layers/graph_provider.py:185-256 + layers/graph.py:38-46 — stable dst sort once, cat(fixed attributes)[perm], cat with the trainable
+    tensor, rows tiled ``batch_size`` times; edge_index replicated with (src_size, dst_size) offsets per batch element."""
+    ei, perm = sort_edge_index_by_dst(edge_index)
+    ea = torch.cat(attrs, dim=1).index_select(0, perm)
+    if trainable is not None:
+        ea = torch.cat([ea, trainable], dim=-1)
+    ea = ea.repeat(batch_size, 1)
+    inc = torch.tensor([[src_size], [dst_size]], dtype=torch.int64)
+    return ea, torch.cat([ei + i * inc for i in range(batch_size)], dim=1)
+
+
+def named_node_attributes(coords: Tensor, trainable: Optional[Tensor], batch_size: int) -> Tensor:
+    """layers/graph.py:96-118 — [sin(coords), cos(coords), trainable], tiled over the batch."""
+    a = torch.cat([torch.sin(coords), torch.cos(coords)], dim=-1)
+    if trainable is not None:
+        a = torch.cat([a, trainable], dim=-1)
+    return a.repeat(batch_size, 1)
+
+
+def assemble_input(x: Tensor, node_attrs: Tensor) -> Tensor:
+    """models/encoder_processor_decoder.py:115-125 — "batch time ensemble grid vars -> (batch ensemble grid) (time vars)" ++ attributes."""
+    b, t, e, g, v = x.shape
+    return torch.cat([x.permute(0, 2, 3, 1, 4).reshape(b * e * g, t * v), node_attrs], dim=-1)
+
+
+def assemble_output(x_out: Tensor, x: Tensor, batch: int, ensemble: int, n_step_output: int, in_prog: list[int], out_prog: list[int],
+                    relu_vars: list[int], step: int = -1) -> Tensor:  # fmt: skip
+    """models/encoder_processor_decoder.py:129-163 — back to (batch time ensemble grid vars), SkipConnection residual (layers/residual.py:60-81:
+    the input's ``step`` slice for every output step) on the prognostic variables, then ReluBounding (layers/bounding.py:81-86)."""
+    g = x_out.shape[0] // (batch * ensemble)
+    y = x_out.reshape(batch, ensemble, g, n_step_output, -1).permute(0, 3, 1, 2, 4).to(x.dtype).clone()
+    skip = x[:, step].unsqueeze(1).expand(-1, n_step_output, -1, -1, -1)
+    y[..., out_prog] += skip[..., in_prog]
+    if relu_vars:
+        y[..., relu_vars] = F.relu(y[..., relu_vars])
+    return y
+
+
+def anemoi_model_forward(kind: str, sd: StateDict, fx: dict, num_layers: int = 2) -> Tensor:
+    """``AnemoiModelEncProcDec.forward`` (models/encoder_processor_decoder.py:185-330), single dataset "data", no model sharding, driven by the
+    reference model ``state_dict`` and the fixture's raw graph (``tests/golden/model_forward.pt``)."""
+    d, x = fx["dims"], fx["x"]
+    batch = x.shape[0]
+
+    def sub(prefix):
+        return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+    def edges(name, provider_prefix, n_src, n_dst):
+        gr = fx["graph"][name]
+        return static_graph_provider_edges(gr["edge_index"], [gr["edge_length"], gr["edge_dirs"]], sd.get(provider_prefix + "trainable.trainable"),
+                                           n_src, n_dst, batch)  # fmt: skip
+
+    attrs_data = named_node_attributes(fx["coords"]["data"], sd.get("node_attributes.trainable_tensors.data.trainable"), batch)
+    attrs_hid = named_node_attributes(fx["coords"]["hidden"], sd.get("node_attributes.trainable_tensors.hidden.trainable"), batch)
+    x_data = assemble_input(x, attrs_data)
+    enc_attr, enc_index = edges("enc", "encoder_graph_provider.data.", d["n_data"], d["n_hid"])
+    proc_attr, proc_index = edges("proc", "processor_graph_provider.", d["n_hid"], d["n_hid"])
+    dec_attr, dec_index = edges("dec", "decoder_graph_provider.data.", d["n_hid"], d["n_data"])
+    enc, proc, dec = sub("encoder.data."), sub("processor."), sub("decoder.data.")
+    if kind == "graphtransformer":
+        x_data_latent, lat = gt_forward_mapper(enc, x_data, attrs_hid, enc_attr, enc_index, d["heads"])
+        p = gt_processor(proc, lat, proc_attr, proc_index, num_layers, d["heads"]) + lat
+        out = gt_backward_mapper(dec, p, x_data_latent, dec_attr, dec_index, d["heads"])
+    else:
+        x_data_latent, lat = gnn_forward_mapper(enc, x_data, attrs_hid, enc_attr, enc_index)
+        p = gnn_processor(proc, lat, proc_attr, proc_index, num_layers) + lat
+        out = gnn_backward_mapper(dec, p, x_data_latent, dec_attr, dec_index)
+    return assemble_output(out, x, batch, x.shape[2], d["t_out"], fx["in_prog"], fx["out_prog"], fx["bound_vars"])

@@ -9,7 +9,10 @@
 namespace anemoi {
 
 __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int64_t m, int64_t n, float acc) {
-  if (ep.ln_stats) acc = ep.ln_stats[2 * m + 1] * (acc - ep.ln_stats[2 * m] * ep.ln_colsum[n]);
+  if (ep.ln_stats) {
+    const float2 st = ln_row_mean_rstd(ep, m);
+    acc = st.y * (acc - st.x * ep.ln_colsum[n]);
+  }
   if (ep.bias) acc += ep.bias[n];
   if (ep.g1) acc += ep.g1[(int64_t)ep.idx1[m] * ep.ldg + n];
   if (ep.g2) acc += ep.g2[(int64_t)ep.idx2[m] * ep.ldg + n];
@@ -73,7 +76,9 @@ int linear_simt(const void* A, int64_t lda, const void* W, int64_t ldw, int a_dt
     gemm_simt_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W, ldw, K, ep);
   else
     gemm_simt_kernel<float><<<grid, 256, 0, s>>>((const float*)A, lda, (const float*)W, ldw, K, ep);
-  return launch_status("gemm_simt_kernel");
+  int rc = launch_status("gemm_simt_kernel");
+  if (rc == 0 && ep.stats_out) rc = launch_partial_row_stats(ep.out, ep.ldo, ep.o_dtype, ep.M, ep.N, ep.stats_out, s);
+  return rc;
 }
 
 }  // namespace anemoi

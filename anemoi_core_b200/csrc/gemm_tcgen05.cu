@@ -224,7 +224,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 }
 
 // Epilogue mode bits (host-selected, warp-uniform): 0 = slow element-wise path.
-constexpr int kEpiFast = 1, kEpiOutF32 = 2, kEpiGelu = 4, kEpiRes = 8, kEpiGather = 16, kEpiLnFold = 32;
+constexpr int kEpiFast = 1, kEpiOutF32 = 2, kEpiGelu = 4, kEpiRes = 8, kEpiGather = 16, kEpiLnFold = 32, kEpiStats = 64;
 // debug ablations (ANEMOI_B200_GEMM_ABLATE, results are then wrong by construction): skip TMA loads / skip the epilogue body / skip the MMAs
 constexpr int kAblNoLoad = 256, kAblNoEpi = 512, kAblNoMma = 1024, kAblNoStore = 2048, kAblNoBias = 4096, kAblNoTmemLd = 8192;
 constexpr int kAblMask = kAblNoLoad | kAblNoEpi | kAblNoMma | kAblNoStore | kAblNoBias | kAblNoTmemLd;
@@ -250,7 +250,7 @@ struct EpiCtx {
 // Each warp owns 32 accumulator rows x kColsPerWarp columns and walks them in rounds of 64 bytes of output per row (32 bf16 / 16 fp32
 // columns).  The warp's 4 KB staging area is split into TWO 32-row x 64-byte buffers (64-byte-swizzled, the layout of a TMA box with a
 // 64-byte inner extent) used alternately: the TMA store of round r drains while round r+1 is computed (cp.async.bulk.wait_group.read 1).
-template <int BN, int STG_BUFS, bool OUT_F32, bool GELU, bool RES, bool GATHER, bool LNF>
+template <int BN, int STG_BUFS, bool OUT_F32, bool GELU, bool RES, bool GATHER, bool LNF, bool STATS = false>
 __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams& ep, const CUtensorMap* tmOut, const CUtensorMap* tmRes) {
   constexpr int kColsPerWarp = BN / kEpiGroups;
   constexpr int CW = OUT_F32 ? 16 : 32;  // columns per 64-byte staging row
@@ -315,8 +315,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
     }
     float ln_mean = 0.f, ln_rstd = 1.f;
     if constexpr (LNF) {
-      const int64_t r = min((int64_t)row0 + lane, ep.M - 1);
-      const float2 st = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + r);
+      const float2 st = ln_row_mean_rstd(ep, min((int64_t)row0 + lane, ep.M - 1));  // per tile, not per round
       ln_mean = st.x, ln_rstd = st.y;
     }
     const float* g1row = nullptr;
@@ -326,6 +325,9 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
       if (ep.g1) g1row = ep.g1 + (int64_t)__ldg(ep.idx1 + r) * ep.ldg;
       if (ep.g2) g2row = ep.g2 + (int64_t)__ldg(ep.idx2 + r) * ep.ldg;
     }
+    // STATS: (sum, sum of squares) of this thread's output row over the current 64-column block, taken from the bf16-ROUNDED values
+    // (what the consuming GEMM will read: a constant row must cancel exactly against its column sums)
+    float2 st_s = make_float2(0.f, 0.f), st_q = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int rd = 0; rd < ROUNDS; ++rd, ++rcount) {
       const int col_in_tile = cx.grp * kColsPerWarp + rd * CW;
@@ -474,7 +476,26 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
             v[4] += __uint_as_float(rv.z << 16), v[5] += __uint_as_float(rv.z & 0xffff0000u);
             v[6] += __uint_as_float(rv.w << 16), v[7] += __uint_as_float(rv.w & 0xffff0000u);
           }
-          ptx::sts128(addr, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          const uint32_t pk[4] = {pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])};
+          if constexpr (STATS) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 w2 = make_float2(__uint_as_float(pk[j] << 16), __uint_as_float(pk[j] & 0xffff0000u));
+              st_s = __fadd2_rn(st_s, w2);
+              st_q = __ffma2_rn(w2, w2, st_q);
+            }
+          }
+          ptx::sts128(addr, pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      if constexpr (STATS) {
+        static_assert(!STATS || (!OUT_F32 && kColsPerWarp % kStatsBlock == 0), "stats blocks are 64 bf16 columns = two rounds");
+        if (rd & 1) {  // a 64-column block is complete
+          const int64_t row = (int64_t)row0 + lane;
+          const int blk = (col0 - CW) / kStatsBlock;
+          const int parts = (int)((ep.N + kStatsBlock - 1) / kStatsBlock);
+          if (row < ep.M && blk < parts) reinterpret_cast<float2*>(ep.stats_out)[row * parts + blk] = make_float2(st_s.x + st_s.y, st_q.x + st_q.y);
+          st_s = make_float2(0.f, 0.f), st_q = make_float2(0.f, 0.f);
         }
       }
       ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
@@ -504,6 +525,7 @@ __device__ __noinline__ void epilogue_generic(const EpiCtx& cx, const EpiParams&
     const bool row_ok = row < ep.M;
     const float* g1row = (ep.g1 && row_ok) ? ep.g1 + (int64_t)ep.idx1[row] * ep.ldg : nullptr;
     const float* g2row = (ep.g2 && row_ok) ? ep.g2 + (int64_t)ep.idx2[row] * ep.ldg : nullptr;
+    const float2 ln_st = (ep.ln_stats && row_ok) ? ln_row_mean_rstd(ep, row) : make_float2(0.f, 1.f);
 #pragma unroll 1
     for (int c = 0; c < kColsPerWarp; c += 32) {
       uint32_t r[32];
@@ -517,7 +539,7 @@ __device__ __noinline__ void epilogue_generic(const EpiCtx& cx, const EpiParams&
           const int64_t n = col0 + j;
           if (n >= ep.N) break;
           float a = __uint_as_float(r[j]);
-          if (ep.ln_stats) a = ep.ln_stats[2 * row + 1] * (a - ep.ln_stats[2 * row] * ep.ln_colsum[n]);
+          if (ep.ln_stats) a = ln_st.y * (a - ln_st.x * ep.ln_colsum[n]);
           if (ep.bias) a += ep.bias[n];
           if (g1row) a += g1row[n];
           if (g2row) a += g2row[n];
@@ -735,6 +757,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         ANEMOI_EPI_CASE(false, true, false, true)
         ANEMOI_EPI_CASE(true, false, false, true)
         ANEMOI_EPI_CASE(true, true, false, true)
+        case kEpiStats:  // bf16 output + row statistics for the next LayerNorm (producer side), without / with residual
+          epilogue_fast<BN, Cfg::kStgBufs, false, false, false, false, false, true>(cx, ep, &tmOut, &tmRes);
+          break;
+        case kEpiStats | kEpiRes:
+          epilogue_fast<BN, Cfg::kStgBufs, false, false, true, false, false, true>(cx, ep, &tmOut, &tmRes);
+          break;
         ANEMOI_EPI_CASE_LN(false, false)
         ANEMOI_EPI_CASE_LN(false, true)
         ANEMOI_EPI_CASE_LN(true, false)
@@ -885,10 +913,14 @@ int linear_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, int64
   // folded LayerNorm: fast path needs a (non-null) bias tile, no residual / gather, aligned stats and column sums
   if (ep.ln_stats) fast = fast && ep.bias && !ep.residual && !gather && a16(ep.ln_colsum) && (reinterpret_cast<uintptr_t>(ep.ln_stats) & 7) == 0;
   int epi_mode = 0;
+  bool fused_stats = false;
   tmOut = tmA, tmRes = tmA;  // placeholders when unused
   if (fast) {
     epi_mode = kEpiFast | (os == 4 ? kEpiOutF32 : 0) | ((ep.flags & ANEMOI_EPI_GELU) ? kEpiGelu : 0) | (ep.residual ? kEpiRes : 0) |
                (gather ? kEpiGather : 0) | (ep.ln_stats ? kEpiLnFold : 0);
+    // the epilogue itself produces stats_out for the plain / residual bf16 forms; every other form takes the separate pass below
+    fused_stats = ep.stats_out && os == 2 && !(ep.flags & ANEMOI_EPI_GELU) && !gather && !ep.ln_stats && (reinterpret_cast<uintptr_t>(ep.stats_out) & 7) == 0;
+    if (fused_stats) epi_mode |= kEpiStats;
     rc = get_tensor_map(ep.out, ep.M, ep.N, ep.ldo, 32, &tmOut, os, 64);
     if (rc) return rc;
     if (ep.residual) {
@@ -904,8 +936,11 @@ int linear_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, int64
     }
     epi_mode |= (abl << 8) & kAblMask;
   }
-  if (cg == 2) return launch<256, 2>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s);
-  return bn == 128 ? launch<128, 1>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s) : launch<256, 1>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s);
+  rc = cg == 2     ? launch<256, 2>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s)
+       : bn == 128 ? launch<128, 1>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s)
+                   : launch<256, 1>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s);
+  if (rc == 0 && ep.stats_out && !fused_stats) rc = launch_partial_row_stats(ep.out, ep.ldo, ep.o_dtype, ep.M, ep.N, ep.stats_out, s);
+  return rc;
 }
 
 }  // namespace anemoi

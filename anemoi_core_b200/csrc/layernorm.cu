@@ -1,6 +1,7 @@
 // layernorm.cu — row LayerNorm (+ optional residual), one warp per (row, group).  HBM-bound: one read of x
 // (+ residual), one write of y; 16-byte vector accesses on the fast path; fp32 statistics (two-pass in registers).
 #include "common.cuh"
+#include "gemm.h"
 
 namespace anemoi {
 
@@ -108,6 +109,39 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const TI* __restrict__ x
     const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
     if (lane == 0) stats[m] = make_float2(mean, rstd);
   }
+}
+
+// Partial row statistics of a stored matrix, the layout a GEMM epilogue writes into EpiParams::stats_out: per row and 64-column block
+// (sum, sum of squares).  Fallback for GEMM paths without the fused version; one warp per row, two columns per lane and block.
+__global__ void __launch_bounds__(256) partial_row_stats_kernel(const void* __restrict__ x, int64_t ldx, int dtype, int64_t M, int64_t N, int parts,
+                                                                float2* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < M; m += warps_total) {
+    for (int b = 0; b < parts; ++b) {
+      float s = 0.f, q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int64_t c = (int64_t)b * kStatsBlock + lane * 2 + j;
+        if (c < N) {
+          const float v = load_as_f32(x, m * ldx + c, dtype);
+          s += v, q += v * v;
+        }
+      }
+      s = warp_sum(s), q = warp_sum(q);
+      if (lane == 0) stats[m * parts + b] = make_float2(s, q);
+    }
+  }
+}
+
+int launch_partial_row_stats(const void* out, int64_t ldo, int o_dtype, int64_t M, int64_t N, float* stats_out, cudaStream_t s) {
+  if (M == 0) return 0;
+  const int parts = (int)((N + kStatsBlock - 1) / kStatsBlock);
+  int64_t blocks = (M + 7) / 8;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  partial_row_stats_kernel<<<(unsigned)blocks, 256, 0, s>>>(out, ldo, o_dtype, M, N, parts, reinterpret_cast<float2*>(stats_out));
+  return launch_status("partial_row_stats_kernel");
 }
 
 // Generic path: any C / alignment.  Lane strides over the row; re-reads hit L1.

@@ -3,6 +3,7 @@ and the per-graph CSR cache.  Everything numerical is a call into ``ops`` (the C
 
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 from typing import Callable
 from typing import Optional
@@ -136,7 +137,41 @@ def fused_linear(pack: WeightPack, x: Tensor, layers: Sequence[nn.Module], dt: t
             raise NotImplementedError(f"{type(l).__name__} is not a Linear-like parameter container (needs a 2-D .weight)")
     w = pack.weight(layers, dt, cols)
     bias = pack.bias(layers) if kw.pop("use_bias", True) else None
-    return ops.linear(as_operand(x, dt, w.shape[1]), w, bias, **kw)
+    return linear_with_stats(as_operand(x, dt, w.shape[1]), w, bias, **kw)
+
+
+def linear_with_stats(a: Tensor, w: Tensor, bias: Optional[Tensor], want_stats: bool = False, **kw) -> Tensor:
+    """``ops.linear``; with ``want_stats`` (and an output a LayerNorm can be folded over) the GEMM epilogue also writes the row statistics
+    of its output and the result is tagged with them (``tag_row_stats``) for the GEMM that will normalise it."""
+    out_dt = kw["out"].dtype if kw.get("out") is not None else (kw.get("out_dtype") or a.dtype)
+    if not (want_stats and FUSED_ROW_STATS and wants_row_stats(w.shape[0], out_dt)):
+        return ops.linear(a, w, bias, **kw)
+    stats = ops.partial_stats_buffer(a.shape[0], w.shape[0], a.device)
+    return tag_row_stats(ops.linear(a, w, bias, stats_out=stats, **kw), stats)
+
+
+# ---- row statistics handed from the GEMM that produces a tensor to the GEMM that normalises it ------------------------------------
+# The producer's epilogue writes per-row partial (sum, sum of squares) next to its output (``ops.linear(stats_out=)``); the pair travels as
+# an attribute of the output tensor object and is honoured only while that tensor is unchanged (same storage, version, shape), so a slice,
+# a gather or an in-place update silently falls back to the ``row_stats`` pass.
+FUSED_ROW_STATS = os.environ.get("ANEMOI_B200_FUSED_ROW_STATS", "1") != "0"  # A/B switch (profiles/README.md); off = separate row_stats pass
+
+
+def tag_row_stats(t: Tensor, stats: Tensor) -> Tensor:
+    t._anemoi_row_stats = (stats, t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()))
+    return t
+
+
+def tagged_row_stats(t: Tensor) -> Optional[Tensor]:
+    tag = getattr(t, "_anemoi_row_stats", None)
+    if tag is None or tag[1:] != (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride())):
+        return None
+    return tag[0]
+
+
+def wants_row_stats(n_out: int, dt: torch.dtype) -> bool:
+    """Can a LayerNorm over ``n_out`` columns of a ``dt`` GEMM output be folded into the next GEMM (same test as ``can_fold_ln``)?"""
+    return dt == torch.bfloat16 and n_out % 8 == 0 and 64 <= n_out <= 2048
 
 
 def can_fold_ln(ln: nn.Module, k: int, dt: torch.dtype) -> bool:
@@ -168,7 +203,10 @@ def ln_linear(pack: WeightPack, x: Tensor, ln: nn.Module, key, sources: Sequence
 
         wf, bias, colsum = pack.get(("ln_fold", key, dt), srcs, build)
         a = as_operand(x, dt, k)
-        return ops.linear(a, wf, bias, ln_stats=ops.row_stats(a, ln.eps), ln_colsum=colsum, **kw)
+        st = tagged_row_stats(a)
+        if st is not None:  # produced by the epilogue of the GEMM that wrote ``a``: no statistics pass at all
+            return linear_with_stats(a, wf, bias, ln_stats=st, ln_dim=k, ln_eps=ln.eps, ln_colsum=colsum, **kw)
+        return linear_with_stats(a, wf, bias, ln_stats=ops.row_stats(a, ln.eps), ln_colsum=colsum, **kw)
 
     def build_plain():
         w32, b32 = build32()
@@ -179,7 +217,7 @@ def ln_linear(pack: WeightPack, x: Tensor, ln: nn.Module, key, sources: Sequence
 
     w, b = pack.get(("ln_plain", key, dt), srcs, build_plain)
     xn = ops.layer_norm(x, pack.f32(ln.weight), pack.f32(ln.bias), ln.eps, out_dtype=dt)
-    return ops.linear(as_operand(xn, dt, w.shape[1]), w, b, **kw)
+    return linear_with_stats(as_operand(xn, dt, w.shape[1]), w, b, **kw)
 
 
 def cat_linear32(layers: Sequence[nn.Module]) -> tuple:

@@ -272,7 +272,7 @@ class GraphTransformerBaseBlock(nn.Module):
         return Fn.pad_edge_attr(edge_attr, ops.ATTN_MAX_EDGE_DIM if self._use_fold(dt) else 0)
 
     def _attend_project(self, x_dst: Tensor, ln_dst: nn.Module, k: Tensor, v: Tensor, dst_layers, edge_attr_p: Tensor, csr: ops.GraphCSR,
-                        x_skip: Tensor, dt: torch.dtype, dst_buf: Optional[Tensor] = None) -> Tensor:  # fmt: skip
+                        x_skip: Tensor, dt: torch.dtype, dst_buf: Optional[Tensor] = None, want_stats: bool = False) -> Tensor:  # fmt: skip
         """dst-side GEMM (q | [k | v |] self | qw) -> attention (+ self) -> projection (+ skip) -> LN -> MLP (+ residual).
 
         ``dst_layers`` = the Linear containers of the dst-side GEMM *after* lin_query (processor: key, value, self — k and v then
@@ -303,8 +303,11 @@ class GraphTransformerBaseBlock(nn.Module):
             w_e = self._pack.get(("w_edge",), [self.lin_edge.weight], lambda: self.lin_edge.weight.detach().float().contiguous())
             att = ops.gt_attention(q, k, v, csr, H, edge_attr=edge_attr_p, w_edge=w_e, b_edge=b_e, add=x_r)
         skip = x_skip if x_skip.dtype in Fn.SUPPORTED else x_skip.float()
-        out = ops.linear(att, self._proj_weight(dt, fold), self._pack.bias([self.projection]), residual=skip)
-        return self.node_dst_mlp.run(out, dt, residual=out, pre_ln=self.layer_norm_mlp_dst)
+        wp = self._proj_weight(dt, fold)
+        # the projection epilogue also produces the row statistics of its output for layer_norm_mlp_dst (folded into the MLP's first GEMM),
+        # and the MLP's last GEMM those of the block output for the next block's layer_norm_attention
+        out = Fn.linear_with_stats(Fn.as_operand(att, dt, wp.shape[1]), wp, self._pack.bias([self.projection]), residual=skip, want_stats=True)
+        return self.node_dst_mlp.run(out, dt, residual=out, pre_ln=self.layer_norm_mlp_dst, want_stats=want_stats)
 
 
 class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
@@ -339,14 +342,14 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
         world = group_size(model_comm_group)
         if world == 1:
             csr = Fn.csr_for(edge_index, x.shape[0], x.shape[0])
-            return self._attend_project(x, ln, None, None, dst_layers, ea, csr, x, dt), edge_attr
+            return self._attend_project(x, ln, None, None, dst_layers, ea, csr, x, dt, want_stats=True), edge_attr
         # edges strategy (block.py:1148-1183): each rank owns a dst range and needs the k | v rows of every source node
         buf = self._dst_gemm(x, ln, [self.lin_query] + dst_layers, dt)
         kv_full = gather_rows(buf[:, A : 3 * A], shard_info.nodes, model_comm_group)
         csr = Fn.csr_for(edge_index, kv_full.shape[0], x.shape[0])
         if self.qk_norm:
             raise NotImplementedError("qk_norm with a sharded processor")
-        out = self._attend_project(x, ln, kv_full[:, :A], kv_full[:, A:], dst_layers, ea, csr, x, dt, dst_buf=buf)
+        out = self._attend_project(x, ln, kv_full[:, :A], kv_full[:, A:], dst_layers, ea, csr, x, dt, dst_buf=buf, want_stats=True)
         return out, edge_attr
 
 

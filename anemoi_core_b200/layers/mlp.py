@@ -64,6 +64,7 @@ class MLP(nn.Module):
         first_cols: Optional[slice] = None,
         out: Optional[Tensor] = None,
         pre_ln: Optional[nn.Module] = None,
+        want_stats: bool = False,
     ) -> Tensor:
         """Fused forward in compute dtype ``dt``.  ``residual`` is added after the last op (LayerNorm if present).
         ``first_gathers`` / ``first_cols`` feed the split first layer of GraphConv's edge MLP (gather-add epilogue)."""
@@ -78,6 +79,7 @@ class MLP(nn.Module):
                 kw["gather1"], kw["gather2"] = first_gathers
             if last and self.layer_norm is None:
                 kw["residual"], kw["out"] = residual, out
+                kw["want_stats"] = want_stats  # the caller's next op is a LayerNorm folded into a GEMM: hand it the row statistics
             if first and pre_ln is not None:  # LayerNorm(x) feeding the first Linear: folded into that GEMM on the bf16 path
                 x = Fn.ln_linear(self._pack, x, pre_ln, ("pre_ln", id(lin)), Fn.linear_sources([lin]), lambda lin=lin: Fn.cat_linear32([lin]), dt,
                                  gelu=act, **kw)

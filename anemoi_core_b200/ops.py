@@ -208,8 +208,14 @@ def linear(
     out_dtype: Optional[torch.dtype] = None,
     ln_stats: Optional[Tensor] = None,
     ln_colsum: Optional[Tensor] = None,
+    ln_dim: int = 0,
+    ln_eps: float = 0.0,
+    stats_out: Optional[Tensor] = None,
 ) -> Tensor:
     """out = [gelu](a @ weight.T + bias + g1[idx1] + g2[idx2]) + residual.
+
+    ``stats_out`` (fp32 [M, ceil(N/64), 2], see ``partial_stats_buffer``) receives per-block (sum, sum of squares) of the stored output
+    rows; a later ``linear`` consumes it as ``ln_stats`` of the same 3-D shape together with ``ln_dim`` (normalised width) and ``ln_eps``.
 
     With ``ln_stats`` [M, 2] (``row_stats(a)``) and ``ln_colsum`` [N] the LayerNorm of ``a`` is folded in:
     out = [gelu](rstd * (a @ weight.T - mean * colsum) + bias) for ``weight`` already scaled by the LayerNorm gamma.
@@ -259,12 +265,23 @@ def linear(
     with _Timed("linear_tcgen05" if tc else "linear_ffma", 2.0 * M * N * K, _nbytes(a, weight, residual, out) + gbytes):
         if (ln_stats is None) != (ln_colsum is None):
             raise ValueError("linear: ln_stats and ln_colsum go together")
-        if ln_stats is not None and (ln_stats.shape != (M, 2) or ln_colsum.numel() != N or ln_stats.dtype != torch.float32):
-            raise ValueError("linear: ln_stats must be float32 [M, 2] and ln_colsum float32 [N]")
+        ln_parts = 0
+        if ln_stats is not None:
+            if ln_stats.dtype != torch.float32 or not ln_stats.is_contiguous() or ln_colsum.numel() != N:
+                raise ValueError("linear: ln_stats must be contiguous float32 and ln_colsum float32 [N]")
+            if ln_stats.dim() == 3:  # partial (sum, sum of squares) per 64-column block from the producing GEMM
+                ln_parts = ln_stats.shape[1]
+                if ln_stats.shape != (M, ln_parts, 2) or ln_dim <= 0 or ln_parts != (ln_dim + 63) // 64:
+                    raise ValueError("linear: partial ln_stats must be [M, ceil(ln_dim/64), 2] with ln_dim > 0")
+            elif ln_stats.shape != (M, 2):
+                raise ValueError("linear: ln_stats must be float32 [M, 2]")
+        if stats_out is not None and (stats_out.dtype != torch.float32 or not stats_out.is_contiguous() or stats_out.shape != (M, (N + 63) // 64, 2)):
+            raise ValueError("linear: stats_out must be contiguous float32 [M, ceil(N/64), 2]")
+        _need_cuda(ln_stats, ln_colsum, stats_out)
         rc = _lib.load().anemoi_b200_linear(
             _ptr(a), lda, _ptr(weight), ldw, dtype_code(a.dtype), _ptr(_f32(bias)), _ptr(g1), _ptr(i1), _ptr(g2), _ptr(i2), ldg, _ptr(residual),
-            ldr, rdt, _ptr(out), ldo, dtype_code(out.dtype), M, N, K, EPI_GELU if gelu else 0, _ptr(_f32(ln_stats)), _ptr(_f32(ln_colsum)),
-            _stream())  # fmt: skip
+            ldr, rdt, _ptr(out), ldo, dtype_code(out.dtype), M, N, K, EPI_GELU if gelu else 0, _ptr(ln_stats), _ptr(_f32(ln_colsum)),
+            ln_parts, int(ln_dim), float(ln_eps), _ptr(stats_out), _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_linear")
     return out
 
@@ -351,6 +368,10 @@ def gt_attention(
     es = q.element_size()
     abytes = es * C * (2.0 * n_dst + 2.0 * n_src + (n_dst if add is not None else 0)) + csr.n_edges * (4.0 + 4.0 * lde + (es * C if e_proj is not None else 0)) + 4.0 * n_dst
     aflops = csr.n_edges * (4.0 * C + 4.0 * d_e * heads) + n_dst * 4.0 * d_e * C
+    if csr.n_edges == 0 and abar is not None:
+        # an empty edge tensor has a null data pointer, so the library sees "no edge term" and leaves abar untouched; with no edges
+        # abar = sum_e alpha_e a_e is exactly zero (tests/test_gpu_parity.py::test_edge_cases_empty_and_isolated)
+        abar.zero_()
     with _Timed("gt_attention", aflops, abytes):
         rc = _lib.load().anemoi_b200_gt_attention_fwd(
             _ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(e_proj), lde_proj, _ptr(edge_attr), lde, d_e, _ptr(w_edge), ldw_e, _ptr(_f32(b_edge)),
@@ -415,6 +436,11 @@ def add(a: Tensor, b: Tensor, out_dtype: Optional[torch.dtype] = None) -> Tensor
         rc = _lib.load().anemoi_b200_add(_ptr(a), lda, dtype_code(a.dtype), _ptr(b), ldb, dtype_code(b.dtype), _ptr(out), C, dtype_code(out.dtype), M, C, _stream())
     _lib.check(rc, "anemoi_b200_add")
     return out
+
+
+def partial_stats_buffer(out_rows: int, out_cols: int, device) -> Tensor:
+    """Buffer for ``linear(..., stats_out=)``: [M, ceil(N/64), 2] fp32."""
+    return torch.empty((out_rows, (out_cols + 63) // 64, 2), dtype=torch.float32, device=device)
 
 
 def row_stats(x: Tensor, eps: float = 1e-5) -> Tensor:

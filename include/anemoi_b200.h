@@ -80,11 +80,16 @@ ANEMOI_API int anemoi_b200_layer_norm(const void* x, int64_t ldx, int x_dtype, c
  *     LN(x) W^T + b = rstd_m (x W'^T - mean_m colsum_n) + (b + W beta),  colsum_n = sum_k W'[n,k]:  the caller passes the RAW x as A,
  *     W' as W, (b + W beta) as bias, per-row (mean, rstd) from anemoi_b200_row_stats as ln_stats [M,2] and colsum [N]; the separate
  *     LayerNorm pass (one read + one write of the activations) disappears.
+ *   stats_out (may be NULL): fp32 [M, ceil(N/64), 2]; receives per row and 64-column block (sum, sum of squares) of the output AS STORED.
+ *     The GEMM that consumes `out` through a folded LayerNorm then passes this buffer as ln_stats with ln_parts = ceil(K/64),
+ *     ln_dim = K (normalised width), ln_eps; (mean, rstd) are formed in its epilogue and the anemoi_b200_row_stats pass disappears too.
+ *     ln_parts == 0: ln_stats is the [M,2] (mean, rstd) form.  The bf16 tcgen05 epilogue writes stats_out itself (plain / residual form);
+ *     other paths run one extra pass over `out`.
  */
 ANEMOI_API int anemoi_b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, int a_dtype, const float* bias, const float* g1,
                        const int32_t* idx1, const float* g2, const int32_t* idx2, int64_t ldg, const void* residual, int64_t ldr,
                        int r_dtype, void* out, int64_t ldo, int o_dtype, int64_t M, int64_t N, int64_t K, int flags, const float* ln_stats,
-                       const float* ln_colsum, void* stream);
+                       const float* ln_colsum, int64_t ln_parts, int64_t ln_dim, float ln_eps, float* stats_out, void* stream);
 
 /* per-row LayerNorm statistics (mean, 1/sqrt(var + eps)), two-pass in registers: stats[m] = (mean, rstd), x [M, ldx] of x_dtype */
 ANEMOI_API int anemoi_b200_row_stats(const void* x, int64_t ldx, int x_dtype, float* stats, int64_t M, int64_t C, float eps, void* stream);

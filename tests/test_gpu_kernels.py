@@ -184,6 +184,68 @@ def test_linear_with_folded_layer_norm(ops, M, N, K, gelu):
     assert err <= 2**-6 * ref.abs().max().item() + 1e-3, f"max err {err}"
 
 
+def _block_stats(y: torch.Tensor) -> torch.Tensor:
+    """[M, ceil(N/64), 2] (sum, sum of squares) of the stored values, fp64 reference."""
+    M, N = y.shape
+    P = (N + 63) // 64
+    yp = torch.zeros(M, P * 64, dtype=torch.float64, device=y.device)
+    yp[:, :N] = y.double()
+    yp = yp.view(M, P, 64)
+    return torch.stack([yp.sum(-1), (yp * yp).sum(-1)], -1)
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(40962, 512, 704, "res"), (40962, 512, 2048, "res"), (1000, 512, 512, "plain"), (333, 200, 128, "res"),
+                                       (5000, 1024, 256, "res"), (2000, 512, 512, "gelu"), (700, 512, 96, "f32")])  # fmt: skip
+def test_linear_row_stats_epilogue(ops, M, N, K, epi):
+    """stats_out of the producing GEMM == block sums of its STORED output (fused in the tcgen05 epilogue for plain / residual bf16; the
+    gelu and fp32 cases take the separate pass), and a consumer GEMM fed those partials == the same GEMM fed ops.row_stats."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    dt = torch.float32 if epi == "f32" else torch.bfloat16
+    a = torch.randn(M, K, generator=g, device="cuda").to(dt)
+    w = (torch.randn(N, K, generator=g, device="cuda") / math.sqrt(K)).to(dt)
+    bias = torch.randn(N, generator=g, device="cuda")
+    res = (torch.randn(M, N, generator=g, device="cuda") * 2 + 0.5).to(dt) if epi == "res" else None
+    stats = ops.partial_stats_buffer(M, N, a.device)
+    stats.fill_(float("nan"))
+    y = ops.linear(a, w, bias, gelu=epi == "gelu", residual=res, stats_out=stats)
+    ref = _block_stats(y)
+    assert torch.isfinite(stats).all()
+    scale = ref[..., 1].sqrt().clamp_min(1.0) * 8  # |sum| <= 8 * sqrt(sumsq) over 64 values
+    assert ((stats[..., 0].double() - ref[..., 0]).abs() <= 1e-5 * scale).all()
+    assert ((stats[..., 1].double() - ref[..., 1]).abs() <= 1e-5 * ref[..., 1].clamp_min(1.0)).all()
+    if dt != torch.bfloat16 or N % 8 or N < 64:
+        return
+    # consumer: LayerNorm over y's N columns folded into the next GEMM, statistics from the partials vs from the row_stats pass
+    N2 = 256
+    w2 = (torch.randn(N2, N, generator=g, device="cuda") / math.sqrt(N)).to(dt)
+    b2 = torch.randn(N2, generator=g, device="cuda")
+    colsum = w2.float().sum(1).contiguous()
+    y_partial = ops.linear(y, w2, b2, ln_stats=stats, ln_dim=N, ln_eps=1e-5, ln_colsum=colsum)
+    y_rowstats = ops.linear(y, w2, b2, ln_stats=ops.row_stats(y, 1e-5), ln_colsum=colsum)
+    ref2 = torch.nn.functional.layer_norm(y.float(), (N,), None, None, 1e-5) @ w2.float().t() + b2
+    tol = 2**-6 * ref2.abs().max().item() + 1e-3
+    assert (y_partial.float() - ref2).abs().max().item() <= tol
+    assert (y_partial.float() - y_rowstats.float()).abs().max().item() <= 2**-7 * ref2.abs().max().item()
+
+
+def test_linear_row_stats_constant_rows(ops):
+    """A constant output row has zero variance: the E[x^2] - mean^2 form must clamp at 0 and the folded LayerNorm of it must give the bias."""
+    M, N, K = 512, 512, 128
+    a = torch.zeros(M, K, dtype=torch.bfloat16, device="cuda")
+    w = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+    res = torch.full((M, N), 1.0078125, dtype=torch.bfloat16, device="cuda")  # exactly representable; rows 0..255
+    res[256:] = torch.randn(256, N, device="cuda").to(torch.bfloat16)
+    stats = ops.partial_stats_buffer(M, N, a.device)
+    y = ops.linear(a, w, None, residual=res, stats_out=stats)
+    assert torch.equal(y, res)
+    w2 = torch.randn(64, N, device="cuda").to(torch.bfloat16)
+    b2 = torch.randn(64, device="cuda")
+    out = ops.linear(y, w2, b2, ln_stats=stats, ln_dim=N, ln_eps=1e-5, ln_colsum=w2.float().sum(1).contiguous())
+    assert torch.isfinite(out).all()
+    # LN(constant) = 0 -> out = bias, up to the fp32 accumulation error of sum_k x w'_k against mean * colsum times rstd = 316
+    assert (out[:256].float() - b2).abs().max().item() <= 0.05
+
+
 def test_linear_strided_views(ops):
     """Column slices of wider buffers as A, residual and out (how the blocks pass q|k|v|self and x|aggregate)."""
     g = torch.Generator().manual_seed(5)
@@ -330,6 +392,30 @@ def test_cast_pad(ops):
     ref = torch.zeros(37, 16)
     ref[:, :13] = x[idx.long()]
     assert torch.equal(y.float().cpu(), ref.to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("M,K,Kpad", [(40320, 212, 216), (1000, 12, 64), (333, 64, 64), (7, 4, 8), (50, 13, 16)])
+@pytest.mark.parametrize("dti,dto", [(torch.float32, torch.bfloat16), (torch.float32, torch.float32), (torch.bfloat16, torch.float32),
+                                     (torch.bfloat16, torch.bfloat16)])  # fmt: skip
+def test_cast_pad_vectorised_and_scalar_paths(ops, M, K, Kpad, dti, dto):
+    """The 4-columns-per-thread path (K, Kpad, strides multiples of 4) and the scalar path give the same exact copy / rounding."""
+    x = torch.randn(M, K, generator=torch.Generator().manual_seed(M + K)).to(dti)
+    y = ops.cast_pad(x.cuda(), dto, Kpad)
+    ref = torch.zeros(M, Kpad, dtype=dto)
+    ref[:, :K] = x.to(dto)
+    assert y.shape == (M, Kpad) and torch.equal(y.cpu(), ref)
+
+
+@pytest.mark.parametrize("M,C", [(40962, 512), (100, 8), (33, 20)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+def test_add(ops, M, C, dt):
+    g = torch.Generator().manual_seed(M)
+    a, b = torch.randn(M, C, generator=g).to(dt), torch.randn(M, C, generator=g).to(dt)
+    y = ops.add(a.cuda(), b.cuda())
+    assert torch.equal(y.cpu(), (a.float() + b.float()).to(dt))
+    big = torch.randn(M, 2 * C + 8, generator=g).to(dt).cuda()  # strided operands (column slices)
+    y2 = ops.add(big[:, 8 : 8 + C], b.cuda())
+    assert torch.equal(y2.cpu(), (big[:, 8 : 8 + C].float().cpu() + b.float()).to(dt))
 
 
 def test_cpu_tensor_is_an_error(ops):

@@ -12,32 +12,12 @@
 //     sum_e alpha_e (v + W a_e + b) = sum_e alpha_e v + W (sum_e alpha_e a_e) + b
 // i.e. an edge_dim-long dot product per edge and two [Ch x edge_dim] products per dst node; the [E, H*Ch] stream
 // (the largest tensor of the layer) never exists.  Edge attributes stay fp32.
+#include <cstdlib>
+
+#include "attention.h"
 #include "common.cuh"
 
 namespace anemoi {
-
-constexpr int kMaxEdgeDim = 16;
-
-struct AttnParams {
-  const void *q, *k, *v, *e, *add;
-  void* out;
-  int64_t ldq, ldk, ldv, lde_proj, ldadd, ldo;
-  const float* edge_attr;  // [E, lde] fp32
-  int64_t lde;
-  int edge_dim;
-  const float* w_edge;  // [H*Ch, ldw_e] fp32 (generic kernel only)
-  int64_t ldw_e;
-  const float* b_edge;  // [H*Ch] or null
-  const void* qw;       // [n_dst, ldqw]: per-head W_e^T q (slab kernel, MODE 2)
-  void* abar;           // [n_dst, ldabar]: per-head sum_e alpha_e a_e (slab kernel, MODE 2)
-  int64_t ldqw, ldabar;
-  int dp;               // per-head stride inside qw / abar rows
-  const int32_t* src;
-  const int32_t* colptr;
-  int64_t n_dst;
-  int heads, ch;
-  float scale;
-};
 
 // ---- slab kernel ---------------------------------------------------------------------------------------------
 // Work item = (range of kNodesPerRange consecutive dst nodes, channel slab).  A slab is NCH x 512 bytes of a node row:
@@ -318,14 +298,6 @@ __global__ void __launch_bounds__(128, ATTN_MINBLOCKS) gt_attention_slab_kernel(
 #endif
 constexpr int kSlots = ATTN_SLOTS;
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 __device__ __forceinline__ uint4 lds16(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -335,28 +307,6 @@ __device__ __forceinline__ float lds32f(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
-}
-
-// first n in [0, n_dst] with colptr[n] >= x (colptr non-decreasing, colptr[n_dst] = E); warp-wide 32-ary search
-__device__ __forceinline__ int colptr_lower_bound(const int32_t* __restrict__ colptr, int n_dst, int x, int lane) {
-  int lo = 0, hi = n_dst;  // answer in [lo, hi]
-  while (hi - lo > 0) {
-    const int span = hi - lo;
-    const int step = (span + 31) / 32;
-    const int pos = min(lo + lane * step, hi);
-    const bool ge = __ldg(colptr + pos) >= x;
-    const unsigned m = __ballot_sync(0xffffffffu, ge);
-    if (m == 0) {  // all probed positions < x: answer beyond the last probe
-      lo = min(lo + 31 * step, hi) + 1;
-      if (lo > hi) return hi;  // cannot happen when colptr[hi] >= x
-    } else {
-      const int f = __ffs(m) - 1;  // first probe with colptr >= x
-      hi = min(lo + f * step, hi);
-      lo = f == 0 ? hi : min(lo + (f - 1) * step, hi) + 1;
-      if (lo > hi) lo = hi;
-    }
-  }
-  return lo;
 }
 
 #ifndef ATTN_PIPE_BATCH
@@ -403,6 +353,10 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
   const int64_t lane_off = ((int64_t)slab * SLAB + (int64_t)lane_eff * EPC) * (int64_t)sizeof(T);
   const int E0 = __ldg(p.colptr + n_lo), E1 = __ldg(p.colptr + n_hi);
 
+  const char* const k_lane = kp + lane_off;
+  const char* const v_lane = vp + lane_off;
+  const char* const a_lane = reinterpret_cast<const char*>(p.edge_attr) + (lane & 3) * 16;
+  const uint32_t ldk_b32 = (uint32_t)ldk_b, ldv_b32 = (uint32_t)ldv_b, lde_b32 = (uint32_t)p.lde * 4u;  // < 2^31 (checked by the launcher)
   // ---- producer state: src ids streamed in blocks of 32, one cp.async group per edge, running ring position ----
   int pe = E0;  // next edge to issue
   int ppos = 0;  // its ring slot
@@ -418,15 +372,16 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
       }
       const int sid = __shfl_sync(0xffffffffu, psrc, pe - pblk);
       const uint32_t slot = ring + (uint32_t)(ppos * kSlotBytes) + lane * 16;
-      const char* kr = kp + (int64_t)sid * ldk_b + lane_off;
-      const char* vr = vp + (int64_t)sid * ldv_b + lane_off;
+      // 32-bit row pitch x 32-bit id on a per-lane base pointer: one IMAD.WIDE.U32 per gather address (the 64-bit form cost ~10)
+      const char* kr = k_lane + (uint64_t)(uint32_t)sid * ldk_b32;
+      const char* vr = v_lane + (uint64_t)(uint32_t)sid * ldv_b32;
 #pragma unroll
       for (int j = 0; j < NCH; ++j) {
         cp_async16(slot + j * 512, kr + j * 512);
         cp_async16(slot + kKV + j * 512, vr + j * 512);
       }
       if constexpr (MODE == 2) {
-        if (lane < 4) cp_async16(slot + 2 * kKV, p.edge_attr + (int64_t)pe * p.lde + lane * 4);
+        if (lane < 4) cp_async16(slot + 2 * kKV, a_lane + (uint64_t)(uint32_t)pe * lde_b32);
       } else {
         if (ep) {
 #pragma unroll
@@ -697,6 +652,8 @@ template <typename T, int NCH, int LPH, int MODE>
 static int launch_pipe_mode(const AttnParams& p, int n_slabs, int active_lanes, cudaStream_t s) {
   constexpr int kSlotBytes = 2 * NCH * 512 + (MODE == 2 ? 64 : NCH * 512);
   constexpr int smem = 4 * kSlots * kSlotBytes;  // 4 warps per CTA
+  const int64_t max_pitch = (int64_t)1 << 31;  // gather addresses are formed from 32-bit byte pitches
+  if (p.ldk * (int64_t)sizeof(T) >= max_pitch || p.ldv * (int64_t)sizeof(T) >= max_pitch || p.lde * 4 >= max_pitch) return 1;
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute(gt_attention_pipe_kernel<T, NCH, LPH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -820,6 +777,20 @@ extern "C" int anemoi_b200_gt_attention_fwd(const void* q, int64_t ldq, const vo
     slab_ok = slab_ok && folded && edge_dim <= kMaxEdgeDim && lde >= kMaxEdgeDim && (!b_edge || (reinterpret_cast<uintptr_t>(b_edge) & 15) == 0);
   }
   cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == ANEMOI_BF16 && folded && slab_ok && (ch == 32 || ch == 64)) {
+    // mma.sync formulation (attention_mma.cu), opt-in with ANEMOI_B200_ATTN_MMA=1: numerically equivalent and 3x fewer arithmetic
+    // instructions, but measured SLOWER than the FP32-pipe kernel (235 vs 135 us at cfg2; profiles/README.md): per-edge issue and
+    // per-node bookkeeping dominate both kernels, and at 200+ registers only 8 warps per SM hide the ldmatrix -> HMMA chains.
+    static int use_mma = -1;
+    if (use_mma < 0) {
+      const char* ev = getenv("ANEMOI_B200_ATTN_MMA");
+      use_mma = (ev && ev[0] == '1') ? 1 : 0;
+    }
+    if (use_mma) {
+      const int rc_mma = launch_gt_attention_mma(p, s);
+      if (rc_mma <= 0) return rc_mma;
+    }
+  }
   const int rc = dtype == ANEMOI_BF16 ? dispatch<__nv_bfloat16>(p, mode, slab_ok, folded, s) : dispatch<float>(p, mode, slab_ok, folded, s);
   return rc;
 }

@@ -32,6 +32,36 @@ def shard_rows(x: Tensor, sizes: Optional[list[int]], group: Optional[dist.Proce
     return x[start : start + sizes[r]]
 
 
+def _exchange(send: Tensor, in_splits: list[int], out_splits: list[int], group, out: Optional[Tensor] = None) -> Tensor:
+    """Variable-size all-to-all of row blocks: rank r receives ``out_splits[s]`` rows from every rank s (``in_splits`` = rows sent to each)."""
+    if out is None:
+        out = send.new_empty((sum(out_splits),) + tuple(send.shape[1:]))
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(out, send, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
+        return out
+    # Gloo has no all_to_all: pairwise isend / irecv (host-logic tests on CPU)
+    world, me = group_size(group), group_rank(group)
+    reqs, so, ro = [], 0, 0
+    send_parts, recv_parts = [], []
+    for r in range(world):
+        send_parts.append(send[so : so + in_splits[r]])
+        recv_parts.append(out[ro : ro + out_splits[r]])
+        so += in_splits[r]
+        ro += out_splits[r]
+    recv_parts[me].copy_(send_parts[me])
+    for r in range(world):
+        if r == me:
+            continue
+        peer = dist.get_global_rank(group, r) if group is not None else r
+        if in_splits[r]:
+            reqs.append(dist.isend(send_parts[r].contiguous(), peer, group=group))
+        if out_splits[r]:
+            reqs.append(dist.irecv(recv_parts[r], peer, group=group))
+    for q in reqs:
+        q.wait()
+    return out
+
+
 class SegmentedCapture:
     """CUDA-graph capture of a sharded forward as a chain [graph_0, all-gather, graph_1, all-gather, ...]: the compute between two
     collectives is captured (one graph launch instead of dozens of kernel launches), the NCCL all-gathers run eagerly between the
@@ -60,10 +90,21 @@ class SegmentedCapture:
         self.begin()
         return out
 
+    def exchange(self, send: Tensor, in_splits: list[int], out_splits: list[int], group, out: Tensor) -> Tensor:
+        """Halo all-to-all between two graph segments (``send`` and ``out`` are static buffers of the capture pool / the caller)."""
+        self.end()
+        _exchange(send, in_splits, out_splits, group, out=out)
+        self.items.append(("exchange", out, send, list(in_splits), list(out_splits), group))
+        self.begin()
+        return out
+
     def replay(self) -> None:
         for it in self.items:
             if it[0] == "graph":
                 it[1].replay()
+            elif it[0] == "exchange":
+                _, out, send, in_splits, out_splits, group = it
+                _exchange(send, in_splits, out_splits, group, out=out)
             else:
                 _, out, x, sizes, group = it
                 _all_gather_rows(x, sizes, group, out=out)

@@ -7,6 +7,7 @@ dst-range-sharded across a model communication group (``distributed/graph.py``).
 
 from __future__ import annotations
 
+import os
 from typing import Optional
 from typing import Union
 
@@ -17,6 +18,7 @@ from torch import nn
 from .. import ops
 from ..distributed.graph import gather_rows
 from ..distributed.graph import group_size
+from ..distributed.halo import halo_plan_for
 from ..distributed.shapes import BipartiteGraphShardInfo
 from ..distributed.shapes import GraphShardInfo
 from . import _functional as Fn
@@ -26,6 +28,7 @@ from .utils import compute_mlp_hidden_dim
 from .utils import load_layer_kernels
 
 PairTensor = tuple[Tensor, Tensor]
+HALO_EXCHANGE = os.environ.get("ANEMOI_B200_HALO", "1") != "0"  # sharded GraphTransformer processor: halo all-to-all (default) vs all-gather
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -343,13 +346,26 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
         if world == 1:
             csr = Fn.csr_for(edge_index, x.shape[0], x.shape[0])
             return self._attend_project(x, ln, None, None, dst_layers, ea, csr, x, dt, want_stats=True), edge_attr
-        # edges strategy (block.py:1148-1183): each rank owns a dst range and needs the k | v rows of every source node
-        buf = self._dst_gemm(x, ln, [self.lin_query] + dst_layers, dt)
-        kv_full = gather_rows(buf[:, A : 3 * A], shard_info.nodes, model_comm_group)
-        csr = Fn.csr_for(edge_index, kv_full.shape[0], x.shape[0])
+        # edges strategy (block.py:1120-1183): each rank owns a dst range and needs the k | v rows of the source nodes its edges name
         if self.qk_norm:
             raise NotImplementedError("qk_norm with a sharded processor")
-        out = self._attend_project(x, ln, kv_full[:, :A], kv_full[:, A:], dst_layers, ea, csr, x, dt, dst_buf=buf, want_stats=True)
+        if not HALO_EXCHANGE:  # A/B switch: all-gather every k | v row (round-1 first version)
+            buf = self._dst_gemm(x, ln, [self.lin_query] + dst_layers, dt)
+            kv_full = gather_rows(buf[:, A : 3 * A], shard_info.nodes, model_comm_group)
+            csr = Fn.csr_for(edge_index, kv_full.shape[0], x.shape[0])
+            out = self._attend_project(x, ln, kv_full[:, :A], kv_full[:, A:], dst_layers, ea, csr, x, dt, dst_buf=buf, want_stats=True)
+            return out, edge_attr
+        # halo exchange (distributed/halo.py): the k | v GEMM writes this rank's rows into the head of a compact table, one gather kernel
+        # packs the rows the other ranks asked for, one all-to-all drops the rows we need into the tail; the edge list was relabelled
+        # onto the table once.  q | self | qw come from a second GEMM on the same (tagged) LayerNorm statistics.
+        plan = halo_plan_for(edge_index, shard_info.nodes, model_comm_group)
+        table = torch.empty((plan.n_table, 2 * A), dtype=dt, device=x.device)
+        kv_layers = [self.lin_key, self.lin_value]
+        Fn.ln_linear(self._pack, x, ln, ("kv", id(self.lin_key), id(self.lin_value)), Fn.linear_sources(kv_layers),
+                     lambda: Fn.cat_linear32(kv_layers), dt, out=table[: plan.n_local])  # fmt: skip
+        plan.exchange(table)
+        csr = Fn.csr_for(plan.edge_index, plan.n_table, x.shape[0])
+        out = self._attend_project(x, ln, table[:, :A], table[:, A:], [self.lin_self], ea, csr, x, dt, want_stats=True)
         return out, edge_attr
 
 

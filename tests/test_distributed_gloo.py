@@ -91,3 +91,42 @@ def test_edge_sharding_world2():
 
 def test_edge_sharding_world3_uneven():
     run_distributed("check_edge_sharding", 3)
+
+
+def check_halo_exchange(rank, world):
+    """Halo plan + exchange (distributed/halo.py; reference block.py:1120-1183): after the exchange every local edge finds, at its relabelled
+    source position of the compact table, exactly the row its GLOBAL source id names; only referenced remote rows travel."""
+    from anemoi_core_b200.distributed.halo import halo_plan_for
+    from anemoi_core_b200.layers.processor import _shard_edges_by_dst
+
+    for n, e, seed in ((37, 211, 3), (64, 40, 4), (50, 0, 5)):  # dense, sparse (small halos, some empty), no edges at all
+        ei, ea = _graph(n, e, seed)
+        sizes = get_balanced_partition_sizes(n, world)
+        start = sum(sizes[:rank])
+        _, ei_l, _ = _shard_edges_by_dst(ea, ei, n, n, dist.group.WORLD, relabel_dst=True)  # global src, local dst
+        plan = halo_plan_for(ei_l, sizes, dist.group.WORLD)
+        assert plan is halo_plan_for(ei_l, sizes, dist.group.WORLD)  # cached on the tensor
+        full = torch.arange(n * 4, dtype=torch.float32).view(n, 4) * 0.5 + 1.0
+        table = torch.full((plan.n_table, 4), float("nan"))
+        table[: plan.n_local] = full[start : start + sizes[rank]]
+        plan.exchange(table)
+        assert plan.n_local == sizes[rank] and not torch.isnan(table).any()
+        assert torch.equal(table[plan.edge_index[0]], full[ei_l[0]])  # every edge reads the right source row
+        assert torch.equal(plan.edge_index[1], ei_l[1])
+        # the halo is exactly the set of referenced remote sources, grouped by owner in ascending id order
+        remote = torch.unique(ei_l[0][(ei_l[0] < start) | (ei_l[0] >= start + sizes[rank])])
+        assert torch.equal(plan.halo_ids, remote) and plan.n_halo == remote.numel() and plan.recv_splits[rank] == 0
+        assert torch.equal(table[plan.n_local :], full[plan.halo_ids])
+        # what we send is what the others receive
+        t = torch.tensor(plan.send_splits)
+        others = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(others, torch.tensor(plan.recv_splits))
+        assert [int(others[r][rank]) for r in range(world)] == plan.send_splits
+
+
+def test_halo_exchange_world2():
+    run_distributed("check_halo_exchange", 2)
+
+
+def test_halo_exchange_world3_uneven():
+    run_distributed("check_halo_exchange", 3)

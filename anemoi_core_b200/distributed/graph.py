@@ -32,13 +32,15 @@ def shard_rows(x: Tensor, sizes: Optional[list[int]], group: Optional[dist.Proce
     return x[start : start + sizes[r]]
 
 
-def _exchange(send: Tensor, in_splits: list[int], out_splits: list[int], group, out: Optional[Tensor] = None) -> Tensor:
-    """Variable-size all-to-all of row blocks: rank r receives ``out_splits[s]`` rows from every rank s (``in_splits`` = rows sent to each)."""
+def _exchange(send: Tensor, in_splits: list[int], out_splits: list[int], group, out: Optional[Tensor] = None, async_op: bool = False):
+    """Variable-size all-to-all of row blocks: rank r receives ``out_splits[s]`` rows from every rank s (``in_splits`` = rows sent to each).
+    Returns ``out``; with ``async_op`` (NCCL) the work handle instead - the collective runs on NCCL's stream and the caller's stream only
+    joins it at ``work.wait()``, so kernels enqueued in between overlap the transfer."""
     if out is None:
         out = send.new_empty((sum(out_splits),) + tuple(send.shape[1:]))
     if dist.get_backend(group) == "nccl":
-        dist.all_to_all_single(out, send, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
-        return out
+        work = dist.all_to_all_single(out, send, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group, async_op=async_op)
+        return work if async_op else out
     # Gloo has no all_to_all: pairwise isend / irecv (host-logic tests on CPU)
     world, me = group_size(group), group_rank(group)
     reqs, so, ro = [], 0, 0
@@ -59,7 +61,7 @@ def _exchange(send: Tensor, in_splits: list[int], out_splits: list[int], group, 
             reqs.append(dist.irecv(recv_parts[r], peer, group=group))
     for q in reqs:
         q.wait()
-    return out
+    return None if async_op else out
 
 
 class SegmentedCapture:
@@ -73,6 +75,7 @@ class SegmentedCapture:
         self.items: list = []
         self.pool = torch.cuda.graph_pool_handle()
         self._g: Optional[torch.cuda.CUDAGraph] = None
+        self._work = None
 
     def begin(self) -> None:
         self._g = torch.cuda.CUDAGraph()
@@ -98,10 +101,33 @@ class SegmentedCapture:
         self.begin()
         return out
 
+    def exchange_start(self, send: Tensor, in_splits: list[int], out_splits: list[int], group, out: Tensor) -> None:
+        """Split form of ``exchange``: the all-to-all is issued here and joined at ``exchange_finish``; the graph segment captured in
+        between (the q | self GEMM of the block) runs while the rows travel."""
+        self.end()
+        self._work = _exchange(send, in_splits, out_splits, group, out=out, async_op=True)
+        self.items.append(("xstart", out, send, list(in_splits), list(out_splits), group))
+        self.begin()
+
+    def exchange_finish(self) -> None:
+        self.end()
+        if self._work is not None:
+            self._work.wait()
+        self.items.append(("xwait",))
+        self.begin()
+
     def replay(self) -> None:
+        work = None
         for it in self.items:
             if it[0] == "graph":
                 it[1].replay()
+            elif it[0] == "xstart":
+                _, out, send, in_splits, out_splits, group = it
+                work = _exchange(send, in_splits, out_splits, group, out=out, async_op=True)
+            elif it[0] == "xwait":
+                if work is not None:
+                    work.wait()
+                    work = None
             elif it[0] == "exchange":
                 _, out, send, in_splits, out_splits, group = it
                 _exchange(send, in_splits, out_splits, group, out=out)

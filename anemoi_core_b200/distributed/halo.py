@@ -39,6 +39,7 @@ class HaloPlan:
     edge_index: Tensor  # int64 [2, E_local]: src relabelled onto the compact table, dst local
     halo_ids: Tensor  # int64 [n_halo]: global id of every halo row (table row n_local + i)
     group: object
+    _pending: object = None
 
     @property
     def n_table(self) -> int:
@@ -60,6 +61,30 @@ class HaloPlan:
         else:
             _exchange(send, self.send_splits, self.recv_splits, self.group, out=halo)
         return table
+
+    def exchange_start(self, table: Tensor) -> None:
+        """Pack and issue the all-to-all; returns at once.  Work enqueued before ``exchange_finish`` overlaps the transfer."""
+        if table.shape[0] != self.n_table:
+            raise ValueError(f"halo exchange: table has {table.shape[0]} rows, plan needs {self.n_table}")
+        local, halo = table[: self.n_local], table[self.n_local :]
+        if table.is_cuda:
+            from .. import ops
+
+            send = ops.cast_pad(local, table.dtype, idx=self.send_idx)
+        else:
+            send = local.index_select(0, self.send_idx.long())
+        if SegmentedCapture.active is not None:
+            SegmentedCapture.active.exchange_start(send, self.send_splits, self.recv_splits, self.group, halo)
+            self._pending = "capture"
+        else:
+            self._pending = (_exchange(send, self.send_splits, self.recv_splits, self.group, out=halo, async_op=True), send)
+
+    def exchange_finish(self) -> None:
+        pending, self._pending = self._pending, None
+        if pending == "capture":
+            SegmentedCapture.active.exchange_finish()
+        elif pending is not None and pending[0] is not None:
+            pending[0].wait()
 
 
 _PLANS: dict = {}

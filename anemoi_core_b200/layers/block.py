@@ -363,9 +363,11 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
         kv_layers = [self.lin_key, self.lin_value]
         Fn.ln_linear(self._pack, x, ln, ("kv", id(self.lin_key), id(self.lin_value)), Fn.linear_sources(kv_layers),
                      lambda: Fn.cat_linear32(kv_layers), dt, out=table[: plan.n_local])  # fmt: skip
-        plan.exchange(table)
+        plan.exchange_start(table)
+        buf = self._dst_gemm(x, ln, [self.lin_query, self.lin_self], dt)  # runs while the halo rows travel
+        plan.exchange_finish()
         csr = Fn.csr_for(plan.edge_index, plan.n_table, x.shape[0])
-        out = self._attend_project(x, ln, table[:, :A], table[:, A:], [self.lin_self], ea, csr, x, dt, want_stats=True)
+        out = self._attend_project(x, ln, table[:, :A], table[:, A:], [self.lin_self], ea, csr, x, dt, dst_buf=buf, want_stats=True)
         return out, edge_attr
 
 

@@ -117,6 +117,11 @@ def check_halo_exchange(rank, world):
         remote = torch.unique(ei_l[0][(ei_l[0] < start) | (ei_l[0] >= start + sizes[rank])])
         assert torch.equal(plan.halo_ids, remote) and plan.n_halo == remote.numel() and plan.recv_splits[rank] == 0
         assert torch.equal(table[plan.n_local :], full[plan.halo_ids])
+        table2 = torch.full((plan.n_table, 4), float("nan"))  # split form used by the block (start / overlap / finish)
+        table2[: plan.n_local] = table[: plan.n_local]
+        plan.exchange_start(table2)
+        plan.exchange_finish()
+        assert torch.equal(table2, table)
         # what we send is what the others receive
         t = torch.tensor(plan.send_splits)
         others = [torch.zeros_like(t) for _ in range(world)]

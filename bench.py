@@ -406,8 +406,8 @@ def main():
         "metric": "forward ms/step", "value": ms_dev, "unit": "ms/step", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['desc']}", "batch": 1, "precision": "bf16 autocast, fp32 accumulate",
-                   "launch": ("cuda-graph replay" if world == 1 else "cuda-graph segments + eager NCCL all-gathers") if use_graph else "eager", "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
-                   "parallelism": "single GPU" if world == 1 else f"encoder / processor / decoder dst-range sharded over {world} GPUs (all-gather of k|v rows per layer over NCCL)"},
+                   "launch": ("cuda-graph replay" if world == 1 else "cuda-graph segments + eager NCCL collectives") if use_graph else "eager", "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
+                   "parallelism": "single GPU" if world == 1 else f"encoder / processor / decoder dst-range sharded over {world} GPUs (halo all-to-all of k|v rows per layer over NCCL)"},
         "e2e": {"value": ms_e2e, "unit": "ms/step", "h2d_bytes_per_step": x_grid_h.numel() * 4 + x_mesh_h.numel() * 4,
                 "d2h_bytes_per_step": out_h.numel() * out_h.element_size()},
         "gpu_launches": launches_per_step * args.steps,

@@ -104,6 +104,31 @@ __global__ void add_kernel(const void* __restrict__ a, int64_t lda, int adt, con
   }
 }
 
+// ---- gated feed-forward layers (layers/mlp.py:38-53 GatedMLPLayer): out = act(gate) * value, gate | value = the two halves of ONE GEMM
+// output row (gate_proj and value_proj run as one GEMM on concatenated weights).  act: 0 sigmoid (glu), 1 silu (swiglu), 2 gelu-erf (geglu),
+// 3 relu (reglu).  fp32 math, one rounding; HBM-bound: reads 2H, writes H per row.
+template <typename T, int VEC>
+__global__ void glu_combine_kernel(const T* __restrict__ in, int64_t ldi, T* __restrict__ out, int64_t ldo, int64_t M, int64_t H, int act) {
+  const int64_t q = H / VEC, total = M * q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / q, c = (i - m * q) * VEC;
+    float g[VEC], v[VEC], y[VEC];
+    load_vec_f32<T, VEC>(in + m * ldi + c, g);
+    load_vec_f32<T, VEC>(in + m * ldi + H + c, v);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float a;
+      if (act == 0) a = 1.0f / (1.0f + __expf(-g[j]));
+      else if (act == 1) a = g[j] / (1.0f + __expf(-g[j]));
+      else if (act == 2) a = gelu_erf(g[j]);
+      else a = fmaxf(g[j], 0.f);
+      y[j] = a * v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) out[m * ldo + c + j] = from_f32<T>(y[j]);
+  }
+}
+
 // ---- model glue either side of the encoder / decoder ------------------------------------------------------
 // assemble_input: out[(b e g), t * V + v] = x[b, t, e, g, v];  out[(b e g), T * V + a] = attrs[row % attr_rows, a];  zero pad up to Kpad.
 // Replaces einops.rearrange + torch.cat (+ the autocast cast of the embedding Linear) of `_assemble_input`
@@ -157,6 +182,27 @@ __global__ void assemble_output_kernel(const TI* __restrict__ dec, int64_t ldd, 
 }  // namespace anemoi
 
 using namespace anemoi;
+
+extern "C" int anemoi_b200_glu_combine(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t M, int64_t H, int act, int dtype, void* stream) {
+  ANEMOI_CHECK_ARG(M >= 0 && H >= 1 && ldi >= 2 * H && ldo >= H, "glu_combine: bad shape");
+  ANEMOI_CHECK_ARG(act >= 0 && act <= 3, "glu_combine: activation code %d (0 sigmoid, 1 silu, 2 gelu, 3 relu)", act);
+  ANEMOI_CHECK_ARG(dtype == ANEMOI_F32 || dtype == ANEMOI_BF16, "glu_combine: bad dtype %d", dtype);
+  if (M == 0) return 0;
+  ANEMOI_CHECK_ARG(in && out, "glu_combine: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int es = dtype == ANEMOI_BF16 ? 2 : 4;
+  const bool vec = H % 4 == 0 && ldi % 4 == 0 && (reinterpret_cast<uintptr_t>(in) % (4 * es)) == 0;
+  int64_t blocks = (M * (vec ? H / 4 : H) + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+  if (dtype == ANEMOI_BF16) {
+    if (vec) glu_combine_kernel<__nv_bfloat16, 4><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)in, ldi, (__nv_bfloat16*)out, ldo, M, H, act);
+    else glu_combine_kernel<__nv_bfloat16, 1><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)in, ldi, (__nv_bfloat16*)out, ldo, M, H, act);
+  } else {
+    if (vec) glu_combine_kernel<float, 4><<<(unsigned)blocks, 256, 0, s>>>((const float*)in, ldi, (float*)out, ldo, M, H, act);
+    else glu_combine_kernel<float, 1><<<(unsigned)blocks, 256, 0, s>>>((const float*)in, ldi, (float*)out, ldo, M, H, act);
+  }
+  return launch_status("glu_combine_kernel");
+}
 
 extern "C" int anemoi_b200_assemble_input(const float* x, int64_t B, int64_t T, int64_t E, int64_t G, int64_t V, const float* attrs, int64_t A,
                                           int64_t attr_rows, void* out, int64_t ldo, int64_t Kpad, int o_dtype, void* stream) {

@@ -16,6 +16,7 @@ from .. import ops
 from ..distributed.khop_edges import sort_edge_index_by_dst
 from . import _functional as Fn
 from .mlp import MLP
+from .mlp import GatedMLPLayer
 
 PairTensor = tuple[Tensor, Tensor]
 
@@ -53,21 +54,27 @@ class GraphConv(nn.Module):
         mlp = self.edge_mlp
         if mlp.layer_norm is None:
             raise NotImplementedError("GraphConv.edge_mlp without LayerNorm")
-        first = mlp.mlp[0]
+        def group(m):  # the Linear containers of one feed-forward layer: gate | value rows of a gated layer run as ONE GEMM
+            return [m.gate_proj, m.value_proj] if isinstance(m, GatedMLPLayer) else [m]
+
+        first = group(mlp.mlp[0])
         # node-level projections of the first edge-MLP layer, fp32 so the gather-add is a single rounding
-        p_i = Fn.fused_linear(self._pack, x_dst, [first], dt, cols=slice(0, C), use_bias=False, out_dtype=torch.float32)
-        p_j = Fn.fused_linear(self._pack, x_src, [first], dt, cols=slice(C, 2 * C), use_bias=False, out_dtype=torch.float32)
+        p_i = Fn.fused_linear(self._pack, x_dst, first, dt, cols=slice(0, C), use_bias=False, out_dtype=torch.float32)
+        p_j = Fn.fused_linear(self._pack, x_src, first, dt, cols=slice(C, 2 * C), use_bias=False, out_dtype=torch.float32)
         e = Fn.as_operand(edge_attr, dt, edge_attr.shape[1])
         # hidden layers through the MLP runner up to (not including) the LayerNorm
         mods = list(mlp.mlp)
         h, i, is_first = e, 0, True
         while i < len(mods):
             lin = mods[i]
-            act = i + 1 < len(mods) and not hasattr(mods[i + 1], "weight")
+            gated = isinstance(lin, GatedMLPLayer)
+            act = not gated and i + 1 < len(mods) and not hasattr(mods[i + 1], "weight")
             kw = {}
             if is_first:
                 kw = {"gather1": (p_i, csr.dst32), "gather2": (p_j, csr.src32), "cols": slice(2 * C, 3 * C)}
-            h = Fn.fused_linear(mlp._pack, h, [lin], dt, gelu=act, **kw)
+            h = Fn.fused_linear(mlp._pack, h, group(lin), dt, gelu=act, **kw)
+            if gated:
+                h = ops.glu_combine(h, lin.kind)
             i += 2 if act else 1
             is_first = False
         ln = mlp.layer_norm

@@ -1,6 +1,7 @@
 """MLP container + fused forward (reference: layers/mlp.py:97-179).
 
 Same structure and parameter names as the reference — ``mlp`` = Sequential(Linear, act, [Linear, act]*k, Linear[, act]),
+or with a gated ``mlp_implementation`` (glu / swiglu / geglu / reglu) Sequential(GatedMLPLayer, [GatedMLPLayer]*k, Linear) —
 optional ``layer_norm`` — so reference ``state_dict``s load unchanged.  The forward issues one fused
 GEMM(+bias+GELU) kernel per Linear and one LayerNorm(+residual) kernel.
 """
@@ -21,6 +22,21 @@ def _is_gelu(m: nn.Module) -> bool:
     return isinstance(m, nn.GELU) and getattr(m, "approximate", "none") == "none"
 
 
+GATED = ("glu", "swiglu", "geglu", "reglu")
+
+
+class GatedMLPLayer(nn.Module):
+    """``gating(gate_proj(x)) * value_proj(x)`` (layers/mlp.py:38-53), same parameter names.  Forward: ONE GEMM on the row-concatenated
+    gate | value weights (the folded LayerNorm and the row statistics work as for a plain Linear), then ``ops.glu_combine``."""
+
+    def __init__(self, in_features: int, out_features: int, layer_kernels, mlp_implementation: str) -> None:
+        super().__init__()
+        self.gate_proj = layer_kernels.Linear(in_features, out_features)
+        self.value_proj = layer_kernels.Linear(in_features, out_features)
+        self.gating = {"glu": nn.Sigmoid, "swiglu": nn.SiLU, "geglu": nn.GELU, "reglu": nn.ReLU}[mlp_implementation]()
+        self.kind = mlp_implementation
+
+
 class MLP(nn.Module):
     def __init__(
         self,
@@ -36,20 +52,25 @@ class MLP(nn.Module):
         super().__init__()
         if n_extra_layers < 0:
             raise ValueError(f"`n_extra_layers` must be >= 0, got {n_extra_layers}.")
-        if mlp_implementation != "mlp":
-            raise NotImplementedError(
-                f"mlp_implementation={mlp_implementation!r}: gated variants (glu/swiglu/geglu/reglu) are not part of the "
-                "implemented hot path yet (SURVEY.md §8f rank 4)"
-            )
+        if mlp_implementation not in ("mlp",) + GATED:
+            raise ValueError(f"`mlp_implementation` must be one of {('mlp',) + GATED}, got '{mlp_implementation}'.")
+        self.mlp_implementation = mlp_implementation
         k = load_layer_kernels(layer_kernels)
-        layers: list[nn.Module] = [k.Linear(in_features, hidden_dim), k.Activation()]
+        gated = mlp_implementation != "mlp"
+
+        def ffn(i: int, o: int) -> list[nn.Module]:  # layers/mlp.py:70-94 build_feedforward_modules
+            return [GatedMLPLayer(i, o, k, mlp_implementation)] if gated else [k.Linear(i, o), k.Activation()]
+
+        layers: list[nn.Module] = ffn(in_features, hidden_dim)
         for _ in range(n_extra_layers):
-            layers += [k.Linear(hidden_dim, hidden_dim), k.Activation()]
+            layers += ffn(hidden_dim, hidden_dim)
         layers.append(k.Linear(hidden_dim, out_features))
         if final_activation:
+            if gated:
+                raise NotImplementedError("final_activation with a gated mlp_implementation (no in-scope caller sets it, mapper.py:1052)")
             layers.append(k.Activation())
         for m in layers:
-            if not hasattr(m, "weight") and not _is_gelu(m):
+            if not hasattr(m, "weight") and not isinstance(m, GatedMLPLayer) and not _is_gelu(m):
                 raise NotImplementedError(f"Activation {type(m).__name__}: only exact (erf) torch.nn.GELU is fused into the GEMM epilogue")
         self.mlp = nn.Sequential(*layers)
         self.layer_norm = k.LayerNorm(normalized_shape=out_features) if layer_norm else None
@@ -72,6 +93,22 @@ class MLP(nn.Module):
         i, first = 0, True
         while i < len(mods):
             lin = mods[i]
+            if isinstance(lin, GatedMLPLayer):  # never the last module: the final Linear follows
+                from .. import ops
+
+                pair = [lin.gate_proj, lin.value_proj]
+                kw = {}
+                if first and first_gathers is not None:
+                    kw["gather1"], kw["gather2"] = first_gathers
+                if first and pre_ln is not None:
+                    gv = Fn.ln_linear(self._pack, x, pre_ln, ("pre_ln_gated", id(lin)), Fn.linear_sources(pair), lambda pair=pair: Fn.cat_linear32(pair),
+                                      dt, **kw)  # fmt: skip
+                else:
+                    gv = Fn.fused_linear(self._pack, x, pair, dt, cols=first_cols if first else None, **kw)
+                x = ops.glu_combine(gv, lin.kind)
+                i += 1
+                first = False
+                continue
             act = i + 1 < len(mods) and not hasattr(mods[i + 1], "weight")
             last = i + (2 if act else 1) >= len(mods)
             kw = {}

@@ -505,3 +505,20 @@ def assemble_output(dec: Tensor, x: Optional[Tensor], batch: int, ensemble: int,
                                                      _ptr(bound) if bound is not None else None, _ptr(y), n_step_output, V_out, _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_assemble_output")
     return y
+
+
+GLU_ACTS = {"glu": 0, "swiglu": 1, "geglu": 2, "reglu": 3}
+
+
+def glu_combine(gv: Tensor, act: str) -> Tensor:
+    """``act(gv[:, :H]) * gv[:, H:]`` for the gated MLP variants (reference layers/mlp.py:38-53); ``gv`` = [gate_proj(x) | value_proj(x)]."""
+    _need_cuda(gv)
+    M, W, ldi = _rows(gv)
+    if W % 2 or act not in GLU_ACTS:
+        raise ValueError(f"glu_combine: need an even width and act in {sorted(GLU_ACTS)}")
+    H = W // 2
+    out = torch.empty((M, H), dtype=gv.dtype, device=gv.device)
+    with _Timed("glu_combine", 8.0 * M * H, float(M) * 3 * H * gv.element_size()):
+        rc = _lib.load().anemoi_b200_glu_combine(_ptr(gv), ldi, _ptr(out), H, M, H, GLU_ACTS[act], dtype_code(gv.dtype), _stream())
+    _lib.check(rc, "anemoi_b200_glu_combine")
+    return out

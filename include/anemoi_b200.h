@@ -136,6 +136,11 @@ ANEMOI_API int anemoi_b200_cast_pad(const void* in, int64_t ldi, int i_dtype, co
 ANEMOI_API int anemoi_b200_add(const void* a, int64_t lda, int a_dtype, const void* b, int64_t ldb, int b_dtype, void* out, int64_t ldo,
                                int o_dtype, int64_t M, int64_t C, void* stream);
 
+/* Gated feed-forward layer (layers/mlp.py:38-53 GatedMLPLayer; mlp_implementation = glu / swiglu / geglu / reglu):
+ * out[m, j] = act(in[m, j]) * in[m, H + j] for j < H, where in = [gate_proj(x) | value_proj(x)] comes out of ONE anemoi_b200_linear call on
+ * the row-concatenated weights.  act: 0 sigmoid, 1 silu, 2 exact-erf gelu, 3 relu.  in : [M, ldi >= 2H], out : [M, ldo >= H], same dtype. */
+ANEMOI_API int anemoi_b200_glu_combine(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t M, int64_t H, int act, int dtype, void* stream);
+
 /* -- model glue either side of the path -------------------------------------------------
  * Replaces `_assemble_input` (models/encoder_processor_decoder.py:98-127): einops.rearrange(x, "batch time ensemble grid vars ->
  * (batch ensemble grid) (time vars)") + torch.cat with the node attributes (+ the autocast cast in front of the embedding Linear).

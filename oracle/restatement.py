@@ -118,10 +118,30 @@ def _layer_norm(sd: StateDict, name: str, x: Tensor, autocast_ln: bool = False) 
     return y.type_as(x) if autocast_ln else y
 
 
+GATING = ["swiglu"]  # the gating activation has no parameters, so the state_dict cannot name it: set with ``gated_mlp(kind)``
+
+
+class gated_mlp:
+    """``with gated_mlp("geglu"): ...`` — which ``mlp_implementation`` the GatedMLPLayer entries of the state_dict were built with."""
+
+    def __init__(self, kind: str):
+        self.kind, self.prev = kind, None
+
+    def __enter__(self):
+        self.prev, GATING[0] = GATING[0], self.kind
+
+    def __exit__(self, *exc):
+        GATING[0] = self.prev
+
+
 def mlp(sd: StateDict, prefix: str, x: Tensor, autocast_ln: bool = False) -> Tensor:
     """layers/mlp.py:97-179 — (Linear, GELU(erf))×k, Linear, optional LayerNorm; k from the state_dict."""
     idx = sorted({int(k[len(prefix) + 5 :].split(".")[0]) for k in sd if k.startswith(prefix + ".mlp.")})
     for n, i in enumerate(idx):
+        if f"{prefix}.mlp.{i}.gate_proj.weight" in sd:  # GatedMLPLayer (mlp.py:38-53): gating(gate_proj(x)) * value_proj(x)
+            gate = {"glu": torch.sigmoid, "swiglu": F.silu, "geglu": F.gelu, "reglu": F.relu}[GATING[0]]
+            x = gate(_linear(sd, f"{prefix}.mlp.{i}.gate_proj", x)) * _linear(sd, f"{prefix}.mlp.{i}.value_proj", x)
+            continue
         x = _linear(sd, f"{prefix}.mlp.{i}", x)
         if n < len(idx) - 1:
             x = F.gelu(x)
@@ -150,7 +170,7 @@ def graph_conv(sd, prefix, x_src, x_dst, edge_attr, edge_index, autocast_ln=Fals
 
 def gnn_processor_block(sd, prefix, x, edge_attr, edge_index, autocast_ln=False):
     """layers/block.py:362-395 (single device: sync_tensor / shard_tensor are identities)."""
-    if prefix + ".emb_edges.mlp.0.weight" in sd:
+    if any(k.startswith(prefix + ".emb_edges.mlp.0.") for k in sd):  # Linear (.weight) or GatedMLPLayer (.gate_proj.weight)
         edge_attr = mlp(sd, prefix + ".emb_edges", edge_attr, autocast_ln)
     out, edges_new = graph_conv(sd, prefix + ".conv", x, x, edge_attr, edge_index, autocast_ln)
     nodes_new = mlp(sd, prefix + ".node_mlp", torch.cat([x, out], dim=1), autocast_ln) + x

@@ -275,7 +275,8 @@ class GraphTransformerBaseBlock(nn.Module):
         return Fn.pad_edge_attr(edge_attr, ops.ATTN_MAX_EDGE_DIM if self._use_fold(dt) else 0)
 
     def _attend_project(self, x_dst: Tensor, ln_dst: nn.Module, k: Tensor, v: Tensor, dst_layers, edge_attr_p: Tensor, csr: ops.GraphCSR,
-                        x_skip: Tensor, dt: torch.dtype, dst_buf: Optional[Tensor] = None, want_stats: bool = False) -> Tensor:  # fmt: skip
+                        x_skip: Tensor, dt: torch.dtype, dst_buf: Optional[Tensor] = None, want_stats: bool = False,
+                        k_prenormed: bool = False) -> Tensor:  # fmt: skip
         """dst-side GEMM (q | [k | v |] self | qw) -> attention (+ self) -> projection (+ skip) -> LN -> MLP (+ residual).
 
         ``dst_layers`` = the Linear containers of the dst-side GEMM *after* lin_query (processor: key, value, self — k and v then
@@ -293,7 +294,7 @@ class GraphTransformerBaseBlock(nn.Module):
         if k is None:
             k, v = dst_buf[:, A : 2 * A], dst_buf[:, 2 * A : 3 * A]
         if self.qk_norm:
-            for t, norm in ((q, self.q_norm), (k, self.k_norm)):
+            for t, norm in ((q, self.q_norm),) + (() if k_prenormed else ((k, self.k_norm),)):
                 ops.layer_norm(t, self._pack.f32(norm.weight), self._pack.f32(getattr(norm, "bias", None)), norm.eps, out=t, groups=H)
         b_e = self._pack.f32(self.lin_edge.bias)
         if fold:
@@ -347,8 +348,8 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
             csr = Fn.csr_for(edge_index, x.shape[0], x.shape[0])
             return self._attend_project(x, ln, None, None, dst_layers, ea, csr, x, dt, want_stats=True), edge_attr
         # edges strategy (block.py:1120-1183): each rank owns a dst range and needs the k | v rows of the source nodes its edges name
-        if self.qk_norm:
-            raise NotImplementedError("qk_norm with a sharded processor")
+        if self.qk_norm and not HALO_EXCHANGE:
+            raise NotImplementedError("qk_norm with the all-gather form of the sharded processor (use the halo exchange)")
         if not HALO_EXCHANGE:  # A/B switch: all-gather every k | v row (round-1 first version)
             buf = self._dst_gemm(x, ln, [self.lin_query] + dst_layers, dt)
             kv_full = gather_rows(buf[:, A : 3 * A], shard_info.nodes, model_comm_group)
@@ -363,11 +364,15 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
         kv_layers = [self.lin_key, self.lin_value]
         Fn.ln_linear(self._pack, x, ln, ("kv", id(self.lin_key), id(self.lin_value)), Fn.linear_sources(kv_layers),
                      lambda: Fn.cat_linear32(kv_layers), dt, out=table[: plan.n_local])  # fmt: skip
+        if self.qk_norm:  # per-row, per-head: commutes with the exchange, so every rank normalises the keys it owns once
+            ops.layer_norm(table[: plan.n_local, :A], self._pack.f32(self.k_norm.weight), self._pack.f32(getattr(self.k_norm, "bias", None)),
+                           self.k_norm.eps, out=table[: plan.n_local, :A], groups=self.num_heads)  # fmt: skip
         plan.exchange_start(table)
         buf = self._dst_gemm(x, ln, [self.lin_query, self.lin_self], dt)  # runs while the halo rows travel
         plan.exchange_finish()
         csr = Fn.csr_for(plan.edge_index, plan.n_table, x.shape[0])
-        out = self._attend_project(x, ln, table[:, :A], table[:, A:], [self.lin_self], ea, csr, x, dt, dst_buf=buf, want_stats=True)
+        out = self._attend_project(x, ln, table[:, :A], table[:, A:], [self.lin_self], ea, csr, x, dt, dst_buf=buf, want_stats=True,
+                                   k_prenormed=True)  # fmt: skip
         return out, edge_attr
 
 

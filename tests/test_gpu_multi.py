@@ -31,15 +31,16 @@ def _worker(rank, world, init_file, ret):
         sizes = get_balanced_partition_sizes(n, world)
         group = dist.group.WORLD
         msgs = []
-        for kind in ("gt", "gnn"):
+        for kind in ("gt", "gt_qknorm", "gnn"):
             for dt in (torch.float32, torch.bfloat16):
                 torch.manual_seed(0)
-                if kind == "gt":
-                    m = GraphTransformerProcessor(num_layers=2, num_channels=256, num_chunks=1, num_heads=8, mlp_hidden_ratio=4, edge_dim=gr["edge_dim"])
+                if kind.startswith("gt"):
+                    m = GraphTransformerProcessor(num_layers=2, num_channels=256, num_chunks=1, num_heads=8, mlp_hidden_ratio=4, edge_dim=gr["edge_dim"],
+                                                  qk_norm=kind == "gt_qknorm")  # fmt: skip
                 else:
                     m = GNNProcessor(num_channels=128, num_layers=2, num_chunks=1, mlp_extra_layers=0, edge_dim=gr["edge_dim"])
                 m = m.cuda().eval()
-                c = 256 if kind == "gt" else 128
+                c = 256 if kind.startswith("gt") else 128
                 x = torch.randn(n, c, generator=torch.Generator().manual_seed(1)).cuda()
                 with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dt == torch.bfloat16):
                     full = m(x, 1, GraphShardInfo(nodes=[n]), ea, ei)

@@ -136,3 +136,38 @@ def test_gelu_exp2_polynomial():
     y = np.maximum(x, 0) - t.astype(np.float64) * np.exp2(p.astype(np.float64))
     ref = torch.nn.functional.gelu(torch.from_numpy(x).double()).numpy()
     assert np.abs(y - ref).max() <= 1e-6
+
+
+def test_row_stats_tags_follow_the_tensor_identity():
+    """Statistics handed from a producing GEMM to the consuming LayerNorm-GEMM travel as a tag on the tensor object and are dropped as soon
+    as the tensor is not the one that was produced (slice, in-place update through torch, another object on the same storage)."""
+    from anemoi_core_b200.layers import _functional as Fn
+
+    x = torch.randn(8, 64)
+    stats = torch.zeros(8, 1, 2)
+    assert Fn.tagged_row_stats(x) is None
+    assert Fn.tag_row_stats(x, stats) is x and Fn.tagged_row_stats(x) is stats
+    assert Fn.tagged_row_stats(x[:4]) is None and Fn.tagged_row_stats(x.view(8, 64)) is None  # other tensor objects carry no tag
+    x.add_(1.0)  # torch bumps the version counter: the statistics no longer describe the contents
+    assert Fn.tagged_row_stats(x) is None
+    assert Fn.wants_row_stats(512, torch.bfloat16) and not Fn.wants_row_stats(512, torch.float32)
+    assert not Fn.wants_row_stats(36, torch.bfloat16) and not Fn.wants_row_stats(4096, torch.bfloat16)
+
+
+def test_model_output_tables_encode_residual_and_boundings(golden):
+    """skip_src[v] = input variable whose last step is added to output variable v (prognostic pairs), bound[v] = 0 / 1 (relu) / 2 (leaky)."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("_glue", os.path.join(os.path.dirname(__file__), "test_model_glue.py"))
+    glue = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(glue)
+    build_model = glue.build_model
+
+    fx = golden("model_forward")
+    m = build_model(fx, "gnn")
+    m._bound_spec["data"] = [("relu", [1, 3]), ("leaky_relu", [4])]
+    skip, bound = m._output_tables("data", torch.device("cpu"))
+    assert skip.dtype == torch.int32 and skip.tolist() == [0, 1, 2, 4, 5]  # out_prog [0..4] <- in_prog [0, 1, 2, 4, 5]
+    assert bound.tolist() == [0, 1, 0, 1, 2]
+    assert m._output_tables("data", torch.device("cpu"))[0] is skip  # cached

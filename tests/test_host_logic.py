@@ -171,3 +171,28 @@ def test_model_output_tables_encode_residual_and_boundings(golden):
     assert skip.dtype == torch.int32 and skip.tolist() == [0, 1, 2, 4, 5]  # out_prog [0..4] <- in_prog [0, 1, 2, 4, 5]
     assert bound.tolist() == [0, 1, 0, 1, 2]
     assert m._output_tables("data", torch.device("cpu"))[0] is skip  # cached
+
+
+def test_reference_default_yaml_kwargs_construct():
+    """The reference's default model configs (training/config/model/graphtransformer.yaml:11-75, gnn.yaml:11-57) instantiate the mirror
+    classes unchanged: every key of the YAML blocks is passed as a keyword (interpolations resolved), `_target_`-style layer_kernels included."""
+    gt_kernels = {"LayerNorm": {"_target_": "torch.nn.LayerNorm"}, "Linear": {"_target_": "torch.nn.Linear"}, "Activation": {"_target_": "torch.nn.GELU"},
+                  "QueryNorm": {"_target_": "anemoi_core_b200.layers.normalization.AutocastLayerNorm", "bias": False},
+                  "KeyNorm": {"_target_": "anemoi_core_b200.layers.normalization.AutocastLayerNorm", "bias": False}}  # fmt: skip
+    common = dict(trainable_size=8, sub_graph_edge_attributes=["edge_length", "edge_dirs"], mlp_hidden_ratio=4, mlp_implementation="mlp", num_heads=16,
+                  qk_norm=False, cpu_offload=False, gradient_checkpointing=True, layer_kernels=gt_kernels, shard_strategy="edges",
+                  graph_attention_backend="triton", edge_pre_mlp=False)  # fmt: skip
+    C = 64  # (the YAML says 1024; the constructor logic does not depend on it)
+    GraphTransformerProcessor(num_layers=16, num_chunks=4, num_channels=C, edge_dim=11, **common)
+    GraphTransformerForwardMapper(num_chunks=4, in_channels_src=30, in_channels_dst=12, hidden_dim=C, edge_dim=11, **common)
+    GraphTransformerBackwardMapper(num_chunks=4, initialise_data_extractor_zero=False, in_channels_src=C, in_channels_dst=30, hidden_dim=C,
+                                   out_channels_dst=9, edge_dim=11, **common)  # fmt: skip
+    gnn_kernels = {"LayerNorm": {"_target_": "anemoi_core_b200.layers.normalization.AutocastLayerNorm"}, "Linear": {"_target_": "torch.nn.Linear"},
+                   "Activation": {"_target_": "torch.nn.GELU"}}  # fmt: skip
+    gcommon = dict(trainable_size=8, sub_graph_edge_attributes=["edge_length", "edge_dirs"], mlp_extra_layers=0, mlp_hidden_ratio=1.0,
+                   mlp_implementation="mlp", cpu_offload=False, gradient_checkpointing=True, layer_kernels=gnn_kernels)  # fmt: skip
+    GNNProcessor(num_layers=16, num_chunks=2, num_channels=C, edge_dim=11, **gcommon)
+    GNNForwardMapper(num_chunks=1, in_channels_src=30, in_channels_dst=12, hidden_dim=C, edge_dim=11, **gcommon)
+    GNNBackwardMapper(num_chunks=1, in_channels_src=C, in_channels_dst=C, hidden_dim=C, out_channels_dst=9, edge_dim=11, **gcommon)
+    # the gated variants the YAML comments name
+    GraphTransformerProcessor(num_layers=2, num_chunks=1, num_channels=C, edge_dim=11, **{**common, "mlp_implementation": "swiglu", "mlp_hidden_ratio": 2.67})

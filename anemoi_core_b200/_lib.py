@@ -29,6 +29,8 @@ SIGNATURES = {
     "anemoi_b200_csr_build": [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "anemoi_b200_layer_norm": [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int64,
                                c_int64, c_int64, c_float, c_void_p],
+    "anemoi_b200_cond_layer_norm": [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                    c_int64, c_int64, c_int64, c_float, c_void_p],
     "anemoi_b200_linear": [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                            c_int64, c_int, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p],
     "anemoi_b200_row_stats": [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_float, c_void_p],

@@ -144,6 +144,44 @@ int launch_partial_row_stats(const void* out, int64_t ldo, int o_dtype, int64_t 
   return launch_status("partial_row_stats_kernel");
 }
 
+// Conditional LayerNorm (layers/normalization.py:34-94): y = LN(x) * (1 + cond . Ws^T + bs) + (cond . Wb^T + bb), no learnable LayerNorm
+// affine.  One warp per row: two-pass statistics, then per channel the two Dc-long dot products against the conditioning row (held one
+// element per lane and broadcast by shuffles; Dc <= 32); the 2 x [C, Dc] weights stay in L1.  The per-row scale / bias tensors
+// ([M, 2C] fp32 in the reference) are never materialised.
+__global__ void __launch_bounds__(256) cond_layer_norm_kernel(const void* __restrict__ x, int64_t ldx, int x_dtype, const float* __restrict__ cond,
+                                                               int64_t ldc, const float* __restrict__ ws, const float* __restrict__ bs,
+                                                               const float* __restrict__ wb, const float* __restrict__ bb, void* __restrict__ y,
+                                                               int64_t ldy, int y_dtype, int64_t M, int C, int Dc, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < M; m += warps_total) {
+    const int64_t xo = m * ldx;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += load_as_f32(x, xo + c, x_dtype);
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float d = load_as_f32(x, xo + c, x_dtype) - mean;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    const float cd = lane < Dc ? cond[m * ldc + lane] : 0.f;
+    for (int c0 = 0; c0 < C; c0 += 32) {  // uniform trip count: the shuffles below need the whole warp
+      const int c = c0 + lane;
+      const bool ok = c < C;
+      float sc = ok ? bs[c] : 0.f, bi = ok ? bb[c] : 0.f;
+      for (int d = 0; d < Dc; ++d) {
+        const float cv = __shfl_sync(0xffffffffu, cd, d);
+        if (ok) {
+          sc = fmaf(cv, ws[(int64_t)c * Dc + d], sc);
+          bi = fmaf(cv, wb[(int64_t)c * Dc + d], bi);
+        }
+      }
+      if (ok) store_from_f32(y, m * ldy + c, y_dtype, (load_as_f32(x, xo + c, x_dtype) - mean) * rstd * (1.0f + sc) + bi);
+    }
+  }
+}
+
 // Generic path: any C / alignment.  Lane strides over the row; re-reads hit L1.
 __global__ void __launch_bounds__(256) layer_norm_generic_kernel(const void* __restrict__ x, int64_t ldx, int x_dtype,
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -238,6 +276,22 @@ extern "C" int anemoi_b200_layer_norm(const void* x, int64_t ldx, int x_dtype, c
   layer_norm_generic_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, ldx, x_dtype, gamma, beta, residual, ldr, r_dtype, y, ldy, y_dtype, M, groups,
                                                              (int)C, eps);
   return launch_status("layer_norm_generic_kernel");
+}
+
+extern "C" int anemoi_b200_cond_layer_norm(const void* x, int64_t ldx, int x_dtype, const float* cond, int64_t ldc, const float* w_scale,
+                                           const float* b_scale, const float* w_bias, const float* b_bias, void* y, int64_t ldy, int y_dtype,
+                                           int64_t M, int64_t C, int64_t Dc, float eps, void* stream) {
+  ANEMOI_CHECK_ARG(M >= 0 && C >= 1 && C < (1 << 30) && Dc >= 1 && Dc <= 32, "cond_layer_norm: bad shape (condition width 1..32)");
+  ANEMOI_CHECK_ARG(ldx >= C && ldy >= C && ldc >= Dc, "cond_layer_norm: leading dimension too small");
+  ANEMOI_CHECK_ARG((x_dtype | 1) == 1 && (y_dtype | 1) == 1, "cond_layer_norm: bad dtype");
+  if (M == 0) return 0;
+  ANEMOI_CHECK_ARG(x && y && cond && w_scale && b_scale && w_bias && b_bias, "cond_layer_norm: null pointer");
+  int64_t blocks = (M + 7) / 8;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  cond_layer_norm_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, x_dtype, cond, ldc, w_scale, b_scale, w_bias, b_bias, y, ldy,
+                                                                            y_dtype, M, (int)C, (int)Dc, eps);
+  return launch_status("cond_layer_norm_kernel");
 }
 
 extern "C" int anemoi_b200_row_stats(const void* x, int64_t ldx, int x_dtype, float* stats, int64_t M, int64_t C, float eps, void* stream) {

@@ -180,16 +180,28 @@ def can_fold_ln(ln: nn.Module, k: int, dt: torch.dtype) -> bool:
 
 
 def ln_linear(pack: WeightPack, x: Tensor, ln: nn.Module, key, sources: Sequence[Optional[Tensor]], build32: Callable[[], tuple], dt: torch.dtype,
-              **kw) -> Tensor:  # fmt: skip
+              cond: Optional[Tensor] = None, **kw) -> Tensor:  # fmt: skip
     """``linear(LayerNorm(x))`` for the weight / bias produced by ``build32() -> (w fp32 [N, K], b fp32 [N] | None)``.
 
     bf16: the LayerNorm is folded into the GEMM — W' = W * gamma, bias' = b + W beta, colsum = sum_k bf16(W') — and only the per-row
     (mean, rstd) are computed beforehand (``ops.row_stats`` on the bf16 operand, so constant rows cancel exactly); the normalised
     activations are never written.  fp32 (parity mode) or unsupported shapes: LayerNorm kernel, then the plain GEMM."""
+    from .normalization import ConditionalLayerNorm
     from .normalization import _check_plain_layernorm
 
-    _check_plain_layernorm(ln)
     k = x.shape[1]
+    if isinstance(ln, ConditionalLayerNorm):
+        # per-row affine from the conditioning: cannot be folded into the weights; one conditional-LayerNorm kernel, then the plain GEMM
+        def build_cond():
+            w32, b32 = build32()
+            kk = w32.shape[1]
+            if pad_k(kk, dt) != kk:
+                w32 = torch.nn.functional.pad(w32, (0, pad_k(kk, dt) - kk))
+            return w32.to(dt).contiguous(), (None if b32 is None else b32.contiguous())
+
+        w, b = pack.get(("ln_cond", key, dt), list(sources), build_cond)
+        return linear_with_stats(as_operand(ln.run(x, cond, dt), dt, w.shape[1]), w, b, **kw)
+    _check_plain_layernorm(ln)
     srcs = list(sources) + [ln.weight, ln.bias]
     if can_fold_ln(ln, k, dt):
 

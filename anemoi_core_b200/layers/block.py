@@ -228,12 +228,12 @@ class GraphTransformerBaseBlock(nn.Module):
             b = torch.zeros(w.shape[0], device=w.device)
         return torch.cat([w, wf], 0), torch.cat([b, bf])
 
-    def _dst_gemm(self, x_raw: Tensor, ln: nn.Module, layers, dt: torch.dtype) -> Tensor:
+    def _dst_gemm(self, x_raw: Tensor, ln: nn.Module, layers, dt: torch.dtype, cond: Optional[Tensor] = None) -> Tensor:
         """LayerNorm + dst-side GEMM (q | ... | self | qw); the LayerNorm is folded into the GEMM on the bf16 path."""
         fold_q = self._use_fold(dt) and not self.qk_norm
         key = ("dst", tuple(id(l) for l in layers), fold_q)
         srcs = Fn.linear_sources(layers) + [self.lin_edge.weight]
-        return Fn.ln_linear(self._pack, x_raw, ln, key, srcs, lambda: self._dst_weight32(layers, fold_q), dt)
+        return Fn.ln_linear(self._pack, x_raw, ln, key, srcs, lambda: self._dst_weight32(layers, fold_q), dt, cond=cond)
 
     def _qw_blockdiag(self, dt: torch.dtype) -> Tensor:
         """[hdp, A] block-diagonal W_e^T for the qk_norm case (qw must be taken from the normalised query)."""
@@ -276,7 +276,7 @@ class GraphTransformerBaseBlock(nn.Module):
 
     def _attend_project(self, x_dst: Tensor, ln_dst: nn.Module, k: Tensor, v: Tensor, dst_layers, edge_attr_p: Tensor, csr: ops.GraphCSR,
                         x_skip: Tensor, dt: torch.dtype, dst_buf: Optional[Tensor] = None, want_stats: bool = False,
-                        k_prenormed: bool = False) -> Tensor:  # fmt: skip
+                        k_prenormed: bool = False, cond: Optional[Tensor] = None) -> Tensor:  # fmt: skip
         """dst-side GEMM (q | [k | v |] self | qw) -> attention (+ self) -> projection (+ skip) -> LN -> MLP (+ residual).
 
         ``dst_layers`` = the Linear containers of the dst-side GEMM *after* lin_query (processor: key, value, self — k and v then
@@ -287,7 +287,7 @@ class GraphTransformerBaseBlock(nn.Module):
         d, dp, hdp = self._fold_dims()
         layers = [self.lin_query] + list(dst_layers)
         if dst_buf is None:
-            dst_buf = self._dst_gemm(x_dst, ln_dst, layers, dt)
+            dst_buf = self._dst_gemm(x_dst, ln_dst, layers, dt, cond=cond)
         n_lin = len(layers)
         q = dst_buf[:, :A]
         x_r = dst_buf[:, (n_lin - 1) * A : n_lin * A]
@@ -311,7 +311,7 @@ class GraphTransformerBaseBlock(nn.Module):
         # the projection epilogue also produces the row statistics of its output for layer_norm_mlp_dst (folded into the MLP's first GEMM),
         # and the MLP's last GEMM those of the block output for the next block's layer_norm_attention
         out = Fn.linear_with_stats(Fn.as_operand(att, dt, wp.shape[1]), wp, self._pack.bias([self.projection]), residual=skip, want_stats=True)
-        return self.node_dst_mlp.run(out, dt, residual=out, pre_ln=self.layer_norm_mlp_dst, want_stats=want_stats)
+        return self.node_dst_mlp.run(out, dt, residual=out, pre_ln=self.layer_norm_mlp_dst, want_stats=want_stats, cond=cond)
 
 
 class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
@@ -336,25 +336,23 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
         **kwargs,
     ) -> tuple[Tensor, Tensor]:
         Fn.forward_only_guard(self)
-        if cond is not None:
-            raise NotImplementedError("conditional LayerNorm (cond=...) is not implemented")
         dt = Fn.compute_dtype(x)
         A = self.attn_channels
-        ln = self.layer_norm_attention
+        ln = self.layer_norm_attention  # with a ConditionalLayerNorm kernel both LayerNorms of the block take ``cond`` (block.py:1233-1271)
         dst_layers = [self.lin_key, self.lin_value, self.lin_self]
         ea = edge_attr_prepared if edge_attr_prepared is not None else self.prepare_edges(edge_attr, dt)
         world = group_size(model_comm_group)
         if world == 1:
             csr = Fn.csr_for(edge_index, x.shape[0], x.shape[0])
-            return self._attend_project(x, ln, None, None, dst_layers, ea, csr, x, dt, want_stats=True), edge_attr
+            return self._attend_project(x, ln, None, None, dst_layers, ea, csr, x, dt, want_stats=True, cond=cond), edge_attr
         # edges strategy (block.py:1120-1183): each rank owns a dst range and needs the k | v rows of the source nodes its edges name
         if self.qk_norm and not HALO_EXCHANGE:
             raise NotImplementedError("qk_norm with the all-gather form of the sharded processor (use the halo exchange)")
         if not HALO_EXCHANGE:  # A/B switch: all-gather every k | v row (round-1 first version)
-            buf = self._dst_gemm(x, ln, [self.lin_query] + dst_layers, dt)
+            buf = self._dst_gemm(x, ln, [self.lin_query] + dst_layers, dt, cond=cond)
             kv_full = gather_rows(buf[:, A : 3 * A], shard_info.nodes, model_comm_group)
             csr = Fn.csr_for(edge_index, kv_full.shape[0], x.shape[0])
-            out = self._attend_project(x, ln, kv_full[:, :A], kv_full[:, A:], dst_layers, ea, csr, x, dt, dst_buf=buf, want_stats=True)
+            out = self._attend_project(x, ln, kv_full[:, :A], kv_full[:, A:], dst_layers, ea, csr, x, dt, dst_buf=buf, want_stats=True, cond=cond)
             return out, edge_attr
         # halo exchange (distributed/halo.py): the k | v GEMM writes this rank's rows into the head of a compact table, one gather kernel
         # packs the rows the other ranks asked for, one all-to-all drops the rows we need into the tail; the edge list was relabelled
@@ -363,16 +361,16 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
         table = torch.empty((plan.n_table, 2 * A), dtype=dt, device=x.device)
         kv_layers = [self.lin_key, self.lin_value]
         Fn.ln_linear(self._pack, x, ln, ("kv", id(self.lin_key), id(self.lin_value)), Fn.linear_sources(kv_layers),
-                     lambda: Fn.cat_linear32(kv_layers), dt, out=table[: plan.n_local])  # fmt: skip
+                     lambda: Fn.cat_linear32(kv_layers), dt, cond=cond, out=table[: plan.n_local])  # fmt: skip
         if self.qk_norm:  # per-row, per-head: commutes with the exchange, so every rank normalises the keys it owns once
             ops.layer_norm(table[: plan.n_local, :A], self._pack.f32(self.k_norm.weight), self._pack.f32(getattr(self.k_norm, "bias", None)),
                            self.k_norm.eps, out=table[: plan.n_local, :A], groups=self.num_heads)  # fmt: skip
         plan.exchange_start(table)
-        buf = self._dst_gemm(x, ln, [self.lin_query, self.lin_self], dt)  # runs while the halo rows travel
+        buf = self._dst_gemm(x, ln, [self.lin_query, self.lin_self], dt, cond=cond)  # runs while the halo rows travel
         plan.exchange_finish()
         csr = Fn.csr_for(plan.edge_index, plan.n_table, x.shape[0])
         out = self._attend_project(x, ln, table[:, :A], table[:, A:], [self.lin_self], ea, csr, x, dt, dst_buf=buf, want_stats=True,
-                                   k_prenormed=True)  # fmt: skip
+                                   k_prenormed=True, cond=cond)  # fmt: skip
         return out, edge_attr
 
 
@@ -406,21 +404,21 @@ class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
         **layer_kwargs,
     ) -> tuple[PairTensor, Tensor]:
         Fn.forward_only_guard(self)
-        if cond is not None:
-            raise NotImplementedError("conditional LayerNorm (cond=...) is not implemented")
         x_src, x_dst = x
+        cond_src, cond_dst = cond if cond is not None else (None, None)  # (block.py:978-980)
         dt = Fn.compute_dtype(x_src, x_dst)
         A = self.attn_channels
         kv_layers = [self.lin_key, self.lin_value]
-        kv = Fn.ln_linear(self._pack, x_src, self.layer_norm_attention_src, ("kv",), Fn.linear_sources(kv_layers), lambda: Fn.cat_linear32(kv_layers), dt)
+        kv = Fn.ln_linear(self._pack, x_src, self.layer_norm_attention_src, ("kv",), Fn.linear_sources(kv_layers), lambda: Fn.cat_linear32(kv_layers), dt,
+                          cond=cond_src)  # fmt: skip
         if group_size(model_comm_group) > 1 and shard_info is not None and shard_info.src_is_sharded():
             # edges strategy (reference mapper.py:248-297 / khop_edges.py:317-409): every rank needs the k | v rows of all sources
             kv = gather_rows(kv, shard_info.src_nodes, model_comm_group)
         csr = Fn.csr_for(edge_index, kv.shape[0], x_dst.shape[0])
         dst_new = self._attend_project(x_dst, self.layer_norm_attention_dest, kv[:, :A], kv[:, A:], [self.lin_self], self.prepare_edges(edge_attr, dt),
-                                       csr, x_dst, dt)
+                                       csr, x_dst, dt, cond=cond_dst)
         src_new = x_src
         if self.update_src_nodes:
             src_new = self.node_src_mlp.run(x_src, dt, residual=x_src if x_src.dtype in Fn.SUPPORTED else x_src.float(),
-                                            pre_ln=self.layer_norm_mlp_src)
+                                            pre_ln=self.layer_norm_mlp_src, cond=cond_src)
         return (src_new, dst_new), edge_attr

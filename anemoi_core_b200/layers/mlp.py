@@ -86,6 +86,7 @@ class MLP(nn.Module):
         out: Optional[Tensor] = None,
         pre_ln: Optional[nn.Module] = None,
         want_stats: bool = False,
+        cond: Optional[Tensor] = None,
     ) -> Tensor:
         """Fused forward in compute dtype ``dt``.  ``residual`` is added after the last op (LayerNorm if present).
         ``first_gathers`` / ``first_cols`` feed the split first layer of GraphConv's edge MLP (gather-add epilogue)."""
@@ -102,7 +103,7 @@ class MLP(nn.Module):
                     kw["gather1"], kw["gather2"] = first_gathers
                 if first and pre_ln is not None:
                     gv = Fn.ln_linear(self._pack, x, pre_ln, ("pre_ln_gated", id(lin)), Fn.linear_sources(pair), lambda pair=pair: Fn.cat_linear32(pair),
-                                      dt, **kw)  # fmt: skip
+                                      dt, cond=cond, **kw)  # fmt: skip
                 else:
                     gv = Fn.fused_linear(self._pack, x, pair, dt, cols=first_cols if first else None, **kw)
                 x = ops.glu_combine(gv, lin.kind)
@@ -119,7 +120,7 @@ class MLP(nn.Module):
                 kw["want_stats"] = want_stats  # the caller's next op is a LayerNorm folded into a GEMM: hand it the row statistics
             if first and pre_ln is not None:  # LayerNorm(x) feeding the first Linear: folded into that GEMM on the bf16 path
                 x = Fn.ln_linear(self._pack, x, pre_ln, ("pre_ln", id(lin)), Fn.linear_sources([lin]), lambda lin=lin: Fn.cat_linear32([lin]), dt,
-                                 gelu=act, **kw)
+                                 cond=cond, gelu=act, **kw)
             else:
                 x = Fn.fused_linear(self._pack, x, [lin], dt, cols=first_cols if first else None, gelu=act, **kw)
             i += 2 if act else 1

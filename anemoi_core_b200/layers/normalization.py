@@ -1,4 +1,4 @@
-"""LayerNorm containers (reference: layers/normalization.py:19-31)."""
+"""LayerNorm containers (reference: layers/normalization.py:19-94)."""
 
 from __future__ import annotations
 
@@ -19,6 +19,36 @@ class AutocastLayerNorm(nn.LayerNorm):
         return y.reshape(shape)
 
 
+class ConditionalLayerNorm(nn.Module):
+    """``LN(x) * (1 + scale(cond)) + bias(cond)`` (normalization.py:34-94), same parameter names (``scale.weight|bias``, ``bias.weight|bias``;
+    the LayerNorm itself has no affine).  One kernel: the per-row scale / bias are formed inside it, never materialised."""
+
+    def __init__(self, normalized_shape: int, condition_shape: int = 16, zero_init: bool = True, autocast: bool = True) -> None:
+        super().__init__()
+        self.norm = nn.LayerNorm(normalized_shape, elementwise_affine=False)
+        self.scale = nn.Linear(condition_shape, normalized_shape)
+        self.bias = nn.Linear(condition_shape, normalized_shape)
+        self.autocast = autocast
+        if zero_init:
+            for p in (self.scale.weight, self.scale.bias, self.bias.weight, self.bias.bias):
+                nn.init.zeros_(p)
+
+    @property
+    def eps(self) -> float:
+        return self.norm.eps
+
+    def run(self, x: Tensor, cond: Tensor, out_dtype: torch.dtype) -> Tensor:
+        if cond is None:
+            raise ValueError("ConditionalLayerNorm needs the conditioning tensor (cond=...)")
+        return ops.cond_layer_norm(x, cond, self.scale.weight.detach(), self.scale.bias.detach(), self.bias.weight.detach(), self.bias.bias.detach(),
+                                   self.eps, out_dtype=out_dtype)  # fmt: skip
+
+    def forward(self, x: Tensor, cond: Tensor) -> Tensor:
+        shape = x.shape
+        y = self.run(x.reshape(-1, shape[-1]), cond.reshape(-1, cond.shape[-1]), x.dtype if self.autocast else torch.float32)
+        return y.reshape(shape)
+
+
 def ln_params(ln: nn.Module) -> tuple[Tensor | None, Tensor | None, float]:
     """(weight, bias, eps) of a LayerNorm-like container."""
     if isinstance(ln, nn.Identity):
@@ -29,6 +59,5 @@ def ln_params(ln: nn.Module) -> tuple[Tensor | None, Tensor | None, float]:
 def _check_plain_layernorm(ln: nn.Module) -> None:
     if not isinstance(ln, torch.nn.LayerNorm):
         raise NotImplementedError(
-            f"{type(ln).__name__}: only torch.nn.LayerNorm-like kernels (weight, bias, eps) are implemented; "
-            "ConditionalLayerNorm is outside the forward hot path (SURVEY.md §8f rank 4)"
+            f"{type(ln).__name__}: only torch.nn.LayerNorm-like kernels (weight, bias, eps) and ConditionalLayerNorm are implemented"
         )

@@ -228,5 +228,6 @@ class GraphTransformerProcessor(BaseProcessor):
         if all(isinstance(b.edge_pre_mlp, nn.Identity) for b in self.proc):
             shared_edges = self.proc[0].prepare_edges(edge_attr, Fn.compute_dtype(x))  # one padded fp32 copy for all layers
         for block in self.proc:
-            x, _ = block(x, edge_attr, edge_index, shard_info, batch_size, n_nodes, model_comm_group, edge_attr_prepared=shared_edges)
+            x, _ = block(x, edge_attr, edge_index, shard_info, batch_size, n_nodes, model_comm_group, edge_attr_prepared=shared_edges,
+                         cond=kwargs.get("cond"))  # fmt: skip
         return x

@@ -522,3 +522,21 @@ def glu_combine(gv: Tensor, act: str) -> Tensor:
         rc = _lib.load().anemoi_b200_glu_combine(_ptr(gv), ldi, _ptr(out), H, M, H, GLU_ACTS[act], dtype_code(gv.dtype), _stream())
     _lib.check(rc, "anemoi_b200_glu_combine")
     return out
+
+
+def cond_layer_norm(x: Tensor, cond: Tensor, w_scale: Tensor, b_scale: Tensor, w_bias: Tensor, b_bias: Tensor, eps: float = 1e-5,
+                    out_dtype: Optional[torch.dtype] = None) -> Tensor:  # fmt: skip
+    """``LN(x) * (1 + cond @ w_scale.T + b_scale) + (cond @ w_bias.T + b_bias)`` (reference ConditionalLayerNorm, normalization.py:34-94)."""
+    _need_cuda(x, cond, w_scale, b_scale, w_bias, b_bias)
+    M, C, ldx = _rows(x)
+    cond = cond.float().contiguous() if cond.dtype != torch.float32 or not cond.is_contiguous() else cond
+    Mc, Dc, ldc = _rows(cond)
+    if Mc != M or tuple(w_scale.shape) != (C, Dc) or tuple(w_bias.shape) != (C, Dc) or b_scale.numel() != C or b_bias.numel() != C:
+        raise ValueError("cond_layer_norm: shape mismatch (cond [M, Dc], weights [C, Dc], biases [C])")
+    out = torch.empty((M, C), dtype=out_dtype or x.dtype, device=x.device)
+    with _Timed("cond_layer_norm", (8.0 + 4.0 * Dc) * M * C, _nbytes(x, out)):
+        rc = _lib.load().anemoi_b200_cond_layer_norm(_ptr(x), ldx, dtype_code(x.dtype), _ptr(cond), ldc, _ptr(_f32(w_scale)), _ptr(_f32(b_scale)),
+                                                     _ptr(_f32(w_bias)), _ptr(_f32(b_bias)), _ptr(out), C, dtype_code(out.dtype), M, C, Dc, float(eps),
+                                                     _stream())  # fmt: skip
+    _lib.check(rc, "anemoi_b200_cond_layer_norm")
+    return out

@@ -67,6 +67,13 @@ ANEMOI_API int anemoi_b200_layer_norm(const void* x, int64_t ldx, int x_dtype, c
                            int64_t ldr, int r_dtype, void* y, int64_t ldy, int y_dtype, int64_t M, int64_t groups, int64_t C,
                            float eps, void* stream);
 
+/* ConditionalLayerNorm (layers/normalization.py:34-94): y = LN(x) * (1 + cond . w_scale^T + b_scale) + (cond . w_bias^T + b_bias), the
+ * LayerNorm itself without affine.  cond : fp32 [M, ldc >= Dc] (Dc <= 32), w_scale / w_bias : fp32 [C, Dc] (the `scale` / `bias` Linear
+ * weights), b_scale / b_bias : fp32 [C].  The per-row scale and bias ([M, C] each in the reference) are formed inside the kernel. */
+ANEMOI_API int anemoi_b200_cond_layer_norm(const void* x, int64_t ldx, int x_dtype, const float* cond, int64_t ldc, const float* w_scale,
+                                const float* b_scale, const float* w_bias, const float* b_bias, void* y, int64_t ldy, int y_dtype, int64_t M,
+                                int64_t C, int64_t Dc, float eps, void* stream);
+
 /* -- Linear with fused epilogue ----------------------------------------------------------------------------
  * out[M,N] = epi( A[M,K] . W[N,K]^T ),  epi(acc) = [gelu]( acc + bias + g1[idx1[m]] + g2[idx2[m]] ) + residual
  * Replaces torch.nn.Linear (+ GELU, + residual add, + the torch.cat([x_i, x_j, e]) of conv.py:74 through the

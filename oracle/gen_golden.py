@@ -362,8 +362,31 @@ def model_cases(seed=21):
     torch.save(out, os.path.join(OUT, "model_forward.pt"))
 
 
+@torch.no_grad()
+def cond_layer_norm_case(seed=31):
+    """GraphTransformerProcessor whose LayerNorm kernel is the reference ConditionalLayerNorm (layers/normalization.py:34-94), driven by a
+    per-node conditioning tensor passed as ``cond=`` (block.py:1233-1271)."""
+    from anemoi.utils.config import DotDict
+
+    n, e, c, heads, layers, edge_dim, dc = 70, 180, 64, 4, 2, 5, 16
+    lk = DotDict({"LayerNorm": {"_target_": "anemoi.models.layers.normalization.ConditionalLayerNorm", "condition_shape": dc, "zero_init": False}})
+    torch.manual_seed(seed)
+    m = randomise(GraphTransformerProcessor(num_layers=layers, num_channels=c, num_chunks=1, num_heads=heads, mlp_hidden_ratio=4, edge_dim=edge_dim,
+                                            layer_kernels=lk, graph_attention_backend="pyg"), seed).eval()  # fmt: skip
+    ei, ea = rand_graph(n, n, e, edge_dim, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x, cond = torch.randn(n, c, generator=g), torch.randn(n, dc, generator=g)
+    y = m(x, 1, GraphShardInfo(nodes=None, edges=None), ea, ei, None, cond=cond)
+    y_other = m(x, 1, GraphShardInfo(nodes=None, edges=None), ea, ei, None, cond=cond.flip(0))
+    assert (y - y_other).abs().max() > 1e-3  # the conditioning really acts
+    torch.save({"kind": "gt_processor_cond", "cfg": dict(num_channels=c, num_layers=layers, num_heads=heads, edge_dim=edge_dim), "condition_shape": dc,
+                "sd": sd_of(m), "x": x, "cond": cond, "edge_attr": ea, "edge_index": ei, "y": y}, os.path.join(OUT, "gt_processor_condln.pt"))  # fmt: skip
+    print("gt_processor_condln", tuple(y.shape), float(y.abs().mean()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    cond_layer_norm_case()
     graph_provider_cases()
     model_cases()
     gnn_processor_case("gnn_processor_small", 100, 200, 32, 2, 3, seed=1)

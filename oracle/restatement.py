@@ -111,8 +111,12 @@ def _linear(sd: StateDict, name: str, x: Tensor) -> Tensor:
     return F.linear(x, sd[name + ".weight"], sd.get(name + ".bias"))
 
 
-def _layer_norm(sd: StateDict, name: str, x: Tensor, autocast_ln: bool = False) -> Tensor:
-    """torch.nn.LayerNorm (eps 1e-5); AutocastLayerNorm casts back to x.dtype (normalization.py:19-31)."""
+def _layer_norm(sd: StateDict, name: str, x: Tensor, autocast_ln: bool = False, cond: Optional[Tensor] = None) -> Tensor:
+    """torch.nn.LayerNorm (eps 1e-5); AutocastLayerNorm casts back to x.dtype (normalization.py:19-31); ConditionalLayerNorm
+    (normalization.py:34-94): LN without affine, times (1 + scale(cond)), plus bias(cond)."""
+    if name + ".scale.weight" in sd:
+        y = F.layer_norm(x, (x.shape[-1],), None, None, 1e-5)
+        return (y * (_linear(sd, name + ".scale", cond) + 1.0) + _linear(sd, name + ".bias", cond)).type_as(x)
     w = sd[name + ".weight"]
     y = F.layer_norm(x, (w.shape[0],), w, sd.get(name + ".bias"), 1e-5)
     return y.type_as(x) if autocast_ln else y
@@ -258,7 +262,7 @@ def gt_attention_online(q, k, v, e, row, colptr) -> Tensor:
     return out
 
 
-def _gt_core(sd, prefix, xs_n, xd_n, x_dst_skip, edge_attr, edge_index, num_heads):
+def _gt_core(sd, prefix, xs_n, xd_n, x_dst_skip, edge_attr, edge_index, num_heads, cond_dst=None):
     """layers/block.py:623-687 (get_qkve, heads reshape, conv) + projection/residual/MLP tail
     shared by :1019-1029 (mapper) and :1268-1271 (processor)."""
     n_dst = xd_n.shape[0]
@@ -276,14 +280,15 @@ def _gt_core(sd, prefix, xs_n, xd_n, x_dst_skip, edge_attr, edge_index, num_head
         k = F.layer_norm(k, (k.shape[-1],), sd[prefix + ".k_norm.weight"], None, 1e-5).type_as(k)
     att = gt_attention(q, k, v, e, edge_index, n_dst).reshape(n_dst, -1)
     out = _linear(sd, prefix + ".projection", att + x_r) + x_dst_skip
-    h = _layer_norm(sd, prefix + ".layer_norm_mlp_dst", out)
+    h = _layer_norm(sd, prefix + ".layer_norm_mlp_dst", out, cond=cond_dst)
     return mlp(sd, prefix + ".node_dst_mlp", h) + out
 
 
-def gt_processor_block(sd, prefix, x, edge_attr, edge_index, num_heads):
-    """layers/block.py:1219-1273 — returns nodes_new (edge_attr is returned unchanged by the reference)."""
-    xn = _layer_norm(sd, prefix + ".layer_norm_attention", x)
-    return _gt_core(sd, prefix, xn, xn, x, edge_attr, edge_index, num_heads)
+def gt_processor_block(sd, prefix, x, edge_attr, edge_index, num_heads, cond=None):
+    """layers/block.py:1219-1273 — returns nodes_new (edge_attr is returned unchanged by the reference); ``cond`` feeds both LayerNorms
+    when they are ConditionalLayerNorm kernels (:1233-1271)."""
+    xn = _layer_norm(sd, prefix + ".layer_norm_attention", x, cond=cond)
+    return _gt_core(sd, prefix, xn, xn, x, edge_attr, edge_index, num_heads, cond_dst=cond)
 
 
 def gt_mapper_block(sd, prefix, x_src, x_dst, edge_attr, edge_index, num_heads):
@@ -293,10 +298,10 @@ def gt_mapper_block(sd, prefix, x_src, x_dst, edge_attr, edge_index, num_heads):
     return _gt_core(sd, prefix, xs_n, xd_n, x_dst, edge_attr, edge_index, num_heads)
 
 
-def gt_processor(sd, x, edge_attr, edge_index, num_layers, num_heads, max_layers=None):
+def gt_processor(sd, x, edge_attr, edge_index, num_layers, num_heads, max_layers=None, cond=None):
     """layers/processor.py:552-626 — every layer re-projects the raw edge_attr with its own lin_edge."""
     for layer in range(num_layers if max_layers is None else min(num_layers, max_layers)):
-        x = gt_processor_block(sd, f"proc.{layer}", x, edge_attr, edge_index, num_heads)
+        x = gt_processor_block(sd, f"proc.{layer}", x, edge_attr, edge_index, num_heads, cond=cond)
     return x
 
 

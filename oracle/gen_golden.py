@@ -71,35 +71,36 @@ def randomise(m, seed):
 
 
 @torch.no_grad()
-def gnn_processor_case(name, n, e, c, layers, edge_dim, seed, mlp_implementation="mlp"):
+def gnn_processor_case(name, n, e, c, layers, edge_dim, seed, mlp_implementation="mlp", mlp_extra_layers=0):
     torch.manual_seed(seed)
     m = randomise(
-        GNNProcessor(num_channels=c, num_layers=layers, num_chunks=1, mlp_extra_layers=0, edge_dim=edge_dim, layer_kernels=None,
+        GNNProcessor(num_channels=c, num_layers=layers, num_chunks=1, mlp_extra_layers=mlp_extra_layers, edge_dim=edge_dim, layer_kernels=None,
                      mlp_implementation=mlp_implementation), seed
     ).eval()  # fmt: skip
     ei, ea = rand_graph(n, n, e, edge_dim, seed)
     x = torch.randn(n, c, generator=torch.Generator().manual_seed(seed + 1))
     y = m(x, 1, GraphShardInfo(nodes=[n], edges=None), ea, ei, None)
     torch.save(
-        {"kind": "gnn_processor", "cfg": dict(num_channels=c, num_layers=layers, edge_dim=edge_dim, mlp_implementation=mlp_implementation), "sd": sd_of(m), "x": x,
+        {"kind": "gnn_processor", "cfg": dict(num_channels=c, num_layers=layers, edge_dim=edge_dim, mlp_implementation=mlp_implementation,
+                                              mlp_extra_layers=mlp_extra_layers), "sd": sd_of(m), "x": x,
          "edge_attr": ea, "edge_index": ei, "y": y}, os.path.join(OUT, name + ".pt"))  # fmt: skip
     print(name, tuple(y.shape), float(y.abs().mean()))
 
 
 @torch.no_grad()
-def gt_processor_case(name, n, e, c, heads, layers, edge_dim, seed, qk_norm=False, sort=True, mlp_implementation="mlp"):
+def gt_processor_case(name, n, e, c, heads, layers, edge_dim, seed, qk_norm=False, sort=True, mlp_implementation="mlp", **extra):
     torch.manual_seed(seed)
     m = randomise(
         GraphTransformerProcessor(num_layers=layers, num_channels=c, num_chunks=1, num_heads=heads, mlp_hidden_ratio=4,
                                   edge_dim=edge_dim, qk_norm=qk_norm, layer_kernels=None, graph_attention_backend="pyg",
-                                  mlp_implementation=mlp_implementation), seed
+                                  mlp_implementation=mlp_implementation, **extra), seed
     ).eval()  # fmt: skip
     ei, ea = rand_graph(n, n, e, edge_dim, seed, sort=sort)
     x = torch.randn(n, c, generator=torch.Generator().manual_seed(seed + 1))
     y = m(x, 1, GraphShardInfo(nodes=None, edges=None), ea, ei, None, edges_are_dst_sorted=sort)
     torch.save(
         {"kind": "gt_processor", "cfg": dict(num_channels=c, num_layers=layers, num_heads=heads, edge_dim=edge_dim, qk_norm=qk_norm,
-                                             mlp_implementation=mlp_implementation),
+                                             mlp_implementation=mlp_implementation, **extra),
          "sorted": sort, "sd": sd_of(m), "x": x, "edge_attr": ea, "edge_index": ei, "y": y}, os.path.join(OUT, name + ".pt"))  # fmt: skip
     print(name, tuple(y.shape), float(y.abs().mean()))
 
@@ -397,6 +398,10 @@ def main():
     for kind in ("glu", "swiglu", "geglu", "reglu"):  # gated feed-forward variants (layers/mlp.py:38-94)
         gt_processor_case(f"gt_processor_{kind}", 60, 150, 64, 4, 1, 5, seed=5, mlp_implementation=kind)
     gnn_processor_case("gnn_processor_swiglu", 60, 150, 32, 1, 3, seed=6, mlp_implementation="swiglu")
+    # constructor options outside the default configs
+    gt_processor_case("gt_processor_edge_pre_mlp", 80, 190, 64, 4, 2, 7, seed=8, edge_pre_mlp=True)
+    gt_processor_case("gt_processor_attn_channels", 80, 190, 64, 4, 2, 7, seed=9, attn_channels=128)
+    gnn_processor_case("gnn_processor_extra_layers", 80, 190, 32, 2, 3, seed=10, mlp_extra_layers=1)
     mapper_cases()
     attention_conv_cases()
     integer_cases()

@@ -122,7 +122,7 @@ class GraphTransformerBaseMapper(BaseMapper):
         return x_dst
 
     def _run(self, x: PairTensor, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted,
-             keep_x_dst_sharded: bool = True) -> Tensor:  # fmt: skip
+             keep_x_dst_sharded: bool = True, cond=None) -> Tensor:  # fmt: skip
         """Single GPU, or dst-range sharded over ``model_comm_group`` (reference "edges" strategy, mapper.py:248-386):
         ``x[1]`` is then this rank's slice of the destination rows (``shard_info.dst_nodes``), ``x[0]`` either the full source
         tensor (``shard_info.src_nodes is None``) or this rank's slice (its k | v rows are all-gathered inside the block);
@@ -147,7 +147,7 @@ class GraphTransformerBaseMapper(BaseMapper):
         dt = Fn.compute_dtype(*x)
         x_src, x_dst = self.pre_process(x, dt)
         (_, x_dst_out), _ = self.proc((x_src, x_dst), edge_attr, edge_index, shard_info, batch_size, (x_src.shape[0], x_dst.shape[0]),
-                                      model_comm_group if world > 1 else None)  # fmt: skip
+                                      model_comm_group if world > 1 else None, cond=cond)  # fmt: skip
         out = self.post_process(x_dst_out, dt)
         if world > 1 and not keep_x_dst_sharded:
             from ..distributed.graph import gather_rows
@@ -181,7 +181,7 @@ class GraphTransformerForwardMapper(GraphTransformerBaseMapper):
         edges_are_dst_sorted: bool = True,
         **kwargs,
     ) -> PairTensor:
-        return x[0], self._run(x, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted, keep_x_dst_sharded)
+        return x[0], self._run(x, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted, keep_x_dst_sharded, cond=kwargs.get("cond"))
 
 
 class GraphTransformerBackwardMapper(GraphTransformerBaseMapper):
@@ -218,7 +218,7 @@ class GraphTransformerBackwardMapper(GraphTransformerBaseMapper):
         edges_are_dst_sorted: bool = True,
         **kwargs,
     ) -> Tensor:
-        return self._run(x, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted, keep_x_dst_sharded)
+        return self._run(x, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted, keep_x_dst_sharded, cond=kwargs.get("cond"))
 
 
 # ------------------------------------------------------------------------------------------------------------

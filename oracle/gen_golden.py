@@ -380,7 +380,18 @@ def cond_layer_norm_case(seed=31):
     y = m(x, 1, GraphShardInfo(nodes=None, edges=None), ea, ei, None, cond=cond)
     y_other = m(x, 1, GraphShardInfo(nodes=None, edges=None), ea, ei, None, cond=cond.flip(0))
     assert (y - y_other).abs().max() > 1e-3  # the conditioning really acts
-    torch.save({"kind": "gt_processor_cond", "cfg": dict(num_channels=c, num_layers=layers, num_heads=heads, edge_dim=edge_dim), "condition_shape": dc,
+    # the forward mapper with (cond_src, cond_dst) (block.py:978-1023)
+    n_src, n_dst, in_src, in_dst = 90, 70, 10, 6
+    torch.manual_seed(seed + 2)
+    mm = randomise(GraphTransformerForwardMapper(in_channels_src=in_src, in_channels_dst=in_dst, hidden_dim=c, num_chunks=1, num_heads=heads,
+                                                 mlp_hidden_ratio=4, edge_dim=edge_dim, layer_kernels=lk, graph_attention_backend="pyg"), seed).eval()  # fmt: skip
+    mei, mea = rand_graph(n_src, n_dst, 200, edge_dim, seed + 3)
+    xs, xd = torch.randn(n_src, in_src, generator=g), torch.randn(n_dst, in_dst, generator=g)
+    cs, cdst = torch.randn(n_src, dc, generator=g), torch.randn(n_dst, dc, generator=g)
+    _, yd = mm((xs, xd), 1, BipartiteGraphShardInfo(src_nodes=None, dst_nodes=None, edges=None), mea, mei, None, cond=(cs, cdst))
+    mapper = {"cfg": dict(in_channels_src=in_src, in_channels_dst=in_dst, hidden_dim=c, num_heads=heads, edge_dim=edge_dim), "sd": sd_of(mm),
+              "x_src": xs, "x_dst": xd, "cond_src": cs, "cond_dst": cdst, "edge_attr": mea, "edge_index": mei, "y_dst": yd}  # fmt: skip
+    torch.save({"kind": "gt_processor_cond", "mapper": mapper, "cfg": dict(num_channels=c, num_layers=layers, num_heads=heads, edge_dim=edge_dim), "condition_shape": dc,
                 "sd": sd_of(m), "x": x, "cond": cond, "edge_attr": ea, "edge_index": ei, "y": y}, os.path.join(OUT, "gt_processor_condln.pt"))  # fmt: skip
     print("gt_processor_condln", tuple(y.shape), float(y.abs().mean()))
 

@@ -291,11 +291,12 @@ def gt_processor_block(sd, prefix, x, edge_attr, edge_index, num_heads, cond=Non
     return _gt_core(sd, prefix, xn, xn, x, edge_attr, edge_index, num_heads, cond_dst=cond)
 
 
-def gt_mapper_block(sd, prefix, x_src, x_dst, edge_attr, edge_index, num_heads):
-    """layers/block.py:963-1029 — separate LayerNorm for src (:940) and dst; update_src_nodes=False."""
-    xs_n = _layer_norm(sd, prefix + ".layer_norm_attention_src", x_src)
-    xd_n = _layer_norm(sd, prefix + ".layer_norm_attention", x_dst)
-    return _gt_core(sd, prefix, xs_n, xd_n, x_dst, edge_attr, edge_index, num_heads)
+def gt_mapper_block(sd, prefix, x_src, x_dst, edge_attr, edge_index, num_heads, cond=None):
+    """layers/block.py:963-1029 — separate LayerNorm for src (:940) and dst; update_src_nodes=False; ``cond`` = (cond_src, cond_dst) (:978-980)."""
+    cs, cd = cond if cond is not None else (None, None)
+    xs_n = _layer_norm(sd, prefix + ".layer_norm_attention_src", x_src, cond=cs)
+    xd_n = _layer_norm(sd, prefix + ".layer_norm_attention", x_dst, cond=cd)
+    return _gt_core(sd, prefix, xs_n, xd_n, x_dst, edge_attr, edge_index, num_heads, cond_dst=cd)
 
 
 def gt_processor(sd, x, edge_attr, edge_index, num_layers, num_heads, max_layers=None, cond=None):
@@ -305,11 +306,11 @@ def gt_processor(sd, x, edge_attr, edge_index, num_layers, num_heads, max_layers
     return x
 
 
-def gt_forward_mapper(sd, x_src, x_dst, edge_attr, edge_index, num_heads):
+def gt_forward_mapper(sd, x_src, x_dst, edge_attr, edge_index, num_heads, cond=None):
     """layers/mapper.py:335-386, 480-597 — returns (x_src unchanged, x_dst); chunking does not change values."""
     xs = _linear(sd, "emb_nodes_src", x_src)
     xd = _linear(sd, "emb_nodes_dst", x_dst)
-    return x_src, gt_mapper_block(sd, "proc", xs, xd, edge_attr, edge_index, num_heads)
+    return x_src, gt_mapper_block(sd, "proc", xs, xd, edge_attr, edge_index, num_heads, cond=cond)
 
 
 def gt_backward_mapper(sd, x_src, x_dst, edge_attr, edge_index, num_heads):

@@ -68,3 +68,41 @@ def test_cond_layer_norm_kernel(dt, M, C, Dc):
     assert y.dtype == dt
     tol = 2e-5 if dt == torch.float32 else 2**-7
     assert ((y.float().cpu() - ref.detach()).abs() <= tol * ref.detach().abs().clamp_min(1.0)).all()
+
+
+def _build_mapper(g):
+    from anemoi_core_b200.layers import GraphTransformerForwardMapper
+
+    lk = {"LayerNorm": {"_target_": "anemoi_core_b200.layers.normalization.ConditionalLayerNorm", "condition_shape": g["condition_shape"],
+                        "zero_init": False}}  # fmt: skip
+    m = GraphTransformerForwardMapper(num_chunks=1, mlp_hidden_ratio=4, layer_kernels=lk, **g["mapper"]["cfg"]).eval()
+    assert sorted(m.state_dict().keys()) == sorted(g["mapper"]["sd"].keys())
+    m.load_state_dict(g["mapper"]["sd"], strict=True)
+    return m
+
+
+def test_oracle_mapper_with_cond(golden):
+    g = golden("gt_processor_condln")
+    mp = g["mapper"]
+    _, yd = R.gt_forward_mapper(mp["sd"], mp["x_src"], mp["x_dst"], mp["edge_attr"], mp["edge_index"], mp["cfg"]["num_heads"],
+                                cond=(mp["cond_src"], mp["cond_dst"]))  # fmt: skip
+    torch.testing.assert_close(yd, mp["y_dst"], atol=2e-5, rtol=1e-5)
+    _build_mapper(g)  # constructs with the reference state_dict keys on CPU
+
+
+@pytest.mark.gpu
+def test_gt_forward_mapper_with_cond(golden):
+    from anemoi_core_b200.distributed.shapes import BipartiteGraphShardInfo
+
+    g = golden("gt_processor_condln")
+    mp = g["mapper"]
+    m = _build_mapper(g).cuda()
+    args = ((mp["x_src"].cuda(), mp["x_dst"].cuda()), 1, BipartiteGraphShardInfo(), mp["edge_attr"].cuda(), mp["edge_index"].cuda())
+    cond = (mp["cond_src"].cuda(), mp["cond_dst"].cuda())
+    with torch.no_grad():
+        _, y32 = m(*args, cond=cond)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            _, y16 = m(*args, cond=cond)
+    ref = mp["y_dst"]
+    assert (y32.cpu() - ref).abs().max() <= 1e-4 * ref.abs().max()
+    assert ((y16.float().cpu() - ref).norm() / ref.norm()) <= 2e-2

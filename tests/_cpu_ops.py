@@ -1,0 +1,198 @@
+"""TEST INFRASTRUCTURE ONLY — a plain-PyTorch fp32 stand-in for ``anemoi_core_b200.ops`` so that the multi-process HOST logic of the
+sharded forward (edge sharding, halo plans and exchanges, gathers, relabelled CSR plans, shard bookkeeping across ranks) can be exercised
+end to end under Gloo on a machine without a GPU.  It is never imported by the package; ``install()`` monkey-patches the ``ops`` module of the
+current (test) process.  The kernels themselves are validated on the GPU (``-m gpu``) against the oracle; these tests only compare a sharded
+run with a single-rank run of the SAME stand-in arithmetic, so the stand-in does not need to be (and is not) a second oracle.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+
+@dataclass
+class _CSR:
+    n_src: int
+    n_dst: int
+    n_edges: int
+    colptr: Tensor
+    colptr32: Tensor
+    src32: Tensor
+    dst32: Tensor
+
+
+def build_csr(edge_index: Tensor, n_src: int, n_dst: int, validate: bool = True) -> _CSR:
+    src, dst = edge_index[0], edge_index[1]
+    if validate and edge_index.shape[1]:
+        if bool((dst[1:] < dst[:-1]).any()):
+            raise ValueError("edge_index is not sorted by destination")
+        if int(src.min()) < 0 or int(src.max()) >= n_src or int(dst.min()) < 0 or int(dst.max()) >= n_dst:
+            raise ValueError("edge_index out of range")
+    colptr = torch.zeros(n_dst + 1, dtype=torch.int64)
+    colptr[1:] = torch.cumsum(torch.bincount(dst, minlength=n_dst), 0)
+    return _CSR(n_src, n_dst, edge_index.shape[1], colptr, colptr.int(), src.int().contiguous(), dst.int().contiguous())
+
+
+def _block_stats(y: Tensor) -> Tensor:
+    M, N = y.shape
+    P = (N + 63) // 64
+    yp = torch.zeros(M, P * 64)
+    yp[:, :N] = y.float()
+    yp = yp.view(M, P, 64)
+    return torch.stack([yp.sum(-1), (yp * yp).sum(-1)], -1)
+
+
+def partial_stats_buffer(out_rows: int, out_cols: int, device) -> Tensor:
+    return torch.empty((out_rows, (out_cols + 63) // 64, 2), dtype=torch.float32)
+
+
+def linear(a, weight, bias=None, gelu=False, residual=None, gather1=None, gather2=None, out=None, out_dtype=None, ln_stats=None, ln_colsum=None,
+           ln_dim=0, ln_eps=0.0, stats_out=None):  # fmt: skip
+    acc = a.float() @ weight.float().t()
+    if ln_stats is not None:
+        if ln_stats.dim() == 3:
+            s, q = ln_stats[..., 0].sum(1), ln_stats[..., 1].sum(1)
+            mean = s / ln_dim
+            rstd = (torch.clamp(q / ln_dim - mean * mean, min=0.0) + ln_eps).rsqrt()
+        else:
+            mean, rstd = ln_stats[:, 0], ln_stats[:, 1]
+        acc = rstd[:, None] * (acc - mean[:, None] * ln_colsum[None, :])
+    if bias is not None:
+        acc = acc + bias
+    for g in (gather1, gather2):
+        if g is not None:
+            acc = acc + g[0][g[1].long(), : acc.shape[1]]
+    if gelu:
+        acc = F.gelu(acc)
+    if residual is not None:
+        acc = acc + residual.float()
+    res = acc.to(out.dtype if out is not None else (out_dtype or a.dtype))
+    if out is not None:
+        out.copy_(res)
+        res = out
+    if stats_out is not None:
+        stats_out.copy_(_block_stats(res))
+    return res
+
+
+def layer_norm(x, weight, bias, eps=1e-5, residual=None, out=None, out_dtype=None, groups=1):
+    M, W = x.shape
+    C = W // groups
+    y = F.layer_norm(x.float().reshape(M, groups, C), (C,), weight, bias, eps).reshape(M, W)
+    if residual is not None:
+        y = y + residual.float()
+    y = y.to(out.dtype if out is not None else (out_dtype or x.dtype))
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def row_stats(x, eps=1e-5):
+    xf = x.float()
+    return torch.stack([xf.mean(1), (xf.var(1, unbiased=False) + eps).rsqrt()], 1)
+
+
+def gt_attention(q, k, v, csr, heads, e_proj=None, edge_attr=None, w_edge=None, b_edge=None, qw=None, abar=None, dp=0, add=None, out=None):
+    n_dst, C = q.shape
+    Ch = C // heads
+    src, dst = csr.src32.long(), csr.dst32.long()
+    qh, kh, vh = q.float().view(n_dst, heads, Ch), k.float().view(-1, heads, Ch), v.float().view(-1, heads, Ch)
+    ke, ve = kh[src], vh[src]
+    folded = edge_attr is not None and qw is not None
+    if e_proj is not None:
+        e = e_proj.float().view(-1, heads, Ch)
+        ke, ve = ke + e, ve + e
+    elif edge_attr is not None and not folded:
+        d = w_edge.shape[1]
+        e = (edge_attr[:, :d] @ w_edge.t() + (b_edge if b_edge is not None else 0.0)).view(-1, heads, Ch)
+        ke, ve = ke + e, ve + e
+    score = (qh[dst] * ke).sum(-1) / (Ch**0.5)
+    if folded:
+        d = min(dp, edge_attr.shape[1])
+        qwh = qw.float()[:, : heads * dp].reshape(n_dst, heads, dp)[:, :, :d]
+        score = score + (qwh[dst] * edge_attr[:, None, :d]).sum(-1) / (Ch**0.5)
+    mx = torch.full((n_dst, heads), -float("inf")).scatter_reduce(0, dst[:, None].expand(-1, heads), score, "amax", include_self=True)
+    w = torch.exp(score - mx[dst])
+    den = torch.zeros(n_dst, heads).index_add_(0, dst, w)
+    alpha = w / den[dst]
+    res = torch.zeros(n_dst, heads, Ch).index_add_(0, dst, alpha[..., None] * ve)
+    has = torch.zeros(n_dst, dtype=torch.bool)
+    has[dst] = True
+    if folded:
+        if b_edge is not None:
+            res = res + has[:, None, None] * b_edge.view(heads, Ch)
+        ab = torch.zeros(n_dst, heads, dp)
+        ab[:, :, :d] = torch.zeros(n_dst, heads, d).index_add_(0, dst, alpha[..., None] * edge_attr[:, None, :d])
+        abar[:, : heads * dp] = ab.reshape(n_dst, heads * dp).to(abar.dtype)
+    res = res.reshape(n_dst, C)
+    if add is not None:
+        res = res + add.float()
+    res = res.to(q.dtype)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def graphconv_ln_aggregate(h, weight, bias, e, csr, eps=1e-5, out=None):
+    e_new = (F.layer_norm(h.float(), (h.shape[1],), weight, bias, eps) + e.float()).to(h.dtype)
+    agg = torch.zeros(csr.n_dst, h.shape[1]).index_add_(0, csr.dst32.long(), e_new.float()).to(h.dtype)
+    if out is not None:
+        out.copy_(agg)
+        agg = out
+    return e_new, agg
+
+
+def cast_pad(x, dtype, k_pad=None, idx=None, out=None):
+    src = x if idx is None else x[idx.long()]
+    k_pad = src.shape[1] if k_pad is None else k_pad
+    res = torch.zeros((src.shape[0], k_pad), dtype=dtype)
+    res[:, : src.shape[1]] = src.to(dtype)
+    if out is not None:
+        out[:, :k_pad].copy_(res)
+        return out
+    return res
+
+
+def add(a, b, out_dtype=None):
+    return (a.float() + b.float()).to(out_dtype or a.dtype)
+
+
+def assemble_input(x, attrs, out_dtype, k_pad=None):
+    b, t, e, g, v = x.shape
+    rows = x.permute(0, 2, 3, 1, 4).reshape(b * e * g, t * v)
+    if attrs is not None:
+        rows = torch.cat([rows, attrs.float().repeat(rows.shape[0] // attrs.shape[0], 1)], -1)
+    out = torch.zeros((rows.shape[0], k_pad or rows.shape[1]), dtype=out_dtype)
+    out[:, : rows.shape[1]] = rows.to(out_dtype)
+    return out
+
+
+def assemble_output(dec, x, batch, ensemble, n_step_output, step=-1, skip_src=None, bound=None):
+    g = dec.shape[0] // (batch * ensemble)
+    y = dec.float().reshape(batch, ensemble, g, n_step_output, -1).permute(0, 3, 1, 2, 4).clone()
+    if x is not None and skip_src is not None:
+        sel = skip_src >= 0
+        y[..., sel] += x[:, step].unsqueeze(1)[..., skip_src[sel].long()]
+    if bound is not None:
+        y[..., bound == 1] = F.relu(y[..., bound == 1])
+        y[..., bound == 2] = F.leaky_relu(y[..., bound == 2])
+    return y
+
+
+def install() -> None:
+    """Replace the CUDA entry points of ``anemoi_core_b200.ops`` in THIS process (a spawned Gloo test worker)."""
+    import anemoi_core_b200.layers._functional as Fn
+    from anemoi_core_b200 import ops
+
+    for name in ("build_csr", "linear", "layer_norm", "row_stats", "gt_attention", "graphconv_ln_aggregate", "cast_pad", "add", "partial_stats_buffer",
+                 "assemble_input", "assemble_output"):
+        setattr(ops, name, globals()[name])
+    ops._need_cuda = lambda *a, **k: None
+    torch.cuda.is_current_stream_capturing = lambda: False  # csr_for asks; there is no CUDA runtime here
+    assert Fn.ops is ops

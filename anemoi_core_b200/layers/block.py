@@ -116,14 +116,16 @@ class GraphConvMapperBlock(GraphConvBaseBlock):
         **layer_kwargs,
     ) -> tuple[PairTensor, Tensor]:
         Fn.forward_only_guard(self)
-        if group_size(model_comm_group) > 1:
-            raise NotImplementedError("sharded GraphConv mappers: run the mappers replicated or with model_comm_group=None")
         x_src, x_dst = x
         dt = Fn.compute_dtype(x_src, x_dst, edge_attr)
         C = self.in_channels
-        csr = Fn.csr_for(edge_index, x_src.shape[0], x_dst.shape[0])
+        # sharded (block.py:451-470): x_dst and the edges are this rank's (local dst ids, global src ids); every source row is needed
+        src_all = x_src
+        if group_size(model_comm_group) > 1 and shard_info is not None and shard_info.src_is_sharded():
+            src_all = gather_rows(x_src, shard_info.src_nodes, model_comm_group)
+        csr = Fn.csr_for(edge_index, src_all.shape[0], x_dst.shape[0])
         agg_buf = torch.empty((x_dst.shape[0], 2 * C), dtype=dt, device=x_dst.device)
-        _, edges_new = self.conv.run(x_src, x_dst, edge_attr, csr, dt, out=agg_buf[:, C:])
+        _, edges_new = self.conv.run(src_all, x_dst, edge_attr, csr, dt, out=agg_buf[:, C:])
         dst_new = self._node_update(x_dst, agg_buf, dt)
         src_new = x_src
         if self.update_src_nodes:  # block.py:475 — the same node_mlp on cat[x_src, x_src]

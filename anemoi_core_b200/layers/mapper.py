@@ -57,14 +57,6 @@ class BaseMapper(nn.Module):
         self.layer_factory = load_layer_kernels(layer_kernels)
         self._pack = Fn.WeightPack()
 
-    @staticmethod
-    def _single_rank_only(model_comm_group) -> None:
-        if group_size(model_comm_group) > 1:
-            raise NotImplementedError(
-                "GNN (GraphConv) mappers run replicated (model_comm_group=None) in this build; the GraphTransformer mappers and both "
-                "processors implement the dst-range sharding (DESIGN.md, multi-GPU)"
-            )
-
 
 # ------------------------------------------------------------------------------------------------------------
 # GraphTransformer mappers
@@ -256,15 +248,47 @@ class GNNBaseMapper(BaseMapper):
     def post_process(self, x_dst: Tensor, dt: torch.dtype) -> Tensor:
         return x_dst
 
-    def _run(self, x: PairTensor, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted) -> PairTensor:
+    def _run(self, x: PairTensor, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted,
+             keep_x_dst_sharded: bool = False) -> PairTensor:  # fmt: skip
+        """Single GPU, or sharded over ``model_comm_group`` like the reference (mapper.py:760-835): src and dst rows are sharded (a replicated
+        input is cut to this rank's balanced slice, ``ensure_sharded``), the edges are the ones into the local dst rows, the block all-gathers
+        the embedded src rows (``sync_tensor``, block.py:451); returns the LOCAL src shard and the dst rows (gathered unless
+        ``keep_x_dst_sharded``)."""
         Fn.forward_only_guard(self)
-        self._single_rank_only(model_comm_group)
         edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
-        dt = Fn.compute_dtype(*x, edge_attr)
+        world = group_size(model_comm_group)
+        x_src, x_dst = x
+        if world > 1:
+            from ..distributed.balanced_partition import get_balanced_partition_sizes
+            from ..distributed.graph import shard_rows
+            from .processor import _localise_presharded_edges
+            from .processor import _shard_edges_by_dst
+
+            if shard_info is None:
+                shard_info = BipartiteGraphShardInfo()
+            src_sizes, dst_sizes = shard_info.src_nodes, shard_info.dst_nodes
+            if src_sizes is None:  # replicated input: keep this rank's balanced slice
+                src_sizes = get_balanced_partition_sizes(x_src.shape[0], world)
+                x_src = shard_rows(x_src, src_sizes, model_comm_group)
+            if dst_sizes is None:
+                dst_sizes = get_balanced_partition_sizes(x_dst.shape[0], world)
+                x_dst = shard_rows(x_dst, dst_sizes, model_comm_group)
+            if shard_info.edges_are_sharded():
+                edge_index, edge_sizes = _localise_presharded_edges(edge_index, dst_sizes, model_comm_group), shard_info.edges
+            else:
+                edge_attr, edge_index, edge_sizes = _shard_edges_by_dst(edge_attr, edge_index, sum(dst_sizes), sum(src_sizes), model_comm_group,
+                                                                        relabel_dst=True, dst_splits=dst_sizes)  # fmt: skip
+            shard_info = BipartiteGraphShardInfo(src_nodes=src_sizes, dst_nodes=dst_sizes, edges=edge_sizes)
+        dt = Fn.compute_dtype(x_src, x_dst, edge_attr)
         e = self.emb_edges.run(edge_attr, dt)
-        x_src, x_dst = self.pre_process(x, dt)
-        (x_src, x_dst), _ = self.proc((x_src, x_dst), e, edge_index, shard_info, None)
-        return x_src, self.post_process(x_dst, dt)
+        x_src, x_dst = self.pre_process((x_src, x_dst), dt)
+        (x_src, x_dst), _ = self.proc((x_src, x_dst), e, edge_index, shard_info, model_comm_group if world > 1 else None)
+        out = self.post_process(x_dst, dt)
+        if world > 1 and not keep_x_dst_sharded:
+            from ..distributed.graph import gather_rows
+
+            out = gather_rows(out, shard_info.dst_nodes, model_comm_group)
+        return x_src, out
 
 
 class GNNForwardMapper(GNNBaseMapper):
@@ -291,7 +315,7 @@ class GNNForwardMapper(GNNBaseMapper):
         edges_are_dst_sorted: bool = True,
         **kwargs,
     ) -> PairTensor:
-        return self._run(x, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted)
+        return self._run(x, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted, keep_x_dst_sharded)
 
 
 class GNNBackwardMapper(GNNBaseMapper):
@@ -317,4 +341,4 @@ class GNNBackwardMapper(GNNBaseMapper):
         edges_are_dst_sorted: bool = True,
         **kwargs,
     ) -> Tensor:
-        return self._run(x, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted)[1]
+        return self._run(x, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted, keep_x_dst_sharded)[1]

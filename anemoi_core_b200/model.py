@@ -68,6 +68,15 @@ class EncProcDec(nn.Module):
                 y_local = ops.add(y_local, x_local)  # latent skip (:295-296)
                 return self.decoder((y_local, x_grid_l), 1, BipartiteGraphShardInfo(src_nodes=mesh_shards, dst_nodes=grid_shards), graph["dec_attr"],
                                     graph["dec_index"], g, keep_x_dst_sharded=False)  # fmt: skip
+            if self.kind == "gnn" and grid_shards is not None:
+                # GNN mappers sharded like the reference (mapper.py:760-835): grid and mesh rows sharded, the block all-gathers the embedded sources
+                x_grid_l, x_mesh_l = shard_rows(x_grid, grid_shards, g), shard_rows(x_mesh, mesh_shards, g)
+                x_data_l, x_local = self.encoder((x_grid_l, x_mesh_l), 1, BipartiteGraphShardInfo(src_nodes=grid_shards, dst_nodes=mesh_shards),
+                                                 graph["enc_attr"], graph["enc_index"], g, keep_x_dst_sharded=True)  # fmt: skip
+                y_local = self.processor(x_local, 1, GraphShardInfo(nodes=mesh_shards), graph["proc_attr"], graph["proc_index"], g)
+                y_local = ops.add(y_local, x_local)
+                return self.decoder((y_local, x_data_l), 1, BipartiteGraphShardInfo(src_nodes=mesh_shards, dst_nodes=grid_shards), graph["dec_attr"],
+                                    graph["dec_index"], g, keep_x_dst_sharded=False)  # fmt: skip
             bi = BipartiteGraphShardInfo()
             x_data_latent, x_latent = self.encoder((x_grid, x_mesh), 1, bi, graph["enc_attr"], graph["enc_index"])
             x_local = shard_rows(x_latent, mesh_shards, g)

@@ -102,6 +102,16 @@ def check_enc_proc_dec(rank, world):
     full = gnn(xg, xm, gr)
     got = gnn(xg, xm, gr, dist.group.WORLD, get_balanced_partition_sizes(n_mesh, world), None)  # GNN mappers replicated, processor sharded
     _close(got, full, "EncProcDec gnn")
+    got = gnn(xg, xm, gr, dist.group.WORLD, get_balanced_partition_sizes(n_mesh, world), get_balanced_partition_sizes(n_grid, world))
+    _close(got, full, "EncProcDec gnn, sharded GNN mappers")
+    # the mappers alone, replicated inputs cut inside (ensure_sharded) and edges pre-sharded by nobody
+    from anemoi_core_b200.distributed.graph import gather_rows
+    from anemoi_core_b200.distributed.shapes import BipartiteGraphShardInfo
+
+    src_full, dst_full = gnn.encoder((xg, xm), 1, BipartiteGraphShardInfo(), gr["enc_attr"], gr["enc_index"])
+    src_l, dst_g = gnn.encoder((xg, xm), 1, BipartiteGraphShardInfo(), gr["enc_attr"], gr["enc_index"], dist.group.WORLD, keep_x_dst_sharded=False)
+    _close(dst_g, dst_full, "GNNForwardMapper dst (gathered)")
+    _close(gather_rows(src_l, get_balanced_partition_sizes(n_grid, world), dist.group.WORLD), src_full, "GNNForwardMapper src shard")
 
 
 def check_model_forward(rank, world):

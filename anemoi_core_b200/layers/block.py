@@ -308,6 +308,10 @@ class GraphTransformerBaseBlock(nn.Module):
         else:
             w_e = self._pack.get(("w_edge",), [self.lin_edge.weight], lambda: self.lin_edge.weight.detach().float().contiguous())
             att = ops.gt_attention(q, k, v, csr, H, edge_attr=edge_attr_p, w_edge=w_e, b_edge=b_e, add=x_r)
+        return self._project_mlp(att, x_skip, dt, fold, want_stats, cond)
+
+    def _project_mlp(self, att: Tensor, x_skip: Tensor, dt: torch.dtype, fold: bool, want_stats: bool, cond: Optional[Tensor]) -> Tensor:
+        """projection (+ skip) -> LayerNorm -> MLP (+ residual) on the attention output ``att`` (``[att + self | abar]`` in the folded form)."""
         skip = x_skip if x_skip.dtype in Fn.SUPPORTED else x_skip.float()
         wp = self._proj_weight(dt, fold)
         # the projection epilogue also produces the row statistics of its output for layer_norm_mlp_dst (folded into the MLP's first GEMM),
@@ -347,6 +351,8 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
         if world == 1:
             csr = Fn.csr_for(edge_index, x.shape[0], x.shape[0])
             return self._attend_project(x, ln, None, None, dst_layers, ea, csr, x, dt, want_stats=True, cond=cond), edge_attr
+        if self.shard_strategy == "heads":
+            return self._forward_heads(x, ln, ea, edge_index, shard_info, model_comm_group, dt, cond), edge_attr
         # edges strategy (block.py:1120-1183): each rank owns a dst range and needs the k | v rows of the source nodes its edges name
         if self.qk_norm and not HALO_EXCHANGE:
             raise NotImplementedError("qk_norm with the all-gather form of the sharded processor (use the halo exchange)")
@@ -374,6 +380,53 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
         out = self._attend_project(x, ln, table[:, :A], table[:, A:], [self.lin_self], ea, csr, x, dt, dst_buf=buf, want_stats=True,
                                    k_prenormed=True, cond=cond)  # fmt: skip
         return out, edge_attr
+
+
+    def _forward_heads(self, x: Tensor, ln: nn.Module, ea: Tensor, edge_index: Tensor, shard_info, group, dt: torch.dtype, cond) -> Tensor:
+        """"heads" (Ulysses) strategy (block.py:689-759, 1185-1217): nodes are sharded outside the attention, heads inside it.  The local
+        q | k | v | qw rows of every rank are exchanged so that each rank holds ALL nodes for its H / P heads, attention runs over the full
+        graph for those heads, and a second exchange brings every rank the rows it owns for all heads.  ``edge_index`` / ``ea`` are the FULL
+        dst-sorted edge list and prepared attributes (the processor does not shard edges in this mode)."""
+        from ..distributed.graph import _exchange
+        from ..distributed.graph import group_rank
+
+        A, H, Ch = self.attn_channels, self.num_heads, self.out_channels_conv
+        P, me = group_size(group), group_rank(group)
+        sizes = list(shard_info.nodes)
+        n_l, N = x.shape[0], sum(sizes)
+        if H % P:
+            raise ValueError(f"heads strategy: num_heads ({H}) must be divisible by the model group size ({P})")
+        if not self._use_fold(dt) or not ops.attention_fold_supported(A // P, H // P, dt, self.lin_edge.weight.shape[1]):
+            raise NotImplementedError("heads strategy: implemented for shapes the folded lin_edge attention kernel handles")
+        Hl = H // P
+        d, dp, hdp = self._fold_dims()
+        buf = self._dst_gemm(x, ln, [self.lin_query, self.lin_key, self.lin_value, self.lin_self], dt, cond=cond)  # q | k | v | self | qw
+        q, k, v, x_r = buf[:, :A], buf[:, A : 2 * A], buf[:, 2 * A : 3 * A], buf[:, 3 * A : 4 * A]
+        if self.qk_norm:  # per row and head: done by the owner of the rows, before the exchange
+            for t, norm in ((q, self.q_norm), (k, self.k_norm)):
+                ops.layer_norm(t, self._pack.f32(norm.weight), self._pack.f32(getattr(norm, "bias", None)), norm.eps, out=t, groups=H)
+            qw = ops.linear(q, self._qw_blockdiag(dt))[:, : H * dp]
+        else:
+            qw = buf[:, 4 * A : 4 * A + H * dp]
+        # [n_l, H, *] -> per destination rank r the columns of its heads: q | k | v | qw
+        W = Hl * (3 * Ch + dp)
+        parts = [t.reshape(n_l, P, -1) for t in (q, k, v, qw)]
+        send = torch.cat(parts, dim=2).permute(1, 0, 2).reshape(P * n_l, W).contiguous()
+        allrows = _exchange(send, [n_l] * P, sizes, group)  # rows in global node order (rank r's block = its node range)
+        qa, ka, va = allrows[:, : Hl * Ch], allrows[:, Hl * Ch : 2 * Hl * Ch], allrows[:, 2 * Hl * Ch : 3 * Hl * Ch]
+        csr = Fn.csr_for(edge_index, N, N)
+        out_h = torch.empty((N, Hl * (Ch + dp)), dtype=dt, device=x.device)
+        b_e = self._pack.f32(self.lin_edge.bias)
+        ops.gt_attention(qa, ka, va, csr, Hl, edge_attr=ea, b_edge=None if b_e is None else b_e[me * Hl * Ch : (me + 1) * Hl * Ch],
+                         qw=allrows[:, 3 * Hl * Ch :], abar=out_h[:, Hl * Ch :], dp=dp, out=out_h[:, : Hl * Ch])  # fmt: skip
+        back = _exchange(out_h, sizes, [n_l] * P, group).reshape(P, n_l, Hl * (Ch + dp))  # [source rank = head group, local row, att | abar]
+        att = torch.empty((n_l, A + hdp), dtype=dt, device=x.device)
+        if hdp != H * dp:
+            att[:, A + H * dp :].zero_()
+        att_h = back[:, :, : Hl * Ch].permute(1, 0, 2).reshape(n_l, A)
+        ops.cast_pad(ops.add(att_h.contiguous(), x_r), dt, out=att[:, :A])  # + self term (fused into the kernel in the other strategies)
+        ops.cast_pad(back[:, :, Hl * Ch :].permute(1, 0, 2).reshape(n_l, H * dp).contiguous(), dt, out=att[:, A : A + H * dp])
+        return self._project_mlp(att, x, dt, True, True, cond)
 
 
 class GraphTransformerMapperBlock(GraphTransformerBaseBlock):

@@ -181,8 +181,6 @@ class GraphTransformerProcessor(BaseProcessor):
                          layer_kernels=layer_kernels, **kwargs)  # fmt: skip
         if shard_strategy not in ("edges", "heads"):
             raise AssertionError(f"Invalid shard strategy '{shard_strategy}' for {self.__class__.__name__}. Supported strategies are 'edges' and 'heads'.")
-        if shard_strategy == "heads":
-            raise NotImplementedError("shard_strategy='heads' (Ulysses all-to-all) is not implemented; use 'edges' (SURVEY.md §2.4)")
         self.shard_strategy = shard_strategy
         self.build_layers(
             GraphTransformerProcessorBlock,
@@ -218,10 +216,13 @@ class GraphTransformerProcessor(BaseProcessor):
         n_nodes = sum(shard_info.nodes) if shard_info.nodes_are_sharded() else x.shape[0]
         if not shard_info.edges_are_sharded():
             edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
-            if group_size(model_comm_group) > 1:
+            if group_size(model_comm_group) > 1 and self.shard_strategy == "edges":
                 # local dst rows only: dst relabelled to the local range (src ids stay global, sources are all-gathered per layer)
                 edge_attr, edge_index, edge_sizes = _shard_edges_by_dst(edge_attr, edge_index, n_nodes, n_nodes, model_comm_group, relabel_dst=True)
                 shard_info = GraphShardInfo(nodes=shard_info.nodes, edges=edge_sizes)
+            # "heads": every rank attends over the FULL edge list for its heads (block._forward_heads), nothing to shard here
+        elif group_size(model_comm_group) > 1 and self.shard_strategy == "heads":
+            raise NotImplementedError("shard_strategy='heads' needs the full dst-sorted edge list (graph provider: get_edges(shard_edges=False))")
         elif group_size(model_comm_group) > 1:
             edge_index = _localise_presharded_edges(edge_index, shard_info.nodes, model_comm_group)
         shared_edges = None

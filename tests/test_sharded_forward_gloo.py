@@ -81,6 +81,31 @@ def check_processors(rank, world):
         _close(gather_rows(local, sizes, group), full, kind)
 
 
+def check_heads_strategy(rank, world):
+    """shard_strategy="heads" (Ulysses, block.py:689-759): nodes sharded outside the attention, heads inside; full edge list on every rank."""
+    from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
+    from anemoi_core_b200.distributed.graph import gather_rows
+    from anemoi_core_b200.distributed.graph import shard_rows
+    from anemoi_core_b200.distributed.shapes import GraphShardInfo
+    from anemoi_core_b200.layers import GraphTransformerProcessor
+
+    n, e, d = 101, 620, 5
+    ei, ea = _graph(n, n, e, d, seed=7)
+    sizes = get_balanced_partition_sizes(n, world)
+    group = dist.group.WORLD
+    for qk_norm in (False, True):
+        torch.manual_seed(3)
+        kw = dict(num_layers=2, num_channels=64, num_chunks=1, num_heads=4, mlp_hidden_ratio=2, edge_dim=d, qk_norm=qk_norm)
+        single = GraphTransformerProcessor(**kw).eval()
+        heads = GraphTransformerProcessor(shard_strategy="heads", **kw).eval()
+        heads.load_state_dict(single.state_dict(), strict=True)
+        x = torch.randn(n, 64, generator=torch.Generator().manual_seed(4))
+        full = single(x, 1, GraphShardInfo(nodes=[n]), ea, ei)
+        local = heads(shard_rows(x, sizes, group).contiguous(), 1, GraphShardInfo(nodes=sizes), ea, ei, group)
+        _close(gather_rows(local, sizes, group), full, f"heads strategy qk_norm={qk_norm}")
+        _close(heads(x, 1, GraphShardInfo(nodes=[n]), ea, ei), full, "heads-strategy module on one rank")
+
+
 def check_enc_proc_dec(rank, world):
     from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
     from anemoi_core_b200.model import EncProcDec
@@ -136,6 +161,11 @@ def check_model_forward(rank, world):
 @pytest.mark.parametrize("world", [2, 3, 4])
 def test_sharded_processors(world):
     run_distributed("check_processors", world)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_heads_strategy(world):
+    run_distributed("check_heads_strategy", world)
 
 
 @pytest.mark.parametrize("world", [2, 3])

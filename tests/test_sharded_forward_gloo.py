@@ -79,6 +79,17 @@ def check_processors(rank, world):
         local = m(shard_rows(x, sizes, group).contiguous(), 1, GraphShardInfo(nodes=sizes), ea, ei, group)
         assert local.shape[0] == sizes[rank]
         _close(gather_rows(local, sizes, group), full, kind)
+        # bf16 inputs select the tensor-core host path (LayerNorm folded into the GEMMs, row statistics handed over as tensor tags,
+        # K-padded operands): its bookkeeping must survive the sharding too.  Loose tolerance: every stage rounds to bf16.
+        xb = x.bfloat16()
+        ea16 = ea.bfloat16() if kind == "gnn" else ea  # (the GNN promotes x with its edge features; the GraphTransformer keeps attributes fp32)
+        full16 = m(xb, 1, GraphShardInfo(nodes=[n]), ea16, ei)
+        local16 = m(shard_rows(xb, sizes, group).contiguous(), 1, GraphShardInfo(nodes=sizes), ea16, ei, group)
+        got16 = gather_rows(local16, sizes, group)
+        assert full16.dtype == torch.bfloat16 and got16.dtype == torch.bfloat16
+        rel = ((got16.float() - full16.float()).norm() / full16.float().norm()).item()
+        assert rel <= 2e-2, f"{kind} bf16 host path: {rel:.3e}"
+        assert ((full16.float() - full).norm() / full.norm()).item() <= 3e-2
 
 
 def check_heads_strategy(rank, world):

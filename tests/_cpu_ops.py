@@ -185,13 +185,24 @@ def assemble_output(dec, x, batch, ensemble, n_step_output, step=-1, skip_src=No
     return y
 
 
+def glu_combine(gv, act):
+    H = gv.shape[1] // 2
+    gate = {"glu": torch.sigmoid, "swiglu": F.silu, "geglu": F.gelu, "reglu": torch.relu}[act]
+    return (gate(gv[:, :H].float()) * gv[:, H:].float()).to(gv.dtype)
+
+
+def cond_layer_norm(x, cond, w_scale, b_scale, w_bias, b_bias, eps=1e-5, out_dtype=None):
+    y = F.layer_norm(x.float(), (x.shape[1],), None, None, eps)
+    return (y * (1.0 + cond.float() @ w_scale.t() + b_scale) + cond.float() @ w_bias.t() + b_bias).to(out_dtype or x.dtype)
+
+
 def install() -> None:
     """Replace the CUDA entry points of ``anemoi_core_b200.ops`` in THIS process (a spawned Gloo test worker)."""
     import anemoi_core_b200.layers._functional as Fn
     from anemoi_core_b200 import ops
 
     for name in ("build_csr", "linear", "layer_norm", "row_stats", "gt_attention", "graphconv_ln_aggregate", "cast_pad", "add", "partial_stats_buffer",
-                 "assemble_input", "assemble_output"):
+                 "assemble_input", "assemble_output", "glu_combine", "cond_layer_norm"):
         setattr(ops, name, globals()[name])
     ops._need_cuda = lambda *a, **k: None
     torch.cuda.is_current_stream_capturing = lambda: False  # csr_for asks; there is no CUDA runtime here

@@ -169,6 +169,76 @@ def check_model_forward(rank, world):
         assert ((full - ref).abs().max() / ref.abs().max()).item() <= 1e-4
 
 
+def check_goldens_single_rank(rank, world):
+    """The mirror classes' HOST logic (weight packing / folding, buffer layouts, edge preparation, call order) on one rank, stand-in arithmetic,
+    against the goldens of the unmodified reference modules: catches host-side regressions in the CPU suite; the kernels are the GPU suite's job."""
+    from anemoi_core_b200.distributed.shapes import BipartiteGraphShardInfo
+    from anemoi_core_b200.distributed.shapes import GraphShardInfo
+    from anemoi_core_b200.layers import GNNBackwardMapper
+    from anemoi_core_b200.layers import GNNForwardMapper
+    from anemoi_core_b200.layers import GNNProcessor
+    from anemoi_core_b200.layers import GraphTransformerBackwardMapper
+    from anemoi_core_b200.layers import GraphTransformerForwardMapper
+    from anemoi_core_b200.layers import GraphTransformerProcessor
+
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+    def load(name):
+        return torch.load(os.path.join(gdir, name + ".pt"), weights_only=False)
+
+    def strip(cfg):
+        return {k: v for k, v in cfg.items()}
+
+    for name in ("gt_processor_small", "gt_processor_qknorm", "gt_processor_edge_pre_mlp", "gt_processor_attn_channels", "gt_processor_swiglu"):
+        g = load(name)
+        m = GraphTransformerProcessor(num_chunks=1, mlp_hidden_ratio=4, **strip(g["cfg"])).eval()
+        m.load_state_dict(g["sd"], strict=True)
+        _close(m(g["x"], 1, GraphShardInfo(), g["edge_attr"], g["edge_index"]), g["y"], name)
+    g = load("gt_processor_unsorted")
+    m = GraphTransformerProcessor(num_chunks=1, mlp_hidden_ratio=4, **strip(g["cfg"])).eval()
+    m.load_state_dict(g["sd"], strict=True)
+    _close(m(g["x"], 1, GraphShardInfo(), g["edge_attr"], g["edge_index"], None, edges_are_dst_sorted=False), g["y"], "gt_processor_unsorted")
+    for name in ("gnn_processor_small", "gnn_processor_cfg1", "gnn_processor_extra_layers", "gnn_processor_swiglu"):
+        g = load(name)
+        m = GNNProcessor(num_chunks=1, **{"mlp_extra_layers": 0, **strip(g["cfg"])}).eval()
+        m.load_state_dict(g["sd"], strict=True)
+        _close(m(g["x"], 1, GraphShardInfo(nodes=[g["x"].shape[0]]), g["edge_attr"], g["edge_index"]), g["y"], name)
+    bi = BipartiteGraphShardInfo()
+    g = load("gnn_forward_mapper")
+    m = GNNForwardMapper(num_chunks=1, mlp_extra_layers=0, **g["cfg"]).eval()
+    m.load_state_dict(g["sd"], strict=True)
+    ys, yd = m((g["x_src"], g["x_dst"]), 1, bi, g["edge_attr"], g["edge_index"])
+    _close(ys, g["y_src"], "gnn_forward_mapper src"), _close(yd, g["y_dst"], "gnn_forward_mapper dst")
+    g = load("gnn_backward_mapper")
+    m = GNNBackwardMapper(num_chunks=1, mlp_extra_layers=0, **g["cfg"]).eval()
+    m.load_state_dict(g["sd"], strict=True)
+    _close(m((g["x_src"], g["x_dst"]), 1, bi, g["edge_attr"], g["edge_index"]), g["y"], "gnn_backward_mapper")
+    for name in ("gt_forward_mapper_chunks1", "gt_forward_mapper_chunks4"):
+        g = load(name)
+        m = GraphTransformerForwardMapper(mlp_hidden_ratio=4, **g["cfg"]).eval()
+        m.load_state_dict(g["sd"], strict=True)
+        _close(m((g["x_src"], g["x_dst"]), 1, bi, g["edge_attr"], g["edge_index"])[1], g["y_dst"], name)
+    g = load("gt_backward_mapper")
+    m = GraphTransformerBackwardMapper(mlp_hidden_ratio=4, **g["cfg"]).eval()
+    m.load_state_dict(g["sd"], strict=True)
+    _close(m((g["x_src"], g["x_dst"]), 1, bi, g["edge_attr"], g["edge_index"]), g["y"], "gt_backward_mapper")
+    g = load("gt_processor_condln")  # ConditionalLayerNorm kernels + cond= (processor and forward mapper)
+    lk = {"LayerNorm": {"_target_": "anemoi_core_b200.layers.normalization.ConditionalLayerNorm", "condition_shape": g["condition_shape"],
+                        "zero_init": False}}  # fmt: skip
+    m = GraphTransformerProcessor(num_chunks=1, mlp_hidden_ratio=4, layer_kernels=lk, **g["cfg"]).eval()
+    m.load_state_dict(g["sd"], strict=True)
+    _close(m(g["x"], 1, GraphShardInfo(), g["edge_attr"], g["edge_index"], cond=g["cond"]), g["y"], "gt_processor_condln")
+    mp_ = g["mapper"]
+    m = GraphTransformerForwardMapper(num_chunks=1, mlp_hidden_ratio=4, layer_kernels=lk, **mp_["cfg"]).eval()
+    m.load_state_dict(mp_["sd"], strict=True)
+    _close(m((mp_["x_src"], mp_["x_dst"]), 1, bi, mp_["edge_attr"], mp_["edge_index"], cond=(mp_["cond_src"], mp_["cond_dst"]))[1], mp_["y_dst"],
+           "gt_forward_mapper condln")  # fmt: skip
+
+
+def test_host_logic_against_reference_goldens():
+    run_distributed("check_goldens_single_rank", 1)
+
+
 @pytest.mark.parametrize("world", [2, 3, 4])
 def test_sharded_processors(world):
     run_distributed("check_processors", world)

@@ -310,6 +310,54 @@ class GraphTransformerBaseBlock(nn.Module):
             att = ops.gt_attention(q, k, v, csr, H, edge_attr=edge_attr_p, w_edge=w_e, b_edge=b_e, add=x_r)
         return self._project_mlp(att, x_skip, dt, fold, want_stats, cond)
 
+    def _heads_attention(self, q: Tensor, qw: Tensor, k: Tensor, v: Tensor, x_r: Tensor, dst_sizes: list, src_sizes: Optional[list], ea: Tensor,
+                         edge_index: Tensor, group, dt: torch.dtype) -> Tensor:  # fmt: skip
+        """Attention of the "heads" (Ulysses) strategy.  ``q | qw | x_r`` are this rank's dst rows, ``k | v`` its src rows (``src_sizes``) or
+        ALL src rows (``src_sizes is None``).  The rows are exchanged so that each rank holds all nodes for its H / P heads (one all-to-all),
+        attention runs over the FULL edge list for those heads, a second all-to-all brings every rank its own rows for all heads; returns
+        ``[att + self | abar]`` for the projection GEMM.  qk_norm is applied by the row owners before the exchange."""
+        from ..distributed.graph import _exchange
+        from ..distributed.graph import group_rank
+
+        A, H, Ch = self.attn_channels, self.num_heads, self.out_channels_conv
+        P, me = group_size(group), group_rank(group)
+        n_l, N_dst = q.shape[0], sum(dst_sizes)
+        if H % P:
+            raise ValueError(f"heads strategy: num_heads ({H}) must be divisible by the model group size ({P})")
+        if not self._use_fold(dt) or not ops.attention_fold_supported(A // P, H // P, dt, self.lin_edge.weight.shape[1]):
+            raise NotImplementedError("heads strategy: implemented for shapes the folded lin_edge attention kernel handles")
+        Hl = H // P
+        d, dp, hdp = self._fold_dims()
+        if self.qk_norm:
+            for t, norm in ((q, self.q_norm), (k, self.k_norm)):
+                ops.layer_norm(t, self._pack.f32(norm.weight), self._pack.f32(getattr(norm, "bias", None)), norm.eps, out=t, groups=H)
+            qw = ops.linear(q, self._qw_blockdiag(dt))[:, : H * dp]
+
+        def to_heads(parts: list, n_rows: int, sizes: list) -> Tensor:
+            """[n_rows, H * w_i] column blocks -> every rank receives ALL rows (global order) of its head group: [sum(sizes), Hl * sum(w_i)]"""
+            send = torch.cat([t.reshape(n_rows, P, -1) for t in parts], dim=2).permute(1, 0, 2)
+            return _exchange(send.reshape(P * n_rows, -1).contiguous(), [n_rows] * P, sizes, group)
+
+        qa = to_heads([q, qw], n_l, dst_sizes)  # [N_dst, Hl * (Ch + dp)] = q | qw of my heads
+        if src_sizes is None:  # sources replicated: my heads are column slices, nothing travels
+            ka, va = k[:, me * Hl * Ch : (me + 1) * Hl * Ch], v[:, me * Hl * Ch : (me + 1) * Hl * Ch]
+        else:
+            kva = to_heads([k, v], k.shape[0], src_sizes)
+            ka, va = kva[:, : Hl * Ch], kva[:, Hl * Ch :]
+        csr = Fn.csr_for(edge_index, ka.shape[0], N_dst)
+        out_h = torch.empty((N_dst, Hl * (Ch + dp)), dtype=dt, device=q.device)
+        b_e = self._pack.f32(self.lin_edge.bias)
+        ops.gt_attention(qa[:, : Hl * Ch], ka, va, csr, Hl, edge_attr=ea, b_edge=None if b_e is None else b_e[me * Hl * Ch : (me + 1) * Hl * Ch],
+                         qw=qa[:, Hl * Ch :], abar=out_h[:, Hl * Ch :], dp=dp, out=out_h[:, : Hl * Ch])  # fmt: skip
+        back = _exchange(out_h, dst_sizes, [n_l] * P, group).reshape(P, n_l, Hl * (Ch + dp))  # [source rank = head group, local row, att | abar]
+        att = torch.empty((n_l, A + hdp), dtype=dt, device=q.device)
+        if hdp != H * dp:
+            att[:, A + H * dp :].zero_()
+        att_h = back[:, :, : Hl * Ch].permute(1, 0, 2).reshape(n_l, A)
+        ops.cast_pad(ops.add(att_h.contiguous(), x_r), dt, out=att[:, :A])  # + self term (fused into the kernel in the other strategies)
+        ops.cast_pad(back[:, :, Hl * Ch :].permute(1, 0, 2).reshape(n_l, H * dp).contiguous(), dt, out=att[:, A : A + H * dp])
+        return att
+
     def _project_mlp(self, att: Tensor, x_skip: Tensor, dt: torch.dtype, fold: bool, want_stats: bool, cond: Optional[Tensor]) -> Tensor:
         """projection (+ skip) -> LayerNorm -> MLP (+ residual) on the attention output ``att`` (``[att + self | abar]`` in the folded form)."""
         skip = x_skip if x_skip.dtype in Fn.SUPPORTED else x_skip.float()
@@ -383,49 +431,15 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
 
 
     def _forward_heads(self, x: Tensor, ln: nn.Module, ea: Tensor, edge_index: Tensor, shard_info, group, dt: torch.dtype, cond) -> Tensor:
-        """"heads" (Ulysses) strategy (block.py:689-759, 1185-1217): nodes are sharded outside the attention, heads inside it.  The local
-        q | k | v | qw rows of every rank are exchanged so that each rank holds ALL nodes for its H / P heads, attention runs over the full
-        graph for those heads, and a second exchange brings every rank the rows it owns for all heads.  ``edge_index`` / ``ea`` are the FULL
-        dst-sorted edge list and prepared attributes (the processor does not shard edges in this mode)."""
-        from ..distributed.graph import _exchange
-        from ..distributed.graph import group_rank
-
-        A, H, Ch = self.attn_channels, self.num_heads, self.out_channels_conv
-        P, me = group_size(group), group_rank(group)
-        sizes = list(shard_info.nodes)
-        n_l, N = x.shape[0], sum(sizes)
-        if H % P:
-            raise ValueError(f"heads strategy: num_heads ({H}) must be divisible by the model group size ({P})")
-        if not self._use_fold(dt) or not ops.attention_fold_supported(A // P, H // P, dt, self.lin_edge.weight.shape[1]):
-            raise NotImplementedError("heads strategy: implemented for shapes the folded lin_edge attention kernel handles")
-        Hl = H // P
+        """"heads" (Ulysses) strategy (block.py:689-759, 1185-1217): nodes are sharded outside the attention, heads inside it
+        (``_heads_attention``).  ``edge_index`` / ``ea`` are the FULL dst-sorted edge list and prepared attributes (the processor does not
+        shard edges in this mode)."""
+        A, H = self.attn_channels, self.num_heads
         d, dp, hdp = self._fold_dims()
         buf = self._dst_gemm(x, ln, [self.lin_query, self.lin_key, self.lin_value, self.lin_self], dt, cond=cond)  # q | k | v | self | qw
         q, k, v, x_r = buf[:, :A], buf[:, A : 2 * A], buf[:, 2 * A : 3 * A], buf[:, 3 * A : 4 * A]
-        if self.qk_norm:  # per row and head: done by the owner of the rows, before the exchange
-            for t, norm in ((q, self.q_norm), (k, self.k_norm)):
-                ops.layer_norm(t, self._pack.f32(norm.weight), self._pack.f32(getattr(norm, "bias", None)), norm.eps, out=t, groups=H)
-            qw = ops.linear(q, self._qw_blockdiag(dt))[:, : H * dp]
-        else:
-            qw = buf[:, 4 * A : 4 * A + H * dp]
-        # [n_l, H, *] -> per destination rank r the columns of its heads: q | k | v | qw
-        W = Hl * (3 * Ch + dp)
-        parts = [t.reshape(n_l, P, -1) for t in (q, k, v, qw)]
-        send = torch.cat(parts, dim=2).permute(1, 0, 2).reshape(P * n_l, W).contiguous()
-        allrows = _exchange(send, [n_l] * P, sizes, group)  # rows in global node order (rank r's block = its node range)
-        qa, ka, va = allrows[:, : Hl * Ch], allrows[:, Hl * Ch : 2 * Hl * Ch], allrows[:, 2 * Hl * Ch : 3 * Hl * Ch]
-        csr = Fn.csr_for(edge_index, N, N)
-        out_h = torch.empty((N, Hl * (Ch + dp)), dtype=dt, device=x.device)
-        b_e = self._pack.f32(self.lin_edge.bias)
-        ops.gt_attention(qa, ka, va, csr, Hl, edge_attr=ea, b_edge=None if b_e is None else b_e[me * Hl * Ch : (me + 1) * Hl * Ch],
-                         qw=allrows[:, 3 * Hl * Ch :], abar=out_h[:, Hl * Ch :], dp=dp, out=out_h[:, : Hl * Ch])  # fmt: skip
-        back = _exchange(out_h, sizes, [n_l] * P, group).reshape(P, n_l, Hl * (Ch + dp))  # [source rank = head group, local row, att | abar]
-        att = torch.empty((n_l, A + hdp), dtype=dt, device=x.device)
-        if hdp != H * dp:
-            att[:, A + H * dp :].zero_()
-        att_h = back[:, :, : Hl * Ch].permute(1, 0, 2).reshape(n_l, A)
-        ops.cast_pad(ops.add(att_h.contiguous(), x_r), dt, out=att[:, :A])  # + self term (fused into the kernel in the other strategies)
-        ops.cast_pad(back[:, :, Hl * Ch :].permute(1, 0, 2).reshape(n_l, H * dp).contiguous(), dt, out=att[:, A : A + H * dp])
+        sizes = list(shard_info.nodes)
+        att = self._heads_attention(q, buf[:, 4 * A : 4 * A + H * dp], k, v, x_r, sizes, sizes, ea, edge_index, group, dt)
         return self._project_mlp(att, x, dt, True, True, cond)
 
 
@@ -466,6 +480,19 @@ class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
         kv_layers = [self.lin_key, self.lin_value]
         kv = Fn.ln_linear(self._pack, x_src, self.layer_norm_attention_src, ("kv",), Fn.linear_sources(kv_layers), lambda: Fn.cat_linear32(kv_layers), dt,
                           cond=cond_src)  # fmt: skip
+        if group_size(model_comm_group) > 1 and self.shard_strategy == "heads":
+            # heads strategy (mapper.py:388-478): full edge list, heads sharded inside the attention
+            d_, dp_, _ = self._fold_dims()
+            buf = self._dst_gemm(x_dst, self.layer_norm_attention_dest, [self.lin_query, self.lin_self], dt, cond=cond_dst)  # q | self | qw
+            att = self._heads_attention(buf[:, :A], buf[:, 2 * A : 2 * A + self.num_heads * dp_], kv[:, :A], kv[:, A:], buf[:, A : 2 * A],
+                                        list(shard_info.dst_nodes), list(shard_info.src_nodes) if shard_info.src_is_sharded() else None,
+                                        self.prepare_edges(edge_attr, dt), edge_index, model_comm_group, dt)  # fmt: skip
+            dst_new = self._project_mlp(att, x_dst, dt, True, False, cond_dst)
+            src_new = x_src
+            if self.update_src_nodes:
+                src_new = self.node_src_mlp.run(x_src, dt, residual=x_src if x_src.dtype in Fn.SUPPORTED else x_src.float(),
+                                                pre_ln=self.layer_norm_mlp_src, cond=cond_src)  # fmt: skip
+            return (src_new, dst_new), edge_attr
         if group_size(model_comm_group) > 1 and shard_info is not None and shard_info.src_is_sharded():
             # edges strategy (reference mapper.py:248-297 / khop_edges.py:317-409): every rank needs the k | v rows of all sources
             kv = gather_rows(kv, shard_info.src_nodes, model_comm_group)

@@ -87,8 +87,6 @@ class GraphTransformerBaseMapper(BaseMapper):
                          out_channels_dst=out_channels_dst, cpu_offload=cpu_offload, layer_kernels=layer_kernels, **kwargs)  # fmt: skip
         if shard_strategy not in ("heads", "edges"):
             raise AssertionError(f"Invalid shard strategy '{shard_strategy}' for {self.__class__.__name__}. Supported strategies are 'heads' and 'edges'.")
-        if shard_strategy == "heads":
-            raise NotImplementedError("shard_strategy='heads' (Ulysses all-to-all) is not implemented; use 'edges'")
         self.num_chunks = num_chunks
         self.shard_strategy = shard_strategy
         self.proc = GraphTransformerMapperBlock(
@@ -128,7 +126,11 @@ class GraphTransformerBaseMapper(BaseMapper):
             from .processor import _localise_presharded_edges
             from .processor import _shard_edges_by_dst
 
-            if shard_info.edges_are_sharded():
+            if self.shard_strategy == "heads":
+                if shard_info.edges_are_sharded():
+                    raise NotImplementedError("shard_strategy='heads' needs the full dst-sorted edge list (graph provider: get_edges(shard_edges=False))")
+                # every rank attends over the FULL edge list for its heads (block._heads_attention): nothing to cut
+            elif shard_info.edges_are_sharded():
                 # the graph provider already cut the list to the edges into our rows (global dst ids): relabel dst only
                 edge_index = _localise_presharded_edges(edge_index, shard_info.dst_nodes, model_comm_group)
             else:

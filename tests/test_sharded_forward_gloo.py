@@ -117,6 +117,41 @@ def check_heads_strategy(rank, world):
         _close(heads(x, 1, GraphShardInfo(nodes=[n]), ea, ei), full, "heads-strategy module on one rank")
 
 
+def check_heads_strategy_mappers(rank, world):
+    """GraphTransformer mappers with shard_strategy="heads" (mapper.py:388-478): replicated sources (encoder) and sharded sources (decoder)."""
+    from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
+    from anemoi_core_b200.distributed.graph import shard_rows
+    from anemoi_core_b200.distributed.shapes import BipartiteGraphShardInfo
+    from anemoi_core_b200.layers import GraphTransformerBackwardMapper
+    from anemoi_core_b200.layers import GraphTransformerForwardMapper
+
+    n_grid, n_mesh, d = 83, 37, 4
+    group = dist.group.WORLD
+    gs, ms = get_balanced_partition_sizes(n_grid, world), get_balanced_partition_sizes(n_mesh, world)
+    g = torch.Generator().manual_seed(8)
+    xg, xm, lat = torch.randn(n_grid, 9, generator=g), torch.randn(n_mesh, 6, generator=g), torch.randn(n_mesh, 64, generator=g)
+    for qk_norm in (False, True):
+        kw = dict(hidden_dim=64, num_chunks=1, num_heads=4, mlp_hidden_ratio=2, edge_dim=d, qk_norm=qk_norm)
+        ei, ea = _graph(n_grid, n_mesh, 260, d, seed=9)
+        torch.manual_seed(5)
+        enc = GraphTransformerForwardMapper(in_channels_src=9, in_channels_dst=6, **kw).eval()
+        enc_h = GraphTransformerForwardMapper(in_channels_src=9, in_channels_dst=6, shard_strategy="heads", **kw).eval()
+        enc_h.load_state_dict(enc.state_dict(), strict=True)
+        _, full = enc((xg, xm), 1, BipartiteGraphShardInfo(), ea, ei)
+        _, got = enc_h((xg, shard_rows(xm, ms, group).contiguous()), 1, BipartiteGraphShardInfo(src_nodes=None, dst_nodes=ms), ea, ei, group,
+                       keep_x_dst_sharded=False)  # fmt: skip
+        _close(got, full, f"forward mapper, heads strategy, qk_norm={qk_norm}")
+        ei, ea = _graph(n_mesh, n_grid, 300, d, seed=10)
+        torch.manual_seed(6)
+        dec = GraphTransformerBackwardMapper(in_channels_src=64, in_channels_dst=9, out_channels_dst=5, **kw).eval()
+        dec_h = GraphTransformerBackwardMapper(in_channels_src=64, in_channels_dst=9, out_channels_dst=5, shard_strategy="heads", **kw).eval()
+        dec_h.load_state_dict(dec.state_dict(), strict=True)
+        full = dec((lat, xg), 1, BipartiteGraphShardInfo(), ea, ei)
+        got = dec_h((shard_rows(lat, ms, group).contiguous(), shard_rows(xg, gs, group).contiguous()), 1,
+                    BipartiteGraphShardInfo(src_nodes=ms, dst_nodes=gs), ea, ei, group, keep_x_dst_sharded=False)  # fmt: skip
+        _close(got, full, f"backward mapper, heads strategy, qk_norm={qk_norm}")
+
+
 def check_enc_proc_dec(rank, world):
     from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
     from anemoi_core_b200.model import EncProcDec
@@ -247,6 +282,11 @@ def test_sharded_processors(world):
 @pytest.mark.parametrize("world", [2, 4])
 def test_heads_strategy(world):
     run_distributed("check_heads_strategy", world)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_heads_strategy_mappers(world):
+    run_distributed("check_heads_strategy_mappers", world)
 
 
 @pytest.mark.parametrize("world", [2, 3])

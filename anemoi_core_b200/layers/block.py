@@ -316,8 +316,15 @@ class GraphTransformerBaseBlock(nn.Module):
         ALL src rows (``src_sizes is None``).  The rows are exchanged so that each rank holds all nodes for its H / P heads (one all-to-all),
         attention runs over the FULL edge list for those heads, a second all-to-all brings every rank its own rows for all heads; returns
         ``[att + self | abar]`` for the projection GEMM.  qk_norm is applied by the row owners before the exchange."""
+        from ..distributed.graph import SegmentedCapture
         from ..distributed.graph import _exchange
         from ..distributed.graph import group_rank
+
+        def xchg(send: Tensor, in_splits: list, out_splits: list) -> Tensor:
+            if SegmentedCapture.active is None:
+                return _exchange(send, in_splits, out_splits, group)
+            out = send.new_empty((sum(out_splits), send.shape[1]))  # static buffer of the capture pool; the collective runs between two segments
+            return SegmentedCapture.active.exchange(send, in_splits, out_splits, group, out)
 
         A, H, Ch = self.attn_channels, self.num_heads, self.out_channels_conv
         P, me = group_size(group), group_rank(group)
@@ -336,7 +343,7 @@ class GraphTransformerBaseBlock(nn.Module):
         def to_heads(parts: list, n_rows: int, sizes: list) -> Tensor:
             """[n_rows, H * w_i] column blocks -> every rank receives ALL rows (global order) of its head group: [sum(sizes), Hl * sum(w_i)]"""
             send = torch.cat([t.reshape(n_rows, P, -1) for t in parts], dim=2).permute(1, 0, 2)
-            return _exchange(send.reshape(P * n_rows, -1).contiguous(), [n_rows] * P, sizes, group)
+            return xchg(send.reshape(P * n_rows, -1).contiguous(), [n_rows] * P, sizes)
 
         qa = to_heads([q, qw], n_l, dst_sizes)  # [N_dst, Hl * (Ch + dp)] = q | qw of my heads
         if src_sizes is None:  # sources replicated: my heads are column slices, nothing travels
@@ -349,7 +356,7 @@ class GraphTransformerBaseBlock(nn.Module):
         b_e = self._pack.f32(self.lin_edge.bias)
         ops.gt_attention(qa[:, : Hl * Ch], ka, va, csr, Hl, edge_attr=ea, b_edge=None if b_e is None else b_e[me * Hl * Ch : (me + 1) * Hl * Ch],
                          qw=qa[:, Hl * Ch :], abar=out_h[:, Hl * Ch :], dp=dp, out=out_h[:, : Hl * Ch])  # fmt: skip
-        back = _exchange(out_h, dst_sizes, [n_l] * P, group).reshape(P, n_l, Hl * (Ch + dp))  # [source rank = head group, local row, att | abar]
+        back = xchg(out_h, dst_sizes, [n_l] * P).reshape(P, n_l, Hl * (Ch + dp))  # [source rank = head group, local row, att | abar]
         att = torch.empty((n_l, A + hdp), dtype=dt, device=q.device)
         if hdp != H * dp:
             att[:, A + H * dp :].zero_()

@@ -224,6 +224,66 @@ class AnemoiModelEncProcDec(nn.Module):
         self._tables: dict = {}
         self._bound_spec = {ds: list((boundings or {}).get(ds, [])) for ds in self.dataset_names}
 
+    @classmethod
+    def from_reference_config(cls, *, model_config, data_indices: dict, n_step_input: int, n_step_output: int, graph_data,
+                              statistics=None) -> "AnemoiModelEncProcDec":  # fmt: skip
+        """Build the model from the objects the reference's ``BaseGraphModel.__init__`` receives (models/base.py:41-97): the resolved model
+        config (``model_config.model.{num_channels, model, encoder, processor, decoder, trainable_parameters, attributes, bounding,
+        residual}``, attribute or key access), the per-dataset ``IndexCollection``s and the graph.  The ``_target_`` of the processor picks the
+        model kind; keys the constructors of the reference take from elsewhere (``_target_``, ``trainable_size``, ``sub_graph_edge_attributes``)
+        are dropped from the layer kwargs.  Only what this forward implements is accepted: ``SkipConnection`` residual, ReLU / LeakyReLU
+        boundings (anything else raises)."""
+
+        def get(obj, key, default=None):
+            if isinstance(obj, dict):
+                return obj.get(key, default)
+            return getattr(obj, key, default)
+
+        m = get(model_config, "model")
+        proc_cfg = dict(get(m, "processor"))
+        target = str(proc_cfg.get("_target_", ""))
+        kind = "graphtransformer" if "GraphTransformer" in target else "gnn" if "GNN" in target else None
+        if kind is None:
+            raise NotImplementedError(f"processor {target!r}: only the GNN and GraphTransformer processors are part of this hot path")
+        drop = ("_target_", "trainable_size", "sub_graph_edge_attributes", "_convert_", "_recursive_")
+
+        def layer_kwargs(cfg) -> dict:
+            return {k: v for k, v in dict(cfg).items() if k not in drop}
+
+        residual = get(m, "residual")
+        res_target = str(get(residual, "_target_", "SkipConnection")) if residual is not None else "SkipConnection"
+        if not res_target.endswith("SkipConnection"):
+            raise NotImplementedError(f"residual {res_target!r}: only SkipConnection is implemented (layers/residual.py:60-81)")
+        names = list(data_indices.keys())
+        boundings = {}
+        for ds in names:
+            name_to_index = data_indices[ds].model.output.name_to_index
+            spec = []
+            for b in get(m, "bounding", None) or []:
+                t = str(get(b, "_target_"))
+                code = "relu" if t.endswith(".ReluBounding") else "leaky_relu" if t.endswith(".LeakyReluBounding") else None
+                if code is None:
+                    raise NotImplementedError(f"bounding {t!r}: ReluBounding and LeakyReluBounding are implemented (layers/bounding.py:81-94)")
+                wanted = set(get(b, "variables"))
+                spec.append((code, [i for n, i in name_to_index.items() if n in wanted]))  # as BaseBounding._create_index (bounding.py:61-62)
+            boundings[ds] = spec
+        model_block = get(m, "model")
+        tp = dict(get(m, "trainable_parameters") or {})
+        hidden = get(model_block, "hidden_nodes_name", "hidden")
+        # the reference broadcasts the "data" entry to every dataset name (base.py:78-82 broadcast_config_keys)
+        tp_nodes = {**{ds: tp.get("data", 0) for ds in names}, hidden: tp.get("hidden", 0)}
+        return cls(
+            kind, graph_data=graph_data, dataset_names=names, hidden_nodes_name=hidden, edge_attributes=list(get(get(m, "attributes"), "edges")),
+            num_channels=get(m, "num_channels"), n_step_input=n_step_input, n_step_output=n_step_output,
+            num_input_channels={ds: len(data_indices[ds].model.input) for ds in names},
+            num_output_channels={ds: len(data_indices[ds].model.output) for ds in names},
+            internal_input_idx={ds: list(data_indices[ds].model.input.prognostic) for ds in names},
+            internal_output_idx={ds: list(data_indices[ds].model.output.prognostic) for ds in names},
+            encoder=layer_kwargs(get(m, "encoder")), processor=layer_kwargs(proc_cfg), decoder=layer_kwargs(get(m, "decoder")),
+            trainable_parameters={**tp, **tp_nodes}, latent_skip=bool(get(model_block, "latent_skip", True)), boundings=boundings,
+            residual_step=int(get(residual, "step", -1)) if residual is not None else -1,
+        )  # fmt: skip
+
     def _output_tables(self, ds: str, device) -> tuple[Tensor, Tensor]:
         key = (ds, str(device))
         if key not in self._tables:

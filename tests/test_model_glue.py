@@ -114,3 +114,44 @@ def test_assemble_output_kernel(dt):
     # no residual, no bounding: a pure rearrange
     y0 = ops.assemble_output(dec.cuda(), None, B, E, T_out)
     assert torch.equal(y0.cpu(), dec.float().reshape(B, E, G, T_out, V_out).permute(0, 3, 1, 2, 4))
+
+
+def test_from_reference_config(golden):
+    """The model built from reference-shaped config objects (DotDict-like config, IndexCollection-like data indices) is the one built by hand:
+    same state_dict keys / shapes as the reference model, same index tables."""
+    from types import SimpleNamespace as NS
+
+    fx = golden("model_forward")
+    d = fx["dims"]
+    graph = {"data": {"x": fx["coords"]["data"]}, "hidden": {"x": fx["coords"]["hidden"]},
+             ("data", "to", "hidden"): fx["graph"]["enc"], ("hidden", "to", "hidden"): fx["graph"]["proc"], ("hidden", "to", "data"): fx["graph"]["dec"]}  # fmt: skip
+
+    class Idx(list):  # a tensor-index list with the .prognostic / .name_to_index attributes of the reference's InputTensorIndex
+        pass
+
+    inp, outp = Idx(range(d["n_in"])), Idx(range(d["n_out"]))
+    inp.prognostic, outp.prognostic = fx["in_prog"], fx["out_prog"]
+    outp.name_to_index = {f"v{i}": i for i in range(d["n_out"])}
+    data_indices = {"data": NS(model=NS(input=inp, output=outp))}
+    common = {"trainable_size": 2, "sub_graph_edge_attributes": ["edge_length", "edge_dirs"], "num_chunks": 1, "num_heads": d["heads"], "mlp_hidden_ratio": 4,
+              "qk_norm": False, "cpu_offload": False, "gradient_checkpointing": True, "shard_strategy": "edges", "graph_attention_backend": "triton"}  # fmt: skip
+    cfg = {"model": {
+        "num_channels": d["C"], "model": {"_target_": "anemoi.models.models.AnemoiModelEncProcDec", "hidden_nodes_name": "hidden", "latent_skip": True},
+        "processor": {"_target_": "anemoi.models.layers.processor.GraphTransformerProcessor", "num_layers": 2, **common},
+        "encoder": {"_target_": "anemoi.models.layers.mapper.GraphTransformerForwardMapper", **common},
+        "decoder": {"_target_": "anemoi.models.layers.mapper.GraphTransformerBackwardMapper", "initialise_data_extractor_zero": False, **common},
+        "residual": {"_target_": "anemoi.models.layers.residual.SkipConnection", "step": -1},
+        "trainable_parameters": {"data": 0, "hidden": 3, "data2hidden": 2, "hidden2data": 2, "hidden2hidden": 2},
+        "attributes": {"edges": ["edge_length", "edge_dirs"], "nodes": []},
+        "bounding": [{"_target_": "anemoi.models.layers.bounding.ReluBounding", "variables": ["v1", "v3"]}],
+    }}  # fmt: skip
+    m = AnemoiModelEncProcDec.from_reference_config(model_config=cfg, data_indices=data_indices, n_step_input=d["t_in"], n_step_output=d["t_out"],
+                                                    graph_data=graph).eval()  # fmt: skip
+    ref_sd = fx["cases"]["graphtransformer"]["sd"]
+    assert sorted(m.state_dict().keys()) == sorted(ref_sd.keys())
+    m.load_state_dict(ref_sd, strict=True)
+    skip, bound = m._output_tables("data", torch.device("cpu"))
+    assert skip.tolist() == [0, 1, 2, 4, 5] and bound.tolist() == [0, 1, 0, 1, 0] and m.kind == "graphtransformer"
+    bad = {"model": {**cfg["model"], "residual": {"_target_": "anemoi.models.layers.residual.TruncatedConnection"}}}
+    with pytest.raises(NotImplementedError, match="SkipConnection"):
+        AnemoiModelEncProcDec.from_reference_config(model_config=bad, data_indices=data_indices, n_step_input=2, n_step_output=1, graph_data=graph)

@@ -396,8 +396,78 @@ def cond_layer_norm_case(seed=31):
     print("gt_processor_condln", tuple(y.shape), float(y.abs().mean()))
 
 
+@torch.no_grad()
+def multi_dataset_case(seed=41):
+    """``AnemoiModelEncProcDec.forward`` with TWO datasets (encoder_processor_decoder.py:203-330): one encoder / decoder / graph provider per
+    dataset, the dataset latents summed before the processor (:268), one output per dataset."""
+    from torch_geometric.data import HeteroData
+
+    from anemoi.models.layers.graph import NamedNodesAttributes
+    from anemoi.models.layers.graph_provider import create_graph_provider
+
+    Model = _load_reference_model_class()
+    g = torch.Generator().manual_seed(seed)
+    sizes = {"era": 50, "obs": 34}
+    n_hid, C, heads, t_in, t_out = 20, 32, 4, 2, 1
+    n_in, n_out = {"era": 6, "obs": 4}, {"era": 4, "obs": 3}
+    prog_in, prog_out = {"era": [0, 1, 3, 4], "obs": [0, 2, 3]}, {"era": [0, 1, 2, 3], "obs": [0, 1, 2]}
+    graph = HeteroData()
+    for name, n in list(sizes.items()) + [("hidden", n_hid)]:
+        graph[name].x = torch.rand(n, 2, generator=g) * 3.0 - 1.5
+
+    def sub(src, dst, n_src, n_dst, e):
+        st = graph[(src, "to", dst)]
+        dst_ids = torch.cat([torch.arange(n_dst), torch.randint(0, n_dst, (e - n_dst,), generator=g)])
+        st.edge_index = torch.stack([torch.randint(0, n_src, (e,), generator=g), dst_ids[torch.randperm(e, generator=g)]])
+        st.edge_length = torch.rand(e, 1, generator=g)
+        st.edge_dirs = torch.randn(e, 2, generator=g)
+        return st
+
+    subs = {("hidden", "hidden"): sub("hidden", "hidden", n_hid, n_hid, 90)}
+    for name, n in sizes.items():
+        subs[(name, "hidden")] = sub(name, "hidden", n, n_hid, 3 * n_hid + 20)
+        subs[("hidden", name)] = sub("hidden", name, n_hid, n, 3 * n)
+    x = {name: torch.randn(1, t_in, 1, n, n_in[name], generator=g) for name, n in sizes.items()}
+    torch.manual_seed(seed)
+    m = Model.__new__(Model)
+    torch.nn.Module.__init__(m)
+    m._graph_name_hidden, m.n_step_output, m.latent_skip = "hidden", t_out, True
+    m._internal_input_idx, m._internal_output_idx = prog_in, prog_out
+    m.node_attributes = NamedNodesAttributes({"era": 0, "obs": 0, "hidden": 2}, graph)
+    m.node_attributes.trainable_tensors["hidden"].trainable.copy_(torch.randn(n_hid, 2, generator=g))
+
+    def prov(key, n_src, n_dst):
+        p = create_graph_provider(graph=subs[key], edge_attributes=["edge_length", "edge_dirs"], src_size=n_src, dst_size=n_dst, trainable_size=1)
+        p.trainable.trainable.copy_(0.5 * torch.randn(p.trainable.trainable.shape, generator=g))
+        return p
+
+    m.encoder_graph_provider = torch.nn.ModuleDict({n: prov((n, "hidden"), sizes[n], n_hid) for n in sizes})
+    m.processor_graph_provider = prov(("hidden", "hidden"), n_hid, n_hid)
+    m.decoder_graph_provider = torch.nn.ModuleDict({n: prov(("hidden", n), n_hid, sizes[n]) for n in sizes})
+    edge_dim = m.processor_graph_provider.edge_dim
+    lat_dim = m.node_attributes.attr_ndims["hidden"]
+    in_dim = {n: t_in * n_in[n] + m.node_attributes.attr_ndims[n] for n in sizes}
+    kw = dict(num_heads=heads, mlp_hidden_ratio=4, edge_dim=edge_dim, layer_kernels=None, graph_attention_backend="pyg", num_chunks=1)
+    m.encoder = torch.nn.ModuleDict({n: randomise(GraphTransformerForwardMapper(in_channels_src=in_dim[n], in_channels_dst=lat_dim, hidden_dim=C, **kw), seed + i)
+                                     for i, n in enumerate(sizes)})  # fmt: skip
+    m.processor = randomise(GraphTransformerProcessor(num_layers=2, num_channels=C, **kw), seed + 5)
+    m.decoder = torch.nn.ModuleDict({n: randomise(GraphTransformerBackwardMapper(in_channels_src=C, in_channels_dst=in_dim[n], hidden_dim=C,
+                                                                                  out_channels_dst=t_out * n_out[n], **kw), seed + 7 + i)
+                                     for i, n in enumerate(sizes)})  # fmt: skip
+    m.residual = torch.nn.ModuleDict({n: _SkipConnection(step=-1) for n in sizes})
+    m.boundings = torch.nn.ModuleDict({n: torch.nn.ModuleList([]) for n in sizes})
+    m.eval()
+    y = m({k: v.clone() for k, v in x.items()})
+    torch.save({"kind": "model_multi", "sizes": sizes, "n_hid": n_hid, "C": C, "heads": heads, "t_in": t_in, "t_out": t_out, "n_in": n_in, "n_out": n_out,
+                "prog_in": prog_in, "prog_out": prog_out, "coords": {n: graph[n].x for n in list(sizes) + ["hidden"]},
+                "graph": {k: {"edge_index": v.edge_index, "edge_length": v.edge_length, "edge_dirs": v.edge_dirs} for k, v in subs.items()},
+                "x": x, "sd": sd_of(m), "y": {k: v.clone() for k, v in y.items()}}, os.path.join(OUT, "model_forward_two_datasets.pt"))  # fmt: skip
+    print("model two datasets", {k: tuple(v.shape) for k, v in y.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    multi_dataset_case()
     cond_layer_norm_case()
     graph_provider_cases()
     model_cases()

@@ -155,3 +155,25 @@ def test_from_reference_config(golden):
     bad = {"model": {**cfg["model"], "residual": {"_target_": "anemoi.models.layers.residual.TruncatedConnection"}}}
     with pytest.raises(NotImplementedError, match="SkipConnection"):
         AnemoiModelEncProcDec.from_reference_config(model_config=bad, data_indices=data_indices, n_step_input=2, n_step_output=1, graph_data=graph)
+
+
+def build_two_dataset_model(fx):
+    graph = {n: {"x": c} for n, c in fx["coords"].items()}
+    graph.update({(src, "to", dst): sub for (src, dst), sub in fx["graph"].items()})
+    names = list(fx["sizes"])
+    common = dict(num_heads=fx["heads"], mlp_hidden_ratio=4, num_chunks=1)
+    return AnemoiModelEncProcDec("graphtransformer", graph_data=graph, dataset_names=names, edge_attributes=["edge_length", "edge_dirs"],
+                                 num_channels=fx["C"], n_step_input=fx["t_in"], n_step_output=fx["t_out"], num_input_channels=fx["n_in"],
+                                 num_output_channels=fx["n_out"], internal_input_idx=fx["prog_in"], internal_output_idx=fx["prog_out"],
+                                 encoder=common, processor=dict(num_layers=2, **common), decoder=common,
+                                 trainable_parameters={"hidden": 2, "data2hidden": 1, "hidden2data": 1, "hidden2hidden": 1}).eval()  # fmt: skip
+
+
+def test_two_dataset_model_state_dict(golden):
+    """Two datasets (encoder_processor_decoder.py:203-330).  The forward itself is checked against the reference golden on CPU with the stand-in
+    arithmetic (tests/test_sharded_forward_gloo.py::test_host_logic_against_reference_goldens); the GPU-parity case for it is still to be
+    added (no GPU time was left in round 1 to run it, and an unrun GPU test does not belong in the suite)."""
+    fx = golden("model_forward_two_datasets")
+    m = build_two_dataset_model(fx)
+    assert sorted(m.state_dict().keys()) == sorted(fx["sd"].keys())  # encoder.era.*, encoder.obs.*, decoder_graph_provider.obs.* ...
+    m.load_state_dict(fx["sd"], strict=True)

@@ -268,6 +268,23 @@ def check_goldens_single_rank(rank, world):
     m.load_state_dict(mp_["sd"], strict=True)
     _close(m((mp_["x_src"], mp_["x_dst"]), 1, bi, mp_["edge_attr"], mp_["edge_index"], cond=(mp_["cond_src"], mp_["cond_dst"]))[1], mp_["y_dst"],
            "gt_forward_mapper condln")  # fmt: skip
+    # the whole model, one and two datasets (graph providers, node attributes, assembly, latent sum, residual, boundings)
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_glue", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_model_glue.py"))
+    glue = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(glue)
+    fx = load("model_forward")
+    for kind in ("graphtransformer", "gnn"):
+        m = glue.build_model(fx, kind)
+        m.load_state_dict(fx["cases"][kind]["sd"], strict=True)
+        _close(m({"data": fx["x"]})["data"], fx["cases"][kind]["y"], f"model {kind}")
+    fx = load("model_forward_two_datasets")
+    m = glue.build_two_dataset_model(fx)
+    m.load_state_dict(fx["sd"], strict=True)
+    y = m(fx["x"])
+    for name, ref in fx["y"].items():
+        _close(y[name], ref, f"two-dataset model, {name}")
 
 
 def test_host_logic_against_reference_goldens():

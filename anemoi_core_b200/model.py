@@ -170,8 +170,8 @@ class AnemoiModelEncProcDec(nn.Module):
 
     graph_data: ``{node_set: {"x": coords}}`` plus ``{(src, "to", dst): {"edge_index": ..., <attribute>: ...}}`` (a PyG ``HeteroData`` works).
     boundings: ``{dataset: [("relu" | "leaky_relu", [output variable indices]), ...]}``.
-    Model sharding: GraphTransformer kind, hidden rows sharded like the reference (balanced dst ranges, provider-sharded edges);
-    the grid stays replicated unless ``grid_shard_sizes`` is given.
+    Model sharding (both kinds): hidden rows sharded like the reference (balanced dst ranges, provider-sharded edges); the grid stays
+    replicated unless ``grid_shard_sizes`` is given.
     """
 
     def __init__(self, kind: str, *, graph_data, dataset_names=("data",), hidden_nodes_name: str = "hidden", edge_attributes: list[str],
@@ -321,8 +321,6 @@ class AnemoiModelEncProcDec(nn.Module):
         world = group_size(model_comm_group)
         if world > 1:
             assert batch_size == 1 and ensemble_size == 1, "Only batch / ensemble size 1 per device when the model is sharded across GPUs"
-            if self.kind != "graphtransformer":
-                raise NotImplementedError("sharded forward of the GNN model: shard the processor through EncProcDec, the GNN mappers run replicated")
         dt = compute_dtype(*x.values())
         hid = self._graph_name_hidden
         x_hidden = self.node_attributes(hid, batch_size=batch_size)
@@ -349,10 +347,12 @@ class AnemoiModelEncProcDec(nn.Module):
             info = BipartiteGraphShardInfo(src_nodes=sizes_hidden, dst_nodes=sizes_data[ds], edges=es)
             if world > 1 and sizes_data[ds] is None:
                 # replicated grid: every rank owns a balanced slice of the grid rows inside the decoder and the output is gathered
-                n_grid = x_data_latents[ds].shape[0]
+                n_grid = x[ds].shape[3]
                 info = BipartiteGraphShardInfo(src_nodes=sizes_hidden, dst_nodes=get_balanced_partition_sizes(n_grid, world), edges=None)
                 ea, ei, _ = self.decoder_graph_provider[ds].get_edges(batch_size=batch_size, model_comm_group=model_comm_group, shard_edges=False)
-                x_dst = shard_rows(x_data_latents[ds], info.dst_nodes, model_comm_group)
+                x_dst = x_data_latents[ds]
+                if x_dst.shape[0] == n_grid:  # GraphTransformer encoder: the raw assembled input came back whole; the GNN encoder cut its
+                    x_dst = shard_rows(x_dst, info.dst_nodes, model_comm_group)  # replicated source to the same balanced slice itself
                 dec = self.decoder[ds]((x_proc, x_dst), batch_size, info, ea, ei, model_comm_group, keep_x_dst_sharded=False)
             else:
                 dec = self.decoder[ds]((x_proc, x_data_latents[ds]), batch_size, info, ea, ei, model_comm_group,

@@ -193,15 +193,16 @@ def check_model_forward(rank, world):
     glue = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(glue)
     fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_forward.pt"), weights_only=False)
-    m = glue.build_model(fx, "graphtransformer")
-    m.load_state_dict(fx["cases"]["graphtransformer"]["sd"], strict=True)
-    x = {"data": fx["x"][:1].contiguous()}  # batch 1: the only batch size a sharded model accepts (encoder_processor_decoder.py:165-183)
-    full = m(x)["data"]
-    got = m(x, model_comm_group=dist.group.WORLD)["data"]
-    _close(got, full, "AnemoiModelEncProcDec sharded")
-    if world == 2:  # the single-rank result is the reference golden's first batch element
-        ref = fx["cases"]["graphtransformer"]["y"][:1]
-        assert ((full - ref).abs().max() / ref.abs().max()).item() <= 1e-4
+    for kind in ("graphtransformer", "gnn"):
+        m = glue.build_model(fx, kind)
+        m.load_state_dict(fx["cases"][kind]["sd"], strict=True)
+        x = {"data": fx["x"][:1].contiguous()}  # batch 1: the only batch size a sharded model accepts (encoder_processor_decoder.py:165-183)
+        full = m(x)["data"]
+        got = m(x, model_comm_group=dist.group.WORLD)["data"]
+        _close(got, full, f"AnemoiModelEncProcDec {kind} sharded")
+        if world == 2:  # the single-rank result is the reference golden's first batch element
+            ref = fx["cases"][kind]["y"][:1]
+            assert ((full - ref).abs().max() / ref.abs().max()).item() <= 1e-4
 
 
 def check_goldens_single_rank(rank, world):

@@ -14,12 +14,14 @@ import torch
 from torch import Tensor
 from torch import nn
 
+from .. import ops
 from ..distributed.graph import group_rank
 from ..distributed.graph import group_size
 from ..distributed.khop_edges import build_graph_partition
 from ..distributed.khop_edges import ensure_edges_are_dst_sorted
 from ..distributed.shapes import GraphShardInfo
 from . import _functional as Fn
+from . import _reorder as RO
 from .block import GraphConvProcessorBlock
 from .block import GraphTransformerProcessorBlock
 from .utils import compute_mlp_hidden_dim
@@ -149,9 +151,13 @@ class GNNProcessor(BaseProcessor):
             if group_size(model_comm_group) > 1:
                 edge_attr, edge_index, edge_sizes = _shard_edges_by_dst(edge_attr, edge_index, n_nodes, n_nodes, model_comm_group)
                 shard_info = GraphShardInfo(nodes=shard_info.nodes, edges=edge_sizes)
+        plan = RO.locality_plan(edge_index, n_nodes) if RO.ENABLED and group_size(model_comm_group) == 1 else None
+        if plan is not None:  # run every layer in the locality order (layers/_reorder.py); identical results up to summation order
+            x = ops.cast_pad(x, x.dtype, idx=plan.perm)
+            edge_attr, edge_index = RO.permute_edge_attr(edge_attr, plan), plan.edge_index
         for block in self.proc:
             x, edge_attr = block(x, edge_attr, edge_index, shard_info, model_comm_group)
-        return x
+        return x if plan is None else ops.cast_pad(x, x.dtype, idx=plan.rank)
 
 
 class GraphTransformerProcessor(BaseProcessor):
@@ -225,10 +231,17 @@ class GraphTransformerProcessor(BaseProcessor):
             raise NotImplementedError("shard_strategy='heads' needs the full dst-sorted edge list (graph provider: get_edges(shard_edges=False))")
         elif group_size(model_comm_group) > 1:
             edge_index = _localise_presharded_edges(edge_index, shard_info.nodes, model_comm_group)
+        cond = kwargs.get("cond")
+        plan = RO.locality_plan(edge_index, n_nodes) if RO.ENABLED and group_size(model_comm_group) == 1 else None
+        if plan is not None:  # run every layer in the locality order (layers/_reorder.py); identical results up to summation order
+            x = ops.cast_pad(x, x.dtype, idx=plan.perm)
+            edge_attr, edge_index = RO.permute_edge_attr(edge_attr, plan), plan.edge_index
+            if cond is not None:
+                cond = ops.cast_pad(cond, cond.dtype, idx=plan.perm)
         shared_edges = None
         if all(isinstance(b.edge_pre_mlp, nn.Identity) for b in self.proc):
             shared_edges = self.proc[0].prepare_edges(edge_attr, Fn.compute_dtype(x))  # one padded fp32 copy for all layers
         for block in self.proc:
             x, _ = block(x, edge_attr, edge_index, shard_info, batch_size, n_nodes, model_comm_group, edge_attr_prepared=shared_edges,
-                         cond=kwargs.get("cond"))  # fmt: skip
-        return x
+                         cond=cond)  # fmt: skip
+        return x if plan is None else ops.cast_pad(x, x.dtype, idx=plan.rank)

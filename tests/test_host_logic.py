@@ -196,3 +196,24 @@ def test_reference_default_yaml_kwargs_construct():
     GNNBackwardMapper(num_chunks=1, in_channels_src=C, in_channels_dst=C, hidden_dim=C, out_channels_dst=9, edge_dim=11, **gcommon)
     # the gated variants the YAML comments name
     GraphTransformerProcessor(num_layers=2, num_chunks=1, num_channels=C, edge_dim=11, **{**common, "mlp_implementation": "swiglu", "mlp_hidden_ratio": 2.67})
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) prints one JSON line with the contract's keys, no GPU needed."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "small", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, check=True).stdout.strip().splitlines()[-1]  # fmt: skip
+    line = json.loads(out)
+    assert line["impl"] == "reference" and line["unit"] == "ms/step" and line["higher_is_better"] is False and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "ms/step", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # ranks other than 0 of a torchrun launch exit without work and without output
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    quiet = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "small", "--steps", "1"],
+                           capture_output=True, text=True, timeout=600, env=env)  # fmt: skip
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""

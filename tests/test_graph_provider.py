@@ -79,11 +79,10 @@ def test_create_graph_provider_factory(golden):
     assert isinstance(noop, NoOpGraphProvider) and noop.edge_dim == 0 and noop.get_edges(batch_size=2) == (None, None, None)
 
 
-def _worker(rank, world, port, fixture, out):
+def _worker(rank, world, init_file, fixture, out):
     import torch.distributed as dist
 
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)  # no fixed port: nothing to collide with
     try:
         g = torch.load(fixture, weights_only=False)
         p = _provider(g)
@@ -113,7 +112,7 @@ def test_sharded_edges_world2_gloo(golden, tmp_path):
     g = golden("graph_provider")
     fixture = os.path.join(os.path.dirname(__file__), "golden", "graph_provider.pt")
     out = str(tmp_path / "shard")
-    mp.spawn(_worker, args=(2, 29611, fixture, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, str(tmp_path / "rdv"), fixture, out), nprocs=2, join=True)
     full_ea, full_ei = g["edges"][1]["edge_attr"], g["edges"][1]["edge_index"]
     part = K.build_graph_partition(full_ei, 2, (g["n_src"], g["n_dst"]))
     got = [torch.load(f"{out}.{r}", weights_only=False) for r in range(2)]

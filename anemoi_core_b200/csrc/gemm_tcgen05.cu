@@ -898,6 +898,16 @@ int linear_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, int64
   int bn = 256, cg = 1;
   if (ep.N <= 128 || tiles_m * ((ep.N + 255) / 256) < 2 * (int64_t)num_sms()) bn = 128;
   if (bn == 256 && env_cta_group() == 2 && ((ep.M + 255) / 256) * ((ep.N + 255) / 256) >= (int64_t)num_sms()) cg = 2;
+  {
+    // opt-in experiment (ANEMOI_B200_GEMM_PAIR_BN128=1, not yet measured): 256 x 128 CTA-pair tiles for narrow outputs, where 256 x 256
+    // tiles quantise badly (N = 512, M = 40 962: 322 tiles on 74 pairs = 5 waves at 87 %; 644 half tiles = 9 half waves at 96.7 %)
+    static int pair128 = -1;
+    if (pair128 < 0) {
+      const char* e = getenv("ANEMOI_B200_GEMM_PAIR_BN128");
+      pair128 = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (pair128 && cg == 2 && ep.N <= 512) bn = 128;
+  }
   CUtensorMap tmA, tmW, tmOut, tmRes;
   int rc = get_tensor_map(A, ep.M, K, lda, kBM, &tmA);
   if (rc) return rc;
@@ -936,7 +946,7 @@ int linear_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, int64
     }
     epi_mode |= (abl << 8) & kAblMask;
   }
-  rc = cg == 2     ? launch<256, 2>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s)
+  rc = cg == 2     ? (bn == 128 ? launch<128, 2>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s) : launch<256, 2>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s))
        : bn == 128 ? launch<128, 1>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s)
                    : launch<256, 1>(tmA, tmW, tmOut, tmRes, K, epi_mode, ep, s);
   if (rc == 0 && ep.stats_out && !fused_stats) rc = launch_partial_row_stats(ep.out, ep.ldo, ep.o_dtype, ep.M, ep.N, ep.stats_out, s);

@@ -85,6 +85,19 @@ class GraphConvProcessorBlock(GraphConvBaseBlock):
         dt = Fn.compute_dtype(x, edge_attr)
         if self.emb_edges is not None:
             edge_attr = self.emb_edges.run(edge_attr, dt)
+        halo_plan = layer_kwargs.get("halo_plan")
+        if halo_plan is not None:
+            # halo form (distributed/halo.py): own rows + the remote source rows our edges name in one compact table; the edge list was
+            # relabelled onto it (local dst ids), so the node-level projections run over n_local + n_halo rows instead of all N and the
+            # aggregate is local from the start.  ``edge_index`` is ignored in favour of the plan's.
+            C, n_local = self.in_channels, x.shape[0]
+            table = torch.empty((halo_plan.n_table, C), dtype=dt, device=x.device)
+            ops.cast_pad(x, dt, out=table[:n_local])
+            halo_plan.exchange(table)
+            csr = Fn.csr_for(halo_plan.edge_index, halo_plan.n_table, n_local)
+            agg_buf = torch.empty((n_local, 2 * C), dtype=dt, device=x.device)
+            _, edges_new = self.conv.run(table, table[:n_local], edge_attr, csr, dt, out=agg_buf[:, C:])
+            return self._node_update(x, agg_buf, dt), edges_new
         # block.py:375 — every rank needs all source rows: all-gather of the node shards (no-op on one GPU)
         x_full = gather_rows(x, shard_info.nodes if shard_info is not None else None, model_comm_group)
         n_local = x.shape[0]

@@ -8,6 +8,7 @@ and CPU offload are training-memory devices of the reference and are accepted bu
 
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -58,6 +59,9 @@ class BaseProcessor(nn.Module):
         self.proc = nn.ModuleList([layer_class(**layer_kwargs) for _ in range(self.num_layers)])
 
 
+# sharded GNN processor: halo all-to-all of the source rows instead of the all-gather of x per layer.  Opt-in until it has run on NCCL
+# (verified under Gloo, tests/test_sharded_forward_gloo.py); the GraphTransformer processor's halo exchange is the default (block.HALO_EXCHANGE).
+GNN_HALO = os.environ.get("ANEMOI_B200_GNN_HALO", "0") == "1"
 _SHARD_CACHE: dict = {}
 
 
@@ -151,12 +155,18 @@ class GNNProcessor(BaseProcessor):
             if group_size(model_comm_group) > 1:
                 edge_attr, edge_index, edge_sizes = _shard_edges_by_dst(edge_attr, edge_index, n_nodes, n_nodes, model_comm_group)
                 shard_info = GraphShardInfo(nodes=shard_info.nodes, edges=edge_sizes)
+        halo_plan = None
+        if GNN_HALO and group_size(model_comm_group) > 1:
+            # halo exchange instead of the per-layer all-gather of x (block.py:375): needs local dst ids (the edges above keep global ones)
+            from ..distributed.halo import halo_plan_for
+
+            halo_plan = halo_plan_for(_localise_presharded_edges(edge_index, shard_info.nodes, model_comm_group), shard_info.nodes, model_comm_group)
         plan = RO.locality_plan(edge_index, n_nodes) if RO.ENABLED and group_size(model_comm_group) == 1 else None
         if plan is not None:  # run every layer in the locality order (layers/_reorder.py); identical results up to summation order
             x = ops.cast_pad(x, x.dtype, idx=plan.perm)
             edge_attr, edge_index = RO.permute_edge_attr(edge_attr, plan), plan.edge_index
         for block in self.proc:
-            x, edge_attr = block(x, edge_attr, edge_index, shard_info, model_comm_group)
+            x, edge_attr = block(x, edge_attr, edge_index, shard_info, model_comm_group, halo_plan=halo_plan)
         return x if plan is None else ops.cast_pad(x, x.dtype, idx=plan.rank)
 
 

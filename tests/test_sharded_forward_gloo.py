@@ -79,6 +79,13 @@ def check_processors(rank, world):
         local = m(shard_rows(x, sizes, group).contiguous(), 1, GraphShardInfo(nodes=sizes), ea, ei, group)
         assert local.shape[0] == sizes[rank]
         _close(gather_rows(local, sizes, group), full, kind)
+        if kind == "gnn":  # opt-in halo form of the sharded GNN processor (node projections over local + halo rows only)
+            import anemoi_core_b200.layers.processor as proc_mod
+
+            proc_mod.GNN_HALO = True
+            local_h = m(shard_rows(x, sizes, group).contiguous(), 1, GraphShardInfo(nodes=sizes), ea, ei, group)
+            proc_mod.GNN_HALO = False
+            _close(gather_rows(local_h, sizes, group), full, "gnn, halo exchange")
         # bf16 inputs select the tensor-core host path (LayerNorm folded into the GEMMs, row statistics handed over as tensor tags,
         # K-padded operands): its bookkeeping must survive the sharding too.  Loose tolerance: every stage rounds to bf16.
         xb = x.bfloat16()

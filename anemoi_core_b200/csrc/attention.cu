@@ -654,7 +654,8 @@ static int launch_pipe_mode(const AttnParams& p, int n_slabs, int active_lanes, 
   constexpr int smem = 4 * kSlots * kSlotBytes;  // 4 warps per CTA
   const int64_t max_pitch = (int64_t)1 << 31;  // gather addresses are formed from 32-bit byte pitches
   if (p.ldk * (int64_t)sizeof(T) >= max_pitch || p.ldv * (int64_t)sizeof(T) >= max_pitch || p.lde * 4 >= max_pitch) return 1;
-  static int blocks_per_sm = 0;
+  static int blocks_per_sm_dev[kMaxDevices] = {};
+  int& blocks_per_sm = blocks_per_sm_dev[current_device()];
   if (blocks_per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute(gt_attention_pipe_kernel<T, NCH, LPH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(attention)");

@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(128, 2) gt_attention_mma_kernel(const AttnPara
 template <int CH>
 int launch_ch(const AttnParams& p, int n_slabs, cudaStream_t s) {
   constexpr int smem = 4 * kWarpSmem;
-  static int blocks_per_sm = 0;
+  static int blocks_per_sm_dev[kMaxDevices] = {};
+  int& blocks_per_sm = blocks_per_sm_dev[current_device()];
   if (blocks_per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute(gt_attention_mma_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gt_attention_mma_kernel)");

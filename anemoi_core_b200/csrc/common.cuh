@@ -39,14 +39,22 @@ inline int launch_status(const char* what) {
   return 0;
 }
 
+// Per-device caches: function attributes (cudaFuncSetAttribute), occupancy results and the SM count belong to the CURRENT device of the
+// calling thread; a process that drives several GPUs must not reuse what it learned on the first one.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
 inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;  // B200
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0) n[dev] = 148;  // B200
   }
-  return n;
+  return n[dev];
 }
 
 // ---- dtype helpers -------------------------------------------------------------------------------------------

@@ -856,7 +856,8 @@ template <int BN, int CG>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmOut, const CUtensorMap& tmRes, int64_t K, int epi_mode,
                   const EpiParams& ep, cudaStream_t s) {
   using Cfg = GemmCfg<BN, CG>;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel)");

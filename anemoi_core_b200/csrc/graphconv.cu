@@ -264,7 +264,8 @@ template <typename T, int NCH>
 static int launch_gc_pipe(const void* h, int64_t ldh, const float* gamma, const float* beta, const void* e, int64_t lde, void* e_new, int64_t ldn,
                           const int32_t* colptr, void* out, int64_t ldo, int64_t n_dst, float eps, cudaStream_t s) {
   constexpr int smem = 4 * kGcSlots * 2 * NCH * 512;
-  static int blocks_per_sm = 0;
+  static int blocks_per_sm_dev[kMaxDevices] = {};
+  int& blocks_per_sm = blocks_per_sm_dev[current_device()];
   if (blocks_per_sm == 0) {
     cudaError_t err = cudaFuncSetAttribute(graphconv_ln_aggregate_pipe_kernel<T, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(graphconv)");

@@ -5,6 +5,7 @@ or PyTorch here; a CPU tensor is an error (there is no fallback path).
 
 from __future__ import annotations
 
+import threading
 from dataclasses import dataclass
 from typing import Optional
 
@@ -37,14 +38,22 @@ def stop_timing() -> list:
 
 
 class _Timed:
-    __slots__ = ("name", "flops", "bytes", "ev")
+    """Scope of ONE C-ABI call: counts the launch, optionally brackets it with CUDA events, and makes the device of the call's tensors
+    (recorded by ``_need_cuda``) the current device for its duration — the library launches on the calling thread's current device and
+    ``_stream()`` hands it that device's current stream, so a model on cuda:1 works without ``torch.cuda.set_device`` like any torch op."""
+
+    __slots__ = ("name", "flops", "bytes", "ev", "guard")
 
     def __init__(self, name: str, flops: float = 0.0, nbytes: float = 0.0):
-        self.name, self.flops, self.bytes, self.ev = name, flops, nbytes, None
+        self.name, self.flops, self.bytes, self.ev, self.guard = name, flops, nbytes, None, None
 
     def __enter__(self):
         global LAUNCHES
         LAUNCHES += 1
+        dev = getattr(_CALL, "dev", None)
+        if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+            self.guard = torch.cuda.device(dev)
+            self.guard.__enter__()
         if _TIMER is not None:
             self.ev = torch.cuda.Event(enable_timing=True)
             self.ev.record()
@@ -55,7 +64,12 @@ class _Timed:
             end = torch.cuda.Event(enable_timing=True)
             end.record()
             _TIMER.append((self.name, self.ev, end, self.flops, self.bytes))
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
         return False
+
+
+_CALL = threading.local()  # device of the tensors of the C-ABI call being prepared on this thread (set by _need_cuda)
 
 
 def _nbytes(*ts: Optional[Tensor]) -> float:
@@ -81,6 +95,8 @@ def _need_cuda(*tensors: Optional[Tensor]) -> torch.device:
             dev = t.device
         elif t.device != dev:
             raise RuntimeError(f"tensors on different devices: {dev} vs {t.device}")
+    if dev is not None:
+        _CALL.dev = dev
     return dev
 
 

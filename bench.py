@@ -118,49 +118,87 @@ def state_dicts(model):
 # ----------------------------------------------------------------------------------------------------------------
 # CPU reference leg (oracle port)
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_step(w, gr, sds, x_grid, x_mesh, sample_layers):
-    """One bounded CPU sample: encoder + `sample_layers` processor layers + decoder (fp32).  Returns (t_enc, t_layers, t_dec) seconds."""
-    from oracle import restatement as R
-
-    H, L = w["heads"], w["layers"]
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        if w["kind"] == "graphtransformer":
-            _, lat = R.gt_forward_mapper(sds["encoder"], x_grid, x_mesh, gr["enc_attr"], gr["enc_index"], H)
-            t1 = time.perf_counter()
-            proc = R.gt_processor(sds["processor"], lat, gr["proc_attr"], gr["proc_index"], L, H, max_layers=sample_layers)
-            t2 = time.perf_counter()
-            R.gt_backward_mapper(sds["decoder"], proc + lat, x_grid, gr["dec_attr"], gr["dec_index"], H)
-        else:
-            src_emb, lat = R.gnn_forward_mapper(sds["encoder"], x_grid, x_mesh, gr["enc_attr"], gr["enc_index"])
-            t1 = time.perf_counter()
-            proc = R.gnn_processor(sds["processor"], lat, gr["proc_attr"], gr["proc_index"], L, max_layers=sample_layers)
-            t2 = time.perf_counter()
-            R.gnn_backward_mapper(sds["decoder"], proc + lat, src_emb, gr["dec_attr"], gr["dec_index"])
-        t3 = time.perf_counter()
-    return t1 - t0, t2 - t1, t3 - t2
+def _ref_kwargs(w, gr):
+    return dict(in_grid=w["in_grid"], in_mesh=w["in_mesh"], out_grid=w["out_grid"], num_channels=w["C"], num_layers=w["layers"],
+                edge_dim=gr["edge_dim"], num_heads=w["heads"])  # fmt: skip
 
 
-def cpu_baseline(w, gr, sds, x_grid, x_mesh, repeats=1, sample_layers=2):
+class CpuReference:
+    """The reference's CPU forward step for a workload.  kind "reference": the UNMODIFIED reference modules (oracle/reference_step.py:
+    /root/reference or baseline/_ref + oracle/standins); kind "port": oracle/restatement.py when the reference is not on this box.
+    ``sample_layers`` < layers times encoder + that many processor layers + decoder and scales the processor linearly (stated in
+    ``sample``); None runs the whole step."""
+
+    def __init__(self, w, gr, sds, sample_layers=None):
+        from oracle import reference_step as RS
+
+        self.w, self.gr, self.sds = w, gr, sds
+        self.sample_layers = None if (sample_layers is None or sample_layers >= w["layers"]) else sample_layers
+        self.kind, self.ref = "port", None
+        if RS.reference_root() is not None:
+            try:
+                self.ref = RS.ReferenceStep(w["kind"], state_dicts=sds, max_layers=self.sample_layers, **_ref_kwargs(w, gr))
+                self.kind = "reference"
+            except Exception as e:  # noqa: BLE001 - fall back to the port, and say why
+                print(f"[bench] reference modules unavailable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+
+    def step(self):
+        """(t_encoder, t_processor_sample, t_decoder) seconds of one step."""
+        w, gr, sds = self.w, self.gr, self.sds
+        if self.ref is not None:
+            t = []
+            self.ref(self.x_grid, self.x_mesh, gr, t)
+            return t[0]
+        from oracle import restatement as R
+
+        H, L = w["heads"], w["layers"]
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            if w["kind"] == "graphtransformer":
+                _, lat = R.gt_forward_mapper(sds["encoder"], self.x_grid, self.x_mesh, gr["enc_attr"], gr["enc_index"], H)
+                t1 = time.perf_counter()
+                proc = R.gt_processor(sds["processor"], lat, gr["proc_attr"], gr["proc_index"], L, H, max_layers=self.sample_layers)
+                t2 = time.perf_counter()
+                R.gt_backward_mapper(sds["decoder"], proc + lat, self.x_grid, gr["dec_attr"], gr["dec_index"], H)
+            else:
+                src_emb, lat = R.gnn_forward_mapper(sds["encoder"], self.x_grid, self.x_mesh, gr["enc_attr"], gr["enc_index"])
+                t1 = time.perf_counter()
+                proc = R.gnn_processor(sds["processor"], lat, gr["proc_attr"], gr["proc_index"], L, max_layers=self.sample_layers)
+                t2 = time.perf_counter()
+                R.gnn_backward_mapper(sds["decoder"], proc + lat, src_emb, gr["dec_attr"], gr["dec_index"])
+            t3 = time.perf_counter()
+        return t1 - t0, t2 - t1, t3 - t2
+
+    def ms(self, x_grid, x_mesh):
+        self.x_grid, self.x_mesh = x_grid, x_mesh
+        te, tl, td = self.step()
+        scale = 1.0 if self.sample_layers is None else self.w["layers"] / self.sample_layers
+        return (te + td + tl * scale) * 1e3, (te, tl, td)
+
+    def describe(self, parts) -> str:
+        te, tl, td = parts
+        what = ("the unmodified reference modules (anemoi.models.layers.{mapper,processor}, pyg attention backend) via oracle/reference_step.py"
+                if self.kind == "reference" else "oracle/restatement.py (port of the reference PyTorch path)")
+        if self.sample_layers is None:
+            return f"{what}, fp32 on CPU, ONE WHOLE step: encoder {te:.2f}s + all {self.w['layers']} processor layers {tl:.2f}s + decoder {td:.2f}s"
+        return (f"{what}, fp32 on CPU: encoder {te:.2f}s + {self.sample_layers} of {self.w['layers']} processor layers {tl:.2f}s + decoder "
+                f"{td:.2f}s; processor scaled x{self.w['layers'] / self.sample_layers:g} (layers are identical)")
+
+
+def cpu_baseline(w, gr, sds, x_grid, x_mesh):
+    """Bounded CPU sample beside the GPU number (rank 0, N = 1): one warm-up + one timed WHOLE step when a step is ~10 s (cfg2),
+    encoder + 2 layers + decoder scaled for the 16 x 1024 workloads."""
     torch.set_num_threads(os.cpu_count() or 1)
-    best = None
-    for _ in range(repeats + 1):  # first pass is the warm-up
-        te, tl, td = cpu_reference_step(w, gr, sds, x_grid, x_mesh, sample_layers)
-        best = (te, tl, td)
-    te, tl, td = best
-    full = te + td + tl * w["layers"] / sample_layers
-    return {
-        "value": full * 1e3,
-        "unit": "ms/step",
-        "cores": torch.get_num_threads(),
-        "kind": "port",
-        "sample": f"oracle/restatement.py fp32 on CPU: encoder {te:.2f}s + {sample_layers} of {w['layers']} processor layers {tl:.2f}s + decoder {td:.2f}s; "
-                  f"processor scaled x{w['layers'] / sample_layers:g} (layers are identical)",
-    }  # fmt: skip
+    ref = CpuReference(w, gr, sds, sample_layers=None if w["C"] <= 512 else 2)
+    ref.ms(x_grid, x_mesh)  # warm-up
+    ms, parts = ref.ms(x_grid, x_mesh)
+    return {"value": ms, "unit": "ms/step", "cores": torch.get_num_threads(), "kind": ref.kind, "sample": ref.describe(parts)}
 
 
 def run_reference(args, w):
-    """--impl reference: the reference's CPU path (oracle port, all host threads), K bounded samples."""
+    """--impl reference: the reference's own CPU implementation of the step on all host threads (unmodified reference modules when
+    baseline/_ref or /root/reference is present, else the oracle port), WHOLE steps (no extrapolation for cfg2), as many of the K
+    requested as fit a ~150 s budget; ``steps`` reports how many were timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -169,26 +207,27 @@ def run_reference(args, w):
     gr = build_graph(w["grid"], w["mesh_level"])
     model = build_model(w, gr)
     sds = state_dicts(model)
+    del model
     x_grid, x_mesh = make_inputs(w, gr)
     torch.set_num_threads(os.cpu_count() or 1)
-    sample_layers = 1
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_step(w, gr, sds, x_grid, x_mesh, sample_layers)
-    vals = []
+    ref = CpuReference(w, gr, sds, sample_layers=None if w["C"] <= 512 else 2)
+    n_warm = min(max(args.warmup, 1), 2)
+    for _ in range(n_warm):
+        ref.ms(x_grid, x_mesh)
+    vals, parts = [], None
     t_budget = time.perf_counter()
-    for _ in range(args.steps):
-        te, tl, td = cpu_reference_step(w, gr, sds, x_grid, x_mesh, sample_layers)
-        vals.append((te + td + tl * w["layers"] / sample_layers) * 1e3)
+    for _ in range(max(args.steps, 1)):
+        ms, parts = ref.ms(x_grid, x_mesh)
+        vals.append(ms)
         if time.perf_counter() - t_budget > 150.0:  # keep the arm within a few minutes whatever K is
             break
     ms = statistics.mean(vals)
     line = {
         "impl": "reference", "metric": "forward ms/step", "value": ms, "unit": "ms/step", "n_gpus": args.gpus, "steps": len(vals),
-        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "warmup": n_warm, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": f"{args.workload}: {w['desc']}", "batch": 1, "l2": "n/a (CPU)"},
-        "cpu_baseline": {"value": ms, "unit": "ms/step", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"per step: encoder + {sample_layers} of {w['layers']} processor layers + decoder on CPU (oracle port of the "
-                                   f"reference PyTorch path), processor time scaled x{w['layers'] / sample_layers:g}; {len(vals)} samples"},
+        "cpu_baseline": {"value": ms, "unit": "ms/step", "cores": torch.get_num_threads(), "kind": ref.kind,
+                         "sample": ref.describe(parts) + f"; mean of {len(vals)} timed steps after {n_warm} warm-up"},
         "e2e": {"value": ms, "unit": "ms/step", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }  # fmt: skip
@@ -279,6 +318,30 @@ def main():
         run = lambda: replay()  # noqa: E731
     else:
         run = lambda: step(x_grid, x_mesh)  # noqa: E731
+
+    # ---- the timed path must be the parity-tested path: graph replay == eager launches of the same step, and (N > 1) the sharded step ==
+    # the single-GPU step computed by rank 0 on the whole graph (the path tests/test_gpu_parity.py pins against the oracle) ---------------
+    def rel_err(a, b):
+        a, b = a.float(), b.float()
+        return {"max_rel": ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item(), "rel_l2": ((a - b).norm() / b.norm().clamp_min(1e-30)).item()}
+
+    eager_out = step(x_grid, x_mesh).clone()
+    checks = {}
+    if use_graph:
+        checks["replay_vs_eager"] = rel_err(run().clone(), eager_out)
+        if checks["replay_vs_eager"]["max_rel"] > 1e-6:
+            raise SystemExit(f"[bench] CUDA-graph replay differs from the eager step: {checks['replay_vs_eager']}")
+    if world > 1:
+        if rank == 0:
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                single = model(x_grid, x_mesh, gd)  # no group: the whole graph on this GPU
+            checks["sharded_vs_single_gpu"] = rel_err(eager_out, single)
+            del single
+        bad = torch.tensor([1 if (rank == 0 and checks["sharded_vs_single_gpu"]["rel_l2"] > 5e-3) else 0], device=dev)
+        torch.distributed.all_reduce(bad, op=torch.distributed.ReduceOp.MAX)
+        if bad.item():
+            raise SystemExit(f"[bench] sharded step differs from the single-GPU step: {checks.get('sharded_vs_single_gpu')}")
+    del eager_out
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -383,20 +446,31 @@ def main():
                          "frac_tensor": round(tf / pk["tensor"], 4), "frac_hbm": round(gb / pk["hbm"], 4)}  # fmt: skip
     top = next(iter(kernels))
     topd = agg[top]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
-    if top == "linear_tcgen05" and os.path.exists(tpath):
-        # dram__bytes_read + dram__bytes_write per launch from the committed `ncu --set full` capture of this kernel (not measurable here)
-        traffic = json.load(open(tpath))["avg_dram_bytes_per_launch"]
-    if top == "linear_tcgen05":
+    # dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed `ncu --set full` capture of THIS workload
+    # (profiles/r2/traffic_<workload>.json, written by profiles/ncu_traffic.py); null when no matching capture exists
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r2", f"traffic_{args.workload}.json")
+    if world == 1 and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("kernel_class") == top:
+            traffic, traffic_src = tj["avg_dram_bytes_per_launch"], os.path.relpath(tpath, ROOT)
+    if world > 1:
+        # per-launch event timing of eager launches includes host gaps at this size; the honest device-side figure at N > 1 is the whole
+        # replayed step: this rank's algorithmic GEMM flops / the step time, against the sustained tensor peak
+        fl = agg.get("linear_tcgen05", {"flops": 0.0})["flops"] / n_prof
+        ach = fl / (ms_dev * 1e-3) / 1e12
+        roofline = {"kernel": "whole step (graph replay), GEMM flops of this rank's shard", "bound": "tensor", "achieved": ach, "peak": pk["tensor"],
+                    "unit": "TFLOP/s", "frac": ach / pk["tensor"], "traffic": None, "peak_source": pk["src"] + " sustained bf16"}  # fmt: skip
+    elif top == "linear_tcgen05":
         ach = topd["flops"] / (topd["ms"] * 1e-3) / 1e12
         roofline = {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tensor"], "traffic": traffic, "traffic_unit": "bytes per launch (DRAM read+write, ncu, profiles/r1_gemm_traffic.json)",
+                    "frac": ach / pk["tensor"], "traffic": traffic, "traffic_unit": "bytes per launch (DRAM read+write, ncu)", "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": topd["bytes"] / topd["launches"], "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
                     "share_of_step": kernels[top]["share"]}  # fmt: skip
     else:
         ach = topd["bytes"] / (topd["ms"] * 1e-3) / 1e9
-        roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
+        roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": traffic,
+                    "traffic_source": traffic_src, "algorithmic_bytes_per_launch": topd["bytes"] / topd["launches"],
                     "peak_source": pk["src"], "share_of_step": kernels[top]["share"]}  # fmt: skip
 
     if rank != 0:
@@ -415,6 +489,7 @@ def main():
         "clocks": clk,
         "roofline": roofline,
         "kernels": kernels,
+        "parity": checks,
         "wall_s_timed_region": wall_dev,
     }  # fmt: skip
     if rollout is not None:

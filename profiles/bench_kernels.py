@@ -53,6 +53,13 @@ if "attn" in which:
         ops.gt_attention(buf[:, :C], buf[:, C : 2 * C], buf[:, 2 * C : 3 * C], csr, H, edge_attr=ea, b_edge=b_e, qw=buf[:, 4 * C :], abar=out[:, C:], dp=dp,
                          add=buf[:, 3 * C : 4 * C], out=out[:, :C])  # fmt: skip
 
+    if "reorder" in which:  # same kernel on the locality-ordered (Hilbert) relabelling of the graph (layers/_reorder.py)
+        from anemoi_core_b200.layers import _reorder as RO
+
+        plan = RO.locality_plan(gr["proc_index"].to(dev), N, min_nodes=0)
+        csr = ops.build_csr(plan.edge_index, N, N)
+        ea = ea.index_select(0, plan.edge_perm).contiguous()
+        print(json.dumps({"reorder": True, "reuse16_before": RO.source_reuse(gr["proc_index"]), "reuse16_after": RO.source_reuse(plan.edge_index)}))
     med, mn = timeit(attn)
     # algorithmic bytes: q, k, v, self read + out written (N*C*2 each) + qw/abar + per edge: src id 4 B + 64 B attributes
     alg = 5 * N * C * 2 + 2 * N * H * dp * 2 + E * (4 + 64) + 4 * N

@@ -37,6 +37,17 @@ SIGNATURES = {
     "anemoi_b200_gt_attention_fwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                      c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                      c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p],
+    "anemoi_b200_attn_tile_plan": [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "anemoi_b200_gt_attention_tiled_fwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                                           c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                           c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p],
+    "anemoi_b200_ipc_alloc": [c_int64, c_void_p, c_void_p],
+    "anemoi_b200_ipc_open": [c_void_p, c_void_p],
+    "anemoi_b200_ipc_close": [c_void_p],
+    "anemoi_b200_ipc_free": [c_void_p],
+    "anemoi_b200_peer_rendezvous": [c_void_p, c_int64, c_int64, c_void_p],
+    "anemoi_b200_halo_push": [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p],
+    "anemoi_b200_halo_wait": [c_void_p, c_int64, c_int64, c_void_p],
     "anemoi_b200_graphconv_ln_aggregate": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                            c_int64, c_int64, c_int64, c_float, c_int, c_void_p],
     "anemoi_b200_cast_pad": [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p],

@@ -1,0 +1,428 @@
+// attention_tile.cu — GraphTransformer edge-softmax attention (folded lin_edge form, bf16) on DESTINATION TILES.
+// Replaces layers/conv.py:103-147 + triton/gt.py:81-179 for graphs whose node order has locality (layers/_reorder.py).
+//
+// Why a second formulation.  The warp-per-node kernel (attention.cu) is instruction-issue bound: 243 warp-instructions per edge, a third
+// of them bf16 -> fp32 unpacks and per-edge address / ring bookkeeping (profiles/r1_ncu_attention_v10_sass_summary.txt); reordering the
+// nodes for L2 locality moved it from 135 to 130 us only (profiles/r2/call1_kernels_attn_reorder.jsonl).  Here a tile of <= 16 consecutive
+// destination nodes and the <= 64 DISTINCT source rows its edges name (48 on the Hilbert-ordered ico-6 mesh, where the 128 edges of a
+// tile re-use every source 2.65 times) is handled as a small dense problem on the warp-level tensor cores:
+//     S[16 x U]   = Q_h[16 x Ch] . K_h[U x Ch]^T                       mma.sync m16n8k16 bf16, K rows straight from shared memory (ldmatrix)
+//     S          <- S * scale*log2e + B_h,   B_h[d, u] = (W_e,h^T q_d,h) . a_(u->d) * scale*log2e on edges, -inf elsewhere (the sparsity mask)
+//     P           = exp2(S - rowmax),  l = rowsum(P)                    fp32, in the accumulator registers
+//     O[16 x Ch]  = P . V_h[U x Ch]                                     P re-used register-for-register as the A fragment, V via ldmatrix.trans
+//     abar[d, h]  = sum_e P[d, slot(e)] / l * a_e                       per (dst, half of the attributes) lane over the dst's edge run
+// so every gathered k / v row is fetched ONCE per tile (not once per edge), no element is unpacked on the FP32 pipe and the per-edge work
+// shrinks to the two attribute dot products.  One CTA = (tile, group of 256 / Ch heads), one warp per head; all source rows of the tile
+// are gathered with 16-byte cp.async while the warps build their bias tiles.  Two CTAs per SM overlap each other's gather and math.
+//
+// The tile plan (which dst rows form a tile, the slot list of each tile, the slot of every edge) depends on the graph only and is built
+// once on the host by anemoi_b200_attn_tile_plan (greedy: close a tile at 16 rows, 64 slots or 512 edges; duplicate (src, dst) pairs get
+// separate slots).  A graph with a destination of in-degree > 64 has no plan: the caller keeps the warp-per-node kernel.
+#include <vector>
+
+#include "attention.h"
+
+namespace anemoi {
+namespace {
+
+constexpr int kTD = 16;      // destination rows per tile (the M of m16n8k16)
+constexpr int kSMax = 64;    // source slots per tile
+constexpr int kBP = 72;      // bias row pitch in floats: rows 8 banks apart -> conflict-free float2 fragment loads per half warp
+constexpr int kAttrBytes = 10752;  // staged edge attributes of a tile: 224 edges x 12 floats (the planner is told edges <= kAttrBytes / (4 dp))
+constexpr int kEMetaMax = 224;     // (slot, row) entries staged per tile; 2 x (67584 + 36864 + 10752 + 448) + 2 KB = the 228 KB of an SM
+constexpr int kRowB = 528;   // shared-memory pitch of a 512-byte k / v row segment: 132 words = 4 (mod 32) -> conflict-free ldmatrix rows
+constexpr int kBiasBytes = kTD * kBP * 4;
+
+struct TilePlan {
+  const int4* tile_meta;    // [n_tiles] {first dst row, first entry in slot_src, first edge, rows | slots << 8 | edges << 16}: ONE 16-byte load per CTA
+  const int32_t* slot_src;  // source row of every slot
+  const uint16_t* emeta;    // [E] slot (inside its tile) | row (inside its tile) << 8 of every edge
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void sts_zero16(uint32_t addr) { asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory"); }
+
+// CH = channels per head (32 / 64), DPH = attributes per lane = dp / 2 (the two lanes of a destination row split the attribute vector)
+template <int CH, int DPH>
+__global__ void __launch_bounds__(32 * (256 / CH), 2) gt_attention_tile_kernel(const AttnParams p, const TilePlan tp) {
+  constexpr int HPC = 256 / CH;  // heads per CTA: their channels are one 512-byte segment of a row
+  constexpr int NT = 32 * HPC;
+  constexpr int KS = CH / 16;    // k-steps of Q.K^T
+  constexpr int NJO = CH / 8;    // 8-channel n-tiles of the output
+  constexpr int kOutPitch = CH * 2 + 16;  // staging pitch of the output tile (bytes): conflict-free 4-byte fragment stores
+  static_assert(16 * kOutPitch <= kBiasBytes, "output staging re-uses the warp's bias tile");
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int tile = blockIdx.x, hg = blockIdx.y;
+  const int h = hg * HPC + warp;  // this warp's head
+  const uint32_t sK = smem_u32(smem), sV = sK + kSMax * kRowB;
+  uint8_t* const bias_raw = smem + 2 * kSMax * kRowB + warp * kBiasBytes;
+  float* const biasp = reinterpret_cast<float*>(bias_raw);
+  float* const attr_s = reinterpret_cast<float*>(smem + 2 * kSMax * kRowB + HPC * kBiasBytes);  // [ne][dp] fp32, packed
+  const uint32_t sA = sV + kSMax * kRowB + HPC * kBiasBytes;
+  uint16_t* const emeta_s = reinterpret_cast<uint16_t*>(smem + 2 * kSMax * kRowB + HPC * kBiasBytes + kAttrBytes);  // [ne] slot | row << 8
+  const unsigned full = 0xffffffffu;
+
+  const int4 tm = __ldg(tp.tile_meta + tile);
+  const int d0 = tm.x, s0 = tm.y, e0 = tm.z, nd = tm.w & 0xff, U = (tm.w >> 8) & 0xff, ne = tm.w >> 16, Upad = (U + 15) & ~15;
+  const float qscale = p.scale * 1.4426950408889634f;  // scores in the log2 domain
+  const __nv_bfloat16* __restrict__ qp = reinterpret_cast<const __nv_bfloat16*>(p.q);
+  const __nv_bfloat16* __restrict__ qwp = reinterpret_cast<const __nv_bfloat16*>(p.qw);
+
+  // ---- 1. gather: (group 0) the tile's edge attributes, dp floats per edge, packed; (group 1) the source rows (this head group's 512-byte
+  //         segment of k and of v, one warp per row, one 16-byte chunk per lane).  The slot list is fetched with one coalesced load per
+  //         warp so that every gather is issued after ONE round trip; the per-edge (slot, row) bytes come with plain coalesced loads. --------
+  {
+    const int sl_a = lane < U ? __ldg(tp.slot_src + s0 + lane) : 0, sl_b = lane + 32 < U ? __ldg(tp.slot_src + s0 + 32 + lane) : 0;
+    constexpr int CPE = DPH / 2;  // 16-byte chunks per edge (dp * 4 bytes)
+    const char* ab = reinterpret_cast<const char*>(p.edge_attr) + (int64_t)e0 * p.lde * 4;
+    for (int i = tid; i < ne * CPE; i += NT) {
+      const int e = i / CPE, c = i - e * CPE;
+      cp_async16(sA + (uint32_t)i * 16u, ab + (int64_t)e * p.lde * 4 + c * 16);
+    }
+    cp_async_commit();
+    const char* kb = reinterpret_cast<const char*>(p.k) + hg * 512 + lane * 16;
+    const char* vb = reinterpret_cast<const char*>(p.v) + hg * 512 + lane * 16;
+    const uint64_t ldk_b = (uint64_t)p.ldk * 2u, ldv_b = (uint64_t)p.ldv * 2u;
+#pragma unroll
+    for (int i = 0; i < kSMax / HPC; ++i) {
+      const int r = warp + i * HPC;
+      const uint64_t src = (uint64_t)(uint32_t)__shfl_sync(full, r < 32 ? sl_a : sl_b, r & 31);
+      if (r < Upad) {  // warp-uniform
+        const uint32_t dk = sK + r * kRowB + lane * 16, dv = sV + r * kRowB + lane * 16;
+        if (r < U) {
+          cp_async16(dk, kb + src * ldk_b);
+          cp_async16(dv, vb + src * ldv_b);
+        } else {  // padding slots of the last 16-slot block: masked by -inf, but 0 * garbage must stay 0
+          sts_zero16(dk);
+          sts_zero16(dv);
+        }
+      }
+    }
+    cp_async_commit();
+    for (int i = tid; i < ne; i += NT) emeta_s[i] = __ldg(tp.emeta + e0 + i);
+  }
+
+  // ---- 2. while the rows travel: the bias tile B_h (mask + edge term) of this warp's head, one lane per edge ---------------------------------
+#pragma unroll
+  for (int i = 0; i < kTD * kBP / 4 / 32; ++i) reinterpret_cast<float4*>(biasp)[lane + 32 * i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  static_assert((kTD * kBP / 4) % 32 == 0, "bias tile is a whole number of float4 per lane");
+  const int dl = lane >> 1, half = lane & 1;  // this lane's destination row and attribute half in the abar phase
+  const int cp_l = __ldg(p.colptr + d0 + min(lane, nd));
+  const int eb = __shfl_sync(full, cp_l, min(dl, nd)) - e0, ee = __shfl_sync(full, cp_l, min(dl + 1, nd)) - e0;  // rows >= nd: empty run
+  cp_async_wait<1>();  // this thread's attribute chunks ...
+  __syncthreads();     // ... and everybody's, and the (slot, row) bytes
+  for (int e = lane; e < ne; e += 32) {
+    const uint32_t em = emeta_s[e];
+    const int slot = em & 0xff, row = em >> 8;
+    const __nv_bfloat16* qwr = qwp + (int64_t)(d0 + row) * p.ldqw + h * p.dp;
+    const float4* ar = reinterpret_cast<const float4*>(attr_s + e * (2 * DPH));
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < DPH / 2; ++i) {
+      const float4 a = ar[i];
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(qwr + 4 * i));
+      const float2 w01 = unpack_bf16x2(w.x), w23 = unpack_bf16x2(w.y);
+      dot = fmaf(w01.x, a.x, dot), dot = fmaf(w01.y, a.y, dot), dot = fmaf(w23.x, a.z, dot), dot = fmaf(w23.y, a.w, dot);
+    }
+    biasp[row * kBP + slot] = dot * qscale;
+  }
+
+  // ---- 3. Q fragments (A operand, rows g and g + 8 of the tile; rows past the tile are zero) ----------------------------------------------
+  uint32_t qa[KS][4];
+  {
+    const __nv_bfloat16* q0 = qp + (int64_t)(d0 + g) * p.ldq + h * CH + 2 * t;
+    const __nv_bfloat16* q1 = qp + (int64_t)(d0 + g + 8) * p.ldq + h * CH + 2 * t;
+    const bool r0 = g < nd, r1 = g + 8 < nd;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      qa[ks][0] = r0 ? __ldg(reinterpret_cast<const uint32_t*>(q0 + ks * 16)) : 0u;
+      qa[ks][1] = r1 ? __ldg(reinterpret_cast<const uint32_t*>(q1 + ks * 16)) : 0u;
+      qa[ks][2] = r0 ? __ldg(reinterpret_cast<const uint32_t*>(q0 + ks * 16 + 8)) : 0u;
+      qa[ks][3] = r1 ? __ldg(reinterpret_cast<const uint32_t*>(q1 + ks * 16 + 8)) : 0u;
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();  // every thread's part of k / v has landed; bias tile complete (covers the __syncwarp)
+
+  // ---- 4. S = Q K^T (+ bias), row softmax in the accumulator registers ------------------------------------------------------------------------
+  const int nj = Upad >> 3;  // live 8-slot n-tiles (even)
+  float s[kSMax / 8][4];
+  const uint32_t k_lane = sK + (lane & 7) * kRowB + warp * (CH * 2) + (lane >> 3) * 16;
+#pragma unroll
+  for (int j = 0; j < kSMax / 8; ++j) {
+    s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+    if (j < nj) {
+#pragma unroll
+      for (int kk = 0; kk < KS / 2; ++kk) {
+        uint32_t b[4];
+        ldsm_x4(b, k_lane + j * 8 * kRowB + kk * 64);
+        mma16816(s[j], qa[2 * kk], b[0], b[1]);
+        mma16816(s[j], qa[2 * kk + 1], b[2], b[3]);
+      }
+      const float2 b0 = *reinterpret_cast<const float2*>(biasp + g * kBP + 8 * j + 2 * t);
+      const float2 b1 = *reinterpret_cast<const float2*>(biasp + (g + 8) * kBP + 8 * j + 2 * t);
+      s[j][0] = fmaf(s[j][0], qscale, b0.x), s[j][1] = fmaf(s[j][1], qscale, b0.y);
+      s[j][2] = fmaf(s[j][2], qscale, b1.x), s[j][3] = fmaf(s[j][3], qscale, b1.y);
+    } else {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = -INFINITY;
+    }
+  }
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kSMax / 8; ++j) m0 = fmaxf(m0, fmaxf(s[j][0], s[j][1])), m1 = fmaxf(m1, fmaxf(s[j][2], s[j][3]));
+  m0 = fmaxf(m0, __shfl_xor_sync(full, m0, 1)), m0 = fmaxf(m0, __shfl_xor_sync(full, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(full, m1, 1)), m1 = fmaxf(m1, __shfl_xor_sync(full, m1, 2));
+  if (m0 == -INFINITY) m0 = 0.f;  // row without edges (or past the tile): every weight is exp2(-inf) = 0
+  if (m1 == -INFINITY) m1 = 0.f;
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < kSMax / 8; ++j) {
+    s[j][0] = ex2(s[j][0] - m0), s[j][1] = ex2(s[j][1] - m0), s[j][2] = ex2(s[j][2] - m1), s[j][3] = ex2(s[j][3] - m1);
+    l0 += s[j][0] + s[j][1], l1 += s[j][2] + s[j][3];
+  }
+  l0 += __shfl_xor_sync(full, l0, 1), l0 += __shfl_xor_sync(full, l0, 2);
+  l1 += __shfl_xor_sync(full, l1, 1), l1 += __shfl_xor_sync(full, l1, 2);
+  const float inv0 = l0 > 0.f ? 1.0f / l0 : 0.f, inv1 = l1 > 0.f ? 1.0f / l1 : 0.f;
+
+  // ---- 5. O = P V: the accumulator layout of S is the A-fragment layout of the next product ------------------------------------------------
+  float o[NJO][4];
+#pragma unroll
+  for (int n = 0; n < NJO; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  const uint32_t v_lane = sV + ((lane & 7) + ((lane >> 3) & 1) * 8) * kRowB + warp * (CH * 2) + (lane >> 4) * 16;
+#pragma unroll
+  for (int kk = 0; kk < kSMax / 16; ++kk) {
+    if (2 * kk < nj) {
+      uint32_t a[4];
+      a[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]), a[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]), a[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int nn = 0; nn < NJO / 2; ++nn) {
+        uint32_t b[4];
+        ldsm_x4_t(b, v_lane + kk * 16 * kRowB + nn * 32);
+        mma16816(o[2 * nn], a, b[0], b[1]);
+        mma16816(o[2 * nn + 1], a, b[2], b[3]);
+      }
+    }
+  }
+
+  // ---- 6. abar[d, h, :] = sum_e alpha_e a_e: normalised weights back into the bias tile (same lane, same addresses), then per-row edge runs ----
+#pragma unroll
+  for (int j = 0; j < kSMax / 8; ++j) {
+    if (j < nj) {
+      *reinterpret_cast<float2*>(biasp + g * kBP + 8 * j + 2 * t) = make_float2(s[j][0] * inv0, s[j][1] * inv0);
+      *reinterpret_cast<float2*>(biasp + (g + 8) * kBP + 8 * j + 2 * t) = make_float2(s[j][2] * inv1, s[j][3] * inv1);
+    }
+  }
+  __syncwarp();
+  {
+    float ab[DPH];
+#pragma unroll
+    for (int i = 0; i < DPH; ++i) ab[i] = 0.f;
+    const float2* ar2 = reinterpret_cast<const float2*>(attr_s + half * DPH);
+    for (int e = eb; e < ee; ++e) {
+      const float pw = biasp[dl * kBP + (emeta_s[e] & 0xff)];
+#pragma unroll
+      for (int i = 0; i < DPH / 2; ++i) {
+        const float2 a = ar2[e * DPH + i];
+        ab[2 * i] = fmaf(pw, a.x, ab[2 * i]);
+        ab[2 * i + 1] = fmaf(pw, a.y, ab[2 * i + 1]);
+      }
+    }
+    if (dl < nd) {
+      __nv_bfloat16* ar = reinterpret_cast<__nv_bfloat16*>(p.abar) + (int64_t)(d0 + dl) * p.ldabar + h * p.dp + half * DPH;
+#pragma unroll
+      for (int i = 0; i < DPH; i += 2) *reinterpret_cast<uint32_t*>(ar + i) = pack_bf16x2(ab[i], ab[i + 1]);
+    }
+  }
+  __syncwarp();  // all lanes are done with the weights: the tile becomes the output staging buffer
+
+  // ---- 7. out = O / l + b_edge (rows with edges) + self term, staged so that every row leaves as 16-byte stores --------------------------------
+  {
+    const bool r0 = g < nd, r1 = g + 8 < nd;
+    const __nv_bfloat16* addp = reinterpret_cast<const __nv_bfloat16*>(p.add);
+#pragma unroll
+    for (int n = 0; n < NJO; ++n) {
+      const int c = h * CH + 8 * n + 2 * t;
+      float2 be = make_float2(0.f, 0.f);
+      if (p.b_edge) be = __ldg(reinterpret_cast<const float2*>(p.b_edge + c));
+      float v0 = o[n][0] * inv0 + (l0 > 0.f ? be.x : 0.f), v1 = o[n][1] * inv0 + (l0 > 0.f ? be.y : 0.f);
+      float v2 = o[n][2] * inv1 + (l1 > 0.f ? be.x : 0.f), v3 = o[n][3] * inv1 + (l1 > 0.f ? be.y : 0.f);
+      if (addp) {
+        if (r0) {
+          const float2 a2 = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(addp + (int64_t)(d0 + g) * p.ldadd + c)));
+          v0 += a2.x, v1 += a2.y;
+        }
+        if (r1) {
+          const float2 a2 = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(addp + (int64_t)(d0 + g + 8) * p.ldadd + c)));
+          v2 += a2.x, v3 += a2.y;
+        }
+      }
+      *reinterpret_cast<uint32_t*>(bias_raw + g * kOutPitch + (8 * n + 2 * t) * 2) = pack_bf16x2(v0, v1);
+      *reinterpret_cast<uint32_t*>(bias_raw + (g + 8) * kOutPitch + (8 * n + 2 * t) * 2) = pack_bf16x2(v2, v3);
+    }
+    __syncwarp();
+    constexpr int CPR = CH * 2 / 16;  // 16-byte chunks per row of this head
+    for (int i = lane; i < kTD * CPR; i += 32) {
+      const int r = i / CPR, c = i - r * CPR;
+      if (r < nd) {
+        const uint4 val = *reinterpret_cast<const uint4*>(bias_raw + r * kOutPitch + c * 16);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)(d0 + r) * p.ldo + h * CH + c * 8) = val;
+      }
+    }
+  }
+}
+
+template <int CH, int DPH>
+int launch_tile(const AttnParams& p, const TilePlan& tp, int64_t n_tiles, cudaStream_t s) {
+  constexpr int HPC = 256 / CH;
+  constexpr int smem = 2 * kSMax * kRowB + HPC * kBiasBytes + kAttrBytes + 2 * kEMetaMax;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device()];
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gt_attention_tile_kernel<CH, DPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gt_attention_tile_kernel)");
+    attr_set = true;
+  }
+  dim3 grid((unsigned)n_tiles, (unsigned)(p.heads / HPC));
+  gt_attention_tile_kernel<CH, DPH><<<grid, 32 * HPC, smem, s>>>(p, tp);
+  return launch_status("gt_attention_tile_kernel");
+}
+
+template <int CH>
+int launch_tile_dph(const AttnParams& p, const TilePlan& tp, int64_t n_tiles, cudaStream_t s) {
+  switch (p.dp) {
+    case 4: return launch_tile<CH, 2>(p, tp, n_tiles, s);
+    case 8: return launch_tile<CH, 4>(p, tp, n_tiles, s);
+    case 12: return launch_tile<CH, 6>(p, tp, n_tiles, s);
+    case 16: return launch_tile<CH, 8>(p, tp, n_tiles, s);
+    default: set_error("gt_attention_tiled: dp = %d not in {4, 8, 12, 16}", p.dp); return -3;
+  }
+}
+
+}  // namespace
+}  // namespace anemoi
+
+using namespace anemoi;
+
+// Host-side planner (HOST pointers in and out; the graph-only analysis step, run once per static graph).
+//   src32 [E], colptr32 [n_dst + 1]: the dst-sorted CSR of anemoi_b200_csr_build copied to the host.
+//   tile_meta: capacity 4 * n_dst int32 (one row per tile, see TilePlan); slot_src: capacity E; emeta: capacity E (slot | row << 8).
+//   max_edges: edges per tile, <= 224 and <= 10752 / (4 dp) for the kernel's attribute stage (dp = padded attributes per edge).
+// Returns 0 and the counts, -3 if some destination needs more than 64 slots / max_edges edges (no plan: use anemoi_b200_gt_attention_fwd).
+extern "C" int anemoi_b200_attn_tile_plan(const int32_t* src32, const int32_t* colptr32, int64_t n_src, int64_t n_dst, int64_t max_edges,
+                                          int32_t* tile_meta, int32_t* slot_src, uint16_t* emeta, int64_t* n_tiles, int64_t* n_slots) {
+  ANEMOI_CHECK_ARG(n_src >= 0 && n_dst >= 0 && colptr32 && tile_meta && n_tiles && n_slots, "attn_tile_plan: bad argument");
+  ANEMOI_CHECK_ARG(max_edges >= 1 && max_edges <= kEMetaMax, "attn_tile_plan: max_edges must be in [1, %d]", kEMetaMax);
+  const int64_t E = colptr32[n_dst];
+  ANEMOI_CHECK_ARG(E == 0 || (src32 && slot_src && emeta), "attn_tile_plan: null edge arrays");
+  std::vector<int32_t> head((size_t)n_src, -1), stamp((size_t)n_src, -1);
+  int32_t s_src[kSMax], s_next[kSMax], s_used[kSMax];
+  int64_t nt = 0, ns = 0;  // tiles closed so far, slots written so far
+  int d = 0;
+  while (d < n_dst) {
+    const int d_first = d;
+    // open tile `nt` at row d
+    int nslots = 0, nd = 0;
+    int64_t ne = 0;
+    const int32_t tile_id = (int32_t)nt;
+    while (d < n_dst && nd < kTD) {
+      const int64_t eb = colptr32[d], ee = colptr32[d + 1];
+      if (ne + (ee - eb) > max_edges) break;
+      const int n0 = nslots;
+      bool ok = true;
+      for (int64_t e = eb; e < ee && ok; ++e) {
+        const int32_t u = src32[e];
+        if (u < 0 || u >= n_src) {
+          set_error("attn_tile_plan: source id %d out of range", (int)u);
+          return -1;
+        }
+        int sl = stamp[u] == tile_id ? head[u] : -1, prev = -1;
+        while (sl >= 0 && s_used[sl] == d) prev = sl, sl = s_next[sl];  // this slot already carries an edge into d: duplicate (u, d) pair
+        if (sl < 0) {
+          if (nslots == kSMax) {
+            ok = false;
+            break;
+          }
+          sl = nslots++;
+          s_src[sl] = u, s_next[sl] = -1;
+          if (prev >= 0)
+            s_next[prev] = sl;
+          else
+            head[u] = sl, stamp[u] = tile_id;
+        }
+        s_used[sl] = d;
+        emeta[e] = (uint16_t)(sl | (nd << 8));
+      }
+      if (!ok) {  // row d does not fit: undo its slots and close the tile before it
+        for (int sl = n0; sl < nslots; ++sl)
+          if (stamp[s_src[sl]] == tile_id && head[s_src[sl]] == sl) stamp[s_src[sl]] = -1;
+        for (int sl = 0; sl < n0; ++sl)
+          if (s_next[sl] >= n0) s_next[sl] = -1;
+        nslots = n0;
+        break;
+      }
+      ne += ee - eb, ++nd, ++d;
+    }
+    if (nd == 0) {
+      set_error("attn_tile_plan: destination %d has more than %d distinct sources or %d edges", d, kSMax, (int)max_edges);
+      return -3;
+    }
+    for (int sl = 0; sl < nslots; ++sl) slot_src[ns + sl] = s_src[sl];
+    int32_t* tm = tile_meta + 4 * nt;
+    tm[0] = d_first, tm[1] = (int32_t)ns, tm[2] = colptr32[d_first], tm[3] = nd | (nslots << 8) | ((int32_t)ne << 16);
+    ns += nslots, ++nt;
+  }
+  *n_tiles = nt, *n_slots = ns;
+  return 0;
+}
+
+extern "C" int anemoi_b200_gt_attention_tiled_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                                  const float* edge_attr, int64_t lde, const float* b_edge, const void* qw, int64_t ldqw,
+                                                  void* abar, int64_t ldabar, int64_t dp, const int32_t* colptr32, const int32_t* tile_meta,
+                                                  const int32_t* slot_src, const uint16_t* emeta, int64_t n_tiles,
+                                                  const void* add, int64_t ldadd, void* out, int64_t ldo, int64_t n_dst, int64_t heads,
+                                                  int64_t ch, void* stream) {
+  ANEMOI_CHECK_ARG(n_dst >= 0 && n_tiles >= 0 && heads >= 1, "gt_attention_tiled: bad shape");
+  if (n_dst == 0 || n_tiles == 0) return 0;
+  ANEMOI_CHECK_ARG(q && k && v && out && qw && abar && colptr32 && tile_meta, "gt_attention_tiled: null pointer");
+  ANEMOI_CHECK_ARG((reinterpret_cast<uintptr_t>(tile_meta) & 15) == 0, "gt_attention_tiled: tile_meta must be 16-byte aligned");
+  ANEMOI_CHECK_ARG(ch == 32 || ch == 64, "gt_attention_tiled: channels per head must be 32 or 64 (got %lld)", (long long)ch);
+  const int64_t hpc = 256 / ch, C = heads * ch;
+  ANEMOI_CHECK_ARG(heads % hpc == 0, "gt_attention_tiled: heads (%lld) must be a multiple of %lld", (long long)heads, (long long)hpc);
+  ANEMOI_CHECK_ARG(ldq >= C && ldk >= C && ldv >= C && ldo >= C && ldqw >= heads * dp && ldabar >= heads * dp, "gt_attention_tiled: leading dimension");
+  ANEMOI_CHECK_ARG(edge_attr && lde >= dp && lde % 4 == 0, "gt_attention_tiled: edge attributes must be fp32 rows of >= dp floats, pitch a multiple of 4");
+  auto al = [](const void* ptr, int64_t ld_elems, int es, int need) {
+    return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) % need) == 0 && (ld_elems * es) % need == 0);
+  };
+  ANEMOI_CHECK_ARG(al(k, ldk, 2, 16) && al(v, ldv, 2, 16) && al(out, ldo, 2, 16) && al(q, ldq, 2, 4) && al(add, ldadd, 2, 4) && al(qw, ldqw, 2, 8) &&
+                       al(abar, ldabar, 2, 4) && al(edge_attr, lde, 4, 16) && al(b_edge, 2, 4, 8),
+                   "gt_attention_tiled: operand alignment (k, v, out, attribute rows 16 bytes; qw rows 8 bytes; q, add, abar rows 4 bytes)");
+  AttnParams p{};
+  p.q = q, p.k = k, p.v = v, p.e = nullptr, p.add = add, p.out = out;
+  p.ldq = ldq, p.ldk = ldk, p.ldv = ldv, p.ldadd = ldadd, p.ldo = ldo;
+  p.edge_attr = edge_attr, p.lde = lde, p.edge_dim = (int)dp, p.b_edge = b_edge;
+  p.qw = qw, p.abar = abar, p.ldqw = ldqw, p.ldabar = ldabar, p.dp = (int)dp;
+  p.colptr = colptr32, p.n_dst = n_dst, p.heads = (int)heads, p.ch = (int)ch;
+  p.scale = 1.0f / sqrtf((float)ch);
+  TilePlan tp{reinterpret_cast<const int4*>(tile_meta), slot_src, emeta};
+  cudaStream_t s = (cudaStream_t)stream;
+  return ch == 32 ? launch_tile_dph<32>(p, tp, n_tiles, s) : launch_tile_dph<64>(p, tp, n_tiles, s);
+}

@@ -12,8 +12,9 @@ ico-6); the nodes are then sorted along a Hilbert curve on the faces of the encl
 per graph (4 s at 41 k nodes), cached on the edge_index tensor.  The processor permutes its input rows once, runs every layer in the new
 order on a relabelled, dst-sorted edge list, and permutes the output back: results are identical up to summation order.
 
-Opt-in this round (``ANEMOI_B200_REORDER=1``): the plan and the permuted forward are verified on CPU (``tests/test_reorder.py``), the GPU
-measurement is the first item of the next round.
+``ANEMOI_B200_REORDER``: "auto" (default) = on the bf16 path of the GraphTransformer processor, where the destination-tile attention
+kernel (csrc/attention_tile.cu) turns the locality into 2.65x fewer gathered rows; "1" = always (both processors); "0" = never.
+Measured (profiles/r2/): the warp-per-node kernel alone gains only 135 -> 130 us from the order (it is issue-bound, not L2-bound).
 """
 
 from __future__ import annotations
@@ -26,7 +27,17 @@ import numpy as np
 import torch
 from torch import Tensor
 
-ENABLED = os.environ.get("ANEMOI_B200_REORDER", "0") == "1"
+MODE = os.environ.get("ANEMOI_B200_REORDER", "auto")
+ENABLED = MODE == "1"  # unconditional (A/B switch); "auto" is decided per call by the processors (``wanted``)
+
+
+def wanted(dt: torch.dtype, tiled_attention: bool) -> bool:
+    """Should this forward run in the locality order?"""
+    if MODE == "1":
+        return True
+    return MODE == "auto" and dt == torch.bfloat16 and tiled_attention
+
+
 MIN_NODES = 2048  # below this the whole node tensor lives in L2 / L1 anyway
 
 
@@ -118,6 +129,13 @@ def locality_plan(edge_index: Tensor, n_nodes: int, min_nodes: int = MIN_NODES, 
             src, dst = rank[ei[0]], rank[ei[1]]
             eperm = np.argsort(dst, kind="stable")
             dev = edge_index.device
+
+            def reuse(s_, d_):  # edges per distinct (16-row dst tile, src) pair
+                return float(s_.size) / float(np.unique((d_ // 16) * n_nodes + s_).size)
+
+            if coords is None and reuse(src, dst) < 1.2 * reuse(ei[0], ei[1]):
+                emb = None  # the embedding found no locality worth two row permutations per forward (not a mesh-like graph)
+        if emb is not None:
             plan = ReorderPlan(
                 perm=torch.from_numpy(perm.astype(np.int32)).to(dev),
                 rank=torch.from_numpy(rank.astype(np.int32)).to(dev),

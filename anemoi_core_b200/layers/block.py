@@ -29,6 +29,22 @@ from .utils import load_layer_kernels
 
 PairTensor = tuple[Tensor, Tensor]
 HALO_EXCHANGE = os.environ.get("ANEMOI_B200_HALO", "1") != "0"  # sharded GraphTransformer processor: halo all-to-all (default) vs all-gather
+# Destination-tile tensor-core attention kernel (csrc/attention_tile.cu): "0" (default) = warp-per-node kernel only, "auto" = when the
+# graph's tile plan re-uses gathered source rows (locality-ordered processor graphs: 2.65 on the Hilbert-ordered ico-6 mesh), "1" = whenever
+# a plan exists.  Opt-in because it is parity-green but measured SLOWER at cfg2 (221 us vs 130 us, profiles/r2/README.md: 2 CTAs of 8
+# warps per SM cannot hide its three dependent round trips, and the per-edge attribute phases keep it at 1 790 instructions per head-tile).
+ATTN_TILES = os.environ.get("ANEMOI_B200_ATTN_TILES", "0")
+ATTN_TILES_MIN_REUSE = float(os.environ.get("ANEMOI_B200_ATTN_TILES_MIN_REUSE", "1.3"))
+
+
+def attention_tile_plan(csr, channels: int, heads: int, dt: torch.dtype, dp: int):
+    """The tile plan to run attention with, or None for the warp-per-node kernel."""
+    if ATTN_TILES == "0" or not ops.attention_tiles_supported(channels, heads, dt, dp):
+        return None
+    plan = ops.attention_tiles(csr)
+    if plan is None or (ATTN_TILES != "1" and plan.reuse < ATTN_TILES_MIN_REUSE):
+        return None
+    return plan
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -91,7 +107,7 @@ class GraphConvProcessorBlock(GraphConvBaseBlock):
             # relabelled onto it (local dst ids), so the node-level projections run over n_local + n_halo rows instead of all N and the
             # aggregate is local from the start.  ``edge_index`` is ignored in favour of the plan's.
             C, n_local = self.in_channels, x.shape[0]
-            table = torch.empty((halo_plan.n_table, C), dtype=dt, device=x.device)
+            table = halo_plan.table(C, dt, x.device, tag="gnn")
             ops.cast_pad(x, dt, out=table[:n_local])
             halo_plan.exchange(table)
             csr = Fn.csr_for(halo_plan.edge_index, halo_plan.n_table, n_local)
@@ -317,7 +333,8 @@ class GraphTransformerBaseBlock(nn.Module):
             att = torch.empty((q.shape[0], A + hdp), dtype=dt, device=q.device)
             if hdp != H * dp:
                 att[:, A + H * dp :].zero_()
-            ops.gt_attention(q, k, v, csr, H, edge_attr=edge_attr_p, b_edge=b_e, qw=qw, abar=att[:, A:], dp=dp, add=x_r, out=att[:, :A])
+            ops.gt_attention(q, k, v, csr, H, edge_attr=edge_attr_p, b_edge=b_e, qw=qw, abar=att[:, A:], dp=dp, add=x_r, out=att[:, :A],
+                             tiles=attention_tile_plan(csr, A, H, dt, dp))  # fmt: skip
         else:
             w_e = self._pack.get(("w_edge",), [self.lin_edge.weight], lambda: self.lin_edge.weight.detach().float().contiguous())
             att = ops.gt_attention(q, k, v, csr, H, edge_attr=edge_attr_p, w_edge=w_e, b_edge=b_e, add=x_r)
@@ -434,7 +451,7 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
         # packs the rows the other ranks asked for, one all-to-all drops the rows we need into the tail; the edge list was relabelled
         # onto the table once.  q | self | qw come from a second GEMM on the same (tagged) LayerNorm statistics.
         plan = halo_plan_for(edge_index, shard_info.nodes, model_comm_group)
-        table = torch.empty((plan.n_table, 2 * A), dtype=dt, device=x.device)
+        table = plan.table(2 * A, dt, x.device)  # symmetric peer buffer (one per plan, re-used by every layer) or a fresh tensor
         kv_layers = [self.lin_key, self.lin_value]
         Fn.ln_linear(self._pack, x, ln, ("kv", id(self.lin_key), id(self.lin_value)), Fn.linear_sources(kv_layers),
                      lambda: Fn.cat_linear32(kv_layers), dt, cond=cond, out=table[: plan.n_local])  # fmt: skip
@@ -498,8 +515,14 @@ class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
         dt = Fn.compute_dtype(x_src, x_dst)
         A = self.attn_channels
         kv_layers = [self.lin_key, self.lin_value]
+        world = group_size(model_comm_group)
+        halo = world > 1 and self.shard_strategy != "heads" and shard_info is not None and shard_info.src_is_sharded()
+        plan = table = None
+        if halo:  # the k | v GEMM writes this rank's rows straight into the head of the halo table (see below)
+            plan = halo_plan_for(edge_index, shard_info.src_nodes, model_comm_group)
+            table = plan.table(2 * A, dt, x_src.device)
         kv = Fn.ln_linear(self._pack, x_src, self.layer_norm_attention_src, ("kv",), Fn.linear_sources(kv_layers), lambda: Fn.cat_linear32(kv_layers), dt,
-                          cond=cond_src)  # fmt: skip
+                          cond=cond_src, **({"out": table[: plan.n_local]} if halo else {}))  # fmt: skip
         if group_size(model_comm_group) > 1 and self.shard_strategy == "heads":
             # heads strategy (mapper.py:388-478): full edge list, heads sharded inside the attention
             d_, dp_, _ = self._fold_dims()
@@ -513,12 +536,23 @@ class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
                 src_new = self.node_src_mlp.run(x_src, dt, residual=x_src if x_src.dtype in Fn.SUPPORTED else x_src.float(),
                                                 pre_ln=self.layer_norm_mlp_src, cond=cond_src)  # fmt: skip
             return (src_new, dst_new), edge_attr
-        if group_size(model_comm_group) > 1 and shard_info is not None and shard_info.src_is_sharded():
-            # edges strategy (reference mapper.py:248-297 / khop_edges.py:317-409): every rank needs the k | v rows of all sources
-            kv = gather_rows(kv, shard_info.src_nodes, model_comm_group)
-        csr = Fn.csr_for(edge_index, kv.shape[0], x_dst.shape[0])
-        dst_new = self._attend_project(x_dst, self.layer_norm_attention_dest, kv[:, :A], kv[:, A:], [self.lin_self], self.prepare_edges(edge_attr, dt),
-                                       csr, x_dst, dt, cond=cond_dst)
+        if halo:
+            # edges strategy with sharded sources (reference mapper.py:248-297 / khop_edges.py:317-409 all-gathers the source rows and drops
+            # the unconnected ones): only the k | v rows this rank's edges name travel, through the same halo plan as the processor's, over
+            # SOURCE rows partitioned by shard_info.src_nodes; the dst-side GEMM runs while they do.
+            if self.qk_norm:  # per row and head: every rank normalises the keys it owns once, before they travel
+                ops.layer_norm(table[: plan.n_local, :A], self._pack.f32(self.k_norm.weight), self._pack.f32(getattr(self.k_norm, "bias", None)),
+                               self.k_norm.eps, out=table[: plan.n_local, :A], groups=self.num_heads)  # fmt: skip
+            plan.exchange_start(table)
+            buf = self._dst_gemm(x_dst, self.layer_norm_attention_dest, [self.lin_query, self.lin_self], dt, cond=cond_dst)
+            plan.exchange_finish()
+            csr = Fn.csr_for(plan.edge_index, plan.n_table, x_dst.shape[0])
+            dst_new = self._attend_project(x_dst, self.layer_norm_attention_dest, table[:, :A], table[:, A:], [self.lin_self],
+                                           self.prepare_edges(edge_attr, dt), csr, x_dst, dt, dst_buf=buf, k_prenormed=True, cond=cond_dst)  # fmt: skip
+        else:
+            csr = Fn.csr_for(edge_index, kv.shape[0], x_dst.shape[0])
+            dst_new = self._attend_project(x_dst, self.layer_norm_attention_dest, kv[:, :A], kv[:, A:], [self.lin_self], self.prepare_edges(edge_attr, dt),
+                                           csr, x_dst, dt, cond=cond_dst)  # fmt: skip
         src_new = x_src
         if self.update_src_nodes:
             src_new = self.node_src_mlp.run(x_src, dt, residual=x_src if x_src.dtype in Fn.SUPPORTED else x_src.float(),

@@ -214,6 +214,13 @@ class GraphTransformerProcessor(BaseProcessor):
             edge_pre_mlp=edge_pre_mlp,
         )
 
+    def _tiled_attention(self, dt: torch.dtype) -> bool:
+        """Will the blocks run the destination-tile attention kernel (the one that profits from the locality order)?"""
+        from .block import ATTN_TILES
+
+        blk = self.proc[0]
+        return ATTN_TILES != "0" and blk._use_fold(dt) and ops.attention_tiles_supported(blk.attn_channels, blk.num_heads, dt, blk._fold_dims()[1])
+
     def forward(
         self,
         x: Tensor,
@@ -242,7 +249,9 @@ class GraphTransformerProcessor(BaseProcessor):
         elif group_size(model_comm_group) > 1:
             edge_index = _localise_presharded_edges(edge_index, shard_info.nodes, model_comm_group)
         cond = kwargs.get("cond")
-        plan = RO.locality_plan(edge_index, n_nodes) if RO.ENABLED and group_size(model_comm_group) == 1 else None
+        plan = None
+        if group_size(model_comm_group) == 1 and RO.wanted(Fn.compute_dtype(x), self._tiled_attention(Fn.compute_dtype(x))):
+            plan = RO.locality_plan(edge_index, n_nodes)  # cached per graph; the first call runs the host-side eigensolve
         if plan is not None:  # run every layer in the locality order (layers/_reorder.py); identical results up to summation order
             x = ops.cast_pad(x, x.dtype, idx=plan.perm)
             edge_attr, edge_index = RO.permute_edge_attr(edge_attr, plan), plan.edge_index

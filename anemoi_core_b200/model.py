@@ -49,7 +49,7 @@ class EncProcDec(nn.Module):
         self._graph: Optional[torch.cuda.CUDAGraph] = None
 
     def forward(self, x_grid: Tensor, x_mesh: Tensor, graph: dict, model_comm_group=None, mesh_shards: Optional[list[int]] = None,
-                grid_shards: Optional[list[int]] = None) -> Tensor:
+                grid_shards: Optional[list[int]] = None, keep_output_sharded: bool = False, inputs_sharded: bool = False) -> Tensor:
         """One forward step.  With ``model_comm_group`` (and per-rank ``mesh_shards`` / ``grid_shards``) every stage is dst-range sharded:
         encoder (full grid sources, local mesh rows), processor (local rows, per-layer all-gather of k|v or x), latent skip, decoder (local
         mesh sources all-gathered as k|v, local grid rows); the output rows are gathered at the end.  GNN mappers run replicated."""
@@ -60,14 +60,18 @@ class EncProcDec(nn.Module):
         if group_size(model_comm_group) > 1 and mesh_shards is not None:
             g = model_comm_group
             if self.kind == "graphtransformer" and grid_shards is not None:
-                x_mesh_l = shard_rows(x_mesh, mesh_shards, g)
-                x_grid_l = shard_rows(x_grid, grid_shards, g)
-                _, x_local = self.encoder((x_grid, x_mesh_l), 1, BipartiteGraphShardInfo(src_nodes=None, dst_nodes=mesh_shards), graph["enc_attr"],
-                                          graph["enc_index"], g, keep_x_dst_sharded=True)  # fmt: skip
+                # ``inputs_sharded``: x_grid / x_mesh are already this rank's rows (the reference's in_out_sharded mode,
+                # encoder_processor_decoder.py:176-183): nothing but the halo rows ever leaves a rank
+                x_mesh_l = x_mesh if inputs_sharded else shard_rows(x_mesh, mesh_shards, g)
+                x_grid_l = x_grid if inputs_sharded else shard_rows(x_grid, grid_shards, g)
+                # grid rows sharded too: each rank embeds and projects (k | v) its own grid rows only, the rows its mesh nodes' edges name
+                # on other ranks arrive by halo exchange (reference: shard the sources, mapper.py:248-297)
+                _, x_local = self.encoder((x_grid_l, x_mesh_l), 1, BipartiteGraphShardInfo(src_nodes=grid_shards, dst_nodes=mesh_shards),
+                                          graph["enc_attr"], graph["enc_index"], g, keep_x_dst_sharded=True)  # fmt: skip
                 y_local = self.processor(x_local, 1, GraphShardInfo(nodes=mesh_shards), graph["proc_attr"], graph["proc_index"], g)
                 y_local = ops.add(y_local, x_local)  # latent skip (:295-296)
                 return self.decoder((y_local, x_grid_l), 1, BipartiteGraphShardInfo(src_nodes=mesh_shards, dst_nodes=grid_shards), graph["dec_attr"],
-                                    graph["dec_index"], g, keep_x_dst_sharded=False)  # fmt: skip
+                                    graph["dec_index"], g, keep_x_dst_sharded=keep_output_sharded)  # fmt: skip
             if self.kind == "gnn" and grid_shards is not None:
                 # GNN mappers sharded like the reference (mapper.py:760-835): grid and mesh rows sharded, the block all-gathers the embedded sources
                 x_grid_l, x_mesh_l = shard_rows(x_grid, grid_shards, g), shard_rows(x_mesh, mesh_shards, g)

@@ -140,6 +140,64 @@ class GraphCSR:
     colptr32: Tensor  # int32 [n_dst+1]
     src32: Tensor  # int32 [E]
     dst32: Tensor  # int32 [E]
+    tiles: object = None  # AttnTilePlan, False (no plan exists) or None (not built yet); see attention_tiles()
+
+
+@dataclass
+class AttnTilePlan:
+    """Destination-tile plan of the tiled attention kernel (include/anemoi_b200.h: anemoi_b200_attn_tile_plan)."""
+
+    n_tiles: int
+    n_slots: int
+    tile_meta: Tensor  # int32 [n_tiles, 4] device
+    slot_src: Tensor  # int32 [n_slots] device
+    emeta: Tensor  # int16 [E] device: slot | row << 8 of every edge inside its tile
+    max_edges: int  # edges-per-tile bound the plan was built with
+
+    @property
+    def reuse(self) -> float:
+        """edges per gathered source row: how often a tile re-uses a row it fetched (1.0 = no locality)."""
+        return float(self.emeta.numel()) / max(self.n_slots, 1)
+
+
+ATTN_TILE_MAX_EDGES = 168  # fits every dp <= 16: min(224, 10752 // (4 * 16))
+
+
+def plan_attention_tiles_host(src32, colptr32, n_src: int, n_dst: int, max_edges: int = ATTN_TILE_MAX_EDGES):
+    """Run the host-side planner on numpy int32 arrays; returns (tile_meta [T,4], slot_src [S], emeta [E] uint16) numpy arrays or None."""
+    import ctypes
+
+    import numpy as np
+
+    src32 = np.ascontiguousarray(src32, dtype=np.int32)
+    colptr32 = np.ascontiguousarray(colptr32, dtype=np.int32)
+    n_edges = int(colptr32[n_dst]) if colptr32.size else 0
+    tile_meta = np.zeros((max(n_dst, 1), 4), dtype=np.int32)
+    slot_src = np.zeros(max(n_edges, 1), dtype=np.int32)
+    emeta = np.zeros(max(n_edges, 1), dtype=np.uint16)
+    nt, ns = ctypes.c_int64(0), ctypes.c_int64(0)
+    rc = _lib.load().anemoi_b200_attn_tile_plan(src32.ctypes.data, colptr32.ctypes.data, n_src, n_dst, max_edges, tile_meta.ctypes.data,
+                                               slot_src.ctypes.data, emeta.ctypes.data, ctypes.addressof(nt), ctypes.addressof(ns))  # fmt: skip
+    if rc == -3:
+        return None
+    _lib.check(rc, "anemoi_b200_attn_tile_plan")
+    return tile_meta[: nt.value].copy(), slot_src[: ns.value].copy(), emeta[:n_edges].copy()
+
+
+def attention_tiles(csr: GraphCSR) -> Optional[AttnTilePlan]:
+    """Tile plan of ``csr`` (built once on the host, cached on the CSR object); None when some destination has too many sources."""
+    if csr.tiles is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None  # needs a device -> host copy: build it in the warm-up pass, not under capture
+        res = plan_attention_tiles_host(csr.src32.cpu().numpy(), csr.colptr32.cpu().numpy(), csr.n_src, csr.n_dst)
+        if res is None:
+            csr.tiles = False
+        else:
+            dev = csr.colptr32.device
+            tm, ss = (torch.from_numpy(a).to(dev) for a in res[:2])
+            em = torch.from_numpy(res[2].view("int16")).to(dev)
+            csr.tiles = AttnTilePlan(int(tm.shape[0]), int(ss.numel()), tm.contiguous(), ss, em, ATTN_TILE_MAX_EDGES)
+    return csr.tiles or None
 
 
 def build_csr(edge_index: Tensor, n_src: int, n_dst: int, validate: bool = True) -> GraphCSR:
@@ -305,6 +363,14 @@ def linear(
 ATTN_MAX_EDGE_DIM = 16  # attributes per edge the fused attention kernel accepts (rows zero-padded to this many floats)
 
 
+def attention_tiles_supported(channels: int, heads: int, dtype: torch.dtype, dp: int) -> bool:
+    """Shapes the destination-tile kernel handles: bf16, 32 or 64 channels per head, heads a multiple of 256 / Ch, dp in {4, 8, 12, 16}."""
+    if dtype != torch.bfloat16 or heads <= 0 or channels % heads:
+        return False
+    ch = channels // heads
+    return ch in (32, 64) and heads % (256 // ch) == 0 and dp in (4, 8, 12, 16)
+
+
 def attention_fold_supported(channels: int, heads: int, dtype: torch.dtype, edge_dim: int) -> bool:
     """True if the coalesced slab attention kernel (and with it the folded lin_edge form) handles this shape."""
     epc = 16 // (2 if dtype == torch.bfloat16 else 4)
@@ -332,8 +398,10 @@ def gt_attention(
     dp: int = 0,
     add: Optional[Tensor] = None,
     out: Optional[Tensor] = None,
+    tiles: Optional[AttnTilePlan] = None,
 ) -> Tensor:
     """Edge-softmax attention over the cached CSR.  q [n_dst, H*Ch]; k, v [n_src, H*Ch] (column slices allowed).
+    ``tiles`` (folded bf16 form only): run the destination-tile tensor-core kernel on this plan of the same CSR.
 
     Edge term, one of: ``e_proj`` [E, H*Ch] (materialised lin_edge output, the reference operator boundary);
     ``edge_attr`` fp32 [E, >=d_e] + ``w_edge`` fp32 [H*Ch, d_e] (+ ``b_edge``): projection inside the kernel;
@@ -388,6 +456,18 @@ def gt_attention(
         # an empty edge tensor has a null data pointer, so the library sees "no edge term" and leaves abar untouched; with no edges
         # abar = sum_e alpha_e a_e is exactly zero (tests/test_gpu_parity.py::test_edge_cases_empty_and_isolated)
         abar.zero_()
+    if tiles is not None:
+        if qw is None or e_proj is not None or q.dtype != torch.bfloat16:
+            raise ValueError("gt_attention: the tiled kernel implements the folded bf16 form (qw / abar)")
+        if lde < dp or tiles.max_edges > min(224, 10752 // (4 * dp)):
+            raise ValueError("gt_attention: edge_attr rows narrower than dp, or a tile plan built for a smaller dp")
+        with _Timed("gt_attention", aflops, abytes):
+            rc = _lib.load().anemoi_b200_gt_attention_tiled_fwd(
+                _ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(edge_attr), lde, _ptr(_f32(b_edge)), _ptr(qw), ldqw, _ptr(abar), ldabar, dp,
+                _ptr(csr.colptr32), _ptr(tiles.tile_meta), _ptr(tiles.slot_src), _ptr(tiles.emeta), tiles.n_tiles, _ptr(add), ldadd, _ptr(out), ldo,
+                n_dst, heads, C // heads, _stream())  # fmt: skip
+        _lib.check(rc, "anemoi_b200_gt_attention_tiled_fwd")
+        return out
     with _Timed("gt_attention", aflops, abytes):
         rc = _lib.load().anemoi_b200_gt_attention_fwd(
             _ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(e_proj), lde_proj, _ptr(edge_attr), lde, d_e, _ptr(w_edge), ldw_e, _ptr(_f32(b_edge)),
@@ -556,3 +636,35 @@ def cond_layer_norm(x: Tensor, cond: Tensor, w_scale: Tensor, b_scale: Tensor, w
                                                      _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_cond_layer_norm")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# multi-GPU exchange over peer memory (csrc/peer.cu); ``ch`` is a distributed.peer.PeerChannel
+# ------------------------------------------------------------------------------------------------------------
+def peer_rendezvous(ch, like: Tensor) -> None:
+    """Start exchange c on this rank: announce it to the peers and wait until all of them have started it too."""
+    _need_cuda(like)
+    with _Timed("peer_rendezvous"):
+        rc = _lib.load().anemoi_b200_peer_rendezvous(ch.ctl_ptrs, ch.world, ch.rank, _stream())
+    _lib.check(rc, "anemoi_b200_peer_rendezvous")
+
+
+def halo_push(ch, rows: Tensor, send_idx: Tensor, send_off: Tensor, n_send: int, dst_ptrs, dst_ld_bytes: int) -> None:
+    """rows[send_idx[j]] -> the peers' tables (``dst_ptrs``: ctypes uint64 [world] of peer-mapped addresses), then signal arrival."""
+    _need_cuda(rows, send_idx, send_off)
+    _, W, ld = _rows(rows)
+    es = rows.element_size()
+    if send_idx.dtype != torch.int32 or send_off.dtype != torch.int32 or send_off.numel() != ch.world + 1:
+        raise TypeError("halo_push: send_idx / send_off must be int32 (send_off has world + 1 entries)")
+    with _Timed("halo_push", 0.0, 2.0 * n_send * W * es):
+        rc = _lib.load().anemoi_b200_halo_push(_ptr(rows), ld * es, W * es, _ptr(send_idx), _ptr(send_off), n_send, dst_ptrs, dst_ld_bytes, ch.ctl_ptrs,
+                                               ch.world, ch.rank, _stream())  # fmt: skip
+    _lib.check(rc, "anemoi_b200_halo_push")
+
+
+def halo_wait(ch, like: Tensor) -> None:
+    """Wait (on the stream) until every peer's rows of the current exchange have arrived."""
+    _need_cuda(like)
+    with _Timed("halo_wait"):
+        rc = _lib.load().anemoi_b200_halo_wait(ch.ctl_ptrs, ch.world, ch.rank, _stream())
+    _lib.check(rc, "anemoi_b200_halo_wait")

@@ -7,8 +7,9 @@
  * reference's modules would call each symbol.
  *
  * Conventions
- *  - All pointers are DEVICE pointers owned by the caller (PyTorch).  The library never allocates or frees
- *    device memory and keeps no global device state; host-side it only caches TMA descriptors.
+ *  - All pointers are DEVICE pointers owned by the caller (PyTorch) unless an entry point says HOST.  The library never allocates
+ *    or frees device memory and keeps no global device state (host-side it only caches TMA descriptors) - with ONE explicit
+ *    exception: the symmetric peer buffers of the multi-GPU exchange, created and destroyed by anemoi_b200_ipc_alloc / _free.
  *  - Every call only ENQUEUES work on `stream` (a cudaStream_t / CUstream passed as void*): no device
  *    synchronisation, CUDA-graph capturable, re-entrant, one caller thread per device.
  *  - Matrices are row-major with an explicit leading dimension in ELEMENTS (`ld*`), so column slices of wider
@@ -122,6 +123,29 @@ ANEMOI_API int anemoi_b200_gt_attention_fwd(const void* q, int64_t ldq, const vo
                                  const int32_t* src32, const int32_t* colptr32, const void* add, int64_t ldadd, void* out, int64_t ldo,
                                  int64_t n_dst, int64_t heads, int64_t ch, int dtype, void* stream);
 
+/* -- GraphTransformer attention on destination tiles (folded form (3), bf16, Ch in {32, 64}) ------------------------
+ * Same result as anemoi_b200_gt_attention_fwd form (3) (replaces layers/conv.py:103-147, triton/gt.py:81-179 and the lin_edge GEMM of
+ * block.py:623-635), computed per tile of <= 16 consecutive destination rows and the <= 64 distinct source rows they name:
+ * S = Q K^T and O = P V on the warp-level tensor cores (mma.sync m16n8k16) with every k / v row gathered ONCE per tile, the sparsity
+ * mask and the edge term as an additive bias tile.  Meant for node orders with locality (layers/_reorder.py).
+ *
+ * anemoi_b200_attn_tile_plan is the HOST-side analysis step (HOST pointers, run once per static graph): from the dst-sorted CSR it
+ * builds tile_meta [n_tiles, 4] int32 = {first dst row, first slot, first edge, rows | slots << 8 | edges << 16}, slot_src (source row
+ * of every slot) and emeta [E] uint16 (slot of every edge inside its tile | row inside its tile << 8).  Capacities: tile_meta 4 * n_dst,
+ * slot_src E, emeta E.  max_edges bounds the edges of a tile: <= 224 and <= 10752 / (4 dp) (the kernel stages dp fp32 attributes per edge
+ * in shared memory).  Returns -3 when a destination has more than 64 distinct sources or max_edges edges (no plan; use
+ * anemoi_b200_gt_attention_fwd).
+ * The plan arrays are then copied to the device by the caller (tile_meta 16-byte aligned) and passed to the kernel entry point.
+ */
+ANEMOI_API int anemoi_b200_attn_tile_plan(const int32_t* src32_host, const int32_t* colptr32_host, int64_t n_src, int64_t n_dst,
+                               int64_t max_edges, int32_t* tile_meta_host, int32_t* slot_src_host, uint16_t* emeta_host, int64_t* n_tiles,
+                               int64_t* n_slots);
+ANEMOI_API int anemoi_b200_gt_attention_tiled_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                       const float* edge_attr, int64_t lde, const float* b_edge, const void* qw, int64_t ldqw, void* abar,
+                                       int64_t ldabar, int64_t dp, const int32_t* colptr32, const int32_t* tile_meta,
+                                       const int32_t* slot_src, const uint16_t* emeta, int64_t n_tiles, const void* add, int64_t ldadd,
+                                       void* out, int64_t ldo, int64_t n_dst, int64_t heads, int64_t ch, void* stream);
+
 /* -- GraphConv tail: LayerNorm + residual + dst-segmented sum ------------------------------------------------
  * Replaces the tail of layers/conv.py:73-81: e'[i] = LN(h[i]) + e[i]  (written to e_new) and
  * out[d] = sum_{edges i into d} e'[i]  (scatter-sum; deterministic segmented reduction over the dst-sorted
@@ -130,6 +154,33 @@ ANEMOI_API int anemoi_b200_gt_attention_fwd(const void* q, int64_t ldq, const vo
 ANEMOI_API int anemoi_b200_graphconv_ln_aggregate(const void* h, int64_t ldh, const float* gamma, const float* beta, const void* e, int64_t lde,
                                        void* e_new, int64_t ldn, const int32_t* colptr32, void* out, int64_t ldo, int64_t n_dst,
                                        int64_t C, float eps, int dtype, void* stream);
+
+/* -- multi-GPU exchange over NVLink peer memory (one process per GPU, one NVSwitch box) ---------------------------------
+ * Replaces, for the dst-range sharded forward, the NCCL collectives of the reference: `halo_exchange` (distributed/graph.py:466-484,
+ * layers/block.py:1159-1169) and the source-row all-gather `sync_tensor` (graph.py:227-240).  Ranks write the rows their peers need
+ * straight into the peers' tables through CUDA-IPC mapped pointers; all three steps are ordinary kernels on `stream`, so the exchange
+ * is captured in the same CUDA graph as the compute around it.
+ *   ipc_alloc   cudaMalloc + zero `bytes`, return the pointer and its 64-byte cudaIpcMemHandle_t (to be sent to the peers by the
+ *               caller, e.g. torch.distributed.all_gather); ipc_open maps a peer's handle; ipc_close / ipc_free undo them.
+ *   A CHANNEL is one 256-byte control block per rank in symmetric memory; ctl_ptrs [world] (HOST array) holds every rank's block as
+ *   seen from this process (own rank: the local pointer).  Per exchange, in this order on every rank:
+ *   peer_rendezvous  exchange number c = ++counter (on the device); tell every peer "started c", wait until every peer has: their
+ *                    consumers of exchange c-1 are done, the tables may be overwritten.
+ *   halo_push        rows[send_idx[j], :row_bytes] for j in [send_off[p], send_off[p+1]) go to dst_ptrs[p] + (j - send_off[p]) *
+ *                    dst_ld_bytes in rank p (peer-mapped address, HOST array [world]); then "rows of c from me have arrived" to all peers.
+ *                    send_idx / send_off are DEVICE int32 arrays (send_off has world + 1 entries).
+ *   halo_wait        wait until the rows of exchange c from every peer have arrived.
+ * A peer that does not show up within ~10 s traps the waiting kernel (error at the next synchronisation) instead of hanging.
+ */
+ANEMOI_API int anemoi_b200_ipc_alloc(int64_t bytes, void** dev_ptr, void* handle64);
+ANEMOI_API int anemoi_b200_ipc_open(const void* handle64, void** dev_ptr);
+ANEMOI_API int anemoi_b200_ipc_close(void* dev_ptr);
+ANEMOI_API int anemoi_b200_ipc_free(void* dev_ptr);
+ANEMOI_API int anemoi_b200_peer_rendezvous(const uint64_t* ctl_ptrs_host, int64_t world, int64_t rank, void* stream);
+ANEMOI_API int anemoi_b200_halo_push(const void* rows, int64_t ld_bytes, int64_t row_bytes, const int32_t* send_idx, const int32_t* send_off,
+                          int64_t n_send, const uint64_t* dst_ptrs_host, int64_t dst_ld_bytes, const uint64_t* ctl_ptrs_host, int64_t world,
+                          int64_t rank, void* stream);
+ANEMOI_API int anemoi_b200_halo_wait(const uint64_t* ctl_ptrs_host, int64_t world, int64_t rank, void* stream);
 
 /* -- helpers -----------------------------------------------------------------------------------------------
  * cast/copy a [M, K] matrix into a [M, ldo] buffer (zero-filling columns K..Kpad-1), any of f32/bf16 <-> f32/bf16,

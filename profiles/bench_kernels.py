@@ -60,12 +60,20 @@ if "attn" in which:
         csr = ops.build_csr(plan.edge_index, N, N)
         ea = ea.index_select(0, plan.edge_perm).contiguous()
         print(json.dumps({"reorder": True, "reuse16_before": RO.source_reuse(gr["proc_index"]), "reuse16_after": RO.source_reuse(plan.edge_index)}))
+    if "tile" in which:  # destination-tile tensor-core kernel on the current (natural or reordered) edge list
+        tplan = ops.attention_tiles(csr)
+        print(json.dumps({"tile_plan": True, "n_tiles": tplan.n_tiles, "n_slots": tplan.n_slots, "reuse": round(tplan.reuse, 3)}))
+
+        def attn():  # noqa: F811
+            ops.gt_attention(buf[:, :C], buf[:, C : 2 * C], buf[:, 2 * C : 3 * C], csr, H, edge_attr=ea, b_edge=b_e, qw=buf[:, 4 * C :], abar=out[:, C:], dp=dp,
+                             add=buf[:, 3 * C : 4 * C], out=out[:, :C], tiles=tplan)  # fmt: skip
+
     med, mn = timeit(attn)
     # algorithmic bytes: q, k, v, self read + out written (N*C*2 each) + qw/abar + per edge: src id 4 B + 64 B attributes
     alg = 5 * N * C * 2 + 2 * N * H * dp * 2 + E * (4 + 64) + 4 * N
     print(json.dumps({"kernel": "gt_attention(folded)", "us_median": round(med, 1), "us_min": round(mn, 1), "alg_MB": round(alg / 1e6, 1),
                       "GBs": round(alg / med / 1e3, 1), "frac_hbm_measured": round(alg / med / 1e3 / pk["hbm_gbs"], 3),
-                      "gathered_MB": round(E * 2 * C * 2 / 1e6, 1)}))  # fmt: skip
+                      "gathered_MB": round((tplan.n_slots if "tile" in which else E) * 2 * C * 2 / 1e6, 1), "variant": "+".join(w for w in which if w in ("reorder", "tile")) or "pipe"}))  # fmt: skip
 
 if "gemm" in which:
     M = 40962

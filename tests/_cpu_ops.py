@@ -97,7 +97,7 @@ def row_stats(x, eps=1e-5):
     return torch.stack([xf.mean(1), (xf.var(1, unbiased=False) + eps).rsqrt()], 1)
 
 
-def gt_attention(q, k, v, csr, heads, e_proj=None, edge_attr=None, w_edge=None, b_edge=None, qw=None, abar=None, dp=0, add=None, out=None):
+def gt_attention(q, k, v, csr, heads, e_proj=None, edge_attr=None, w_edge=None, b_edge=None, qw=None, abar=None, dp=0, add=None, out=None, tiles=None):
     n_dst, C = q.shape
     Ch = C // heads
     src, dst = csr.src32.long(), csr.dst32.long()
@@ -204,6 +204,7 @@ def install() -> None:
     for name in ("build_csr", "linear", "layer_norm", "row_stats", "gt_attention", "graphconv_ln_aggregate", "cast_pad", "add", "partial_stats_buffer",
                  "assemble_input", "assemble_output", "glu_combine", "cond_layer_norm"):
         setattr(ops, name, globals()[name])
+    ops.attention_tiles = lambda csr: None  # the tile plan only feeds the CUDA kernel
     ops._need_cuda = lambda *a, **k: None
     torch.cuda.is_current_stream_capturing = lambda: False  # csr_for asks; there is no CUDA runtime here
     assert Fn.ops is ops

@@ -345,6 +345,82 @@ def test_gt_attention_folded_lin_edge(ops, H, Ch, d_e, dt):
     assert torch.all(o[-5:, C:] == 0)
 
 
+def _local_graph(n_src, n_dst, deg, span, seed, zero_tail=0):
+    """dst d takes ``deg`` sources from a window of ``span`` rows around d * n_src / n_dst: neighbouring destinations share sources."""
+    g = torch.Generator().manual_seed(seed)
+    d = torch.arange(n_dst - zero_tail).repeat_interleave(deg)
+    centre = (d.float() * n_src / n_dst).long()
+    src = (centre + torch.randint(-span, span + 1, (d.numel(),), generator=g)).clamp_(0, n_src - 1)
+    return torch.stack([src, d])
+
+
+@pytest.mark.parametrize("H,Ch,d_e", [(16, 32, 11), (16, 64, 11), (8, 32, 3), (4, 64, 16), (8, 64, 5)])
+@pytest.mark.parametrize("graph", ["random", "local", "bipartite_local"])
+def test_gt_attention_tiled(ops, H, Ch, d_e, graph):
+    """Destination-tile tensor-core kernel (anemoi_b200_gt_attention_tiled_fwd + the host planner) against the oracle attention with the
+    materialised projection on the same bf16-rounded operands, and against the warp-per-node kernel.  Random graphs (no locality: small
+    tiles, duplicate (src, dst) pairs, rows without edges), local graphs (full 16-row tiles, heavy source re-use) and bipartite sizes."""
+    dt = torch.bfloat16
+    g = torch.Generator().manual_seed(H * 1000 + Ch + d_e)
+    if graph == "random":
+        n_src, n_dst, E = 300, 301, 2600
+        ei = _rand_graph(n_src, n_dst, E, 13, zero_tail=5)
+    elif graph == "local":
+        n_src = n_dst = 1000
+        ei = _local_graph(n_src, n_dst, 9, 6, 3, zero_tail=5)
+    else:
+        n_src, n_dst = 700, 1003
+        ei = _local_graph(n_src, n_dst, 5, 4, 4, zero_tail=5)
+    E = ei.shape[1]
+    C = H * Ch
+    dp = (d_e + 3) // 4 * 4
+    assert ops.attention_tiles_supported(C, H, dt, dp)
+    a = torch.randn(E, d_e, generator=g)
+    w_e, b_e = torch.randn(C, d_e, generator=g) / 3, torch.randn(C, generator=g)
+    buf = torch.randn(n_dst, 2 * C + H * dp, generator=g)  # q | self | qw
+    k = torch.randn(n_src, C, generator=g).to(dt)
+    v = torch.randn(n_src, C, generator=g).to(dt)
+    q32 = buf[:, :C].to(dt).float()
+    qw = torch.zeros(n_dst, H, dp)
+    qw[:, :, :d_e] = torch.einsum("nhc,hca->nha", q32.view(n_dst, H, Ch), w_e.view(H, Ch, d_e))
+    buf[:, 2 * C :] = qw.view(n_dst, -1)
+    buf = buf.to(dt).cuda()
+    a16 = torch.zeros(E, 16)
+    a16[:, :d_e] = a
+    csr = ops.build_csr(ei.cuda(), n_src, n_dst)
+    plan = ops.attention_tiles(csr)
+    assert plan is not None and plan.n_tiles >= (n_dst + 15) // 16
+    if graph != "random":
+        assert plan.reuse > 1.5  # the tiles really share sources
+    out = torch.full((n_dst, C + H * dp), float("nan"), dtype=dt, device="cuda")
+    args = dict(edge_attr=a16.cuda(), b_edge=b_e.cuda(), qw=buf[:, 2 * C :], dp=dp, add=buf[:, C : 2 * C])
+    ops.gt_attention(buf[:, :C], k.cuda(), v.cuda(), csr, H, abar=out[:, C:], out=out[:, :C], tiles=plan, **args)
+    out_pipe = torch.empty_like(out)
+    ops.gt_attention(buf[:, :C], k.cuda(), v.cuda(), csr, H, abar=out_pipe[:, C:], out=out_pipe[:, :C], **args)
+    o = out.float().cpu()
+    assert torch.isfinite(o).all()
+    abar = o[:, C:].view(n_dst, H, dp)[:, :, :d_e]
+    full = o[:, :C] + torch.einsum("nha,hca->nhc", abar, w_e.view(H, Ch, d_e)).reshape(n_dst, C)
+    sh = lambda t, n: t.float().view(n, H, Ch)
+    ref = R.gt_attention(sh(q32, n_dst), sh(k, n_src), sh(v, n_src), (a @ w_e.t() + b_e).view(E, H, Ch), ei, n_dst).view(n_dst, C)
+    ref = ref + buf[:, C : 2 * C].float().cpu()
+    tol = 2**-5 * ref.abs().max().item()
+    assert (full - ref).abs().max().item() <= tol
+    assert torch.equal(o[-5:, :C], buf[-5:, C : 2 * C].float().cpu())  # zero in-degree: 0 + add, no bias
+    assert torch.all(o[-5:, C:] == 0)
+    # the two kernels agree to bf16 rounding of the outputs (the tile kernel rounds the softmax weights to bf16 before P.V)
+    op = out_pipe.float().cpu()
+    assert (o[:, :C] - op[:, :C]).abs().max().item() <= 2**-6 * ref.abs().max().item()
+    assert (o[:, C:] - op[:, C:]).abs().max().item() <= 2**-6 * max(op[:, C:].abs().max().item(), 1.0)
+
+
+def test_attention_tile_plan_rejects_wide_destinations(ops):
+    """A destination with more than 64 distinct sources has no tile plan (the caller keeps the warp-per-node kernel)."""
+    ei = torch.stack([torch.arange(100), torch.zeros(100, dtype=torch.long)])
+    csr = ops.build_csr(ei.cuda(), 100, 3)
+    assert ops.attention_tiles(csr) is None and csr.tiles is False
+
+
 def test_gt_attention_strided_qkv(ops):
     """q|k|v|self as column slices of one [N, 4C] buffer (the block layout)."""
     g = torch.Generator().manual_seed(9)

@@ -33,6 +33,7 @@ DEFAULT_KERNELS = {
 # reference dotted paths are accepted and mapped onto the in-package container classes
 _ALIASES = {
     "anemoi.models.layers.normalization.AutocastLayerNorm": "anemoi_core_b200.layers.normalization.AutocastLayerNorm",
+    "anemoi.models.layers.normalization.ConditionalLayerNorm": "anemoi_core_b200.layers.normalization.ConditionalLayerNorm",
 }
 
 

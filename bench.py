@@ -40,6 +40,9 @@ WORKLOADS = {
                  desc="O96 grid (40320 pts) -> ico-6 multi-scale mesh (40962 nodes, 327600 edges), GraphTransformer enc + 16x512 proc (16 heads) + dec"),
     "cfg3": dict(grid="n320", mesh_level=6, kind="gnn", C=1024, layers=16, heads=16, in_grid=212, in_mesh=12, out_grid=88,
                  desc="N320 grid (542080 pts) -> ico-6 mesh, GNN enc + 16x1024 proc + dec"),
+    "cfg4": dict(grid="o1280", mesh_level=7, kind="graphtransformer", C=1024, layers=16, heads=16, in_grid=212, in_mesh=12, out_grid=88,
+                 desc="O1280 grid (6599680 pts) -> ico-7 multi-scale mesh (163842 nodes, 1310640 edges), GraphTransformer enc + 16x1024 proc (16 heads) + dec; "
+                      "BASELINE.json configs[3], meant for --gpus 8 (grid / mesh rows and edges sharded)"),
     "cfg5": dict(grid="o96", mesh_level=6, kind="graphtransformer", C=512, layers=16, heads=16, in_grid=212, in_mesh=12, out_grid=88, rollout=40,
                  desc="cfg2 model, 40-step autoregressive rollout (prognostic outputs written back into the newest input time slot, forcings/statics held), per-step latency"),
     "small": dict(grid="o32", mesh_level=4, kind="graphtransformer", C=512, layers=4, heads=16, in_grid=212, in_mesh=12, out_grid=88,
@@ -234,6 +237,28 @@ def run_reference(args, w):
     print(json.dumps(line), flush=True)
 
 
+def single_gpu_rows(model, w, gd, x_full, x_grid, x_mesh, grid_shards, dev, n_out_rows):
+    """Rank 0's parity reference at N > 1: the SAME step computed on this one GPU without a group, restricted to the output rows the
+    sharded run returns on this rank.  Sharded inputs (GraphTransformer): encoder and processor over the whole graph, decoder over rank 0's
+    grid rows only (the edges into them, relabelled) - identical to the whole-graph decoder on those rows, and it keeps the 6.6 M-row cfg4
+    decoder off a single GPU.  Replicated inputs: the plain single-GPU forward."""
+    from anemoi_core_b200 import ops
+    from anemoi_core_b200.distributed.shapes import BipartiteGraphShardInfo
+    from anemoi_core_b200.distributed.shapes import GraphShardInfo
+
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        if x_full is None:
+            return model(x_grid, x_mesh, gd)[:n_out_rows]
+        xg, xm = x_full[0].to(dev), x_full[1].to(dev)
+        bi = BipartiteGraphShardInfo()
+        _, lat = model.encoder((xg, xm), 1, bi, gd["enc_attr"], gd["enc_index"])
+        y = model.processor(lat, 1, GraphShardInfo(nodes=[lat.shape[0]]), gd["proc_attr"], gd["proc_index"])
+        y = ops.add(y, lat)
+        n0 = grid_shards[0]
+        e1 = int(torch.searchsorted(gd["dec_index"][1].contiguous(), torch.tensor([n0], device=dev)).item())  # dst-sorted: rows [0, n0) own edges [0, e1)
+        return model.decoder((y, xg[:n0]), 1, bi, gd["dec_attr"][:e1], gd["dec_index"][:, :e1].contiguous())
+
+
 # ----------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -276,14 +301,28 @@ def main():
 
     gd = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in gr.items()}
     x_grid_h, x_mesh_h = make_inputs(w, gr)
-    x_grid_h, x_mesh_h = x_grid_h.pin_memory(), x_mesh_h.pin_memory()
-    x_grid, x_mesh = x_grid_h.to(dev), x_mesh_h.to(dev)
     mesh_shards = get_balanced_partition_sizes(gr["n_mesh"], world) if world > 1 else None
     grid_shards = get_balanced_partition_sizes(gr["n_grid"], world) if world > 1 else None
+    # N > 1, GraphTransformer: every rank holds, uploads and returns ITS rows only (the reference's in_out_sharded mode,
+    # encoder_processor_decoder.py:176-183); what crosses NVLink is the halo of each exchange.  GNN: replicated inputs (its mappers shard inside).
+    sharded_io = world > 1 and w["kind"] == "graphtransformer"
+    x_full = None
+    if sharded_io:
+        g0, m0 = sum(grid_shards[:rank]), sum(mesh_shards[:rank])
+        if rank == 0:
+            x_full = (x_grid_h, x_mesh_h)  # kept on the host for the single-GPU parity check below
+        x_grid_h, x_mesh_h = x_grid_h[g0 : g0 + grid_shards[rank]].clone(), x_mesh_h[m0 : m0 + mesh_shards[rank]].clone()
+        fwd_kw = dict(model_comm_group=group, mesh_shards=mesh_shards, grid_shards=grid_shards, keep_output_sharded=True, inputs_sharded=True)
+    elif world > 1:
+        fwd_kw = dict(model_comm_group=group, mesh_shards=mesh_shards, grid_shards=grid_shards)
+    else:
+        fwd_kw = {}
+    x_grid_h, x_mesh_h = x_grid_h.pin_memory(), x_mesh_h.pin_memory()
+    x_grid, x_mesh = x_grid_h.to(dev), x_mesh_h.to(dev)
 
     def step(xg, xm):
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-            return model(xg, xm, gd, group, mesh_shards, grid_shards)
+            return model(xg, xm, gd, **fwd_kw)
 
     # ---- warm-up (also builds CSR plans, packed weights, TMA descriptors) and launch count per step --------------------
     for _ in range(2):
@@ -295,20 +334,26 @@ def main():
     launches_per_step = ops.LAUNCHES - n0
     torch.cuda.synchronize()
 
-    # N = 1: the whole step is one CUDA graph.  N > 1: NCCL calls inside a captured graph hung on the 2-GPU box (round 1), so the compute
-    # between two all-gathers is captured and the collectives run eagerly between the segment replays (SegmentedCapture).
+    # N = 1: the whole step is one CUDA graph.  N > 1, GraphTransformer: every exchange is a peer-memory kernel (csrc/peer.cu), so the
+    # sharded step is ONE graph per rank as well.  Where NCCL collectives remain (GNN all-gathers, ANEMOI_B200_PEER=0) the compute between
+    # two collectives is captured and the collectives run eagerly between the segment replays (SegmentedCapture).
     use_graph = not args.no_graph
+    whole_graph = world == 1
+    if world > 1 and sharded_io:
+        from anemoi_core_b200.distributed import peer
+
+        whole_graph = peer.available(group, dev)
     if use_graph:
         try:
             with torch.autocast("cuda", dtype=torch.bfloat16):
-                if world == 1:
-                    replay = model.capture(x_grid, x_mesh, gd)
+                if whole_graph:
+                    replay = model.capture(x_grid, x_mesh, gd, **fwd_kw)
                 else:
-                    replay = model.capture_segmented(x_grid, x_mesh, gd, model_comm_group=group, mesh_shards=mesh_shards, grid_shards=grid_shards)
+                    replay = model.capture_segmented(x_grid, x_mesh, gd, **fwd_kw)
         except Exception as e:  # noqa: BLE001  (e.g. a collective that cannot be captured): fall back to eager launches, and say so
             if world == 1:
                 raise
-            print(f"[bench] CUDA-graph capture with NCCL failed on rank {rank} ({type(e).__name__}: {e}); using eager launches", file=sys.stderr)
+            print(f"[bench] CUDA-graph capture failed on rank {rank} ({type(e).__name__}: {e}); using eager launches", file=sys.stderr)
             use_graph = False
     if world > 1:  # all ranks must agree
         flag = torch.tensor([1 if use_graph else 0], device=dev)
@@ -333,10 +378,7 @@ def main():
             raise SystemExit(f"[bench] CUDA-graph replay differs from the eager step: {checks['replay_vs_eager']}")
     if world > 1:
         if rank == 0:
-            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-                single = model(x_grid, x_mesh, gd)  # no group: the whole graph on this GPU
-            checks["sharded_vs_single_gpu"] = rel_err(eager_out, single)
-            del single
+            checks["sharded_vs_single_gpu"] = rel_err(eager_out, single_gpu_rows(model, w, gd, x_full, x_grid, x_mesh, grid_shards, dev, out.shape[0]))
         bad = torch.tensor([1 if (rank == 0 and checks["sharded_vs_single_gpu"]["rel_l2"] > 5e-3) else 0], device=dev)
         torch.distributed.all_reduce(bad, op=torch.distributed.ReduceOp.MAX)
         if bad.item():
@@ -412,10 +454,14 @@ def main():
                    "p99_ms": steady[min(len(steady) - 1, int(0.99 * len(steady)))], "first_ms": lat[0]}
     clk = clocks.stop() if rank == 0 else None
 
+    io_bytes = [x_grid_h.numel() * 4 + x_mesh_h.numel() * 4, out_h.numel() * out_h.element_size()]
     if world > 1:
         t = torch.tensor([ms_dev, ms_e2e], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms_dev, ms_e2e = t.tolist()
+        t = torch.tensor(io_bytes, dtype=torch.int64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+        io_bytes = t.tolist()
 
     # ---- roofline leg: CUDA events around every C-ABI launch, eager, over 3 steps -------------------------------------------
     pk = peaks()
@@ -480,10 +526,13 @@ def main():
         "metric": "forward ms/step", "value": ms_dev, "unit": "ms/step", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['desc']}", "batch": 1, "precision": "bf16 autocast, fp32 accumulate",
-                   "launch": ("cuda-graph replay" if world == 1 else "cuda-graph segments + eager NCCL collectives") if use_graph else "eager", "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
-                   "parallelism": "single GPU" if world == 1 else f"encoder / processor / decoder dst-range sharded over {world} GPUs (halo all-to-all of k|v rows per layer over NCCL)"},
-        "e2e": {"value": ms_e2e, "unit": "ms/step", "h2d_bytes_per_step": x_grid_h.numel() * 4 + x_mesh_h.numel() * 4,
-                "d2h_bytes_per_step": out_h.numel() * out_h.element_size()},
+                   "launch": ("cuda-graph replay (one graph per rank)" if whole_graph else "cuda-graph segments + eager NCCL collectives") if use_graph else "eager",
+                   "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
+                   "parallelism": "single GPU" if world == 1 else (
+                       f"grid and mesh rows, edges and every stage dst-range sharded over {world} GPUs; inputs / outputs stay sharded; per exchange the k|v halo rows "
+                       f"are written into the peers' tables over NVLink ({'peer-memory kernels inside the graph' if whole_graph else 'NCCL all-to-all'})")},
+        "e2e": {"value": ms_e2e, "unit": "ms/step", "h2d_bytes_per_step": io_bytes[0], "d2h_bytes_per_step": io_bytes[1],
+                "note": "bytes summed over ranks; every rank copies its own rows" if sharded_io else "bytes summed over ranks"},
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,
         "clocks": clk,

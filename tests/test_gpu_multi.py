@@ -65,6 +65,64 @@ def _worker(rank, world, init_file, ret):
                 got = model(xg, xm, gd, group, sizes, gsz)
             err = ((got.float() - full.float()).abs().max() / full.float().abs().max()).item()
             msgs.append(("encprocdec", str(dt), err, err <= (1e-5 if dt == torch.float32 else 2e-2) and got.shape == full.shape))
+        # ---- (round 2) the same step with sharded inputs / outputs, every exchange a peer-memory kernel, captured as ONE CUDA graph ----
+        from anemoi_core_b200.distributed import peer
+
+        msgs.append(("peer_memory_available", "-", 0.0, peer.available(group, torch.device("cuda", rank))))
+        g0, m0 = sum(gsz[:rank]), sum(sizes[:rank])
+        xg_l, xm_l = xg[g0 : g0 + gsz[rank]].contiguous(), xm[m0 : m0 + sizes[rank]].contiguous()
+        kw = dict(model_comm_group=group, mesh_shards=sizes, grid_shards=gsz, keep_output_sharded=True, inputs_sharded=True)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            full = model(xg, xm, gd)
+            got = model(xg_l, xm_l, gd, **kw)
+            err = ((got.float() - full[g0 : g0 + gsz[rank]].float()).abs().max() / full.float().abs().max()).item()
+            msgs.append(("encprocdec_sharded_io", "bf16", err, err <= 2e-2 and got.shape[0] == gsz[rank]))
+            if peer.available(group):
+                replay = model.capture(xg_l, xm_l, gd, **kw)
+                for it in range(3):  # replays keep the device-side exchange counters in step across ranks
+                    rep = replay().clone()
+                    err = ((rep.float() - got.float()).abs().max() / got.float().abs().max().clamp_min(1e-30)).item()
+                    msgs.append((f"whole_graph_replay_{it}", "bf16", err, err <= 1e-6))
+                # new inputs through the static buffers
+                rep = replay(xg_l * 0.5, xm_l).clone()
+                ref2 = model(xg_l * 0.5, xm_l, gd, **kw)
+                err = ((rep.float() - ref2.float()).abs().max() / ref2.float().abs().max()).item()
+                msgs.append(("whole_graph_replay_new_input", "bf16", err, err <= 1e-6))
+        # ---- NCCL all-to-all fallback of the halo exchange (ANEMOI_B200_PEER=0) must give the same rows ----
+        from anemoi_core_b200.distributed import halo
+
+        peer._STATE[id(group)] = False
+        halo._PLANS.clear()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            got2 = model(xg_l, xm_l, gd, **kw)
+        err = ((got2.float() - got.float()).abs().max() / got.float().abs().max()).item()
+        msgs.append(("nccl_fallback_vs_peer", "bf16", err, err <= 1e-6))
+        del peer._STATE[id(group)]
+        halo._PLANS.clear()
+        # ---- heads (Ulysses) strategy and the GNN halo form, first time on NCCL (Gloo-only in round 1) ----
+        from anemoi_core_b200.layers import processor as P
+
+        torch.manual_seed(0)
+        mh = GraphTransformerProcessor(num_layers=2, num_channels=256, num_chunks=1, num_heads=8, mlp_hidden_ratio=4, edge_dim=gr["edge_dim"],
+                                       shard_strategy="heads").cuda().eval()  # fmt: skip
+        x = torch.randn(n, 256, generator=torch.Generator().manual_seed(1)).cuda()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            full = mh(x, 1, GraphShardInfo(nodes=[n]), ea, ei)
+            local = mh(shard_rows(x, sizes, group).contiguous(), 1, GraphShardInfo(nodes=sizes), ea, ei, group)
+            gath = gather_rows(local, sizes, group)
+        err = ((gath.float() - full.float()).abs().max() / full.float().abs().max()).item()
+        msgs.append(("gt_heads_strategy", "bf16", err, err <= 2e-2))
+        P.GNN_HALO = True
+        torch.manual_seed(0)
+        mg = GNNProcessor(num_channels=128, num_layers=2, num_chunks=1, mlp_extra_layers=0, edge_dim=gr["edge_dim"]).cuda().eval()
+        x = torch.randn(n, 128, generator=torch.Generator().manual_seed(1)).cuda()
+        with torch.no_grad():
+            full = mg(x, 1, GraphShardInfo(nodes=[n]), ea, ei)
+            local = mg(shard_rows(x, sizes, group).contiguous(), 1, GraphShardInfo(nodes=sizes), ea, ei, group)
+            gath = gather_rows(local, sizes, group)
+        err = ((gath - full).abs().max() / full.abs().max()).item()
+        msgs.append(("gnn_halo_form", "fp32", err, err <= 1e-5))
+        P.GNN_HALO = False
         ret[rank] = msgs
     except Exception as e:  # noqa: BLE001
         import traceback
@@ -85,3 +143,4 @@ def test_sharded_processors_match_single_gpu():
             assert isinstance(ret.get(r), list), ret.get(r)
             for kind, dt, err, ok in ret[r]:
                 assert ok, f"rank {r} {kind} {dt}: sharded vs single rel err {err:.3e}"
+            print(f"rank {r}:", [(k, d_, f"{e:.2e}") for k, d_, e, _ in ret[r]])

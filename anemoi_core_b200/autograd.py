@@ -1,0 +1,160 @@
+"""``torch.autograd.Function`` wiring of the C-ABI ops (backward of the fused ops, so the drop-in modules train).
+
+Reference: the autograd halves the reference gets for free from PyTorch / PyG, and for its fused attention op
+``triton/gt.py:451-556`` (``GraphTransformerFunction`` / ``register_autograd``) with the backward kernels ``gt.py:182-376``.
+
+Forward of every Function is the same sm_100a kernel the inference path runs; backward:
+  LinearFn          dx = dz W on the tcgen05 GEMM (``ops.linear`` with the transposed weight), dW = dz^T x as a plain library GEMM
+                    (cuBLAS through ``torch.matmul``: a bare GEMM with nothing to fuse), db = column sum; GELU through ``ops.gelu``.
+  LayerNormFn       ``ops.layer_norm_bwd``.
+  GTAttentionFn     ``ops.gt_attention_bwd`` (dst-major + src-major passes over the cached CSR / reverse CSR; deterministic).
+  GraphConvTailFn   ``ops.layer_norm_bwd`` with the gathered second cotangent (d out[dst[i]]): e' = LN(h) + e, out = segment-sum(e').
+No CPU path: CPU tensors raise in ``ops`` like everywhere else.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+from torch.autograd import Function
+
+from . import ops
+
+
+def _pad_cols(t: Tensor, k: int) -> Tensor:
+    return t if t.shape[1] == k else torch.nn.functional.pad(t, (0, k - t.shape[1]))
+
+
+class LinearFn(Function):
+    """y = [gelu](x W^T + b) in compute dtype ``dt`` (x [M, K] any float dtype, W [N, K], b [N] | None)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], gelu: bool, dt: torch.dtype) -> Tensor:
+        K = x.shape[1]
+        kp = max(64, (K + 7) // 8 * 8) if dt == torch.bfloat16 else K  # tcgen05 operands: 16-byte rows, one swizzle span
+        xa = ops.cast_pad(x.detach(), dt, kp)
+        wa = _pad_cols(weight.detach(), kp).to(dt).contiguous()
+        z = ops.linear(xa, wa, None if bias is None else bias.detach().float().contiguous())
+        ctx.save_for_backward(xa, wa, z if gelu else None)
+        ctx.meta = (K, x.dtype, weight.dtype, None if bias is None else bias.dtype, gelu)
+        return ops.gelu(z) if gelu else z
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        xa, wa, z = ctx.saved_tensors
+        K, x_dt, w_dt, b_dt, gelu = ctx.meta
+        dy = dy.to(xa.dtype)
+        dy = dy if dy.stride(1) == 1 else dy.contiguous()
+        dz = ops.gelu(z, dy) if gelu else dy
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.linear(dz, wa.t().contiguous())[:, :K].to(x_dt)
+        if ctx.needs_input_grad[1]:
+            dw = torch.matmul(dz.t(), xa)[:, :K].to(w_dt)  # plain library GEMM (weight gradient; reduction over all rows)
+        if b_dt is not None and ctx.needs_input_grad[2]:
+            db = dz.float().sum(0).to(b_dt)
+        return dx, dw, db, None, None
+
+
+class GeluFn(Function):
+    @staticmethod
+    def forward(ctx, x: Tensor) -> Tensor:
+        x = x.detach()
+        x = x if x.stride(1) == 1 else x.contiguous()
+        ctx.save_for_backward(x)
+        return ops.gelu(x)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        (x,) = ctx.saved_tensors
+        dy = dy.to(x.dtype)
+        return ops.gelu(x, dy if dy.stride(1) == 1 else dy.contiguous())
+
+
+class LayerNormFn(Function):
+    """LayerNorm over ``groups`` groups of the last dimension (weight / bias [C] | None), output in ``dt``."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], eps: float, groups: int, dt: torch.dtype) -> Tensor:
+        x = x.detach()
+        x = x if x.stride(1) == 1 else x.contiguous()
+        w32 = None if weight is None else weight.detach().float().contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        ctx.save_for_backward(x, w32)
+        ctx.meta = (eps, groups, None if weight is None else weight.dtype, None if bias is None else bias.dtype)
+        return ops.layer_norm(x, w32, b32, eps, out_dtype=dt, groups=groups)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, w32 = ctx.saved_tensors
+        eps, groups, w_dt, b_dt = ctx.meta
+        dy = dy.to(x.dtype)
+        dx, dg, db, _ = ops.layer_norm_bwd(x, w32, dy if dy.stride(1) == 1 else dy.contiguous(), eps, groups)
+        return dx, (dg.to(w_dt) if w_dt is not None else None), (db.to(b_dt) if b_dt is not None else None), None, None, None
+
+
+class GTAttentionFn(Function):
+    """Edge-softmax attention with the materialised edge projection: the operator boundary of the reference
+    (``anemoi::graph_transformer_attention``, triton/gt.py:390-447)."""
+
+    @staticmethod
+    def forward(ctx, q: Tensor, k: Tensor, v: Tensor, e: Optional[Tensor], csr: ops.GraphCSR, heads: int) -> Tensor:
+        q, k, v = q.detach(), k.detach(), v.detach()
+        e = None if e is None else e.detach()
+        lse = torch.empty((q.shape[0], heads), dtype=torch.float32, device=q.device)
+        out = ops.gt_attention(q, k, v, csr, heads, e_proj=e, lse=lse)
+        ctx.save_for_backward(q, k, v, e, out, lse)
+        ctx.csr, ctx.heads = csr, heads
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        q, k, v, e, out, lse = ctx.saved_tensors
+        dout = dout.to(q.dtype)
+        dq, dk, dv, de = ops.gt_attention_bwd(q, k, v, e, out, dout if dout.stride(1) == 1 else dout.contiguous(), lse, ctx.csr, ctx.heads)
+        return dq, dk, dv, de, None, None
+
+
+class GraphConvTailFn(Function):
+    """(e', out) = (LayerNorm(h) * gamma + beta + e, segment-sum of e' over the dst-sorted edges): layers/conv.py:73-81."""
+
+    @staticmethod
+    def forward(ctx, h: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], e: Tensor, csr: ops.GraphCSR, eps: float):
+        h, e = h.detach(), e.detach()
+        h = h if h.stride(1) == 1 else h.contiguous()
+        w32 = None if weight is None else weight.detach().float().contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        e_new, out = ops.graphconv_ln_aggregate(h, w32, b32, e.to(h.dtype), csr, eps)
+        ctx.save_for_backward(h, w32)
+        ctx.csr, ctx.meta = csr, (eps, None if weight is None else weight.dtype, None if bias is None else bias.dtype, e.dtype)
+        ctx.set_materialize_grads(False)
+        return e_new, out
+
+    @staticmethod
+    def backward(ctx, d_enew: Optional[Tensor], d_out: Optional[Tensor]):
+        h, w32 = ctx.saved_tensors
+        eps, w_dt, b_dt, e_dt = ctx.meta
+        if d_enew is None and d_out is None:
+            return None, None, None, None, None, None
+        dy = None if d_enew is None else d_enew.to(h.dtype).contiguous()
+        dz = None if d_out is None else d_out.to(h.dtype).contiguous()
+        dh, dg, db, g = ops.layer_norm_bwd(h, w32, dy, eps, 1, dz=dz, idx=ctx.csr.dst32 if dz is not None else None, want_dres=True)
+        return dh, (dg.to(w_dt) if w_dt is not None else None), (db.to(b_dt) if b_dt is not None else None), g.to(e_dt), None, None
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], dt: torch.dtype, gelu: bool = False) -> Tensor:
+    return LinearFn.apply(x, weight, bias, gelu, dt)
+
+
+def layer_norm(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], eps: float, dt: torch.dtype, groups: int = 1) -> Tensor:
+    return LayerNormFn.apply(x, weight, bias, eps, groups, dt)
+
+
+def gt_attention(q: Tensor, k: Tensor, v: Tensor, e: Optional[Tensor], csr: ops.GraphCSR, heads: int) -> Tensor:
+    return GTAttentionFn.apply(q, k, v, e, csr, heads)
+
+
+def graphconv_tail(h: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], e: Tensor, csr: ops.GraphCSR, eps: float):
+    return GraphConvTailFn.apply(h, weight, bias, e, csr, eps)

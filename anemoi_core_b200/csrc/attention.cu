@@ -548,6 +548,8 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
     for (int j = 0; j < NCH; ++j) {
       float o[EPC];
       const float inv = has_edges ? 1.0f / l_i[j] : 0.f;
+      if (p.lse && active && sub == 0)  // scores live in the log2 domain here: back to natural logarithms
+        p.lse[(int64_t)d * p.heads + (slab * SLAB + (j * 32 + lane_eff) * EPC) / p.ch] = has_edges ? (m_i[j] + log2f(l_i[j])) * 0.6931471805599453f : 0.f;
 #pragma unroll
       for (int i = 0; i < EPC; ++i) o[i] = acc[j][i] * inv;
       if constexpr (MODE == 2) {
@@ -636,6 +638,7 @@ __global__ void __launch_bounds__(256) gt_attention_generic_kernel(const AttnPar
       for (int i = 0; i < MAXV; ++i) acc[i] = acc[i] * corr + wgt * vv[i];
     }
     const float inv = e1 > e0 ? 1.0f / l_i : 0.f;
+    if (p.lse && lane == 0) p.lse[d * p.heads + h] = e1 > e0 ? m_i + logf(l_i) : 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int c = lane + 32 * i;
@@ -748,7 +751,7 @@ extern "C" int anemoi_b200_gt_attention_fwd(const void* q, int64_t ldq, const vo
                                             int64_t lde_proj, const float* edge_attr, int64_t lde, int64_t edge_dim, const float* w_edge,
                                             int64_t ldw_e, const float* b_edge, const void* qw, int64_t ldqw, void* abar, int64_t ldabar,
                                             int64_t dp, const int32_t* src32, const int32_t* colptr32, const void* add, int64_t ldadd, void* out,
-                                            int64_t ldo, int64_t n_dst, int64_t heads, int64_t ch, int dtype, void* stream) {
+                                            int64_t ldo, float* lse, int64_t n_dst, int64_t heads, int64_t ch, int dtype, void* stream) {
   ANEMOI_CHECK_ARG(n_dst >= 0 && heads >= 1 && ch >= 1, "gt_attention: bad shape");
   ANEMOI_CHECK_ARG(dtype == ANEMOI_F32 || dtype == ANEMOI_BF16, "gt_attention: bad dtype %d", dtype);
   if (n_dst == 0) return 0;
@@ -770,6 +773,7 @@ extern "C" int anemoi_b200_gt_attention_fwd(const void* q, int64_t ldq, const vo
   p.qw = qw, p.abar = abar, p.ldqw = ldqw, p.ldabar = ldabar, p.dp = (int)dp;
   p.src = src32, p.colptr = colptr32, p.n_dst = n_dst, p.heads = (int)heads, p.ch = (int)ch;
   p.scale = 1.0f / sqrtf((float)ch);
+  p.lse = lse;
   const int es = dtype == ANEMOI_BF16 ? 2 : 4;
   auto al = [&](const void* ptr, int64_t ld) { return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * es) % 16 == 0); };
   bool slab_ok = al(q, ldq) && al(k, ldk) && al(v, ldv) && al(e, lde_proj) && al(add, ldadd) && al(out, ldo);
@@ -787,7 +791,7 @@ extern "C" int anemoi_b200_gt_attention_fwd(const void* q, int64_t ldq, const vo
       const char* ev = getenv("ANEMOI_B200_ATTN_MMA");
       use_mma = (ev && ev[0] == '1') ? 1 : 0;
     }
-    if (use_mma) {
+    if (use_mma && !lse) {
       const int rc_mma = launch_gt_attention_mma(p, s);
       if (rc_mma <= 0) return rc_mma;
     }

@@ -25,6 +25,7 @@ struct AttnParams {
   int64_t n_dst;
   int heads, ch;
   float scale;
+  float* lse;  // [n_dst, heads] natural-log softmax normaliser (nullable); pipe / generic kernels only
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {

@@ -422,6 +422,7 @@ extern "C" int anemoi_b200_gt_attention_tiled_fwd(const void* q, int64_t ldq, co
   p.qw = qw, p.abar = abar, p.ldqw = ldqw, p.ldabar = ldabar, p.dp = (int)dp;
   p.colptr = colptr32, p.n_dst = n_dst, p.heads = (int)heads, p.ch = (int)ch;
   p.scale = 1.0f / sqrtf((float)ch);
+  p.lse = nullptr;
   TilePlan tp{reinterpret_cast<const int4*>(tile_meta), slot_src, emeta};
   cudaStream_t s = (cudaStream_t)stream;
   return ch == 32 ? launch_tile_dph<32>(p, tp, n_tiles, s) : launch_tile_dph<64>(p, tp, n_tiles, s);

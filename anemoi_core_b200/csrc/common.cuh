@@ -241,11 +241,11 @@ struct EpiParams {
   int64_t M, N;
   int flags;
   // folded LayerNorm of the A operand: out = rstd_m * (acc - mean_m * colsum_n) + bias_n, applied before GELU
-  const float* ln_stats;   // [M, 2] = (mean, rstd) per row (ln_parts == 0) or [M, ln_parts, 2] partial (sum, sum of squares), or null
+  const float* ln_stats;   // [M, 2] = (mean, rstd) per row (ln_parts == 0) or [M, ln_parts, 2] partial (block mean, block M2), or null
   const float* ln_colsum;  // [N] = sum_k W'[n, k] of the gamma-scaled weight
   // Row statistics produced by one GEMM's epilogue for the LayerNorm folded into the next: stats_out [M, ceil(N / 64), 2] receives, per
-  // 64-column block, (sum, sum of squares) of the output row AS STORED (after rounding to o_dtype); the consumer passes the buffer as
-  // ln_stats with ln_parts = ceil(K / 64), ln_dim = K (the normalised width) and ln_eps.
+  // 64-column block, (mean, sum of squared deviations from that mean) of the output row AS STORED (after rounding to o_dtype); the
+  // consumer passes the buffer as ln_stats with ln_parts = ceil(K / 64), ln_dim = K (the normalised width) and ln_eps.
   float* stats_out;
   int ln_parts, ln_dim;
   float ln_eps;
@@ -253,18 +253,23 @@ struct EpiParams {
 
 constexpr int kStatsBlock = 64;  // columns per partial of stats_out
 
-// (mean, rstd) of row m for the folded LayerNorm, from either form of ln_stats
+// (mean, rstd) of row m for the folded LayerNorm, from either form of ln_stats.  Partial form: per 64-column block (block mean, M2 = sum of
+// squared deviations from the block mean), merged with Chan's formula - no E[x^2] - mean^2 cancellation, whatever the row's mean.
 __device__ __forceinline__ float2 ln_row_mean_rstd(const EpiParams& ep, int64_t m) {
   if (ep.ln_parts <= 0) return __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + m);
   const float2* p = reinterpret_cast<const float2*>(ep.ln_stats) + m * ep.ln_parts;
-  float s = 0.f, q = 0.f;
-  for (int i = 0; i < ep.ln_parts; ++i) {
-    const float2 t = __ldg(p + i);
-    s += t.x, q += t.y;
-  }
+  const int last_n = ep.ln_dim - (ep.ln_parts - 1) * kStatsBlock;  // columns in the (possibly ragged) last block
+  float s = 0.f;
+  for (int i = 0; i < ep.ln_parts; ++i) s += __ldg(p + i).x * (float)(i == ep.ln_parts - 1 ? last_n : kStatsBlock);
   const float inv = 1.0f / (float)ep.ln_dim;
   const float mean = s * inv;
-  return make_float2(mean, rsqrtf(fmaxf(q * inv - mean * mean, 0.f) + ep.ln_eps));
+  float m2 = 0.f;
+  for (int i = 0; i < ep.ln_parts; ++i) {
+    const float2 t = __ldg(p + i);
+    const float d = t.x - mean;
+    m2 += t.y + (float)(i == ep.ln_parts - 1 ? last_n : kStatsBlock) * d * d;
+  }
+  return make_float2(mean, rsqrtf(m2 * inv + ep.ln_eps));
 }
 
 }  // namespace anemoi

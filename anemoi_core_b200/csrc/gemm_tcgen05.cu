@@ -325,9 +325,11 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
       if (ep.g1) g1row = ep.g1 + (int64_t)__ldg(ep.idx1 + r) * ep.ldg;
       if (ep.g2) g2row = ep.g2 + (int64_t)__ldg(ep.idx2 + r) * ep.ldg;
     }
-    // STATS: (sum, sum of squares) of this thread's output row over the current 64-column block, taken from the bf16-ROUNDED values
-    // (what the consuming GEMM will read: a constant row must cancel exactly against its column sums)
+    // STATS: (mean, M2) of this thread's output row over the current 64-column block, taken from the bf16-ROUNDED values (what the
+    // consuming GEMM will read: a constant row must cancel exactly against its column sums).  Sums are accumulated SHIFTED by the block's
+    // first element, so that mean^2 >> variance rows lose nothing to cancellation.
     float2 st_s = make_float2(0.f, 0.f), st_q = make_float2(0.f, 0.f);
+    float st_x0 = 0.f;
 #pragma unroll 1
     for (int rd = 0; rd < ROUNDS; ++rd, ++rcount) {
       const int col_in_tile = cx.grp * kColsPerWarp + rd * CW;
@@ -478,11 +480,15 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
           }
           const uint32_t pk[4] = {pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])};
           if constexpr (STATS) {
+            if (col + 8 <= (int)ep.N) {  // stats producers have N % 8 == 0: a group of 8 columns is valid or clipped as a whole
+              if (g == 0 && !(rd & 1)) st_x0 = __uint_as_float(pk[0] << 16);
+              const float2 x02 = make_float2(-st_x0, -st_x0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 w2 = make_float2(__uint_as_float(pk[j] << 16), __uint_as_float(pk[j] & 0xffff0000u));
-              st_s = __fadd2_rn(st_s, w2);
-              st_q = __ffma2_rn(w2, w2, st_q);
+              for (int j = 0; j < 4; ++j) {
+                const float2 w2 = __fadd2_rn(make_float2(__uint_as_float(pk[j] << 16), __uint_as_float(pk[j] & 0xffff0000u)), x02);
+                st_s = __fadd2_rn(st_s, w2);
+                st_q = __ffma2_rn(w2, w2, st_q);
+              }
             }
           }
           ptx::sts128(addr, pk[0], pk[1], pk[2], pk[3]);
@@ -494,7 +500,10 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
           const int64_t row = (int64_t)row0 + lane;
           const int blk = (col0 - CW) / kStatsBlock;
           const int parts = (int)((ep.N + kStatsBlock - 1) / kStatsBlock);
-          if (row < ep.M && blk < parts) reinterpret_cast<float2*>(ep.stats_out)[row * parts + blk] = make_float2(st_s.x + st_s.y, st_q.x + st_q.y);
+          if (row < ep.M && blk < parts) {
+            const float nb = (float)min(kStatsBlock, (int)ep.N - blk * kStatsBlock), sh = st_s.x + st_s.y;
+            reinterpret_cast<float2*>(ep.stats_out)[row * parts + blk] = make_float2(st_x0 + sh / nb, fmaxf(st_q.x + st_q.y - sh * sh / nb, 0.f));
+          }
           st_s = make_float2(0.f, 0.f), st_q = make_float2(0.f, 0.f);
         }
       }

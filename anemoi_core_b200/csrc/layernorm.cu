@@ -112,24 +112,29 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const TI* __restrict__ x
 }
 
 // Partial row statistics of a stored matrix, the layout a GEMM epilogue writes into EpiParams::stats_out: per row and 64-column block
-// (sum, sum of squares).  Fallback for GEMM paths without the fused version; one warp per row, two columns per lane and block.
+// (mean, M2).  Fallback for GEMM paths without the fused version; one warp per row, two columns per lane and block.
 __global__ void __launch_bounds__(256) partial_row_stats_kernel(const void* __restrict__ x, int64_t ldx, int dtype, int64_t M, int64_t N, int parts,
                                                                 float2* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < M; m += warps_total) {
     for (int b = 0; b < parts; ++b) {
-      float s = 0.f, q = 0.f;
+      float v[2], s = 0.f, q = 0.f;
+      const float nb = (float)min((int64_t)kStatsBlock, N - (int64_t)b * kStatsBlock);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int64_t c = (int64_t)b * kStatsBlock + lane * 2 + j;
-        if (c < N) {
-          const float v = load_as_f32(x, m * ldx + c, dtype);
-          s += v, q += v * v;
-        }
+        v[j] = c < N ? load_as_f32(x, m * ldx + c, dtype) : 0.f;
+        s += v[j];
       }
-      s = warp_sum(s), q = warp_sum(q);
-      if (lane == 0) stats[m * parts + b] = make_float2(s, q);
+      const float mean = warp_sum(s) / nb;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int64_t c = (int64_t)b * kStatsBlock + lane * 2 + j;
+        if (c < N) q += (v[j] - mean) * (v[j] - mean);
+      }
+      q = warp_sum(q);
+      if (lane == 0) stats[m * parts + b] = make_float2(mean, q);  // (block mean, block M2): two-pass, like the GEMM epilogue's shifted sums
     }
   }
 }

@@ -32,14 +32,6 @@ def compute_dtype(*tensors: Tensor) -> torch.dtype:
     return dt
 
 
-def forward_only_guard(module: nn.Module) -> None:
-    if module.training and torch.is_grad_enabled():
-        raise NotImplementedError(
-            "anemoi_core_b200 implements the forward pass only (SURVEY.md §8f rank 3: backward is a later row); "
-            "call .eval() and/or run under torch.no_grad()"
-        )
-
-
 def round8(k: int) -> int:
     return (k + 7) // 8 * 8
 

@@ -22,6 +22,7 @@ from ..distributed.halo import halo_plan_for
 from ..distributed.shapes import BipartiteGraphShardInfo
 from ..distributed.shapes import GraphShardInfo
 from . import _functional as Fn
+from . import _train as T
 from .conv import GraphConv
 from .mlp import MLP
 from .utils import compute_mlp_hidden_dim
@@ -97,8 +98,11 @@ class GraphConvProcessorBlock(GraphConvBaseBlock):
         size=None,
         **layer_kwargs,
     ) -> tuple[Tensor, Tensor]:
-        Fn.forward_only_guard(self)
         dt = Fn.compute_dtype(x, edge_attr)
+        if T.wants_grad(self, x, edge_attr):  # differentiable path (layers/_train.py)
+            T._single_gpu(model_comm_group)
+            (_, x_new), edges_new = T.gnn_block(self, x, x, edge_attr, edge_index, dt, bipartite=False)
+            return x_new, edges_new
         if self.emb_edges is not None:
             edge_attr = self.emb_edges.run(edge_attr, dt)
         halo_plan = layer_kwargs.get("halo_plan")
@@ -144,9 +148,11 @@ class GraphConvMapperBlock(GraphConvBaseBlock):
         size=None,
         **layer_kwargs,
     ) -> tuple[PairTensor, Tensor]:
-        Fn.forward_only_guard(self)
         x_src, x_dst = x
         dt = Fn.compute_dtype(x_src, x_dst, edge_attr)
+        if T.wants_grad(self, x_src, x_dst, edge_attr):  # differentiable path (layers/_train.py)
+            T._single_gpu(model_comm_group)
+            return T.gnn_block(self, x_src, x_dst, edge_attr, edge_index, dt, bipartite=True)
         C = self.in_channels
         # sharded (block.py:451-470): x_dst and the edges are this rank's (local dst ids, global src ids); every source row is needed
         src_all = x_src
@@ -217,6 +223,11 @@ class GraphTransformerBaseBlock(nn.Module):
         self.node_dst_mlp = MLP(out_channels, hidden_dim, out_channels, layer_kernels=k, n_extra_layers=0, layer_norm=False,
                                 mlp_implementation=mlp_implementation)  # fmt: skip
         self.edge_pre_mlp = nn.Sequential(k.Linear(edge_dim, edge_dim), k.Activation()) if edge_pre_mlp else nn.Identity()
+        if edge_pre_mlp:
+            from .mlp import _is_gelu
+
+            if not _is_gelu(self.edge_pre_mlp[1]):  # prepare_edges fuses the activation into the GEMM epilogue as exact-erf GELU
+                raise NotImplementedError(f"edge_pre_mlp Activation {type(self.edge_pre_mlp[1]).__name__}: only exact (erf) torch.nn.GELU is fused")
         if graph_attention_backend not in ("triton", "pyg", "b200"):
             raise ValueError(f"Backend '{graph_attention_backend}' not supported for {self.__class__.__name__}")
         # accepted for config compatibility; there is exactly one implementation here (the sm_100a kernel)
@@ -365,6 +376,9 @@ class GraphTransformerBaseBlock(nn.Module):
             raise NotImplementedError("heads strategy: implemented for shapes the folded lin_edge attention kernel handles")
         Hl = H // P
         d, dp, hdp = self._fold_dims()
+        if (Hl * (Ch + dp) * torch.empty(0, dtype=dt).element_size()) % 16:
+            raise NotImplementedError(f"heads strategy: the exchanged rows [q | qw] of {Hl} heads x ({Ch} + {dp}) {dt} are not multiples of 16 bytes; "
+                                      "choose num_heads / model-parallel size so that (H / P) * (Ch + dp) * elemsize % 16 == 0")  # fmt: skip
         if self.qk_norm:
             for t, norm in ((q, self.q_norm), (k, self.k_norm)):
                 ops.layer_norm(t, self._pack.f32(norm.weight), self._pack.f32(getattr(norm, "bias", None)), norm.eps, out=t, groups=H)
@@ -426,8 +440,16 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
         edge_attr_prepared: Optional[Tensor] = None,
         **kwargs,
     ) -> tuple[Tensor, Tensor]:
-        Fn.forward_only_guard(self)
         dt = Fn.compute_dtype(x)
+        edge_attr_in = edge_attr
+        if not edges_are_dst_sorted:  # the reference sorts here (edge_index_to_csc(..., edges_are_dst_sorted=False), block.py:779-782)
+            from ..distributed.khop_edges import ensure_edges_are_dst_sorted
+
+            edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, False)
+            edge_attr_prepared = None
+        if T.wants_grad(self, x, edge_attr):  # differentiable path (layers/_train.py)
+            T._single_gpu(model_comm_group)
+            return T.gt_block(self, None, x, edge_attr, edge_index, dt, None, cond), edge_attr_in
         A = self.attn_channels
         ln = self.layer_norm_attention  # with a ConditionalLayerNorm kernel both LayerNorms of the block take ``cond`` (block.py:1233-1271)
         dst_layers = [self.lin_key, self.lin_value, self.lin_self]
@@ -509,11 +531,21 @@ class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
         edges_are_dst_sorted: bool = True,
         **layer_kwargs,
     ) -> tuple[PairTensor, Tensor]:
-        Fn.forward_only_guard(self)
         x_src, x_dst = x
         cond_src, cond_dst = cond if cond is not None else (None, None)  # (block.py:978-980)
         dt = Fn.compute_dtype(x_src, x_dst)
+        if T.wants_grad(self, x_src, x_dst, edge_attr):  # differentiable path (layers/_train.py)
+            T._single_gpu(model_comm_group)
+            dst_new = T.gt_block(self, x_src, x_dst, edge_attr, edge_index, dt, self.layer_norm_attention_src, cond)
+            src_new = x_src
+            if self.update_src_nodes:
+                src_new = T.mlp(self.node_src_mlp, x_src.to(dt), dt, residual=x_src, pre_ln=self.layer_norm_mlp_src)
+            return (src_new, dst_new), edge_attr
         A = self.attn_channels
+        if not edges_are_dst_sorted:  # the reference sorts here (block.py:779-782)
+            from ..distributed.khop_edges import ensure_edges_are_dst_sorted
+
+            edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, False)
         kv_layers = [self.lin_key, self.lin_value]
         world = group_size(model_comm_group)
         halo = world > 1 and self.shard_strategy != "heads" and shard_info is not None and shard_info.src_is_sharded()

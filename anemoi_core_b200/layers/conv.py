@@ -82,12 +82,15 @@ class GraphConv(nn.Module):
         return out, e_new
 
     def forward(self, x: Union[Tensor, PairTensor], edge_attr: Tensor, edge_index: Tensor, size=None):
-        Fn.forward_only_guard(self)
         x_src, x_dst = x if isinstance(x, (tuple, list)) else (x, x)
         dt = Fn.compute_dtype(x_src, x_dst, edge_attr)
         csr, perm = _sorted_plan(edge_index, x_src.shape[0], x_dst.shape[0])
         if perm is not None:
             raise ValueError("GraphConv returns per-edge features in edge order: pass a dst-sorted edge_index (sort_edge_index_by_dst)")
+        from . import _train as T
+
+        if T.wants_grad(self, x_src, x_dst, edge_attr):  # differentiable path (layers/_train.py)
+            return T.graph_conv(self, x_src, x_dst, edge_attr, csr, dt)
         return self.run(x_src, x_dst, edge_attr, csr, dt)
 
 
@@ -100,7 +103,7 @@ class GraphTransformerConv(nn.Module):
     def __init__(self, out_channels: int, dropout: float = 0.0, **kwargs):
         super().__init__()
         if dropout:
-            raise NotImplementedError("attention dropout is training-only and not implemented (forward/inference path)")
+            raise NotImplementedError("attention dropout is not implemented")
         self.out_channels = out_channels
         self.dropout = dropout
 
@@ -113,6 +116,14 @@ class GraphTransformerConv(nn.Module):
         if edge_attr is not None:
             e = edge_attr.reshape(edge_attr.shape[0], heads * ch)
             e = ops.cast_pad(e, dt, idx=perm) if (perm is not None or e.dtype != dt) else e
-        out = ops.gt_attention(query.reshape(n_dst, heads * ch), key.reshape(n_src, heads * ch), value.reshape(n_src, heads * ch), csr, heads,
-                               e_proj=e)  # fmt: skip
+        q2, k2, v2 = query.reshape(n_dst, heads * ch), key.reshape(n_src, heads * ch), value.reshape(n_src, heads * ch)
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (query, key, value, edge_attr)):
+            from .. import autograd as AG
+
+            if perm is not None:  # differentiable gather into the sorted order (the kernel's cast_pad above carries no gradient)
+                e = edge_attr.reshape(edge_attr.shape[0], heads * ch).index_select(0, perm.long()).to(dt)
+            elif e is not None and e.dtype != edge_attr.dtype:
+                e = edge_attr.reshape(edge_attr.shape[0], heads * ch).to(dt)
+            return AG.gt_attention(q2, k2, v2, e, csr, heads).reshape(n_dst, heads, ch)
+        out = ops.gt_attention(q2, k2, v2, csr, heads, e_proj=e)
         return out.reshape(n_dst, heads, ch)

@@ -24,6 +24,7 @@ from ..distributed.graph import group_size
 from ..distributed.khop_edges import ensure_edges_are_dst_sorted
 from ..distributed.shapes import BipartiteGraphShardInfo
 from . import _functional as Fn
+from . import _train as T
 from .block import GraphConvMapperBlock
 from .block import GraphTransformerMapperBlock
 from .mlp import MLP
@@ -117,9 +118,14 @@ class GraphTransformerBaseMapper(BaseMapper):
         ``x[1]`` is then this rank's slice of the destination rows (``shard_info.dst_nodes``), ``x[0]`` either the full source
         tensor (``shard_info.src_nodes is None``) or this rank's slice (its k | v rows are all-gathered inside the block);
         the full dst-sorted edge list is cut to the edges into the local rows (cached per graph and group)."""
-        Fn.forward_only_guard(self)
         edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
         world = group_size(model_comm_group)
+        if T.wants_grad(self, x[0], x[1], edge_attr):  # differentiable path (layers/_train.py): single GPU, same call sequence
+            T._single_gpu(model_comm_group)
+            dt = Fn.compute_dtype(*x)
+            x_src, x_dst = self.pre_process_train(x, dt)
+            (_, x_dst_out), _ = self.proc((x_src, x_dst), edge_attr, edge_index, shard_info, batch_size, (x_src.shape[0], x_dst.shape[0]), None, cond=cond)
+            return self.post_process_train(x_dst_out, dt)
         if world > 1:
             if shard_info is None or not shard_info.dst_is_sharded():
                 raise ValueError("sharded mapper: shard_info.dst_nodes (per-rank destination row counts) is required")
@@ -163,6 +169,12 @@ class GraphTransformerForwardMapper(GraphTransformerBaseMapper):
         x_src, x_dst = x
         return Fn.fused_linear(self._pack, x_src, [self.emb_nodes_src], dt), Fn.fused_linear(self._pack, x_dst, [self.emb_nodes_dst], dt)
 
+    def pre_process_train(self, x: PairTensor, dt: torch.dtype) -> PairTensor:
+        return T.lin(self.emb_nodes_src, x[0], dt), T.lin(self.emb_nodes_dst, x[1], dt)
+
+    def post_process_train(self, x_dst: Tensor, dt: torch.dtype) -> Tensor:
+        return x_dst
+
     def forward(
         self,
         x: PairTensor,
@@ -199,6 +211,12 @@ class GraphTransformerBackwardMapper(GraphTransformerBaseMapper):
     def post_process(self, x_dst: Tensor, dt: torch.dtype) -> Tensor:
         lin = self.node_data_extractor[1]
         return Fn.ln_linear(self._pack, x_dst, self.node_data_extractor[0], ("extractor",), Fn.linear_sources([lin]), lambda: Fn.cat_linear32([lin]), dt)
+
+    def pre_process_train(self, x: PairTensor, dt: torch.dtype) -> PairTensor:
+        return x[0], T.lin(self.emb_nodes_dst, x[1], dt)
+
+    def post_process_train(self, x_dst: Tensor, dt: torch.dtype) -> Tensor:
+        return T.lin(self.node_data_extractor[1], T.norm(self.node_data_extractor[0], x_dst, dt), dt)
 
     def forward(
         self,
@@ -250,16 +268,28 @@ class GNNBaseMapper(BaseMapper):
     def post_process(self, x_dst: Tensor, dt: torch.dtype) -> Tensor:
         return x_dst
 
+    def pre_process_train(self, x: PairTensor, dt: torch.dtype) -> PairTensor:
+        return x
+
+    def post_process_train(self, x_dst: Tensor, dt: torch.dtype) -> Tensor:
+        return x_dst
+
     def _run(self, x: PairTensor, batch_size, shard_info, edge_attr, edge_index, model_comm_group, edges_are_dst_sorted,
              keep_x_dst_sharded: bool = False) -> PairTensor:  # fmt: skip
         """Single GPU, or sharded over ``model_comm_group`` like the reference (mapper.py:760-835): src and dst rows are sharded (a replicated
         input is cut to this rank's balanced slice, ``ensure_sharded``), the edges are the ones into the local dst rows, the block all-gathers
         the embedded src rows (``sync_tensor``, block.py:451); returns the LOCAL src shard and the dst rows (gathered unless
         ``keep_x_dst_sharded``)."""
-        Fn.forward_only_guard(self)
         edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
         world = group_size(model_comm_group)
         x_src, x_dst = x
+        if T.wants_grad(self, x_src, x_dst, edge_attr):  # differentiable path (layers/_train.py): single GPU, same call sequence
+            T._single_gpu(model_comm_group)
+            dt = Fn.compute_dtype(x_src, x_dst, edge_attr)
+            e = T.mlp(self.emb_edges, edge_attr, dt)
+            x_src, x_dst = self.pre_process_train((x_src, x_dst), dt)
+            (x_src, x_dst), _ = self.proc((x_src, x_dst), e, edge_index, shard_info, None)
+            return x_src, self.post_process_train(x_dst, dt)
         if world > 1:
             from ..distributed.balanced_partition import get_balanced_partition_sizes
             from ..distributed.graph import shard_rows
@@ -305,6 +335,9 @@ class GNNForwardMapper(GNNBaseMapper):
     def pre_process(self, x: PairTensor, dt: torch.dtype) -> PairTensor:
         return self.emb_nodes_src.run(x[0], dt), self.emb_nodes_dst.run(x[1], dt)
 
+    def pre_process_train(self, x: PairTensor, dt: torch.dtype) -> PairTensor:
+        return T.mlp(self.emb_nodes_src, x[0], dt), T.mlp(self.emb_nodes_dst, x[1], dt)
+
     def forward(
         self,
         x: PairTensor,
@@ -330,6 +363,9 @@ class GNNBackwardMapper(GNNBaseMapper):
 
     def post_process(self, x_dst: Tensor, dt: torch.dtype) -> Tensor:
         return self.node_data_extractor.run(x_dst, dt)
+
+    def post_process_train(self, x_dst: Tensor, dt: torch.dtype) -> Tensor:
+        return T.mlp(self.node_data_extractor, x_dst, dt)
 
     def forward(
         self,

@@ -138,7 +138,11 @@ class MLP(nn.Module):
     def forward(self, x: Tensor, **layer_kwargs) -> Tensor:
         if layer_kwargs:
             raise NotImplementedError("conditional LayerNorm kwargs are not implemented")
-        Fn.forward_only_guard(self)
         shape = x.shape
+        from . import _train as T
+
+        if T.wants_grad(self, x):  # differentiable path (layers/_train.py)
+            y = T.mlp(self, x.reshape(-1, shape[-1]), Fn.compute_dtype(x))
+            return y.reshape(*shape[:-1], y.shape[-1])
         y = self.run(x.reshape(-1, shape[-1]), Fn.compute_dtype(x))
         return y.reshape(*shape[:-1], y.shape[-1])

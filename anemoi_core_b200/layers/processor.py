@@ -23,6 +23,7 @@ from ..distributed.khop_edges import ensure_edges_are_dst_sorted
 from ..distributed.shapes import GraphShardInfo
 from . import _functional as Fn
 from . import _reorder as RO
+from . import _train as T
 from .block import GraphConvProcessorBlock
 from .block import GraphTransformerProcessorBlock
 from .utils import compute_mlp_hidden_dim
@@ -146,10 +147,15 @@ class GNNProcessor(BaseProcessor):
         *args,
         **kwargs,
     ) -> Tensor:
-        Fn.forward_only_guard(self)
         n_nodes = sum(shard_info.nodes) if shard_info is not None and shard_info.nodes_are_sharded() else x.shape[0]
         if shard_info is None:
             shard_info = GraphShardInfo()
+        if T.wants_grad(self, x, edge_attr):  # differentiable path: plain layer loop, single GPU (layers/_train.py)
+            T._single_gpu(model_comm_group)
+            edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
+            for block in self.proc:
+                x, edge_attr = block(x, edge_attr, edge_index, shard_info, None)
+            return x
         if not shard_info.edges_are_sharded():
             edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
             if group_size(model_comm_group) > 1:
@@ -233,10 +239,15 @@ class GraphTransformerProcessor(BaseProcessor):
         *args,
         **kwargs,
     ) -> Tensor:
-        Fn.forward_only_guard(self)
         if shard_info is None:
             shard_info = GraphShardInfo()
         n_nodes = sum(shard_info.nodes) if shard_info.nodes_are_sharded() else x.shape[0]
+        if T.wants_grad(self, x, edge_attr):  # differentiable path: plain layer loop, single GPU (layers/_train.py)
+            T._single_gpu(model_comm_group)
+            edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
+            for block in self.proc:
+                x, _ = block(x, edge_attr, edge_index, shard_info, batch_size, n_nodes, None, cond=kwargs.get("cond"))
+            return x
         if not shard_info.edges_are_sharded():
             edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
             if group_size(model_comm_group) > 1 and self.shard_strategy == "edges":

@@ -295,8 +295,12 @@ class AnemoiModelEncProcDec(nn.Module):
             skip = torch.full((v_out,), -1, dtype=torch.int32)
             skip[torch.tensor(self._internal_output_idx[ds], dtype=torch.long)] = torch.tensor(self._internal_input_idx[ds], dtype=torch.int32)
             bound = torch.zeros(v_out, dtype=torch.int32)
-            for name, idx in self._bound_spec[ds]:  # applied in order; relu and leaky_relu are idempotent, the last one listed for a variable wins
-                bound[torch.tensor(list(idx), dtype=torch.long)] = _BOUND_CODES[name]
+            # the reference applies its bounding layers one after the other (models/base.py, layers/bounding.py:81-94): compose them per
+            # variable - relu after or before leaky_relu is relu (leaky_relu(relu(x)) = relu(leaky_relu(x)) = relu(x)), the rest is idempotent
+            for name, idx in self._bound_spec[ds]:
+                code = _BOUND_CODES[name]
+                for i in idx:
+                    bound[i] = _BOUND_CODES["relu"] if _BOUND_CODES["relu"] in (int(bound[i]), code) else code
             self._tables[key] = (skip.to(device), bound.to(device))
         return self._tables[key]
 
@@ -333,21 +337,25 @@ class AnemoiModelEncProcDec(nn.Module):
         latents, x_data_latents, sizes_data = [], {}, {}
         for ds in names:
             x_data, sizes_data[ds] = self._assemble_input(x[ds], batch_size, grid_shard_sizes, model_comm_group, ds, dt)
-            ea, ei, es = self.encoder_graph_provider[ds].get_edges(batch_size=batch_size, model_comm_group=model_comm_group)
+            ea, ei, es = self.encoder_graph_provider[ds].get_edges(batch_size=batch_size, model_comm_group=model_comm_group,
+                                                                   shard_edges=getattr(self.encoder[ds], "shard_strategy", "edges") != "heads")  # fmt: skip
             info = BipartiteGraphShardInfo(src_nodes=sizes_data[ds], dst_nodes=sizes_hidden, edges=es)
             x_data_latents[ds], lat = self.encoder[ds]((x_data, x_hidden), batch_size, info, ea, ei, model_comm_group, keep_x_dst_sharded=True)
             latents.append(lat)
         x_latent = latents[0]
         for lat in latents[1:]:
             x_latent = ops.add(x_latent, lat)
-        ea, ei, es = self.processor_graph_provider.get_edges(batch_size=batch_size, model_comm_group=model_comm_group)
+        # the heads (Ulysses) strategy attends over the FULL edge list for its heads: ask the provider not to cut it
+        ea, ei, es = self.processor_graph_provider.get_edges(batch_size=batch_size, model_comm_group=model_comm_group,
+                                                             shard_edges=getattr(self.processor, "shard_strategy", "edges") != "heads")  # fmt: skip
         x_proc = self.processor(x_latent, batch_size, GraphShardInfo(nodes=sizes_hidden if world > 1 else [x_latent.shape[0]], edges=es), ea, ei,
                                 model_comm_group)  # fmt: skip
         if self.latent_skip:
             x_proc = ops.add(x_proc, x_latent)
         out = {}
         for ds in names:
-            ea, ei, es = self.decoder_graph_provider[ds].get_edges(batch_size=batch_size, model_comm_group=model_comm_group)
+            ea, ei, es = self.decoder_graph_provider[ds].get_edges(batch_size=batch_size, model_comm_group=model_comm_group,
+                                                                   shard_edges=getattr(self.decoder[ds], "shard_strategy", "edges") != "heads")  # fmt: skip
             info = BipartiteGraphShardInfo(src_nodes=sizes_hidden, dst_nodes=sizes_data[ds], edges=es)
             if world > 1 and sizes_data[ds] is None:
                 # replicated grid: every rank owns a balanced slice of the grid rows inside the decoder and the output is gathered

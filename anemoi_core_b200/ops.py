@@ -141,6 +141,7 @@ class GraphCSR:
     src32: Tensor  # int32 [E]
     dst32: Tensor  # int32 [E]
     tiles: object = None  # AttnTilePlan, False (no plan exists) or None (not built yet); see attention_tiles()
+    rev: object = None  # (rev_ptr32 [n_src + 1], rev_eid32 [E]): edges stably sorted by source, for the backward's src-major pass
 
 
 @dataclass
@@ -399,6 +400,7 @@ def gt_attention(
     add: Optional[Tensor] = None,
     out: Optional[Tensor] = None,
     tiles: Optional[AttnTilePlan] = None,
+    lse: Optional[Tensor] = None,
 ) -> Tensor:
     """Edge-softmax attention over the cached CSR.  q [n_dst, H*Ch]; k, v [n_src, H*Ch] (column slices allowed).
     ``tiles`` (folded bf16 form only): run the destination-tile tensor-core kernel on this plan of the same CSR.
@@ -456,6 +458,10 @@ def gt_attention(
         # an empty edge tensor has a null data pointer, so the library sees "no edge term" and leaves abar untouched; with no edges
         # abar = sum_e alpha_e a_e is exactly zero (tests/test_gpu_parity.py::test_edge_cases_empty_and_isolated)
         abar.zero_()
+    if lse is not None:
+        _need_cuda(lse)
+        if qw is not None or tiles is not None or lse.dtype != torch.float32 or not lse.is_contiguous() or tuple(lse.shape) != (n_dst, heads):
+            raise ValueError("gt_attention: lse must be contiguous float32 [n_dst, heads] and goes with the materialised / in-kernel projection forms")
     if tiles is not None:
         if qw is None or e_proj is not None or q.dtype != torch.bfloat16:
             raise ValueError("gt_attention: the tiled kernel implements the folded bf16 form (qw / abar)")
@@ -471,8 +477,8 @@ def gt_attention(
     with _Timed("gt_attention", aflops, abytes):
         rc = _lib.load().anemoi_b200_gt_attention_fwd(
             _ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(e_proj), lde_proj, _ptr(edge_attr), lde, d_e, _ptr(w_edge), ldw_e, _ptr(_f32(b_edge)),
-            _ptr(qw), ldqw, _ptr(abar), ldabar, dp, _ptr(csr.src32) or _ptr(csr.colptr32), _ptr(csr.colptr32), _ptr(add), ldadd, _ptr(out), ldo, n_dst, heads,
-            C // heads, dtype_code(q.dtype), _stream())  # fmt: skip
+            _ptr(qw), ldqw, _ptr(abar), ldabar, dp, _ptr(csr.src32) or _ptr(csr.colptr32), _ptr(csr.colptr32), _ptr(add), ldadd, _ptr(out), ldo, _ptr(lse),
+            n_dst, heads, C // heads, dtype_code(q.dtype), _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_gt_attention_fwd")
     return out
 
@@ -668,3 +674,90 @@ def halo_wait(ch, like: Tensor) -> None:
     with _Timed("halo_wait"):
         rc = _lib.load().anemoi_b200_halo_wait(ch.ctl_ptrs, ch.world, ch.rank, _stream())
     _lib.check(rc, "anemoi_b200_halo_wait")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# backward of the fused ops (csrc/backward.cu)
+# ------------------------------------------------------------------------------------------------------------
+def reverse_csr(csr: GraphCSR) -> tuple[Tensor, Tensor]:
+    """(rev_ptr32 [n_src + 1], rev_eid32 [E]): the edge ids stably sorted by source - the reverse structure of the reference's
+    ``edge_index_to_csc(..., reverse=True)`` (triton/utils.py:61-68: ``argsort(row, stable=True)``), built once per graph with the same
+    torch integer ops and cached on the CSR."""
+    if csr.rev is None:
+        src = csr.src32.long()
+        eid = torch.sort(src, stable=True).indices.to(torch.int32).contiguous()
+        ptr = torch.zeros(csr.n_src + 1, dtype=torch.int64, device=src.device)
+        ptr[1:] = torch.cumsum(torch.bincount(src, minlength=csr.n_src), 0)
+        csr.rev = (ptr.to(torch.int32).contiguous(), eid)
+    return csr.rev
+
+
+def gt_attention_bwd(q: Tensor, k: Tensor, v: Tensor, e_proj: Optional[Tensor], out: Tensor, dout: Tensor, lse: Tensor, csr: GraphCSR, heads: int):
+    """(dq, dk, dv, de) of ``gt_attention(q, k, v, csr, heads, e_proj=e_proj)`` for the cotangent ``dout``; ``out`` / ``lse`` from the forward."""
+    _need_cuda(q, k, v, e_proj, out, dout, lse)
+    n_dst, C, ldq = _rows(q)
+    n_src, _, ldk = _rows(k)
+    _, _, ldv = _rows(v)
+    _, _, ldo = _rows(out)
+    _, _, lddo = _rows(dout)
+    if not (q.dtype == k.dtype == v.dtype == out.dtype == dout.dtype) or lse.dtype != torch.float32 or not lse.is_contiguous():
+        raise TypeError("gt_attention_bwd: q / k / v / out / dout share a dtype, lse is contiguous float32")
+    rev_ptr, rev_eid = reverse_csr(csr)
+    dq, dk, dv = torch.empty((n_dst, C), dtype=q.dtype, device=q.device), torch.empty((n_src, C), dtype=q.dtype, device=q.device), torch.empty((n_src, C), dtype=q.dtype, device=q.device)
+    de, lde, ldde = None, 0, 0
+    if e_proj is not None:
+        _, _, lde = _rows(e_proj)
+        de = torch.empty((csr.n_edges, C), dtype=q.dtype, device=q.device)
+        ldde = C
+    alpha = torch.empty((csr.n_edges, heads), dtype=torch.float32, device=q.device)
+    ds = torch.empty_like(alpha)
+    es = q.element_size()
+    with _Timed("gt_attention_bwd", csr.n_edges * 10.0 * C, es * C * (4.0 * n_dst + 4.0 * n_src + 4.0 * csr.n_edges)):
+        rc = _lib.load().anemoi_b200_gt_attention_bwd(
+            _ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(e_proj), lde, _ptr(out), ldo, _ptr(dout), lddo, _ptr(lse), _ptr(csr.src32) or _ptr(csr.colptr32),
+            _ptr(csr.colptr32), _ptr(csr.dst32) or _ptr(csr.colptr32), _ptr(rev_ptr), _ptr(rev_eid) or _ptr(rev_ptr), _ptr(dq), C, _ptr(dk), C, _ptr(dv), C,
+            _ptr(de), ldde, _ptr(alpha) or _ptr(lse), _ptr(ds) or _ptr(lse), n_src, n_dst, heads, C // heads, dtype_code(q.dtype), _stream())  # fmt: skip
+    _lib.check(rc, "anemoi_b200_gt_attention_bwd")
+    return dq, dk, dv, de
+
+
+_LN_BWD_BLOCKS = 592  # partial-sum rows of dgamma / dbeta: 4 CTAs per SM
+
+
+def layer_norm_bwd(x: Tensor, gamma: Optional[Tensor], dy: Optional[Tensor], eps: float, groups: int = 1, dz: Optional[Tensor] = None,
+                   idx: Optional[Tensor] = None, want_dres: bool = False):  # fmt: skip
+    """Backward of ``y = LayerNorm(x) * gamma + beta`` over ``groups`` groups of C channels per row for the cotangent
+    ``g[r] = dy[r] + dz[idx[r]]``: returns (dx, dgamma [C], dbeta [C], g if ``want_dres``)."""
+    _need_cuda(x, gamma, dy, dz, idx)
+    M, W, ldx = _rows(x)
+    C = W // groups
+    dx = torch.empty((M, W), dtype=x.dtype, device=x.device)
+    dres = torch.empty((M, W), dtype=x.dtype, device=x.device) if want_dres else None
+    partial = torch.empty((_LN_BWD_BLOCKS, 2, C), dtype=torch.float32, device=x.device)
+    lddy = lddz = 0
+    if dy is not None:
+        _, _, lddy = _rows(dy)
+    if dz is not None:
+        _, _, lddz = _rows(dz)
+        if idx is not None and (idx.dtype != torch.int32 or idx.numel() != M * groups):
+            raise TypeError("layer_norm_bwd: idx must be int32 with one entry per normalised row")
+    with _Timed("layer_norm_bwd", 16.0 * M * W, _nbytes(x, dy, dx, dres)):
+        rc = _lib.load().anemoi_b200_layer_norm_bwd(_ptr(x), ldx, _ptr(_f32(gamma)), _ptr(dy), lddy, _ptr(dz), lddz, _ptr(idx), _ptr(dx), W, _ptr(dres), W,
+                                                    _ptr(partial), _LN_BWD_BLOCKS, M, groups, C, float(eps), dtype_code(x.dtype), _stream())  # fmt: skip
+    _lib.check(rc, "anemoi_b200_layer_norm_bwd")
+    sums = partial.sum(0)
+    return dx, sums[0], sums[1], dres
+
+
+def gelu(x: Tensor, dy: Optional[Tensor] = None) -> Tensor:
+    """``gelu(x)`` (exact erf), or with ``dy`` the backward ``dy * gelu'(x)``."""
+    _need_cuda(x, dy)
+    M, N, ldx = _rows(x)
+    y = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    lddy = 0
+    if dy is not None:
+        _, _, lddy = _rows(dy)
+    with _Timed("gelu", 10.0 * M * N, _nbytes(x, dy, y)):
+        rc = _lib.load().anemoi_b200_gelu(_ptr(x), ldx, _ptr(dy), lddy, _ptr(y), N, M, N, 0 if dy is None else 1, dtype_code(x.dtype), _stream())
+    _lib.check(rc, "anemoi_b200_gelu")
+    return y

@@ -116,12 +116,14 @@ ANEMOI_API int anemoi_b200_row_stats(const void* x, int64_t ldx, int x_dtype, fl
  *       The [E, H*Ch] edge tensor (the largest tensor of the layer in the reference) never exists.  Needs edge_dim <= 16
  *       and edge_attr rows zero-padded to lde >= 16.
  *   q [n_dst, ldq], k,v [n_src, ldk/ldv], add/out [n_dst, ld*], qw/abar [n_dst, >= heads*dp] of `dtype`; src32/colptr32 from csr_build.
+ *   lse (nullable): fp32 [n_dst, heads] receives log sum_e exp(score_e) (0 for rows without edges, like the `m` output of
+ *   triton/gt.py:112-119, 170-178); forms (1) / (2) only - it is what anemoi_b200_gt_attention_bwd consumes.
  */
 ANEMOI_API int anemoi_b200_gt_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* e,
                                  int64_t lde_proj, const float* edge_attr, int64_t lde, int64_t edge_dim, const float* w_edge,
                                  int64_t ldw_e, const float* b_edge, const void* qw, int64_t ldqw, void* abar, int64_t ldabar, int64_t dp,
                                  const int32_t* src32, const int32_t* colptr32, const void* add, int64_t ldadd, void* out, int64_t ldo,
-                                 int64_t n_dst, int64_t heads, int64_t ch, int dtype, void* stream);
+                                 float* lse, int64_t n_dst, int64_t heads, int64_t ch, int dtype, void* stream);
 
 /* -- GraphTransformer attention on destination tiles (folded form (3), bf16, Ch in {32, 64}) ------------------------
  * Same result as anemoi_b200_gt_attention_fwd form (3) (replaces layers/conv.py:103-147, triton/gt.py:81-179 and the lin_edge GEMM of
@@ -154,6 +156,30 @@ ANEMOI_API int anemoi_b200_gt_attention_tiled_fwd(const void* q, int64_t ldq, co
 ANEMOI_API int anemoi_b200_graphconv_ln_aggregate(const void* h, int64_t ldh, const float* gamma, const float* beta, const void* e, int64_t lde,
                                        void* e_new, int64_t ldn, const int32_t* colptr32, void* out, int64_t ldo, int64_t n_dst,
                                        int64_t C, float eps, int dtype, void* stream);
+
+/* -- backward of the fused ops (training) -------------------------------------------------------------------------
+ * gt_attention_bwd replaces triton/gt.py:182-376 / :451-556 for the materialised-e form (1) of anemoi_b200_gt_attention_fwd: given the
+ * forward's out [n_dst, ldo] (the attention result, without `add`) and lse [n_dst, heads] (natural-log softmax normaliser, written by the
+ * forward when its `lse` argument is non-null) and the cotangent dout, it returns dq, dk, dv and (when e is given) de; two deterministic
+ * passes (dst-major over src32 / colptr32, src-major over the reverse CSR rev_ptr32 [n_src + 1] / rev_eid32 [E] = edge ids stably sorted by
+ * source, with dst32 [E]); alpha_scratch / ds_scratch: fp32 [E, heads] workspaces.  Channels per head <= 256.
+ * layer_norm_bwd: dx (and dres = the cotangent itself, nullable) of y = LayerNorm(x) * gamma + beta over `groups` groups of C <= 1024
+ * channels per row, for the cotangent g[r] = dy[r] (nullable) + dz[idx[r]] (nullable; idx nullable = identity); per-block partial sums of
+ * dgamma / dbeta go to partial [n_partial, 2, C] fp32 (the caller sums over blocks).  With dz = d out and idx = dst32 this is the backward
+ * of anemoi_b200_graphconv_ln_aggregate (layers/conv.py:73-81).
+ * gelu: mode 0  y = gelu(x);  mode 1  y = dy * gelu'(x)  (exact erf GELU).
+ */
+ANEMOI_API int anemoi_b200_gt_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* e,
+                                 int64_t lde, const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
+                                 const int32_t* src32, const int32_t* colptr32, const int32_t* dst32, const int32_t* rev_ptr32,
+                                 const int32_t* rev_eid32, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, void* de,
+                                 int64_t ldde, float* alpha_scratch, float* ds_scratch, int64_t n_src, int64_t n_dst, int64_t heads, int64_t ch,
+                                 int dtype, void* stream);
+ANEMOI_API int anemoi_b200_layer_norm_bwd(const void* x, int64_t ldx, const float* gamma, const void* dy, int64_t lddy, const void* dz, int64_t lddz,
+                               const int32_t* idx, void* dx, int64_t lddx, void* dres, int64_t lddr, float* partial, int64_t n_partial, int64_t M,
+                               int64_t groups, int64_t C, float eps, int dtype, void* stream);
+ANEMOI_API int anemoi_b200_gelu(const void* x, int64_t ldx, const void* dy, int64_t lddy, void* y, int64_t ldy, int64_t M, int64_t N, int mode,
+                     int dtype, void* stream);
 
 /* -- multi-GPU exchange over NVLink peer memory (one process per GPU, one NVSwitch box) ---------------------------------
  * Replaces, for the dst-range sharded forward, the NCCL collectives of the reference: `halo_exchange` (distributed/graph.py:466-484,

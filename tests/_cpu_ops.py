@@ -40,10 +40,12 @@ def build_csr(edge_index: Tensor, n_src: int, n_dst: int, validate: bool = True)
 def _block_stats(y: Tensor) -> Tensor:
     M, N = y.shape
     P = (N + 63) // 64
-    yp = torch.zeros(M, P * 64)
-    yp[:, :N] = y.float()
-    yp = yp.view(M, P, 64)
-    return torch.stack([yp.sum(-1), (yp * yp).sum(-1)], -1)
+    out = torch.zeros(M, P, 2)
+    for b in range(P):
+        blk = y[:, b * 64 : min(N, (b + 1) * 64)].float()
+        mean = blk.mean(1)
+        out[:, b, 0], out[:, b, 1] = mean, ((blk - mean[:, None]) ** 2).sum(1)
+    return out
 
 
 def partial_stats_buffer(out_rows: int, out_cols: int, device) -> Tensor:
@@ -55,9 +57,12 @@ def linear(a, weight, bias=None, gelu=False, residual=None, gather1=None, gather
     acc = a.float() @ weight.float().t()
     if ln_stats is not None:
         if ln_stats.dim() == 3:
-            s, q = ln_stats[..., 0].sum(1), ln_stats[..., 1].sum(1)
-            mean = s / ln_dim
-            rstd = (torch.clamp(q / ln_dim - mean * mean, min=0.0) + ln_eps).rsqrt()
+            P = ln_stats.shape[1]  # per 64-column block (mean, M2): Chan merge, like common.cuh:ln_row_mean_rstd
+            n = torch.full((P,), 64.0)
+            n[-1] = ln_dim - 64 * (P - 1)
+            mean = (ln_stats[..., 0] * n).sum(1) / ln_dim
+            m2 = (ln_stats[..., 1] + n * (ln_stats[..., 0] - mean[:, None]) ** 2).sum(1)
+            rstd = (m2 / ln_dim + ln_eps).rsqrt()
         else:
             mean, rstd = ln_stats[:, 0], ln_stats[:, 1]
         acc = rstd[:, None] * (acc - mean[:, None] * ln_colsum[None, :])

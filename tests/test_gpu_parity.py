@@ -4,8 +4,8 @@ UNMODIFIED reference modules (tests/golden, fp32) and (b) the oracle restatement
 Tolerances (stated):
   fp32  : max|ours - ref| <= 1e-4 * max|ref|  and rel-L2 <= 1e-4  (BASELINE.json north_star; the reference's own kernel
           test uses atol 1e-4, test_triton_gt.py:135-136)
-  bf16  : rel-L2(ours_bf16, ref_fp32) <= 2e-2 after the stack, and ours is no worse than 1.5x the error of the oracle run
-          with bf16-rounded weights/activations at layer boundaries is NOT assumed — we only bound against fp32.
+  bf16  : rel-L2(ours_bf16, ref_fp32) <= 2e-2 after a stack (<= 8e-3 for the full cfg2 step); the SURVEY §8(d) criterion
+          err(ours) <= 1.5 x err(reference under autocast) is tested in tests/test_gpu_bars.py on reference fixtures.
 """
 import pytest
 import torch
@@ -214,7 +214,7 @@ def test_full_cfg2_step_parity():
             y16 = m(xg.cuda(), xm.cuda(), gd)
     assert_fp32_parity(y32, ref, "cfg2 full step fp32")
     mx, l2 = rel_err(y16, ref)
-    assert y16.dtype == torch.bfloat16 and l2 <= 2e-2, f"cfg2 bf16 rel-L2 {l2:.3e} (max-rel {mx:.3e})"
+    assert y16.dtype == torch.bfloat16 and l2 <= 8e-3, f"cfg2 bf16 rel-L2 {l2:.3e} (max-rel {mx:.3e}); bar 8e-3 (observed 3.8e-3 in round 1)"
 
 
 def test_edge_cases_empty_and_isolated():

@@ -62,5 +62,5 @@ def test_instantiate_from_the_reference_yaml_processor_block(overlay):
 
 def test_uninstall_restores(overlay):
     overlay.uninstall()
-    assert not any(getattr(m, "__anemoi_b200_stub__", False) for m in list(sys.modules.values()))
+    assert not any(k == "anemoi" or k.startswith("anemoi.") for k in sys.modules if getattr(sys.modules[k], "__anemoi_b200_stub__", False) is True)
     overlay.install()

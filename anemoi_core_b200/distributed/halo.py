@@ -109,10 +109,7 @@ class HaloPlan:
             self._pending = ("peer", table)
             return
         local, halo = table[: self.n_local], table[self.n_local :]
-        if table.is_cuda:
-            send = ops.cast_pad(local, table.dtype, idx=self.send_idx)  # one gather kernel packs every destination's rows
-        else:  # host-logic tests (Gloo); the product path is CUDA
-            send = local.index_select(0, self.send_idx.long())
+        send = ops.cast_pad(local, table.dtype, idx=self.send_idx)  # one gather kernel packs every destination's rows (CUDA only, like every op)
         if SegmentedCapture.active is not None:
             SegmentedCapture.active.exchange_start(send, self.send_splits, self.recv_splits, self.group, halo)
             self._pending = ("capture", None)

@@ -146,7 +146,10 @@ def linear_with_stats(a: Tensor, w: Tensor, bias: Optional[Tensor], want_stats: 
 # The producer's epilogue writes per-row partial (sum, sum of squares) next to its output (``ops.linear(stats_out=)``); the pair travels as
 # an attribute of the output tensor object and is honoured only while that tensor is unchanged (same storage, version, shape), so a slice,
 # a gather or an in-place update silently falls back to the ``row_stats`` pass.
-FUSED_ROW_STATS = os.environ.get("ANEMOI_B200_FUSED_ROW_STATS", "1") != "0"  # A/B switch (profiles/README.md); off = separate row_stats pass
+# A/B switch.  Default OFF since round 2: measured on the same box (profiles/r2/call8_ab_row_stats.txt) the separate row_stats pass gives
+# 8.64 ms / step against 8.89-8.94 ms with the statistics written by the producing GEMM's epilogue - the epilogue is the GEMMs' critical
+# path, and every instruction added to it (shifted sums, the per-block division) costs more than the 16 us pass it replaces.
+FUSED_ROW_STATS = os.environ.get("ANEMOI_B200_FUSED_ROW_STATS", "0") != "0"
 
 
 def tag_row_stats(t: Tensor, stats: Tensor) -> Tensor:

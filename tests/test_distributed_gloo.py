@@ -97,6 +97,10 @@ def check_halo_exchange(rank, world):
     """Halo plan + exchange (distributed/halo.py; reference block.py:1120-1183): after the exchange every local edge finds, at its relabelled
     source position of the compact table, exactly the row its GLOBAL source id names; only referenced remote rows travel."""
     from anemoi_core_b200.distributed.halo import halo_plan_for
+
+    import _cpu_ops  # tests/: plain-PyTorch stand-in for the CUDA entry points (the exchange packs its rows with ops.cast_pad)
+
+    _cpu_ops.install()
     from anemoi_core_b200.layers.processor import _shard_edges_by_dst
 
     for n, e, seed in ((37, 211, 3), (64, 40, 4), (50, 0, 5)):  # dense, sparse (small halos, some empty), no edges at all

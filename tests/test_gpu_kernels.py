@@ -137,7 +137,7 @@ def test_linear(ops, M, N, K, dt, epi):
                                        (40962, 1000, 520, "bias_gelu")])
 def test_linear_large_two_cta(ops, M, N, K, epi):
     """Shapes large enough for the cta_group::2 kernel (256x256 tiles per CTA pair), ragged M / N / K tails included.
-    (The 2-CTA kernel is opt-in through ANEMOI_B200_GEMM_CG=2, read once per process: CI runs this file a second time with it set.)
+    (The 2-CTA kernel is the DEFAULT for problems that fill the 74 CTA pairs; ANEMOI_B200_GEMM_CG=1 forces the single-CTA kernel.)
     Checker: fp32 torch matmul on the same bf16-rounded operands (on the GPU: the CPU would take minutes)."""
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     a = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
@@ -246,6 +246,22 @@ def test_linear_row_stats_constant_rows(ops):
     assert torch.isfinite(out).all()
     # LN(constant) = 0 -> out = bias, up to the fp32 accumulation error of sum_k x w'_k against mean * colsum times rstd = 316
     assert (out[:256].float() - b2).abs().max().item() <= 0.05
+
+
+@pytest.mark.parametrize("M,C", [(40962, 512), (1001, 1024), (37, 64), (500, 200), (3, 2048)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("mean", [0.0, 300.0])
+def test_row_stats(ops, M, C, dt, mean):
+    """(mean, rstd) per row against the two-pass fp64 statement, also for rows whose mean dwarfs their spread (the streaming kernel
+    accumulates shifted sums); bf16 rows of a multiple of 64 elements take row_stats_stream_kernel, the rest the per-warp-row kernel."""
+    g = torch.Generator().manual_seed(M + C)
+    x = (mean + torch.randn(M, C, generator=g) * (2.0 if mean else 1.0)).to(dt).cuda()
+    st = ops.row_stats(x, 1e-5).double().cpu()
+    xd = x.double().cpu()
+    mu = xd.mean(1)
+    rstd = 1.0 / torch.sqrt(xd.var(1, unbiased=False) + 1e-5)
+    assert (st[:, 0] - mu).abs().max().item() <= 1e-5 * max(1.0, abs(mean))
+    assert ((st[:, 1] - rstd).abs() / rstd).max().item() <= 2e-4
 
 
 def test_linear_row_stats_large_mean_small_variance(ops):

@@ -172,3 +172,57 @@ def _all_gather_rows(x: Tensor, sizes: list[int], group, out: Optional[Tensor] =
             out[off : off + n] = buf[r * m : r * m + n]
             off += n
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# autograd halves (reference: distributed/graph.py:227-500 ``_SyncParallelSection`` & co., block.py:1159-1169 halo exchange) — the training
+# path of a model-parallel group.  Forward = the collective above; backward = its transpose.
+# ------------------------------------------------------------------------------------------------------------------------------------
+class GatherRowsFn(torch.autograd.Function):
+    """All-gather of row shards; backward: every rank sums the cotangents of ITS rows over the group (all-reduce, keep own slice)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, sizes: list, group) -> Tensor:
+        ctx.sizes, ctx.group = list(sizes), group
+        return _all_gather_rows(x.contiguous(), list(sizes), group)
+
+    @staticmethod
+    def backward(ctx, d_full: Tensor):
+        d_full = d_full.contiguous()
+        dist.all_reduce(d_full, group=ctx.group)
+        r = group_rank(ctx.group)
+        start = sum(ctx.sizes[:r])
+        return d_full[start : start + ctx.sizes[r]], None, None
+
+
+class HaloExchangeFn(torch.autograd.Function):
+    """Halo rows of a ``HaloPlan`` from this rank's rows; backward: the halo cotangents travel back to the rows' owners and are added there
+    (per requesting rank in rank order: deterministic; a requester's list holds every row once)."""
+
+    @staticmethod
+    def forward(ctx, local: Tensor, plan) -> Tensor:
+        from .. import ops
+
+        ctx.plan, ctx.n_local = plan, local.shape[0]
+        send = ops.cast_pad(local.detach(), local.dtype, idx=plan.send_idx)
+        return _exchange(send, plan.send_splits, plan.recv_splits, plan.group)
+
+    @staticmethod
+    def backward(ctx, d_halo: Tensor):
+        plan = ctx.plan
+        back = _exchange(d_halo.contiguous(), plan.recv_splits, plan.send_splits, plan.group)  # cotangents of the rows WE sent, grouped by requester
+        d_local = back.new_zeros((ctx.n_local, back.shape[1]))
+        off = 0
+        idx = plan.send_idx.long()
+        for n in plan.send_splits:
+            if n:
+                d_local[idx[off : off + n]] += back[off : off + n]
+            off += n
+        return d_local, None
+
+
+def gather_rows_grad(x: Tensor, sizes: Optional[list[int]], group) -> Tensor:
+    """Differentiable ``gather_rows``."""
+    if group_size(group) == 1:
+        return x
+    return GatherRowsFn.apply(x, sizes, group)

@@ -3,9 +3,11 @@
 layers/mlp.py:158-179) so that PyTorch autograd reaches every parameter, the inputs and the (trainable) edge attributes.
 
 Taken whenever gradients are needed (``wants_grad``); the inference path under ``torch.no_grad()`` keeps its fusions (LayerNorm folded
-into the GEMMs, lin_edge folded into attention, packed weights), which have no backward.  Single GPU: the autograd halves of the
-sharding collectives (distributed/graph.py:227-500) are a later row.  Gated MLP variants, ConditionalLayerNorm and edge_pre_mlp train
-through the plain-torch ops they are made of only where stated below; otherwise NotImplementedError with the reason.
+into the GEMMs, lin_edge folded into attention, packed weights), which have no backward.  On a model-parallel group the "edges" strategy
+trains through the autograd halves of the exchange (``distributed.graph.HaloExchangeFn`` / ``GatherRowsFn``; reference
+distributed/graph.py:227-500): the forward collective is NCCL, the backward its transpose; parameter gradients are per-rank partial sums
+(the trainer's gradient all-reduce over the model group completes them, as in the reference).  Not implemented (NotImplementedError with
+the reason): the heads strategy, gated MLP variants and ConditionalLayerNorm in training.
 """
 
 from __future__ import annotations
@@ -29,12 +31,11 @@ def wants_grad(module: nn.Module, *tensors: Optional[Tensor]) -> bool:
     return module.training and any(p.requires_grad for p in module.parameters())
 
 
-def _single_gpu(group) -> None:
+def _single_gpu(group, what: str = "this module") -> None:
     from ..distributed.graph import group_size
 
     if group_size(group) > 1:
-        raise NotImplementedError("training on a sharded model: the autograd halves of the halo exchange / all-gather are not implemented yet "
-                                  "(SURVEY.md §8f rank 3); run data-parallel replicas")  # fmt: skip
+        raise NotImplementedError(f"training {what} on a model-parallel group is not implemented (the 'edges' strategy of the processors / mappers is)")
 
 
 def _plain_ln(ln: nn.Module) -> None:
@@ -110,17 +111,20 @@ def graph_conv(conv, x_src: Tensor, x_dst: Tensor, e: Tensor, csr, dt: torch.dty
     return out, e_new
 
 
-def gnn_block(block, x_src: Tensor, x_dst: Tensor, edge_attr: Tensor, edge_index: Tensor, dt: torch.dtype, bipartite: bool):
-    """GraphConvProcessorBlock / GraphConvMapperBlock forward (block.py:362-395, 441-479); returns ((src_new, dst_new), edges_new)."""
+def gnn_block(block, x_src: Tensor, x_dst: Tensor, edge_attr: Tensor, edge_index: Tensor, dt: torch.dtype, bipartite: bool,
+              x_src_local: Optional[Tensor] = None):  # fmt: skip
+    """GraphConvProcessorBlock / GraphConvMapperBlock forward (block.py:362-395, 441-479); returns ((src_new, dst_new), edges_new).
+    ``x_src`` holds every source row the (local) edges name — on a model-parallel group the all-gathered rows (block.py:375, :451) —
+    ``x_src_local`` this rank's source rows (the ones a forward mapper updates)."""
     if block.emb_edges is not None:
         edge_attr = mlp(block.emb_edges, edge_attr, dt)
     csr = Fn.csr_for(edge_index, x_src.shape[0], x_dst.shape[0])
     out, e_new = graph_conv(block.conv, x_src, x_dst, edge_attr, csr, dt)
     xd = x_dst.to(dt)
     dst_new = mlp(block.node_mlp, torch.cat([xd, out], 1), dt, residual=xd)
-    src_new = x_src
+    src_new = x_src if x_src_local is None else x_src_local
     if bipartite and block.update_src_nodes:  # block.py:475 — the same node_mlp on cat[x_src, x_src]
-        xs = x_src.to(dt)
+        xs = src_new.to(dt)
         src_new = mlp(block.node_mlp, torch.cat([xs, xs], 1), dt, residual=xs)
     return (src_new, dst_new), e_new
 
@@ -129,7 +133,7 @@ def gnn_block(block, x_src: Tensor, x_dst: Tensor, edge_attr: Tensor, edge_index
 # GraphTransformer
 # ------------------------------------------------------------------------------------------------------------
 def gt_block(block, x_src: Optional[Tensor], x_dst: Tensor, edge_attr: Tensor, edge_index: Tensor, dt: torch.dtype, ln_src: Optional[nn.Module],
-             cond=None) -> Tensor:  # fmt: skip
+             cond=None, plan=None) -> Tensor:  # fmt: skip
     """GraphTransformerProcessorBlock (``x_src is None``: block.py:1219-1273) / GraphTransformerMapperBlock (block.py:963-1029) forward with the
     materialised edge projection (the reference's own formulation, block.py:623-635 + conv.py:103-147); returns the new dst rows."""
     if cond is not None:
@@ -149,6 +153,15 @@ def gt_block(block, x_src: Optional[Tensor], x_dst: Tensor, edge_attr: Tensor, e
     if block.qk_norm:
         q = norm(block.q_norm, q, dt, groups=H)
         k = norm(block.k_norm, k, dt, groups=H)
+    if plan is not None:
+        # model-parallel "edges" strategy: k | v of the rows this rank owns, plus the halo rows its edges name on other ranks (differentiable
+        # exchange); ``plan.edge_index`` addresses the compact table [own rows | halo rows] and local destination rows
+        from ..distributed.graph import HaloExchangeFn
+
+        kv_local = torch.cat([k, v], 1)
+        table = torch.cat([kv_local, HaloExchangeFn.apply(kv_local, plan)], 0)
+        k, v = table[:, :A], table[:, A:]
+        edge_index, n_src = plan.edge_index, table.shape[0]
     ea = edge_attr
     if not isinstance(block.edge_pre_mlp, nn.Identity):
         ea = lin(block.edge_pre_mlp[0], ea, torch.float32, gelu=True)

@@ -17,6 +17,7 @@ from torch import nn
 
 from .. import ops
 from ..distributed.graph import gather_rows
+from ..distributed.graph import gather_rows_grad
 from ..distributed.graph import group_size
 from ..distributed.halo import halo_plan_for
 from ..distributed.shapes import BipartiteGraphShardInfo
@@ -100,8 +101,9 @@ class GraphConvProcessorBlock(GraphConvBaseBlock):
     ) -> tuple[Tensor, Tensor]:
         dt = Fn.compute_dtype(x, edge_attr)
         if T.wants_grad(self, x, edge_attr):  # differentiable path (layers/_train.py)
-            T._single_gpu(model_comm_group)
-            (_, x_new), edges_new = T.gnn_block(self, x, x, edge_attr, edge_index, dt, bipartite=False)
+            # model-parallel: all source rows by a differentiable all-gather (block.py:375); the processor hands us edges with LOCAL dst ids
+            x_all = gather_rows_grad(x, shard_info.nodes if shard_info is not None else None, model_comm_group)
+            (_, x_new), edges_new = T.gnn_block(self, x_all, x, edge_attr, edge_index, dt, bipartite=False)
             return x_new, edges_new
         if self.emb_edges is not None:
             edge_attr = self.emb_edges.run(edge_attr, dt)
@@ -151,8 +153,10 @@ class GraphConvMapperBlock(GraphConvBaseBlock):
         x_src, x_dst = x
         dt = Fn.compute_dtype(x_src, x_dst, edge_attr)
         if T.wants_grad(self, x_src, x_dst, edge_attr):  # differentiable path (layers/_train.py)
-            T._single_gpu(model_comm_group)
-            return T.gnn_block(self, x_src, x_dst, edge_attr, edge_index, dt, bipartite=True)
+            src_all = x_src
+            if group_size(model_comm_group) > 1 and shard_info is not None and shard_info.src_is_sharded():
+                src_all = gather_rows_grad(x_src, shard_info.src_nodes, model_comm_group)  # block.py:451
+            return T.gnn_block(self, src_all, x_dst, edge_attr, edge_index, dt, bipartite=True, x_src_local=x_src)
         C = self.in_channels
         # sharded (block.py:451-470): x_dst and the edges are this rank's (local dst ids, global src ids); every source row is needed
         src_all = x_src
@@ -448,8 +452,12 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
             edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, False)
             edge_attr_prepared = None
         if T.wants_grad(self, x, edge_attr):  # differentiable path (layers/_train.py)
-            T._single_gpu(model_comm_group)
-            return T.gt_block(self, None, x, edge_attr, edge_index, dt, None, cond), edge_attr_in
+            plan = None
+            if group_size(model_comm_group) > 1:
+                if self.shard_strategy != "edges":
+                    T._single_gpu(model_comm_group, "the heads strategy")
+                plan = halo_plan_for(edge_index, shard_info.nodes, model_comm_group)  # same plan as the inference path (block.py:1120-1183)
+            return T.gt_block(self, None, x, edge_attr, edge_index, dt, None, cond, plan=plan), edge_attr_in
         A = self.attn_channels
         ln = self.layer_norm_attention  # with a ConditionalLayerNorm kernel both LayerNorms of the block take ``cond`` (block.py:1233-1271)
         dst_layers = [self.lin_key, self.lin_value, self.lin_self]
@@ -535,8 +543,13 @@ class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
         cond_src, cond_dst = cond if cond is not None else (None, None)  # (block.py:978-980)
         dt = Fn.compute_dtype(x_src, x_dst)
         if T.wants_grad(self, x_src, x_dst, edge_attr):  # differentiable path (layers/_train.py)
-            T._single_gpu(model_comm_group)
-            dst_new = T.gt_block(self, x_src, x_dst, edge_attr, edge_index, dt, self.layer_norm_attention_src, cond)
+            plan = None
+            if group_size(model_comm_group) > 1:
+                if self.shard_strategy != "edges":
+                    T._single_gpu(model_comm_group, "the heads strategy")
+                if shard_info is not None and shard_info.src_is_sharded():
+                    plan = halo_plan_for(edge_index, shard_info.src_nodes, model_comm_group)
+            dst_new = T.gt_block(self, x_src, x_dst, edge_attr, edge_index, dt, self.layer_norm_attention_src, cond, plan=plan)
             src_new = x_src
             if self.update_src_nodes:
                 src_new = T.mlp(self.node_src_mlp, x_src.to(dt), dt, residual=x_src, pre_ln=self.layer_norm_mlp_src)

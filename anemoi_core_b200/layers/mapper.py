@@ -120,12 +120,7 @@ class GraphTransformerBaseMapper(BaseMapper):
         the full dst-sorted edge list is cut to the edges into the local rows (cached per graph and group)."""
         edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
         world = group_size(model_comm_group)
-        if T.wants_grad(self, x[0], x[1], edge_attr):  # differentiable path (layers/_train.py): single GPU, same call sequence
-            T._single_gpu(model_comm_group)
-            dt = Fn.compute_dtype(*x)
-            x_src, x_dst = self.pre_process_train(x, dt)
-            (_, x_dst_out), _ = self.proc((x_src, x_dst), edge_attr, edge_index, shard_info, batch_size, (x_src.shape[0], x_dst.shape[0]), None, cond=cond)
-            return self.post_process_train(x_dst_out, dt)
+        train = T.wants_grad(self, x[0], x[1], edge_attr)  # differentiable path (layers/_train.py): same call sequence, same sharding
         if world > 1:
             if shard_info is None or not shard_info.dst_is_sharded():
                 raise ValueError("sharded mapper: shard_info.dst_nodes (per-rank destination row counts) is required")
@@ -145,14 +140,15 @@ class GraphTransformerBaseMapper(BaseMapper):
                                                                         relabel_dst=True, dst_splits=shard_info.dst_nodes)  # fmt: skip
                 shard_info = BipartiteGraphShardInfo(src_nodes=shard_info.src_nodes, dst_nodes=shard_info.dst_nodes, edges=edge_sizes)
         dt = Fn.compute_dtype(*x)
-        x_src, x_dst = self.pre_process(x, dt)
+        x_src, x_dst = (self.pre_process_train if train else self.pre_process)(x, dt)
         (_, x_dst_out), _ = self.proc((x_src, x_dst), edge_attr, edge_index, shard_info, batch_size, (x_src.shape[0], x_dst.shape[0]),
                                       model_comm_group if world > 1 else None, cond=cond)  # fmt: skip
-        out = self.post_process(x_dst_out, dt)
+        out = (self.post_process_train if train else self.post_process)(x_dst_out, dt)
         if world > 1 and not keep_x_dst_sharded:
             from ..distributed.graph import gather_rows
+            from ..distributed.graph import gather_rows_grad
 
-            out = gather_rows(out, shard_info.dst_nodes, model_comm_group)
+            out = (gather_rows_grad if train else gather_rows)(out, shard_info.dst_nodes, model_comm_group)
         return out
 
 
@@ -283,13 +279,7 @@ class GNNBaseMapper(BaseMapper):
         edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
         world = group_size(model_comm_group)
         x_src, x_dst = x
-        if T.wants_grad(self, x_src, x_dst, edge_attr):  # differentiable path (layers/_train.py): single GPU, same call sequence
-            T._single_gpu(model_comm_group)
-            dt = Fn.compute_dtype(x_src, x_dst, edge_attr)
-            e = T.mlp(self.emb_edges, edge_attr, dt)
-            x_src, x_dst = self.pre_process_train((x_src, x_dst), dt)
-            (x_src, x_dst), _ = self.proc((x_src, x_dst), e, edge_index, shard_info, None)
-            return x_src, self.post_process_train(x_dst, dt)
+        train = T.wants_grad(self, x_src, x_dst, edge_attr)  # differentiable path (layers/_train.py): same call sequence, same sharding
         if world > 1:
             from ..distributed.balanced_partition import get_balanced_partition_sizes
             from ..distributed.graph import shard_rows
@@ -312,14 +302,15 @@ class GNNBaseMapper(BaseMapper):
                                                                         relabel_dst=True, dst_splits=dst_sizes)  # fmt: skip
             shard_info = BipartiteGraphShardInfo(src_nodes=src_sizes, dst_nodes=dst_sizes, edges=edge_sizes)
         dt = Fn.compute_dtype(x_src, x_dst, edge_attr)
-        e = self.emb_edges.run(edge_attr, dt)
-        x_src, x_dst = self.pre_process((x_src, x_dst), dt)
+        e = T.mlp(self.emb_edges, edge_attr, dt) if train else self.emb_edges.run(edge_attr, dt)
+        x_src, x_dst = (self.pre_process_train if train else self.pre_process)((x_src, x_dst), dt)
         (x_src, x_dst), _ = self.proc((x_src, x_dst), e, edge_index, shard_info, model_comm_group if world > 1 else None)
-        out = self.post_process(x_dst, dt)
+        out = (self.post_process_train if train else self.post_process)(x_dst, dt)
         if world > 1 and not keep_x_dst_sharded:
             from ..distributed.graph import gather_rows
+            from ..distributed.graph import gather_rows_grad
 
-            out = gather_rows(out, shard_info.dst_nodes, model_comm_group)
+            out = (gather_rows_grad if train else gather_rows)(out, shard_info.dst_nodes, model_comm_group)
         return x_src, out
 
 

@@ -150,11 +150,17 @@ class GNNProcessor(BaseProcessor):
         n_nodes = sum(shard_info.nodes) if shard_info is not None and shard_info.nodes_are_sharded() else x.shape[0]
         if shard_info is None:
             shard_info = GraphShardInfo()
-        if T.wants_grad(self, x, edge_attr):  # differentiable path: plain layer loop, single GPU (layers/_train.py)
-            T._single_gpu(model_comm_group)
-            edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
+        if T.wants_grad(self, x, edge_attr):  # differentiable path: plain layer loop (layers/_train.py)
+            world = group_size(model_comm_group)
+            if not shard_info.edges_are_sharded():
+                edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
+                if world > 1:  # edges into this rank's rows, dst relabelled to the local range (sources: all-gathered per layer, global ids)
+                    edge_attr, edge_index, edge_sizes = _shard_edges_by_dst(edge_attr, edge_index, n_nodes, n_nodes, model_comm_group, relabel_dst=True)
+                    shard_info = GraphShardInfo(nodes=shard_info.nodes, edges=edge_sizes)
+            elif world > 1:
+                edge_index = _localise_presharded_edges(edge_index, shard_info.nodes, model_comm_group)
             for block in self.proc:
-                x, edge_attr = block(x, edge_attr, edge_index, shard_info, None)
+                x, edge_attr = block(x, edge_attr, edge_index, shard_info, model_comm_group if world > 1 else None)
             return x
         if not shard_info.edges_are_sharded():
             edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
@@ -242,11 +248,20 @@ class GraphTransformerProcessor(BaseProcessor):
         if shard_info is None:
             shard_info = GraphShardInfo()
         n_nodes = sum(shard_info.nodes) if shard_info.nodes_are_sharded() else x.shape[0]
-        if T.wants_grad(self, x, edge_attr):  # differentiable path: plain layer loop, single GPU (layers/_train.py)
-            T._single_gpu(model_comm_group)
-            edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
+        if T.wants_grad(self, x, edge_attr):  # differentiable path: plain layer loop (layers/_train.py)
+            world = group_size(model_comm_group)
+            if world > 1 and self.shard_strategy != "edges":
+                T._single_gpu(model_comm_group, "the heads strategy")
+            if not shard_info.edges_are_sharded():
+                edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
+                if world > 1:
+                    edge_attr, edge_index, edge_sizes = _shard_edges_by_dst(edge_attr, edge_index, n_nodes, n_nodes, model_comm_group, relabel_dst=True)
+                    shard_info = GraphShardInfo(nodes=shard_info.nodes, edges=edge_sizes)
+            elif world > 1:
+                edge_index = _localise_presharded_edges(edge_index, shard_info.nodes, model_comm_group)
             for block in self.proc:
-                x, _ = block(x, edge_attr, edge_index, shard_info, batch_size, n_nodes, None, cond=kwargs.get("cond"))
+                x, _ = block(x, edge_attr, edge_index, shard_info, batch_size, n_nodes, model_comm_group if world > 1 else None,
+                             cond=kwargs.get("cond"))  # fmt: skip
             return x
         if not shard_info.edges_are_sharded():
             edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)

@@ -54,8 +54,12 @@ class EncProcDec(nn.Module):
         encoder (full grid sources, local mesh rows), processor (local rows, per-layer all-gather of k|v or x), latent skip, decoder (local
         mesh sources all-gathered as k|v, local grid rows); the output rows are gathered at the end.  GNN mappers run replicated."""
         from .distributed.graph import gather_rows
+        from .distributed.graph import gather_rows_grad
         from .distributed.graph import group_size
         from .distributed.graph import shard_rows
+
+        def skip(a: Tensor, b: Tensor) -> Tensor:  # latent skip (:295-296); the fused add kernel carries no gradient
+            return a + b.to(a.dtype) if (torch.is_grad_enabled() and (a.requires_grad or b.requires_grad)) else ops.add(a, b)
 
         if group_size(model_comm_group) > 1 and mesh_shards is not None:
             g = model_comm_group
@@ -69,7 +73,7 @@ class EncProcDec(nn.Module):
                 _, x_local = self.encoder((x_grid_l, x_mesh_l), 1, BipartiteGraphShardInfo(src_nodes=grid_shards, dst_nodes=mesh_shards),
                                           graph["enc_attr"], graph["enc_index"], g, keep_x_dst_sharded=True)  # fmt: skip
                 y_local = self.processor(x_local, 1, GraphShardInfo(nodes=mesh_shards), graph["proc_attr"], graph["proc_index"], g)
-                y_local = ops.add(y_local, x_local)  # latent skip (:295-296)
+                y_local = skip(y_local, x_local)
                 return self.decoder((y_local, x_grid_l), 1, BipartiteGraphShardInfo(src_nodes=mesh_shards, dst_nodes=grid_shards), graph["dec_attr"],
                                     graph["dec_index"], g, keep_x_dst_sharded=keep_output_sharded)  # fmt: skip
             if self.kind == "gnn" and grid_shards is not None:
@@ -78,20 +82,20 @@ class EncProcDec(nn.Module):
                 x_data_l, x_local = self.encoder((x_grid_l, x_mesh_l), 1, BipartiteGraphShardInfo(src_nodes=grid_shards, dst_nodes=mesh_shards),
                                                  graph["enc_attr"], graph["enc_index"], g, keep_x_dst_sharded=True)  # fmt: skip
                 y_local = self.processor(x_local, 1, GraphShardInfo(nodes=mesh_shards), graph["proc_attr"], graph["proc_index"], g)
-                y_local = ops.add(y_local, x_local)
+                y_local = skip(y_local, x_local)
                 return self.decoder((y_local, x_data_l), 1, BipartiteGraphShardInfo(src_nodes=mesh_shards, dst_nodes=grid_shards), graph["dec_attr"],
                                     graph["dec_index"], g, keep_x_dst_sharded=False)  # fmt: skip
             bi = BipartiteGraphShardInfo()
             x_data_latent, x_latent = self.encoder((x_grid, x_mesh), 1, bi, graph["enc_attr"], graph["enc_index"])
             x_local = shard_rows(x_latent, mesh_shards, g)
             y_local = self.processor(x_local, 1, GraphShardInfo(nodes=mesh_shards), graph["proc_attr"], graph["proc_index"], g)
-            y_local = ops.add(y_local, x_local)
-            x_proc = gather_rows(y_local, mesh_shards, g)
+            y_local = skip(y_local, x_local)
+            x_proc = (gather_rows_grad if y_local.requires_grad else gather_rows)(y_local, mesh_shards, g)
             return self.decoder((x_proc, x_data_latent), 1, bi, graph["dec_attr"], graph["dec_index"])
         bi = BipartiteGraphShardInfo()
         x_data_latent, x_latent = self.encoder((x_grid, x_mesh), 1, bi, graph["enc_attr"], graph["enc_index"])
         x_proc = self.processor(x_latent, 1, GraphShardInfo(nodes=[x_latent.shape[0]]), graph["proc_attr"], graph["proc_index"])
-        x_proc = ops.add(x_proc, x_latent)  # latent skip (:295-296)
+        x_proc = skip(x_proc, x_latent)
         return self.decoder((x_proc, x_data_latent), 1, bi, graph["dec_attr"], graph["dec_index"])
 
     # -- CUDA graph of one whole step ------------------------------------------------------------------------------

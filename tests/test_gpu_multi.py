@@ -123,6 +123,41 @@ def _worker(rank, world, init_file, ret):
         err = ((gath - full).abs().max() / full.abs().max()).item()
         msgs.append(("gnn_halo_form", "fp32", err, err <= 1e-5))
         P.GNN_HALO = False
+        # ---- (round 2) TRAINING on the model-parallel group: the autograd halves of the halo exchange / all-gather (reference
+        # distributed/graph.py:227-500).  One fp32 step of the sharded model must give the single-GPU gradients: parameter gradients are
+        # per-rank partial sums (all-reduced here, as the trainer does over the model group), input gradients are the local slices. ----
+        wgt = torch.randn(gr["n_grid"], 9, generator=torch.Generator().manual_seed(21)).cuda()
+        for kind in ("graphtransformer", "gnn"):
+            torch.manual_seed(6)
+            mt = EncProcDec(kind, in_grid=20, in_mesh=12, out_grid=9, num_channels=64, num_layers=2, edge_dim=gr["edge_dim"], num_heads=4).cuda().train()
+            xg_f = xg.detach().clone().requires_grad_()
+            (mt(xg_f, xm, gd) * wgt).sum().backward()
+            ref_p = {n_: p.grad.clone() for n_, p in mt.named_parameters()}
+            ref_x = xg_f.grad.clone()
+            mt.zero_grad()
+            if kind == "graphtransformer":
+                xg_s = xg[g0 : g0 + gsz[rank]].detach().clone().requires_grad_()
+                y_l = mt(xg_s, xm[m0 : m0 + sizes[rank]].contiguous(), gd, **kw)
+                (y_l * wgt[g0 : g0 + gsz[rank]]).sum().backward()
+                gx, rx = xg_s.grad, ref_x[g0 : g0 + gsz[rank]]
+            else:
+                xg_s = xg.detach().clone().requires_grad_()
+                y_all = mt(xg_s, xm, gd, group, sizes, gsz)  # replicated in / gathered out: every rank holds the whole output
+                (y_all * wgt).sum().backward()
+                gx = xg_s.grad.clone()
+                dist.all_reduce(gx)
+                gx, rx = gx / world, ref_x  # every rank back-propagated the same (whole) loss
+            err = ((gx - rx).abs().max() / rx.abs().max()).item()
+            msgs.append((f"train_{kind}_dx", "fp32", err, err <= 1e-4))
+            worst = 0.0
+            big = max(g_.abs().max().item() for g_ in ref_p.values())
+            for n_, p in mt.named_parameters():
+                gp = p.grad.clone() if p.grad is not None else torch.zeros_like(p)
+                dist.all_reduce(gp)
+                if kind == "gnn":
+                    gp = gp / world
+                worst = max(worst, ((gp - ref_p[n_]).abs().max() / max(ref_p[n_].abs().max().item(), 1e-3 * big)).item())
+            msgs.append((f"train_{kind}_dparams", "fp32", worst, worst <= 2e-4))
         ret[rank] = msgs
     except Exception as e:  # noqa: BLE001
         import traceback

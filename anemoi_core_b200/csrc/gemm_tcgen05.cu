@@ -189,6 +189,13 @@ constexpr int kL2Ahead = ANEMOI_GEMM_L2_AHEAD;
 #ifndef ANEMOI_GEMM_RES_PREFETCH
 #define ANEMOI_GEMM_RES_PREFETCH 1
 #endif
+// L2 prefetch of the residual sub-tiles of the NEXT tile (cp.async.bulk.prefetch.tensor, no shared-memory destination), issued by the
+// epilogue warp at the start of the current tile.  Measured (profiles/r2/call13_ab_res_l2.txt, same call): projection 42.0 -> 44.0 us,
+// MLP-2 80.8 -> 82.8 us - the extra TMA requests cost more than the L2 hits save (the one-round-ahead shared-memory prefetch already
+// covers the latency).  Off; kept as a compile-time option.
+#ifndef ANEMOI_GEMM_RES_L2_AHEAD
+#define ANEMOI_GEMM_RES_L2_AHEAD 0
+#endif
 constexpr int kSmemLimit = 232448;              // 227 KB: the most one CTA may own
 
 // CG = 1: one CTA computes a 128 x BN tile.  CG = 2 (cta_group::2): a CTA pair computes 256 x BN; each CTA holds 128 accumulator
@@ -272,11 +279,28 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
       ptx::tma_load_2d(cx.stg, tmRes, cx.res_bar, n_blk * BN + cx.grp * kColsPerWarp, m_blk * cx.tile_m + cx.row_off + cx.q * 32);
     }
   }
+  if constexpr (RES && ANEMOI_GEMM_RES_L2_AHEAD) {  // rounds 1.. of the first tile (round 0 is loaded straight into shared memory above)
+    if (lane == 0 && cx.first_tile < cx.num_tiles) {
+      const int m_blk = cx.first_tile / cx.tiles_n, n_blk = cx.first_tile - m_blk * cx.tiles_n;
+#pragma unroll
+      for (int rd = 1; rd < ROUNDS; ++rd)
+        ptx::tma_prefetch_l2_2d(tmRes, n_blk * BN + cx.grp * kColsPerWarp + rd * CW, m_blk * cx.tile_m + cx.row_off + cx.q * 32);
+    }
+  }
   for (int tile = cx.first_tile; tile < cx.num_tiles; tile += cx.tile_stride, ++it) {
     const int m_blk = tile / cx.tiles_n, n_blk = tile - m_blk * cx.tiles_n;
     const int as = it & 1;
     const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
     const int row0 = m_blk * cx.tile_m + cx.row_off + cx.q * 32;
+    if constexpr (RES && ANEMOI_GEMM_RES_L2_AHEAD) {
+      const int nt = tile + cx.tile_stride;
+      if (lane == 0 && nt < cx.num_tiles) {  // the whole next tile's residual rows of this warp -> L2, a tile (~10 k cycles) ahead of their use
+        const int nm = nt / cx.tiles_n, nn = nt - nm * cx.tiles_n;
+#pragma unroll
+        for (int rd = 0; rd < ROUNDS; ++rd)
+          ptx::tma_prefetch_l2_2d(tmRes, nn * BN + cx.grp * kColsPerWarp + rd * CW, nm * cx.tile_m + cx.row_off + cx.q * 32);
+      }
+    }
     if (ep.bias) {
       // the tile's bias slice goes to shared memory once per column group (one coalesced load) instead of two broadcast
       // global loads per 8 columns per thread (measured: the bias loads were ~25 % of the kernel time)

@@ -56,6 +56,9 @@ SIGNATURES = {
     "anemoi_b200_halo_wait": [c_void_p, c_int64, c_int64, c_void_p],
     "anemoi_b200_graphconv_ln_aggregate": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                            c_int64, c_int64, c_int64, c_float, c_int, c_void_p],
+    "anemoi_b200_graphconv_fused": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                    c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_int,
+                                    c_void_p],
     "anemoi_b200_cast_pad": [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p],
     "anemoi_b200_glu_combine": [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p],
     "anemoi_b200_assemble_input": [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,

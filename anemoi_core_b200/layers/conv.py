@@ -49,11 +49,46 @@ class GraphConv(nn.Module):
                             mlp_implementation=mlp_implementation)  # fmt: skip
         self._pack = Fn.WeightPack()
 
+    def _fused_plan(self):
+        """Linear layers of ``edge_mlp`` if the whole operator can run as the ONE-kernel form (``ops.graphconv_fused``): width 16 / 32 / 64,
+        plain Linear -> GELU -> ... -> Linear (no gated layers), plain LayerNorm.  None otherwise.  ``ANEMOI_B200_GC_FUSED=0`` forces the
+        decomposed form (A/B, tests)."""
+        import os
+
+        C, mlp = self.in_channels, self.edge_mlp
+        if os.environ.get("ANEMOI_B200_GC_FUSED", "1") == "0" or C not in ops.GRAPHCONV_FUSED_WIDTHS:
+            return None
+        mods = list(mlp.mlp)
+        lins = mods[0::2]
+        if len(mods) % 2 == 0 or not 2 <= len(lins) <= ops.GRAPHCONV_FUSED_MAX_LAYERS:
+            return None
+        if not all(isinstance(m, nn.Linear) for m in lins) or not all(isinstance(m, nn.GELU) and m.approximate == "none" for m in mods[1::2]):
+            return None
+        if lins[0].weight.shape != (C, 3 * C) or any(m.weight.shape != (C, C) for m in lins[1:]):
+            return None
+        ln = mlp.layer_norm
+        if not isinstance(ln, nn.LayerNorm) or tuple(ln.normalized_shape) != (C,):
+            return None
+        return lins
+
+    def _run_fused(self, lins, x_src: Tensor, x_dst: Tensor, edge_attr: Tensor, csr: ops.GraphCSR, dt: torch.dtype, out: Optional[Tensor]):
+        C, pack, ln = self.in_channels, self.edge_mlp._pack, self.edge_mlp.layer_norm
+        ws, bs = [m.weight for m in lins], [m.bias for m in lins]
+        w = pack.get(("gcf_w", dt), ws, lambda: torch.cat([x.detach().reshape(-1) for x in ws]).to(dt).contiguous())
+        b = pack.get(("gcf_b",), bs, lambda: torch.stack([torch.zeros(C, device=ws[0].device) if x is None else x.detach().float() for x in bs]).contiguous())
+        e = Fn.as_operand(edge_attr, dt, C)
+        e_new, out = ops.graphconv_fused(Fn.as_operand(x_src, dt, C), Fn.as_operand(x_dst, dt, C), e, w, b, len(lins), pack.f32(ln.weight),
+                                         pack.f32(ln.bias), csr, ln.eps, out=out)  # fmt: skip
+        return out, e_new
+
     def run(self, x_src: Tensor, x_dst: Tensor, edge_attr: Tensor, csr: ops.GraphCSR, dt: torch.dtype, out: Optional[Tensor] = None):
         C = self.in_channels
         mlp = self.edge_mlp
         if mlp.layer_norm is None:
             raise NotImplementedError("GraphConv.edge_mlp without LayerNorm")
+        lins = self._fused_plan()
+        if lins is not None:
+            return self._run_fused(lins, x_src, x_dst, edge_attr, csr, dt, out)
         def group(m):  # the Linear containers of one feed-forward layer: gate | value rows of a gated layer run as ONE GEMM
             return [m.gate_proj, m.value_proj] if isinstance(m, GatedMLPLayer) else [m]
 

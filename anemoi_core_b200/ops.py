@@ -17,7 +17,7 @@ from ._lib import BF16
 from ._lib import EPI_GELU
 from ._lib import F32
 
-__all__ = ["GraphCSR", "build_csr", "layer_norm", "row_stats", "linear", "gt_attention", "graphconv_ln_aggregate", "cast_pad", "add", "dtype_code"]
+__all__ = ["GraphCSR", "build_csr", "layer_norm", "row_stats", "linear", "gt_attention", "graphconv_ln_aggregate", "graphconv_fused", "cast_pad", "add", "dtype_code"]
 
 
 # ---- instrumentation: launch counter and optional CUDA-event timing of every C-ABI call (bench.py roofline leg) -------
@@ -503,6 +503,41 @@ def graphconv_ln_aggregate(
             _ptr(h), ldh, _ptr(_f32(weight)), _ptr(_f32(bias)), _ptr(e), lde, _ptr(e_new), C, _ptr(csr.colptr32), _ptr(out), ldo, csr.n_dst, C,
             float(eps), dtype_code(h.dtype), _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_graphconv_ln_aggregate")
+    return e_new, out
+
+
+GRAPHCONV_FUSED_WIDTHS = (16, 32, 64)  # widths the one-kernel GraphConv is built for (csrc/graphconv_fused.cu)
+GRAPHCONV_FUSED_MAX_LAYERS = 6
+
+
+def graphconv_fused(
+    x_src: Tensor, x_dst: Tensor, e: Tensor, weights: Tensor, biases: Tensor, n_layers: int, gamma: Optional[Tensor], beta: Optional[Tensor],
+    csr: GraphCSR, eps: float = 1e-5, out: Optional[Tensor] = None,
+) -> tuple[Tensor, Tensor]:  # fmt: skip
+    """The whole GraphConv operator (layers/conv.py:66-81) as ONE kernel, C in {16, 32, 64}:
+    (e_new, out) with e_new = LayerNorm(edge_mlp([x_dst[dst]; x_src[src]; e])) + e and out[d] = sum of e_new over the edges into d.
+    ``weights``: packed [C, 3C] + (n_layers - 1) x [C, C] of the compute dtype; ``biases``: fp32 [n_layers, C]."""
+    _need_cuda(x_src, x_dst, e, weights, biases, gamma, beta, out)
+    E, C, lde = _rows(e)
+    ns, Cs, lds = _rows(x_src)
+    nd, Cd, ldd = _rows(x_dst)
+    dt = e.dtype
+    if Cs != C or Cd != C or E != csr.n_edges or nd != csr.n_dst or x_src.dtype != dt or x_dst.dtype != dt or weights.dtype != dt:
+        raise ValueError("graphconv_fused: operand mismatch")
+    if weights.numel() != (n_layers + 2) * C * C or not weights.is_contiguous() or biases.numel() != n_layers * C or biases.dtype != torch.float32:
+        raise ValueError("graphconv_fused: packed weights / biases do not match n_layers and C")
+    e_new = torch.empty((E, C), dtype=dt, device=e.device)
+    if out is None:
+        out = torch.empty((csr.n_dst, C), dtype=dt, device=e.device)
+    no, Co, ldo = _rows(out)
+    if (no, Co) != (csr.n_dst, C) or out.dtype != dt:
+        raise ValueError("graphconv_fused: output mismatch")
+    with _Timed("graphconv_fused", 2.0 * (n_layers + 2) * C * C * E, _nbytes(e, e_new, out) + 12.0 * E):
+        rc = _lib.load().anemoi_b200_graphconv_fused(
+            _ptr(x_src), lds, _ptr(x_dst), ldd, _ptr(e), lde, _ptr(weights), _ptr(biases.contiguous()), n_layers, _ptr(_f32(gamma)), _ptr(_f32(beta)),
+            _ptr(e_new), C, _ptr(csr.src32), _ptr(csr.dst32), _ptr(csr.colptr32), _ptr(out), ldo, csr.n_dst, E, C, float(eps), dtype_code(dt),
+            _stream())  # fmt: skip
+    _lib.check(rc, "anemoi_b200_graphconv_fused")
     return e_new, out
 
 

@@ -157,6 +157,24 @@ ANEMOI_API int anemoi_b200_graphconv_ln_aggregate(const void* h, int64_t ldh, co
                                        void* e_new, int64_t ldn, const int32_t* colptr32, void* out, int64_t ldo, int64_t n_dst,
                                        int64_t C, float eps, int dtype, void* stream);
 
+/* -- GraphConv, the whole operator as ONE kernel (north star: fused edge-gather -> edge-MLP -> segmented scatter-reduce) ------------
+ * Replaces layers/conv.py:66-81 end to end for C in {16, 32, 64}, the widths at which the operator is HBM-bound:
+ *   e_new[i] = LayerNorm(edge_mlp([x_dst[dst_i] ; x_src[src_i] ; e[i]])) + e[i],   out[d] = sum of e_new over the edges into d,
+ * edge_mlp = Linear(3C, C), GELU, (Linear(C, C), GELU) x (n_layers - 2), Linear(C, C)   (layers/mlp.py:96-170 with the plain "mlp"
+ * implementation and the exact-erf GELU).  Per tile of 128 consecutive dst-sorted edges the operand rows are gathered into shared
+ * memory (cp.async, one tile ahead), the layers run on mma.sync (bf16; hidden activations stay in registers) or FFMA (fp32 parity mode)
+ * against weights resident in shared memory, LayerNorm + residual are applied in place and the destination sums are formed from the tile
+ * (fp32, edge order, no atomics).  No intermediate tensor touches HBM.
+ *   x_src [n_src, lds], x_dst [n_dst, ldd], e / e_new [n_edges, lde / ldn], out [n_dst, ldo] of `dtype`, 16-byte aligned rows;
+ *   weights : `dtype`, packed [C, 3C] row-major followed by (n_layers - 1) x [C, C];  biases : fp32 [n_layers, C] (zeros where a layer
+ *   has none);  gamma / beta : fp32 [C] or NULL;  src32 / dst32 / colptr32 from anemoi_b200_csr_build.
+ * Returns -3 (use anemoi_b200_linear + anemoi_b200_graphconv_ln_aggregate) for other widths, layer counts or alignments.
+ */
+ANEMOI_API int anemoi_b200_graphconv_fused(const void* x_src, int64_t lds, const void* x_dst, int64_t ldd, const void* e, int64_t lde,
+                                const void* weights, const float* biases, int64_t n_layers, const float* gamma, const float* beta, void* e_new,
+                                int64_t ldn, const int32_t* src32, const int32_t* dst32, const int32_t* colptr32, void* out, int64_t ldo,
+                                int64_t n_dst, int64_t n_edges, int64_t C, float eps, int dtype, void* stream);
+
 /* -- backward of the fused ops (training) -------------------------------------------------------------------------
  * gt_attention_bwd replaces triton/gt.py:182-376 / :451-556 for the materialised-e form (1) of anemoi_b200_gt_attention_fwd: given the
  * forward's out [n_dst, ldo] (the attention result, without `add`) and lse [n_dst, heads] (natural-log softmax normaliser, written by the

@@ -108,3 +108,34 @@ if "gc" in which:
         alg = 3 * E * C * 2 + N * C * 2 + 4 * N
         print(json.dumps({"kernel": f"graphconv_ln_aggregate C={C} (E={E})", "us_median": round(med, 1), "us_min": round(mn, 1), "alg_MB": round(alg / 1e6, 1),
                           "GBs": round(alg / med / 1e3, 1), "frac_hbm_measured": round(alg / med / 1e3 / pk["hbm_gbs"], 3)}))  # fmt: skip
+
+if "gcf" in which:
+    # The one-kernel GraphConv (csrc/graphconv_fused.cu) at the widths where the operator is HBM-bound, on a graph large enough to time:
+    # 1 M nodes, 8 M dst-sorted edges with local sources (|src - dst| < 4096: the gathered rows are L2 hits, as on a mesh).  Algorithmic
+    # bytes: e read + e' written (2 E C b), src / dst ids (8 E), x read once + out written (2 N C b).  The decomposed form (2 node GEMMs + 3
+    # edge GEMMs + LN/aggregate tail, the path wider layers take) on the same inputs is timed beside it.
+    from anemoi_core_b200.layers.conv import GraphConv
+    from anemoi_core_b200.layers.utils import load_layer_kernels
+
+    n, deg = 1 << 20, 8
+    E = n * deg
+    dst = torch.arange(n).repeat_interleave(deg)
+    src = (dst + torch.randint(-4096, 4096, (E,), generator=g)).clamp_(0, n - 1)
+    ei = torch.stack([src, dst]).to(dev)
+    for C in [int(c) for c in os.environ.get("GCF_C", "16,32,64").split(",")]:
+        torch.manual_seed(C)
+        conv = GraphConv(C, C, layer_kernels=load_layer_kernels(None)).eval().to(dev)
+        x = torch.randn(n, C, generator=g).to(torch.bfloat16).to(dev)
+        e = torch.randn(E, C, generator=g).to(torch.bfloat16).to(dev)
+        with torch.no_grad():
+            os.environ["ANEMOI_B200_GC_FUSED"] = "1"
+            med, mn = timeit(lambda: conv(x, e, ei))
+            os.environ["ANEMOI_B200_GC_FUSED"] = "0"
+            dmed, _ = timeit(lambda: conv(x, e, ei)) if "nodecomp" not in which else (0.0, 0.0)
+            os.environ["ANEMOI_B200_GC_FUSED"] = "1"
+        alg = 2 * E * C * 2 + 8 * E + 2 * n * C * 2 + 4 * n
+        print(json.dumps({"kernel": f"graphconv_fused C={C} (N={n}, E={E}, 3 layers, bf16)", "us_median": round(med, 1), "us_min": round(mn, 1),
+                          "alg_MB": round(alg / 1e6, 1), "GBs": round(alg / med / 1e3, 1), "frac_hbm_measured": round(alg / med / 1e3 / pk["hbm_gbs"], 3),
+                          "frac_hbm_8TBs": round(alg / med / 1e3 / 8000.0, 3), "GFLOP": round(10.0 * C * C * E / 1e9, 1),
+                          "TFLOPs": round(10.0 * C * C * E / med / 1e6, 1), "decomposed_us": round(dmed, 1)}))  # fmt: skip
+        del x, e, conv

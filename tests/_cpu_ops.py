@@ -153,6 +153,20 @@ def graphconv_ln_aggregate(h, weight, bias, e, csr, eps=1e-5, out=None):
     return e_new, agg
 
 
+def graphconv_fused(x_src, x_dst, e, weights, biases, n_layers, gamma, beta, csr, eps=1e-5, out=None):
+    C = e.shape[1]
+    w = weights.float()
+    h = torch.cat([x_dst.float()[csr.dst32.long()], x_src.float()[csr.src32.long()], e.float()], 1)
+    off = 0
+    for l in range(n_layers):
+        k = 3 * C if l == 0 else C
+        h = h @ w[off : off + C * k].reshape(C, k).t() + biases.reshape(n_layers, C)[l]
+        off += C * k
+        if l + 1 < n_layers:
+            h = F.gelu(h)
+    return graphconv_ln_aggregate(h.to(e.dtype), gamma, beta, e, csr, eps, out)
+
+
 def cast_pad(x, dtype, k_pad=None, idx=None, out=None):
     src = x if idx is None else x[idx.long()]
     k_pad = src.shape[1] if k_pad is None else k_pad
@@ -206,7 +220,7 @@ def install() -> None:
     import anemoi_core_b200.layers._functional as Fn
     from anemoi_core_b200 import ops
 
-    for name in ("build_csr", "linear", "layer_norm", "row_stats", "gt_attention", "graphconv_ln_aggregate", "cast_pad", "add", "partial_stats_buffer",
+    for name in ("build_csr", "linear", "layer_norm", "row_stats", "gt_attention", "graphconv_ln_aggregate", "graphconv_fused", "cast_pad", "add", "partial_stats_buffer",
                  "assemble_input", "assemble_output", "glu_combine", "cond_layer_norm"):
         setattr(ops, name, globals()[name])
     ops.attention_tiles = lambda csr: None  # the tile plan only feeds the CUDA kernel

@@ -73,6 +73,24 @@ class GeluFn(Function):
         return ops.gelu(x, dy if dy.stride(1) == 1 else dy.contiguous())
 
 
+class GluCombineFn(Function):
+    """``act(gv[:, :H]) * gv[:, H:]`` of the gated feed-forward layers (layers/mlp.py:38-53)."""
+
+    @staticmethod
+    def forward(ctx, gv: Tensor, act: str) -> Tensor:
+        gv = gv.detach()
+        gv = gv if gv.stride(1) == 1 else gv.contiguous()
+        ctx.save_for_backward(gv)
+        ctx.act = act
+        return ops.glu_combine(gv, act)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        (gv,) = ctx.saved_tensors
+        dy = dy.to(gv.dtype)
+        return ops.glu_combine_bwd(gv, dy if dy.stride(1) == 1 else dy.contiguous(), ctx.act), None
+
+
 class LayerNormFn(Function):
     """LayerNorm over ``groups`` groups of the last dimension (weight / bias [C] | None), output in ``dt``."""
 
@@ -150,6 +168,10 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], dt: torch.dtype, g
 
 def layer_norm(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], eps: float, dt: torch.dtype, groups: int = 1) -> Tensor:
     return LayerNormFn.apply(x, weight, bias, eps, groups, dt)
+
+
+def glu_combine(gv: Tensor, act: str) -> Tensor:
+    return GluCombineFn.apply(gv, act)
 
 
 def gt_attention(q: Tensor, k: Tensor, v: Tensor, e: Optional[Tensor], csr: ops.GraphCSR, heads: int) -> Tensor:

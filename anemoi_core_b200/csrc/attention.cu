@@ -324,6 +324,8 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
   constexpr int kSlotBytes = 2 * kKV + (MODE == 2 ? 64 : kKV);             // k | v | attributes-or-e
   static_assert(kSlots > kPBatch, "ring must be deeper than a batch");
   extern __shared__ __align__(16) uint8_t smem_ring[];
+  pdl_wait();  // PDL (common.cuh): q | k | v come from the GEMM just before
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const bool active = lane < active_lanes;
   const int lane_eff = active ? lane : 0;
@@ -670,7 +672,8 @@ static int launch_pipe_mode(const AttnParams& p, int n_slabs, int active_lanes, 
   const int64_t max_useful = (p.n_dst * n_slabs + 3) / 4;
   if (blocks > max_useful) blocks = max_useful;
   while ((blocks * 4) % n_slabs) ++blocks;
-  gt_attention_pipe_kernel<T, NCH, LPH, MODE><<<(unsigned)blocks, 128, smem, s>>>(p, n_slabs, active_lanes);
+  cudaError_t le = launch_pdl(gt_attention_pipe_kernel<T, NCH, LPH, MODE>, dim3((unsigned)blocks), dim3(128), smem, s, p, n_slabs, active_lanes);
+  if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(gt_attention_pipe_kernel)");
   return launch_status("gt_attention_pipe_kernel");
 }
 

@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/anemoi_b200.h"
 
@@ -55,6 +56,35 @@ inline int num_sms() {
     if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0) n[dev] = 148;  // B200
   }
   return n[dev];
+}
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (become resident, run its prologue: barrier init,
+// TMEM allocation, descriptor prefetch, index arithmetic) while its predecessor in the stream is still draining; griddepcontrol.wait then
+// blocks until the predecessor has COMPLETED and its writes are visible, so everything that touches global memory sits after it.  Each
+// kernel triggers its own dependents right after its wait (at most one kernel runs ahead).  Both instructions are no-ops for a kernel
+// launched without the attribute, and the attribute is captured into CUDA graphs as a programmatic edge.  ANEMOI_B200_PDL=0 turns the
+// attribute off (A/B).  What it hides: ~2-3 us of launch latency + prologue per launch, 109 launches per cfg2 step, ~180 per 8-GPU step.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ANEMOI_B200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+// <<<grid, block, smem, stream>>> with the PDL attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ---- dtype helpers -------------------------------------------------------------------------------------------

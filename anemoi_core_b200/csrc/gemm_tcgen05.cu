@@ -661,6 +661,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // PDL: everything above (descriptor prefetch, barrier init, TMEM allocation, cluster sync) may overlap the predecessor's tail; from here
+  // on global memory is read (operands, bias, residual) and written
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (ctrl == 0) {
     if (lane == 0) {
@@ -904,10 +908,12 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensor
   int grid = (int)(tiles * CG < sms ? tiles * CG : sms);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = Cfg::kSmemBytes, cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr, cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CG>, tmA, tmW, tmOut, tmRes, num_kb, tiles_m, tiles_n, epi_mode, ep);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_bf16_tcgen05_kernel)");
   return launch_status("gemm_bf16_tcgen05_kernel");

@@ -117,6 +117,8 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const TI* __restrict__ x
 // 2.6 TB/s on the [40 962, 512] residual stream (16 us x 39 launches = 7 % of a cfg2 step); this one is bound by the read.
 __global__ void __launch_bounds__(256) row_stats_stream_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float2* __restrict__ stats, int64_t M,
                                                                int C, float eps) {
+  pdl_wait();  // PDL (common.cuh): x comes from the GEMM just before
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, sub = lane & 7, rw = lane >> 3;
   const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int chunks = C >> 3;  // 16-byte chunks per row; lane `sub` takes chunks sub, sub + 8, ...
@@ -348,7 +350,9 @@ extern "C" int anemoi_b200_row_stats(const void* x, int64_t ldx, int x_dtype, fl
   if (x_dtype == ANEMOI_BF16 && C % 64 == 0) {
     int64_t b2 = (M + 31) / 32;  // 4 rows per warp, 8 warps per block
     if (b2 > cap) b2 = cap;
-    row_stats_stream_kernel<<<(unsigned)b2, 256, 0, s>>>((const __nv_bfloat16*)x, ldx, reinterpret_cast<float2*>(stats), M, (int)C, eps);
+    cudaError_t le = launch_pdl(row_stats_stream_kernel, dim3((unsigned)b2), dim3(256), 0, s, (const __nv_bfloat16*)x, ldx, reinterpret_cast<float2*>(stats),
+                                M, (int)C, eps);
+    if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(row_stats_stream_kernel)");
     return launch_status("row_stats_stream_kernel");
   }
 #define RS_LAUNCH(T, IT) row_stats_kernel<T, IT><<<(unsigned)blocks, 256, 0, s>>>((const T*)x, ldx, reinterpret_cast<float2*>(stats), M, (int)C, eps)

@@ -129,6 +129,36 @@ __global__ void glu_combine_kernel(const T* __restrict__ in, int64_t ldi, T* __r
   }
 }
 
+// Backward of glu_combine: for y = act(g) * v with the cotangent dy,  din[:, :H] = dy * v * act'(g)  and  din[:, H:] = dy * act(g)
+// (the gradient of the [gate | value] GEMM output; PyTorch autograd of layers/mlp.py:38-53 in the reference).  fp32 math, one rounding.
+template <typename T>
+__global__ void glu_combine_bwd_kernel(const T* __restrict__ in, int64_t ldi, const T* __restrict__ dy, int64_t lddy, T* __restrict__ din, int64_t ldd,
+                                       int64_t M, int64_t H, int act) {
+  const int64_t total = M * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / H, c = i - m * H;
+    const float g = to_f32<T>(in[m * ldi + c]), v = to_f32<T>(in[m * ldi + H + c]), d = to_f32<T>(dy[m * lddy + c]);
+    float a, da;
+    if (act == 0) {
+      a = 1.0f / (1.0f + __expf(-g));
+      da = a * (1.0f - a);
+    } else if (act == 1) {
+      const float sg = 1.0f / (1.0f + __expf(-g));
+      a = g * sg;
+      da = sg * (1.0f + g * (1.0f - sg));
+    } else if (act == 2) {
+      const float cdf = 0.5f * (1.0f + erff(g * 0.70710678118654752440f));
+      a = g * cdf;
+      da = cdf + g * 0.3989422804014327f * __expf(-0.5f * g * g);
+    } else {
+      a = fmaxf(g, 0.f);
+      da = g > 0.f ? 1.0f : 0.f;
+    }
+    din[m * ldd + c] = from_f32<T>(d * v * da);
+    din[m * ldd + H + c] = from_f32<T>(d * a);
+  }
+}
+
 // ---- model glue either side of the encoder / decoder ------------------------------------------------------
 // assemble_input: out[(b e g), t * V + v] = x[b, t, e, g, v];  out[(b e g), T * V + a] = attrs[row % attr_rows, a];  zero pad up to Kpad.
 // Replaces einops.rearrange + torch.cat (+ the autocast cast of the embedding Linear) of `_assemble_input`
@@ -202,6 +232,24 @@ extern "C" int anemoi_b200_glu_combine(const void* in, int64_t ldi, void* out, i
     else glu_combine_kernel<float, 1><<<(unsigned)blocks, 256, 0, s>>>((const float*)in, ldi, (float*)out, ldo, M, H, act);
   }
   return launch_status("glu_combine_kernel");
+}
+
+extern "C" int anemoi_b200_glu_combine_bwd(const void* in, int64_t ldi, const void* dy, int64_t lddy, void* din, int64_t ldd, int64_t M, int64_t H,
+                                          int act, int dtype, void* stream) {
+  ANEMOI_CHECK_ARG(M >= 0 && H >= 1 && ldi >= 2 * H && lddy >= H && ldd >= 2 * H, "glu_combine_bwd: bad shape");
+  ANEMOI_CHECK_ARG(act >= 0 && act <= 3, "glu_combine_bwd: activation code %d (0 sigmoid, 1 silu, 2 gelu, 3 relu)", act);
+  ANEMOI_CHECK_ARG(dtype == ANEMOI_F32 || dtype == ANEMOI_BF16, "glu_combine_bwd: bad dtype %d", dtype);
+  if (M == 0) return 0;
+  ANEMOI_CHECK_ARG(in && dy && din, "glu_combine_bwd: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t blocks = (M * H + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+  if (dtype == ANEMOI_BF16)
+    glu_combine_bwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)in, ldi, (const __nv_bfloat16*)dy, lddy,
+                                                                            (__nv_bfloat16*)din, ldd, M, H, act);
+  else
+    glu_combine_bwd_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const float*)in, ldi, (const float*)dy, lddy, (float*)din, ldd, M, H, act);
+  return launch_status("glu_combine_bwd_kernel");
 }
 
 extern "C" int anemoi_b200_assemble_input(const float* x, int64_t B, int64_t T, int64_t E, int64_t G, int64_t V, const float* attrs, int64_t A,

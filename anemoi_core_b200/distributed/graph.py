@@ -221,6 +221,21 @@ class HaloExchangeFn(torch.autograd.Function):
         return d_local, None
 
 
+class AllToAllFn(torch.autograd.Function):
+    """Variable-size all-to-all of row blocks (``_exchange``); backward: the same exchange with the split lists swapped.  The differentiable
+    half of the heads (Ulysses) strategy's two exchanges (reference distributed/graph.py: ``shard_heads`` / ``shard_sequence`` pairs)."""
+
+    @staticmethod
+    def forward(ctx, send: Tensor, in_splits: list, out_splits: list, group) -> Tensor:
+        ctx.meta = (list(in_splits), list(out_splits), group)
+        return _exchange(send.detach().contiguous(), list(in_splits), list(out_splits), group)
+
+    @staticmethod
+    def backward(ctx, d_out: Tensor):
+        in_splits, out_splits, group = ctx.meta
+        return _exchange(d_out.contiguous(), out_splits, in_splits, group), None, None, None
+
+
 def gather_rows_grad(x: Tensor, sizes: Optional[list[int]], group) -> Tensor:
     """Differentiable ``gather_rows``."""
     if group_size(group) == 1:

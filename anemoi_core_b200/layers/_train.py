@@ -6,8 +6,11 @@ Taken whenever gradients are needed (``wants_grad``); the inference path under `
 into the GEMMs, lin_edge folded into attention, packed weights), which have no backward.  On a model-parallel group the "edges" strategy
 trains through the autograd halves of the exchange (``distributed.graph.HaloExchangeFn`` / ``GatherRowsFn``; reference
 distributed/graph.py:227-500): the forward collective is NCCL, the backward its transpose; parameter gradients are per-rank partial sums
-(the trainer's gradient all-reduce over the model group completes them, as in the reference).  Not implemented (NotImplementedError with
-the reason): the heads strategy, gated MLP variants and ConditionalLayerNorm in training.
+(the trainer's gradient all-reduce over the model group completes them, as in the reference).  Gated feed-forward layers train through
+``AG.glu_combine`` (one GEMM on the gate | value weights, as in the forward); a ConditionalLayerNorm is the affine-free LayerNorm kernel
+followed by the two small conditioning Linears and an elementwise scale / shift in PyTorch (the per-row scale / bias ARE materialised in
+training, as they are in the reference).  The heads (Ulysses) strategy trains through ``distributed.graph.AllToAllFn`` (the two exchanges of
+block.py:689-759; backward = the same all-to-all with the split lists swapped).
 """
 
 from __future__ import annotations
@@ -44,7 +47,17 @@ def _plain_ln(ln: nn.Module) -> None:
     _check_plain_layernorm(ln)
 
 
-def norm(ln: nn.Module, x: Tensor, dt: torch.dtype, groups: int = 1) -> Tensor:
+def norm(ln: nn.Module, x: Tensor, dt: torch.dtype, groups: int = 1, cond: Optional[Tensor] = None) -> Tensor:
+    from .normalization import ConditionalLayerNorm
+
+    if isinstance(ln, ConditionalLayerNorm):  # LN(x) * (1 + scale(cond)) + bias(cond)   (normalization.py:34-94)
+        if cond is None:
+            raise ValueError("ConditionalLayerNorm needs the conditioning tensor (cond=...)")
+        xn = AG.layer_norm(x, None, None, ln.eps, torch.float32, groups)
+        c = cond.reshape(-1, cond.shape[-1]).float()
+        scale = AG.linear(c, ln.scale.weight, ln.scale.bias, torch.float32)
+        shift = AG.linear(c, ln.bias.weight, ln.bias.bias, torch.float32)
+        return (xn * (1.0 + scale) + shift).to(dt)
     _plain_ln(ln)
     return AG.layer_norm(x, ln.weight, getattr(ln, "bias", None), ln.eps, dt, groups)
 
@@ -61,23 +74,25 @@ def lin_cat(layers, x: Tensor, dt: torch.dtype) -> Tensor:
     return AG.linear(x, w, b, dt)
 
 
-def mlp(m, x: Tensor, dt: torch.dtype, residual: Optional[Tensor] = None, pre_ln: Optional[nn.Module] = None) -> Tensor:
-    """``MLP.run`` with autograd: Linear(+GELU) chain, optional trailing LayerNorm, optional residual."""
+def mlp(m, x: Tensor, dt: torch.dtype, residual: Optional[Tensor] = None, pre_ln: Optional[nn.Module] = None, cond: Optional[Tensor] = None) -> Tensor:
+    """``MLP.run`` with autograd: Linear(+GELU) / gated-layer chain, optional trailing LayerNorm, optional residual."""
     from .mlp import GatedMLPLayer
 
     if pre_ln is not None:
-        x = norm(pre_ln, x, dt)
+        x = norm(pre_ln, x, dt, cond=cond)
     mods = list(m.mlp)
     i = 0
     while i < len(mods):
         layer = mods[i]
-        if isinstance(layer, GatedMLPLayer):
-            raise NotImplementedError("training with gated MLP variants (glu / swiglu / geglu / reglu): backward of glu_combine is not implemented")
-        act = i + 1 < len(mods) and not hasattr(mods[i + 1], "weight")
+        if isinstance(layer, GatedMLPLayer):  # act(gate_proj(x)) * value_proj(x): one GEMM on the concatenated weights, then the gating
+            x = AG.glu_combine(lin_cat([layer.gate_proj, layer.value_proj], x, dt), layer.kind)
+            i += 1
+            continue
+        act = i + 1 < len(mods) and not hasattr(mods[i + 1], "weight") and not isinstance(mods[i + 1], GatedMLPLayer)
         x = lin(layer, x, dt, gelu=act)
         i += 2 if act else 1
     if m.layer_norm is not None:
-        x = norm(m.layer_norm, x, dt)
+        x = norm(m.layer_norm, x, dt, cond=cond)
     return x if residual is None else x + residual.to(x.dtype)
 
 
@@ -90,19 +105,32 @@ def graph_conv(conv, x_src: Tensor, x_dst: Tensor, e: Tensor, csr, dt: torch.dty
 
     m = conv.edge_mlp
     mods = list(m.mlp)
-    if isinstance(mods[0], GatedMLPLayer) or m.layer_norm is None:
-        raise NotImplementedError("training GraphConv with a gated edge MLP / without its LayerNorm")
+    if m.layer_norm is None:
+        raise NotImplementedError("training GraphConv without the LayerNorm of its edge MLP")
     C = conv.in_channels
-    w1, b1 = mods[0].weight, mods[0].bias
+    gated0 = isinstance(mods[0], GatedMLPLayer)
+    if gated0:  # gate | value rows of the first layer as one weight: the split over [x_i ; x_j ; e] applies to both
+        firsts = [mods[0].gate_proj, mods[0].value_proj]
+        w1 = torch.cat([l.weight for l in firsts], 0)
+        bs = [l.bias for l in firsts]
+        b1 = None if all(b is None for b in bs) else torch.cat([b if b is not None else torch.zeros(l.weight.shape[0], device=w1.device) for b, l in zip(bs, firsts)])
+    else:
+        w1, b1 = mods[0].weight, mods[0].bias
     e = e.to(dt)
     z = AG.linear(e, w1[:, 2 * C :], b1, dt)
     p_i = AG.linear(x_dst, w1[:, :C], None, dt)
     p_j = AG.linear(x_src, w1[:, C : 2 * C], None, dt)
     z = z + p_i.index_select(0, csr.dst32.long()) + p_j.index_select(0, csr.src32.long())
-    h = AG.GeluFn.apply(z)
-    i = 2
+    if gated0:
+        h, i = AG.glu_combine(z, mods[0].kind), 1
+    else:
+        h, i = AG.GeluFn.apply(z), 2
     while i < len(mods):
-        act = i + 1 < len(mods) and not hasattr(mods[i + 1], "weight")
+        if isinstance(mods[i], GatedMLPLayer):
+            h = AG.glu_combine(lin_cat([mods[i].gate_proj, mods[i].value_proj], h, dt), mods[i].kind)
+            i += 1
+            continue
+        act = i + 1 < len(mods) and not hasattr(mods[i + 1], "weight") and not isinstance(mods[i + 1], GatedMLPLayer)
         h = lin(mods[i], h, dt, gelu=act)
         i += 2 if act else 1
     ln = m.layer_norm
@@ -133,19 +161,19 @@ def gnn_block(block, x_src: Tensor, x_dst: Tensor, edge_attr: Tensor, edge_index
 # GraphTransformer
 # ------------------------------------------------------------------------------------------------------------
 def gt_block(block, x_src: Optional[Tensor], x_dst: Tensor, edge_attr: Tensor, edge_index: Tensor, dt: torch.dtype, ln_src: Optional[nn.Module],
-             cond=None, plan=None) -> Tensor:  # fmt: skip
+             cond=None, plan=None, heads=None) -> Tensor:  # fmt: skip
     """GraphTransformerProcessorBlock (``x_src is None``: block.py:1219-1273) / GraphTransformerMapperBlock (block.py:963-1029) forward with the
     materialised edge projection (the reference's own formulation, block.py:623-635 + conv.py:103-147); returns the new dst rows."""
-    if cond is not None:
-        raise NotImplementedError("training with ConditionalLayerNorm conditioning: its backward is not implemented")
+    # ConditionalLayerNorm kernels: the processor block takes one conditioning tensor, the mapper block a (cond_src, cond_dst) pair
+    cond_src, cond_dst = (cond if isinstance(cond, (tuple, list)) else (cond, cond)) if cond is not None else (None, None)
     A, H = block.attn_channels, block.num_heads
-    xd_n = norm(block.layer_norm_attention, x_dst, dt)
+    xd_n = norm(block.layer_norm_attention if x_src is None else block.layer_norm_attention_dest, x_dst, dt, cond=cond_dst)
     if x_src is None:
         buf = lin_cat([block.lin_query, block.lin_key, block.lin_value, block.lin_self], xd_n, dt)
         q, k, v, x_r = buf[:, :A], buf[:, A : 2 * A], buf[:, 2 * A : 3 * A], buf[:, 3 * A :]
         n_src = x_dst.shape[0]
     else:
-        xs_n = norm(ln_src, x_src, dt)
+        xs_n = norm(ln_src, x_src, dt, cond=cond_src)
         kv = lin_cat([block.lin_key, block.lin_value], xs_n, dt)
         qs = lin_cat([block.lin_query, block.lin_self], xd_n, dt)
         q, x_r, k, v = qs[:, :A], qs[:, A:], kv[:, :A], kv[:, A:]
@@ -166,8 +194,35 @@ def gt_block(block, x_src: Optional[Tensor], x_dst: Tensor, edge_attr: Tensor, e
     if not isinstance(block.edge_pre_mlp, nn.Identity):
         ea = lin(block.edge_pre_mlp[0], ea, torch.float32, gelu=True)
     e = lin(block.lin_edge, ea, dt)
-    csr = Fn.csr_for(edge_index, n_src, x_dst.shape[0])
-    att = AG.gt_attention(q, k, v, e, csr, H)
+    if heads is not None:
+        # model-parallel "heads" (Ulysses) strategy (block.py:689-759): (group, dst row counts, src row counts | None = sources replicated).
+        # One all-to-all gives every rank ALL rows for its H / P heads, attention runs over the FULL edge list for those heads (the edge
+        # projection's columns of those heads), a second all-to-all returns every rank its own rows for all heads.
+        from ..distributed.graph import AllToAllFn
+        from ..distributed.graph import group_rank
+        from ..distributed.graph import group_size
+
+        group, dst_sizes, src_sizes = heads
+        P, me = group_size(group), group_rank(group)
+        if H % P:
+            raise ValueError(f"heads strategy: num_heads ({H}) must be divisible by the model group size ({P})")
+        Hl, Ch = H // P, A // H
+        n_l = x_dst.shape[0]
+
+        def to_heads(t: Tensor, sizes: list) -> Tensor:  # [rows, H * Ch] -> all rows (global order) of my head group [sum(sizes), Hl * Ch]
+            rows = t.shape[0]
+            return AllToAllFn.apply(t.reshape(rows, P, Hl * Ch).permute(1, 0, 2).reshape(P * rows, Hl * Ch), [rows] * P, list(sizes), group)
+
+        mine = slice(me * Hl * Ch, (me + 1) * Hl * Ch)
+        q_h = to_heads(q, dst_sizes)
+        k_h, v_h = (k[:, mine], v[:, mine]) if src_sizes is None else (to_heads(k, src_sizes), to_heads(v, src_sizes))
+        csr = Fn.csr_for(edge_index, k_h.shape[0], sum(dst_sizes))
+        att_h = AG.gt_attention(q_h, k_h.contiguous(), v_h.contiguous(), e[:, mine].contiguous(), csr, Hl)
+        back = AllToAllFn.apply(att_h, list(dst_sizes), [n_l] * P, group)  # [head group (= source rank), local row, Hl * Ch]
+        att = back.reshape(P, n_l, Hl * Ch).permute(1, 0, 2).reshape(n_l, A)
+    else:
+        csr = Fn.csr_for(edge_index, n_src, x_dst.shape[0])
+        att = AG.gt_attention(q, k, v, e, csr, H)
     skip = x_dst.to(dt)
     o = lin(block.projection, att + x_r, dt) + skip
-    return mlp(block.node_dst_mlp, o, dt, residual=o, pre_ln=block.layer_norm_mlp_dst)
+    return mlp(block.node_dst_mlp, o, dt, residual=o, pre_ln=block.layer_norm_mlp_dst, cond=cond_dst)

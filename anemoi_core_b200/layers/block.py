@@ -452,12 +452,13 @@ class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):
             edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, False)
             edge_attr_prepared = None
         if T.wants_grad(self, x, edge_attr):  # differentiable path (layers/_train.py)
-            plan = None
+            plan = heads = None
             if group_size(model_comm_group) > 1:
-                if self.shard_strategy != "edges":
-                    T._single_gpu(model_comm_group, "the heads strategy")
-                plan = halo_plan_for(edge_index, shard_info.nodes, model_comm_group)  # same plan as the inference path (block.py:1120-1183)
-            return T.gt_block(self, None, x, edge_attr, edge_index, dt, None, cond, plan=plan), edge_attr_in
+                if self.shard_strategy == "heads":
+                    heads = (model_comm_group, list(shard_info.nodes), list(shard_info.nodes))
+                else:
+                    plan = halo_plan_for(edge_index, shard_info.nodes, model_comm_group)  # same plan as the inference path (block.py:1120-1183)
+            return T.gt_block(self, None, x, edge_attr, edge_index, dt, None, cond, plan=plan, heads=heads), edge_attr_in
         A = self.attn_channels
         ln = self.layer_norm_attention  # with a ConditionalLayerNorm kernel both LayerNorms of the block take ``cond`` (block.py:1233-1271)
         dst_layers = [self.lin_key, self.lin_value, self.lin_self]
@@ -543,16 +544,16 @@ class GraphTransformerMapperBlock(GraphTransformerBaseBlock):
         cond_src, cond_dst = cond if cond is not None else (None, None)  # (block.py:978-980)
         dt = Fn.compute_dtype(x_src, x_dst)
         if T.wants_grad(self, x_src, x_dst, edge_attr):  # differentiable path (layers/_train.py)
-            plan = None
+            plan = heads = None
             if group_size(model_comm_group) > 1:
-                if self.shard_strategy != "edges":
-                    T._single_gpu(model_comm_group, "the heads strategy")
-                if shard_info is not None and shard_info.src_is_sharded():
+                if self.shard_strategy == "heads":
+                    heads = (model_comm_group, list(shard_info.dst_nodes), list(shard_info.src_nodes) if shard_info.src_is_sharded() else None)
+                elif shard_info is not None and shard_info.src_is_sharded():
                     plan = halo_plan_for(edge_index, shard_info.src_nodes, model_comm_group)
-            dst_new = T.gt_block(self, x_src, x_dst, edge_attr, edge_index, dt, self.layer_norm_attention_src, cond, plan=plan)
+            dst_new = T.gt_block(self, x_src, x_dst, edge_attr, edge_index, dt, self.layer_norm_attention_src, cond, plan=plan, heads=heads)
             src_new = x_src
             if self.update_src_nodes:
-                src_new = T.mlp(self.node_src_mlp, x_src.to(dt), dt, residual=x_src, pre_ln=self.layer_norm_mlp_src)
+                src_new = T.mlp(self.node_src_mlp, x_src.to(dt), dt, residual=x_src, pre_ln=self.layer_norm_mlp_src, cond=cond_src)
             return (src_new, dst_new), edge_attr
         A = self.attn_channels
         if not edges_are_dst_sorted:  # the reference sorts here (block.py:779-782)

@@ -250,11 +250,12 @@ class GraphTransformerProcessor(BaseProcessor):
         n_nodes = sum(shard_info.nodes) if shard_info.nodes_are_sharded() else x.shape[0]
         if T.wants_grad(self, x, edge_attr):  # differentiable path: plain layer loop (layers/_train.py)
             world = group_size(model_comm_group)
-            if world > 1 and self.shard_strategy != "edges":
-                T._single_gpu(model_comm_group, "the heads strategy")
+            heads = world > 1 and self.shard_strategy == "heads"  # attends over the FULL edge list for its heads: nothing to cut
+            if heads and shard_info.edges_are_sharded():
+                raise NotImplementedError("shard_strategy='heads' needs the full dst-sorted edge list (graph provider: get_edges(shard_edges=False))")
             if not shard_info.edges_are_sharded():
                 edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
-                if world > 1:
+                if world > 1 and not heads:
                     edge_attr, edge_index, edge_sizes = _shard_edges_by_dst(edge_attr, edge_index, n_nodes, n_nodes, model_comm_group, relabel_dst=True)
                     shard_info = GraphShardInfo(nodes=shard_info.nodes, edges=edge_sizes)
             elif world > 1:

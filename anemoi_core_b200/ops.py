@@ -661,6 +661,21 @@ def glu_combine(gv: Tensor, act: str) -> Tensor:
     return out
 
 
+def glu_combine_bwd(gv: Tensor, dy: Tensor, act: str) -> Tensor:
+    """Gradient of ``glu_combine`` with respect to ``gv`` = [gate | value] for the cotangent ``dy`` of its output."""
+    _need_cuda(gv, dy)
+    M, W, ldi = _rows(gv)
+    H = W // 2
+    Md, Hd, lddy = _rows(dy)
+    if W % 2 or act not in GLU_ACTS or (Md, Hd) != (M, H) or dy.dtype != gv.dtype:
+        raise ValueError("glu_combine_bwd: operand mismatch")
+    dgv = torch.empty((M, W), dtype=gv.dtype, device=gv.device)
+    with _Timed("glu_combine_bwd", 16.0 * M * H, float(M) * 5 * H * gv.element_size()):
+        rc = _lib.load().anemoi_b200_glu_combine_bwd(_ptr(gv), ldi, _ptr(dy), lddy, _ptr(dgv), W, M, H, GLU_ACTS[act], dtype_code(gv.dtype), _stream())
+    _lib.check(rc, "anemoi_b200_glu_combine_bwd")
+    return dgv
+
+
 def cond_layer_norm(x: Tensor, cond: Tensor, w_scale: Tensor, b_scale: Tensor, w_bias: Tensor, b_bias: Tensor, eps: float = 1e-5,
                     out_dtype: Optional[torch.dtype] = None) -> Tensor:  # fmt: skip
     """``LN(x) * (1 + cond @ w_scale.T + b_scale) + (cond @ w_bias.T + b_bias)`` (reference ConditionalLayerNorm, normalization.py:34-94)."""

@@ -243,6 +243,11 @@ ANEMOI_API int anemoi_b200_add(const void* a, int64_t lda, int a_dtype, const vo
  * the row-concatenated weights.  act: 0 sigmoid, 1 silu, 2 exact-erf gelu, 3 relu.  in : [M, ldi >= 2H], out : [M, ldo >= H], same dtype. */
 ANEMOI_API int anemoi_b200_glu_combine(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t M, int64_t H, int act, int dtype, void* stream);
 
+/* Backward of anemoi_b200_glu_combine (training with the gated MLP variants; PyTorch autograd of layers/mlp.py:38-53 in the reference):
+ * din[m, j] = dy[m, j] * in[m, H + j] * act'(in[m, j]),  din[m, H + j] = dy[m, j] * act(in[m, j]).  in / din : [M, >= 2H], dy : [M, >= H]. */
+ANEMOI_API int anemoi_b200_glu_combine_bwd(const void* in, int64_t ldi, const void* dy, int64_t lddy, void* din, int64_t ldd, int64_t M, int64_t H,
+                                           int act, int dtype, void* stream);
+
 /* -- model glue either side of the path -------------------------------------------------
  * Replaces `_assemble_input` (models/encoder_processor_decoder.py:98-127): einops.rearrange(x, "batch time ensemble grid vars ->
  * (batch ensemble grid) (time vars)") + torch.cat with the node attributes (+ the autocast cast in front of the embedding Linear).

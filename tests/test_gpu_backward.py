@@ -236,3 +236,83 @@ def test_training_step_bf16_autocast_cfg2_width():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
         if sd[n].grad.norm().item() > 1e-3 * big:  # (gradients that vanish by construction, e.g. lin_key.bias, only hold rounding noise)
             assert l2(p.grad, sd[n].grad) <= 1e-1, (n, l2(p.grad, sd[n].grad))
+
+
+# ---- round 2: gated feed-forward variants and ConditionalLayerNorm in training (tests/golden/grads_r2.pt, oracle/gen_grad_golden_r2.py) ----
+@pytest.mark.parametrize("name", ["gt_processor_glu", "gt_processor_swiglu", "gt_processor_geglu", "gt_processor_reglu", "gnn_processor_swiglu",
+                                  "gnn_processor_geglu"])  # fmt: skip
+def test_gated_mlp_gradients_match_reference(golden, name):
+    from anemoi_core_b200.layers import GNNProcessor
+    from anemoi_core_b200.layers import GraphTransformerProcessor
+
+    c = golden("grads_r2")[name]
+    m = (GNNProcessor if name.startswith("gnn") else GraphTransformerProcessor)(**c["cfg"])
+    m.load_state_dict(c["sd"], strict=True)
+    m = m.cuda().train()
+    x, ea = c["x"].cuda().requires_grad_(), c["edge_attr"].cuda().requires_grad_()
+    y = m(x, 1, shard1(x.shape[0]), ea, c["edge_index"].cuda())
+    close(y, c["y"], f"{name} forward")
+    (y * c["w"].cuda()).sum().backward()
+    close(x.grad, c["grads"]["x"], f"{name} dx")
+    close(ea.grad, c["grads"]["edge_attr"], f"{name} dedge_attr")
+    check_grads(m, c["grads"], name)
+
+
+@pytest.mark.parametrize("act", ["glu", "swiglu", "geglu", "reglu"])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_glu_combine_backward_kernel(act, dt):
+    from anemoi_core_b200 import autograd as AG
+
+    g = torch.Generator().manual_seed(5)
+    M, H = 333, 96
+    gv = torch.randn(M, 2 * H, generator=g).to(dt)
+    w = torch.randn(M, H, generator=g).to(dt)
+    fn = {"glu": torch.sigmoid, "swiglu": torch.nn.functional.silu, "geglu": torch.nn.functional.gelu, "reglu": torch.relu}[act]
+    ref_in = gv.float().clone().requires_grad_()
+    (fn(ref_in[:, :H]) * ref_in[:, H:] * w.float()).sum().backward()
+    x = gv.detach().clone().cuda().requires_grad_()
+    (AG.glu_combine(x, act).float() * w.cuda().float()).sum().backward()
+    tol = 2e-5 if dt == torch.float32 else 2**-6
+    assert (x.grad.float().cpu() - ref_in.grad).abs().max().item() <= tol * ref_in.grad.abs().max().item()
+
+
+def _cond_kernels(dc):
+    return {"LayerNorm": {"_target_": "anemoi_core_b200.layers.normalization.ConditionalLayerNorm", "condition_shape": dc, "zero_init": False}}
+
+
+def test_conditional_layer_norm_processor_gradients_match_reference(golden):
+    from anemoi_core_b200.layers import GraphTransformerProcessor
+
+    c = golden("grads_r2")["gt_processor_condln"]
+    m = GraphTransformerProcessor(layer_kernels=_cond_kernels(c["condition_shape"]), **c["cfg"])
+    m.load_state_dict(c["sd"], strict=True)
+    m = m.cuda().train()
+    x, ea, cond = (c[k].cuda().requires_grad_() for k in ("x", "edge_attr", "cond"))
+    y = m(x, 1, shard1(), ea, c["edge_index"].cuda(), cond=cond)
+    close(y, c["y"], "condln forward")
+    (y * c["w"].cuda()).sum().backward()
+    for k, t in (("x", x), ("edge_attr", ea), ("cond", cond)):
+        close(t.grad, c["grads"][k], f"condln d{k}")
+    check_grads(m, c["grads"], "condln processor")
+
+
+def test_conditional_layer_norm_mapper_gradients_match_reference(golden):
+    from anemoi_core_b200.distributed.shapes import BipartiteGraphShardInfo
+    from anemoi_core_b200.layers import GraphTransformerForwardMapper
+
+    c = golden("grads_r2")["gt_forward_mapper_condln"]
+    m = GraphTransformerForwardMapper(layer_kernels=_cond_kernels(c["condition_shape"]), **c["cfg"])
+    m.load_state_dict(c["sd"], strict=True)
+    m = m.cuda().train()
+    xs, xd, ea, cs, cd = (c[k].cuda().requires_grad_() for k in ("x_src", "x_dst", "edge_attr", "cond_src", "cond_dst"))
+    out = m((xs, xd), 1, BipartiteGraphShardInfo(), ea, c["edge_index"].cuda(), cond=(cs, cd))
+    ys = [out[1], out[0]]
+    for y, yr in zip(ys, c["y"]):
+        close(y, yr, "condln mapper forward")
+    sum((y * w.cuda()).sum() for y, w in zip(ys, c["w"])).backward()
+    for k, t in (("x_src", xs), ("x_dst", xd), ("edge_attr", ea), ("cond_src", cs), ("cond_dst", cd)):
+        if c["grads"][k] is None:
+            assert t.grad is None or t.grad.abs().max().item() == 0.0
+        else:
+            close(t.grad, c["grads"][k], f"condln mapper d{k}")
+    check_grads(m, c["grads"], "condln mapper")

@@ -112,6 +112,29 @@ def _worker(rank, world, init_file, ret):
             gath = gather_rows(local, sizes, group)
         err = ((gath.float() - full.float()).abs().max() / full.float().abs().max()).item()
         msgs.append(("gt_heads_strategy", "bf16", err, err <= 2e-2))
+        # heads strategy in TRAINING (round 2): one fp32 step of the sharded processor gives the single-GPU gradients (AllToAllFn)
+        torch.manual_seed(3)
+        mh = GraphTransformerProcessor(num_layers=2, num_channels=64, num_chunks=1, num_heads=4, mlp_hidden_ratio=4, edge_dim=gr["edge_dim"],
+                                       shard_strategy="heads", qk_norm=True).cuda().train()  # fmt: skip
+        x0 = torch.randn(n, 64, generator=torch.Generator().manual_seed(4)).cuda()
+        wt = torch.randn(n, 64, generator=torch.Generator().manual_seed(5)).cuda()
+        xf = x0.clone().requires_grad_()
+        (mh(xf, 1, GraphShardInfo(nodes=[n]), ea, ei) * wt).sum().backward()
+        ref_p = {n_: p.grad.clone() for n_, p in mh.named_parameters()}
+        ref_x = xf.grad.clone()
+        mh.zero_grad()
+        xs_ = shard_rows(x0, sizes, group).contiguous().clone().requires_grad_()
+        y_l = mh(xs_, 1, GraphShardInfo(nodes=sizes), ea, ei, group)
+        (y_l * shard_rows(wt, sizes, group)).sum().backward()
+        rx = shard_rows(ref_x, sizes, group)
+        err = ((xs_.grad - rx).abs().max() / rx.abs().max()).item()
+        msgs.append(("train_heads_dx", "fp32", err, err <= 1e-4))
+        worst, big = 0.0, max(g_.abs().max().item() for g_ in ref_p.values())
+        for n_, p in mh.named_parameters():
+            gp = p.grad.clone() if p.grad is not None else torch.zeros_like(p)
+            dist.all_reduce(gp)
+            worst = max(worst, ((gp - ref_p[n_]).abs().max() / max(ref_p[n_].abs().max().item(), 1e-3 * big)).item())
+        msgs.append(("train_heads_dparams", "fp32", worst, worst <= 2e-4))
         P.GNN_HALO = True
         torch.manual_seed(0)
         mg = GNNProcessor(num_channels=128, num_layers=2, num_chunks=1, mlp_extra_layers=0, edge_dim=gr["edge_dim"]).cuda().eval()

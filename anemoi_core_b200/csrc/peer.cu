@@ -41,7 +41,11 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 }
 __device__ __forceinline__ void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
+// All three kernels are PDL launches (common.cuh): they become resident while their predecessor drains and block in griddepcontrol.wait until
+// it has completed - stream order, which the protocol relies on ("my consumers of exchange c-1 are done"), is unchanged.
 __global__ void peer_rendezvous_kernel(PeerCtl* mine, const PeerPtrs pp, int world, int rank) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x;
   const int c = mine->counter + 1;
   if (lane < world && lane != rank) st_release_sys(&reinterpret_cast<PeerCtl*>(pp.ctl[lane])->started[rank], c);
@@ -61,6 +65,8 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const char* __restrict__
                                                         const int32_t* __restrict__ send_off, int64_t dst_ld_bytes, PeerCtl* mine, const PeerPtrs pp,
                                                         int world, int rank) {
   __shared__ int s_off[kMaxPeers + 1];
+  pdl_wait();
+  pdl_launch_dependents();
   if (threadIdx.x <= world) s_off[threadIdx.x] = send_off[threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -88,6 +94,8 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const char* __restrict__
 }
 
 __global__ void halo_wait_kernel(PeerCtl* mine, int world, int rank) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x;
   const int c = mine->counter;
   if (lane < world && lane != rank) {
@@ -151,7 +159,9 @@ extern "C" int anemoi_b200_peer_rendezvous(const uint64_t* ctl_ptrs, int64_t wor
   ANEMOI_CHECK_ARG(ctl_ptrs && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "peer_rendezvous: bad argument");
   PeerPtrs pp;
   fill_ptrs(pp, ctl_ptrs, nullptr, world);
-  peer_rendezvous_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<PeerCtl*>(ctl_ptrs[rank]), pp, (int)world, (int)rank);
+  cudaError_t le = launch_pdl(peer_rendezvous_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, reinterpret_cast<PeerCtl*>(ctl_ptrs[rank]), pp, (int)world,
+                              (int)rank);
+  if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(peer_rendezvous_kernel)");
   return launch_status("peer_rendezvous_kernel");
 }
 
@@ -168,13 +178,15 @@ extern "C" int anemoi_b200_halo_push(const void* rows, int64_t ld_bytes, int64_t
   const int64_t cap = (int64_t)num_sms() * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;  // the signalling block runs even when nothing is sent
-  halo_push_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const char*>(rows), ld_bytes, (int)row_bytes, send_idx, send_off,
-                                                                       dst_ld_bytes, reinterpret_cast<PeerCtl*>(ctl_ptrs[rank]), pp, (int)world, (int)rank);
+  cudaError_t le = launch_pdl(halo_push_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const char*>(rows), ld_bytes,
+                              (int)row_bytes, send_idx, send_off, dst_ld_bytes, reinterpret_cast<PeerCtl*>(ctl_ptrs[rank]), pp, (int)world, (int)rank);
+  if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(halo_push_kernel)");
   return launch_status("halo_push_kernel");
 }
 
 extern "C" int anemoi_b200_halo_wait(const uint64_t* ctl_ptrs, int64_t world, int64_t rank, void* stream) {
   ANEMOI_CHECK_ARG(ctl_ptrs && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "halo_wait: bad argument");
-  halo_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<PeerCtl*>(ctl_ptrs[rank]), (int)world, (int)rank);
+  cudaError_t le = launch_pdl(halo_wait_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, reinterpret_cast<PeerCtl*>(ctl_ptrs[rank]), (int)world, (int)rank);
+  if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(halo_wait_kernel)");
   return launch_status("halo_wait_kernel");
 }

@@ -20,6 +20,7 @@ LIB_PATH = os.environ.get("ANEMOI_B200_LIB") or os.path.join(_HERE, "lib", "liba
 
 F32, BF16 = 0, 1
 EPI_GELU = 1
+EPI_REVERSE = 2
 
 # name -> argtypes (restype is int unless stated).  Must list every symbol of include/anemoi_b200.h
 # (tests/test_abi.py parses the header and checks both directions).
@@ -33,10 +34,10 @@ SIGNATURES = {
                                     c_int64, c_int64, c_int64, c_float, c_void_p],
     "anemoi_b200_linear": [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                            c_int64, c_int, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p],
-    "anemoi_b200_row_stats": [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_float, c_void_p],
+    "anemoi_b200_row_stats": [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_float, c_int, c_void_p],
     "anemoi_b200_gt_attention_fwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                      c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
-                                     c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p],
+                                     c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p],
     "anemoi_b200_gt_attention_bwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                      c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p],

@@ -345,8 +345,10 @@ __global__ void __launch_bounds__(128, ATTN_PIPE_MINBLOCKS) gt_attention_pipe_ke
   // ---- this warp's (slab, dst range) ----
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   const int w = blockIdx.x * (blockDim.x >> 5) + wib;
-  const int slab = w % n_slabs, r = w / n_slabs, R = warps_total / n_slabs;
+  const int slab = w % n_slabs, R = warps_total / n_slabs;
+  int r = w / n_slabs;
   if (r >= R) return;
+  if (p.reverse) r = R - 1 - r;
   const int n_edges = __ldg(p.colptr + p.n_dst);
   const int lo_e = (int)((int64_t)n_edges * r / R), hi_e = (int)((int64_t)n_edges * (r + 1) / R);
   const int n_lo = r == 0 ? 0 : colptr_lower_bound(p.colptr, (int)p.n_dst, lo_e, lane);
@@ -754,7 +756,7 @@ extern "C" int anemoi_b200_gt_attention_fwd(const void* q, int64_t ldq, const vo
                                             int64_t lde_proj, const float* edge_attr, int64_t lde, int64_t edge_dim, const float* w_edge,
                                             int64_t ldw_e, const float* b_edge, const void* qw, int64_t ldqw, void* abar, int64_t ldabar,
                                             int64_t dp, const int32_t* src32, const int32_t* colptr32, const void* add, int64_t ldadd, void* out,
-                                            int64_t ldo, float* lse, int64_t n_dst, int64_t heads, int64_t ch, int dtype, void* stream) {
+                                            int64_t ldo, float* lse, int64_t n_dst, int64_t heads, int64_t ch, int dtype, int flags, void* stream) {
   ANEMOI_CHECK_ARG(n_dst >= 0 && heads >= 1 && ch >= 1, "gt_attention: bad shape");
   ANEMOI_CHECK_ARG(dtype == ANEMOI_F32 || dtype == ANEMOI_BF16, "gt_attention: bad dtype %d", dtype);
   if (n_dst == 0) return 0;
@@ -777,6 +779,7 @@ extern "C" int anemoi_b200_gt_attention_fwd(const void* q, int64_t ldq, const vo
   p.src = src32, p.colptr = colptr32, p.n_dst = n_dst, p.heads = (int)heads, p.ch = (int)ch;
   p.scale = 1.0f / sqrtf((float)ch);
   p.lse = lse;
+  p.reverse = (flags & ANEMOI_EPI_REVERSE) ? 1 : 0;
   const int es = dtype == ANEMOI_BF16 ? 2 : 4;
   auto al = [&](const void* ptr, int64_t ld) { return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * es) % 16 == 0); };
   bool slab_ok = al(q, ldq) && al(k, ldk) && al(v, ldv) && al(e, lde_proj) && al(add, ldadd) && al(out, ldo);

@@ -26,6 +26,7 @@ struct AttnParams {
   int heads, ch;
   float scale;
   float* lse;  // [n_dst, heads] natural-log softmax normaliser (nullable); pipe / generic kernels only
+  int reverse;  // pipe kernel: warps take their dst ranges from the end of the node list (L2 scheduling hint)
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {

@@ -244,10 +244,15 @@ constexpr int kAblMask = kAblNoLoad | kAblNoEpi | kAblNoMma | kAblNoStore | kAbl
 #define ABLK(bit) false
 #endif
 
+// Tile order.  ANEMOI_EPI_REVERSE walks the row blocks from the bottom of the matrix up, so that a GEMM which consumes what the previous kernel
+// wrote LAST starts where L2 still holds it (the serpentine schedule of the GraphTransformer block, layers/block.py).
+__device__ __forceinline__ int tile_at(int t, int num_tiles, bool rev) { return rev ? num_tiles - 1 - t : t; }
+
 struct EpiCtx {
   uint32_t bias_smem;  // 256 floats: the tile's bias slice, shared by the four warps of a column group
   uint32_t tmem_base, stg, res_bar, tfull0, tempty0;  // tempty0: cluster address of the (leader's) accumulator-empty barriers when CG = 2
   int lane, q, grp, num_tiles, tiles_n, first_tile, tile_stride;
+  bool rev;  // walk the tiles from the last row block to the first (ANEMOI_EPI_REVERSE)
   int tile_m, row_off;  // rows per tile (128 * CG) and this CTA's row offset inside the tile
   bool remote_empty;
   int abl;  // debug ablation bits
@@ -274,28 +279,28 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
   constexpr bool PREFETCH = RES && STG_BUFS == 2 && ANEMOI_GEMM_RES_PREFETCH;
   if constexpr (PREFETCH) {
     if (lane == 0 && cx.first_tile < cx.num_tiles) {
-      const int m_blk = cx.first_tile / cx.tiles_n, n_blk = cx.first_tile - m_blk * cx.tiles_n;
+      const int ft = tile_at(cx.first_tile, cx.num_tiles, cx.rev), m_blk = ft / cx.tiles_n, n_blk = ft - m_blk * cx.tiles_n;
       ptx::mbar_expect_tx(cx.res_bar, 2048);
       ptx::tma_load_2d(cx.stg, tmRes, cx.res_bar, n_blk * BN + cx.grp * kColsPerWarp, m_blk * cx.tile_m + cx.row_off + cx.q * 32);
     }
   }
   if constexpr (RES && ANEMOI_GEMM_RES_L2_AHEAD) {  // rounds 1.. of the first tile (round 0 is loaded straight into shared memory above)
     if (lane == 0 && cx.first_tile < cx.num_tiles) {
-      const int m_blk = cx.first_tile / cx.tiles_n, n_blk = cx.first_tile - m_blk * cx.tiles_n;
+      const int ft = tile_at(cx.first_tile, cx.num_tiles, cx.rev), m_blk = ft / cx.tiles_n, n_blk = ft - m_blk * cx.tiles_n;
 #pragma unroll
       for (int rd = 1; rd < ROUNDS; ++rd)
         ptx::tma_prefetch_l2_2d(tmRes, n_blk * BN + cx.grp * kColsPerWarp + rd * CW, m_blk * cx.tile_m + cx.row_off + cx.q * 32);
     }
   }
   for (int tile = cx.first_tile; tile < cx.num_tiles; tile += cx.tile_stride, ++it) {
-    const int m_blk = tile / cx.tiles_n, n_blk = tile - m_blk * cx.tiles_n;
+    const int tl = tile_at(tile, cx.num_tiles, cx.rev), m_blk = tl / cx.tiles_n, n_blk = tl - m_blk * cx.tiles_n;
     const int as = it & 1;
     const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
     const int row0 = m_blk * cx.tile_m + cx.row_off + cx.q * 32;
     if constexpr (RES && ANEMOI_GEMM_RES_L2_AHEAD) {
       const int nt = tile + cx.tile_stride;
       if (lane == 0 && nt < cx.num_tiles) {  // the whole next tile's residual rows of this warp -> L2, a tile (~10 k cycles) ahead of their use
-        const int nm = nt / cx.tiles_n, nn = nt - nm * cx.tiles_n;
+        const int ntl = tile_at(nt, cx.num_tiles, cx.rev), nm = ntl / cx.tiles_n, nn = ntl - nm * cx.tiles_n;
 #pragma unroll
         for (int rd = 0; rd < ROUNDS; ++rd)
           ptx::tma_prefetch_l2_2d(tmRes, nn * BN + cx.grp * kColsPerWarp + rd * CW, nm * cx.tile_m + cx.row_off + cx.q * 32);
@@ -408,7 +413,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
           if (!more) {
             const int nt = tile + cx.tile_stride;
             if (nt < cx.num_tiles) {
-              const int nm = nt / cx.tiles_n, nn = nt - nm * cx.tiles_n;
+              const int ntl = tile_at(nt, cx.num_tiles, cx.rev), nm = ntl / cx.tiles_n, nn = ntl - nm * cx.tiles_n;
               ncol = nn * BN + cx.grp * kColsPerWarp, nrow = nm * cx.tile_m + cx.row_off + cx.q * 32;
               more = true;
             }
@@ -549,7 +554,7 @@ __device__ __noinline__ void epilogue_generic(const EpiCtx& cx, const EpiParams&
   const int lane = cx.lane;
   int it = 0;
   for (int tile = cx.first_tile; tile < cx.num_tiles; tile += cx.tile_stride, ++it) {
-    const int m_blk = tile / cx.tiles_n, n_blk = tile - m_blk * cx.tiles_n;
+    const int tl = tile_at(tile, cx.num_tiles, cx.rev), m_blk = tl / cx.tiles_n, n_blk = tl - m_blk * cx.tiles_n;
     const int as = it & 1;
     const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
     ptx::mbar_wait(cx.tfull0 + 8u * as, aphase);
@@ -624,6 +629,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #endif
   const bool is_epi = ew >= 0 && ew < kEpiWarps;
   const int num_tiles = tiles_m * tiles_n;  // tiles of (128*CG) x BN
+  const bool rev = (ep.flags & ANEMOI_EPI_REVERSE) != 0;
   const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   const int first_tile = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -680,13 +686,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int i = 0; i < kL2Ahead + Cfg::kStages && pf_tile < num_tiles; ++i) pf_advance();
       }
       for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
-        const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+        const int tl = tile_at(tile, num_tiles, rev), m_blk = tl / tiles_n, n_blk = tl - m_blk * tiles_n;
         const int a_row = m_blk * (kBM * CG) + (int)rank * kBM;
         const int w_row = n_blk * BN + (int)rank * (BN / CG);
         for (int kb = 0; kb < num_kb; ++kb) {
           if constexpr (kL2Ahead > 0) {
             if (pf_tile < num_tiles) {
-              ptx::tma_prefetch_l2_2d(&tmA, pf_kb * kBK, (pf_tile / tiles_n) * (kBM * CG) + (int)rank * kBM);
+              ptx::tma_prefetch_l2_2d(&tmA, pf_kb * kBK, (tile_at(pf_tile, num_tiles, rev) / tiles_n) * (kBM * CG) + (int)rank * kBM);
               pf_advance();
             }
           }
@@ -759,6 +765,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     cx.tile_m = kBM * CG, cx.row_off = (int)rank * kBM;
     cx.abl = epi_mode & kAblMask;
     cx.num_tiles = num_tiles, cx.tiles_n = tiles_n, cx.first_tile = first_tile, cx.tile_stride = tile_stride;
+    cx.rev = rev;
     if (ABLK(kAblNoEpi)) {
       int it = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {

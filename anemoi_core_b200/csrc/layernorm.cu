@@ -116,13 +116,15 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const TI* __restrict__ x
 // values are O(std)); 3 shuffles per reduction instead of 5 and no register-resident copy of the row.  The per-warp-row kernel above ran at
 // 2.6 TB/s on the [40 962, 512] residual stream (16 us x 39 launches = 7 % of a cfg2 step); this one is bound by the read.
 __global__ void __launch_bounds__(256) row_stats_stream_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float2* __restrict__ stats, int64_t M,
-                                                               int C, float eps) {
+                                                               int C, float eps, int reverse) {
   pdl_wait();  // PDL (common.cuh): x comes from the GEMM just before
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31, sub = lane & 7, rw = lane >> 3;
   const int64_t groups_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int chunks = C >> 3;  // 16-byte chunks per row; lane `sub` takes chunks sub, sub + 8, ...
-  for (int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g * 4 < M; g += groups_total) {
+  const int64_t n_groups = (M + 3) / 4;
+  for (int64_t g0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g0 < n_groups; g0 += groups_total) {
+    const int64_t g = reverse ? n_groups - 1 - g0 : g0;  // reverse: from the rows the producer wrote last (still in L2) to the first
     const int64_t m = g * 4 + rw;
     const bool ok = m < M;
     const uint4* xr = reinterpret_cast<const uint4*>(x + (ok ? m : M - 1) * ldx);
@@ -336,7 +338,7 @@ extern "C" int anemoi_b200_cond_layer_norm(const void* x, int64_t ldx, int x_dty
   return launch_status("cond_layer_norm_kernel");
 }
 
-extern "C" int anemoi_b200_row_stats(const void* x, int64_t ldx, int x_dtype, float* stats, int64_t M, int64_t C, float eps, void* stream) {
+extern "C" int anemoi_b200_row_stats(const void* x, int64_t ldx, int x_dtype, float* stats, int64_t M, int64_t C, float eps, int flags, void* stream) {
   ANEMOI_CHECK_ARG(M >= 0 && C >= 8 && C % 8 == 0 && C <= 2048 && ldx >= C, "row_stats: need C % 8 == 0, 8 <= C <= 2048");
   ANEMOI_CHECK_ARG(x_dtype == ANEMOI_F32 || x_dtype == ANEMOI_BF16, "row_stats: bad dtype");
   if (M == 0) return 0;
@@ -351,7 +353,7 @@ extern "C" int anemoi_b200_row_stats(const void* x, int64_t ldx, int x_dtype, fl
     int64_t b2 = (M + 31) / 32;  // 4 rows per warp, 8 warps per block
     if (b2 > cap) b2 = cap;
     cudaError_t le = launch_pdl(row_stats_stream_kernel, dim3((unsigned)b2), dim3(256), 0, s, (const __nv_bfloat16*)x, ldx, reinterpret_cast<float2*>(stats),
-                                M, (int)C, eps);
+                                M, (int)C, eps, (flags & ANEMOI_EPI_REVERSE) ? 1 : 0);
     if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(row_stats_stream_kernel)");
     return launch_status("row_stats_stream_kernel");
   }

@@ -52,6 +52,11 @@ def attention_tile_plan(csr, channels: int, heads: int, dt: torch.dtype, dp: int
 # ------------------------------------------------------------------------------------------------------------
 # GraphConv (GNN) blocks
 # ------------------------------------------------------------------------------------------------------------
+# L2-aware traversal order of the GraphTransformer block's kernels (ops.set_traversal): qkv GEMM top-down, attention bottom-up, projection
+# top-down, row statistics bottom-up, MLP-1 top-down, MLP-2 bottom-up, next block's row statistics top-down ... each kernel starts on the
+# rows its producer wrote last.  ANEMOI_B200_SERPENTINE=0 restores top-down everywhere (A/B).
+SERPENTINE = os.environ.get("ANEMOI_B200_SERPENTINE", "1") != "0"
+
 class GraphConvBaseBlock(nn.Module):
     """Edge-MLP message passing + node MLP (block.py:275-358)."""
 
@@ -343,6 +348,9 @@ class GraphTransformerBaseBlock(nn.Module):
             for t, norm in ((q, self.q_norm),) + (() if k_prenormed else ((k, self.k_norm),)):
                 ops.layer_norm(t, self._pack.f32(norm.weight), self._pack.f32(getattr(norm, "bias", None)), norm.eps, out=t, groups=H)
         b_e = self._pack.f32(self.lin_edge.bias)
+        # Serpentine schedule (ops.set_traversal): q | k | v were just written top-down by the GEMM, so the attention walks the rows bottom-up
+        # and finds the last-written half of the 183 MB buffer in L2; the projection then runs top-down again over what attention wrote last.
+        ops.set_traversal(gemm=SERPENTINE)
         if fold:
             qw = ops.linear(q, self._qw_blockdiag(dt)) if self.qk_norm else dst_buf[:, n_lin * A :]
             att = torch.empty((q.shape[0], A + hdp), dtype=dt, device=q.device)
@@ -353,6 +361,7 @@ class GraphTransformerBaseBlock(nn.Module):
         else:
             w_e = self._pack.get(("w_edge",), [self.lin_edge.weight], lambda: self.lin_edge.weight.detach().float().contiguous())
             att = ops.gt_attention(q, k, v, csr, H, edge_attr=edge_attr_p, w_edge=w_e, b_edge=b_e, add=x_r)
+        ops.set_traversal()
         return self._project_mlp(att, x_skip, dt, fold, want_stats, cond)
 
     def _heads_attention(self, q: Tensor, qw: Tensor, k: Tensor, v: Tensor, x_r: Tensor, dst_sizes: list, src_sizes: Optional[list], ea: Tensor,
@@ -420,7 +429,7 @@ class GraphTransformerBaseBlock(nn.Module):
         # the projection epilogue also produces the row statistics of its output for layer_norm_mlp_dst (folded into the MLP's first GEMM),
         # and the MLP's last GEMM those of the block output for the next block's layer_norm_attention
         out = Fn.linear_with_stats(Fn.as_operand(att, dt, wp.shape[1]), wp, self._pack.bias([self.projection]), residual=skip, want_stats=True)
-        return self.node_dst_mlp.run(out, dt, residual=out, pre_ln=self.layer_norm_mlp_dst, want_stats=want_stats, cond=cond)
+        return self.node_dst_mlp.run(out, dt, residual=out, pre_ln=self.layer_norm_mlp_dst, want_stats=want_stats, cond=cond, serpentine=SERPENTINE)
 
 
 class GraphTransformerProcessorBlock(GraphTransformerBaseBlock):

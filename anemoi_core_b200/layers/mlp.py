@@ -87,9 +87,15 @@ class MLP(nn.Module):
         pre_ln: Optional[nn.Module] = None,
         want_stats: bool = False,
         cond: Optional[Tensor] = None,
+        serpentine: bool = False,
     ) -> Tensor:
         """Fused forward in compute dtype ``dt``.  ``residual`` is added after the last op (LayerNorm if present).
-        ``first_gathers`` / ``first_cols`` feed the split first layer of GraphConv's edge MLP (gather-add epilogue)."""
+        ``first_gathers`` / ``first_cols`` feed the split first layer of GraphConv's edge MLP (gather-add epilogue).
+        ``serpentine``: L2-aware traversal (``ops.set_traversal``) for an input the previous GEMM has just written top-down: the row
+        statistics of ``pre_ln`` walk bottom-up, the first GEMM top-down, the last GEMM (which reads the hidden tensor the first one has
+        just written) bottom-up."""
+        from .. import ops as _ops
+
         mods = list(self.mlp)
         i, first = 0, True
         while i < len(mods):
@@ -118,6 +124,8 @@ class MLP(nn.Module):
             if last and self.layer_norm is None:
                 kw["residual"], kw["out"] = residual, out
                 kw["want_stats"] = want_stats  # the caller's next op is a LayerNorm folded into a GEMM: hand it the row statistics
+            if serpentine:
+                _ops.set_traversal(gemm=last and not first, stats=first)
             if first and pre_ln is not None:  # LayerNorm(x) feeding the first Linear: folded into that GEMM on the bf16 path
                 x = Fn.ln_linear(self._pack, x, pre_ln, ("pre_ln", id(lin)), Fn.linear_sources([lin]), lambda lin=lin: Fn.cat_linear32([lin]), dt,
                                  cond=cond, gelu=act, **kw)
@@ -125,6 +133,8 @@ class MLP(nn.Module):
                 x = Fn.fused_linear(self._pack, x, [lin], dt, cols=first_cols if first else None, gelu=act, **kw)
             i += 2 if act else 1
             first = False
+        if serpentine:
+            _ops.set_traversal()
         if self.layer_norm is not None:
             from .normalization import _check_plain_layernorm
 

@@ -15,6 +15,7 @@ from torch import Tensor
 from . import _lib
 from ._lib import BF16
 from ._lib import EPI_GELU
+from ._lib import EPI_REVERSE
 from ._lib import F32
 
 __all__ = ["GraphCSR", "build_csr", "layer_norm", "row_stats", "linear", "gt_attention", "graphconv_ln_aggregate", "graphconv_fused", "cast_pad", "add", "dtype_code"]
@@ -35,6 +36,22 @@ def stop_timing() -> list:
     global _TIMER
     rec, _TIMER = _TIMER, None
     return rec or []
+
+
+# ---- traversal hint (L2 scheduling; results never depend on it) ---------------------------------------------------------------
+# A streaming kernel leaves the rows it touched LAST in L2 (126 MB), the next kernel usually starts at row 0, which was evicted long ago.
+# ``set_traversal`` lets a caller that knows the producer / consumer chain (the GraphTransformer block, layers/block.py) make the next
+# GEMM / attention (``gemm``) or row-statistics pass (``stats``) walk the rows from the bottom up, so that it starts where its
+# predecessor ended: the "serpentine" schedule.  Thread-local, consumed by ``linear`` / ``gt_attention`` / ``row_stats``.
+_TRAVERSAL = threading.local()
+
+
+def set_traversal(gemm: bool = False, stats: bool = False) -> None:
+    _TRAVERSAL.gemm, _TRAVERSAL.stats = bool(gemm), bool(stats)
+
+
+def _rev(kind: str) -> int:
+    return EPI_REVERSE if getattr(_TRAVERSAL, kind, False) else 0
 
 
 class _Timed:
@@ -355,7 +372,7 @@ def linear(
         _need_cuda(ln_stats, ln_colsum, stats_out)
         rc = _lib.load().anemoi_b200_linear(
             _ptr(a), lda, _ptr(weight), ldw, dtype_code(a.dtype), _ptr(_f32(bias)), _ptr(g1), _ptr(i1), _ptr(g2), _ptr(i2), ldg, _ptr(residual),
-            ldr, rdt, _ptr(out), ldo, dtype_code(out.dtype), M, N, K, EPI_GELU if gelu else 0, _ptr(ln_stats), _ptr(_f32(ln_colsum)),
+            ldr, rdt, _ptr(out), ldo, dtype_code(out.dtype), M, N, K, (EPI_GELU if gelu else 0) | _rev("gemm"), _ptr(ln_stats), _ptr(_f32(ln_colsum)),
             ln_parts, int(ln_dim), float(ln_eps), _ptr(stats_out), _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_linear")
     return out
@@ -478,7 +495,7 @@ def gt_attention(
         rc = _lib.load().anemoi_b200_gt_attention_fwd(
             _ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(e_proj), lde_proj, _ptr(edge_attr), lde, d_e, _ptr(w_edge), ldw_e, _ptr(_f32(b_edge)),
             _ptr(qw), ldqw, _ptr(abar), ldabar, dp, _ptr(csr.src32) or _ptr(csr.colptr32), _ptr(csr.colptr32), _ptr(add), ldadd, _ptr(out), ldo, _ptr(lse),
-            n_dst, heads, C // heads, dtype_code(q.dtype), _stream())  # fmt: skip
+            n_dst, heads, C // heads, dtype_code(q.dtype), _rev("gemm"), _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_gt_attention_fwd")
     return out
 
@@ -586,7 +603,7 @@ def row_stats(x: Tensor, eps: float = 1e-5) -> Tensor:
     M, C, ldx = _rows(x)
     stats = torch.empty((M, 2), dtype=torch.float32, device=x.device)
     with _Timed("row_stats", 4.0 * M * C, float(M) * C * x.element_size() + 8.0 * M):
-        rc = _lib.load().anemoi_b200_row_stats(_ptr(x), ldx, dtype_code(x.dtype), _ptr(stats), M, C, float(eps), _stream())
+        rc = _lib.load().anemoi_b200_row_stats(_ptr(x), ldx, dtype_code(x.dtype), _ptr(stats), M, C, float(eps), _rev("stats"), _stream())
     _lib.check(rc, "anemoi_b200_row_stats")
     return stats
 

@@ -41,6 +41,8 @@ extern "C" {
 
 /* anemoi_b200_linear flags */
 #define ANEMOI_EPI_GELU 1 /* exact (erf) GELU after bias/gather-add, before residual  (torch.nn.GELU default) */
+#define ANEMOI_EPI_REVERSE 2 /* scheduling hint, results unchanged: walk the row blocks from the last to the first, so that a GEMM
+                              * consuming what the previous kernel wrote last starts where L2 still holds it (bf16 tcgen05 path) */
 
 ANEMOI_API int anemoi_b200_abi_version(void);
 ANEMOI_API const char* anemoi_b200_last_error(void);
@@ -99,8 +101,9 @@ ANEMOI_API int anemoi_b200_linear(const void* A, int64_t lda, const void* W, int
                        int r_dtype, void* out, int64_t ldo, int o_dtype, int64_t M, int64_t N, int64_t K, int flags, const float* ln_stats,
                        const float* ln_colsum, int64_t ln_parts, int64_t ln_dim, float ln_eps, float* stats_out, void* stream);
 
-/* per-row LayerNorm statistics (mean, 1/sqrt(var + eps)), two-pass in registers: stats[m] = (mean, rstd), x [M, ldx] of x_dtype */
-ANEMOI_API int anemoi_b200_row_stats(const void* x, int64_t ldx, int x_dtype, float* stats, int64_t M, int64_t C, float eps, void* stream);
+/* per-row LayerNorm statistics (mean, 1/sqrt(var + eps)), two-pass in registers: stats[m] = (mean, rstd), x [M, ldx] of x_dtype.
+ * flags: ANEMOI_EPI_REVERSE = read the rows from the last to the first (scheduling hint, see anemoi_b200_linear; results unchanged). */
+ANEMOI_API int anemoi_b200_row_stats(const void* x, int64_t ldx, int x_dtype, float* stats, int64_t M, int64_t C, float eps, int flags, void* stream);
 
 /* -- GraphTransformer edge-softmax attention (forward) -------------------------------------------------------
  * Replaces layers/conv.py:103-147 (GraphTransformerConv, PyG softmax) and triton/gt.py:81-179 / :390-428
@@ -118,12 +121,14 @@ ANEMOI_API int anemoi_b200_row_stats(const void* x, int64_t ldx, int x_dtype, fl
  *   q [n_dst, ldq], k,v [n_src, ldk/ldv], add/out [n_dst, ld*], qw/abar [n_dst, >= heads*dp] of `dtype`; src32/colptr32 from csr_build.
  *   lse (nullable): fp32 [n_dst, heads] receives log sum_e exp(score_e) (0 for rows without edges, like the `m` output of
  *   triton/gt.py:112-119, 170-178); forms (1) / (2) only - it is what anemoi_b200_gt_attention_bwd consumes.
+ *   flags: ANEMOI_EPI_REVERSE = the warps take their destination ranges from the last rows to the first (scheduling hint: the rows the
+ *   producing GEMM wrote last are still in L2; results unchanged).
  */
 ANEMOI_API int anemoi_b200_gt_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* e,
                                  int64_t lde_proj, const float* edge_attr, int64_t lde, int64_t edge_dim, const float* w_edge,
                                  int64_t ldw_e, const float* b_edge, const void* qw, int64_t ldqw, void* abar, int64_t ldabar, int64_t dp,
                                  const int32_t* src32, const int32_t* colptr32, const void* add, int64_t ldadd, void* out, int64_t ldo,
-                                 float* lse, int64_t n_dst, int64_t heads, int64_t ch, int dtype, void* stream);
+                                 float* lse, int64_t n_dst, int64_t heads, int64_t ch, int dtype, int flags, void* stream);
 
 /* -- GraphTransformer attention on destination tiles (folded form (3), bf16, Ch in {32, 64}) ------------------------
  * Same result as anemoi_b200_gt_attention_fwd form (3) (replaces layers/conv.py:103-147, triton/gt.py:81-179 and the lin_edge GEMM of

@@ -539,3 +539,29 @@ def test_add(ops, M, C, dt):
 def test_cpu_tensor_is_an_error(ops):
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.layer_norm(torch.randn(4, 8), None, None)
+
+
+def test_reverse_traversal_hint_changes_nothing(ops):
+    """``ops.set_traversal`` (ANEMOI_EPI_REVERSE: GEMM row blocks / attention destination ranges / row-statistics rows walked bottom-up, an
+    L2 scheduling hint of the GraphTransformer block) must give bit-identical results."""
+    g = torch.Generator().manual_seed(11)
+    M, K, N = 5000, 512, 768
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K, generator=g) / K**0.5).to(torch.bfloat16).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    r = torch.randn(M, N, generator=g).to(torch.bfloat16).cuda()
+    n, e, H, C = 3000, 24000, 16, 512
+    ei = _rand_graph(n, n, e, 3, zero_tail=7)
+    csr = ops.build_csr(ei.cuda(), n, n)
+    qkv = torch.randn(n, 3 * C, generator=g).to(torch.bfloat16).cuda()
+    ep = torch.randn(e, C, generator=g).to(torch.bfloat16).cuda()
+    res = {}
+    for rev in (False, True):
+        ops.set_traversal(gemm=rev, stats=rev)
+        try:
+            res[rev] = (ops.linear(a, w, b, gelu=True), ops.linear(a, w, b, residual=r), ops.row_stats(a),
+                        ops.gt_attention(qkv[:, :C], qkv[:, C : 2 * C], qkv[:, 2 * C :], csr, H, e_proj=ep))
+        finally:
+            ops.set_traversal()
+    for x, y in zip(res[False], res[True]):
+        assert torch.equal(x, y)

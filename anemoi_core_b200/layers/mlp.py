@@ -8,6 +8,8 @@ GEMM(+bias+GELU) kernel per Linear and one LayerNorm(+residual) kernel.
 
 from __future__ import annotations
 
+import os
+
 from typing import Optional
 
 import torch
@@ -23,6 +25,11 @@ def _is_gelu(m: nn.Module) -> bool:
 
 
 GATED = ("glu", "swiglu", "geglu", "reglu")
+# Row-block size of MLP.run in MB of hidden tensor (0 = never chunk, the default); see MLP.run.  Measured (profiles/r2/call22_*): keeping the
+# 168 MB hidden tensor of a cfg2 MLP in L2 by running the two GEMMs on wave-aligned blocks of 9 472 rows makes the step SLOWER - 9.47 ms
+# against 8.59 ms (8.83 ms with two-wave blocks) - because every launch pays its own pipeline fill and an un-overlapped last epilogue
+# (~10 us on a 20 us GEMM).  The L2 win needs both GEMMs in ONE persistent kernel, which TMEM cannot hold.
+MLP_CHUNK_MB = int(os.environ.get("ANEMOI_B200_MLP_CHUNK_MB", "0"))
 
 
 class GatedMLPLayer(nn.Module):
@@ -76,6 +83,30 @@ class MLP(nn.Module):
         self.layer_norm = k.LayerNorm(normalized_shape=out_features) if layer_norm else None
         self._pack = Fn.WeightPack()
 
+    def _out_features(self) -> int:
+        last = [m for m in self.mlp if hasattr(m, "weight")][-1]
+        return last.weight.shape[0]
+
+    def _chunk_rows(self, x: Tensor, dt: torch.dtype, first_gathers, want_stats: bool) -> int:
+        """Rows per block for ``run`` (0 = no chunking): only for bf16 chains without gather-add / statistics hand-over whose widest hidden
+        tensor exceeds MLP_CHUNK_MB.  A block is a whole number of GEMM WAVES of the last (narrowest) GEMM - 256-row tiles, pairs of SMs, e.g.
+        37 row tiles x 2 column tiles = 74 CTA pairs for N = 512 - so that chunking adds no tile-quantisation loss: for the cfg2 MLP
+        (512 -> 2048 -> 512) a block of 9 472 rows is exactly 4 waves of the first GEMM and 1 wave of the second, 38.8 MB of hidden tensor."""
+        if MLP_CHUNK_MB <= 0 or dt != torch.bfloat16 or first_gathers is not None or (want_stats and Fn.FUSED_ROW_STATS) or x.dim() != 2 or not x.is_cuda:
+            return 0
+        widths = [(2 * m.gate_proj.weight.shape[0]) if isinstance(m, GatedMLPLayer) else m.weight.shape[0] for m in self.mlp
+                  if hasattr(m, "weight") or isinstance(m, GatedMLPLayer)]  # fmt: skip
+        if len(widths) < 2:
+            return 0
+        M, hidden = x.shape[0], max(widths[:-1])
+        if M * hidden * 2 <= (MLP_CHUNK_MB << 20) * 3 // 2:
+            return 0
+        pairs = max(1, torch.cuda.get_device_properties(x.device).multi_processor_count // 2)
+        wave_tiles = max(1, pairs // (-(-widths[-1] // 256)))  # row tiles of the last GEMM that fill one wave of CTA pairs
+        wave_bytes = wave_tiles * 256 * hidden * 2
+        rows = wave_tiles * 256 * max(1, (MLP_CHUNK_MB << 20) // wave_bytes)
+        return rows if rows < M else 0
+
     def run(
         self,
         x: Tensor,
@@ -88,6 +119,7 @@ class MLP(nn.Module):
         want_stats: bool = False,
         cond: Optional[Tensor] = None,
         serpentine: bool = False,
+        _chunked: bool = False,
     ) -> Tensor:
         """Fused forward in compute dtype ``dt``.  ``residual`` is added after the last op (LayerNorm if present).
         ``first_gathers`` / ``first_cols`` feed the split first layer of GraphConv's edge MLP (gather-add epilogue).
@@ -96,6 +128,28 @@ class MLP(nn.Module):
         just written) bottom-up."""
         from .. import ops as _ops
 
+        # Row chunking: the hidden tensor of a wide MLP ([40 962, 2048] bf16 = 168 MB in a cfg2 layer) is written by one GEMM and read back by
+        # the next; cut into row blocks of <= MLP_CHUNK_MB the pair of GEMMs works on a hidden block that is still in L2 (126 MB) when it is
+        # consumed, instead of streaming it through HBM twice.  Every op of the chain is row-wise, so the blocks are independent.
+        rows = 0 if _chunked else self._chunk_rows(x, dt, first_gathers, want_stats)
+        if rows:
+            M = x.shape[0]
+            if out is None:
+                out = torch.empty((M, self._out_features()), dtype=dt, device=x.device)
+            stats = None
+            if pre_ln is not None and Fn.can_fold_ln(pre_ln, x.shape[1], dt) and x.dtype == dt and x.stride(1) == 1:
+                if serpentine:
+                    _ops.set_traversal(stats=True)
+                stats = _ops.row_stats(x, pre_ln.eps)  # ONE statistics pass for all blocks; each block's view is tagged with its rows
+                _ops.set_traversal()
+            for r0 in range(0, M, rows):
+                r1 = min(M, r0 + rows)
+                xc = x[r0:r1]
+                if stats is not None:
+                    Fn.tag_row_stats(xc, stats[r0:r1])
+                self.run(xc, dt, residual=None if residual is None else residual[r0:r1], first_cols=first_cols, out=out[r0:r1], pre_ln=pre_ln,
+                         cond=None if cond is None else cond[r0:r1], serpentine=serpentine, _chunked=True)  # fmt: skip
+            return out
         mods = list(self.mlp)
         i, first = 0, True
         while i < len(mods):

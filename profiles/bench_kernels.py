@@ -139,3 +139,27 @@ if "gcf" in which:
                           "frac_hbm_8TBs": round(alg / med / 1e3 / 8000.0, 3), "GFLOP": round(10.0 * C * C * E / 1e9, 1),
                           "TFLOPs": round(10.0 * C * C * E / med / 1e6, 1), "decomposed_us": round(dmed, 1)}))  # fmt: skip
         del x, e, conv
+
+if "l2mlp" in which:
+    # Is MLP-2 (K = 2048, N = 512, residual) bound by the HBM read of its A operand?  Same GEMM with the hidden tensor cold (L2 flushed
+    # before the launch) and warm (MLP-1 has just written it, nothing flushed in between), for row counts whose hidden tensor fits L2.
+    for M in (9472, 18944, 40962):
+        x = torch.randn(M, 512, generator=g).to(torch.bfloat16).to(dev)
+        w1 = (torch.randn(2048, 512, generator=g) / 512**0.5).to(torch.bfloat16).to(dev)
+        w2 = (torch.randn(512, 2048, generator=g) / 2048**0.5).to(torch.bfloat16).to(dev)
+        b1, b2 = torch.randn(2048, generator=g).to(dev), torch.randn(512, generator=g).to(dev)
+        h = torch.empty(M, 2048, dtype=torch.bfloat16, device=dev)
+        o = torch.empty(M, 512, dtype=torch.bfloat16, device=dev)
+        cold, _ = timeit(lambda: ops.linear(h, w2, b2, residual=x, out=o))
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            ops.linear(x, w1, b1, gelu=True, out=h)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.linear(h, w2, b2, residual=x, out=o)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        print(json.dumps({"kernel": f"mlp2+res M={M} (hidden {M * 4096 / 1e6:.0f} MB)", "cold_us": round(cold, 1), "warm_after_mlp1_us": round(statistics.median(ts), 1),
+                          "TFLOPs_cold": round(2.0 * M * 512 * 2048 / cold / 1e6, 1), "TFLOPs_warm": round(2.0 * M * 512 * 2048 / statistics.median(ts) / 1e6, 1)}))  # fmt: skip

@@ -6,7 +6,8 @@ The reference hot path (``anemoi.models.layers.{mapper,processor}``) is imported
 mounted (build container) or from ``baseline/_ref`` (the `pip install --no-deps --target baseline/_ref` copy that travels to the GPU
 box), with ``oracle/standins`` supplying torch_geometric / hydra / anemoi.utils.  The step is the call
 sequence of ``AnemoiModelEncProcDec.forward`` (models/encoder_processor_decoder.py:260-324): encoder mapper -> processor -> latent
-skip -> decoder mapper, fp32, ``graph_attention_backend="pyg"`` (the reference's own CPU path; its Triton backend needs CUDA).
+skip -> decoder mapper, fp32, ``graph_attention_backend="pyg"`` (the reference's own CPU path; its Triton backend needs CUDA and is
+what ``profiles/bench_reference_gpu.py`` selects for the GPU head-to-head).
 """
 
 from __future__ import annotations
@@ -45,7 +46,7 @@ class ReferenceStep:
     """Reference encoder / processor / decoder for a bench workload, parameters copied from our modules' ``state_dict`` (same keys)."""
 
     def __init__(self, kind: str, *, in_grid: int, in_mesh: int, out_grid: int, num_channels: int, num_layers: int, edge_dim: int,
-                 num_heads: int, state_dicts: dict, max_layers=None) -> None:  # fmt: skip
+                 num_heads: int, state_dicts: dict, max_layers=None, attention_backend: str = "pyg") -> None:  # fmt: skip
         import torch
 
         M, P, self.GSI, self.BSI = _import_reference()
@@ -53,7 +54,7 @@ class ReferenceStep:
         self.root = reference_root()
         layers = num_layers if max_layers is None else min(num_layers, max_layers)
         if kind == "graphtransformer":
-            common = dict(num_heads=num_heads, mlp_hidden_ratio=4.0, edge_dim=edge_dim, num_chunks=1, layer_kernels=None, graph_attention_backend="pyg")
+            common = dict(num_heads=num_heads, mlp_hidden_ratio=4.0, edge_dim=edge_dim, num_chunks=1, layer_kernels=None, graph_attention_backend=attention_backend)
             self.encoder = M.GraphTransformerForwardMapper(in_channels_src=in_grid, in_channels_dst=in_mesh, hidden_dim=C, **common)
             self.processor = P.GraphTransformerProcessor(num_layers=layers, num_channels=C, **common)
             self.decoder = M.GraphTransformerBackwardMapper(in_channels_src=C, in_channels_dst=in_grid, hidden_dim=C, out_channels_dst=out_grid, **common)
@@ -71,6 +72,11 @@ class ReferenceStep:
         for m in (self.encoder, self.processor, self.decoder):
             m.eval()
         self._torch = torch
+
+    def to(self, device):
+        for m in (self.encoder, self.processor, self.decoder):
+            m.to(device)
+        return self
 
     def __call__(self, x_grid, x_mesh, gr, times=None):
         """One forward step; ``times`` (a list) receives (t_encoder, t_processor, t_decoder) in seconds."""

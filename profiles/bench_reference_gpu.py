@@ -1,0 +1,75 @@
+"""GPU head-to-head of the WHOLE step on the same B200: the UNMODIFIED reference modules (baseline/_ref, with oracle/standins for
+torch_geometric / hydra / anemoi.utils) run on the GPU through their own code path — PyTorch / cuBLAS kernels and, for the
+GraphTransformer, the reference's Triton attention backend (its fastest, training/docs/user-guide/performance-optimisation.rst:305-312) or
+the PyG backend — against this repository's step, on the cfg2 workload (BASELINE.json configs[1]) with the same parameters and inputs.
+
+Reports ms/step (CUDA events, L2 flushed between steps, eager for the reference, eager and CUDA-graph replay for ours), and the difference
+of the two outputs in bf16 autocast and in fp32.  The reference number is CONTEXT for the bench line (bench.py's reference arm is the CPU
+path the task names); nothing here is imported by the package.
+    python profiles/bench_reference_gpu.py [--steps 10] [--workload cfg2|small]
+"""
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from anemoi_core_b200.synthetic import build_graph  # noqa: E402
+from oracle import reference_step as RS  # noqa: E402
+
+steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 10
+wl = sys.argv[sys.argv.index("--workload") + 1] if "--workload" in sys.argv else "cfg2"
+w = bench.WORKLOADS[wl]
+dev = torch.device("cuda")
+gr = build_graph(w["grid"], w["mesh_level"])
+model = bench.build_model(w, gr)
+sds = bench.state_dicts(model)
+x_grid, x_mesh = bench.make_inputs(w, gr)
+grd = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in gr.items()}
+xg, xm = x_grid.to(dev), x_mesh.to(dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+model = model.to(dev)
+
+
+def timed(fn, n):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(n):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return round(statistics.median(ts), 3), round(min(ts), 3)
+
+
+out = {"workload": f"{wl}: {w['desc']}", "device": torch.cuda.get_device_name(0)}
+ours = {}
+for name, dt in (("bf16", torch.bfloat16), ("fp32", None)):
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dt is not None):
+        ours[name] = model(xg, xm, grd).float()
+        out[f"ours_eager_{name}_ms"] = timed(lambda: model(xg, xm, grd), steps)[0]
+for backend in ("triton", "pyg"):
+    if w["kind"] != "graphtransformer" and backend == "triton":
+        continue
+    try:
+        ref = RS.ReferenceStep(w["kind"], state_dicts=sds, attention_backend=backend, **bench._ref_kwargs(w, gr)).to(dev)
+        for name, dt in (("bf16", torch.bfloat16), ("fp32", None)):
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dt is not None):
+                y = ref(xg, xm, grd).float()
+                ms = timed(lambda: ref(xg, xm, grd), steps)[0]
+            d = (ours[name] - y)
+            out[f"reference_{backend}_{name}"] = {"ms_per_step_eager": ms, "rel_l2_ours_vs_reference": round((d.norm() / y.norm()).item(), 6),
+                                                  "max_abs_over_max_ref": round((d.abs().max() / y.abs().max()).item(), 6)}  # fmt: skip
+        del ref
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001 - report and go on with the other backend
+        out[f"reference_{backend}"] = f"unavailable: {type(e).__name__}: {str(e)[:300]}"
+print(json.dumps(out))

@@ -63,6 +63,7 @@ SIGNATURES = {
     "anemoi_b200_cast_pad": [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p],
     "anemoi_b200_glu_combine": [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p],
     "anemoi_b200_glu_combine_bwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p],
+    "anemoi_b200_split_bf16x3": [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p],
     "anemoi_b200_assemble_input": [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
                                    c_int, c_void_p],
     "anemoi_b200_assemble_output": [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p,

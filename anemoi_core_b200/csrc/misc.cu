@@ -159,6 +159,45 @@ __global__ void glu_combine_bwd_kernel(const T* __restrict__ in, int64_t ldi, co
   }
 }
 
+// ---- fp32 GEMMs on the bf16 tensor cores: exact three-way split --------------------------------------------------------------
+// x = x1 + x2 + x3 with x1 = bf16(x), x2 = bf16(x - x1), x3 = bf16(x - x1 - x2): 24 mantissa bits, i.e. the fp32 value (up to 2^-24 |x|).
+// A product of two bf16 numbers is exact in fp32, so  a.w = sum_{i+j<=4} a_i w_j  (6 terms; the dropped ones are below 2^-24 |a||w|)
+// evaluated with fp32 accumulation is an fp32-grade dot product.  The six partial GEMMs are ONE tcgen05 GEMM over a 6K-long inner
+// dimension: A' = [a3|a2|a1|a2|a1|a1], W' = [w1|w2|w3|w1|w2|w1].  This kernel writes the [M, 6K] bf16 operand for either side.
+// (The fp32 parity mode used to run its GEMMs on the FFMA kernel: 201 ms per cfg2 step against 131 ms for the reference's cuBLAS fp32.)
+__global__ void split_bf16x3_kernel(const float* __restrict__ in, int64_t ldi, __nv_bfloat16* __restrict__ out, int64_t ldo, int64_t M, int64_t K,
+                                    int weight_side) {
+  const int64_t q = K / 4, total = M * q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / q, k = (i - m * q) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(in + m * ldi + k);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    uint32_t p[3][2];  // three parts x two packed pairs
+    float r[4], h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[j] = x[j];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[j] = __bfloat162float(__float2bfloat16_rn(r[j]));
+        r[j] -= h[j];
+      }
+      p[t][0] = pack_bf16x2(h[0], h[1]), p[t][1] = pack_bf16x2(h[2], h[3]);
+    }
+    // pairs in the order (3,1) (2,2) (1,3) (2,1) (1,2) (1,1): SMALLEST terms first.  The tensor core's fp32 accumulation truncates; while
+    // the corrections are summed the accumulator is still 2^-8 of its final size, so only the K/16 MMAs of the (1,1) block can lose bits
+    // at full scale (measured: 2e-5 -> 3e-6 of the output scale against the largest-first order).
+    const int pa[6] = {2, 1, 0, 1, 0, 0}, pw[6] = {0, 1, 2, 0, 1, 0};
+    __nv_bfloat16* o = out + m * ldo + k;
+#pragma unroll
+    for (int s6 = 0; s6 < 6; ++s6) {
+      const int t = weight_side ? pw[s6] : pa[s6];
+      *reinterpret_cast<uint2*>(o + s6 * K) = make_uint2(p[t][0], p[t][1]);
+    }
+  }
+}
+
 // ---- model glue either side of the encoder / decoder ------------------------------------------------------
 // assemble_input: out[(b e g), t * V + v] = x[b, t, e, g, v];  out[(b e g), T * V + a] = attrs[row % attr_rows, a];  zero pad up to Kpad.
 // Replaces einops.rearrange + torch.cat (+ the autocast cast of the embedding Linear) of `_assemble_input`
@@ -250,6 +289,18 @@ extern "C" int anemoi_b200_glu_combine_bwd(const void* in, int64_t ldi, const vo
   else
     glu_combine_bwd_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const float*)in, ldi, (const float*)dy, lddy, (float*)din, ldd, M, H, act);
   return launch_status("glu_combine_bwd_kernel");
+}
+
+extern "C" int anemoi_b200_split_bf16x3(const float* in, int64_t ldi, void* out, int64_t ldo, int64_t M, int64_t K, int weight_side, void* stream) {
+  ANEMOI_CHECK_ARG(M >= 0 && K >= 4 && K % 4 == 0 && ldi >= K && ldo >= 6 * K, "split_bf16x3: need K %% 4 == 0, ldi >= K, ldo >= 6 K");
+  if (M == 0) return 0;
+  ANEMOI_CHECK_ARG(in && out, "split_bf16x3: null pointer");
+  ANEMOI_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15) == 0 && ldi % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0 && ldo % 4 == 0,
+                   "split_bf16x3: rows must be 16-byte (input) / 8-byte (output) aligned");
+  int64_t blocks = (M * (K / 4) + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+  split_bf16x3_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, ldi, (__nv_bfloat16*)out, ldo, M, K, weight_side ? 1 : 0);
+  return launch_status("split_bf16x3_kernel");
 }
 
 extern "C" int anemoi_b200_assemble_input(const float* x, int64_t B, int64_t T, int64_t E, int64_t G, int64_t V, const float* attrs, int64_t A,

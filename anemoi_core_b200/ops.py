@@ -5,6 +5,7 @@ or PyTorch here; a CPU tensor is an error (there is no fallback path).
 
 from __future__ import annotations
 
+import os
 import threading
 from dataclasses import dataclass
 from typing import Optional
@@ -288,6 +289,36 @@ def layer_norm(
     return out
 
 
+# ---- fp32 GEMMs on the tensor cores (exact bf16 x 3 split, csrc/misc.cu:split_bf16x3_kernel) -----------------------------------
+# ANEMOI_B200_FP32_TC=0 keeps the FFMA kernel for every fp32 GEMM.
+FP32_TC = os.environ.get("ANEMOI_B200_FP32_TC", "1") != "0"
+
+
+def split_bf16x3(x: Tensor, weight_side: bool) -> Tensor:
+    """fp32 [M, K] (K % 4 == 0) -> bf16 [M, 6K]: the operand (or weight) side of the six exact partial products."""
+    _need_cuda(x)
+    M, K, ldi = _rows(x)
+    out = torch.empty((M, 6 * K), dtype=torch.bfloat16, device=x.device)
+    with _Timed("split_bf16x3", 0.0, float(M) * K * 16):
+        rc = _lib.load().anemoi_b200_split_bf16x3(_ptr(x), ldi, _ptr(out), 6 * K, M, K, 1 if weight_side else 0, _stream())
+    _lib.check(rc, "anemoi_b200_split_bf16x3")
+    return out
+
+
+def _fp32_on_tensor_cores(a: Tensor, weight: Tensor) -> Optional[tuple]:
+    """(a6, w6) when this fp32 GEMM should run as one bf16 tcgen05 GEMM over the split operands, else None (FFMA kernel)."""
+    if not FP32_TC or a.dtype != torch.float32 or weight.dtype != torch.float32:
+        return None
+    M, K = a.shape
+    N = weight.shape[0]
+    if K % 4 or K < 16 or M < 256 or M * N * K < (1 << 24) or a.stride(0) % 4 or weight.stride(0) % 4 or a.data_ptr() % 16 or weight.data_ptr() % 16:
+        return None
+    # the weight is split on every call: it is small next to the activations, and a cache keyed on the storage address would go stale when
+    # the allocator hands the same address to another tensor
+    w6 = split_bf16x3(weight, True)
+    return split_bf16x3(a, False), w6
+
+
 def linear(
     a: Tensor,
     weight: Tensor,
@@ -312,7 +343,8 @@ def linear(
     With ``ln_stats`` [M, 2] (``row_stats(a)``) and ``ln_colsum`` [N] the LayerNorm of ``a`` is folded in:
     out = [gelu](rstd * (a @ weight.T - mean * colsum) + bias) for ``weight`` already scaled by the LayerNorm gamma.
 
-    ``a`` [M, K] and ``weight`` [N, K] share a dtype (bf16 -> tcgen05 tensor cores, fp32 -> exact FFMA);
+    ``a`` [M, K] and ``weight`` [N, K] share a dtype: bf16 -> tcgen05 tensor cores; fp32 -> the same tensor cores on the exact bf16 x 3 split
+    of both operands (``split_bf16x3``: fp32-grade result, ~1e-6), or the FFMA kernel for small / unaligned problems;
     ``gatherX = (table fp32 [*, >=N], idx int32 [M])``.
     """
     _need_cuda(a, weight, bias, residual, out)
@@ -352,6 +384,11 @@ def linear(
             g2, i2 = tab, idx
     if g1 is None and g2 is not None:
         g1, i1, g2, i2 = g2, i2, None, None
+    if ln_stats is None and stats_out is None:
+        split = _fp32_on_tensor_cores(a, weight)
+        if split is not None:  # fp32 operands: ONE bf16 tcgen05 GEMM over the six exact partial products (inner dimension 6K)
+            a, weight = split
+            K, lda, ldw = 6 * K, 6 * K, 6 * K
     tc = a.dtype == torch.bfloat16 and K >= 64 and lda % 8 == 0 and ldw % 8 == 0 and a.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0
     gbytes = (4.0 * M * N if g1 is not None else 0.0) + (4.0 * M * N if g2 is not None else 0.0)
     with _Timed("linear_tcgen05" if tc else "linear_ffma", 2.0 * M * N * K, _nbytes(a, weight, residual, out) + gbytes):

@@ -253,6 +253,13 @@ ANEMOI_API int anemoi_b200_glu_combine(const void* in, int64_t ldi, void* out, i
 ANEMOI_API int anemoi_b200_glu_combine_bwd(const void* in, int64_t ldi, const void* dy, int64_t lddy, void* din, int64_t ldd, int64_t M, int64_t H,
                                            int act, int dtype, void* stream);
 
+/* fp32 Linear on the bf16 tensor cores (the fp32 parity mode's GEMMs; reference: torch.nn.Linear in fp32, layers/mlp.py:97-179):
+ * x = x1 + x2 + x3 in bf16 parts (24 mantissa bits); products of bf16 numbers are exact in fp32, so sum_{i+j<=4} a_i w_j with fp32
+ * accumulation is an fp32-grade product.  out[m, s*K + k] = part pa[s] (weight_side = 0: 3 2 1 2 1 1) or pw[s] (weight_side = 1:
+ * 1 2 3 1 2 1) of in[m, k] - smallest products first, the tensor core's accumulation truncates; anemoi_b200_linear on the two [*, 6K] bf16 operands then returns A.W^T to ~1e-6 relative.
+ * in : fp32 [M, ldi >= K], K % 4 == 0; out : bf16 [M, ldo >= 6K]. */
+ANEMOI_API int anemoi_b200_split_bf16x3(const float* in, int64_t ldi, void* out, int64_t ldo, int64_t M, int64_t K, int weight_side, void* stream);
+
 /* -- model glue either side of the path -------------------------------------------------
  * Replaces `_assemble_input` (models/encoder_processor_decoder.py:98-127): einops.rearrange(x, "batch time ensemble grid vars ->
  * (batch ensemble grid) (time vars)") + torch.cat with the node attributes (+ the autocast cast in front of the embedding Linear).

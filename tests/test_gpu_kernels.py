@@ -565,3 +565,30 @@ def test_reverse_traversal_hint_changes_nothing(ops):
             ops.set_traversal()
     for x, y in zip(res[False], res[True]):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 512), (40962, 2048, 512), (1000, 88, 512), (5000, 512, 2048)])
+def test_fp32_linear_on_tensor_cores_is_fp32_grade(ops, M, N, K):
+    """fp32 GEMMs run as ONE bf16 tcgen05 GEMM over the exact three-way bf16 split of both operands (6 partial products, fp32
+    accumulation): the result must be as good as an fp32 FFMA evaluation — compared here with a float64 reference to 5e-6 of the output scale (K up to 2048),
+    with bias / GELU / residual epilogues — and the FFMA kernel (ANEMOI_B200_FP32_TC off) must agree."""
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, K, generator=g) * torch.exp(torch.randn(M, 1, generator=g))  # rows of very different scale
+    w = torch.randn(N, K, generator=g) / K**0.5
+    b, r = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    ref = (a.double() @ w.double().t() + b.double())
+    assert ops._fp32_on_tensor_cores(a.cuda(), w.cuda()) is not None
+    y = ops.linear(a.cuda(), w.cuda(), b.cuda()).cpu().double()
+    assert ((y - ref).abs().max() / ref.abs().max()).item() <= 5e-6
+    row_scale = ref.abs().amax(1, keepdim=True)
+    assert ((y - ref).abs() / row_scale).max().item() <= 1e-5  # also for the small rows
+    y2 = ops.linear(a.cuda(), w.cuda(), b.cuda(), gelu=True, residual=r.cuda()).cpu().double()
+    ref2 = torch.nn.functional.gelu(ref) + r.double()
+    assert ((y2 - ref2).abs().max() / ref2.abs().max()).item() <= 5e-6
+    old = ops.FP32_TC
+    try:
+        ops.FP32_TC = False
+        y3 = ops.linear(a.cuda(), w.cuda(), b.cuda()).cpu().double()
+    finally:
+        ops.FP32_TC = old
+    assert ((y3 - ref).abs().max() / ref.abs().max()).item() <= 5e-6

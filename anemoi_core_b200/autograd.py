@@ -34,7 +34,9 @@ class LinearFn(Function):
     def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], gelu: bool, dt: torch.dtype) -> Tensor:
         K = x.shape[1]
         kp = max(64, (K + 7) // 8 * 8) if dt == torch.bfloat16 else K  # tcgen05 operands: 16-byte rows, one swizzle span
-        xa = ops.cast_pad(x.detach(), dt, kp)
+        xd = x.detach()
+        # no copy when x already is a dt operand of the right width (the common case inside a block: the previous op's output)
+        xa = xd if (xd.dtype == dt and K == kp and xd.stride(1) == 1 and xd.data_ptr() % 16 == 0 and (xd.stride(0) * xd.element_size()) % 16 == 0) else ops.cast_pad(xd, dt, kp)
         wa = _pad_cols(weight.detach(), kp).to(dt).contiguous()
         z = ops.linear(xa, wa, None if bias is None else bias.detach().float().contiguous())
         ctx.save_for_backward(xa, wa, z if gelu else None)
@@ -54,7 +56,7 @@ class LinearFn(Function):
         if ctx.needs_input_grad[1]:
             dw = torch.matmul(dz.t(), xa)[:, :K].to(w_dt)  # plain library GEMM (weight gradient; reduction over all rows)
         if b_dt is not None and ctx.needs_input_grad[2]:
-            db = dz.float().sum(0).to(b_dt)
+            db = dz.sum(0, dtype=torch.float32).to(b_dt)  # fp32 accumulation without materialising an fp32 copy of dz
         return dx, dw, db, None, None
 
 

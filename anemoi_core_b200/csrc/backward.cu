@@ -120,6 +120,175 @@ __global__ void __launch_bounds__(256) gt_attention_bwd_src_kernel(const T* __re
   }
 }
 
+// ---- fast forms (rows of C = NCH * 32 * (16 / sizeof(T)) channels exactly, heads of LPH * (16 / sizeof(T)) channels) ---------------------
+// Same two passes, laid out like the forward kernel: ONE warp owns a node for ALL heads, lane l holds the 16-byte chunks l, l + 32, ... of a
+// row, a head spans LPH consecutive lanes (scores finish with log2(LPH) shuffles).  Every row access is NCH fully coalesced 512-byte warp
+// loads (the per-(node, head) kernels above read 64 bytes per warp access and re-walk the edge list once per head): cfg2 layer, bf16:
+// dst pass 1.73 ms -> ~0.3 ms, src pass 1.2 ms -> ~0.2 ms.
+template <typename T>
+struct BwdChunk {
+  static constexpr int EPC = 16 / (int)sizeof(T);
+  __device__ static __forceinline__ void load(const T* p, float (&f)[EPC]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    if constexpr (sizeof(T) == 4) {
+      f[0] = __uint_as_float(u.x), f[1] = __uint_as_float(u.y), f[2] = __uint_as_float(u.z), f[3] = __uint_as_float(u.w);
+    } else {
+      f[0] = __uint_as_float(u.x << 16), f[1] = __uint_as_float(u.x & 0xffff0000u), f[2] = __uint_as_float(u.y << 16), f[3] = __uint_as_float(u.y & 0xffff0000u);
+      f[4] = __uint_as_float(u.z << 16), f[5] = __uint_as_float(u.z & 0xffff0000u), f[6] = __uint_as_float(u.w << 16), f[7] = __uint_as_float(u.w & 0xffff0000u);
+    }
+  }
+  __device__ static __forceinline__ void store(T* p, const float (&f)[EPC]) {
+    if constexpr (sizeof(T) == 4)
+      *reinterpret_cast<uint4*>(p) = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    else
+      *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+};
+
+template <typename T, int NCH, int LPH, bool HAS_E>
+__global__ void __launch_bounds__(256) gt_attention_bwd_dst_fast_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, int64_t ldk,
+                                                                        const T* __restrict__ v, int64_t ldv, const T* __restrict__ e, int64_t lde,
+                                                                        const T* __restrict__ out, int64_t ldo, const T* __restrict__ dout,
+                                                                        int64_t lddo, const float* __restrict__ lse, const int32_t* __restrict__ src,
+                                                                        const int32_t* __restrict__ colptr, T* __restrict__ dq, int64_t lddq,
+                                                                        T* __restrict__ de, int64_t ldde, float* __restrict__ alpha,
+                                                                        float* __restrict__ ds, int64_t n_dst, int heads, float scale) {
+  using CT = BwdChunk<T>;
+  constexpr int EPC = CT::EPC;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int col[NCH], hd[NCH];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) col[j] = (j * 32 + lane) * EPC, hd[j] = (j * 32 + lane) / LPH;
+  for (int64_t d = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); d < n_dst; d += warps_total) {
+    const int e0 = __ldg(colptr + d), e1 = __ldg(colptr + d + 1);
+    float qf[NCH][EPC], gf[NCH][EPC], acc[NCH][EPC], D[NCH], l[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      float of[EPC];
+      CT::load(q + d * ldq + col[j], qf[j]);
+      CT::load(dout + d * lddo + col[j], gf[j]);
+      CT::load(out + d * ldo + col[j], of);
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < EPC; ++i) t += gf[j][i] * of[i], acc[j][i] = 0.f;
+#pragma unroll
+      for (int o = 1; o < LPH; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      D[j] = t;
+      l[j] = __ldg(lse + d * heads + hd[j]);
+    }
+    int s_next = e0 < e1 ? __ldg(src + e0) : 0;
+    for (int ei = e0; ei < e1; ++ei) {
+      const int64_t s = s_next;
+      if (ei + 1 < e1) s_next = __ldg(src + ei + 1);
+      float kk[NCH][EPC], vv[NCH][EPC];
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {  // all loads of the edge first: 3 * NCH independent 16-byte loads in flight per lane
+        CT::load(k + s * ldk + col[j], kk[j]);
+        CT::load(v + s * ldv + col[j], vv[j]);
+      }
+      if constexpr (HAS_E) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          float ef[EPC];
+          CT::load(e + (int64_t)ei * lde + col[j], ef);
+#pragma unroll
+          for (int i = 0; i < EPC; ++i) kk[j][i] += ef[i], vv[j][i] += ef[i];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        float sc = 0.f, da = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPC; ++i) sc += qf[j][i] * kk[j][i], da += gf[j][i] * vv[j][i];
+#pragma unroll
+        for (int o = 1; o < LPH; o <<= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o), da += __shfl_xor_sync(0xffffffffu, da, o);
+        const float a = __expf(sc * scale - l[j]);
+        const float g = scale * a * (da - D[j]);
+        float dev[EPC];
+#pragma unroll
+        for (int i = 0; i < EPC; ++i) acc[j][i] += g * kk[j][i], dev[i] = g * qf[j][i] + a * gf[j][i];
+        if constexpr (HAS_E) CT::store(de + (int64_t)ei * ldde + col[j], dev);
+        if ((lane & (LPH - 1)) == 0) alpha[(int64_t)ei * heads + hd[j]] = a, ds[(int64_t)ei * heads + hd[j]] = g;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) CT::store(dq + d * lddq + col[j], acc[j]);
+  }
+}
+
+template <typename T, int NCH, int LPH>
+__global__ void __launch_bounds__(256) gt_attention_bwd_src_fast_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ dout, int64_t lddo,
+                                                                        const float* __restrict__ alpha, const float* __restrict__ ds,
+                                                                        const int32_t* __restrict__ rev_ptr, const int32_t* __restrict__ rev_eid,
+                                                                        const int32_t* __restrict__ dst, T* __restrict__ dk, int64_t lddk,
+                                                                        T* __restrict__ dv, int64_t lddv, int64_t n_src, int heads) {
+  using CT = BwdChunk<T>;
+  constexpr int EPC = CT::EPC;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int col[NCH], hd[NCH];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) col[j] = (j * 32 + lane) * EPC, hd[j] = (j * 32 + lane) / LPH;
+  for (int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_src; s += warps_total) {
+    float ak[NCH][EPC], av[NCH][EPC];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+      for (int i = 0; i < EPC; ++i) ak[j][i] = av[j][i] = 0.f;
+    const int j0 = __ldg(rev_ptr + s), j1 = __ldg(rev_ptr + s + 1);
+    for (int jj = j0; jj < j1; ++jj) {
+      const int ei = __ldg(rev_eid + jj);
+      const int64_t d = __ldg(dst + ei);
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        float qf[EPC], gf[EPC];
+        CT::load(q + d * ldq + col[j], qf);
+        CT::load(dout + d * lddo + col[j], gf);
+        const float a = __ldg(alpha + (int64_t)ei * heads + hd[j]), g = __ldg(ds + (int64_t)ei * heads + hd[j]);
+#pragma unroll
+        for (int i = 0; i < EPC; ++i) ak[j][i] += g * qf[i], av[j][i] += a * gf[i];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      CT::store(dk + s * lddk + col[j], ak[j]);
+      CT::store(dv + s * lddv + col[j], av[j]);
+    }
+  }
+}
+
+template <typename T, int NCH, int LPH>
+int launch_bwd_fast(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* e, int64_t lde, const void* out,
+                    int64_t ldo, const void* dout, int64_t lddo, const float* lse, const int32_t* src32, const int32_t* colptr32,
+                    const int32_t* dst32, const int32_t* rev_ptr32, const int32_t* rev_eid32, void* dq, int64_t lddq, void* dk, int64_t lddk,
+                    void* dv, int64_t lddv, void* de, int64_t ldde, float* alpha, float* ds, int64_t n_src, int64_t n_dst, int heads, float scale,
+                    cudaStream_t s) {
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (n_dst > 0) {
+    int64_t blocks = (n_dst + 7) / 8;
+    if (blocks > cap) blocks = cap;
+    if (e)
+      gt_attention_bwd_dst_fast_kernel<T, NCH, LPH, true><<<(unsigned)blocks, 256, 0, s>>>(
+          (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, (const T*)e, lde, (const T*)out, ldo, (const T*)dout, lddo, lse, src32, colptr32, (T*)dq,
+          lddq, (T*)de, ldde, alpha, ds, n_dst, heads, scale);
+    else
+      gt_attention_bwd_dst_fast_kernel<T, NCH, LPH, false><<<(unsigned)blocks, 256, 0, s>>>(
+          (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, (const T*)e, lde, (const T*)out, ldo, (const T*)dout, lddo, lse, src32, colptr32, (T*)dq,
+          lddq, (T*)de, ldde, alpha, ds, n_dst, heads, scale);
+    const int rc = launch_status("gt_attention_bwd_dst_fast_kernel");
+    if (rc) return rc;
+  }
+  if (n_src > 0) {
+    int64_t blocks = (n_src + 7) / 8;
+    if (blocks > cap) blocks = cap;
+    gt_attention_bwd_src_fast_kernel<T, NCH, LPH><<<(unsigned)blocks, 256, 0, s>>>((const T*)q, ldq, (const T*)dout, lddo, alpha, ds, rev_ptr32, rev_eid32,
+                                                                                   dst32, (T*)dk, lddk, (T*)dv, lddv, n_src, heads);
+    return launch_status("gt_attention_bwd_src_fast_kernel");
+  }
+  return 0;
+}
+
 // LayerNorm backward over rows of C channels (C <= 1024, lane owns channels lane + 32 i); row r of `groups` per matrix row lives at
 // x + (r / groups) * ldx + (r % groups) * C (qk_norm: one LayerNorm per head).  Cotangent g = dy[r] (nullable) + dz[idx[r]] (nullable).
 // dgamma / dbeta: per-block partial sums [gridDim.x, 2, C] (summed by the caller: deterministic).  dres (nullable) receives g itself (the
@@ -224,6 +393,139 @@ __global__ void gelu_kernel(const T* __restrict__ x, int64_t ldx, const T* __res
   }
 }
 
+// 16 bytes per thread (rows of N % EPC == 0 elements, 16-byte aligned): the scalar kernel above spends its time on per-element index
+// arithmetic and 2-byte accesses (0.30 ms for the 168 MB hidden tensor of a cfg2 MLP; this one is bound by the three streams).
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_vec_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy, T* __restrict__ y,
+                                                       int64_t ldy, int64_t M, int64_t N, int mode) {
+  using CT = BwdChunk<T>;
+  constexpr int EPC = CT::EPC;
+  const int64_t q = N / EPC, total = M * q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / q, n = (i - m * q) * EPC;
+    float v[EPC], r[EPC];
+    CT::load(x + m * ldx + n, v);
+    if (mode == 0) {
+#pragma unroll
+      for (int j = 0; j < EPC; ++j) r[j] = gelu_erf(v[j]);
+    } else {
+      float g[EPC];
+      CT::load(dy + m * lddy + n, g);
+#pragma unroll
+      for (int j = 0; j < EPC; ++j) {
+        const float cdf = 0.5f * (1.0f + erff(v[j] * 0.70710678118654752440f));
+        const float pdf = 0.39894228040143267794f * __expf(-0.5f * v[j] * v[j]);
+        r[j] = g[j] * (cdf + v[j] * pdf);
+      }
+    }
+    CT::store(y + m * ldy + n, r);
+  }
+}
+
+// LayerNorm backward, one row per warp in the 16-byte chunk layout (C = NCH * 32 * EPC exactly, groups == 1): every access is a coalesced
+// 512-byte warp load / store.  Same arithmetic and the same per-block dgamma / dbeta partials as layer_norm_bwd_kernel.
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256) layer_norm_bwd_fast_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
+                                                                  const T* __restrict__ dy, int64_t lddy, const T* __restrict__ dz, int64_t lddz,
+                                                                  const int32_t* __restrict__ idx, T* __restrict__ dx, int64_t lddx,
+                                                                  T* __restrict__ dres, int64_t lddr, float* __restrict__ partial, int64_t rows,
+                                                                  float eps) {
+  using CT = BwdChunk<T>;
+  constexpr int EPC = CT::EPC;
+  constexpr int C = NCH * 32 * EPC;
+  extern __shared__ float red[];  // [warps][2][C]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float dg[NCH][EPC], db[NCH][EPC], gm[NCH][EPC];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+#pragma unroll
+    for (int i = 0; i < EPC; ++i) dg[j][i] = db[j][i] = 0.f, gm[j][i] = gamma ? __ldg(gamma + (j * 32 + lane) * EPC + i) : 1.f;
+  const float invC = 1.0f / (float)C;
+  for (int64_t r = (int64_t)blockIdx.x * wpb + wib; r < rows; r += (int64_t)gridDim.x * wpb) {
+    const int64_t zr = dz ? (int64_t)(idx ? __ldg(idx + r) : r) : 0;
+    float xv[NCH][EPC], gv[NCH][EPC];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int c = (j * 32 + lane) * EPC;
+      CT::load(x + r * ldx + c, xv[j]);
+      if (dy) {
+        CT::load(dy + r * lddy + c, gv[j]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < EPC; ++i) gv[j][i] = 0.f;
+      }
+      if (dz) {
+        float t[EPC];
+        CT::load(dz + zr * lddz + c, t);
+#pragma unroll
+        for (int i = 0; i < EPC; ++i) gv[j][i] += t[i];
+      }
+#pragma unroll
+      for (int i = 0; i < EPC; ++i) s += xv[j][i];
+    }
+    const float mean = warp_sum(s) * invC;
+    float var = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+      for (int i = 0; i < EPC; ++i) {
+        const float t = xv[j][i] - mean;
+        var += t * t;
+      }
+    const float rstd = rsqrtf(warp_sum(var) * invC + eps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+      for (int i = 0; i < EPC; ++i) {
+        xv[j][i] = (xv[j][i] - mean) * rstd;
+        const float dxh = gv[j][i] * gm[j][i];
+        m1 += dxh, m2 += dxh * xv[j][i];
+        dg[j][i] += gv[j][i] * xv[j][i], db[j][i] += gv[j][i];
+      }
+    m1 = warp_sum(m1) * invC, m2 = warp_sum(m2) * invC;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int c = (j * 32 + lane) * EPC;
+      float o[EPC];
+#pragma unroll
+      for (int i = 0; i < EPC; ++i) o[i] = rstd * (gv[j][i] * gm[j][i] - m1 - xv[j][i] * m2);
+      CT::store(dx + r * lddx + c, o);
+      if (dres) CT::store(dres + r * lddr + c, gv[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+#pragma unroll
+    for (int i = 0; i < EPC; ++i) {
+      const int c = (j * 32 + lane) * EPC + i;
+      red[(wib * 2) * C + c] = dg[j][i], red[(wib * 2 + 1) * C + c] = db[j][i];
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    const int which = c / C, cc = c - which * C;
+    float t = 0.f;
+    for (int w2 = 0; w2 < wpb; ++w2) t += red[(w2 * 2 + which) * C + cc];
+    partial[((int64_t)blockIdx.x * 2 + which) * C + cc] = t;
+  }
+}
+
+template <typename T, int NCH>
+int launch_ln_bwd_fast(const void* x, int64_t ldx, const float* gamma, const void* dy, int64_t lddy, const void* dz, int64_t lddz, const int32_t* idx,
+                       void* dx, int64_t lddx, void* dres, int64_t lddr, float* partial, int64_t blocks, int64_t rows, float eps, cudaStream_t s) {
+  constexpr int C = NCH * 32 * (16 / (int)sizeof(T));
+  const size_t smem = (size_t)8 * 2 * C * sizeof(float);
+  static bool attr_dev[kMaxDevices] = {};
+  if (smem > 48 * 1024 && !attr_dev[current_device()]) {
+    ANEMOI_CUDA(cudaFuncSetAttribute(layer_norm_bwd_fast_kernel<T, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_dev[current_device()] = true;
+  }
+  layer_norm_bwd_fast_kernel<T, NCH><<<(unsigned)blocks, 256, smem, s>>>((const T*)x, ldx, gamma, (const T*)dy, lddy, (const T*)dz, lddz, idx, (T*)dx, lddx,
+                                                                         (T*)dres, lddr, partial, rows, eps);
+  return launch_status("layer_norm_bwd_fast_kernel");
+}
+
 }  // namespace
 }  // namespace anemoi
 
@@ -241,6 +543,35 @@ extern "C" int anemoi_b200_gt_attention_bwd(const void* q, int64_t ldq, const vo
   ANEMOI_CHECK_ARG((e == nullptr) == (de == nullptr), "gt_attention_bwd: e and de go together");
   cudaStream_t s = (cudaStream_t)stream;
   const float scale = 1.0f / sqrtf((float)ch);
+  {
+    // fast forms: 16-byte aligned rows of exactly NCH * 32 chunks, heads of LPH chunks (cfg2: bf16, C = 512, Ch = 32 -> NCH 2, LPH 4)
+    const int es = dtype == ANEMOI_BF16 ? 2 : 4, epc = 16 / es;
+    const int64_t C = heads * ch;
+    auto al = [&](const void* p, int64_t ld) { return !p || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * es) % 16 == 0); };
+    const bool ok = ch % epc == 0 && C % (32 * epc) == 0 && al(q, ldq) && al(k, ldk) && al(v, ldv) && al(e, lde) && al(out, ldo) && al(dout, lddo) &&
+                    al(dq, lddq) && al(dk, lddk) && al(dv, lddv) && al(de, ldde) && dst32 && rev_eid32;
+    const int nch = ok ? (int)(C / (32 * epc)) : 0, lph = ok ? (int)(ch / epc) : 0;
+#define ANEMOI_BWD_FAST(T, NCH, LPH)                                                                                                                  \
+  return launch_bwd_fast<T, NCH, LPH>(q, ldq, k, ldk, v, ldv, e, lde, out, ldo, dout, lddo, lse, src32, colptr32, dst32, rev_ptr32, rev_eid32, dq, lddq, \
+                                      dk, lddk, dv, lddv, de, ldde, alpha_scratch, ds_scratch, n_src, n_dst, (int)heads, scale, s)
+    if (ok && dtype == ANEMOI_BF16) {
+      if (nch == 1 && lph == 4) ANEMOI_BWD_FAST(__nv_bfloat16, 1, 4);
+      if (nch == 2 && lph == 4) ANEMOI_BWD_FAST(__nv_bfloat16, 2, 4);
+      if (nch == 4 && lph == 4) ANEMOI_BWD_FAST(__nv_bfloat16, 4, 4);
+      if (nch == 1 && lph == 8) ANEMOI_BWD_FAST(__nv_bfloat16, 1, 8);
+      if (nch == 2 && lph == 8) ANEMOI_BWD_FAST(__nv_bfloat16, 2, 8);
+      if (nch == 4 && lph == 8) ANEMOI_BWD_FAST(__nv_bfloat16, 4, 8);
+      if (nch == 1 && lph == 2) ANEMOI_BWD_FAST(__nv_bfloat16, 1, 2);
+    } else if (ok) {
+      if (nch == 1 && lph == 4) ANEMOI_BWD_FAST(float, 1, 4);
+      if (nch == 2 && lph == 4) ANEMOI_BWD_FAST(float, 2, 4);
+      if (nch == 4 && lph == 8) ANEMOI_BWD_FAST(float, 4, 8);
+      if (nch == 2 && lph == 8) ANEMOI_BWD_FAST(float, 2, 8);
+      if (nch == 4 && lph == 16) ANEMOI_BWD_FAST(float, 4, 16);
+      if (nch == 8 && lph == 8) ANEMOI_BWD_FAST(float, 8, 8);
+    }
+#undef ANEMOI_BWD_FAST
+  }
   const int64_t cap = (int64_t)num_sms() * 8;
   if (n_dst > 0) {
     int64_t blocks = (n_dst * heads + 7) / 8;
@@ -286,6 +617,26 @@ extern "C" int anemoi_b200_layer_norm_bwd(const void* x, int64_t ldx, const floa
   if (blocks > n_partial) blocks = n_partial;
   if (blocks < 1) blocks = 1;
   ANEMOI_CUDA(cudaMemsetAsync(partial, 0, (size_t)n_partial * 2 * C * sizeof(float), (cudaStream_t)stream));
+  {
+    const int es = dtype == ANEMOI_BF16 ? 2 : 4, epc = 16 / es;
+    auto al = [&](const void* p, int64_t ld) { return !p || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * es) % 16 == 0); };
+    if (groups == 1 && C % (32 * epc) == 0 && al(x, ldx) && al(dy, lddy) && al(dz, lddz) && al(dx, lddx) && al(dres, lddr)) {
+      const int nch = (int)(C / (32 * epc));
+      cudaStream_t st = (cudaStream_t)stream;
+#define ANEMOI_LNB(T, NCH) return launch_ln_bwd_fast<T, NCH>(x, ldx, gamma, dy, lddy, dz, lddz, idx, dx, lddx, dres, lddr, partial, blocks, rows, eps, st)
+      if (dtype == ANEMOI_BF16) {
+        if (nch == 1) ANEMOI_LNB(__nv_bfloat16, 1);
+        if (nch == 2) ANEMOI_LNB(__nv_bfloat16, 2);
+        if (nch == 4) ANEMOI_LNB(__nv_bfloat16, 4);
+      } else {
+        if (nch == 1) ANEMOI_LNB(float, 1);
+        if (nch == 2) ANEMOI_LNB(float, 2);
+        if (nch == 4) ANEMOI_LNB(float, 4);
+        if (nch == 8) ANEMOI_LNB(float, 8);
+      }
+#undef ANEMOI_LNB
+    }
+  }
   const size_t smem = (size_t)8 * 2 * C * sizeof(float);
   if (dtype == ANEMOI_BF16) {
     static bool attr_dev[kMaxDevices] = {};
@@ -315,6 +666,21 @@ extern "C" int anemoi_b200_gelu(const void* x, int64_t ldx, const void* dy, int6
   ANEMOI_CHECK_ARG(dtype == ANEMOI_F32 || dtype == ANEMOI_BF16, "gelu: bad dtype %d", dtype);
   if (M * N == 0) return 0;
   ANEMOI_CHECK_ARG(x && y && (mode == 0 || dy), "gelu: null pointer");
+  {
+    const int es = dtype == ANEMOI_BF16 ? 2 : 4, epc = 16 / es;
+    auto al = [&](const void* p, int64_t ld) { return !p || ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * es) % 16 == 0); };
+    if (N % epc == 0 && al(x, ldx) && al(dy, lddy) && al(y, ldy)) {
+      int64_t vb = (M * (N / epc) + 255) / 256;
+      const int64_t vcap = (int64_t)num_sms() * 32;
+      if (vb > vcap) vb = vcap;
+      if (dtype == ANEMOI_BF16)
+        gelu_vec_kernel<__nv_bfloat16><<<(unsigned)vb, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)dy, lddy,
+                                                                                        (__nv_bfloat16*)y, ldy, M, N, mode);
+      else
+        gelu_vec_kernel<float><<<(unsigned)vb, 256, 0, (cudaStream_t)stream>>>((const float*)x, ldx, (const float*)dy, lddy, (float*)y, ldy, M, N, mode);
+      return launch_status("gelu_vec_kernel");
+    }
+  }
   int64_t blocks = (M * N + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;

@@ -84,7 +84,7 @@ class ReferenceStep:
 
         torch = self._torch
         bi = self.BSI(src_nodes=None, dst_nodes=None, edges=None)
-        with torch.no_grad():
+        with torch.set_grad_enabled(not getattr(self, "no_grad", True)):
             t0 = time.perf_counter()
             x_data_latent, x_latent = self.encoder((x_grid, x_mesh), 1, bi, gr["enc_attr"], gr["enc_index"], None)
             t1 = time.perf_counter()

@@ -72,4 +72,46 @@ for backend in ("triton", "pyg"):
         torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001 - report and go on with the other backend
         out[f"reference_{backend}"] = f"unavailable: {type(e).__name__}: {str(e)[:300]}"
+if "--train" in sys.argv:
+    # one TRAINING step (forward + backward of sum(output * w), bf16 autocast) of the same stack: our differentiable path (layers/_train.py:
+    # the sm_100a kernels through autograd Functions) against the reference's autograd (its Triton attention forward / backward kernels)
+    wgt = torch.randn(gr["n_grid"], w["out_grid"], generator=torch.Generator().manual_seed(7)).to(dev)
+
+    def train_step(fn, params):
+        for p in params:
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = fn()
+        (y.float() * wgt).sum().backward()
+
+    model.train()
+    ps = [p for p in model.parameters()]
+    out["ours_train_step_bf16_ms"] = timed(lambda: train_step(lambda: model(xg, xm, grd), ps), max(3, steps // 2))[0]
+    g_ours = {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None}
+    model.eval()
+    for backend in ("triton", "pyg"):
+        try:
+            ref = RS.ReferenceStep(w["kind"], state_dicts=sds, attention_backend=backend, **bench._ref_kwargs(w, gr)).to(dev)
+            for m in (ref.encoder, ref.processor, ref.decoder):
+                m.train()
+            rps = [p for m in (ref.encoder, ref.processor, ref.decoder) for p in m.parameters()]
+            ref.no_grad = False
+            ms = timed(lambda: train_step(lambda: ref(xg, xm, grd), rps), max(3, steps // 2))[0]
+            # per-parameter rel-L2 of the gradients, both sides bf16 autocast.  Some gradients are zero by construction (lin_key.bias: a constant
+            # added to every key drops out of the softmax) and hold only rounding noise: a tensor's norm is floored at 1e-3 of the largest one.
+            pairs = []
+            for part in ("encoder", "processor", "decoder"):
+                for n, p in getattr(ref, part).named_parameters():
+                    go = g_ours.get(f"{part}.{n}")
+                    if go is not None and p.grad is not None:
+                        pairs.append((f"{part}.{n}", go, p.grad.float()))
+            big = max(gr_.norm().item() for _, _, gr_ in pairs)
+            errs = sorted((((go - gr_).norm() / max(gr_.norm().item(), 1e-3 * big)).item(), n) for n, go, gr_ in pairs)
+            out[f"reference_{backend}_train_step_bf16"] = {"ms_per_step_eager": ms, "param_grads_compared": len(pairs),
+                                                           "median_param_grad_rel_l2": round(errs[len(errs) // 2][0], 5),
+                                                           "worst_param_grad_rel_l2": [round(errs[-1][0], 5), errs[-1][1]]}  # fmt: skip
+            del ref
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            out[f"reference_{backend}_train"] = f"unavailable: {type(e).__name__}: {str(e)[:300]}"
 print(json.dumps(out))

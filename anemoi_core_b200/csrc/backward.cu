@@ -526,6 +526,36 @@ int launch_ln_bwd_fast(const void* x, int64_t ldx, const float* gamma, const voi
   return launch_status("layer_norm_bwd_fast_kernel");
 }
 
+// out[n] = sum over j in [ptr[n], ptr[n+1]) of rows[eid ? eid[j] : j]  — the backward of a row gather table[idx] when the gathering index
+// list is sorted (ptr = CSR offsets of the dst-sorted edges, eid = null) or comes with its reverse CSR (ptr / eid = edges grouped by source).
+// Deterministic (fixed order, fp32 accumulation), one warp per output row, 16-byte chunks; replaces PyTorch's index_add_ (atomics:
+// 3.6 ms per [327 600, 1024] bf16 cotangent on a B200, against ~0.2 ms for the read).
+template <typename T>
+__global__ void __launch_bounds__(256) segment_sum_kernel(const T* __restrict__ rows, int64_t ld, const int32_t* __restrict__ ptr,
+                                                          const int32_t* __restrict__ eid, T* __restrict__ out, int64_t ldo, int64_t n_out, int C) {
+  using CT = BwdChunk<T>;
+  constexpr int EPC = CT::EPC;
+  const int lane = threadIdx.x & 31;
+  const int chunks = C / EPC;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); n < n_out; n += warps_total) {
+    const int j0 = __ldg(ptr + n), j1 = __ldg(ptr + n + 1);
+    for (int c = lane; c < chunks; c += 32) {
+      float acc[EPC];
+#pragma unroll
+      for (int i = 0; i < EPC; ++i) acc[i] = 0.f;
+      for (int j = j0; j < j1; ++j) {
+        const int64_t r = eid ? (int64_t)__ldg(eid + j) : (int64_t)j;
+        float f[EPC];
+        CT::load(rows + r * ld + c * EPC, f);
+#pragma unroll
+        for (int i = 0; i < EPC; ++i) acc[i] += f[i];
+      }
+      CT::store(out + n * ldo + c * EPC, acc);
+    }
+  }
+}
+
 }  // namespace
 }  // namespace anemoi
 
@@ -690,4 +720,25 @@ extern "C" int anemoi_b200_gelu(const void* x, int64_t ldx, const void* dy, int6
   else
     gelu_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)x, ldx, (const float*)dy, lddy, (float*)y, ldy, M, N, mode);
   return launch_status("gelu_kernel");
+}
+
+extern "C" int anemoi_b200_segment_sum(const void* rows, int64_t ld, const int32_t* ptr32, const int32_t* eid32, void* out, int64_t ldo, int64_t n_out,
+                                       int64_t C, int dtype, void* stream) {
+  ANEMOI_CHECK_ARG(n_out >= 0 && C >= 1 && ld >= C && ldo >= C, "segment_sum: bad shape");
+  ANEMOI_CHECK_ARG(dtype == ANEMOI_F32 || dtype == ANEMOI_BF16, "segment_sum: bad dtype %d", dtype);
+  if (n_out == 0) return 0;
+  ANEMOI_CHECK_ARG(ptr32 && out, "segment_sum: null pointer");
+  const int es = dtype == ANEMOI_BF16 ? 2 : 4;
+  ANEMOI_CHECK_ARG(C % (16 / es) == 0 && (!rows || (reinterpret_cast<uintptr_t>(rows) & 15) == 0) && (ld * es) % 16 == 0 &&
+                       (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo * es) % 16 == 0,
+                   "segment_sum: rows of whole 16-byte chunks, 16-byte aligned");
+  int64_t blocks = (n_out + 7) / 8;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (dtype == ANEMOI_BF16)
+    segment_sum_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)rows, ld, ptr32, eid32, (__nv_bfloat16*)out,
+                                                                                          ldo, n_out, (int)C);
+  else
+    segment_sum_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)rows, ld, ptr32, eid32, (float*)out, ldo, n_out, (int)C);
+  return launch_status("segment_sum_kernel");
 }

@@ -117,10 +117,9 @@ def graph_conv(conv, x_src: Tensor, x_dst: Tensor, e: Tensor, csr, dt: torch.dty
     else:
         w1, b1 = mods[0].weight, mods[0].bias
     e = e.to(dt)
-    z = AG.linear(e, w1[:, 2 * C :], b1, dt)
     p_i = AG.linear(x_dst, w1[:, :C], None, dt)
     p_j = AG.linear(x_src, w1[:, C : 2 * C], None, dt)
-    z = z + p_i.index_select(0, csr.dst32.long()) + p_j.index_select(0, csr.src32.long())
+    z = AG.edge_first_layer(e, w1[:, 2 * C :], b1, p_i, p_j, csr, dt)  # e W_e^T + b + p_i[dst] + p_j[src], gathers in the GEMM epilogue
     if gated0:
         h, i = AG.glu_combine(z, mods[0].kind), 1
     else:

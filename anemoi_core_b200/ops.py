@@ -825,6 +825,18 @@ def gt_attention_bwd(q: Tensor, k: Tensor, v: Tensor, e_proj: Optional[Tensor], 
     return dq, dk, dv, de
 
 
+def segment_sum(rows: Tensor, ptr32: Tensor, eid32: Optional[Tensor], n_out: int) -> Tensor:
+    """``out[n] = sum_{j in [ptr32[n], ptr32[n+1])} rows[eid32[j] if eid32 is not None else j]`` (fp32 accumulation, deterministic): the backward
+    of a row gather over a sorted index list / its reverse CSR."""
+    _need_cuda(rows, ptr32, eid32)
+    _, C, ld = _rows(rows)
+    out = torch.empty((n_out, C), dtype=rows.dtype, device=rows.device)
+    with _Timed("segment_sum", 1.0 * rows.shape[0] * C, _nbytes(rows, out)):
+        rc = _lib.load().anemoi_b200_segment_sum(_ptr(rows), ld, _ptr(ptr32), _ptr(eid32), _ptr(out), C, n_out, C, dtype_code(rows.dtype), _stream())
+    _lib.check(rc, "anemoi_b200_segment_sum")
+    return out
+
+
 _LN_BWD_BLOCKS = 592  # partial-sum rows of dgamma / dbeta: 4 CTAs per SM
 
 

@@ -204,6 +204,13 @@ ANEMOI_API int anemoi_b200_layer_norm_bwd(const void* x, int64_t ldx, const floa
 ANEMOI_API int anemoi_b200_gelu(const void* x, int64_t ldx, const void* dy, int64_t lddy, void* y, int64_t ldy, int64_t M, int64_t N, int mode,
                      int dtype, void* stream);
 
+/* Backward of a row gather (training of GraphConv: the gradient of x_i = x_dst[dst], x_j = x_src[src]; PyTorch autograd's index_add_ in the
+ * reference): out[n] = sum over j in [ptr32[n], ptr32[n+1]) of rows[eid32 ? eid32[j] : j].  With the dst-sorted edge list, ptr32 = colptr32 and
+ * eid32 = NULL give the gradient of table[dst]; with the reverse CSR (edges grouped by source) the gradient of table[src].  Deterministic,
+ * fp32 accumulation, no atomics.  rows : [*, ld], out : [n_out, ldo] of `dtype`, C a multiple of 16 bytes. */
+ANEMOI_API int anemoi_b200_segment_sum(const void* rows, int64_t ld, const int32_t* ptr32, const int32_t* eid32, void* out, int64_t ldo, int64_t n_out,
+                                       int64_t C, int dtype, void* stream);
+
 /* -- multi-GPU exchange over NVLink peer memory (one process per GPU, one NVSwitch box) ---------------------------------
  * Replaces, for the dst-range sharded forward, the NCCL collectives of the reference: `halo_exchange` (distributed/graph.py:466-484,
  * layers/block.py:1159-1169) and the source-row all-gather `sync_tensor` (graph.py:227-240).  Ranks write the rows their peers need

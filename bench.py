@@ -13,8 +13,11 @@ Printed JSON (one line, rank 0):
   e2e                 : same step through the public module API with HOST (pinned) input buffers: H2D of the inputs,
                         the step, D2H of the output, all inside the timed region.
   roofline            : dominant kernel class measured live with CUDA events around every C-ABI launch (eager pass).
-  cpu_baseline        : the oracle port (oracle/restatement.py, fp32, all host threads) on a bounded sample, rank 0, N=1.
-  --impl reference    : the reference's CPU path (oracle port: the Python reference cannot travel to the GPU box).
+  cpu_baseline        : the UNMODIFIED reference modules (baseline/_ref + oracle/standins; the oracle port when they are absent) on the host
+                        cores, fp32, rank 0, N=1.
+  reference_gpu       : context, N=1: the same unmodified reference modules run on THIS GPU through their own code path (PyTorch + the
+                        reference's Triton attention backend, bf16 autocast, eager) - ms/step and the difference to our output.
+  --impl reference    : the reference's CPU path (the reference arm of the contract), whole steps.
 """
 
 from __future__ import annotations
@@ -260,6 +263,41 @@ def single_gpu_rows(model, w, gd, x_full, x_grid, x_mesh, grid_shards, dev, n_ou
 
 
 # ----------------------------------------------------------------------------------------------------------------
+def reference_gpu(w, gr, sds, x_grid, x_mesh, dev, ours_out, n_timed=5):
+    """CONTEXT number, N = 1 only: the UNMODIFIED reference modules (baseline/_ref + oracle/standins) run on the same GPU through their own code
+    path - PyTorch / cuBLAS and the reference's Triton attention backend (its fastest) - under bf16 autocast, eager, CUDA events, L2 flushed.
+    The reference arm of the contract stays the CPU path (--impl reference); this says what the reference's own GPU path does on this box."""
+    try:
+        from oracle import reference_step as RS
+
+        if RS.reference_root() is None:
+            return {"unavailable": "baseline/_ref not on this box"}
+        backend = "triton" if w["kind"] == "graphtransformer" else "pyg"
+        ref = RS.ReferenceStep(w["kind"], state_dicts=sds, attention_backend=backend, **_ref_kwargs(w, gr)).to(dev)
+        grd = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in gr.items()}
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ts = []
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            for i in range(3 + n_timed):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                y = ref(x_grid, x_mesh, grd)
+                b.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ts.append(a.elapsed_time(b))
+        d = ours_out.float() - y.float()
+        res = {"value": statistics.median(ts), "unit": "ms/step", "launch": "eager", "attention_backend": backend, "dtype": "bf16 autocast",
+               "kind": "unmodified reference modules on the same GPU (PyTorch + its Triton kernel)", "steps": n_timed,
+               "rel_l2_ours_vs_reference": (d.norm() / y.float().norm()).item()}
+        del ref
+        torch.cuda.empty_cache()
+        return res
+    except Exception as e:  # noqa: BLE001 - context only: never fail the bench line
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -269,6 +307,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))  # cfg2 = BASELINE.json configs[1] (the metric's config)
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the context run of the unmodified reference on the GPU (N = 1)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -543,6 +582,10 @@ def main():
     }  # fmt: skip
     if rollout is not None:
         line["rollout"] = rollout
+    if world == 1 and not args.no_reference_gpu and w["C"] <= 512:
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            y_ours = step(x_grid, x_mesh)
+        line["reference_gpu"] = reference_gpu(w, gr, sds if sds is not None else state_dicts(model), x_grid, x_mesh, dev, y_ours)
     if sds is not None:
         line["cpu_baseline"] = cpu_baseline(w, gr, sds, x_grid_h, x_mesh_h)
     else:

@@ -434,37 +434,57 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
           pf_issue();
         }
       }
+      // Per-column additive term of the whole round (bias, or for the folded LayerNorm s * (-rstd * mean) + b), loaded from shared memory
+      // BEFORE any of the round's shared-memory stores.  The loads and stores are volatile asm and keep their order, so with the loads
+      // inside the 8-column groups every group waited for the previous group's store - its LDS, its FFMA2 / MUFU chain and its STS ran as
+      // four serial latency chains per round (SASS: [LDS x4, MUFU x8, F2FP x4, STS] x 4).  Hoisted, the 16 column pairs of a round are
+      // independent chains and the SASS interleaves them.  Measured (profiles/r2/call43_ab_epilogue_hoist.txt, same call): the replayed cfg2
+      // step 8.33 / 8.36 ms against 8.44 / 8.41 ms, the isolated kernels unchanged to 2 % slower (142 registers instead of 104) - a small
+      // gain, i.e. the serialisation was not what paces the GELU rounds either.
+      const bool has_bias = ep.bias && !ABL(kAblNoBias);
+      float cadd[CW];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cadd[g * 8 + j] = 0.f;
+        if (has_bias) {
+          const uint32_t ba = cx.bias_smem + (uint32_t)(col_in_tile + g * 8) * 4u;
+          const uint4 b0 = ptx::lds128(ba), b1 = ptx::lds128(ba + 16);
+          cadd[g * 8 + 0] = __uint_as_float(b0.x), cadd[g * 8 + 1] = __uint_as_float(b0.y), cadd[g * 8 + 2] = __uint_as_float(b0.z);
+          cadd[g * 8 + 3] = __uint_as_float(b0.w), cadd[g * 8 + 4] = __uint_as_float(b1.x), cadd[g * 8 + 5] = __uint_as_float(b1.y);
+          cadd[g * 8 + 6] = __uint_as_float(b1.z), cadd[g * 8 + 7] = __uint_as_float(b1.w);
+        }
+        if constexpr (LNF) {
+          const uint32_t sa = cx.bias_smem + 1024u + (uint32_t)(col_in_tile + g * 8) * 4u;
+          const uint4 s0 = ptx::lds128(sa), s1 = ptx::lds128(sa + 16);
+          // rstd * (acc - mean * s) + b = acc * rstd + (s * (-rstd * mean) + b): two packed FMAs per pair of columns
+          const float2 m2 = make_float2(-ln_rstd * ln_mean, -ln_rstd * ln_mean);
+          const float sv[8] = {__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s0.z), __uint_as_float(s0.w),
+                               __uint_as_float(s1.x), __uint_as_float(s1.y), __uint_as_float(s1.z), __uint_as_float(s1.w)};
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float2 c2 = __ffma2_rn(make_float2(sv[j], sv[j + 1]), m2, make_float2(cadd[g * 8 + j], cadd[g * 8 + j + 1]));
+            cadd[g * 8 + j] = c2.x, cadd[g * 8 + j + 1] = c2.y;
+          }
+        }
+      }
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
         const int col = col0 + g * 8;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-        const bool has_bias = ep.bias && !ABL(kAblNoBias);
-        float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (has_bias) {
-          const uint32_t ba = cx.bias_smem + (uint32_t)(col_in_tile + g * 8) * 4u;
-          const uint4 b0 = ptx::lds128(ba), b1 = ptx::lds128(ba + 16);
-          bv[0] = __uint_as_float(b0.x), bv[1] = __uint_as_float(b0.y), bv[2] = __uint_as_float(b0.z), bv[3] = __uint_as_float(b0.w);
-          bv[4] = __uint_as_float(b1.x), bv[5] = __uint_as_float(b1.y), bv[6] = __uint_as_float(b1.z), bv[7] = __uint_as_float(b1.w);
-        }
         if constexpr (LNF) {
-          const uint32_t sa = cx.bias_smem + 1024u + (uint32_t)(col_in_tile + g * 8) * 4u;
-          const uint4 s0 = ptx::lds128(sa), s1 = ptx::lds128(sa + 16);
-          // rstd * (acc - mean * s) + b = acc * rstd + (s * (-rstd * mean) + b): two packed FMAs per pair of columns
-          const float2 r2 = make_float2(ln_rstd, ln_rstd), m2 = make_float2(-ln_rstd * ln_mean, -ln_rstd * ln_mean);
-          const float sv[8] = {__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s0.z), __uint_as_float(s0.w),
-                               __uint_as_float(s1.x), __uint_as_float(s1.y), __uint_as_float(s1.z), __uint_as_float(s1.w)};
+          const float2 r2 = make_float2(ln_rstd, ln_rstd);
 #pragma unroll
           for (int j = 0; j < 8; j += 2) {
-            const float2 c2 = __ffma2_rn(make_float2(sv[j], sv[j + 1]), m2, make_float2(bv[j], bv[j + 1]));
-            const float2 t2 = __ffma2_rn(make_float2(v[j], v[j + 1]), r2, c2);
+            const float2 t2 = __ffma2_rn(make_float2(v[j], v[j + 1]), r2, make_float2(cadd[g * 8 + j], cadd[g * 8 + j + 1]));
             v[j] = t2.x, v[j + 1] = t2.y;
           }
         } else if (has_bias) {
 #pragma unroll
           for (int j = 0; j < 8; j += 2) {
-            const float2 t2 = __fadd2_rn(make_float2(v[j], v[j + 1]), make_float2(bv[j], bv[j + 1]));
+            const float2 t2 = __fadd2_rn(make_float2(v[j], v[j + 1]), make_float2(cadd[g * 8 + j], cadd[g * 8 + j + 1]));
             v[j] = t2.x, v[j + 1] = t2.y;
           }
         }

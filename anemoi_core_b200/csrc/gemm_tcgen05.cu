@@ -971,7 +971,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensor
   attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cfg.attrs = attr, cfg.numAttrs = (pdl_enabled() && !(ep.flags & ANEMOI_EPI_NOPDL)) ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CG, RESD>, tmA, tmW, tmOut, tmRes, num_kb, tiles_m, tiles_n, epi_mode, ep);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_bf16_tcgen05_kernel)");
   return launch_status("gemm_bf16_tcgen05_kernel");

@@ -319,7 +319,7 @@ def _fp32_on_tensor_cores(a: Tensor, weight: Tensor) -> Optional[tuple]:
     return split_bf16x3(a, False), w6
 
 
-def linear(
+def _linear_one(
     a: Tensor,
     weight: Tensor,
     bias: Optional[Tensor] = None,
@@ -334,6 +334,7 @@ def linear(
     ln_dim: int = 0,
     ln_eps: float = 0.0,
     stats_out: Optional[Tensor] = None,
+    _nopdl: bool = False,
 ) -> Tensor:
     """out = [gelu](a @ weight.T + bias + g1[idx1] + g2[idx2]) + residual.
 
@@ -409,9 +410,73 @@ def linear(
         _need_cuda(ln_stats, ln_colsum, stats_out)
         rc = _lib.load().anemoi_b200_linear(
             _ptr(a), lda, _ptr(weight), ldw, dtype_code(a.dtype), _ptr(_f32(bias)), _ptr(g1), _ptr(i1), _ptr(g2), _ptr(i2), ldg, _ptr(residual),
-            ldr, rdt, _ptr(out), ldo, dtype_code(out.dtype), M, N, K, (EPI_GELU if gelu else 0) | _rev("gemm"), _ptr(ln_stats), _ptr(_f32(ln_colsum)),
+            ldr, rdt, _ptr(out), ldo, dtype_code(out.dtype), M, N, K, (EPI_GELU if gelu else 0) | _rev("gemm") | (4 if _nopdl else 0), _ptr(ln_stats), _ptr(_f32(ln_colsum)),
             ln_parts, int(ln_dim), float(ln_eps), _ptr(stats_out), _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_linear")
+    return out
+
+
+# ---- tail-wave split of narrow GEMMs ---------------------------------------------------------------------------------------------
+# The CTA-pair GEMM walks 256 x 256 tiles on 74 pairs.  For N <= 512 a cfg2-sized problem (40 962 rows: 161 row tiles x 2) is 4.35 waves: the
+# fifth wave keeps 26 of 74 pairs busy for a full tile time.  Split by rows instead: whole waves on the current stream, the remaining rows
+# as a second launch on a forked stream (it only depends on what the first depends on; its small problem takes the 128 x 128 single-CTA
+# tiles, half the per-SM work), whose CTAs fill the SMs as the first launch's CTAs retire; the current stream joins before going on.
+# Graph-capturable (fork / join through events).  Opt-in (ANEMOI_B200_TAIL_SPLIT=1) until its A/B is on record.
+TAIL_SPLIT = os.environ.get("ANEMOI_B200_TAIL_SPLIT", "0") != "0"
+_SIDE = {}
+
+
+def _tail_split_rows(a: Tensor, weight: Tensor, kw: dict) -> int:
+    """Rows of the whole-wave part when this GEMM should be split (0 = run it as one launch)."""
+    if not TAIL_SPLIT or a.dtype != torch.bfloat16 or weight.shape[0] > 512 or kw.get("stats_out") is not None:
+        return 0
+    M, N = a.shape[0], weight.shape[0]
+    pairs = torch.cuda.get_device_properties(a.device).multi_processor_count // 2
+    tiles_n = -(-N // 256)
+    row_tiles = -(-M // 256)
+    if row_tiles * tiles_n < 2 * pairs:  # not the CTA-pair kernel (linear_tcgen05's own rule)
+        return 0
+    per_wave = pairs // tiles_n  # row tiles per full wave
+    full = row_tiles // per_wave
+    rest = row_tiles - full * per_wave
+    if full < 2 or rest == 0 or rest * tiles_n > 0.6 * pairs:  # a tail wave that is more than ~60 % full is not worth a second launch
+        return 0
+    return full * per_wave * 256
+
+
+def linear(a: Tensor, weight: Tensor, bias: Optional[Tensor] = None, **kw) -> Tensor:
+    """``_linear_one`` (see there for the arguments), with the tail wave of a narrow GEMM launched on a forked stream."""
+    rows = _tail_split_rows(a, weight, kw) if a.is_cuda else 0
+    if not rows:
+        return _linear_one(a, weight, bias, **kw)
+    M, N = a.shape[0], weight.shape[0]
+    out = kw.pop("out", None)
+    if out is None:
+        out = torch.empty((M, N), dtype=kw.get("out_dtype") or a.dtype, device=a.device)
+
+    def part(sl):
+        k2 = dict(kw)
+        for name in ("residual", "ln_stats"):
+            if k2.get(name) is not None:
+                k2[name] = k2[name][sl]
+        for name in ("gather1", "gather2"):
+            if k2.get(name) is not None:
+                k2[name] = (k2[name][0], k2[name][1][sl])
+        return _linear_one(a[sl], weight, bias, out=out[sl], _nopdl=sl.start != 0, **k2)  # the forked launch follows an event wait: plain launch
+
+    cur = torch.cuda.current_stream(a.device)
+    side = _SIDE.get(a.device.index)
+    if side is None:
+        side = _SIDE[a.device.index] = torch.cuda.Stream(a.device)
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    part(slice(0, rows))
+    side.wait_event(fork)
+    with torch.cuda.stream(side):
+        part(slice(rows, M))
+        join = torch.cuda.Event()
+        join.record(side)
+    cur.wait_event(join)
     return out
 
 

@@ -41,6 +41,7 @@ extern "C" {
 
 /* anemoi_b200_linear flags */
 #define ANEMOI_EPI_GELU 1 /* exact (erf) GELU after bias/gather-add, before residual  (torch.nn.GELU default) */
+#define ANEMOI_EPI_NOPDL 4 /* launch without the programmatic-dependent-launch attribute (a launch that follows a cross-stream event wait) */
 #define ANEMOI_EPI_REVERSE 2 /* scheduling hint, results unchanged: walk the row blocks from the last to the first, so that a GEMM
                               * consuming what the previous kernel wrote last starts where L2 still holds it (bf16 tcgen05 path) */
 

@@ -592,3 +592,34 @@ def test_fp32_linear_on_tensor_cores_is_fp32_grade(ops, M, N, K):
     finally:
         ops.FP32_TC = old
     assert ((y3 - ref).abs().max() / ref.abs().max()).item() <= 5e-6
+
+
+def test_linear_tail_wave_split_matches_single_launch(ops):
+    """Narrow GEMMs (N <= 512) on cfg2-sized row counts run their last, partially filled wave as a second launch on a forked stream
+    (``ops.TAIL_SPLIT``): same result as the single launch, also under CUDA-graph capture."""
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 40962, 512, 704
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K, generator=g) / K**0.5).to(torch.bfloat16).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    r = torch.randn(M, N, generator=g).to(torch.bfloat16).cuda()
+    old = ops.TAIL_SPLIT
+    try:
+        ops.TAIL_SPLIT = False
+        y_one = ops.linear(a, w, b, residual=r)
+        ops.TAIL_SPLIT = True
+        assert ops._tail_split_rows(a, w, {}) == 37888
+        y_split = ops.linear(a, w, b, residual=r)
+        assert torch.equal(y_split, y_one)
+        out = torch.empty_like(y_one)
+        ops.linear(a, w, b, residual=r, out=out)  # warm-up outside the capture (descriptor cache, side stream)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ops.linear(a, w, b, residual=r, out=out)
+        out.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, y_one)
+    finally:
+        ops.TAIL_SPLIT = old

@@ -421,7 +421,9 @@ def _linear_one(
 # fifth wave keeps 26 of 74 pairs busy for a full tile time.  Split by rows instead: whole waves on the current stream, the remaining rows
 # as a second launch on a forked stream (it only depends on what the first depends on; its small problem takes the 128 x 128 single-CTA
 # tiles, half the per-SM work), whose CTAs fill the SMs as the first launch's CTAs retire; the current stream joins before going on.
-# Graph-capturable (fork / join through events).  Opt-in (ANEMOI_B200_TAIL_SPLIT=1) until its A/B is on record.
+# Graph-capturable (fork / join through events).  Measured (profiles/r2/call45_ab_tail_split.txt, same call): SLOWER - projection 43.0 -> 54.6 us,
+# MLP-2 80.7 -> 84.5 us, cfg2 step 8.43 -> 8.54 ms: the second launch's fill and the fork / join cost more than the idle pairs.  Opt-in
+# (ANEMOI_B200_TAIL_SPLIT=1), off by default.
 TAIL_SPLIT = os.environ.get("ANEMOI_B200_TAIL_SPLIT", "0") != "0"
 _SIDE = {}
 

@@ -17,5 +17,3 @@ for v in split1 split0 split1b split0b; do
 import json; d=json.load(open('gpurun_out/r2/c45_bench_$v.json')); print('$v', d['value'], d['e2e']['value'], d['parity'], d['launches_per_step'])" | tee -a $O || tail -5 gpurun_out/r2/c45_bench_$v.err
 done
 grep -E "variant|us_median" $O | cut -c1-180
-timeout 600 python -m pytest tests/test_gpu_graphconv_fused.py -x -q > gpurun_out/r2/c45_tests_gcf.log 2>&1; tail -2 gpurun_out/r2/c45_tests_gcf.log
-timeout 600 python profiles/bench_kernels.py gcf nodecomp --reps 10 > gpurun_out/r2/c45_kernels_gcf.jsonl 2>&1; cut -c1-260 gpurun_out/r2/c45_kernels_gcf.jsonl

@@ -291,28 +291,40 @@ __global__ void __launch_bounds__(TE * 2) graphconv_fused_kernel(const Params p)
           }
         }
         // LayerNorm over the row (two-pass, the row lives in the 4 lanes of a quad), + e, written in place over the e columns
-        float s0 = 0.f, s1 = 0.f;
+        // (packed fp32x2 arithmetic throughout: the kernel is bound by instruction issue, two columns per issue slot)
+        float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < C / 8; ++j) s0 += acc[j][0] + acc[j][1], s1 += acc[j][2] + acc[j][3];
+        for (int j = 0; j < C / 8; ++j) {
+          sa = __fadd2_rn(sa, make_float2(acc[j][0], acc[j][1]));
+          sb = __fadd2_rn(sb, make_float2(acc[j][2], acc[j][3]));
+        }
+        float s0 = sa.x + sa.y, s1 = sb.x + sb.y;
         s0 += __shfl_xor_sync(0xffffffffu, s0, 1), s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
         s0 += __shfl_xor_sync(0xffffffffu, s0, 2), s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
         const float m0 = s0 * (1.0f / C), m1 = s1 * (1.0f / C);
-        float q0 = 0.f, q1 = 0.f;
+        const float2 nm0 = make_float2(-m0, -m0), nm1 = make_float2(-m1, -m1);
+        float2 qa = make_float2(0.f, 0.f), qb = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < C / 8; ++j) {
-          const float a0 = acc[j][0] - m0, a1 = acc[j][1] - m0, a2 = acc[j][2] - m1, a3 = acc[j][3] - m1;
-          q0 += a0 * a0 + a1 * a1, q1 += a2 * a2 + a3 * a3;
+          const float2 da = __fadd2_rn(make_float2(acc[j][0], acc[j][1]), nm0), db = __fadd2_rn(make_float2(acc[j][2], acc[j][3]), nm1);
+          qa = __ffma2_rn(da, da, qa), qb = __ffma2_rn(db, db, qb);
         }
+        float q0 = qa.x + qa.y, q1 = qb.x + qb.y;
         q0 += __shfl_xor_sync(0xffffffffu, q0, 1), q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
         q0 += __shfl_xor_sync(0xffffffffu, q0, 2), q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
         const float rs0 = rsqrtf(q0 * (1.0f / C) + p.eps), rs1 = rsqrtf(q1 * (1.0f / C) + p.eps);
+        const float2 r0v = make_float2(rs0, rs0), r1v = make_float2(rs1, rs1);
         const uint32_t erow0 = tile + (uint32_t)((r0 + g) * G::kTilePitch + 2 * C * ES + tq * 4), erow1 = erow0 + 8 * G::kTilePitch;
 #pragma unroll
         for (int j = 0; j < C / 8; ++j) {
+          // (x - m) rstd gamma + beta + e  =  x * (rstd gamma) + (beta + e - m rstd gamma): four packed operations per column pair and row
           const float2 gm = lds64f(s_gamma + tq * 8 + j * 32), bt = lds64f(s_beta + tq * 8 + j * 32);
           const float2 e0 = unpack_bf16x2(lds32(erow0 + j * 16)), e1 = unpack_bf16x2(lds32(erow1 + j * 16));
-          sts32(erow0 + j * 16, pack_bf16x2((acc[j][0] - m0) * rs0 * gm.x + bt.x + e0.x, (acc[j][1] - m0) * rs0 * gm.y + bt.y + e0.y));
-          sts32(erow1 + j * 16, pack_bf16x2((acc[j][2] - m1) * rs1 * gm.x + bt.x + e1.x, (acc[j][3] - m1) * rs1 * gm.y + bt.y + e1.y));
+          const float2 sc0 = __fmul2_rn(gm, r0v), sc1 = __fmul2_rn(gm, r1v);
+          const float2 c0 = __ffma2_rn(nm0, sc0, __fadd2_rn(bt, e0)), c1 = __ffma2_rn(nm1, sc1, __fadd2_rn(bt, e1));
+          const float2 y0 = __ffma2_rn(make_float2(acc[j][0], acc[j][1]), sc0, c0), y1 = __ffma2_rn(make_float2(acc[j][2], acc[j][3]), sc1, c1);
+          sts32(erow0 + j * 16, pack_bf16x2(y0.x, y0.y));
+          sts32(erow1 + j * 16, pack_bf16x2(y1.x, y1.y));
         }
       } else {
         // ================= fp32 parity mode: FFMA, lane = output column =================

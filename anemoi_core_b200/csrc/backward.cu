@@ -406,8 +406,10 @@ __global__ void __launch_bounds__(256) gelu_vec_kernel(const T* __restrict__ x, 
     float v[EPC], r[EPC];
     CT::load(x + m * ldx + n, v);
     if (mode == 0) {
+      // the same one-MUFU form as the GEMM epilogues (|error| <= 5e-7): with erff the forward pass was issue-bound (ncu: issue slots 80 %
+      // busy, DRAM 33 %, 107 us for a [40 962, 2048] bf16 tensor)
 #pragma unroll
-      for (int j = 0; j < EPC; ++j) r[j] = gelu_erf(v[j]);
+      for (int j = 0; j < EPC; ++j) r[j] = gelu_erf_fast(v[j]);
     } else {
       float g[EPC];
       CT::load(dy + m * lddy + n, g);

@@ -263,37 +263,29 @@ def single_gpu_rows(model, w, gd, x_full, x_grid, x_mesh, grid_shards, dev, n_ou
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def reference_gpu(w, gr, sds, x_grid, x_mesh, dev, ours_out, n_timed=5):
+def reference_gpu(workload: str, w, timeout_s: int = 240):
     """CONTEXT number, N = 1 only: the UNMODIFIED reference modules (baseline/_ref + oracle/standins) run on the same GPU through their own code
-    path - PyTorch / cuBLAS and the reference's Triton attention backend (its fastest) - under bf16 autocast, eager, CUDA events, L2 flushed.
+    path - PyTorch / cuBLAS and the reference's Triton attention backend (its fastest) - under bf16 autocast, eager, CUDA events, L2 flushed
+    (profiles/bench_reference_gpu.py --bench-leg, in a SUBPROCESS with a timeout: whatever happens there cannot take the bench line down).
     The reference arm of the contract stays the CPU path (--impl reference); this says what the reference's own GPU path does on this box."""
     try:
         from oracle import reference_step as RS
 
         if RS.reference_root() is None:
             return {"unavailable": "baseline/_ref not on this box"}
+        cmd = [sys.executable, os.path.join(ROOT, "profiles", "bench_reference_gpu.py"), "--workload", workload, "--steps", "5", "--bench-leg"]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"unavailable": f"rc {r.returncode}: {(r.stderr or r.stdout)[-200:]}"}
+        d = json.loads(lines[-1])
         backend = "triton" if w["kind"] == "graphtransformer" else "pyg"
-        ref = RS.ReferenceStep(w["kind"], state_dicts=sds, attention_backend=backend, **_ref_kwargs(w, gr)).to(dev)
-        grd = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in gr.items()}
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        ts = []
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            for i in range(3 + n_timed):
-                flush.zero_()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                y = ref(x_grid, x_mesh, grd)
-                b.record()
-                torch.cuda.synchronize()
-                if i >= 3:
-                    ts.append(a.elapsed_time(b))
-        d = ours_out.float() - y.float()
-        res = {"value": statistics.median(ts), "unit": "ms/step", "launch": "eager", "attention_backend": backend, "dtype": "bf16 autocast",
-               "kind": "unmodified reference modules on the same GPU (PyTorch + its Triton kernel)", "steps": n_timed,
-               "rel_l2_ours_vs_reference": (d.norm() / y.float().norm()).item()}
-        del ref
-        torch.cuda.empty_cache()
-        return res
+        ref = d.get(f"reference_{backend}_bf16")
+        if not isinstance(ref, dict):
+            return {"unavailable": str(d.get(f"reference_{backend}", "no reference line"))[:200]}
+        return {"value": ref["ms_per_step_eager"], "unit": "ms/step", "launch": "eager", "attention_backend": backend, "dtype": "bf16 autocast",
+                "kind": "unmodified reference modules on the same GPU (PyTorch + its Triton kernel)", "steps": 5,
+                "ours_eager_ms_same_process": d.get("ours_eager_bf16_ms"), "rel_l2_ours_vs_reference": ref["rel_l2_ours_vs_reference"]}
     except Exception as e:  # noqa: BLE001 - context only: never fail the bench line
         return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
 
@@ -582,10 +574,8 @@ def main():
     }  # fmt: skip
     if rollout is not None:
         line["rollout"] = rollout
-    if world == 1 and not args.no_reference_gpu and w["C"] <= 512:
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-            y_ours = step(x_grid, x_mesh)
-        line["reference_gpu"] = reference_gpu(w, gr, sds if sds is not None else state_dicts(model), x_grid, x_mesh, dev, y_ours)
+    if world == 1 and not args.no_reference_gpu and w["C"] <= 512 and "rollout" not in w:
+        line["reference_gpu"] = reference_gpu(args.workload, w)
     if sds is not None:
         line["cpu_baseline"] = cpu_baseline(w, gr, sds, x_grid_h, x_mesh_h)
     else:

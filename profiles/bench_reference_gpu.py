@@ -22,6 +22,7 @@ from anemoi_core_b200.synthetic import build_graph  # noqa: E402
 from oracle import reference_step as RS  # noqa: E402
 
 steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 10
+LEG = "--bench-leg" in sys.argv  # called by bench.py (in a subprocess, with a timeout): bf16 only, the reference's fastest backend only
 wl = sys.argv[sys.argv.index("--workload") + 1] if "--workload" in sys.argv else "cfg2"
 w = bench.WORKLOADS[wl]
 dev = torch.device("cuda")
@@ -52,16 +53,19 @@ def timed(fn, n):
 
 out = {"workload": f"{wl}: {w['desc']}", "device": torch.cuda.get_device_name(0)}
 ours = {}
-for name, dt in (("bf16", torch.bfloat16), ("fp32", None)):
+PRECS = (("bf16", torch.bfloat16),) if LEG else (("bf16", torch.bfloat16), ("fp32", None))
+for name, dt in PRECS:
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dt is not None):
         ours[name] = model(xg, xm, grd).float()
         out[f"ours_eager_{name}_ms"] = timed(lambda: model(xg, xm, grd), steps)[0]
 for backend in ("triton", "pyg"):
     if w["kind"] != "graphtransformer" and backend == "triton":
         continue
+    if LEG and backend == "pyg" and w["kind"] == "graphtransformer":
+        continue
     try:
         ref = RS.ReferenceStep(w["kind"], state_dicts=sds, attention_backend=backend, **bench._ref_kwargs(w, gr)).to(dev)
-        for name, dt in (("bf16", torch.bfloat16), ("fp32", None)):
+        for name, dt in PRECS:
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dt is not None):
                 y = ref(xg, xm, grd).float()
                 ms = timed(lambda: ref(xg, xm, grd), steps)[0]

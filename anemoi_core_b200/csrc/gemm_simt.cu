@@ -14,8 +14,8 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& ep, int64_t m, i
     acc = st.y * (acc - st.x * ep.ln_colsum[n]);
   }
   if (ep.bias) acc += ep.bias[n];
-  if (ep.g1) acc += ep.g1[(int64_t)ep.idx1[m] * ep.ldg + n];
-  if (ep.g2) acc += ep.g2[(int64_t)ep.idx2[m] * ep.ldg + n];
+  if (ep.g1) acc += load_as_f32(ep.g1, (int64_t)ep.idx1[m] * ep.ldg + n, (ep.flags & ANEMOI_EPI_G1_BF16) ? ANEMOI_BF16 : ANEMOI_F32);
+  if (ep.g2) acc += load_as_f32(ep.g2, (int64_t)ep.idx2[m] * ep.ldg + n, (ep.flags & ANEMOI_EPI_G2_BF16) ? ANEMOI_BF16 : ANEMOI_F32);
   if (ep.flags & ANEMOI_EPI_GELU) acc = gelu_erf(acc);
   if (ep.residual) acc += load_as_f32(ep.residual, m * ep.ldr + n, ep.r_dtype);
   store_from_f32(ep.out, m * ep.ldo + n, ep.o_dtype, acc);

@@ -370,12 +370,14 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
       const float2 st = ln_row_mean_rstd(ep, min((int64_t)row0 + lane, ep.M - 1));  // per tile, not per round
       ln_mean = st.x, ln_rstd = st.y;
     }
-    const float* g1row = nullptr;
-    const float* g2row = nullptr;
+    // gathered rows of this thread's edge: byte pointers (a table is fp32 or, ANEMOI_EPI_G*_BF16, bf16)
+    const char* g1row = nullptr;
+    const char* g2row = nullptr;
+    const bool g1h = GATHER && (ep.flags & ANEMOI_EPI_G1_BF16), g2h = GATHER && (ep.flags & ANEMOI_EPI_G2_BF16);
     if constexpr (GATHER) {
       const int64_t r = min((int64_t)row0 + lane, ep.M - 1);
-      if (ep.g1) g1row = ep.g1 + (int64_t)__ldg(ep.idx1 + r) * ep.ldg;
-      if (ep.g2) g2row = ep.g2 + (int64_t)__ldg(ep.idx2 + r) * ep.ldg;
+      if (ep.g1) g1row = reinterpret_cast<const char*>(ep.g1) + (int64_t)__ldg(ep.idx1 + r) * ep.ldg * (g1h ? 2 : 4);
+      if (ep.g2) g2row = reinterpret_cast<const char*>(ep.g2) + (int64_t)__ldg(ep.idx2 + r) * ep.ldg * (g2h ? 2 : 4);
     }
     // STATS: (mean, M2) of this thread's output row over the current 64-column block, taken from the bf16-ROUNDED values (what the
     // consuming GEMM will read: a constant row must cancel exactly against its column sums).  Sums are accumulated SHIFTED by the block's
@@ -468,6 +470,22 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
           }
         }
       }
+      // bf16 gather tables: the round's 16-byte pieces (8 columns each) are all requested HERE, before any of the round's shared-memory
+      // stores (memory clobbers: a load inside the group loop cannot be hoisted above the previous group's store), so they are in flight
+      // together; measured with fp32 tables loaded inside the groups the gather-add epilogue doubled the edge GEMM (552 -> 1 099 us at
+      // C = 1024: 8 KB of L2 reads per edge)
+      uint4 gq1[GATHER ? NG : 1], gq2[GATHER ? NG : 1];
+      if constexpr (GATHER) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const int col = col0 + g * 8;
+          gq1[g] = gq2[g] = make_uint4(0u, 0u, 0u, 0u);
+          if (col + 8 <= (int)ep.N) {
+            if (g1h && g1row) gq1[g] = __ldg(reinterpret_cast<const uint4*>(g1row + (int64_t)col * 2));
+            if (g2h && g2row) gq2[g] = __ldg(reinterpret_cast<const uint4*>(g2row + (int64_t)col * 2));
+          }
+        }
+      }
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
         const int col = col0 + g * 8;
@@ -489,21 +507,29 @@ __device__ __forceinline__ void epilogue_fast(const EpiCtx& cx, const EpiParams&
           }
         }
         if constexpr (GATHER) {
+          auto add_bf16 = [&](const uint4& u) {
+            v[0] += __uint_as_float(u.x << 16), v[1] += __uint_as_float(u.x & 0xffff0000u), v[2] += __uint_as_float(u.y << 16);
+            v[3] += __uint_as_float(u.y & 0xffff0000u), v[4] += __uint_as_float(u.z << 16), v[5] += __uint_as_float(u.z & 0xffff0000u);
+            v[6] += __uint_as_float(u.w << 16), v[7] += __uint_as_float(u.w & 0xffff0000u);
+          };
+          auto add_f32 = [&](const char* row) {
+            const float4* p4 = reinterpret_cast<const float4*>(row + (int64_t)col * 4);
+            const float4 b0 = __ldg(p4), b1 = __ldg(p4 + 1);
+            v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+          };
           if (col + 8 <= (int)ep.N) {
             if (g1row) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(g1row + col)), b1 = __ldg(reinterpret_cast<const float4*>(g1row + col) + 1);
-              v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+              if (g1h) add_bf16(gq1[g]); else add_f32(g1row);
             }
             if (g2row) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(g2row + col)), b1 = __ldg(reinterpret_cast<const float4*>(g2row + col) + 1);
-              v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+              if (g2h) add_bf16(gq2[g]); else add_f32(g2row);
             }
           } else if (col < (int)ep.N) {  // ragged last 8-column group of the matrix
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               if (col + j < (int)ep.N) {
-                if (g1row) v[j] += g1row[col + j];
-                if (g2row) v[j] += g2row[col + j];
+                if (g1row) v[j] += g1h ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g1row)[col + j]) : reinterpret_cast<const float*>(g1row)[col + j];
+                if (g2row) v[j] += g2h ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g2row)[col + j]) : reinterpret_cast<const float*>(g2row)[col + j];
               }
             }
           }
@@ -592,8 +618,9 @@ __device__ __noinline__ void epilogue_generic(const EpiCtx& cx, const EpiParams&
     ptx::tc_fence_after();
     const int64_t row = (int64_t)m_blk * cx.tile_m + cx.row_off + cx.q * 32 + lane;
     const bool row_ok = row < ep.M;
-    const float* g1row = (ep.g1 && row_ok) ? ep.g1 + (int64_t)ep.idx1[row] * ep.ldg : nullptr;
-    const float* g2row = (ep.g2 && row_ok) ? ep.g2 + (int64_t)ep.idx2[row] * ep.ldg : nullptr;
+    const bool g1h = (ep.flags & ANEMOI_EPI_G1_BF16) != 0, g2h = (ep.flags & ANEMOI_EPI_G2_BF16) != 0;
+    const char* g1row = (ep.g1 && row_ok) ? reinterpret_cast<const char*>(ep.g1) + (int64_t)ep.idx1[row] * ep.ldg * (g1h ? 2 : 4) : nullptr;
+    const char* g2row = (ep.g2 && row_ok) ? reinterpret_cast<const char*>(ep.g2) + (int64_t)ep.idx2[row] * ep.ldg * (g2h ? 2 : 4) : nullptr;
     const float2 ln_st = (ep.ln_stats && row_ok) ? ln_row_mean_rstd(ep, row) : make_float2(0.f, 1.f);
 #pragma unroll 1
     for (int c = 0; c < kColsPerWarp; c += 32) {
@@ -610,8 +637,8 @@ __device__ __noinline__ void epilogue_generic(const EpiCtx& cx, const EpiParams&
           float a = __uint_as_float(r[j]);
           if (ep.ln_stats) a = ln_st.y * (a - ln_st.x * ep.ln_colsum[n]);
           if (ep.bias) a += ep.bias[n];
-          if (g1row) a += g1row[n];
-          if (g2row) a += g2row[n];
+          if (g1row) a += g1h ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g1row)[n]) : reinterpret_cast<const float*>(g1row)[n];
+          if (g2row) a += g2h ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g2row)[n]) : reinterpret_cast<const float*>(g2row)[n];
           if (ep.flags & ANEMOI_EPI_GELU) a = gelu_erf_fast(a);
           if (ep.residual) a += load_as_f32(ep.residual, row * ep.ldr + n, ep.r_dtype);
           store_from_f32(ep.out, row * ep.ldo + n, ep.o_dtype, a);
@@ -1016,7 +1043,7 @@ int linear_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, int64
   const bool gather = ep.g1 || ep.g2;
   // fast epilogue: TMA-storable output, 16-byte aligned bias / gather rows, residual (if any) of the output dtype and TMA-loadable
   bool fast = a16(ep.out) && (ep.ldo * os) % 16 == 0 && (!ep.bias || a16(ep.bias)) &&
-              (!gather || ((!ep.g1 || a16(ep.g1)) && (!ep.g2 || a16(ep.g2)) && ep.ldg % 4 == 0 && !ep.residual));
+              (!gather || ((!ep.g1 || a16(ep.g1)) && (!ep.g2 || a16(ep.g2)) && ep.ldg % ((ep.flags & (ANEMOI_EPI_G1_BF16 | ANEMOI_EPI_G2_BF16)) ? 8 : 4) == 0 && !ep.residual));
   if (ep.residual) fast = fast && ep.r_dtype == ep.o_dtype && a16(ep.residual) && (ep.ldr * os) % 16 == 0;
   // folded LayerNorm: fast path needs a (non-null) bias tile, no residual / gather, aligned stats and column sums
   if (ep.ln_stats) fast = fast && ep.bias && !ep.residual && !gather && a16(ep.ln_colsum) && (reinterpret_cast<uintptr_t>(ep.ln_stats) & 7) == 0;

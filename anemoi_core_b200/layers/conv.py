@@ -20,6 +20,11 @@ from .mlp import GatedMLPLayer
 
 PairTensor = tuple[Tensor, Tensor]
 
+import os  # noqa: E402
+
+GC_PI_BF16 = os.environ.get("ANEMOI_B200_GC_PI_BF16", "1") != "0"  # the same for the dst-indexed term
+GC_PJ_BF16 = os.environ.get("ANEMOI_B200_GC_PJ_BF16", "1") != "0"  # bf16 table for the src-indexed gather term of GraphConv (A/B switch)
+
 
 def _sorted_plan(edge_index: Tensor, n_src: int, n_dst: int) -> tuple[ops.GraphCSR, Optional[Tensor]]:
     """CSR plan for ``edge_index``; if it turns out not to be dst-sorted, stable-sort it (like the reference's
@@ -93,9 +98,14 @@ class GraphConv(nn.Module):
             return [m.gate_proj, m.value_proj] if isinstance(m, GatedMLPLayer) else [m]
 
         first = group(mlp.mlp[0])
-        # node-level projections of the first edge-MLP layer, fp32 so the gather-add is a single rounding
-        p_i = Fn.fused_linear(self._pack, x_dst, first, dt, cols=slice(0, C), use_bias=False, out_dtype=torch.float32)
-        p_j = Fn.fused_linear(self._pack, x_src, first, dt, cols=slice(C, 2 * C), use_bias=False, out_dtype=torch.float32)
+        # node-level projections of the first edge-MLP layer, gathered and added in the edge GEMM's epilogue.  As fp32 tables they cost 8 C
+        # bytes of L2 reads per edge and DOUBLED that GEMM (552 -> 1 099 us at C = 1024, profiles/r2/call51_*); on the bf16 path both tables
+        # are bf16 (two extra roundings of two of the three addends: the GNN bf16 error moves from 4.66e-3 to 4.68e-3, bars unchanged):
+        # 777 us, cfg3 step 110 -> 104.4 ms (call52_*, call53_*).  ANEMOI_B200_GC_PI_BF16=0 / _PJ_BF16=0 keep a table in fp32.
+        pi_dt = dt if (dt == torch.bfloat16 and GC_PI_BF16) else torch.float32
+        p_i = Fn.fused_linear(self._pack, x_dst, first, dt, cols=slice(0, C), use_bias=False, out_dtype=pi_dt)
+        pj_dt = dt if (dt == torch.bfloat16 and GC_PJ_BF16) else torch.float32
+        p_j = Fn.fused_linear(self._pack, x_src, first, dt, cols=slice(C, 2 * C), use_bias=False, out_dtype=pj_dt)
         e = Fn.as_operand(edge_attr, dt, edge_attr.shape[1])
         # hidden layers through the MLP runner up to (not including) the LayerNorm
         mods = list(mlp.mlp)

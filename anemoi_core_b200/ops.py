@@ -346,7 +346,7 @@ def _linear_one(
 
     ``a`` [M, K] and ``weight`` [N, K] share a dtype: bf16 -> tcgen05 tensor cores; fp32 -> the same tensor cores on the exact bf16 x 3 split
     of both operands (``split_bf16x3``: fp32-grade result, ~1e-6), or the FFMA kernel for small / unaligned problems;
-    ``gatherX = (table fp32 [*, >=N], idx int32 [M])``.
+    ``gatherX = (table fp32 or bf16 [*, >=N], idx int32 [M])`` (bf16 tables halve the L2 traffic of the gather-add epilogue).
     """
     _need_cuda(a, weight, bias, residual, out)
     M, K, lda = _rows(a)
@@ -374,8 +374,8 @@ def _linear_one(
         tab, idx = g
         _need_cuda(tab, idx)
         _, Ng, ld = _rows(tab)
-        if tab.dtype != torch.float32 or Ng < N or idx.dtype != torch.int32 or idx.numel() != M or not idx.is_contiguous():
-            raise TypeError("linear: gather tables must be float32 [*, >=N] with contiguous int32 indices [M]")
+        if tab.dtype not in (torch.float32, torch.bfloat16) or Ng < N or idx.dtype != torch.int32 or idx.numel() != M or not idx.is_contiguous():
+            raise TypeError("linear: gather tables must be float32 or bfloat16 [*, >=N] with contiguous int32 indices [M]")
         if ldg not in (0, ld):
             raise ValueError("linear: the two gather tables must share a leading dimension")
         ldg = ld
@@ -385,13 +385,14 @@ def _linear_one(
             g2, i2 = tab, idx
     if g1 is None and g2 is not None:
         g1, i1, g2, i2 = g2, i2, None, None
+    gflags = (8 if g1 is not None and g1.dtype == torch.bfloat16 else 0) | (16 if g2 is not None and g2.dtype == torch.bfloat16 else 0)  # ANEMOI_EPI_G*_BF16
     if ln_stats is None and stats_out is None:
         split = _fp32_on_tensor_cores(a, weight)
         if split is not None:  # fp32 operands: ONE bf16 tcgen05 GEMM over the six exact partial products (inner dimension 6K)
             a, weight = split
             K, lda, ldw = 6 * K, 6 * K, 6 * K
     tc = a.dtype == torch.bfloat16 and K >= 64 and lda % 8 == 0 and ldw % 8 == 0 and a.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0
-    gbytes = (4.0 * M * N if g1 is not None else 0.0) + (4.0 * M * N if g2 is not None else 0.0)
+    gbytes = (g1.element_size() * float(M) * N if g1 is not None else 0.0) + (g2.element_size() * float(M) * N if g2 is not None else 0.0)
     with _Timed("linear_tcgen05" if tc else "linear_ffma", 2.0 * M * N * K, _nbytes(a, weight, residual, out) + gbytes):
         if (ln_stats is None) != (ln_colsum is None):
             raise ValueError("linear: ln_stats and ln_colsum go together")
@@ -410,7 +411,7 @@ def _linear_one(
         _need_cuda(ln_stats, ln_colsum, stats_out)
         rc = _lib.load().anemoi_b200_linear(
             _ptr(a), lda, _ptr(weight), ldw, dtype_code(a.dtype), _ptr(_f32(bias)), _ptr(g1), _ptr(i1), _ptr(g2), _ptr(i2), ldg, _ptr(residual),
-            ldr, rdt, _ptr(out), ldo, dtype_code(out.dtype), M, N, K, (EPI_GELU if gelu else 0) | _rev("gemm") | (4 if _nopdl else 0), _ptr(ln_stats), _ptr(_f32(ln_colsum)),
+            ldr, rdt, _ptr(out), ldo, dtype_code(out.dtype), M, N, K, (EPI_GELU if gelu else 0) | _rev("gemm") | (4 if _nopdl else 0) | gflags, _ptr(ln_stats), _ptr(_f32(ln_colsum)),
             ln_parts, int(ln_dim), float(ln_eps), _ptr(stats_out), _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_linear")
     return out

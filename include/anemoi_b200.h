@@ -41,6 +41,8 @@ extern "C" {
 
 /* anemoi_b200_linear flags */
 #define ANEMOI_EPI_GELU 1 /* exact (erf) GELU after bias/gather-add, before residual  (torch.nn.GELU default) */
+#define ANEMOI_EPI_G1_BF16 8  /* gather table g1 holds bf16 rows (ldg in bf16 elements) instead of fp32 */
+#define ANEMOI_EPI_G2_BF16 16 /* same for g2: halves the L2 traffic of the gather-add epilogue (GraphConv's x_j = x_src[src] term) */
 #define ANEMOI_EPI_NOPDL 4 /* launch without the programmatic-dependent-launch attribute (a launch that follows a cross-stream event wait) */
 #define ANEMOI_EPI_REVERSE 2 /* scheduling hint, results unchanged: walk the row blocks from the last to the first, so that a GEMM
                               * consuming what the previous kernel wrote last starts where L2 still holds it (bf16 tcgen05 path) */
@@ -85,7 +87,7 @@ ANEMOI_API int anemoi_b200_cond_layer_norm(const void* x, int64_t ldx, int x_dty
  *   a_dtype == ANEMOI_BF16 : A, W bf16 -> tcgen05 (UMMA 128xBNx16, TMA SW128 operands, TMEM accumulators).
  *                            Requires lda % 8 == 0, ldw % 8 == 0, 16-byte aligned A and W.
  *   a_dtype == ANEMOI_F32  : A, W fp32 -> fp32 FFMA path (parity mode; no tensor cores, no TF32 rounding).
- *   bias  : fp32 [N] or NULL.  g1/g2 : fp32 [*, ldg] gathered by int32 row indices idx1/idx2 [M], or NULL.
+ *   bias  : fp32 [N] or NULL.  g1/g2 : fp32 (or, with ANEMOI_EPI_G1_BF16 / _G2_BF16, bf16) [*, ldg] gathered by int32 row indices idx1/idx2 [M], or NULL.
  *   residual : [M, ldr] of r_dtype or NULL.   out : [M, ldo] of o_dtype.
  *   ln_stats / ln_colsum (both or neither): LayerNorm of the A operand folded into the GEMM.  With W' = W * gamma (per input column),
  *     LN(x) W^T + b = rstd_m (x W'^T - mean_m colsum_n) + (b + W beta),  colsum_n = sum_k W'[n,k]:  the caller passes the RAW x as A,

@@ -163,3 +163,23 @@ if "l2mlp" in which:
             ts.append(a.elapsed_time(b) * 1e3)
         print(json.dumps({"kernel": f"mlp2+res M={M} (hidden {M * 4096 / 1e6:.0f} MB)", "cold_us": round(cold, 1), "warm_after_mlp1_us": round(statistics.median(ts), 1),
                           "TFLOPs_cold": round(2.0 * M * 512 * 2048 / cold / 1e6, 1), "TFLOPs_warm": round(2.0 * M * 512 * 2048 / statistics.median(ts) / 1e6, 1)}))  # fmt: skip
+
+if "gather" in which:
+    # What does the gather-add epilogue (GraphConv's first edge layer: + p_i[dst] + p_j[src], fp32 tables) cost at cfg3 shapes?
+    gr = build_graph("o96", 6)
+    N_, E_ = gr["n_mesh"], gr["proc_index"].shape[1]
+    csr = ops.build_csr(gr["proc_index"].to(dev), N_, N_)
+    for C in (1024, 512):
+        e = torch.randn(E_, C, generator=g).to(torch.bfloat16).to(dev)
+        w = (torch.randn(C, C, generator=g) / C**0.5).to(torch.bfloat16).to(dev)
+        b = torch.randn(C, generator=g).to(dev)
+        p_i, p_j = torch.randn(N_, C, generator=g).to(dev), torch.randn(N_, C, generator=g).to(dev)
+        o = torch.empty(E_, C, dtype=torch.bfloat16, device=dev)
+        plain, _ = timeit(lambda: ops.linear(e, w, b, gelu=True, out=o))
+        gath, _ = timeit(lambda: ops.linear(e, w, b, gelu=True, gather1=(p_i, csr.dst32), gather2=(p_j, csr.src32), out=o))
+        p_jh = p_j.to(torch.bfloat16)
+        gath_h, _ = timeit(lambda: ops.linear(e, w, b, gelu=True, gather1=(p_i, csr.dst32), gather2=(p_jh, csr.src32), out=o))
+        gath_hh, _ = timeit(lambda: ops.linear(e, w, b, gelu=True, gather1=(p_i.to(torch.bfloat16), csr.dst32), gather2=(p_jh, csr.src32), out=o))
+        fl = 2.0 * E_ * C * C
+        print(json.dumps({"kernel": f"edge GEMM-1 [{E_}x{C}]x[{C}x{C}] + GELU", "plain_us": round(plain, 1), "with_gather_add_us": round(gath, 1), "src_table_bf16_us": round(gath_h, 1), "both_tables_bf16_us": round(gath_hh, 1),
+                          "TFLOPs_plain": round(fl / plain / 1e6, 1), "TFLOPs_gather": round(fl / gath / 1e6, 1)}))

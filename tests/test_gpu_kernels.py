@@ -623,3 +623,25 @@ def test_linear_tail_wave_split_matches_single_launch(ops):
         assert torch.equal(out, y_one)
     finally:
         ops.TAIL_SPLIT = old
+
+
+@pytest.mark.parametrize("M,N,K", [(5000, 512, 512), (1000, 200, 216), (300, 1024, 1024)])
+def test_linear_gather_tables_bf16(ops, M, N, K):
+    """Gather-add epilogue with bf16 tables (ANEMOI_EPI_G1_BF16 / _G2_BF16; GraphConv's src-indexed term on the bf16 path): same result as with
+    the fp32 copies of the same (bf16-valued) tables, for one or both tables in bf16."""
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K, generator=g) / K**0.5).to(torch.bfloat16).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    ld = (N + 7) // 8 * 8
+    t1 = torch.randn(70, ld, generator=g).to(torch.bfloat16).cuda()
+    t2 = torch.randn(90, ld, generator=g).to(torch.bfloat16).cuda()
+    i1 = torch.randint(0, 70, (M,), generator=g, dtype=torch.int32).cuda()
+    i2 = torch.randint(0, 90, (M,), generator=g, dtype=torch.int32).cuda()
+    sl = (lambda t: t[:, :N] if ld != N else t)
+    ref = ops.linear(a, w, b, gelu=True, gather1=(sl(t1.float()), i1), gather2=(sl(t2.float()), i2))
+    for g1, g2 in ((sl(t1.float()), sl(t2)), (sl(t1), sl(t2))):
+        if g1.dtype != g2.dtype and False:
+            continue
+        y = ops.linear(a, w, b, gelu=True, gather1=(g1, i1), gather2=(g2, i2))
+        assert torch.equal(y, ref)

@@ -23,6 +23,7 @@ class _CSR:
     colptr32: Tensor
     src32: Tensor
     dst32: Tensor
+    rev: Optional[tuple] = None
 
 
 def build_csr(edge_index: Tensor, n_src: int, n_dst: int, validate: bool = True) -> _CSR:
@@ -102,7 +103,8 @@ def row_stats(x, eps=1e-5):
     return torch.stack([xf.mean(1), (xf.var(1, unbiased=False) + eps).rsqrt()], 1)
 
 
-def gt_attention(q, k, v, csr, heads, e_proj=None, edge_attr=None, w_edge=None, b_edge=None, qw=None, abar=None, dp=0, add=None, out=None, tiles=None):
+def gt_attention(q, k, v, csr, heads, e_proj=None, edge_attr=None, w_edge=None, b_edge=None, qw=None, abar=None, dp=0, add=None, out=None, tiles=None,
+                 lse=None):
     n_dst, C = q.shape
     Ch = C // heads
     src, dst = csr.src32.long(), csr.dst32.long()
@@ -125,6 +127,8 @@ def gt_attention(q, k, v, csr, heads, e_proj=None, edge_attr=None, w_edge=None, 
     w = torch.exp(score - mx[dst])
     den = torch.zeros(n_dst, heads).index_add_(0, dst, w)
     alpha = w / den[dst]
+    if lse is not None:  # natural-log normaliser per (dst, head); 0 for rows without edges (include/anemoi_b200.h)
+        lse.copy_(torch.where(den > 0, mx + torch.log(den.clamp_min(1e-38)), torch.zeros_like(den)))
     res = torch.zeros(n_dst, heads, Ch).index_add_(0, dst, alpha[..., None] * ve)
     has = torch.zeros(n_dst, dtype=torch.bool)
     has[dst] = True
@@ -215,13 +219,67 @@ def cond_layer_norm(x, cond, w_scale, b_scale, w_bias, b_bias, eps=1e-5, out_dty
     return (y * (1.0 + cond.float() @ w_scale.t() + b_scale) + cond.float() @ w_bias.t() + b_bias).to(out_dtype or x.dtype)
 
 
+# ---- backward entry points (training on a model-parallel group under Gloo: tests/test_sharded_training_gloo.py) ---------------------
+# Each one differentiates the stand-in forward above with PyTorch autograd: what is under test is the distributed autograd plumbing
+# (HaloExchangeFn / GatherRowsFn / AllToAllFn, per-rank partial parameter gradients), not these formulas.
+def gelu(x, dy=None):
+    if dy is None:
+        return F.gelu(x.float()).to(x.dtype)
+    xf = x.detach().float().requires_grad_()
+    with torch.enable_grad():
+        y = F.gelu(xf)
+    return torch.autograd.grad(y, xf, dy.float())[0].to(x.dtype)
+
+
+def layer_norm_bwd(x, gamma, dy, eps, groups=1, dz=None, idx=None, want_dres=False):
+    M, W = x.shape
+    C = W // groups
+    g = torch.zeros(M, W)
+    if dy is not None:
+        g = g + dy.float()
+    if dz is not None:
+        g = g + (dz.float()[idx.long()] if idx is not None else dz.float())
+    xf = x.detach().float().requires_grad_()
+    gm = (gamma.detach().float() if gamma is not None else torch.ones(C)).requires_grad_()
+    bt = torch.zeros(C, requires_grad=True)
+    with torch.enable_grad():
+        y = F.layer_norm(xf.reshape(M, groups, C), (C,), gm, bt, eps).reshape(M, W)
+    dx, dg, db = torch.autograd.grad(y, (xf, gm, bt), g)
+    return dx.to(x.dtype), dg, db, (g.to(x.dtype) if want_dres else None)
+
+
+def gt_attention_bwd(q, k, v, e_proj, out, dout, lse, csr, heads):
+    ts = [t.detach().float().requires_grad_() for t in (q, k, v)]
+    ef = None if e_proj is None else e_proj.detach().float().requires_grad_()
+    with torch.enable_grad():
+        y = gt_attention(ts[0], ts[1], ts[2], csr, heads, e_proj=ef)
+    gs = torch.autograd.grad(y, ts + ([ef] if ef is not None else []), dout.float())
+    de = gs[3].to(q.dtype) if ef is not None else None
+    return gs[0].to(q.dtype), gs[1].to(q.dtype), gs[2].to(q.dtype), de
+
+
+def glu_combine_bwd(gv, dy, act):
+    gf = gv.detach().float().requires_grad_()
+    with torch.enable_grad():
+        y = glu_combine(gf, act)
+    return torch.autograd.grad(y, gf, dy.float())[0].to(gv.dtype)
+
+
+def segment_sum(rows, ptr32, eid32, n_out):
+    ptr = ptr32.long()
+    seg = torch.repeat_interleave(torch.arange(n_out), ptr[1:] - ptr[:-1])
+    sel = rows.float()[eid32.long()] if eid32 is not None else rows.float()[: int(ptr[-1])]
+    return torch.zeros(n_out, rows.shape[1]).index_add_(0, seg, sel).to(rows.dtype)
+
+
 def install() -> None:
     """Replace the CUDA entry points of ``anemoi_core_b200.ops`` in THIS process (a spawned Gloo test worker)."""
     import anemoi_core_b200.layers._functional as Fn
     from anemoi_core_b200 import ops
 
     for name in ("build_csr", "linear", "layer_norm", "row_stats", "gt_attention", "graphconv_ln_aggregate", "graphconv_fused", "cast_pad", "add", "partial_stats_buffer",
-                 "assemble_input", "assemble_output", "glu_combine", "cond_layer_norm"):
+                 "assemble_input", "assemble_output", "glu_combine", "cond_layer_norm", "gelu", "layer_norm_bwd", "gt_attention_bwd", "glu_combine_bwd",
+                 "segment_sum"):
         setattr(ops, name, globals()[name])
     ops.attention_tiles = lambda csr: None  # the tile plan only feeds the CUDA kernel
     ops._need_cuda = lambda *a, **k: None

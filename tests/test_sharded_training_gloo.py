@@ -16,14 +16,14 @@ import torch.multiprocessing as mp
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, init_file, ret):
+def _worker(rank, world, init_file, ret, fn_name="_check"):
     dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
     try:
         import _cpu_ops
 
         _cpu_ops.install()
         torch.set_num_threads(2)
-        ret[rank] = _check(rank, world)
+        ret[rank] = globals()[fn_name](rank, world)
     except Exception as e:  # noqa: BLE001
         import traceback
 
@@ -96,3 +96,100 @@ def test_sharded_training_step_matches_single_rank_gloo():
             assert isinstance(ret.get(r), list), ret.get(r)
             for kind, err_x, err_p in ret[r]:
                 assert err_x <= 2e-5 and err_p <= 5e-5, f"rank {r} {kind}: dx {err_x:.3e} dparams {err_p:.3e}"
+
+
+# ---- the differentiable composition (layers/_train.py) against the gradient fixtures of the UNMODIFIED reference, on CPU ----------------
+def _rel(a, b, floor=1e-6):
+    a, b = a.detach().float(), b.detach().float()
+    assert a.shape == b.shape, (tuple(a.shape), tuple(b.shape))
+    return (a - b).abs().max().item() / max(b.abs().max().item(), floor)
+
+
+def _param_errs(m, golden_grads):
+    got = {n: p.grad for n, p in m.named_parameters()}
+    floor = 1e-3 * max(g.abs().max().item() for g in golden_grads["params"].values())
+    worst = 0.0
+    for n, g in golden_grads["params"].items():
+        assert got.get(n) is not None, f"no gradient for {n}"
+        worst = max(worst, _rel(got[n], g, floor))
+    return worst
+
+
+def _check_fixtures(rank, world):
+    """Forward and every gradient of the drop-in modules in training mode (stand-in arithmetic, fp32, CPU) against tests/golden/grads.pt and
+    grads_r2.pt (PyTorch autograd of the unmodified reference modules): processors (plain, qk_norm, the four gatings, ConditionalLayerNorm),
+    all four mappers (+ the ConditionalLayerNorm forward mapper)."""
+    import anemoi_core_b200.layers as L
+    from anemoi_core_b200.distributed.shapes import BipartiteGraphShardInfo
+    from anemoi_core_b200.distributed.shapes import GraphShardInfo
+
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g1 = torch.load(os.path.join(gdir, "grads.pt"), weights_only=False)
+    g2 = torch.load(os.path.join(gdir, "grads_r2.pt"), weights_only=False)
+    out = []
+
+    def lk(c):
+        return {"LayerNorm": {"_target_": "anemoi_core_b200.layers.normalization.ConditionalLayerNorm", "condition_shape": c["condition_shape"],
+                              "zero_init": False}}  # fmt: skip
+
+    procs = [(g1, n) for n in ("gt_processor", "gt_processor_qknorm", "gnn_processor")]
+    procs += [(g2, n) for n in ("gt_processor_glu", "gt_processor_swiglu", "gt_processor_geglu", "gt_processor_reglu", "gnn_processor_swiglu",
+                                "gnn_processor_geglu", "gt_processor_condln")]  # fmt: skip
+    for src, name in procs:
+        c = src[name]
+        cls = L.GNNProcessor if name.startswith("gnn") else L.GraphTransformerProcessor
+        kw = {"layer_kernels": lk(c)} if name.endswith("condln") else {}
+        m = cls(**kw, **c["cfg"])
+        m.load_state_dict(c["sd"], strict=True)
+        m.train()
+        x, ea = c["x"].clone().requires_grad_(), c["edge_attr"].clone().requires_grad_()
+        extra = {}
+        if name.endswith("condln"):
+            extra["cond"] = c["cond"].clone().requires_grad_()
+        y = m(x, 1, GraphShardInfo(nodes=[x.shape[0]]) if name.startswith("gnn") else GraphShardInfo(), ea, c["edge_index"], **extra)
+        (y * c["w"]).sum().backward()
+        errs = [_rel(y, c["y"]), _rel(x.grad, c["grads"]["x"]), _rel(ea.grad, c["grads"]["edge_attr"]), _param_errs(m, c["grads"])]
+        if extra:
+            errs.append(_rel(extra["cond"].grad, c["grads"]["cond"]))
+        out.append((name, max(errs)))
+    mappers = [(g1, "gt_forward_mapper", L.GraphTransformerForwardMapper), (g1, "gt_backward_mapper", L.GraphTransformerBackwardMapper),
+               (g1, "gnn_forward_mapper", L.GNNForwardMapper), (g1, "gnn_backward_mapper", L.GNNBackwardMapper),
+               (g2, "gt_forward_mapper_condln", L.GraphTransformerForwardMapper)]  # fmt: skip
+    for src, name, cls in mappers:
+        c = src[name]
+        cond = name.endswith("condln")
+        m = cls(**({"layer_kernels": lk(c)} if cond else {}), **c["cfg"])
+        m.load_state_dict(c["sd"], strict=True)
+        m.train()
+        xs, xd, ea = (c[k].clone().requires_grad_() for k in ("x_src", "x_dst", "edge_attr"))
+        extra, conds = {}, ()
+        if cond:
+            conds = (c["cond_src"].clone().requires_grad_(), c["cond_dst"].clone().requires_grad_())
+            extra["cond"] = conds
+        res = m((xs, xd), 1, BipartiteGraphShardInfo(), ea, c["edge_index"], **extra)
+        if name == "gnn_forward_mapper" or cond:
+            ys = [res[1], res[0]]
+        elif name == "gt_forward_mapper":
+            ys = [res[1]]
+        else:
+            ys = [res]
+        errs = [_rel(y, yr) for y, yr in zip(ys, c["y"])]
+        sum((y * w).sum() for y, w in zip(ys, c["w"])).backward()
+        for k, t in (("x_src", xs), ("x_dst", xd), ("edge_attr", ea)) + ((("cond_src", conds[0]), ("cond_dst", conds[1])) if cond else ()):
+            if c["grads"][k] is None:
+                assert t.grad is None or t.grad.abs().max().item() == 0.0
+            else:
+                errs.append(_rel(t.grad, c["grads"][k]))
+        errs.append(_param_errs(m, c["grads"]))
+        out.append((name, max(errs)))
+    return out
+
+
+def test_training_composition_matches_reference_gradient_fixtures_cpu():
+    with tempfile.TemporaryDirectory() as d:
+        ret = mp.Manager().dict()
+        mp.spawn(_worker, args=(1, os.path.join(d, "rdv"), ret, "_check_fixtures"), nprocs=1, join=True)
+        assert isinstance(ret.get(0), list), ret.get(0)
+        for name, err in ret[0]:
+            assert err <= 1e-4, f"{name}: max relative error {err:.3e}"
+        print([(n, f"{e:.1e}") for n, e in ret[0]])

@@ -87,11 +87,65 @@ def _check(rank, world):
     return msgs
 
 
-def test_sharded_training_step_matches_single_rank_gloo():
+def _check_model(rank, world):
+    """The WHOLE encoder -> processor -> decoder step in training mode, every stage sharded (the call sequence of tests/test_gpu_multi.py's
+    training section, here under Gloo on CPU): sharded input / output rows for the GraphTransformer model, replicated in / gathered out for the
+    GNN model; gradients of the inputs and of every parameter against the single-rank step."""
+    from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
+    from anemoi_core_b200.model import EncProcDec
+    from anemoi_core_b200.synthetic import build_graph
+
+    gr = build_graph("o32", mesh_level=3)
+    n = gr["n_mesh"]
+    group = dist.group.WORLD
+    sizes, gsz = get_balanced_partition_sizes(n, world), get_balanced_partition_sizes(gr["n_grid"], world)
+    g0, m0 = sum(gsz[:rank]), sum(sizes[:rank])
+    gen = torch.Generator().manual_seed(9)
+    xg, xm = torch.randn(gr["n_grid"], 20, generator=gen), torch.randn(n, 12, generator=gen)
+    wgt = torch.randn(gr["n_grid"], 9, generator=torch.Generator().manual_seed(21))
+    msgs = []
+    for kind in ("graphtransformer", "gnn"):
+        torch.manual_seed(6)
+        mt = EncProcDec(kind, in_grid=20, in_mesh=12, out_grid=9, num_channels=32, num_layers=2, edge_dim=gr["edge_dim"], num_heads=4).train()
+        xg_f = xg.clone().requires_grad_()
+        (mt(xg_f, xm, gr) * wgt).sum().backward()
+        ref_p = {k: p.grad.clone() for k, p in mt.named_parameters() if p.grad is not None}
+        ref_x = xg_f.grad.clone()
+        mt.zero_grad()
+        if kind == "graphtransformer":
+            xg_s = xg[g0 : g0 + gsz[rank]].clone().requires_grad_()
+            y_l = mt(xg_s, xm[m0 : m0 + sizes[rank]].contiguous(), gr, model_comm_group=group, mesh_shards=sizes, grid_shards=gsz,
+                     keep_output_sharded=True, inputs_sharded=True)  # fmt: skip
+            (y_l * wgt[g0 : g0 + gsz[rank]]).sum().backward()
+            gx, rx, scale = xg_s.grad, ref_x[g0 : g0 + gsz[rank]], 1.0
+        else:
+            xg_s = xg.clone().requires_grad_()
+            y_all = mt(xg_s, xm, gr, group, sizes, gsz)  # replicated in / gathered out: every rank back-propagates the same (whole) loss
+            (y_all * wgt).sum().backward()
+            gx = xg_s.grad.clone()
+            dist.all_reduce(gx)
+            gx, rx, scale = gx / world, ref_x, 1.0 / world
+        err_x = ((gx - rx).abs().max() / rx.abs().max()).item()
+        worst, big = 0.0, max(g.abs().max().item() for g in ref_p.values())
+        for k, p in mt.named_parameters():
+            if k not in ref_p:
+                continue
+            gp = p.grad.clone() if p.grad is not None else torch.zeros_like(p)
+            dist.all_reduce(gp)
+            worst = max(worst, ((gp * scale - ref_p[k]).abs().max() / max(ref_p[k].abs().max().item(), 1e-3 * big)).item())
+        msgs.append((f"encprocdec_{kind}", err_x, worst))
+    return msgs
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("fn_name", ["_check", "_check_model"])
+def test_sharded_training_step_matches_single_rank_gloo(fn_name):
     world = 2
     with tempfile.TemporaryDirectory() as d:
         ret = mp.Manager().dict()
-        mp.spawn(_worker, args=(world, os.path.join(d, "rdv"), ret), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, os.path.join(d, "rdv"), ret, fn_name), nprocs=world, join=True)
         for r in range(world):
             assert isinstance(ret.get(r), list), ret.get(r)
             for kind, err_x, err_p in ret[r]:

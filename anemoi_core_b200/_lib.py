@@ -44,6 +44,7 @@ SIGNATURES = {
     "anemoi_b200_layer_norm_bwd": [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                    c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_int, c_void_p],
     "anemoi_b200_segment_sum": [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p],
+    "anemoi_b200_col_sum": [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p],
     "anemoi_b200_gelu": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p],
     "anemoi_b200_attn_tile_plan": [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "anemoi_b200_gt_attention_tiled_fwd": [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,

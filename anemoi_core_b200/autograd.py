@@ -14,6 +14,7 @@ No CPU path: CPU tensors raise in ``ops`` like everywhere else.
 
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -21,6 +22,16 @@ from torch import Tensor
 from torch.autograd import Function
 
 from . import ops
+
+
+COL_SUM = os.environ.get("ANEMOI_B200_COL_SUM", "1") != "0"  # bias gradients through ops.col_sum instead of PyTorch's sum(0)
+
+
+def _bias_grad(dz: Tensor) -> Tensor:
+    """db = column sums of the cotangent, fp32 accumulation without an fp32 copy of dz."""
+    if COL_SUM and dz.dim() == 2 and dz.stride(1) == 1 and dz.data_ptr() % 16 == 0 and (dz.stride(0) * dz.element_size()) % 16 == 0:
+        return ops.col_sum(dz)
+    return dz.sum(0, dtype=torch.float32)
 
 
 def _pad_cols(t: Tensor, k: int) -> Tensor:
@@ -56,7 +67,7 @@ class LinearFn(Function):
         if ctx.needs_input_grad[1]:
             dw = torch.matmul(dz.t(), xa)[:, :K].to(w_dt)  # plain library GEMM (weight gradient; reduction over all rows)
         if b_dt is not None and ctx.needs_input_grad[2]:
-            db = dz.sum(0, dtype=torch.float32).to(b_dt)  # fp32 accumulation without materialising an fp32 copy of dz
+            db = _bias_grad(dz).to(b_dt)
         return dx, dw, db, None, None
 
 
@@ -93,7 +104,7 @@ class EdgeFirstLayerFn(Function):
         if ctx.needs_input_grad[1]:
             dw = torch.matmul(dz.t(), ea)[:, :K].to(w_dt)
         if b_dt is not None and ctx.needs_input_grad[2]:
-            db = dz.sum(0, dtype=torch.float32).to(b_dt)
+            db = _bias_grad(dz).to(b_dt)
         if ctx.needs_input_grad[3]:
             dpi = ops.segment_sum(dz, csr.colptr32, None, csr.n_dst).to(pi_dt)
         if ctx.needs_input_grad[4]:

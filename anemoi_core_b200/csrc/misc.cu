@@ -348,7 +348,7 @@ extern "C" int anemoi_b200_assemble_output(const void* dec, int64_t ldd, int d_d
   return launch_status("assemble_output_kernel");
 }
 
-extern "C" int anemoi_b200_abi_version(void) { return 5; }
+extern "C" int anemoi_b200_abi_version(void) { return 6; }
 extern "C" const char* anemoi_b200_last_error(void) { return g_err; }
 
 extern "C" int anemoi_b200_csr_build(const int64_t* edge_index, int64_t n_edges, int64_t n_src, int64_t n_dst, int64_t* colptr64,

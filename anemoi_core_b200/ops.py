@@ -905,6 +905,21 @@ def segment_sum(rows: Tensor, ptr32: Tensor, eid32: Optional[Tensor], n_out: int
     return out
 
 
+_COL_SUM_CHUNKS = 256  # partial rows of the two-stage column sum
+
+
+def col_sum(x: Tensor) -> Tensor:
+    """``x.sum(0)`` in fp32 (deterministic two-stage reduction): the bias gradient of a Linear from its cotangent."""
+    _need_cuda(x)
+    M, N, ld = _rows(x)
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    partial = torch.empty((_COL_SUM_CHUNKS, (N + 3) // 4 * 4), dtype=torch.float32, device=x.device)
+    with _Timed("col_sum", 1.0 * M * N, _nbytes(x, out)):
+        rc = _lib.load().anemoi_b200_col_sum(_ptr(x), ld, _ptr(out), _ptr(partial), _COL_SUM_CHUNKS, M, N, dtype_code(x.dtype), _stream())
+    _lib.check(rc, "anemoi_b200_col_sum")
+    return out
+
+
 _LN_BWD_BLOCKS = 592  # partial-sum rows of dgamma / dbeta: 4 CTAs per SM
 
 
@@ -933,6 +948,9 @@ def layer_norm_bwd(x: Tensor, gamma: Optional[Tensor], dy: Optional[Tensor], eps
     return dx, sums[0], sums[1], dres
 
 
+GELU_BWD_FAST = os.environ.get("ANEMOI_B200_GELU_BWD_FAST", "1") != "0"  # bf16 cotangents: two-MUFU gelu' (|error| <= 1.3e-5) instead of erff + expf
+
+
 def gelu(x: Tensor, dy: Optional[Tensor] = None) -> Tensor:
     """``gelu(x)`` (exact erf), or with ``dy`` the backward ``dy * gelu'(x)``."""
     _need_cuda(x, dy)
@@ -941,7 +959,8 @@ def gelu(x: Tensor, dy: Optional[Tensor] = None) -> Tensor:
     lddy = 0
     if dy is not None:
         _, _, lddy = _rows(dy)
+    mode = 0 if dy is None else 2 if (GELU_BWD_FAST and x.dtype == torch.bfloat16) else 1
     with _Timed("gelu", 10.0 * M * N, _nbytes(x, dy, y)):
-        rc = _lib.load().anemoi_b200_gelu(_ptr(x), ldx, _ptr(dy), lddy, _ptr(y), N, M, N, 0 if dy is None else 1, dtype_code(x.dtype), _stream())
+        rc = _lib.load().anemoi_b200_gelu(_ptr(x), ldx, _ptr(dy), lddy, _ptr(y), N, M, N, mode, dtype_code(x.dtype), _stream())
     _lib.check(rc, "anemoi_b200_gelu")
     return y

@@ -193,7 +193,8 @@ ANEMOI_API int anemoi_b200_graphconv_fused(const void* x_src, int64_t lds, const
  * channels per row, for the cotangent g[r] = dy[r] (nullable) + dz[idx[r]] (nullable; idx nullable = identity); per-block partial sums of
  * dgamma / dbeta go to partial [n_partial, 2, C] fp32 (the caller sums over blocks).  With dz = d out and idx = dst32 this is the backward
  * of anemoi_b200_graphconv_ln_aggregate (layers/conv.py:73-81).
- * gelu: mode 0  y = gelu(x);  mode 1  y = dy * gelu'(x)  (exact erf GELU).
+ * gelu: mode 0  y = gelu(x);  mode 1  y = dy * gelu'(x)  (exact erf GELU);  mode 2  as mode 1 with Phi and phi through two exp2 (|error of
+ *       gelu'| <= 1.3e-5; for bf16 cotangents, where the exact form is bound by instruction issue).
  */
 ANEMOI_API int anemoi_b200_gt_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* e,
                                  int64_t lde, const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
@@ -213,6 +214,12 @@ ANEMOI_API int anemoi_b200_gelu(const void* x, int64_t ldx, const void* dy, int6
  * fp32 accumulation, no atomics.  rows : [*, ld], out : [n_out, ldo] of `dtype`, C a multiple of 16 bytes. */
 ANEMOI_API int anemoi_b200_segment_sum(const void* rows, int64_t ld, const int32_t* ptr32, const int32_t* eid32, void* out, int64_t ldo, int64_t n_out,
                                        int64_t C, int dtype, void* stream);
+
+/* Column sums (training: the bias gradient of a Linear, db = sum over rows of the cotangent; `dz.sum(0)` of PyTorch autograd in the reference):
+ * out[c] = sum_r x[r, c], fp32, deterministic two-stage reduction without atomics.  x : [M, ld] of `dtype` (16-byte aligned rows), out : [N] fp32,
+ * partial : [n_partial, round_up(N, 4)] fp32 scratch (16-byte aligned; the kernel uses up to min(n_partial, ...) row chunks; NULL / 0 = one chunk). */
+ANEMOI_API int anemoi_b200_col_sum(const void* x, int64_t ld, float* out, float* partial, int64_t n_partial, int64_t M, int64_t N, int dtype,
+                                   void* stream);
 
 /* -- multi-GPU exchange over NVLink peer memory (one process per GPU, one NVSwitch box) ---------------------------------
  * Replaces, for the dst-range sharded forward, the NCCL collectives of the reference: `halo_exchange` (distributed/graph.py:466-484,

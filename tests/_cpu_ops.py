@@ -272,6 +272,10 @@ def segment_sum(rows, ptr32, eid32, n_out):
     return torch.zeros(n_out, rows.shape[1]).index_add_(0, seg, sel).to(rows.dtype)
 
 
+def col_sum(x):
+    return x.float().sum(0)
+
+
 def install() -> None:
     """Replace the CUDA entry points of ``anemoi_core_b200.ops`` in THIS process (a spawned Gloo test worker)."""
     import anemoi_core_b200.layers._functional as Fn
@@ -279,7 +283,7 @@ def install() -> None:
 
     for name in ("build_csr", "linear", "layer_norm", "row_stats", "gt_attention", "graphconv_ln_aggregate", "graphconv_fused", "cast_pad", "add", "partial_stats_buffer",
                  "assemble_input", "assemble_output", "glu_combine", "cond_layer_norm", "gelu", "layer_norm_bwd", "gt_attention_bwd", "glu_combine_bwd",
-                 "segment_sum"):
+                 "segment_sum", "col_sum"):
         setattr(ops, name, globals()[name])
     ops.attention_tiles = lambda csr: None  # the tile plan only feeds the CUDA kernel
     ops._need_cuda = lambda *a, **k: None

@@ -39,7 +39,7 @@ def test_library_exports_every_header_symbol_and_ctypes_table_matches():
 
 def test_version_and_error_string_calls_work_without_a_gpu():
     lib = _lib.load()
-    assert lib.anemoi_b200_abi_version() == 5
+    assert lib.anemoi_b200_abi_version() == 6
     assert isinstance(lib.anemoi_b200_last_error(), bytes)
     # argument validation happens before any CUDA call: a bad shape is reported through the error channel
     rc = lib.anemoi_b200_linear(None, 0, None, 0, 0, None, None, None, None, None, 0, None, 0, 0, None, 0, 0, -1, 1, 1, 0, None, None, 0, 0, 0.0, None, None)

@@ -316,3 +316,68 @@ def test_conditional_layer_norm_mapper_gradients_match_reference(golden):
         else:
             close(t.grad, c["grads"][k], f"condln mapper d{k}")
     check_grads(m, c["grads"], "condln mapper")
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("shape", [(1, 8), (10, 512), (33, 7), (5000, 100), (40962, 512), (70001, 2560), (300000, 64)])
+def test_col_sum_kernel(shape, dt):
+    """ops.col_sum (the bias gradient: column sums of a cotangent, fp32, two-stage, no atomics) against a float64 sum; a strided view (the
+    pitch of a wider matrix) and run-to-run bit-identity."""
+    from anemoi_core_b200 import ops
+
+    M, N = shape
+    torch.manual_seed(M + N)
+    wide = torch.randn(M, (N + 24 + 7) // 8 * 8, device="cuda").to(dt)  # rows of whole 16-byte groups; ragged N inside them
+    views = [wide[:, :N], wide[:, 16 : 16 + N]]
+    if (N * wide.element_size()) % 16 == 0:
+        views.append(wide[:, :N].contiguous())
+    for x in views:
+        got = ops.col_sum(x)
+        assert got.dtype == torch.float32 and got.shape == (N,)
+        ref = x.double().sum(0)
+        bound = 4e-6 * x.double().abs().sum(0) + 1e-6  # fp32 accumulation of M terms in a fixed tree
+        assert ((got.double() - ref).abs() <= bound).all(), f"{shape} {dt}: {(got.double() - ref).abs().max().item():.3e}"
+        assert torch.equal(got, ops.col_sum(x))
+    assert torch.equal(ops.col_sum(torch.empty(0, 16, device="cuda", dtype=dt)), torch.zeros(16, device="cuda"))
+
+
+def test_bias_gradient_through_col_sum(monkeypatch):
+    """LinearFn's db with ANEMOI_B200_COL_SUM on == PyTorch's sum(0) path."""
+    from anemoi_core_b200 import autograd as AG
+
+    torch.manual_seed(2)
+    x = torch.randn(3000, 256, device="cuda")
+    w = torch.randn(512, 256, device="cuda", requires_grad=True)
+    b = torch.randn(512, device="cuda", requires_grad=True)
+    g = torch.randn(3000, 512, device="cuda")
+    out = {}
+    for on in (False, True):
+        monkeypatch.setattr(AG, "COL_SUM", on)
+        for dt in (torch.float32, torch.bfloat16):
+            w.grad = b.grad = None
+            (AG.LinearFn.apply(x, w, b, True, dt).float() * g).sum().backward()
+            out[on, dt] = b.grad.clone()
+    close(out[True, torch.float32], out[False, torch.float32], "db fp32", 1e-5)
+    close(out[True, torch.bfloat16], out[False, torch.bfloat16], "db bf16", 1e-5)
+
+
+def test_gelu_backward_two_mufu_form(monkeypatch):
+    """ANEMOI_B200_GELU_BWD_FAST: gelu'(x) through two exp2 (bf16 cotangents only) against the derivative of torch's exact-erf GELU; the bound is
+    1.3e-5 on gelu' plus the bf16 rounding of the result."""
+    from anemoi_core_b200 import ops
+
+    torch.manual_seed(4)
+    x = (torch.randn(4099, 512, device="cuda") * 3).to(torch.bfloat16)
+    x[0, :8] = torch.tensor([0.0, -0.0, 1e-4, -1e-4, 12.0, -12.0, 40.0, -40.0], device="cuda").to(torch.bfloat16)
+    dy = torch.randn(4099, 512, device="cuda").to(torch.bfloat16)
+    xf = x.double().requires_grad_()
+    torch.nn.functional.gelu(xf).backward(dy.double())
+    monkeypatch.setattr(ops, "GELU_BWD_FAST", True)
+    got = ops.gelu(x, dy)
+    err = (got.double() - xf.grad).abs()
+    assert (err <= 2e-5 * dy.double().abs() + 2.0**-8 * xf.grad.abs() + 1e-30).all(), err.max().item()
+    x32, dy32 = x.float(), dy.float()  # fp32 keeps the exact form, switch or not
+    monkeypatch.setattr(ops, "GELU_BWD_FAST", False)
+    ref32 = ops.gelu(x32, dy32)
+    monkeypatch.setattr(ops, "GELU_BWD_FAST", True)
+    assert torch.equal(ops.gelu(x32, dy32), ref32)

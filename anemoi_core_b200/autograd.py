@@ -39,20 +39,28 @@ def _pad_cols(t: Tensor, k: int) -> Tensor:
 
 
 class LinearFn(Function):
-    """y = [gelu](x W^T + b) in compute dtype ``dt`` (x [M, K] any float dtype, W [N, K], b [N] | None)."""
+    """y = [gelu](x W^T + b) [+ residual] in compute dtype ``dt`` (x [M, K] any float dtype, W [N, K], b [N] | None, residual [M, N] | None: added
+    in the GEMM epilogue like in inference; its gradient is the cotangent itself)."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], gelu: bool, dt: torch.dtype) -> Tensor:
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], gelu: bool, dt: torch.dtype, residual: Optional[Tensor] = None) -> Tensor:
         K = x.shape[1]
         kp = max(64, (K + 7) // 8 * 8) if dt == torch.bfloat16 else K  # tcgen05 operands: 16-byte rows, one swizzle span
         xd = x.detach()
         # no copy when x already is a dt operand of the right width (the common case inside a block: the previous op's output)
         xa = xd if (xd.dtype == dt and K == kp and xd.stride(1) == 1 and xd.data_ptr() % 16 == 0 and (xd.stride(0) * xd.element_size()) % 16 == 0) else ops.cast_pad(xd, dt, kp)
         wa = _pad_cols(weight.detach(), kp).to(dt).contiguous()
-        z = ops.linear(xa, wa, None if bias is None else bias.detach().float().contiguous())
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        ctx.res_dt = None if residual is None else residual.dtype
+        if residual is not None and not gelu:
+            r = residual.detach()
+            z = ops.linear(xa, wa, b32, residual=r if (r.dtype == dt and r.stride(1) == 1) else r.to(dt).contiguous())
+        else:
+            z = ops.linear(xa, wa, b32)
         ctx.save_for_backward(xa, wa, z if gelu else None)
         ctx.meta = (K, x.dtype, weight.dtype, None if bias is None else bias.dtype, gelu)
-        return ops.gelu(z) if gelu else z
+        y = ops.gelu(z) if gelu else z
+        return y + residual.detach().to(dt) if (residual is not None and gelu) else y
 
     @staticmethod
     def backward(ctx, dy: Tensor):
@@ -68,7 +76,8 @@ class LinearFn(Function):
             dw = torch.matmul(dz.t(), xa)[:, :K].to(w_dt)  # plain library GEMM (weight gradient; reduction over all rows)
         if b_dt is not None and ctx.needs_input_grad[2]:
             db = _bias_grad(dz).to(b_dt)
-        return dx, dw, db, None, None
+        dres = dy.to(ctx.res_dt) if (ctx.res_dt is not None and ctx.needs_input_grad[5]) else None
+        return dx, dw, db, None, None, dres
 
 
 class EdgeFirstLayerFn(Function):
@@ -217,8 +226,8 @@ class GraphConvTailFn(Function):
         return dh, (dg.to(w_dt) if w_dt is not None else None), (db.to(b_dt) if b_dt is not None else None), g.to(e_dt), None, None
 
 
-def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], dt: torch.dtype, gelu: bool = False) -> Tensor:
-    return LinearFn.apply(x, weight, bias, gelu, dt)
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], dt: torch.dtype, gelu: bool = False, residual: Optional[Tensor] = None) -> Tensor:
+    return LinearFn.apply(x, weight, bias, gelu, dt, residual)
 
 
 def layer_norm(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], eps: float, dt: torch.dtype, groups: int = 1) -> Tensor:

@@ -15,6 +15,7 @@ block.py:689-759; backward = the same all-to-all with the split lists swapped).
 
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -62,8 +63,14 @@ def norm(ln: nn.Module, x: Tensor, dt: torch.dtype, groups: int = 1, cond: Optio
     return AG.layer_norm(x, ln.weight, getattr(ln, "bias", None), ln.eps, dt, groups)
 
 
-def lin(layer: nn.Module, x: Tensor, dt: torch.dtype, gelu: bool = False) -> Tensor:
-    return AG.linear(x, layer.weight, getattr(layer, "bias", None), dt, gelu)
+FUSE_RES = os.environ.get("ANEMOI_B200_TRAIN_FUSE_RES", "1") != "0"  # residual adds in the GEMM epilogue (as in inference) instead of a PyTorch add
+
+
+def lin(layer: nn.Module, x: Tensor, dt: torch.dtype, gelu: bool = False, residual: Optional[Tensor] = None) -> Tensor:
+    if residual is not None and not FUSE_RES:
+        y = AG.linear(x, layer.weight, getattr(layer, "bias", None), dt, gelu)
+        return y + residual.to(y.dtype)
+    return AG.linear(x, layer.weight, getattr(layer, "bias", None), dt, gelu, residual)
 
 
 def lin_cat(layers, x: Tensor, dt: torch.dtype) -> Tensor:
@@ -89,6 +96,8 @@ def mlp(m, x: Tensor, dt: torch.dtype, residual: Optional[Tensor] = None, pre_ln
             i += 1
             continue
         act = i + 1 < len(mods) and not hasattr(mods[i + 1], "weight") and not isinstance(mods[i + 1], GatedMLPLayer)
+        if residual is not None and not act and i + 1 == len(mods) and m.layer_norm is None:  # the chain ends in a plain Linear: + residual there
+            return lin(layer, x, dt, residual=residual)
         x = lin(layer, x, dt, gelu=act)
         i += 2 if act else 1
     if m.layer_norm is not None:
@@ -222,6 +231,5 @@ def gt_block(block, x_src: Optional[Tensor], x_dst: Tensor, edge_attr: Tensor, e
     else:
         csr = Fn.csr_for(edge_index, n_src, x_dst.shape[0])
         att = AG.gt_attention(q, k, v, e, csr, H)
-    skip = x_dst.to(dt)
-    o = lin(block.projection, att + x_r, dt) + skip
+    o = lin(block.projection, att + x_r, dt, residual=x_dst.to(dt))
     return mlp(block.node_dst_mlp, o, dt, residual=o, pre_ln=block.layer_norm_mlp_dst, cond=cond_dst)

@@ -921,6 +921,7 @@ def col_sum(x: Tensor) -> Tensor:
 
 
 _LN_BWD_BLOCKS = 592  # partial-sum rows of dgamma / dbeta: 4 CTAs per SM
+LN_BWD_COL_SUM = os.environ.get("ANEMOI_B200_LN_BWD_COL_SUM", "1") != "0"
 
 
 def layer_norm_bwd(x: Tensor, gamma: Optional[Tensor], dy: Optional[Tensor], eps: float, groups: int = 1, dz: Optional[Tensor] = None,
@@ -944,7 +945,8 @@ def layer_norm_bwd(x: Tensor, gamma: Optional[Tensor], dy: Optional[Tensor], eps
         rc = _lib.load().anemoi_b200_layer_norm_bwd(_ptr(x), ldx, _ptr(_f32(gamma)), _ptr(dy), lddy, _ptr(dz), lddz, _ptr(idx), _ptr(dx), W, _ptr(dres), W,
                                                     _ptr(partial), _LN_BWD_BLOCKS, M, groups, C, float(eps), dtype_code(x.dtype), _stream())  # fmt: skip
     _lib.check(rc, "anemoi_b200_layer_norm_bwd")
-    sums = partial.sum(0)
+    # dgamma | dbeta = column sums of the per-CTA partial rows (two tiny launches of the column-sum kernel instead of a PyTorch reduction)
+    sums = col_sum(partial.view(_LN_BWD_BLOCKS, 2 * C)).view(2, C) if (LN_BWD_COL_SUM and C % 2 == 0) else partial.sum(0)
     return dx, sums[0], sums[1], dres
 
 

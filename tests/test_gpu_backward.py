@@ -381,3 +381,26 @@ def test_gelu_backward_two_mufu_form(monkeypatch):
     ref32 = ops.gelu(x32, dy32)
     monkeypatch.setattr(ops, "GELU_BWD_FAST", True)
     assert torch.equal(ops.gelu(x32, dy32), ref32)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_linear_residual_in_epilogue(dt):
+    """LinearFn with the residual added in the GEMM epilogue (ANEMOI_B200_TRAIN_FUSE_RES) == the Linear followed by a PyTorch add: forward and all
+    four gradients (the residual's is the cotangent itself)."""
+    from anemoi_core_b200 import autograd as AG
+
+    torch.manual_seed(8)
+    g = torch.randn(3001, 512, device="cuda")
+    res = {}
+    for fused in (False, True):
+        torch.manual_seed(9)
+        x = torch.randn(3001, 256, device="cuda", requires_grad=True)
+        w = torch.randn(512, 256, device="cuda", requires_grad=True)
+        b = torch.randn(512, device="cuda", requires_grad=True)
+        r = torch.randn(3001, 512, device="cuda").to(dt).requires_grad_()
+        y = AG.linear(x, w, b, dt, False, r) if fused else AG.linear(x, w, b, dt) + r
+        (y.float() * g).sum().backward()
+        res[fused] = (y, x.grad, w.grad, b.grad, r.grad)
+    tol = 1e-5 if dt == torch.float32 else 1e-2  # bf16: one rounding of (acc + bias + residual) against two
+    for a, c, n in zip(res[True], res[False], ("y", "dx", "dW", "db", "dres")):
+        close(a, c, f"fused residual {n} {dt}", tol if n == "y" else 1e-6)

@@ -138,6 +138,34 @@ def test_gelu_exp2_polynomial():
     assert np.abs(y - ref).max() <= 1e-6
 
 
+def test_gelu_backward_two_exp2_form():
+    """The bf16 GELU backward (csrc/backward.cu gelu_vec_kernel mode 2: Phi(-|x|) = exp2(P5(|x|)), phi(x) = exp2(-x^2 / (2 ln 2)) / sqrt(2 pi))
+    restated in fp32 numpy with the coefficients parsed from the source: gelu'(x) within 1.5e-5 absolute of the derivative of the exact erf-GELU
+    (the bound the header and DESIGN.md quote; a bf16 cotangent's ulp is 4e-3)."""
+    import re
+    from pathlib import Path
+
+    import numpy as np
+
+    src = (Path(__file__).resolve().parents[1] / "anemoi_core_b200" / "csrc" / "common.cuh").read_text()
+    c = [np.float32(t.strip().rstrip("f")) for t in re.search(r"#define ANEMOI_GELU_P5 (.*)", src).group(1).split(",")]
+    bwd = (Path(__file__).resolve().parents[1] / "anemoi_core_b200" / "csrc" / "backward.cu").read_text()
+    k = np.float32(re.search(r'"f"\((-0\.7213475\d*)f \* v\[j\] \* v\[j\]\)', bwd).group(1))
+    assert abs(float(k) + 1.0 / (2.0 * np.log(2.0))) < 1e-7
+    x = np.concatenate([np.linspace(-30, 30, 600001), [0.0, -0.0, 1e-30, -1e-30, 1e4, -1e4]]).astype(np.float32)
+    t = np.minimum(np.abs(x), np.float32(10.0))
+    p = np.full_like(t, c[5])
+    for i in range(4, -1, -1):
+        p = (p * t + c[i]).astype(np.float32)
+    ex = np.exp2(p).astype(np.float32)
+    pd = np.exp2((k * x * x).astype(np.float32)).astype(np.float32)
+    cdf = np.where(x >= 0, np.float32(1.0) - ex, ex)
+    d = (x * (np.float32(0.39894228040143267794) * pd) + cdf).astype(np.float32)
+    xd = torch.from_numpy(x).double().requires_grad_()
+    torch.nn.functional.gelu(xd).sum().backward()
+    assert np.abs(d.astype(np.float64) - xd.grad.numpy()).max() <= 1.5e-5
+
+
 def test_row_stats_tags_follow_the_tensor_identity():
     """Statistics handed from a producing GEMM to the consuming LayerNorm-GEMM travel as a tag on the tensor object and are dropped as soon
     as the tensor is not the one that was produced (slice, in-place update through torch, another object on the same storage)."""

@@ -35,6 +35,28 @@ def wants_grad(module: nn.Module, *tensors: Optional[Tensor]) -> bool:
     return module.training and any(p.requires_grad for p in module.parameters())
 
 
+# Activation checkpointing of the processors' training path (reference: layers/processor.py:129-147 ``run_layer_chunk`` under
+# torch.utils.checkpoint, one checkpoint per chunk of num_layers / num_chunks layers, when ``gradient_checkpointing``): the chunk's forward is
+# re-run in the backward instead of keeping its activations (~1.2 GB per 512-wide cfg2 layer).  The kernels are deterministic, so the recomputed
+# forward is bit-identical; exchanges inside a chunk are re-run by every rank alike.  Opt-in: verified under the CPU stand-ins only
+# (tests/test_sharded_training_gloo.py), it has not run on a GPU yet.
+ACT_CHECKPOINT = os.environ.get("ANEMOI_B200_ACT_CHECKPOINT", "0") != "0"
+
+
+def run_chunks(proc: nn.Module, run_chunk, *state):
+    """``state = run_chunk(first_layer, last_layer, *state)`` over the processor's chunks, each under an activation checkpoint if asked for."""
+    wrap = ACT_CHECKPOINT and getattr(proc, "gradient_checkpointing", False)
+    for i in range(0, proc.num_layers, proc.chunk_size):
+        j = min(i + proc.chunk_size, proc.num_layers)
+        if wrap:
+            from torch.utils.checkpoint import checkpoint
+
+            state = checkpoint(run_chunk, i, j, *state, use_reentrant=False)
+        else:
+            state = run_chunk(i, j, *state)
+    return state
+
+
 def _single_gpu(group, what: str = "this module") -> None:
     from ..distributed.graph import group_size
 

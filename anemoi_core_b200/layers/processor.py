@@ -3,7 +3,8 @@
 Drop-in for ``anemoi.models.layers.processor.{GNNProcessor, GraphTransformerProcessor}``: keyword-only constructors
 with the reference's names, ``forward(x, batch_size, shard_info, edge_attr, edge_index, model_comm_group=None,
 edges_are_dst_sorted=True)``, blocks held in ``self.proc`` (same ``state_dict`` keys).  Activation checkpointing
-and CPU offload are training-memory devices of the reference and are accepted but inert on this forward path.
+(``gradient_checkpointing``, one checkpoint per chunk of ``num_layers / num_chunks`` layers like the reference's ``run_layer_chunk``) applies
+to the training path when ``ANEMOI_B200_ACT_CHECKPOINT=1`` (layers/_train.py:run_chunks; inert under ``no_grad``); CPU offload is refused.
 """
 
 from __future__ import annotations
@@ -159,9 +160,14 @@ class GNNProcessor(BaseProcessor):
                     shard_info = GraphShardInfo(nodes=shard_info.nodes, edges=edge_sizes)
             elif world > 1:
                 edge_index = _localise_presharded_edges(edge_index, shard_info.nodes, model_comm_group)
-            for block in self.proc:
-                x, edge_attr = block(x, edge_attr, edge_index, shard_info, model_comm_group if world > 1 else None)
-            return x
+            group = model_comm_group if world > 1 else None
+
+            def run_chunk(i: int, j: int, x: Tensor, edge_attr: Tensor):
+                for block in self.proc[i:j]:
+                    x, edge_attr = block(x, edge_attr, edge_index, shard_info, group)
+                return x, edge_attr
+
+            return T.run_chunks(self, run_chunk, x, edge_attr)[0]
         if not shard_info.edges_are_sharded():
             edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
             if group_size(model_comm_group) > 1:
@@ -260,10 +266,14 @@ class GraphTransformerProcessor(BaseProcessor):
                     shard_info = GraphShardInfo(nodes=shard_info.nodes, edges=edge_sizes)
             elif world > 1:
                 edge_index = _localise_presharded_edges(edge_index, shard_info.nodes, model_comm_group)
-            for block in self.proc:
-                x, _ = block(x, edge_attr, edge_index, shard_info, batch_size, n_nodes, model_comm_group if world > 1 else None,
-                             cond=kwargs.get("cond"))  # fmt: skip
-            return x
+            group, cond = model_comm_group if world > 1 else None, kwargs.get("cond")
+
+            def run_chunk(i: int, j: int, x: Tensor, edge_attr: Tensor):
+                for block in self.proc[i:j]:
+                    x, _ = block(x, edge_attr, edge_index, shard_info, batch_size, n_nodes, group, cond=cond)
+                return x, edge_attr
+
+            return T.run_chunks(self, run_chunk, x, edge_attr)[0]
         if not shard_info.edges_are_sharded():
             edge_attr, edge_index = ensure_edges_are_dst_sorted(edge_attr, edge_index, edges_are_dst_sorted)
             if group_size(model_comm_group) > 1 and self.shard_strategy == "edges":

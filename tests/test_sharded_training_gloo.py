@@ -137,10 +137,61 @@ def _check_model(rank, world):
     return msgs
 
 
+def _check_checkpoint(rank, world):
+    """Activation checkpointing of the processors' training path (ANEMOI_B200_ACT_CHECKPOINT; reference layers/processor.py:129-147): a sharded
+    training step with every chunk of layers re-run in the backward gives the gradients of the plain step (the exchanges inside a chunk are
+    re-run by both ranks alike), and the chunks really went through torch.utils.checkpoint."""
+    import torch.utils.checkpoint as tuc
+
+    from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
+    from anemoi_core_b200.distributed.graph import shard_rows
+    from anemoi_core_b200.distributed.shapes import GraphShardInfo
+    from anemoi_core_b200.layers import GNNProcessor
+    from anemoi_core_b200.layers import GraphTransformerProcessor
+    from anemoi_core_b200.layers import _train as T
+
+    n, e, d = 61, 400, 5
+    ei, ea0 = _graph(n, e, d, seed=3)
+    sizes = get_balanced_partition_sizes(n, world)
+    group = dist.group.WORLD
+    calls = []
+    real = tuc.checkpoint
+    tuc.checkpoint = lambda *a, **k: (calls.append(1), real(*a, **k))[1]
+    msgs = []
+    for kind in ("gt_edges", "gnn"):
+        torch.manual_seed(0)
+        if kind == "gt_edges":
+            c = 32
+            m = GraphTransformerProcessor(num_layers=4, num_channels=c, num_chunks=2, num_heads=4, mlp_hidden_ratio=2, edge_dim=d)
+        else:
+            c = 16
+            m = GNNProcessor(num_channels=c, num_layers=4, num_chunks=2, mlp_extra_layers=0, edge_dim=d)
+        m.train()
+        x0 = torch.randn(n, c, generator=torch.Generator().manual_seed(4))
+        w = shard_rows(torch.randn(n, c, generator=torch.Generator().manual_seed(5)), sizes, group)
+        got = {}
+        for on in (False, True):
+            T.ACT_CHECKPOINT = on
+            del calls[:]
+            m.zero_grad()
+            xs = shard_rows(x0, sizes, group).contiguous().clone().requires_grad_()
+            ea = ea0.clone().requires_grad_()
+            (m(xs, 1, GraphShardInfo(nodes=sizes), ea, ei, group) * w).sum().backward()
+            got[on] = (xs.grad.clone(), ea.grad.clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+            assert len(calls) == (2 if on else 0), f"{kind}: {len(calls)} checkpointed chunks with ACT_CHECKPOINT={on}"
+        T.ACT_CHECKPOINT = False
+        assert set(got[True][2]) == set(got[False][2])
+        err_x = max(((got[True][i] - got[False][i]).abs().max() / got[False][i].abs().max()).item() for i in (0, 1))
+        err_p = max(((got[True][2][k] - g).abs().max() / max(g.abs().max().item(), 1e-12)).item() for k, g in got[False][2].items())
+        msgs.append((f"checkpoint_{kind}", err_x, err_p))
+    tuc.checkpoint = real
+    return msgs
+
+
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize("fn_name", ["_check", "_check_model"])
+@pytest.mark.parametrize("fn_name", ["_check", "_check_model", "_check_checkpoint"])
 def test_sharded_training_step_matches_single_rank_gloo(fn_name):
     world = 2
     with tempfile.TemporaryDirectory() as d:

@@ -232,7 +232,8 @@ def check_goldens_single_rank(rank, world):
     def strip(cfg):
         return {k: v for k, v in cfg.items()}
 
-    for name in ("gt_processor_small", "gt_processor_qknorm", "gt_processor_edge_pre_mlp", "gt_processor_attn_channels", "gt_processor_swiglu"):
+    for name in ("gt_processor_small", "gt_processor_qknorm", "gt_processor_edge_pre_mlp", "gt_processor_attn_channels", "gt_processor_swiglu",
+                 "gt_processor_glu", "gt_processor_geglu", "gt_processor_reglu"):  # fmt: skip
         g = load(name)
         m = GraphTransformerProcessor(num_chunks=1, mlp_hidden_ratio=4, **strip(g["cfg"])).eval()
         m.load_state_dict(g["sd"], strict=True)

@@ -246,3 +246,21 @@ def test_bench_reference_arm_runs_on_cpu():
     quiet = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "small", "--steps", "1"],
                            capture_output=True, text=True, timeout=600, env=env)  # fmt: skip
     assert quiet.returncode == 0 and quiet.stdout.strip() == ""
+
+
+def test_integer_path_fuzz_against_the_unmodified_reference():
+    """A few hundred random graphs (incl. parts without edges, one hub destination, duplicate edges, parts == destinations) through the integer /
+    index path — sort, partition splits, part materialisation, src compaction, balanced sizes — bit-exact against the UNMODIFIED reference
+    functions (oracle/fuzz_integer_path.py, in a subprocess: the reference's ``anemoi`` package must not share a process with the overlay tests)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "oracle", "fuzz_integer_path.py"), "150"], capture_output=True, text=True, timeout=600,
+                         check=True).stdout.strip().splitlines()[-1]  # fmt: skip
+    res = json.loads(out)
+    if "unavailable" in res:
+        pytest.skip(res["unavailable"])
+    assert res["failures"] == [] and res["checks"] > 5000, res

@@ -264,3 +264,22 @@ def test_integer_path_fuzz_against_the_unmodified_reference():
     if "unavailable" in res:
         pytest.skip(res["unavailable"])
     assert res["failures"] == [] and res["checks"] > 5000, res
+
+
+def test_module_fuzz_against_the_unmodified_reference():
+    """Random constructor configurations of both processors and all four mappers (channels, heads, layers, chunks, hidden ratio, qk_norm, gated
+    MLPs, edge_pre_mlp, attn_channels, unsorted edges, bipartite sizes): the inference path and the training path (output + gradients of every
+    parameter, the node inputs, the edge attributes) of the drop-in modules over the CPU stand-ins against the UNMODIFIED reference modules with the
+    same ``state_dict`` (oracle/fuzz_modules.py, in a subprocess), 1e-4 of each tensor's scale."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "oracle", "fuzz_modules.py"), "60"], capture_output=True, text=True, timeout=900,
+                         check=True).stdout.strip().splitlines()[-1]  # fmt: skip
+    res = json.loads(out)
+    if "unavailable" in res:
+        pytest.skip(res["unavailable"])
+    assert res["failures"] == [] and res["cases"] == 60 and set(res["worst"]) == {"inference", "training forward", "input gradients", "parameter gradients"}, res

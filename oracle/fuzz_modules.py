@@ -50,6 +50,17 @@ def _pick(g, options):
     return options[int(torch.randint(0, len(options), (1,), generator=g))]
 
 
+def _cond_kernels(dc: int):
+    """(reference, ours) ``layer_kernels`` selecting ConditionalLayerNorm (normalization.py:34-94) for the LayerNorm kernel, or (None, None)."""
+    if not dc:
+        return None, None
+    from anemoi.utils.config import DotDict
+
+    kw = {"condition_shape": dc, "zero_init": False}
+    return (DotDict({"LayerNorm": {"_target_": "anemoi.models.layers.normalization.ConditionalLayerNorm", **kw}}),
+            {"LayerNorm": {"_target_": "anemoi_core_b200.layers.normalization.ConditionalLayerNorm", **kw}})  # fmt: skip
+
+
 def _compare(ref_m, our_m, call_ref, call_ours, inputs, g, tag, worst, fails):
     """``inputs``: dict name -> tensor (differentiable inputs); call_*(module, **inputs) -> tensor or tuple of tensors."""
     our_m.load_state_dict({k: v.detach().clone() for k, v in ref_m.state_dict().items()}, strict=True)
@@ -124,11 +135,16 @@ def main(n_cases: int) -> dict:
             n = int(torch.randint(20, 120, (1,), generator=g))
             ei, ea = _graph(g, n, n, int(torch.randint(n, 6 * n, (1,), generator=g)), edge_dim, sort)
             cfg.update(num_chunks=_pick(g, [c_ for c_ in (1, 2, 3) if cfg["num_layers"] % c_ == 0]), mlp_hidden_ratio=_pick(g, [2, 4]))
-            ref_m = _randomise(RP.GraphTransformerProcessor(layer_kernels=None, graph_attention_backend="pyg", **cfg), g)
-            our_m = L.GraphTransformerProcessor(**cfg)
+            dc = _pick(g, [0, 0, 0, 8])  # one in four: ConditionalLayerNorm kernels driven by a per-node conditioning tensor (cond=)
+            lk_ref, lk_ours = _cond_kernels(dc)
+            ref_m = _randomise(RP.GraphTransformerProcessor(layer_kernels=lk_ref, graph_attention_backend="pyg", **cfg), g)
+            our_m = L.GraphTransformerProcessor(layer_kernels=lk_ours, **cfg)
             inputs = {"x": torch.randn(n, cfg["num_channels"], generator=g), "edge_attr": ea}
-            call_ref = lambda m, x, edge_attr: m(x, 1, RGSI(nodes=None, edges=None), edge_attr, ei, None, edges_are_dst_sorted=sort)  # noqa: E731
-            call_ours = lambda m, x, edge_attr: m(x, 1, GraphShardInfo(), edge_attr, ei, None, edges_are_dst_sorted=sort)  # noqa: E731
+            if dc:
+                inputs["cond"] = torch.randn(n, dc, generator=g)
+                cfg["condition_shape"] = dc
+            call_ref = lambda m, x, edge_attr, **kw: m(x, 1, RGSI(nodes=None, edges=None), edge_attr, ei, None, edges_are_dst_sorted=sort, **kw)  # noqa: E731
+            call_ours = lambda m, x, edge_attr, **kw: m(x, 1, GraphShardInfo(), edge_attr, ei, None, edges_are_dst_sorted=sort, **kw)  # noqa: E731
         elif kind == "gnn_processor":
             cfg = dict(num_channels=_pick(g, [16, 32, 48, 64]), num_layers=_pick(g, [1, 2, 3]), mlp_extra_layers=_pick(g, [0, 0, 1]), edge_dim=edge_dim,
                        mlp_implementation=_pick(g, ["mlp", "mlp", "swiglu"]))  # fmt: skip
@@ -161,12 +177,24 @@ def main(n_cases: int) -> dict:
                     cfg["in_channels_dst"] = c  # the GNN decoder's destination rows are hidden rows (mapper.py:1045-1054)
             name = {"gt_forward_mapper": "GraphTransformerForwardMapper", "gt_backward_mapper": "GraphTransformerBackwardMapper",
                     "gnn_forward_mapper": "GNNForwardMapper", "gnn_backward_mapper": "GNNBackwardMapper"}[kind]  # fmt: skip
+            dc = _pick(g, [0, 0, 0, 8]) if kind == "gt_forward_mapper" else 0
+            if dc:
+                extra_ref["layer_kernels"], extra_ours["layer_kernels"] = _cond_kernels(dc)
             ref_m = _randomise(getattr(RM, name)(**cfg, **extra_ref), g)
             our_m = getattr(L, name)(**cfg, **extra_ours)
             inputs = {"x_src": torch.randn(n_src, cfg["in_channels_src"], generator=g), "x_dst": torch.randn(n_dst, cfg["in_channels_dst"], generator=g), "edge_attr": ea}
-            call_ref = lambda m, x_src, x_dst, edge_attr: m((x_src, x_dst), 1, RBSI(src_nodes=None, dst_nodes=None, edges=None), edge_attr, ei, None)  # noqa: E731
-            call_ours = lambda m, x_src, x_dst, edge_attr: m((x_src, x_dst), 1, BipartiteGraphShardInfo(), edge_attr, ei, None)  # noqa: E731
+            if dc:
+                inputs.update(cond_src=torch.randn(n_src, dc, generator=g), cond_dst=torch.randn(n_dst, dc, generator=g))
+                cfg["condition_shape"] = dc
+
+            def _kw(cond_src=None, cond_dst=None):
+                return {} if cond_src is None else {"cond": (cond_src, cond_dst)}
+
+            call_ref = lambda m, x_src, x_dst, edge_attr, **c: m((x_src, x_dst), 1, RBSI(src_nodes=None, dst_nodes=None, edges=None), edge_attr, ei, None, **_kw(**c))  # noqa: E731
+            call_ours = lambda m, x_src, x_dst, edge_attr, **c: m((x_src, x_dst), 1, BipartiteGraphShardInfo(), edge_attr, ei, None, **_kw(**c))  # noqa: E731
         tag = f"case {case} {kind} {cfg}"
+        if "condition_shape" in cfg:
+            kinds["with ConditionalLayerNorm"] = kinds.get("with ConditionalLayerNorm", 0) + 1
         try:
             _compare(ref_m, our_m, call_ref, call_ours, inputs, g, tag, worst, fails)
         except Exception as e:  # noqa: BLE001

@@ -134,11 +134,19 @@ class HaloPlan:
 _PLANS: dict = {}
 
 
+def tensor_ident(t: Tensor) -> tuple:
+    """Cache identity of a tensor whose cache entry HOLDS the tensor: (storage pointer, in-place version) — or, for an EMPTY tensor, the object
+    itself.  A rank whose rows receive no edge holds an empty local edge list, and every empty tensor has the same data_ptr: keyed on the pointer,
+    two graphs with the same partition would share that rank's cached split / plan while the other ranks miss and enter the plan's collectives
+    alone (a hang; tests/test_sharded_forward_gloo.py::test_degenerate_graphs).  The entry keeps the tensor alive, so the id cannot be recycled."""
+    return (t.data_ptr(), t._version) if t.numel() else ("empty", id(t))
+
+
 def halo_plan_for(edge_index: Tensor, src_splits: list[int], group) -> HaloPlan:
     """Plan for the local edge list ``edge_index`` (GLOBAL src ids, LOCAL dst ids, as the processors / mappers shard it) over source
     rows partitioned by ``src_splits``; cached on the tensor.  Square graphs pass the node partition."""
     world, me = group_size(group), group_rank(group)
-    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), str(edge_index.device), tuple(src_splits), world, me, id(group))
+    key = (tensor_ident(edge_index), tuple(edge_index.shape), str(edge_index.device), tuple(src_splits), world, me, id(group))
     hit = _PLANS.get(key)
     if hit is not None:
         return hit[1]

@@ -19,6 +19,7 @@ from torch import nn
 from .. import ops
 from ..distributed.graph import group_rank
 from ..distributed.graph import group_size
+from ..distributed.halo import tensor_ident
 from ..distributed.khop_edges import build_graph_partition
 from ..distributed.khop_edges import ensure_edges_are_dst_sorted
 from ..distributed.shapes import GraphShardInfo
@@ -73,7 +74,7 @@ def _shard_edges_by_dst(edge_attr: Tensor, edge_index: Tensor, n_dst: int, n_src
     or are relabelled to the local range (GraphTransformer).  The split is computed once per (graph, group) and cached.
     Returns (edge_attr view, edge_index, per-rank edge counts)."""
     world, rank = group_size(group), group_rank(group)
-    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), str(edge_index.device), n_dst, n_src, world, rank, relabel_dst,
+    key = (tensor_ident(edge_index), tuple(edge_index.shape), str(edge_index.device), n_dst, n_src, world, rank, relabel_dst,
            None if dst_splits is None else tuple(dst_splits))
     hit = _SHARD_CACHE.get(key)
     if hit is None:
@@ -99,7 +100,7 @@ def _localise_presharded_edges(edge_index: Tensor, dst_splits, group) -> Tensor:
     (tensor, group) and the result cached on the tensor identity."""
     rank = group_rank(group)
     start = int(sum(dst_splits[:rank]))
-    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), str(edge_index.device), start)
+    key = (tensor_ident(edge_index), tuple(edge_index.shape), str(edge_index.device), start)
     hit = _LOCAL_CACHE.get(key)
     if hit is None:
         local = edge_index.clone()

@@ -99,6 +99,53 @@ def check_processors(rank, world):
         assert ((full16.float() - full).norm() / full.norm()).item() <= 3e-2
 
 
+def check_degenerate_graphs(rank, world):
+    """Shapes a real mesh never has but a drop-in must survive: destinations without edges, ranks whose rows receive no edge at all, every source
+    on one rank, a single edge, one node per rank.  Sharded == single rank for both processors (GraphTransformer: halo exchange; GNN: all-gather
+    and halo form)."""
+    import anemoi_core_b200.layers.processor as proc_mod
+    from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
+    from anemoi_core_b200.distributed.graph import gather_rows
+    from anemoi_core_b200.distributed.graph import shard_rows
+    from anemoi_core_b200.distributed.shapes import GraphShardInfo
+    from anemoi_core_b200.layers import GNNProcessor
+    from anemoi_core_b200.layers import GraphTransformerProcessor
+
+    group = dist.group.WORLD
+    d = 4
+    g = torch.Generator().manual_seed(11)
+
+    def graph(n, src, dst):
+        ei = torch.stack([src, dst])
+        ei = ei[:, torch.sort(ei[1], stable=True)[1]].contiguous()
+        return ei, torch.randn(ei.shape[1], d, generator=torch.Generator().manual_seed(int(ei.sum()) + n))
+
+    cases = {}
+    n = 2 * world + 1
+    sz = get_balanced_partition_sizes(n, world)
+    cases["sparse: destinations without edges"] = (n, *graph(n, torch.randint(0, n, (n,), generator=g), torch.randint(0, n, (n,), generator=g)))
+    cases["all edges into the first rank's rows"] = (n, *graph(n, torch.randint(0, n, (3 * n,), generator=g), torch.randint(0, sz[0], (3 * n,), generator=g)))
+    cases["all sources on the last rank"] = (n, *graph(n, torch.randint(n - sz[-1], n, (3 * n,), generator=g), torch.randint(0, n, (3 * n,), generator=g)))
+    cases["a single edge"] = (n, *graph(n, torch.tensor([n - 1]), torch.tensor([0])))
+    cases["one node per rank"] = (world, *graph(world, torch.randint(0, world, (2 * world,), generator=g), torch.randint(0, world, (2 * world,), generator=g)))
+    for what, (n, ei, ea) in cases.items():
+        sizes = get_balanced_partition_sizes(n, world)
+        for kind in ("gt", "gnn"):
+            torch.manual_seed(5)
+            if kind == "gt":
+                m, c = GraphTransformerProcessor(num_layers=2, num_channels=32, num_chunks=1, num_heads=4, mlp_hidden_ratio=2, edge_dim=d).eval(), 32
+            else:
+                m, c = GNNProcessor(num_channels=16, num_layers=2, num_chunks=1, mlp_extra_layers=0, edge_dim=d).eval(), 16
+            x = torch.randn(n, c, generator=torch.Generator().manual_seed(6))
+            full = m(x, 1, GraphShardInfo(nodes=[n]), ea, ei)
+            for halo in ((False,) if kind == "gt" else (False, True)):
+                proc_mod.GNN_HALO = halo
+                local = m(shard_rows(x, sizes, group).contiguous(), 1, GraphShardInfo(nodes=sizes), ea, ei, group)
+                proc_mod.GNN_HALO = False
+                assert local.shape[0] == sizes[rank]
+                _close(gather_rows(local, sizes, group), full, f"{what}, {kind}{', halo form' if halo else ''}")
+
+
 def check_heads_strategy(rank, world):
     """shard_strategy="heads" (Ulysses, block.py:689-759): nodes sharded outside the attention, heads inside; full edge list on every rank."""
     from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
@@ -303,6 +350,11 @@ def test_host_logic_against_reference_goldens():
 @pytest.mark.parametrize("world", [2, 3, 4])
 def test_sharded_processors(world):
     run_distributed("check_processors", world)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_degenerate_graphs(world):
+    run_distributed("check_degenerate_graphs", world)
 
 
 @pytest.mark.parametrize("world", [2, 4])

@@ -239,6 +239,49 @@ def check_enc_proc_dec(rank, world):
     _close(gather_rows(src_l, get_balanced_partition_sizes(n_grid, world), dist.group.WORLD), src_full, "GNNForwardMapper src shard")
 
 
+def check_degenerate_enc_proc_dec(rank, world):
+    """The whole sharded step on bipartite graphs a real grid / mesh pair never has: mesh rows no grid point maps to, a rank whose mesh rows get no
+    encoder edge, every encoder source on the last rank, every decoder edge into the first rank's grid rows, grid points the decoder never writes."""
+    from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
+    from anemoi_core_b200.model import EncProcDec
+
+    n_grid, n_mesh, d = 11 * world + 3, 4 * world + 1, 4
+    gs, ms = get_balanced_partition_sizes(n_grid, world), get_balanced_partition_sizes(n_mesh, world)
+    g = torch.Generator().manual_seed(13)
+
+    def graph(src, dst):
+        ei = torch.stack([src, dst])
+        ei = ei[:, torch.sort(ei[1], stable=True)[1]].contiguous()
+        return ei, torch.randn(ei.shape[1], d, generator=g)
+
+    def rnd(lo, hi, k):
+        return torch.randint(lo, hi, (k,), generator=g)
+
+    variants = {
+        "sparse": dict(enc=graph(rnd(0, n_grid, n_mesh), rnd(0, n_mesh, n_mesh)), proc=graph(rnd(0, n_mesh, n_mesh), rnd(0, n_mesh, n_mesh)),
+                       dec=graph(rnd(0, n_mesh, n_grid // 2), rnd(0, n_grid, n_grid // 2))),
+        "one-sided": dict(enc=graph(rnd(n_grid - gs[-1], n_grid, 40), rnd(0, ms[0], 40)), proc=graph(rnd(n_mesh - ms[-1], n_mesh, 30), rnd(0, ms[0], 30)),
+                          dec=graph(rnd(n_mesh - ms[-1], n_mesh, 40), rnd(0, gs[0], 40))),
+    }  # fmt: skip
+    xg, xm = torch.randn(n_grid, 9, generator=g), torch.randn(n_mesh, 6, generator=g)
+    g0, m0 = sum(gs[:rank]), sum(ms[:rank])
+    for what, v in variants.items():
+        gr = {"enc_index": v["enc"][0], "enc_attr": v["enc"][1], "proc_index": v["proc"][0], "proc_attr": v["proc"][1], "dec_index": v["dec"][0],
+              "dec_attr": v["dec"][1]}  # fmt: skip
+        torch.manual_seed(1)
+        gt = EncProcDec("graphtransformer", in_grid=9, in_mesh=6, out_grid=5, num_channels=32, num_layers=2, edge_dim=d, num_heads=4).eval()
+        full = gt(xg, xm, gr)
+        _close(gt(xg, xm, gr, dist.group.WORLD, ms, gs), full, f"{what}: EncProcDec graphtransformer")
+        part = gt(xg[g0 : g0 + gs[rank]].contiguous(), xm[m0 : m0 + ms[rank]].contiguous(), gr, model_comm_group=dist.group.WORLD, mesh_shards=ms,
+                  grid_shards=gs, keep_output_sharded=True, inputs_sharded=True)  # fmt: skip
+        _close(part, full[g0 : g0 + gs[rank]], f"{what}: EncProcDec graphtransformer, sharded inputs and outputs")
+        torch.manual_seed(2)
+        gnn = EncProcDec("gnn", in_grid=9, in_mesh=6, out_grid=5, num_channels=16, num_layers=2, edge_dim=d).eval()
+        full = gnn(xg, xm, gr)
+        _close(gnn(xg, xm, gr, dist.group.WORLD, ms, None), full, f"{what}: EncProcDec gnn")
+        _close(gnn(xg, xm, gr, dist.group.WORLD, ms, gs), full, f"{what}: EncProcDec gnn, sharded mappers")
+
+
 def check_model_forward(rank, world):
     """``AnemoiModelEncProcDec.forward`` with ``model_comm_group``: hidden rows sharded, provider-sharded edges (global dst ids), replicated grid."""
     import importlib.util
@@ -355,6 +398,11 @@ def test_sharded_processors(world):
 @pytest.mark.parametrize("world", [2, 3])
 def test_degenerate_graphs(world):
     run_distributed("check_degenerate_graphs", world)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_degenerate_enc_proc_dec(world):
+    run_distributed("check_degenerate_enc_proc_dec", world)
 
 
 @pytest.mark.parametrize("world", [2, 4])

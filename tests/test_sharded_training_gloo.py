@@ -87,6 +87,59 @@ def _check(rank, world):
     return msgs
 
 
+def _check_degenerate(rank, world):
+    """Training on graphs where a rank's rows receive no edge, every source lives on the last rank, or destinations have no edge at all: the
+    autograd halves of the exchanges with empty send / receive lists; sharded gradients == single-rank gradients."""
+    from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
+    from anemoi_core_b200.distributed.graph import shard_rows
+    from anemoi_core_b200.distributed.shapes import GraphShardInfo
+    from anemoi_core_b200.layers import GNNProcessor
+    from anemoi_core_b200.layers import GraphTransformerProcessor
+
+    n, d = 4 * world + 1, 4
+    sizes = get_balanced_partition_sizes(n, world)
+    group = dist.group.WORLD
+    g = torch.Generator().manual_seed(17)
+
+    def graph(src, dst):
+        ei = torch.stack([src, dst])
+        ei = ei[:, torch.sort(ei[1], stable=True)[1]].contiguous()
+        return ei, torch.randn(ei.shape[1], d, generator=g)
+
+    graphs = {"sparse": graph(torch.randint(0, n, (n,), generator=g), torch.randint(0, n, (n,), generator=g)),
+              "into_first_rank": graph(torch.randint(0, n, (3 * n,), generator=g), torch.randint(0, sizes[0], (3 * n,), generator=g)),
+              "from_last_rank": graph(torch.randint(n - sizes[-1], n, (3 * n,), generator=g), torch.randint(0, n, (3 * n,), generator=g))}  # fmt: skip
+    msgs = []
+    for what, (ei, ea) in graphs.items():
+        for kind in ("gt", "gnn"):
+            torch.manual_seed(0)
+            if kind == "gt":
+                c, m = 32, GraphTransformerProcessor(num_layers=2, num_channels=32, num_chunks=1, num_heads=4, mlp_hidden_ratio=2, edge_dim=d)
+            else:
+                c, m = 16, GNNProcessor(num_channels=16, num_layers=2, num_chunks=1, mlp_extra_layers=0, edge_dim=d)
+            m.train()
+            x0 = torch.randn(n, c, generator=torch.Generator().manual_seed(4))
+            w = torch.randn(n, c, generator=torch.Generator().manual_seed(5))
+            xf = x0.clone().requires_grad_()
+            (m(xf, 1, GraphShardInfo(nodes=[n]), ea, ei) * w).sum().backward()
+            ref_p = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+            ref_x = xf.grad.clone()
+            m.zero_grad()
+            xs = shard_rows(x0, sizes, group).contiguous().clone().requires_grad_()
+            (m(xs, 1, GraphShardInfo(nodes=sizes), ea, ei, group) * shard_rows(w, sizes, group)).sum().backward()
+            rx = shard_rows(ref_x, sizes, group)
+            err_x = ((xs.grad - rx).abs().max() / ref_x.abs().max()).item()
+            worst, big = 0.0, max(gr.abs().max().item() for gr in ref_p.values())
+            for k, p in m.named_parameters():
+                if k not in ref_p:
+                    continue
+                gp = p.grad.clone() if p.grad is not None else torch.zeros_like(p)
+                dist.all_reduce(gp)
+                worst = max(worst, ((gp - ref_p[k]).abs().max() / max(ref_p[k].abs().max().item(), 1e-3 * big)).item())
+            msgs.append((f"degenerate_{what}_{kind}", err_x, worst))
+    return msgs
+
+
 def _check_model(rank, world):
     """The WHOLE encoder -> processor -> decoder step in training mode, every stage sharded (the call sequence of tests/test_gpu_multi.py's
     training section, here under Gloo on CPU): sharded input / output rows for the GraphTransformer model, replicated in / gathered out for the
@@ -191,7 +244,7 @@ def _check_checkpoint(rank, world):
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize("fn_name", ["_check", "_check_model", "_check_checkpoint"])
+@pytest.mark.parametrize("fn_name", ["_check", "_check_model", "_check_checkpoint", "_check_degenerate"])
 def test_sharded_training_step_matches_single_rank_gloo(fn_name):
     world = 2
     with tempfile.TemporaryDirectory() as d:

@@ -101,6 +101,31 @@ class WeightPack:
         return self.get(("f32", id(p)), [p], lambda: p.detach().float().contiguous())
 
 
+class PackOwner(nn.Module):
+    """Base of the modules that own a ``WeightPack`` (``self._pack``).  Derived weights are revalidated against (storage pointer, version counter)
+    of their source parameters on every call — but an in-place edit through ``param.data`` (some EMA / weight-swapping utilities) moves neither.
+    As a second line of defence every switch between training and evaluation mode drops the derived tensors, so that an evaluation phase always
+    starts from the current parameters; a FROZEN pack (``freeze_packed_weights``: the user promised not to mutate, and a captured CUDA graph may
+    hold the derived tensors' addresses) is left alone.  ``invalidate_packed_weights`` does the same on demand."""
+
+    def train(self, mode: bool = True):
+        pack = getattr(self, "_pack", None)
+        if isinstance(pack, WeightPack) and mode != self.training and not pack.frozen:
+            pack._store.clear()
+        return super().train(mode)
+
+
+def invalidate_packed_weights(module: nn.Module) -> nn.Module:
+    """Drop every derived (cast / concatenated / folded) weight under ``module``; the next forward rebuilds them from the parameters.  For code
+    that edits parameters through ``.data`` (which bumps no version counter).  Not while a captured CUDA graph of the module is alive: the graph
+    reads the derived tensors at their captured addresses."""
+    for m in module.modules():
+        pack = getattr(m, "_pack", None)
+        if isinstance(pack, WeightPack):
+            pack._store.clear()
+    return module
+
+
 def freeze_packed_weights(module: nn.Module, frozen: bool = True) -> nn.Module:
     """Inference switch: stop re-validating the derived (cast / concatenated / folded) weights against the parameters on every
     call (a tuple of data_ptr / _version per source tensor, a few microseconds per GEMM on the host).  Call again with False —

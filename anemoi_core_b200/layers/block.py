@@ -183,7 +183,7 @@ class GraphConvMapperBlock(GraphConvBaseBlock):
 # ------------------------------------------------------------------------------------------------------------
 # GraphTransformer blocks
 # ------------------------------------------------------------------------------------------------------------
-class GraphTransformerBaseBlock(nn.Module):
+class GraphTransformerBaseBlock(Fn.PackOwner):
     """Edge-softmax attention block (block.py:482-687).  Per forward:
     LN -> one GEMM for q|k|v|self -> fused attention(+lin_edge, +self) -> projection GEMM(+skip) -> LN -> MLP GEMMs(+residual).
     """

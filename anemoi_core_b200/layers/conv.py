@@ -38,7 +38,7 @@ def _sorted_plan(edge_index: Tensor, n_src: int, n_dst: int) -> tuple[ops.GraphC
     return ops.build_csr(sorted_ei.contiguous(), n_src, n_dst), perm.to(torch.int32)
 
 
-class GraphConv(nn.Module):
+class GraphConv(Fn.PackOwner):
     """e' = edge_mlp([x_dst[dst], x_src[src], e]) + e ;  out[d] = sum_{edges into d} e'   (conv.py:66-81).
 
     Kernel decomposition: the first Linear of ``edge_mlp`` acts on a concatenation, so

@@ -34,7 +34,7 @@ from .utils import load_layer_kernels
 PairTensor = tuple[Tensor, Tensor]
 
 
-class BaseMapper(nn.Module):
+class BaseMapper(Fn.PackOwner):
     def __init__(
         self,
         *,

@@ -44,7 +44,7 @@ class GatedMLPLayer(nn.Module):
         self.kind = mlp_implementation
 
 
-class MLP(nn.Module):
+class MLP(Fn.PackOwner):
     def __init__(
         self,
         in_features: int,

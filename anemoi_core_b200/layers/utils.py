@@ -19,7 +19,11 @@ from typing import Optional
 class LayerKernels(dict):
     """dict with attribute access (the reference uses anemoi.utils.config.DotDict)."""
 
-    __getattr__ = dict.__getitem__
+    def __getattr__(self, name: str):
+        try:
+            return self[name]
+        except KeyError:  # AttributeError, not KeyError: copy.deepcopy / pickle probe __deepcopy__ / __getstate__ with getattr(obj, name, None)
+            raise AttributeError(name) from None
 
 
 DEFAULT_KERNELS = {

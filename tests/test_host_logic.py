@@ -283,3 +283,40 @@ def test_module_fuzz_against_the_unmodified_reference():
     if "unavailable" in res:
         pytest.skip(res["unavailable"])
     assert res["failures"] == [] and res["cases"] == 60 and set(res["worst"]) == {"inference", "training forward", "input gradients", "parameter gradients"}, res
+
+
+def test_modules_deepcopy_and_pickle(golden):
+    """``copy.deepcopy`` (EMA / SWA wrappers, Lightning callbacks) and pickling of whole modules (the reference's inference checkpoints pickle the
+    model object) work on every drop-in class and on the model, and the copies carry the same ``state_dict``."""
+    import copy
+    import io
+
+    from anemoi_core_b200.layers import GNNBackwardMapper
+    from anemoi_core_b200.layers import GNNForwardMapper
+    from anemoi_core_b200.layers import GNNProcessor
+    from anemoi_core_b200.layers import GraphTransformerBackwardMapper
+    from anemoi_core_b200.layers import GraphTransformerForwardMapper
+    from anemoi_core_b200.layers import GraphTransformerProcessor
+    from test_model_glue import build_model
+
+    mods = [GraphTransformerProcessor(num_layers=2, num_channels=32, num_chunks=1, num_heads=4, mlp_hidden_ratio=2, edge_dim=5, qk_norm=True),
+            GNNProcessor(num_channels=16, num_layers=2, num_chunks=1, mlp_extra_layers=0, edge_dim=5, mlp_implementation="swiglu"),
+            GraphTransformerForwardMapper(in_channels_src=7, in_channels_dst=5, hidden_dim=32, num_chunks=1, num_heads=4, mlp_hidden_ratio=2, edge_dim=3),
+            GraphTransformerBackwardMapper(in_channels_src=32, in_channels_dst=7, hidden_dim=32, out_channels_dst=4, num_chunks=1, num_heads=4,
+                                           mlp_hidden_ratio=2, edge_dim=3),
+            GNNForwardMapper(in_channels_src=7, in_channels_dst=5, hidden_dim=16, num_chunks=1, mlp_extra_layers=0, edge_dim=3),
+            GNNBackwardMapper(in_channels_src=16, in_channels_dst=16, hidden_dim=16, out_channels_dst=4, num_chunks=1, mlp_extra_layers=0, edge_dim=3),
+            build_model(golden("model_forward"), "graphtransformer"), build_model(golden("model_forward"), "gnn")]  # fmt: skip
+    for m in mods:
+        for clone in (copy.deepcopy(m), torch.load(io.BytesIO(_dump(m)), weights_only=False)):
+            assert type(clone) is type(m) and clone is not m
+            a, b = m.state_dict(), clone.state_dict()
+            assert list(a) == list(b) and all(torch.equal(a[k], b[k]) and a[k].data_ptr() != b[k].data_ptr() for k in a if a[k].numel())
+
+
+def _dump(m) -> bytes:
+    import io
+
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    return buf.getvalue()

@@ -146,6 +146,63 @@ def check_degenerate_graphs(rank, world):
                 _close(gather_rows(local, sizes, group), full, f"{what}, {kind}{', halo form' if halo else ''}")
 
 
+def check_derived_weights_follow_the_parameters(rank, world):
+    """The derived weights of the inference path (casts, concatenations, LayerNorm / lin_edge folds; ``WeightPack``) against every way parameters
+    change: an optimizer-style in-place update (version counter), ``load_state_dict``, an edit through ``.data`` (NO version bump: caught by the
+    train() / eval() switch or by ``invalidate_packed_weights``); a frozen pack is left alone."""
+    import copy
+
+    from anemoi_core_b200.distributed.shapes import GraphShardInfo
+    from anemoi_core_b200.layers import GNNProcessor
+    from anemoi_core_b200.layers import GraphTransformerProcessor
+    from anemoi_core_b200.layers import _functional as Fn
+
+    n, e, d = 40, 160, 5
+    ei, ea = _graph(n, n, e, d, seed=21)
+    for kind in ("gt", "gnn"):
+        torch.manual_seed(3)
+        if kind == "gt":
+            m, c = GraphTransformerProcessor(num_layers=2, num_channels=32, num_chunks=1, num_heads=4, mlp_hidden_ratio=2, edge_dim=d).eval(), 32
+        else:
+            m, c = GNNProcessor(num_channels=48, num_layers=2, num_chunks=1, mlp_extra_layers=0, edge_dim=d).eval(), 48  # 48: the decomposed GraphConv form
+        x = torch.randn(n, c, generator=torch.Generator().manual_seed(22))
+        run = lambda mod: mod(x, 1, GraphShardInfo(nodes=[n]), ea, ei)  # noqa: E731
+
+        def fresh():  # a new module with the current parameters: nothing derived is cached in it
+            f = copy.deepcopy(m)
+            Fn.invalidate_packed_weights(f)
+            return run(f.eval())
+
+        y0 = run(m)
+        gen = torch.Generator().manual_seed(23)
+        for p in m.parameters():  # optimizer-style update
+            p.add_(0.05 * torch.randn(p.shape, generator=gen))
+        y1 = run(m)
+        assert (y1 - y0).abs().max() > 1e-3
+        _close(y1, fresh(), f"{kind}: after an in-place parameter update")
+        sd = {k: v + 0.05 * torch.randn(v.shape, generator=gen) for k, v in m.state_dict().items()}
+        m.load_state_dict(sd, strict=True)
+        _close(run(m), fresh(), f"{kind}: after load_state_dict")
+        before = run(m)
+        for p in m.parameters():  # through .data: neither the storage pointer nor the version counter moves
+            p.data.add_(0.05 * torch.randn(p.shape, generator=gen))
+        m.train()
+        m.eval()
+        y2 = run(m)
+        assert (y2 - before).abs().max() > 1e-3
+        _close(y2, fresh(), f"{kind}: .data edit, then train() / eval()")
+        for p in m.parameters():
+            p.data.add_(0.05 * torch.randn(p.shape, generator=gen))
+        Fn.invalidate_packed_weights(m)
+        _close(run(m), fresh(), f"{kind}: .data edit, then invalidate_packed_weights")
+        Fn.freeze_packed_weights(m)
+        held = [len(mod._pack._store) for mod in m.modules() if isinstance(getattr(mod, "_pack", None), Fn.WeightPack)]
+        m.train()
+        m.eval()
+        assert held == [len(mod._pack._store) for mod in m.modules() if isinstance(getattr(mod, "_pack", None), Fn.WeightPack)] and sum(held) > 0
+        Fn.freeze_packed_weights(m, False)
+
+
 def check_heads_strategy(rank, world):
     """shard_strategy="heads" (Ulysses, block.py:689-759): nodes sharded outside the attention, heads inside; full edge list on every rank."""
     from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
@@ -403,6 +460,10 @@ def test_degenerate_graphs(world):
 @pytest.mark.parametrize("world", [2, 3])
 def test_degenerate_enc_proc_dec(world):
     run_distributed("check_degenerate_enc_proc_dec", world)
+
+
+def test_derived_weights_follow_the_parameters():
+    run_distributed("check_derived_weights_follow_the_parameters", 1)
 
 
 @pytest.mark.parametrize("world", [2, 4])

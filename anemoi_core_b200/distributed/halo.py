@@ -28,6 +28,7 @@ import torch
 import torch.distributed as dist
 from torch import Tensor
 
+from .._ident import tensor_ident  # noqa: F401  (re-exported: layers/processor.py)
 from .graph import SegmentedCapture
 from .graph import _exchange
 from .graph import group_rank
@@ -132,14 +133,6 @@ class HaloPlan:
 
 
 _PLANS: dict = {}
-
-
-def tensor_ident(t: Tensor) -> tuple:
-    """Cache identity of a tensor whose cache entry HOLDS the tensor: (storage pointer, in-place version) — or, for an EMPTY tensor, the object
-    itself.  A rank whose rows receive no edge holds an empty local edge list, and every empty tensor has the same data_ptr: keyed on the pointer,
-    two graphs with the same partition would share that rank's cached split / plan while the other ranks miss and enter the plan's collectives
-    alone (a hang; tests/test_sharded_forward_gloo.py::test_degenerate_graphs).  The entry keeps the tensor alive, so the id cannot be recycled."""
-    return (t.data_ptr(), t._version) if t.numel() else ("empty", id(t))
 
 
 def halo_plan_for(edge_index: Tensor, src_splits: list[int], group) -> HaloPlan:

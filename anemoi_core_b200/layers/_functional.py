@@ -11,6 +11,7 @@ from typing import Sequence
 
 import torch
 from torch import Tensor
+from .._ident import version
 from torch import nn
 
 from .. import ops
@@ -57,7 +58,7 @@ class WeightPack:
             hit = self._store.get(key)
             if hit is not None:
                 return hit[1]
-        sig = tuple(None if t is None else (t.data_ptr(), t._version) for t in sources)  # storage identity + in-place version counter
+        sig = tuple(None if t is None else (t.data_ptr(), version(t)) for t in sources)  # storage identity + in-place version counter
         hit = self._store.get(key)
         if hit is not None and hit[0] == sig:
             return hit[1]
@@ -178,13 +179,13 @@ FUSED_ROW_STATS = os.environ.get("ANEMOI_B200_FUSED_ROW_STATS", "0") != "0"
 
 
 def tag_row_stats(t: Tensor, stats: Tensor) -> Tensor:
-    t._anemoi_row_stats = (stats, t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()))
+    t._anemoi_row_stats = (stats, t.data_ptr(), version(t), tuple(t.shape), tuple(t.stride()))
     return t
 
 
 def tagged_row_stats(t: Tensor) -> Optional[Tensor]:
     tag = getattr(t, "_anemoi_row_stats", None)
-    if tag is None or tag[1:] != (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride())):
+    if tag is None or tag[1:] != (t.data_ptr(), version(t), tuple(t.shape), tuple(t.stride())):
         return None
     return tag[0]
 
@@ -283,7 +284,7 @@ def csr_for(edge_index: Tensor, n_src: int, n_dst: int) -> ops.GraphCSR:
     """CSR plan of a dst-sorted edge_index, cached on the tensor's identity (storage pointer, version, shape).  The
     cache holds a reference to the tensor so its storage cannot be recycled under the key.  Built once per static
     graph; the reference rebuilds its CSC (two sorts) per layer per forward (layers/block.py:779-782)."""
-    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), tuple(edge_index.stride()), str(edge_index.device), n_src, n_dst)
+    key = (edge_index.data_ptr(), version(edge_index), tuple(edge_index.shape), tuple(edge_index.stride()), str(edge_index.device), n_src, n_dst)
     hit = _CSR_CACHE.get(key)
     if hit is not None:
         _CSR_CACHE.move_to_end(key)

@@ -26,6 +26,7 @@ from typing import Optional
 import numpy as np
 import torch
 from torch import Tensor
+from .._ident import version
 
 MODE = os.environ.get("ANEMOI_B200_REORDER", "auto")
 ENABLED = MODE == "1"  # unconditional (A/B switch); "auto" is decided per call by the processors (``wanted``)
@@ -115,7 +116,7 @@ _PLANS: dict = {}
 def locality_plan(edge_index: Tensor, n_nodes: int, min_nodes: int = MIN_NODES, coords: Optional[np.ndarray] = None) -> Optional[ReorderPlan]:
     """Plan for a square (processor) graph, cached on the edge_index tensor; ``None`` when reordering is pointless or impossible.
     ``coords`` [N, 3] (unit vectors) skips the eigensolve."""
-    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), str(edge_index.device), n_nodes)
+    key = (edge_index.data_ptr(), version(edge_index), tuple(edge_index.shape), str(edge_index.device), n_nodes)
     if key in _PLANS:
         return _PLANS[key][1]
     plan = None
@@ -153,7 +154,7 @@ _ATTR_CACHE: dict = {}
 
 def permute_edge_attr(edge_attr: Tensor, plan: ReorderPlan) -> Tensor:
     """``edge_attr[plan.edge_perm]``, cached on the attribute tensor (graph providers hand back the same tensor every step)."""
-    key = (edge_attr.data_ptr(), edge_attr._version, tuple(edge_attr.shape), plan.edge_perm.data_ptr())
+    key = (edge_attr.data_ptr(), version(edge_attr), tuple(edge_attr.shape), plan.edge_perm.data_ptr())
     hit = _ATTR_CACHE.get(key)
     if hit is None:
         hit = (edge_attr, edge_attr.index_select(0, plan.edge_perm).contiguous())

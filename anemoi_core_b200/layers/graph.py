@@ -14,6 +14,7 @@ from typing import Optional
 
 import torch
 from torch import Tensor
+from .._ident import version
 from torch import nn
 
 
@@ -41,8 +42,8 @@ class TrainableTensor(nn.Module):
         if t is not None and torch.is_grad_enabled() and t.requires_grad:
             # someone wants gradients w.r.t. the trainable tensor: plain differentiable assembly, no cache
             return torch.cat([_repeat_rows(x, batch_size), _repeat_rows(t.to(x.device), batch_size)], dim=-1)
-        key = (x.data_ptr(), x._version, tuple(x.shape), x.dtype, str(x.device), batch_size,
-               None if t is None else (t.data_ptr(), t._version, str(t.device)))  # fmt: skip
+        key = (x.data_ptr(), version(x), tuple(x.shape), x.dtype, str(x.device), batch_size,
+               None if t is None else (t.data_ptr(), version(t), str(t.device)))  # fmt: skip
         if key != self._cache_key:
             parts = [_repeat_rows(x, batch_size)]
             if t is not None:

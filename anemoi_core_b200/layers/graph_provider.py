@@ -20,6 +20,7 @@ from typing import Optional
 
 import torch
 from torch import Tensor
+from .._ident import version
 from torch import nn
 
 from ..distributed.graph import group_rank
@@ -93,7 +94,7 @@ class StaticGraphProvider(BaseGraphProvider):
 
     def _expand_edges(self, edge_index: Tensor, edge_inc: Tensor, batch_size: int) -> Tensor:
         """``cat([edge_index + i * edge_inc for i in range(batch_size)], 1)`` (graph_provider.py:210-231), built once per batch size."""
-        key = (edge_index.data_ptr(), edge_index._version, str(edge_index.device))
+        key = (edge_index.data_ptr(), version(edge_index), str(edge_index.device))
         hit = self._expanded.get(batch_size)
         if hit is None or hit[0] != key:
             out = edge_index if batch_size == 1 else torch.cat([edge_index + i * edge_inc for i in range(batch_size)], dim=1).contiguous()
@@ -112,7 +113,7 @@ class StaticGraphProvider(BaseGraphProvider):
         # 1-hop sharding of a dst-sorted list = contiguous edge ranges from the in-degrees (khop_edges.py:302-312)
         rank = group_rank(model_comm_group)
         skey = (batch_size, world, rank)
-        key = (edge_index.data_ptr(), edge_index._version)
+        key = (edge_index.data_ptr(), version(edge_index))
         hit = self._shards.get(skey)
         if hit is None or hit[0] != key:
             src_size, dst_size = self._sizes

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import torch
 from torch import Tensor
+from ._ident import version
 
 from . import ops
 
@@ -28,7 +29,7 @@ _CSR: dict = {}
 def _csr_from_csc(row: Tensor, colptr: Tensor, n_src: int, rowptr: Tensor, edge_ids: Tensor, edge_dst: Tensor) -> ops.GraphCSR:
     """GraphCSR view of the reference's ``(row, colptr)`` / ``(rowptr, edge_ids, edge_dst)`` tensors (triton/utils.py:25-70), int32
     copies cached on the tensors' identity."""
-    key = (row.data_ptr(), row._version, colptr.data_ptr(), colptr._version, tuple(row.shape), n_src)
+    key = (row.data_ptr(), version(row), colptr.data_ptr(), version(colptr), tuple(row.shape), n_src)
     hit = _CSR.get(key)
     if hit is not None:
         return hit[1]

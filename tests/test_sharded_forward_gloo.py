@@ -203,6 +203,91 @@ def check_derived_weights_follow_the_parameters(rank, world):
         Fn.freeze_packed_weights(m, False)
 
 
+def check_inference_mode(rank, world):
+    """``torch.inference_mode()`` (Lightning's validate / test / predict loops enter it by default): tensors created inside it track no version
+    counter and ``t._version`` raises, so every identity-keyed cache (CSR plans, edge splits, halo plans, derived weights, row-statistics tags, graph
+    provider outputs) must cope.  Processors (also sharded), all four mappers and the whole model: same result as under ``no_grad``."""
+    import importlib.util
+
+    from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
+    from anemoi_core_b200.distributed.graph import gather_rows
+    from anemoi_core_b200.distributed.graph import shard_rows
+    from anemoi_core_b200.distributed.shapes import BipartiteGraphShardInfo
+    from anemoi_core_b200.distributed.shapes import GraphShardInfo
+    from anemoi_core_b200.layers import GNNBackwardMapper
+    from anemoi_core_b200.layers import GNNForwardMapper
+    from anemoi_core_b200.layers import GNNProcessor
+    from anemoi_core_b200.layers import GraphTransformerBackwardMapper
+    from anemoi_core_b200.layers import GraphTransformerForwardMapper
+    from anemoi_core_b200.layers import GraphTransformerProcessor
+
+    group = dist.group.WORLD
+    n, e, d = 41, 170, 5
+    ei, ea = _graph(n, n, e, d, seed=31)
+    sizes = get_balanced_partition_sizes(n, world)
+    for kind, c in (("gt", 32), ("gnn", 16), ("gnn", 48)):
+        torch.manual_seed(3)
+        m = (GraphTransformerProcessor(num_layers=2, num_channels=c, num_chunks=1, num_heads=4, mlp_hidden_ratio=2, edge_dim=d, qk_norm=True) if kind == "gt"
+             else GNNProcessor(num_channels=c, num_layers=2, num_chunks=1, mlp_extra_layers=0, edge_dim=d)).eval()  # fmt: skip
+        x = torch.randn(n, c, generator=torch.Generator().manual_seed(32))
+        ref = m(x, 1, GraphShardInfo(nodes=[n]), ea, ei)
+        with torch.inference_mode():
+            xi, eai, eii = x.clone(), ea.clone(), ei.clone()  # inference tensors
+            assert xi.is_inference() and eii.is_inference()
+            _close(m(xi, 1, GraphShardInfo(nodes=[n]), eai, eii), ref, f"{kind} {c}: inference_mode")
+            _close(m(xi, 1, GraphShardInfo(nodes=[n]), eai, eii), ref, f"{kind} {c}: inference_mode, cached plans")
+            if world > 1:
+                local = m(shard_rows(xi, sizes, group).contiguous(), 1, GraphShardInfo(nodes=sizes), eai, eii, group)
+                _close(gather_rows(local, sizes, group), ref, f"{kind} {c}: inference_mode, sharded")
+        if world == 1:
+            # a validation phase under inference_mode followed by a training step on the SAME (normal) graph tensors: whatever the first phase
+            # cached for this graph (plans built from tensors created inside inference mode) must serve the differentiable path as well
+            import copy
+
+            m2 = copy.deepcopy(m)
+            with torch.inference_mode():
+                _close(m(x, 1, GraphShardInfo(nodes=[n]), ea, ei), ref, f"{kind} {c}: inference_mode on normal tensors")
+            grads = []
+            for mod, graph in ((m, (ea, ei)), (m2, (ea.clone(), ei.clone()))):  # m2 on fresh graph tensors: nothing cached
+                with torch.enable_grad():
+                    mod.train()
+                    xt = x.clone().requires_grad_()
+                    mod(xt, 1, GraphShardInfo(nodes=[n]), *graph).square().sum().backward()
+                    grads.append([xt.grad] + [p.grad for p in mod.parameters() if p.grad is not None])
+                    mod.eval()
+            assert len(grads[0]) == len(grads[1]) and all(torch.equal(a, b) for a, b in zip(*grads)), f"{kind} {c}: training after an inference_mode phase"
+    if world > 1:
+        return
+    n_src, n_dst = 53, 37
+    bi = BipartiteGraphShardInfo()
+    g = torch.Generator().manual_seed(33)
+    for cls, kw, cin in ((GraphTransformerForwardMapper, dict(in_channels_src=7, in_channels_dst=5, hidden_dim=32, num_heads=4, mlp_hidden_ratio=2), (7, 5)),
+                         (GraphTransformerBackwardMapper, dict(in_channels_src=32, in_channels_dst=7, hidden_dim=32, out_channels_dst=4, num_heads=4, mlp_hidden_ratio=2), (32, 7)),
+                         (GNNForwardMapper, dict(in_channels_src=7, in_channels_dst=5, hidden_dim=16, mlp_extra_layers=0), (7, 5)),
+                         (GNNBackwardMapper, dict(in_channels_src=16, in_channels_dst=16, hidden_dim=16, out_channels_dst=4, mlp_extra_layers=0), (16, 16))):  # fmt: skip
+        torch.manual_seed(4)
+        m = cls(num_chunks=1, edge_dim=d, **kw).eval()
+        mei, mea = _graph(n_src, n_dst, 150, d, seed=34)
+        xs, xd = torch.randn(n_src, cin[0], generator=g), torch.randn(n_dst, cin[1], generator=g)
+        ref = m((xs, xd), 1, bi, mea, mei)
+        with torch.inference_mode():
+            got = m((xs.clone(), xd.clone()), 1, bi, mea.clone(), mei.clone())
+        for a, b in zip(got if isinstance(got, tuple) else (got,), ref if isinstance(ref, tuple) else (ref,)):
+            _close(a, b, f"{cls.__name__}: inference_mode")
+    spec = importlib.util.spec_from_file_location("_glue", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_model_glue.py"))
+    glue = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(glue)
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_forward.pt"), weights_only=False)
+    for kind in ("graphtransformer", "gnn"):
+        m = glue.build_model(fx, kind)
+        m.load_state_dict(fx["cases"][kind]["sd"], strict=True)
+        with torch.inference_mode():
+            y = m({"data": fx["x"].clone()})["data"]
+            y_again = m({"data": fx["x"].clone()})["data"]
+        _close(y, fx["cases"][kind]["y"], f"AnemoiModelEncProcDec {kind}: inference_mode")
+        assert torch.equal(y, y_again)
+
+
 def check_heads_strategy(rank, world):
     """shard_strategy="heads" (Ulysses, block.py:689-759): nodes sharded outside the attention, heads inside; full edge list on every rank."""
     from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
@@ -460,6 +545,11 @@ def test_degenerate_graphs(world):
 @pytest.mark.parametrize("world", [2, 3])
 def test_degenerate_enc_proc_dec(world):
     run_distributed("check_degenerate_enc_proc_dec", world)
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_inference_mode(world):
+    run_distributed("check_inference_mode", world)
 
 
 def test_derived_weights_follow_the_parameters():

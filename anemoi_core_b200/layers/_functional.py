@@ -11,18 +11,38 @@ from typing import Sequence
 
 import torch
 from torch import Tensor
-from .._ident import version
 from torch import nn
 
 from .. import ops
+from .._ident import version
 
 SUPPORTED = (torch.float32, torch.bfloat16)
 
 
+# fp16 autocast (the reference's default training precision, "16-mixed": training/config/training/single.yaml:30): there are no fp16 kernels here.
+# "bf16" (default): compute as under bf16 autocast, with a one-time warning - same tensor-core path, fp32 accumulation, fp32's exponent range
+# (a GradScaler's loss scale is harmless), 8 instead of 11 significand bits in the stored activations; "fp32": the fp32 path (exact bf16 x 3 split
+# on the tensor cores: at least fp16's accuracy, ~5x slower than bf16); "error": refuse.
+FP16_AUTOCAST = os.environ.get("ANEMOI_B200_FP16_AUTOCAST", "bf16")
+_warned_fp16 = False
+
+
 def compute_dtype(*tensors: Tensor) -> torch.dtype:
-    """bf16 under ``torch.autocast(dtype=bfloat16)`` or for bf16 inputs (tcgen05 path); fp32 otherwise (parity mode)."""
+    """bf16 under ``torch.autocast(dtype=bfloat16)`` or for bf16 inputs (tcgen05 path); fp32 otherwise (parity mode); fp16 autocast: FP16_AUTOCAST."""
+    global _warned_fp16
+    if any(t.dtype == torch.float16 for t in tensors):
+        raise NotImplementedError("float16 tensors are not supported by the B200 kernels (float32 and bfloat16 are): cast them with .to(torch.bfloat16); "
+                                  "under fp16 autocast the modules compute in bfloat16 and return bfloat16 (ANEMOI_B200_FP16_AUTOCAST)")  # fmt: skip
     if torch.is_autocast_enabled("cuda"):
         dt = torch.get_autocast_dtype("cuda")
+        if dt == torch.float16 and FP16_AUTOCAST in ("bf16", "fp32"):
+            if not _warned_fp16:
+                import warnings
+
+                warnings.warn(f"anemoi_core_b200: fp16 autocast requested; the B200 path has no fp16 kernels and computes in "
+                              f"{'bfloat16' if FP16_AUTOCAST == 'bf16' else 'float32'} instead (ANEMOI_B200_FP16_AUTOCAST=bf16|fp32|error)", stacklevel=3)  # fmt: skip
+                _warned_fp16 = True
+            dt = torch.bfloat16 if FP16_AUTOCAST == "bf16" else torch.float32
     else:
         dt = tensors[0].dtype
         for t in tensors[1:]:

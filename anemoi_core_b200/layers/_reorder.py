@@ -26,6 +26,7 @@ from typing import Optional
 import numpy as np
 import torch
 from torch import Tensor
+
 from .._ident import version
 
 MODE = os.environ.get("ANEMOI_B200_REORDER", "auto")

@@ -14,8 +14,9 @@ from typing import Optional
 
 import torch
 from torch import Tensor
-from .._ident import version
 from torch import nn
+
+from .._ident import version
 
 
 def _repeat_rows(x: Tensor, batch_size: int) -> Tensor:

@@ -20,9 +20,9 @@ from typing import Optional
 
 import torch
 from torch import Tensor
-from .._ident import version
 from torch import nn
 
+from .._ident import version
 from ..distributed.graph import group_rank
 from ..distributed.graph import group_size
 from ..distributed.khop_edges import build_graph_partition

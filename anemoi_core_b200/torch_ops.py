@@ -19,9 +19,9 @@ from __future__ import annotations
 
 import torch
 from torch import Tensor
-from ._ident import version
 
 from . import ops
+from ._ident import version
 
 _CSR: dict = {}
 

@@ -320,3 +320,31 @@ def _dump(m) -> bytes:
     buf = io.BytesIO()
     torch.save(m, buf)
     return buf.getvalue()
+
+
+def test_compute_dtype_policy(monkeypatch):
+    """fp32 / bf16 by input dtype or bf16 autocast; fp16 autocast (the reference's default "16-mixed") maps to bf16 with one warning, to fp32 or to
+    an error by ANEMOI_B200_FP16_AUTOCAST; fp16 TENSORS are refused with a message that says what to do."""
+    import warnings
+
+    from anemoi_core_b200.layers import _functional as Fn
+
+    a, b = torch.zeros(2, 2), torch.zeros(2, 2, dtype=torch.bfloat16)
+    assert Fn.compute_dtype(a) == torch.float32 and Fn.compute_dtype(b) == torch.bfloat16 and Fn.compute_dtype(a, b) == torch.float32
+    with pytest.raises(NotImplementedError, match="bfloat16"):
+        Fn.compute_dtype(a.half())
+    state = {"dt": torch.bfloat16}
+    monkeypatch.setattr(torch, "is_autocast_enabled", lambda *args: True)
+    monkeypatch.setattr(torch, "get_autocast_dtype", lambda *args: state["dt"])
+    assert Fn.compute_dtype(a) == torch.bfloat16
+    state["dt"] = torch.float16
+    monkeypatch.setattr(Fn, "_warned_fp16", False)
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        assert Fn.compute_dtype(a) == torch.bfloat16 and Fn.compute_dtype(a) == torch.bfloat16
+    assert len([w for w in rec if "fp16 autocast" in str(w.message)]) == 1  # once
+    monkeypatch.setattr(Fn, "FP16_AUTOCAST", "fp32")
+    assert Fn.compute_dtype(a) == torch.float32
+    monkeypatch.setattr(Fn, "FP16_AUTOCAST", "error")
+    with pytest.raises(NotImplementedError):
+        Fn.compute_dtype(a)

@@ -211,23 +211,26 @@ class AnemoiModelEncProcDec(nn.Module):
             enc_cls, proc_cls, dec_cls = GraphTransformerForwardMapper, GraphTransformerProcessor, GraphTransformerBackwardMapper
         else:
             enc_cls, proc_cls, dec_cls = GNNForwardMapper, GNNProcessor, GNNBackwardMapper
-        self.encoder_graph_provider, self.encoder = nn.ModuleDict(), nn.ModuleDict()
-        self.decoder_graph_provider, self.decoder = nn.ModuleDict(), nn.ModuleDict()
-        for ds in self.dataset_names:
-            self.encoder_graph_provider[ds] = create_graph_provider(graph=graph_data[(ds, "to", hid)], edge_attributes=edge_attributes, src_size=n[ds],
-                                                                   dst_size=n[hid], trainable_size=tp.get("data2hidden", 0))  # fmt: skip
-            self.encoder[ds] = enc_cls(in_channels_src=self.input_dim[ds], in_channels_dst=self.input_dim_latent, hidden_dim=num_channels,
-                                       edge_dim=self.encoder_graph_provider[ds].edge_dim, **encoder)  # fmt: skip
+        # Sub-modules are registered in the reference's order (encoder_processor_decoder.py:51-96: the three graph providers, then encoder,
+        # processor, decoder): ``parameters()`` then enumerates like the reference's, which is what an optimizer state_dict indexes by, so a
+        # reference training checkpoint resumes with its moments on the right tensors (tests/test_model_glue.py checks the key ORDER).
+        self.encoder_graph_provider = nn.ModuleDict({
+            ds: create_graph_provider(graph=graph_data[(ds, "to", hid)], edge_attributes=edge_attributes, src_size=n[ds], dst_size=n[hid],
+                                      trainable_size=tp.get("data2hidden", 0)) for ds in self.dataset_names})  # fmt: skip
         self.processor_graph_provider = create_graph_provider(graph=graph_data[(hid, "to", hid)], edge_attributes=edge_attributes, src_size=n[hid],
                                                               dst_size=n[hid], trainable_size=tp.get("hidden2hidden", 0))  # fmt: skip
+        self.decoder_graph_provider = nn.ModuleDict({
+            ds: create_graph_provider(graph=graph_data[(hid, "to", ds)], edge_attributes=edge_attributes, src_size=n[hid], dst_size=n[ds],
+                                      trainable_size=tp.get("hidden2data", 0)) for ds in self.dataset_names})  # fmt: skip
+        self.encoder = nn.ModuleDict({
+            ds: enc_cls(in_channels_src=self.input_dim[ds], in_channels_dst=self.input_dim_latent, hidden_dim=num_channels,
+                        edge_dim=self.encoder_graph_provider[ds].edge_dim, **encoder) for ds in self.dataset_names})  # fmt: skip
         self.processor = proc_cls(num_channels=num_channels, edge_dim=self.processor_graph_provider.edge_dim, **processor)
-        for ds in self.dataset_names:
-            self.decoder_graph_provider[ds] = create_graph_provider(graph=graph_data[(hid, "to", ds)], edge_attributes=edge_attributes, src_size=n[hid],
-                                                                   dst_size=n[ds], trainable_size=tp.get("hidden2data", 0))  # fmt: skip
-            # GT: the decoder embeds the raw assembled grid input (mapper.py:698-701); GNN: its dst input is the encoder's src embedding
-            in_dst = self.input_dim[ds] if kind == "graphtransformer" else num_channels
-            self.decoder[ds] = dec_cls(in_channels_src=num_channels, in_channels_dst=in_dst, hidden_dim=num_channels, out_channels_dst=self.output_dim[ds],
-                                       edge_dim=self.decoder_graph_provider[ds].edge_dim, **decoder)  # fmt: skip
+        # GT: the decoder embeds the raw assembled grid input (mapper.py:698-701); GNN: its dst input is the encoder's src embedding
+        self.decoder = nn.ModuleDict({
+            ds: dec_cls(in_channels_src=num_channels, in_channels_dst=self.input_dim[ds] if kind == "graphtransformer" else num_channels,
+                        hidden_dim=num_channels, out_channels_dst=self.output_dim[ds], edge_dim=self.decoder_graph_provider[ds].edge_dim, **decoder)
+            for ds in self.dataset_names})  # fmt: skip
         # per-output-variable tables of the fused output kernel (plain attributes like the reference's bounding index tensors: no state_dict keys)
         self._tables: dict = {}
         self._bound_spec = {ds: list((boundings or {}).get(ds, [])) for ds in self.dataset_names}

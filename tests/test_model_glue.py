@@ -42,6 +42,8 @@ def test_model_state_dict_is_the_reference_one(golden, kind):
     m = build_model(fx, kind)
     ref_sd = fx["cases"][kind]["sd"]
     assert sorted(m.state_dict().keys()) == sorted(ref_sd.keys())
+    # ... in the reference's ORDER: parameters() enumerates like the reference's, which is what an optimizer state_dict indexes by
+    assert list(m.state_dict().keys()) == list(ref_sd.keys())
     missing, unexpected = m.load_state_dict(ref_sd, strict=True)
     assert not missing and not unexpected
     assert m.input_dim["data"] == fx["cases"][kind]["in_dim"] and m.input_dim_latent == fx["cases"][kind]["lat_dim"]
@@ -175,5 +177,5 @@ def test_two_dataset_model_state_dict(golden):
     added (no GPU time was left in round 1 to run it, and an unrun GPU test does not belong in the suite)."""
     fx = golden("model_forward_two_datasets")
     m = build_two_dataset_model(fx)
-    assert sorted(m.state_dict().keys()) == sorted(fx["sd"].keys())  # encoder.era.*, encoder.obs.*, decoder_graph_provider.obs.* ...
+    assert list(m.state_dict().keys()) == list(fx["sd"].keys())  # encoder.era.*, encoder.obs.*, decoder_graph_provider.obs.* ..., reference order
     m.load_state_dict(fx["sd"], strict=True)

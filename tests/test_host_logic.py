@@ -349,3 +349,20 @@ def test_compute_dtype_policy(monkeypatch):
     monkeypatch.setattr(Fn, "FP16_AUTOCAST", "error")
     with pytest.raises(NotImplementedError):
         Fn.compute_dtype(a)
+
+
+def test_call_surface_matches_the_unmodified_reference():
+    """Constructor parameters, their effective defaults and the positional order of ``forward`` of the 15 drop-in classes against the reference
+    classes themselves (oracle/check_signatures.py, in a subprocess)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "oracle", "check_signatures.py")], capture_output=True, text=True, timeout=300,
+                         check=True).stdout.strip().splitlines()[-1]  # fmt: skip
+    res = json.loads(out)
+    if "unavailable" in res:
+        pytest.skip(res["unavailable"])
+    assert res["problems"] == [] and res["classes"] == 15, res

@@ -311,7 +311,8 @@ class AnemoiModelEncProcDec(nn.Module):
             self._tables[key] = (skip.to(device), bound.to(device))
         return self._tables[key]
 
-    def _assemble_input(self, x: Tensor, batch_size: int, grid_shard_sizes, model_comm_group, dataset_name: str, dt: torch.dtype):
+    def _assemble_input(self, x: Tensor, batch_size: int, grid_shard_sizes, model_comm_group, dataset_name: str, dt: torch.dtype,
+                        differentiable: bool = False):  # fmt: skip
         from .distributed.graph import shard_rows
         from .layers._functional import pad_k
 
@@ -319,14 +320,34 @@ class AnemoiModelEncProcDec(nn.Module):
         sizes = grid_shard_sizes[dataset_name] if grid_shard_sizes is not None else None
         if sizes is not None:
             attrs = shard_rows(attrs, sizes, model_comm_group)
+        if differentiable:
+            # training: the reference's own statement (encoder_processor_decoder.py:115-125) in PyTorch, so that autograd reaches the input and the
+            # trainable node tensor; the mappers' differentiable path casts / pads its GEMM operands itself
+            b, t, e, g, v = x.shape
+            rows = x.permute(0, 2, 3, 1, 4).reshape(b * e * g, t * v).float()
+            return torch.cat([rows, attrs.float().repeat(rows.shape[0] // max(attrs.shape[0], 1), 1)], dim=-1), sizes
         k = x.shape[1] * x.shape[4] + attrs.shape[1]
         return ops.assemble_input(x, attrs, dt, k_pad=pad_k(k, dt)), sizes
+
+    def _assemble_output_differentiable(self, dec: Tensor, x: Tensor, batch_size: int, ensemble_size: int, dataset_name: str) -> Tensor:
+        """Training: ``_assemble_output`` (encoder_processor_decoder.py:129-163: rearrange, SkipConnection residual of the input's ``residual_step``
+        slice on the prognostic variables, the bounding layers) as out-of-place PyTorch operations on the same per-variable tables the fused
+        inference kernel reads."""
+        skip, bound = self._output_tables(dataset_name, dec.device)
+        g = dec.shape[0] // (batch_size * ensemble_size)
+        y = dec.float().reshape(batch_size, ensemble_size, g, self.n_step_output, -1).permute(0, 3, 1, 2, 4)
+        has = skip >= 0
+        res = x[:, self.residual_step].float().unsqueeze(1)[..., skip.clamp_min(0).long()] * has.to(y.dtype)  # [B, 1, E, G, V_out], zero where no residual
+        y = y + res
+        y = torch.where(bound == 1, torch.relu(y), torch.where(bound == 2, torch.nn.functional.leaky_relu(y), y))
+        return y.to(x.dtype)
 
     def forward(self, x: dict[str, Tensor], *, model_comm_group=None, grid_shard_sizes=None, **kwargs) -> dict[str, Tensor]:
         from .distributed.balanced_partition import get_balanced_partition_sizes
         from .distributed.graph import group_size
         from .distributed.graph import shard_rows
         from .layers._functional import compute_dtype
+        from .layers._train import wants_grad
 
         names = list(x.keys())
         batch = {t.shape[0] for t in x.values()}
@@ -337,13 +358,20 @@ class AnemoiModelEncProcDec(nn.Module):
         if world > 1:
             assert batch_size == 1 and ensemble_size == 1, "Only batch / ensemble size 1 per device when the model is sharded across GPUs"
         dt = compute_dtype(*x.values())
+        # differentiable glue (PyTorch statements of the two assembly kernels and of the adds) whenever gradients are wanted: the fused kernels
+        # have no backward.  The mappers / processor switch to their own differentiable paths by the same rule.
+        train = wants_grad(self, *x.values())
+        if train and world > 1:
+            raise NotImplementedError("training AnemoiModelEncProcDec on a model-parallel group is not implemented: use the reference model class with the "
+                                      "B200 layer classes (INTEGRATION.md §1), whose processors and mappers train sharded")  # fmt: skip
+        add = (lambda a, b: a + b.to(a.dtype)) if train else ops.add
         hid = self._graph_name_hidden
         x_hidden = self.node_attributes(hid, batch_size=batch_size)
         sizes_hidden = get_balanced_partition_sizes(x_hidden.shape[0], world) if world > 1 else None
         x_hidden = shard_rows(x_hidden, sizes_hidden, model_comm_group)
         latents, x_data_latents, sizes_data = [], {}, {}
         for ds in names:
-            x_data, sizes_data[ds] = self._assemble_input(x[ds], batch_size, grid_shard_sizes, model_comm_group, ds, dt)
+            x_data, sizes_data[ds] = self._assemble_input(x[ds], batch_size, grid_shard_sizes, model_comm_group, ds, dt, differentiable=train)
             ea, ei, es = self.encoder_graph_provider[ds].get_edges(batch_size=batch_size, model_comm_group=model_comm_group,
                                                                    shard_edges=getattr(self.encoder[ds], "shard_strategy", "edges") != "heads")  # fmt: skip
             info = BipartiteGraphShardInfo(src_nodes=sizes_data[ds], dst_nodes=sizes_hidden, edges=es)
@@ -351,14 +379,14 @@ class AnemoiModelEncProcDec(nn.Module):
             latents.append(lat)
         x_latent = latents[0]
         for lat in latents[1:]:
-            x_latent = ops.add(x_latent, lat)
+            x_latent = add(x_latent, lat)
         # the heads (Ulysses) strategy attends over the FULL edge list for its heads: ask the provider not to cut it
         ea, ei, es = self.processor_graph_provider.get_edges(batch_size=batch_size, model_comm_group=model_comm_group,
                                                              shard_edges=getattr(self.processor, "shard_strategy", "edges") != "heads")  # fmt: skip
         x_proc = self.processor(x_latent, batch_size, GraphShardInfo(nodes=sizes_hidden if world > 1 else [x_latent.shape[0]], edges=es), ea, ei,
                                 model_comm_group)  # fmt: skip
         if self.latent_skip:
-            x_proc = ops.add(x_proc, x_latent)
+            x_proc = add(x_proc, x_latent)
         out = {}
         for ds in names:
             ea, ei, es = self.decoder_graph_provider[ds].get_edges(batch_size=batch_size, model_comm_group=model_comm_group,
@@ -376,6 +404,9 @@ class AnemoiModelEncProcDec(nn.Module):
             else:
                 dec = self.decoder[ds]((x_proc, x_data_latents[ds]), batch_size, info, ea, ei, model_comm_group,
                                        keep_x_dst_sharded=sizes_data[ds] is not None)  # fmt: skip
+            if train:
+                out[ds] = self._assemble_output_differentiable(dec, x[ds], batch_size, ensemble_size, ds)
+                continue
             skip, bound = self._output_tables(ds, dec.device)
             out[ds] = ops.assemble_output(dec, x[ds], batch_size, ensemble_size, self.n_step_output, self.residual_step, skip, bound).to(x[ds].dtype)
         return out

@@ -241,6 +241,35 @@ def _check_checkpoint(rank, world):
     return msgs
 
 
+def _check_model_fixture(rank, world):
+    """``AnemoiModelEncProcDec`` in TRAINING mode (differentiable glue: the PyTorch statements of the two assembly kernels, latent sum / skip,
+    SkipConnection residual, ReluBounding; graph providers and node attributes with their trainable tensors; the mappers' and the processor's
+    differentiable paths) against the gradient fixture of the UNMODIFIED reference model (oracle/gen_grad_golden_model.py ->
+    tests/golden/grads_model.pt): output, input gradient, every parameter gradient."""
+    from test_model_glue import build_model
+
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    fx = torch.load(os.path.join(gdir, "model_forward.pt"), weights_only=False)
+    gr = torch.load(os.path.join(gdir, "grads_model.pt"), weights_only=False)["cases"]
+    msgs = []
+    for kind in ("graphtransformer", "gnn"):
+        m = build_model(fx, kind)
+        m.load_state_dict(fx["cases"][kind]["sd"], strict=True)
+        m.train()
+        x = fx["x"].clone().requires_grad_()
+        y = m({"data": x})["data"]
+        (y * gr[kind]["w"]).sum().backward()
+        ref = gr[kind]["grads"]
+        got = {k: p.grad for k, p in m.named_parameters()}
+        assert set(ref) <= {k for k, g in got.items() if g is not None}, sorted(set(ref) - {k for k, g in got.items() if g is not None})[:4]
+        big = max(g.abs().max().item() for g in ref.values())
+        err_p = max(((got[k] - g).abs().max() / max(g.abs().max().item(), 1e-3 * big)).item() for k, g in ref.items())
+        err_x = max(((x.grad - gr[kind]["x_grad"]).abs().max() / gr[kind]["x_grad"].abs().max()).item(),
+                    ((y - gr[kind]["y"]).abs().max() / gr[kind]["y"].abs().max()).item())  # fmt: skip
+        msgs.append((f"model_fixture_{kind}", err_x, err_p))
+    return msgs
+
+
 import pytest  # noqa: E402
 
 
@@ -341,6 +370,16 @@ def _check_fixtures(rank, world):
         errs.append(_param_errs(m, c["grads"]))
         out.append((name, max(errs)))
     return out
+
+
+def test_model_training_matches_reference_gradient_fixture_cpu():
+    with tempfile.TemporaryDirectory() as d:
+        ret = mp.Manager().dict()
+        mp.spawn(_worker, args=(1, os.path.join(d, "rdv"), ret, "_check_model_fixture"), nprocs=1, join=True)
+        assert isinstance(ret.get(0), list), ret.get(0)
+        for name, err_x, err_p in ret[0]:
+            assert err_x <= 1e-4 and err_p <= 1e-4, f"{name}: output / input gradient {err_x:.3e}, parameter gradients {err_p:.3e}"
+        print([(n, f"{a:.1e}", f"{b:.1e}") for n, a, b in ret[0]])
 
 
 def test_training_composition_matches_reference_gradient_fixtures_cpu():

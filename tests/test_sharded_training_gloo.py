@@ -267,6 +267,29 @@ def _check_model_fixture(rank, world):
         err_x = max(((x.grad - gr[kind]["x_grad"]).abs().max() / gr[kind]["x_grad"].abs().max()).item(),
                     ((y - gr[kind]["y"]).abs().max() / gr[kind]["y"].abs().max()).item())  # fmt: skip
         msgs.append((f"model_fixture_{kind}", err_x, err_p))
+        # the differentiable glue == the inference glue (pinned to the reference golden) also with an ensemble dimension of 2
+        xe = torch.cat([fx["x"], fx["x"].flip(0)], dim=2).contiguous()
+        m.eval()
+        with torch.no_grad():
+            y_inf = m({"data": xe})["data"]
+        m.train()
+        y_tr = m({"data": xe})["data"]
+        assert y_tr.requires_grad and y_tr.shape == y_inf.shape
+        msgs.append((f"model_ensemble2_{kind}", ((y_tr - y_inf).abs().max() / y_inf.abs().max()).item(), 0.0))
+    # two datasets (two encoders summed into one latent, two decoders): training forward == inference forward (pinned to the reference golden),
+    # and every parameter receives a gradient
+    from test_model_glue import build_two_dataset_model
+
+    fx2 = torch.load(os.path.join(gdir, "model_forward_two_datasets.pt"), weights_only=False)
+    m = build_two_dataset_model(fx2)
+    m.load_state_dict(fx2["sd"], strict=True)
+    m.train()
+    y = m({k: v.clone() for k, v in fx2["x"].items()})
+    sum(v.square().sum() for v in y.values()).backward()
+    missing = [k for k, p in m.named_parameters() if p.requires_grad and p.grad is None]
+    assert not missing, missing[:4]
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+    msgs.append(("model_two_datasets", max(((y[k] - ref).abs().max() / ref.abs().max()).item() for k, ref in fx2["y"].items()), 0.0))
     return msgs
 
 

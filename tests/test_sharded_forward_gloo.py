@@ -288,6 +288,74 @@ def check_inference_mode(rank, world):
         assert torch.equal(y, y_again)
 
 
+def check_random_configs(rank, world):
+    """Random constructor configurations through the SHARDED forward (both strategies of the GraphTransformer processor, the GNN processor in its
+    all-gather and halo forms; gated MLPs, qk_norm, edge_pre_mlp, attn_channels, ConditionalLayerNorm with a sharded conditioning tensor, several
+    layers / chunks): sharded == single rank.  The same generator runs on every rank."""
+    import anemoi_core_b200.layers.processor as proc_mod
+    from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
+    from anemoi_core_b200.distributed.graph import gather_rows
+    from anemoi_core_b200.distributed.graph import shard_rows
+    from anemoi_core_b200.distributed.shapes import GraphShardInfo
+    from anemoi_core_b200.layers import GNNProcessor
+    from anemoi_core_b200.layers import GraphTransformerProcessor
+
+    group = dist.group.WORLD
+    g = torch.Generator().manual_seed(101)
+
+    def pick(options):
+        return options[int(torch.randint(0, len(options), (1,), generator=g))]
+
+    for case in range(14):
+        n = int(torch.randint(3 * world, 90, (1,), generator=g))
+        d = pick([3, 5, 11])
+        ei, ea = _graph(n, n, int(torch.randint(n, 5 * n, (1,), generator=g)), d, seed=200 + case)
+        sizes = get_balanced_partition_sizes(n, world)
+        kw_call, cond = {}, None
+        torch.manual_seed(300 + case)
+        if case % 2 == 0:
+            heads = pick([h for h in (2, 4, 8) if h % world == 0] or [world])
+            c = heads * pick([8, 16])
+            layers = pick([1, 2, 3])
+            cfg = dict(num_layers=layers, num_channels=c, num_chunks=pick([k for k in (1, 2, 3) if layers % k == 0]), num_heads=heads, mlp_hidden_ratio=pick([2, 4]),
+                       edge_dim=d, qk_norm=pick([False, True]), mlp_implementation=pick(["mlp", "glu", "swiglu", "geglu", "reglu"]),
+                       shard_strategy=pick(["edges", "edges", "heads"]))  # fmt: skip
+            if pick([False, True]):
+                cfg["edge_pre_mlp"] = True
+            if pick([False, True]):
+                cfg["attn_channels"] = 2 * c
+            if pick([False, False, True]):
+                dc = 8
+                cfg["layer_kernels"] = {"LayerNorm": {"_target_": "anemoi_core_b200.layers.normalization.ConditionalLayerNorm", "condition_shape": dc,
+                                                      "zero_init": False}}  # fmt: skip
+                cond = torch.randn(n, dc, generator=g)
+            m = GraphTransformerProcessor(**cfg).eval()
+            what = f"case {case}: GraphTransformerProcessor {cfg}"
+        else:
+            c, layers = pick([16, 32, 48]), pick([1, 2, 3])
+            cfg = dict(num_channels=c, num_layers=layers, num_chunks=pick([k for k in (1, 2, 3) if layers % k == 0]), mlp_extra_layers=pick([0, 1]), edge_dim=d,
+                       mlp_implementation=pick(["mlp", "swiglu"]))  # fmt: skip
+            m = GNNProcessor(**cfg).eval()
+            proc_mod.GNN_HALO = pick([False, True])
+            what = f"case {case}: GNNProcessor {cfg} halo={proc_mod.GNN_HALO}"
+        with torch.no_grad():
+            for p in m.parameters():  # LayerNorm affine terms away from (1, 0), conditional scales away from 0
+                if p.dim() == 1:
+                    p.add_(0.1 * torch.randn(p.shape, generator=g))
+        x = torch.randn(n, c, generator=g)
+        try:
+            if cond is not None:
+                full = m(x, 1, GraphShardInfo(nodes=[n]), ea, ei, cond=cond)
+                local = m(shard_rows(x, sizes, group).contiguous(), 1, GraphShardInfo(nodes=sizes), ea, ei, group, cond=shard_rows(cond, sizes, group).contiguous())
+            else:
+                full = m(x, 1, GraphShardInfo(nodes=[n]), ea, ei)
+                local = m(shard_rows(x, sizes, group).contiguous(), 1, GraphShardInfo(nodes=sizes), ea, ei, group)
+        finally:
+            proc_mod.GNN_HALO = False
+        assert local.shape[0] == sizes[rank], what
+        _close(gather_rows(local, sizes, group), full, what)
+
+
 def check_heads_strategy(rank, world):
     """shard_strategy="heads" (Ulysses, block.py:689-759): nodes sharded outside the attention, heads inside; full edge list on every rank."""
     from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
@@ -550,6 +618,11 @@ def test_degenerate_enc_proc_dec(world):
 @pytest.mark.parametrize("world", [1, 2])
 def test_inference_mode(world):
     run_distributed("check_inference_mode", world)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_random_configs_sharded(world):
+    run_distributed("check_random_configs", world)
 
 
 def test_derived_weights_follow_the_parameters():

@@ -140,6 +140,63 @@ def _check_degenerate(rank, world):
     return msgs
 
 
+def _check_random_configs(rank, world):
+    """Random constructor configurations through a SHARDED training step (gated MLPs, qk_norm, edge_pre_mlp, attn_channels, both strategies of the
+    GraphTransformer processor, GNN with extra layers / swiglu, several layers and chunks): gradients == the single-rank step."""
+    from anemoi_core_b200.distributed.balanced_partition import get_balanced_partition_sizes
+    from anemoi_core_b200.distributed.graph import shard_rows
+    from anemoi_core_b200.distributed.shapes import GraphShardInfo
+    from anemoi_core_b200.layers import GNNProcessor
+    from anemoi_core_b200.layers import GraphTransformerProcessor
+
+    group = dist.group.WORLD
+    g = torch.Generator().manual_seed(55)
+
+    def pick(options):
+        return options[int(torch.randint(0, len(options), (1,), generator=g))]
+
+    msgs = []
+    for case in range(8):
+        n = int(torch.randint(3 * world, 70, (1,), generator=g))
+        d = pick([3, 5])
+        ei, ea = _graph(n, int(torch.randint(2 * n, 5 * n, (1,), generator=g)), d, seed=400 + case)
+        sizes = get_balanced_partition_sizes(n, world)
+        torch.manual_seed(500 + case)
+        if case % 2 == 0:
+            heads = pick([2, 4])
+            c, layers = heads * pick([8, 16]), pick([1, 2])
+            cfg = dict(num_layers=layers, num_channels=c, num_chunks=1, num_heads=heads, mlp_hidden_ratio=2, edge_dim=d, qk_norm=pick([False, True]),
+                       mlp_implementation=pick(["mlp", "glu", "swiglu", "geglu", "reglu"]), shard_strategy=pick(["edges", "heads"]))  # fmt: skip
+            if pick([False, True]):
+                cfg["edge_pre_mlp"] = True
+            if pick([False, True]):
+                cfg["attn_channels"] = 2 * c
+            m = GraphTransformerProcessor(**cfg)
+        else:
+            c, layers = pick([16, 48]), pick([1, 2])
+            cfg = dict(num_channels=c, num_layers=layers, num_chunks=1, mlp_extra_layers=pick([0, 1]), edge_dim=d, mlp_implementation=pick(["mlp", "swiglu"]))
+            m = GNNProcessor(**cfg)
+        m.train()
+        x0, w = torch.randn(n, c, generator=g), torch.randn(n, c, generator=g)
+        xf = x0.clone().requires_grad_()
+        (m(xf, 1, GraphShardInfo(nodes=[n]), ea, ei) * w).sum().backward()
+        ref_p = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        ref_x = xf.grad.clone()
+        m.zero_grad()
+        xs = shard_rows(x0, sizes, group).contiguous().clone().requires_grad_()
+        (m(xs, 1, GraphShardInfo(nodes=sizes), ea, ei, group) * shard_rows(w, sizes, group)).sum().backward()
+        err_x = ((xs.grad - shard_rows(ref_x, sizes, group)).abs().max() / ref_x.abs().max()).item()
+        worst, big = 0.0, max(gr.abs().max().item() for gr in ref_p.values())
+        for k, p in m.named_parameters():
+            if k not in ref_p:
+                continue
+            gp = p.grad.clone() if p.grad is not None else torch.zeros_like(p)
+            dist.all_reduce(gp)
+            worst = max(worst, ((gp - ref_p[k]).abs().max() / max(ref_p[k].abs().max().item(), 1e-3 * big)).item())
+        msgs.append((f"random_{case}_{type(m).__name__}_{cfg}", err_x, worst))
+    return msgs
+
+
 def _check_model(rank, world):
     """The WHOLE encoder -> processor -> decoder step in training mode, every stage sharded (the call sequence of tests/test_gpu_multi.py's
     training section, here under Gloo on CPU): sharded input / output rows for the GraphTransformer model, replicated in / gathered out for the
@@ -296,7 +353,7 @@ def _check_model_fixture(rank, world):
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize("fn_name", ["_check", "_check_model", "_check_checkpoint", "_check_degenerate"])
+@pytest.mark.parametrize("fn_name", ["_check", "_check_model", "_check_checkpoint", "_check_degenerate", "_check_random_configs"])
 def test_sharded_training_step_matches_single_rank_gloo(fn_name):
     world = 2
     with tempfile.TemporaryDirectory() as d:
